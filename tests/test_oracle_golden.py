@@ -1,0 +1,83 @@
+"""The numpy oracle (oracle/dmrg_oracle.py) against records dumped from the REAL reference (tests/golden/*.npz,
+produced by tests/golden/make_golden.py from oracle/_ref/block_dump).  This is what pins the oracle; the CUDA
+path is then compared with the oracle and with the same records in test_gpu_*.py.  CPU only."""
+import numpy as np
+
+from oracle import dmrg_oracle as O
+from oracle import dumpio
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+def test_layout_is_bit_exact(golden):
+    rec, big = golden
+    assert big.size == rec["rpsi"].size
+    assert (big.allowed.astype(int) == rec["psi_allowed"]).all()
+    pairs = list(big.offsets)
+    assert [p[0] for p in pairs] == list(rec["big.lmap"])        # StateInfo.C:213-227 order == FlattenInto order
+    assert [p[1] for p in pairs] == list(rec["big.rmap"])
+    assert [big.offsets[p] for p in pairs] == list(rec["big.unblocked"])
+    assert [int(big.left.dims[l] * big.right.dims[r]) for l, r in pairs] == list(rec["big.dims"])
+
+
+def test_sigma_matches_reference(golden):
+    rec, big = golden
+    v = big.flatten(O.multiply_h(big, big.unflatten(rec["rpsi"])))
+    assert rel(v, rec["rsigma"]) < 1e-13                         # north_star: 1e-10 relative
+    for i in range(int(rec["meta"][4])):
+        v = big.flatten(O.multiply_h(big, big.unflatten(rec["psi%d" % i])))
+        assert rel(v, rec["sigma%d" % i]) < 1e-13
+
+
+def test_diagonal_matches_reference(golden):
+    rec, big = golden
+    assert rel(O.diagonal_h(big), rec["diag"]) < 1e-13
+
+
+def test_davidson_matches_reference(golden):
+    rec, big = golden
+    nroots = int(rec["meta"][4])
+    hmul = lambda x: big.flatten(O.multiply_h(big, big.unflatten(x)))
+    ev, vecs, nmult = O.block_davidson(hmul, [rec["guess%d" % i] for i in range(nroots)], rec["diag"],
+                                       float(rec["dav_tol"][0]), int(rec["dav_in"][4]), int(rec["dav_in"][5]))
+    assert np.abs(ev - rec["dav_evals"][:nroots]).max() < 1e-10   # north_star: 1e-8 Eh
+    assert nmult == int(rec["dav_out"][0])                        # same number of H applications
+    for i in range(nroots):
+        assert abs(abs(np.dot(vecs[i], rec["psi%d" % i])) - 1.0) < 1e-8
+
+
+def test_density_truncation_rotation(golden):
+    rec, big = golden
+    nroots = int(rec["meta"][4])
+    waves = [big.unflatten(rec["psi%d" % i]) for i in range(nroots)]
+    rho = O.make_density(big, waves, rec["weights"])
+    assert rel(np.concatenate([r.ravel() for r in rho]), rec["rdm.data"]) < 1e-13
+    evals, evecs = O.diagonalise_dm(rho)
+    kept, err = O.select_states(evals, int(rec["meta"][5]))
+    ref_rot = dumpio.rotation_from(rec)
+    assert [len(k) for k in kept] == [r.shape[1] for r in ref_rot]   # identical retained sectors and state counts
+    assert abs(err - rec["error"][0]) < 1e-12
+    rot = O.rotation_matrices(evecs, kept)
+    for q in range(len(rot)):
+        if rot[q].shape[1]:
+            assert np.abs(rot[q] @ rot[q].T - ref_rot[q] @ ref_rot[q].T).max() < 1e-7
+    N = dumpio.block_from(rec, "N.")
+    keepq = [q for q in range(len(ref_rot)) if ref_rot[q].shape[1] > 0]
+    assert (N.q == big.left.q[keepq]).all()
+    assert list(N.dims) == [ref_rot[q].shape[1] for q in keepq]
+    for nop in N.ops:
+        src = big.left.get(nop.optype, nop.orbs, nop.comp)
+        assert src is not None
+        r = O.rotate_op(src, ref_rot)
+        assert (r.allowed == nop.allowed).all()
+        for k in r.blocks:
+            assert np.abs(r.blocks[k] - nop.blocks[k]).max() < 1e-12
+
+
+def test_flop_count_matches_executed(golden):
+    rec, big = golden
+    fl = [0.0]
+    O.multiply_h(big, big.unflatten(rec["rpsi"]), fl)
+    assert fl[0] == O.sigma_flops(big)

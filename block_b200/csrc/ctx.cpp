@@ -1,0 +1,1270 @@
+// C ABI (include/block_b200.h) of the B200 DMRG hot path: context, device arenas, orchestration.
+// Compiled by nvcc as host C++ (no kernels here: those are in kernels.cu / gemm_grouped.cuh).
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/block_b200.h"
+#include "kernels.h"
+#include "plan.hpp"
+
+using namespace b2d;
+
+namespace {
+
+std::string g_create_error;
+
+struct DevBuf {   // growable raw device buffer
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr; cap = 0;
+    cudaError_t e = cudaMalloc(&p, bytes);
+    if (e == cudaSuccess) cap = bytes;
+    return e;
+  }
+  void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+};
+
+// device copy of a host Schedule: one allocation, typed views per chunk
+struct DevSchedule {
+  DevBuf buf;
+  struct DC { DevBatch s1, s2; };
+  std::vector<DC> chunks;
+  void clear() { chunks.clear(); }
+};
+
+// NCCL through dlopen: the library ships inside the torch wheel (nvidia/nccl/lib/libnccl.so.2), no link-time dependency
+struct Nccl {
+  struct Id128 { char b[128]; };   // ncclUniqueId (passed by value)
+  void* h = nullptr;
+  void* comm = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, Id128, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+  bool load(std::string& err) {
+    if (h) return true;
+    const char* env = getenv("B2D_NCCL_LIB");
+    const char* names[] = {env, "libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      if (!n) continue;
+      h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (h) break;
+    }
+    if (!h) { err = std::string("cannot dlopen NCCL (set B2D_NCCL_LIB): ") + dlerror(); return false; }
+    GetUniqueId = (decltype(GetUniqueId))dlsym(h, "ncclGetUniqueId");
+    CommInitRank = (decltype(CommInitRank))dlsym(h, "ncclCommInitRank");
+    AllReduce = (decltype(AllReduce))dlsym(h, "ncclAllReduce");
+    CommDestroy = (decltype(CommDestroy))dlsym(h, "ncclCommDestroy");
+    GetErrorString = (decltype(GetErrorString))dlsym(h, "ncclGetErrorString");
+    if (!GetUniqueId || !CommInitRank || !AllReduce || !CommDestroy) { err = "NCCL symbols missing"; return false; }
+    return true;
+  }
+};
+
+}  // namespace
+
+struct b2d_ctx {
+  int device = -1;
+  bool has_device = false;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  AngMom am;
+
+  Side side[2];
+  PsiLayout psi;
+  bool planned = false;
+  double core_energy = 0.0;
+  bool hubbard = false;
+  int norbs = 0, rank = 0, nranks = 1;
+  std::vector<Term> terms_all, terms_mine;
+  Schedule sched;
+  DevSchedule dsched;
+  double flops_all = 0.0;
+
+  // options
+  double workspace_mb = 2048.0;
+  int max_davidson_iter = 2000;
+  int forced_class = -1;
+  bool sync_debug = false;
+
+  // operator arena: slabs with bump allocation
+  struct Slab { char* p; size_t cap, used; };
+  std::vector<Slab> slabs;
+  int64_t arena_doubles = 0;
+
+  // scratch
+  DevBuf staging, desc_scratch, work, flat_in, flat_out;
+  DevBuf psi_blocks;       // BlockDesc per psi block
+  DevBuf diag_tasks, diag_begin;
+  DevBuf partials, scalars;   // level-1 partial sums; G / theta / alpha / misc scalars
+  double* h_pinned = nullptr; // 64 doubles
+
+  // wavefunction slots
+  DevBuf user_pool, dav_pool;
+  int nuser = 0, ndav = 0;
+
+  // density / rotation
+  DevBuf rho, eig_g, eig_vt, eig_vals, eig_sweeps, sector_desc, rot, gather_desc, gather_rows;
+  std::vector<int64_t> rho_off;          // per left sector offset in rho (padded)
+  int64_t rho_padded = 0;
+  std::vector<std::vector<double>> evals; // per sector ascending, clamped
+  std::vector<std::vector<int>> eval_row; // per sector: Jacobi row index of the i-th ascending eigenvalue
+  bool have_eig = false;
+  std::vector<int> kept;                  // kept columns per sector
+  std::vector<int64_t> rot_off;           // per sector offset in rot (padded ld = pad_ld(kept))
+  bool have_rot = false;
+  // rotated operators
+  Side rotated;                           // sectors + ops of the renormalised left block
+  std::vector<int> rotated_old;           // old sector index per new sector
+  DevBuf rotated_arena;
+  bool have_rotated = false;
+
+  // timing / accounting
+  int64_t launches = 0;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool timing_valid = false;
+  std::vector<cudaEvent_t> phase_events;
+  bool phase_timing = false;
+  double last_step_ms[2] = {0, 0};
+
+  Nccl nccl;
+};
+
+namespace {
+
+int fail(b2d_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg; else g_create_error = msg;
+  return code;
+}
+#define CU(call)                                                                                         \
+  do {                                                                                                   \
+    cudaError_t e__ = (call);                                                                            \
+    if (e__ != cudaSuccess) return fail(ctx, B2D_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__)); \
+  } while (0)
+#define NEED_DEVICE()                                                                                     \
+  do {                                                                                                    \
+    if (!ctx) return B2D_ERR_ARG;                                                                         \
+    if (!ctx->has_device) return fail(ctx, B2D_ERR_NO_DEVICE, "no CUDA device bound to this context (planning-only); there is no CPU fallback"); \
+  } while (0)
+#define NEED_PLAN()                                                                     \
+  do {                                                                                  \
+    if (!ctx->planned) return fail(ctx, B2D_ERR_ARG, "call b2d_plan first");            \
+  } while (0)
+
+cudaError_t arena_alloc(b2d_ctx* ctx, size_t bytes, double** out) {
+  bytes = (bytes + 255) / 256 * 256;
+  for (auto& s : ctx->slabs)
+    if (s.cap - s.used >= bytes) { *out = (double*)(s.p + s.used); s.used += bytes; return cudaSuccess; }
+  size_t cap = std::max(bytes, (size_t)256 << 20);
+  char* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, cap);
+  if (e != cudaSuccess) {   // fall back to an exact-size slab
+    cap = bytes;
+    e = cudaMalloc(&p, cap);
+    if (e != cudaSuccess) return e;
+  }
+  ctx->slabs.push_back({p, cap, bytes});
+  *out = (double*)p;
+  return cudaSuccess;
+}
+
+double* user_vec(b2d_ctx* ctx, int slot) { return (double*)ctx->user_pool.p + (int64_t)slot * ctx->psi.Wp; }
+double* dav_vec(b2d_ctx* ctx, int slot) { return (double*)ctx->dav_pool.p + (int64_t)slot * ctx->psi.Wp; }
+
+// BlockDesc table of one operator (host)
+std::vector<BlockDesc> op_blocks(const Side& s, const OpRec& op) {
+  std::vector<BlockDesc> v;
+  int64_t ref = 0;
+  for (int i = 0; i < s.nq; ++i)
+    for (int j = 0; j < s.nq; ++j)
+      if (op.allowed[(size_t)i * s.nq + j]) {
+        BlockDesc d;
+        d.ref_off = ref; d.dev_off = op.off[(size_t)i * s.nq + j];
+        d.rows = s.dims[i]; d.cols = s.dims[j]; d.ld = pad_ld(s.dims[j]); d.pad = 0;
+        ref += (int64_t)d.rows * d.cols;
+        v.push_back(d);
+      }
+  return v;
+}
+
+int upload_desc(b2d_ctx* ctx, DevBuf& buf, const void* host, size_t bytes) {
+  if (bytes == 0) return B2D_OK;
+  CU(buf.reserve(bytes));
+  CU(cudaMemcpyAsync(buf.p, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));   // host vectors are temporaries
+  return B2D_OK;
+}
+
+int upload_schedule(b2d_ctx* ctx, const Schedule& S, DevSchedule& D) {
+  D.clear();
+  size_t bytes = 0;
+  auto add = [&](size_t n) { size_t o = bytes; bytes += (n + 255) / 256 * 256; return o; };
+  struct Off { size_t segs, groups, tiles[B2D_NUM_TILE_CLASSES]; };
+  std::vector<Off> o1(S.chunks.size()), o2(S.chunks.size());
+  auto plan = [&](const GemmBatch& b, Off& o) {
+    o.segs = add(b.segs.size() * sizeof(GSeg));
+    o.groups = add(b.groups.size() * sizeof(GGroup));
+    for (int c = 0; c < B2D_NUM_TILE_CLASSES; ++c) o.tiles[c] = add(b.tiles[c].size() * sizeof(GTile));
+  };
+  for (size_t i = 0; i < S.chunks.size(); ++i) { plan(S.chunks[i].step1, o1[i]); plan(S.chunks[i].step2, o2[i]); }
+  if (bytes == 0) return B2D_OK;
+  std::vector<char> host(bytes);
+  auto fill = [&](const GemmBatch& b, const Off& o) {
+    if (!b.segs.empty()) memcpy(&host[o.segs], b.segs.data(), b.segs.size() * sizeof(GSeg));
+    if (!b.groups.empty()) memcpy(&host[o.groups], b.groups.data(), b.groups.size() * sizeof(GGroup));
+    for (int c = 0; c < B2D_NUM_TILE_CLASSES; ++c)
+      if (!b.tiles[c].empty()) memcpy(&host[o.tiles[c]], b.tiles[c].data(), b.tiles[c].size() * sizeof(GTile));
+  };
+  for (size_t i = 0; i < S.chunks.size(); ++i) { fill(S.chunks[i].step1, o1[i]); fill(S.chunks[i].step2, o2[i]); }
+  int rc = upload_desc(ctx, D.buf, host.data(), bytes);
+  if (rc) return rc;
+  char* base = (char*)D.buf.p;
+  auto view = [&](const GemmBatch& b, const Off& o) {
+    DevBatch d;
+    d.segs = (const GSeg*)(base + o.segs);
+    d.groups = (const GGroup*)(base + o.groups);
+    for (int c = 0; c < B2D_NUM_TILE_CLASSES; ++c) { d.tiles[c] = (const GTile*)(base + o.tiles[c]); d.ntiles[c] = (int)b.tiles[c].size(); }
+    return d;
+  };
+  D.chunks.resize(S.chunks.size());
+  for (size_t i = 0; i < S.chunks.size(); ++i) { D.chunks[i].s1 = view(S.chunks[i].step1, o1[i]); D.chunks[i].s2 = view(S.chunks[i].step2, o2[i]); }
+  return B2D_OK;
+}
+
+// run a two-step schedule: bases for SRC / DST / AUX supplied by the caller, WORK = ctx->work
+int run_schedule(b2d_ctx* ctx, const Schedule& S, const DevSchedule& D, double* src, double* dst, double* aux) {
+  CU(ctx->work.reserve((size_t)std::max<int64_t>(S.work_max, 16) * 8));
+  double* bases[B2D_NUM_BASES] = {nullptr, src, (double*)ctx->work.p, dst, aux};
+  const bool pt = ctx->phase_timing;
+  size_t need_ev = pt ? D.chunks.size() * 2 + 1 : 0;
+  while (ctx->phase_events.size() < need_ev) {
+    cudaEvent_t e;
+    CU(cudaEventCreate(&e));
+    ctx->phase_events.push_back(e);
+  }
+  if (pt) CU(cudaEventRecord(ctx->phase_events[0], ctx->stream));
+  for (size_t i = 0; i < D.chunks.size(); ++i) {
+    CU(launch_gemm_batch(D.chunks[i].s1, bases, ctx->stream, &ctx->launches));
+    if (pt) CU(cudaEventRecord(ctx->phase_events[2 * i + 1], ctx->stream));
+    CU(launch_gemm_batch(D.chunks[i].s2, bases, ctx->stream, &ctx->launches));
+    if (pt) CU(cudaEventRecord(ctx->phase_events[2 * i + 2], ctx->stream));
+    if (ctx->sync_debug) CU(cudaStreamSynchronize(ctx->stream));
+  }
+  if (pt) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->last_step_ms[0] = ctx->last_step_ms[1] = 0.0;
+    for (size_t i = 0; i < D.chunks.size(); ++i) {
+      float a = 0.f, b = 0.f;
+      cudaEventElapsedTime(&a, ctx->phase_events[2 * i], ctx->phase_events[2 * i + 1]);
+      cudaEventElapsedTime(&b, ctx->phase_events[2 * i + 1], ctx->phase_events[2 * i + 2]);
+      ctx->last_step_ms[0] += a; ctx->last_step_ms[1] += b;
+    }
+  }
+  return B2D_OK;
+}
+
+int allreduce(b2d_ctx* ctx, double* p, int64_t n) {
+  if (ctx->nranks <= 1 || !ctx->nccl.comm) return B2D_OK;
+  int r = ctx->nccl.AllReduce(p, p, (size_t)n, /*ncclFloat64*/ 8, /*ncclSum*/ 0, ctx->nccl.comm, ctx->stream);
+  if (r != 0) return fail(ctx, B2D_ERR_NCCL, std::string("ncclAllReduce: ") + (ctx->nccl.GetErrorString ? ctx->nccl.GetErrorString(r) : "error"));
+  return B2D_OK;
+}
+
+int sigma_dev(b2d_ctx* ctx, double* src, double* dst, bool accumulate, bool reduce) {
+  if (!accumulate) CU(cudaMemsetAsync(dst, 0, (size_t)ctx->psi.Wp * 8, ctx->stream));
+  int rc = run_schedule(ctx, ctx->sched, ctx->dsched, src, dst, nullptr);
+  if (rc) return rc;
+  if (reduce) return allreduce(ctx, dst, ctx->psi.Wp);
+  return B2D_OK;
+}
+
+void begin_timing(b2d_ctx* ctx) { cudaEventRecord(ctx->ev[0], ctx->stream); ctx->timing_valid = true; }
+void end_timing(b2d_ctx* ctx) { cudaEventRecord(ctx->ev[1], ctx->stream); }
+
+}  // namespace
+
+extern "C" {
+
+int b2d_abi_version(void) { return 1; }
+
+int b2d_create(int device, b2d_ctx** out) {
+  if (!out) return B2D_ERR_ARG;
+  *out = nullptr;
+  std::unique_ptr<b2d_ctx> c(new b2d_ctx());
+  b2d_ctx* ctx = nullptr;   // errors before the context exists go to the global slot
+  if (device >= 0) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || device >= n)
+      return fail(nullptr, B2D_ERR_NO_DEVICE, std::string("CUDA device ") + std::to_string(device) + " not available: " + (e != cudaSuccess ? cudaGetErrorString(e) : "index out of range"));
+    CU(cudaSetDevice(device));
+    c->device = device;
+    c->has_device = true;
+    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    for (auto& ev : c->ev) CU(cudaEventCreate(&ev));
+    CU(gemm_init());
+    CU(cudaMallocHost(&c->h_pinned, 64 * sizeof(double)));
+    CU(c->partials.reserve((size_t)L1_MAX_BLOCKS * L1_MAX_VECS * 8));
+    CU(c->scalars.reserve(8192 * 8));
+  }
+  *out = c.release();
+  return B2D_OK;
+}
+
+void b2d_destroy(b2d_ctx* ctx) {
+  if (!ctx) return;
+  if (ctx->has_device) {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->nccl.comm) ctx->nccl.CommDestroy(ctx->nccl.comm);
+    for (auto& s : ctx->slabs) cudaFree(s.p);
+    DevBuf* bufs[] = {&ctx->staging, &ctx->desc_scratch, &ctx->work, &ctx->flat_in, &ctx->flat_out, &ctx->psi_blocks, &ctx->diag_tasks,
+                      &ctx->diag_begin, &ctx->partials, &ctx->scalars, &ctx->user_pool, &ctx->dav_pool, &ctx->rho, &ctx->eig_g, &ctx->eig_vt,
+                      &ctx->eig_vals, &ctx->eig_sweeps, &ctx->sector_desc, &ctx->rot, &ctx->gather_desc, &ctx->gather_rows,
+                      &ctx->rotated_arena, &ctx->dsched.buf};
+    for (DevBuf* b : bufs) b->release();
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
+    for (auto& ev : ctx->phase_events) cudaEventDestroy(ev);
+    cudaStreamDestroy(ctx->stream);
+  }
+  delete ctx;
+}
+
+const char* b2d_last_error(const b2d_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int b2d_set_option(b2d_ctx* ctx, const char* key, double value) {
+  if (!ctx || !key) return B2D_ERR_ARG;
+  std::string k(key);
+  if (k == "workspace_mb") ctx->workspace_mb = value;
+  else if (k == "max_davidson_iter") ctx->max_davidson_iter = (int)value;
+  else if (k == "tile_class") ctx->forced_class = (int)value;
+  else if (k == "sync_debug") ctx->sync_debug = value != 0;
+  else if (k == "phase_timing") ctx->phase_timing = value != 0;
+  else return fail(ctx, B2D_ERR_ARG, "unknown option " + k);
+  return B2D_OK;
+}
+
+int b2d_set_block(b2d_ctx* ctx, int side, int nq, const int32_t* q, const int32_t* dims, int is_loop, int nsites, const int32_t* sites) {
+  if (!ctx || side < 0 || side > 1 || nq <= 0 || !q || !dims) return fail(ctx, B2D_ERR_ARG, "b2d_set_block: bad arguments");
+  Side& s = ctx->side[side];
+  s = Side();
+  s.nq = nq;
+  s.q.assign(q, q + 3 * nq);
+  s.dims.assign(dims, dims + nq);
+  for (int d : s.dims) if (d <= 0) return fail(ctx, B2D_ERR_ARG, "b2d_set_block: sector with no states");
+  s.loop = is_loop != 0;
+  if (sites) s.sites.assign(sites, sites + nsites);
+  ctx->planned = false;
+  return B2D_OK;
+}
+
+int b2d_add_op(b2d_ctx* ctx, int side, int optype, int norb, const int32_t* orbs, int comp, const int32_t* dq, int fermion,
+               const uint8_t* allowed, const double* data, int* op_id) {
+  if (!ctx || side < 0 || side > 1 || norb < 0 || norb > 2 || !dq || !allowed) return fail(ctx, B2D_ERR_ARG, "b2d_add_op: bad arguments");
+  Side& s = ctx->side[side];
+  if (s.nq == 0) return fail(ctx, B2D_ERR_ARG, "b2d_add_op: call b2d_set_block first");
+  OpRec op;
+  op.optype = optype; op.norb = norb; op.comp = comp;
+  for (int k = 0; k < norb; ++k) op.orbs[k] = orbs[k];
+  memcpy(op.dq, dq, sizeof(op.dq));
+  op.fermion = fermion != 0;
+  op.allowed.assign(allowed, allowed + (size_t)s.nq * s.nq);
+  layout_op(s, op);
+  if (ctx->has_device) {
+    CU(cudaSetDevice(ctx->device));
+    if (op.dev_size > 0) {
+      CU(arena_alloc(ctx, (size_t)op.dev_size * 8, &op.dev));
+      ctx->arena_doubles += op.dev_size;
+      CU(cudaMemsetAsync(op.dev, 0, (size_t)op.dev_size * 8, ctx->stream));
+      if (data) {
+        std::vector<BlockDesc> bd = op_blocks(s, op);
+        CU(ctx->staging.reserve((size_t)op.packed_size * 8));
+        CU(cudaMemcpyAsync(ctx->staging.p, data, (size_t)op.packed_size * 8, cudaMemcpyHostToDevice, ctx->stream));
+        int rc = upload_desc(ctx, ctx->desc_scratch, bd.data(), bd.size() * sizeof(BlockDesc));
+        if (rc) return rc;
+        CU(launch_pack((const BlockDesc*)ctx->desc_scratch.p, (int)bd.size(), (const double*)ctx->staging.p, op.dev, ctx->stream, &ctx->launches));
+        CU(cudaStreamSynchronize(ctx->stream));
+      }
+    }
+  }
+  s.ops.push_back(std::move(op));
+  if (op_id) *op_id = (int)s.ops.size() - 1;
+  ctx->planned = false;
+  return B2D_OK;
+}
+
+int64_t b2d_op_size(const b2d_ctx* ctx, int side, int op_id) {
+  if (!ctx || side < 0 || side > 1 || op_id < 0 || op_id >= (int)ctx->side[side].ops.size()) return -1;
+  return ctx->side[side].ops[op_id].packed_size;
+}
+
+int b2d_download_op(b2d_ctx* ctx, int side, int op_id, double* data) {
+  NEED_DEVICE();
+  if (side < 0 || side > 1 || op_id < 0 || op_id >= (int)ctx->side[side].ops.size() || !data) return fail(ctx, B2D_ERR_ARG, "b2d_download_op: bad arguments");
+  const Side& s = ctx->side[side];
+  const OpRec& op = s.ops[op_id];
+  if (op.packed_size == 0) return B2D_OK;
+  std::vector<BlockDesc> bd = op_blocks(s, op);
+  CU(ctx->staging.reserve((size_t)op.packed_size * 8));
+  int rc = upload_desc(ctx, ctx->desc_scratch, bd.data(), bd.size() * sizeof(BlockDesc));
+  if (rc) return rc;
+  CU(launch_unpack((const BlockDesc*)ctx->desc_scratch.p, (int)bd.size(), op.dev, (double*)ctx->staging.p, ctx->stream, &ctx->launches));
+  CU(cudaMemcpyAsync(data, ctx->staging.p, (size_t)op.packed_size * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return B2D_OK;
+}
+
+int b2d_fill_op_random(b2d_ctx* ctx, int side, int op_id, uint64_t seed, double amplitude, int symmetric) {
+  NEED_DEVICE();
+  if (side < 0 || side > 1 || op_id < 0 || op_id >= (int)ctx->side[side].ops.size()) return fail(ctx, B2D_ERR_ARG, "b2d_fill_op_random: bad arguments");
+  const Side& s = ctx->side[side];
+  const OpRec& op = s.ops[op_id];
+  if (op.packed_size == 0) return B2D_OK;
+  std::vector<BlockDesc> bd = op_blocks(s, op);
+  int rc = upload_desc(ctx, ctx->desc_scratch, bd.data(), bd.size() * sizeof(BlockDesc));
+  if (rc) return rc;
+  CU(launch_fill_random(op.dev, (const BlockDesc*)ctx->desc_scratch.p, (int)bd.size(), seed, amplitude, ctx->stream, &ctx->launches));
+  if (symmetric) {
+    // self-adjoint in the reduced sense: A[(j,i)] = A[(i,j)]^T / scaling_t(i,j)   (Transposeview::get_scaling, BaseOperator.C:56-91)
+    if (op.dq[0] != 0 || op.dq[2] != 0) return fail(ctx, B2D_ERR_ARG, "symmetric fill needs a particle-number conserving, totally symmetric operator");
+    std::vector<SymPair> pairs;
+    try {
+      for (int i = 0; i < s.nq; ++i)
+        for (int j = i; j < s.nq; ++j) {
+          if (!op.allowed[(size_t)i * s.nq + j]) continue;
+          if (!op.allowed[(size_t)j * s.nq + i]) return fail(ctx, B2D_ERR_ARG, "symmetric fill: allowed mask is not symmetric");
+          SymPair p;
+          p.off_a = op.off[(size_t)i * s.nq + j]; p.off_b = op.off[(size_t)j * s.nq + i];
+          p.rows = s.dims[i]; p.cols = s.dims[j]; p.ld_a = pad_ld(s.dims[j]); p.ld_b = pad_ld(s.dims[i]);
+          p.f = 1.0 / ctx->am.transpose_scaling(op.dq[1], s.quantum(i)[1], s.quantum(j)[1]);
+          pairs.push_back(p);
+        }
+    } catch (const std::exception& e) { return fail(ctx, B2D_ERR_ARG, e.what()); }
+    rc = upload_desc(ctx, ctx->desc_scratch, pairs.data(), pairs.size() * sizeof(SymPair));
+    if (rc) return rc;
+    CU(launch_symmetrise(op.dev, (const SymPair*)ctx->desc_scratch.p, (int)pairs.size(), ctx->stream, &ctx->launches));
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  return B2D_OK;
+}
+
+int b2d_plan(b2d_ctx* ctx, const int32_t* psi_dq, double core_energy, int hubbard, int norbs, int rank, int nranks) {
+  if (!ctx || !psi_dq || nranks < 1 || rank < 0 || rank >= nranks) return fail(ctx, B2D_ERR_ARG, "b2d_plan: bad arguments");
+  if (ctx->side[0].nq == 0 || ctx->side[1].nq == 0) return fail(ctx, B2D_ERR_ARG, "b2d_plan: set both blocks first");
+  try {
+    ctx->core_energy = core_energy; ctx->hubbard = hubbard != 0; ctx->norbs = norbs; ctx->rank = rank; ctx->nranks = nranks;
+    int dq[3] = {psi_dq[0], psi_dq[1], psi_dq[2]};
+    ctx->psi.build(ctx->side[0], ctx->side[1], dq);
+    ctx->terms_all = enumerate_terms(ctx->side[0], ctx->side[1], core_energy, ctx->hubbard, norbs, nranks, ctx->am);
+    ctx->terms_mine.clear();
+    for (const Term& t : ctx->terms_all) if (t.owner == rank) ctx->terms_mine.push_back(t);
+    int64_t budget = (int64_t)(ctx->workspace_mb * 1024.0 * 1024.0 / 8.0);
+    ctx->sched = build_schedule(ctx->side[0], ctx->side[1], ctx->psi, ctx->terms_mine, 0, budget, ctx->forced_class, ctx->am);
+    if (nranks > 1) {
+      // algorithmic flops of the whole sigma (all ranks) without keeping the other ranks' schedules
+      Schedule all = build_schedule(ctx->side[0], ctx->side[1], ctx->psi, ctx->terms_all, 0, budget, ctx->forced_class, ctx->am);
+      ctx->flops_all = all.flops_alg;
+    } else ctx->flops_all = ctx->sched.flops_alg;
+  } catch (const std::exception& e) { return fail(ctx, B2D_ERR_ARG, std::string("b2d_plan: ") + e.what()); }
+  ctx->planned = true;
+  ctx->have_eig = ctx->have_rot = ctx->have_rotated = false;
+  if (ctx->has_device) {
+    CU(cudaSetDevice(ctx->device));
+    int rc = upload_schedule(ctx, ctx->sched, ctx->dsched);
+    if (rc) return rc;
+    std::vector<BlockDesc> bd(ctx->psi.nblocks());
+    for (int p = 0; p < ctx->psi.nblocks(); ++p) {
+      bd[p].ref_off = ctx->psi.ref_off[p]; bd[p].dev_off = ctx->psi.dev_off[p];
+      bd[p].rows = ctx->psi.rows[p]; bd[p].cols = ctx->psi.cols[p]; bd[p].ld = ctx->psi.ld[p]; bd[p].pad = 0;
+    }
+    rc = upload_desc(ctx, ctx->psi_blocks, bd.data(), bd.size() * sizeof(BlockDesc));
+    if (rc) return rc;
+    CU(ctx->flat_in.reserve((size_t)std::max<int64_t>(ctx->psi.W, 1) * 8));
+    CU(ctx->flat_out.reserve((size_t)std::max<int64_t>(ctx->psi.W, 1) * 8));
+    // a re-plan changes Wp: drop the slots
+    ctx->user_pool.release(); ctx->dav_pool.release(); ctx->nuser = ctx->ndav = 0;
+  }
+  return B2D_OK;
+}
+
+int64_t b2d_psi_size(const b2d_ctx* ctx) { return ctx && ctx->planned ? ctx->psi.W : -1; }
+int64_t b2d_psi_padded_size(const b2d_ctx* ctx) { return ctx && ctx->planned ? ctx->psi.Wp : -1; }
+int b2d_psi_num_blocks(const b2d_ctx* ctx) { return ctx && ctx->planned ? ctx->psi.nblocks() : -1; }
+int b2d_psi_blocks(const b2d_ctx* ctx, int32_t* lq, int32_t* rq, int64_t* offset) {
+  if (!ctx || !ctx->planned) return B2D_ERR_ARG;
+  for (int p = 0; p < ctx->psi.nblocks(); ++p) {
+    if (lq) lq[p] = ctx->psi.bl[p];
+    if (rq) rq[p] = ctx->psi.br[p];
+    if (offset) offset[p] = ctx->psi.ref_off[p];
+  }
+  return B2D_OK;
+}
+
+int b2d_num_terms(const b2d_ctx* ctx, int all_ranks) {
+  if (!ctx || !ctx->planned) return -1;
+  return (int)(all_ranks ? ctx->terms_all.size() : ctx->terms_mine.size());
+}
+int b2d_terms(const b2d_ctx* ctx, int all_ranks, int32_t* left_op, int32_t* right_op, int32_t* flags, double* scale, int32_t* owner) {
+  if (!ctx || !ctx->planned) return B2D_ERR_ARG;
+  const std::vector<Term>& T = all_ranks ? ctx->terms_all : ctx->terms_mine;
+  for (size_t i = 0; i < T.size(); ++i) {
+    if (left_op) left_op[i] = T[i].lop;
+    if (right_op) right_op[i] = T[i].rop;
+    if (flags) flags[i] = (T[i].lt ? 1 : 0) | (T[i].rt ? 2 : 0);
+    if (scale) scale[i] = T[i].scale;
+    if (owner) owner[i] = T[i].owner;
+  }
+  return B2D_OK;
+}
+double b2d_sigma_flops(const b2d_ctx* ctx, int all_ranks) {
+  if (!ctx || !ctx->planned) return -1.0;
+  return all_ranks ? ctx->flops_all : ctx->sched.flops_alg;
+}
+int b2d_plan_stats(const b2d_ctx* ctx, double* out, int n) {
+  if (!ctx || !ctx->planned || !out) return B2D_ERR_ARG;
+  int launches = 0;
+  for (const Chunk& c : ctx->sched.chunks)
+    for (int k = 0; k < B2D_NUM_TILE_CLASSES; ++k) launches += (c.step1.tiles[k].empty() ? 0 : 1) + (c.step2.tiles[k].empty() ? 0 : 1);
+  double v[8] = {(double)ctx->sched.chunks.size(), (double)ctx->sched.n_step1, (double)ctx->sched.n_step2, (double)ctx->sched.n_tiles,
+                 (double)ctx->sched.work_max, (double)ctx->arena_doubles, (double)launches, ctx->sched.flops_exec};
+  for (int i = 0; i < n && i < 8; ++i) out[i] = v[i];
+  return B2D_OK;
+}
+
+// ---- slots --------------------------------------------------------------------------------------------------
+int b2d_vec_reserve(b2d_ctx* ctx, int nslots) {
+  NEED_DEVICE(); NEED_PLAN();
+  if (nslots <= ctx->nuser) return B2D_OK;
+  CU(cudaSetDevice(ctx->device));
+  DevBuf nb;
+  size_t bytes = (size_t)nslots * ctx->psi.Wp * 8;
+  CU(nb.reserve(std::max<size_t>(bytes, 256)));
+  CU(cudaMemsetAsync(nb.p, 0, std::max<size_t>(bytes, 256), ctx->stream));
+  if (ctx->nuser > 0) CU(cudaMemcpyAsync(nb.p, ctx->user_pool.p, (size_t)ctx->nuser * ctx->psi.Wp * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->user_pool.release();
+  ctx->user_pool = nb;
+  ctx->nuser = nslots;
+  return B2D_OK;
+}
+#define CHECK_SLOT(s)                                                                                     \
+  do {                                                                                                    \
+    if ((s) < 0 || (s) >= ctx->nuser) return fail(ctx, B2D_ERR_ARG, "wavefunction slot out of range (b2d_vec_reserve)"); \
+  } while (0)
+
+int b2d_vec_upload(b2d_ctx* ctx, int slot, const double* flat) {
+  NEED_DEVICE(); NEED_PLAN(); CHECK_SLOT(slot);
+  if (!flat) return fail(ctx, B2D_ERR_ARG, "null buffer");
+  CU(cudaMemcpyAsync(ctx->flat_in.p, flat, (size_t)ctx->psi.W * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CU(launch_pack((const BlockDesc*)ctx->psi_blocks.p, ctx->psi.nblocks(), (const double*)ctx->flat_in.p, user_vec(ctx, slot), ctx->stream, &ctx->launches));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return B2D_OK;
+}
+int b2d_vec_download(b2d_ctx* ctx, int slot, double* flat) {
+  NEED_DEVICE(); NEED_PLAN(); CHECK_SLOT(slot);
+  if (!flat) return fail(ctx, B2D_ERR_ARG, "null buffer");
+  CU(launch_unpack((const BlockDesc*)ctx->psi_blocks.p, ctx->psi.nblocks(), user_vec(ctx, slot), (double*)ctx->flat_out.p, ctx->stream, &ctx->launches));
+  CU(cudaMemcpyAsync(flat, ctx->flat_out.p, (size_t)ctx->psi.W * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return B2D_OK;
+}
+int b2d_vec_dot(b2d_ctx* ctx, int a, int b, double* out) {
+  NEED_DEVICE(); NEED_PLAN(); CHECK_SLOT(a); CHECK_SLOT(b);
+  VecList x; x.p[0] = user_vec(ctx, a);
+  double* sc = (double*)ctx->scalars.p;
+  CU(launch_multi_dot(1, x, user_vec(ctx, b), ctx->psi.Wp, (double*)ctx->partials.p, sc, ctx->stream, &ctx->launches));
+  CU(cudaMemcpyAsync(ctx->h_pinned, sc, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  *out = ctx->h_pinned[0];
+  return B2D_OK;
+}
+int b2d_vec_axpy(b2d_ctx* ctx, double alpha, int x, int y) {
+  NEED_DEVICE(); NEED_PLAN(); CHECK_SLOT(x); CHECK_SLOT(y);
+  CU(launch_axpy(user_vec(ctx, y), user_vec(ctx, x), nullptr, alpha, ctx->psi.Wp, ctx->stream, &ctx->launches));
+  return B2D_OK;
+}
+int b2d_vec_scale(b2d_ctx* ctx, double alpha, int x) {
+  NEED_DEVICE(); NEED_PLAN(); CHECK_SLOT(x);
+  CU(launch_scale(user_vec(ctx, x), alpha, ctx->psi.Wp, ctx->stream, &ctx->launches));
+  return B2D_OK;
+}
+int b2d_vec_copy(b2d_ctx* ctx, int src, int dst) {
+  NEED_DEVICE(); NEED_PLAN(); CHECK_SLOT(src); CHECK_SLOT(dst);
+  if (src != dst) CU(cudaMemcpyAsync(user_vec(ctx, dst), user_vec(ctx, src), (size_t)ctx->psi.Wp * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  return B2D_OK;
+}
+int b2d_vec_clear(b2d_ctx* ctx, int slot) {
+  NEED_DEVICE(); NEED_PLAN(); CHECK_SLOT(slot);
+  CU(cudaMemsetAsync(user_vec(ctx, slot), 0, (size_t)ctx->psi.Wp * 8, ctx->stream));
+  return B2D_OK;
+}
+
+// ---- sigma ----------------------------------------------------------------------------------------------------
+int b2d_sigma(b2d_ctx* ctx, int src_slot, int dst_slot, int accumulate) {
+  NEED_DEVICE(); NEED_PLAN(); CHECK_SLOT(src_slot); CHECK_SLOT(dst_slot);
+  if (src_slot == dst_slot) return fail(ctx, B2D_ERR_ARG, "b2d_sigma: src and dst must differ");
+  CU(cudaSetDevice(ctx->device));
+  begin_timing(ctx);
+  int rc;
+  if (accumulate && ctx->nranks > 1 && ctx->nccl.comm) {
+    // partial sums must be reduced before they are added to v: go through a scratch slot of the Davidson pool
+    if (ctx->ndav < 1) { CU(ctx->dav_pool.reserve((size_t)ctx->psi.Wp * 8)); ctx->ndav = 1; }
+    rc = sigma_dev(ctx, user_vec(ctx, src_slot), dav_vec(ctx, 0), false, true);
+    if (rc) return rc;
+    CU(launch_axpy(user_vec(ctx, dst_slot), dav_vec(ctx, 0), nullptr, 1.0, ctx->psi.Wp, ctx->stream, &ctx->launches));
+  } else {
+    rc = sigma_dev(ctx, user_vec(ctx, src_slot), user_vec(ctx, dst_slot), accumulate != 0, true);
+    if (rc) return rc;
+  }
+  end_timing(ctx);
+  return B2D_OK;
+}
+
+int b2d_multiplyH_host(b2d_ctx* ctx, const double* c_flat, double* v_flat, int accumulate) {
+  NEED_DEVICE(); NEED_PLAN();
+  if (!c_flat || !v_flat) return fail(ctx, B2D_ERR_ARG, "null buffer");
+  CU(cudaSetDevice(ctx->device));
+  if (ctx->ndav < 2) {
+    CU(ctx->dav_pool.reserve((size_t)2 * ctx->psi.Wp * 8));
+    CU(cudaMemsetAsync(ctx->dav_pool.p, 0, (size_t)2 * ctx->psi.Wp * 8, ctx->stream));
+    ctx->ndav = std::max(ctx->ndav, 2);
+  }
+  double* c = dav_vec(ctx, 0);
+  double* v = dav_vec(ctx, 1);
+  const BlockDesc* bd = (const BlockDesc*)ctx->psi_blocks.p;
+  begin_timing(ctx);
+  CU(cudaMemcpyAsync(ctx->flat_in.p, c_flat, (size_t)ctx->psi.W * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CU(launch_pack(bd, ctx->psi.nblocks(), (const double*)ctx->flat_in.p, c, ctx->stream, &ctx->launches));
+  int rc = sigma_dev(ctx, c, v, false, true);
+  if (rc) return rc;
+  CU(launch_unpack(bd, ctx->psi.nblocks(), v, (double*)ctx->flat_out.p, ctx->stream, &ctx->launches));
+  if (accumulate) {
+    CU(cudaMemcpyAsync(ctx->flat_in.p, v_flat, (size_t)ctx->psi.W * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(launch_axpy((double*)ctx->flat_out.p, (const double*)ctx->flat_in.p, nullptr, 1.0, ctx->psi.W, ctx->stream, &ctx->launches));
+  }
+  CU(cudaMemcpyAsync(v_flat, ctx->flat_out.p, (size_t)ctx->psi.W * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  end_timing(ctx);
+  CU(cudaStreamSynchronize(ctx->stream));
+  return B2D_OK;
+}
+
+int b2d_tensor_multiply(b2d_ctx* ctx, int left_op, int right_op, int flags, int opq_spin, double scale, int src_slot, int dst_slot) {
+  NEED_DEVICE(); NEED_PLAN(); CHECK_SLOT(src_slot); CHECK_SLOT(dst_slot);
+  if (left_op < 0 || right_op < 0 || left_op >= (int)ctx->side[0].ops.size() || right_op >= (int)ctx->side[1].ops.size())
+    return fail(ctx, B2D_ERR_ARG, "b2d_tensor_multiply: operator id out of range (the one-operator form is not available yet)");
+  if (src_slot == dst_slot) return fail(ctx, B2D_ERR_ARG, "b2d_tensor_multiply: src and dst must differ");
+  std::vector<Term> one(1, Term{left_op, right_op, (flags & 1) != 0, (flags & 2) != 0, scale, ctx->rank});
+  Schedule S;
+  try {
+    S = build_schedule(ctx->side[0], ctx->side[1], ctx->psi, one, opq_spin, (int64_t)1 << 60, ctx->forced_class, ctx->am);
+  } catch (const std::exception& e) { return fail(ctx, B2D_ERR_ARG, e.what()); }
+  DevSchedule D;
+  int rc = upload_schedule(ctx, S, D);
+  if (rc) return rc;
+  rc = run_schedule(ctx, S, D, user_vec(ctx, src_slot), user_vec(ctx, dst_slot), nullptr);
+  CU(cudaStreamSynchronize(ctx->stream));
+  D.buf.release();
+  return rc;
+}
+
+int b2d_diagonal(b2d_ctx* ctx, int dst_slot) {
+  NEED_DEVICE(); NEED_PLAN(); CHECK_SLOT(dst_slot);
+  CU(cudaSetDevice(ctx->device));
+  std::vector<DiagTask> tasks;
+  std::vector<int> begin;
+  try {
+    build_diag_tasks(ctx->side[0], ctx->side[1], ctx->psi, ctx->terms_all, ctx->core_energy, ctx->hubbard, ctx->am, tasks, begin);
+  } catch (const std::exception& e) { return fail(ctx, B2D_ERR_ARG, e.what()); }
+  int rc = upload_desc(ctx, ctx->diag_tasks, tasks.data(), tasks.size() * sizeof(DiagTask));
+  if (rc) return rc;
+  rc = upload_desc(ctx, ctx->diag_begin, begin.data(), begin.size() * sizeof(int));
+  if (rc) return rc;
+  begin_timing(ctx);
+  CU(cudaMemsetAsync(user_vec(ctx, dst_slot), 0, (size_t)ctx->psi.Wp * 8, ctx->stream));
+  CU(launch_diag((const BlockDesc*)ctx->psi_blocks.p, ctx->psi.nblocks(), (const DiagTask*)ctx->diag_tasks.p, (const int*)ctx->diag_begin.p,
+                 user_vec(ctx, dst_slot), ctx->stream, &ctx->launches));
+  end_timing(ctx);
+  return B2D_OK;
+}
+
+// ---- Davidson ---------------------------------------------------------------------------------------------------
+int b2d_davidson(b2d_ctx* ctx, int nroots, int guess_slot0, int diag_slot, double normtol, int deflation_min, int deflation_max,
+                 double* evals, int* n_multiply, double* residual) {
+  NEED_DEVICE(); NEED_PLAN();
+  if (nroots < 1 || deflation_max > 30 || deflation_min < nroots || deflation_max <= deflation_min)
+    return fail(ctx, B2D_ERR_ARG, "b2d_davidson: need nroots >= 1 and nroots <= deflation_min < deflation_max <= 30");
+  for (int i = 0; i < nroots; ++i) CHECK_SLOT(guess_slot0 + i);
+  CHECK_SLOT(diag_slot);
+  CU(cudaSetDevice(ctx->device));
+  const int64_t n = ctx->psi.Wp;
+  const int maxsub = deflation_max + 1;
+  const int need = 2 * maxsub + 1;
+  if (ctx->ndav < need) {
+    CU(ctx->dav_pool.reserve((size_t)need * n * 8));
+    ctx->ndav = need;
+  }
+  // slot pointers: B[i], S[i] (i < maxsub) and the residual scratch R
+  std::vector<double*> B(maxsub), Sg(maxsub);
+  for (int i = 0; i < maxsub; ++i) { B[i] = dav_vec(ctx, i); Sg[i] = dav_vec(ctx, maxsub + i); }
+  double* R = dav_vec(ctx, 2 * maxsub);
+  double* diag = user_vec(ctx, diag_slot);
+  double* partials = (double*)ctx->partials.p;
+  // scalar area: Gt[32*32] | theta[32] | alpha[32*32] | misc[64]
+  double* sc = (double*)ctx->scalars.p;
+  double* Gt = sc; double* theta = sc + 1024; double* alpha = sc + 1056; double* misc = sc + 2080;
+  const int LDG = 32;
+  cudaStream_t st = ctx->stream;
+  int64_t* L = &ctx->launches;
+  begin_timing(ctx);
+  for (int i = 0; i < nroots; ++i) CU(cudaMemcpyAsync(B[i], user_vec(ctx, guess_slot0 + i), (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+  // Gram-Schmidt of the guesses (linear.C:190-198)
+  for (int i = 0; i < nroots; ++i) {
+    for (int j = 0; j < i; ++j) {
+      VecList x; x.p[0] = B[j];
+      CU(launch_multi_dot(1, x, B[i], n, partials, misc, st, L));
+      CU(launch_axpy(B[i], B[j], misc, -1.0, n, st, L));
+    }
+    CU(launch_normalise(B[i], n, partials, misc, st, L));
+  }
+  int nb = nroots, nsig = 0, converged = 0, nmult = 0;
+  double rnorm = 0.0;
+  int rc = B2D_OK;
+  for (int iter = 0;; ++iter) {
+    if (iter >= ctx->max_davidson_iter) { rc = fail(ctx, B2D_ERR_NOCONV, "b2d_davidson: iteration cap reached"); break; }
+    for (int i = nsig; i < nb; ++i) {                                  // linear.C:234-257
+      rc = sigma_dev(ctx, B[i], Sg[i], false, true);
+      if (rc) return rc;
+      ++nmult;
+    }
+    nsig = nb;
+    // subspace matrix (linear.C:266-270): Gt[j][i] = <b_i|sigma_j>, i >= j
+    for (int j = 0; j < nb; ++j) {
+      VecList x;
+      for (int i = j; i < nb; ++i) x.p[i - j] = B[i];
+      CU(launch_multi_dot(nb - j, x, Sg[j], n, partials, Gt + j * LDG + j, st, L));
+    }
+    CU(launch_subspace_eig(Gt, nb, LDG, theta, alpha, st, L));         // :273
+    {                                                                  // Ritz rotation of b and sigma (:279-294)
+      VecList xb, xs;
+      for (int i = 0; i < nb; ++i) { xb.p[i] = B[i]; xs.p[i] = Sg[i]; }
+      CU(launch_rotate(nb, nb, xb, alpha, LDG, n, st, L));
+      CU(launch_rotate(nb, nb, xs, alpha, LDG, n, st, L));
+    }
+    // roots that were converged must still be (:298-307)
+    if (converged > 0) {
+      for (int i = 0; i < converged; ++i) CU(launch_residual(Sg[i], B[i], theta + i, R, n, partials, misc + 8 + i, st, L));
+      CU(cudaMemcpyAsync(ctx->h_pinned, misc + 8, (size_t)converged * 8, cudaMemcpyDeviceToHost, st));
+      CU(cudaStreamSynchronize(st));
+      for (int i = 0; i < converged; ++i)
+        if (ctx->h_pinned[i] > normtol) { converged = i; break; }
+    }
+    CU(launch_residual(Sg[converged], B[converged], theta + converged, R, n, partials, misc + 4, st, L));   // :308-309, :323
+    CU(cudaMemcpyAsync(ctx->h_pinned, misc + 4, 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));                                     // the one host read per iteration
+    rnorm = ctx->h_pinned[0];
+    if (rnorm < normtol) {                                             // :335-348
+      ++converged;
+      if (converged == nroots) break;
+      continue;
+    }
+    CU(launch_olsen(R, B[converged], diag, theta + converged, n, partials, misc, st, L));                   // :331
+    if (nb >= deflation_max) { nb = deflation_min; nsig = deflation_min; }                                  // :352-357
+    for (int j = 0; j < nb; ++j) CU(launch_mgs_step(R, B[j], n, partials, misc, st, L));                    // :358-366
+    CU(launch_normalise(R, n, partials, misc, st, L));
+    std::swap(R, B[nb]);
+    ++nb;
+  }
+  if (rc == B2D_OK) {
+    CU(cudaMemcpyAsync(ctx->h_pinned, theta, (size_t)nroots * 8, cudaMemcpyDeviceToHost, st));
+    for (int i = 0; i < nroots; ++i) CU(cudaMemcpyAsync(user_vec(ctx, guess_slot0 + i), B[i], (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
+    end_timing(ctx);
+    CU(cudaStreamSynchronize(st));
+    for (int i = 0; i < nroots; ++i) evals[i] = ctx->h_pinned[i];
+  }
+  if (n_multiply) *n_multiply = nmult;
+  if (residual) *residual = rnorm;
+  return rc;
+}
+
+// ---- renormalisation ----------------------------------------------------------------------------------------------
+static void density_layout(b2d_ctx* ctx) {
+  const Side& L = ctx->side[0];
+  ctx->rho_off.assign(L.nq, 0);
+  int64_t off = 0;
+  for (int q = 0; q < L.nq; ++q) { ctx->rho_off[q] = off; off += align_up((int64_t)L.dims[q] * pad_ld(L.dims[q]), BLK_ALIGN); }
+  ctx->rho_padded = off;
+}
+
+int b2d_make_density(b2d_ctx* ctx, int nroots, int slot0, const double* weights) {
+  NEED_DEVICE(); NEED_PLAN();
+  if (nroots < 1 || !weights) return fail(ctx, B2D_ERR_ARG, "b2d_make_density: bad arguments");
+  for (int i = 0; i < nroots; ++i) CHECK_SLOT(slot0 + i);
+  CU(cudaSetDevice(ctx->device));
+  const Side& L = ctx->side[0];
+  const PsiLayout& P = ctx->psi;
+  density_layout(ctx);
+  CU(ctx->rho.reserve((size_t)ctx->rho_padded * 8));
+  // one group per left sector, one segment per (root, rQ): rho[q] += w psi[q,r] psi[q,r]^T   (operatorfunctions.C:640-649)
+  Schedule S;
+  Chunk ch;
+  std::vector<std::vector<GSeg>> per(L.nq);
+  for (int i = 0; i < nroots; ++i) {
+    if (std::fabs(weights[i]) < 1e-20) continue;    // density.C:86 skips negligible weights
+    for (int p = 0; p < P.nblocks(); ++p) {
+      GSeg s;
+      memset(&s, 0, sizeof(s));
+      s.a = s.b = (int64_t)(slot0 + i) * P.Wp + P.dev_off[p];
+      s.a_base = s.b_base = B2D_BASE_SRC;
+      s.a_trans = 0; s.b_kmajor = 1;
+      s.lda = s.ldb = P.ld[p];
+      s.k = P.cols[p];
+      s.alpha = weights[i];
+      per[P.bl[p]].push_back(s);
+    }
+  }
+  for (int q = 0; q < L.nq; ++q) {
+    GGroup G;
+    memset(&G, 0, sizeof(G));
+    G.c = ctx->rho_off[q]; G.c_base = B2D_BASE_AUX; G.ldc = pad_ld(L.dims[q]); G.m = G.n = L.dims[q]; G.accumulate = 0;
+    G.seg_begin = (int)ch.step2.segs.size();
+    ch.step2.segs.insert(ch.step2.segs.end(), per[q].begin(), per[q].end());
+    G.seg_end = (int)ch.step2.segs.size();
+    ch.step2.groups.push_back(G);
+  }
+  make_tiles(ch.step2, ctx->forced_class);
+  ch.nterms = 1;
+  S.chunks.push_back(std::move(ch));
+  DevSchedule D;
+  int rc = upload_schedule(ctx, S, D);
+  if (rc) return rc;
+  begin_timing(ctx);
+  CU(cudaMemsetAsync(ctx->rho.p, 0, (size_t)ctx->rho_padded * 8, ctx->stream));
+  rc = run_schedule(ctx, S, D, (double*)ctx->user_pool.p, nullptr, (double*)ctx->rho.p);
+  end_timing(ctx);
+  CU(cudaStreamSynchronize(ctx->stream));
+  D.buf.release();
+  ctx->have_eig = ctx->have_rot = ctx->have_rotated = false;
+  return rc;
+}
+
+int64_t b2d_density_size(const b2d_ctx* ctx) {
+  if (!ctx || ctx->side[0].nq == 0) return -1;
+  int64_t n = 0;
+  for (int d : ctx->side[0].dims) n += (int64_t)d * d;
+  return n;
+}
+
+static std::vector<BlockDesc> density_blocks(b2d_ctx* ctx) {
+  const Side& L = ctx->side[0];
+  std::vector<BlockDesc> bd(L.nq);
+  int64_t ref = 0;
+  for (int q = 0; q < L.nq; ++q) {
+    bd[q].ref_off = ref; bd[q].dev_off = ctx->rho_off[q]; bd[q].rows = bd[q].cols = L.dims[q]; bd[q].ld = pad_ld(L.dims[q]); bd[q].pad = 0;
+    ref += (int64_t)L.dims[q] * L.dims[q];
+  }
+  return bd;
+}
+
+int b2d_density_download(b2d_ctx* ctx, double* rho) {
+  NEED_DEVICE(); NEED_PLAN();
+  if (!ctx->rho.p || !rho) return fail(ctx, B2D_ERR_ARG, "no density matrix yet");
+  std::vector<BlockDesc> bd = density_blocks(ctx);
+  int64_t n = b2d_density_size(ctx);
+  CU(ctx->staging.reserve((size_t)n * 8));
+  int rc = upload_desc(ctx, ctx->desc_scratch, bd.data(), bd.size() * sizeof(BlockDesc));
+  if (rc) return rc;
+  CU(launch_unpack((const BlockDesc*)ctx->desc_scratch.p, (int)bd.size(), (const double*)ctx->rho.p, (double*)ctx->staging.p, ctx->stream, &ctx->launches));
+  CU(cudaMemcpyAsync(rho, ctx->staging.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return B2D_OK;
+}
+
+int b2d_density_upload(b2d_ctx* ctx, const double* rho) {
+  NEED_DEVICE(); NEED_PLAN();
+  if (!rho) return fail(ctx, B2D_ERR_ARG, "null buffer");
+  density_layout(ctx);
+  CU(ctx->rho.reserve((size_t)ctx->rho_padded * 8));
+  CU(cudaMemsetAsync(ctx->rho.p, 0, (size_t)ctx->rho_padded * 8, ctx->stream));
+  std::vector<BlockDesc> bd = density_blocks(ctx);
+  int64_t n = b2d_density_size(ctx);
+  CU(ctx->staging.reserve((size_t)n * 8));
+  CU(cudaMemcpyAsync(ctx->staging.p, rho, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = upload_desc(ctx, ctx->desc_scratch, bd.data(), bd.size() * sizeof(BlockDesc));
+  if (rc) return rc;
+  CU(launch_pack((const BlockDesc*)ctx->desc_scratch.p, (int)bd.size(), (const double*)ctx->staging.p, (double*)ctx->rho.p, ctx->stream, &ctx->launches));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->have_eig = ctx->have_rot = ctx->have_rotated = false;
+  return B2D_OK;
+}
+
+int b2d_diagonalise_dm(b2d_ctx* ctx, double* evals_out) {
+  NEED_DEVICE(); NEED_PLAN();
+  if (!ctx->rho.p) return fail(ctx, B2D_ERR_ARG, "no density matrix yet");
+  CU(cudaSetDevice(ctx->device));
+  const Side& L = ctx->side[0];
+  int64_t nev = 0;
+  std::vector<BlockDesc> sd(L.nq);
+  for (int q = 0; q < L.nq; ++q) {
+    sd[q].rows = sd[q].cols = L.dims[q]; sd[q].ld = pad_ld(L.dims[q]); sd[q].dev_off = ctx->rho_off[q]; sd[q].ref_off = nev; sd[q].pad = 0;
+    nev += L.dims[q];
+  }
+  CU(ctx->eig_g.reserve((size_t)ctx->rho_padded * 8));
+  CU(ctx->eig_vt.reserve((size_t)ctx->rho_padded * 8));
+  CU(ctx->eig_vals.reserve((size_t)nev * 8));
+  CU(ctx->eig_sweeps.reserve((size_t)L.nq * 4));
+  int rc = upload_desc(ctx, ctx->sector_desc, sd.data(), sd.size() * sizeof(BlockDesc));
+  if (rc) return rc;
+  begin_timing(ctx);
+  CU(cudaMemcpyAsync(ctx->eig_g.p, ctx->rho.p, (size_t)ctx->rho_padded * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(launch_sector_eig((const BlockDesc*)ctx->sector_desc.p, L.nq, (double*)ctx->eig_g.p, (double*)ctx->eig_vt.p, (double*)ctx->eig_vals.p,
+                       (int*)ctx->eig_sweeps.p, ctx->stream, &ctx->launches));
+  end_timing(ctx);
+  std::vector<double> raw(nev);
+  CU(cudaMemcpyAsync(raw.data(), ctx->eig_vals.p, (size_t)nev * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  // ascending order per sector (dsyev), clamp < 1e-14 to 0 (rotationmat.C:274-276)
+  ctx->evals.assign(L.nq, std::vector<double>());
+  ctx->eval_row.assign(L.nq, std::vector<int>());
+  int64_t o = 0;
+  for (int q = 0; q < L.nq; ++q) {
+    int d = L.dims[q];
+    std::vector<int> idx(d);
+    for (int i = 0; i < d; ++i) idx[i] = i;
+    std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return raw[o + a] < raw[o + b]; });
+    ctx->eval_row[q] = idx;
+    ctx->evals[q].resize(d);
+    for (int i = 0; i < d; ++i) { double w = raw[o + idx[i]]; ctx->evals[q][i] = w < 1e-14 ? 0.0 : w; }
+    if (evals_out) for (int i = 0; i < d; ++i) evals_out[o + i] = ctx->evals[q][i];
+    o += d;
+  }
+  ctx->have_eig = true;
+  ctx->have_rot = ctx->have_rotated = false;
+  return B2D_OK;
+}
+
+static void rotation_layout(b2d_ctx* ctx) {
+  const Side& L = ctx->side[0];
+  ctx->rot_off.assign(L.nq, 0);
+  int64_t off = 0;
+  for (int q = 0; q < L.nq; ++q) { ctx->rot_off[q] = off; off += align_up((int64_t)L.dims[q] * pad_ld(std::max(ctx->kept[q], 1)), BLK_ALIGN); }
+  ctx->rot.reserve((size_t)std::max<int64_t>(off, 16) * 8);
+}
+
+int b2d_select_states(b2d_ctx* ctx, int keep_states, int32_t* kept_counts, double* discarded) {
+  NEED_DEVICE(); NEED_PLAN();
+  if (!ctx->have_eig) return fail(ctx, B2D_ERR_ARG, "call b2d_diagonalise_dm first");
+  const Side& L = ctx->side[0];
+  std::vector<std::vector<int>> kept;
+  double err = select_states(ctx->evals, keep_states, kept);
+  ctx->kept.assign(L.nq, 0);
+  for (int q = 0; q < L.nq; ++q) ctx->kept[q] = (int)kept[q].size();
+  rotation_layout(ctx);
+  if (!ctx->rot.p) return fail(ctx, B2D_ERR_CUDA, "rotation buffer allocation failed");
+  std::vector<GatherDesc> gd;
+  std::vector<int> rows;
+  for (int q = 0; q < L.nq; ++q) {
+    if (kept[q].empty()) continue;
+    GatherDesc g;
+    g.vt_off = ctx->rho_off[q]; g.u_off = ctx->rot_off[q]; g.d = L.dims[q]; g.ld_vt = pad_ld(L.dims[q]);
+    g.ncols = (int)kept[q].size(); g.ld_u = pad_ld(g.ncols); g.row_begin = (int)rows.size(); g.pad = 0;
+    for (int s : kept[q]) rows.push_back(ctx->eval_row[q][s]);
+    gd.push_back(g);
+  }
+  CU(cudaMemsetAsync(ctx->rot.p, 0, ctx->rot.cap, ctx->stream));
+  int rc = upload_desc(ctx, ctx->gather_desc, gd.data(), gd.size() * sizeof(GatherDesc));
+  if (rc) return rc;
+  rc = upload_desc(ctx, ctx->gather_rows, rows.data(), rows.size() * sizeof(int));
+  if (rc) return rc;
+  CU(launch_gather_rotation((const GatherDesc*)ctx->gather_desc.p, (int)gd.size(), (const int*)ctx->gather_rows.p, (const double*)ctx->eig_vt.p,
+                            (double*)ctx->rot.p, ctx->stream, &ctx->launches));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (kept_counts) for (int q = 0; q < L.nq; ++q) kept_counts[q] = ctx->kept[q];
+  if (discarded) *discarded = err;
+  ctx->have_rot = true;
+  ctx->have_rotated = false;
+  return B2D_OK;
+}
+
+int64_t b2d_rotation_size(const b2d_ctx* ctx) {
+  if (!ctx || !ctx->have_rot) return -1;
+  int64_t n = 0;
+  for (int q = 0; q < ctx->side[0].nq; ++q) n += (int64_t)ctx->side[0].dims[q] * ctx->kept[q];
+  return n;
+}
+
+static std::vector<BlockDesc> rotation_blocks(b2d_ctx* ctx) {
+  const Side& L = ctx->side[0];
+  std::vector<BlockDesc> bd;
+  int64_t ref = 0;
+  for (int q = 0; q < L.nq; ++q) {
+    if (ctx->kept[q] == 0) continue;
+    BlockDesc d;
+    d.ref_off = ref; d.dev_off = ctx->rot_off[q]; d.rows = L.dims[q]; d.cols = ctx->kept[q]; d.ld = pad_ld(ctx->kept[q]); d.pad = 0;
+    ref += (int64_t)d.rows * d.cols;
+    bd.push_back(d);
+  }
+  return bd;
+}
+
+int b2d_rotation_download(b2d_ctx* ctx, double* rot) {
+  NEED_DEVICE(); NEED_PLAN();
+  if (!ctx->have_rot || !rot) return fail(ctx, B2D_ERR_ARG, "no rotation matrices yet");
+  std::vector<BlockDesc> bd = rotation_blocks(ctx);
+  int64_t n = b2d_rotation_size(ctx);
+  if (n == 0) return B2D_OK;
+  CU(ctx->staging.reserve((size_t)n * 8));
+  int rc = upload_desc(ctx, ctx->desc_scratch, bd.data(), bd.size() * sizeof(BlockDesc));
+  if (rc) return rc;
+  CU(launch_unpack((const BlockDesc*)ctx->desc_scratch.p, (int)bd.size(), (const double*)ctx->rot.p, (double*)ctx->staging.p, ctx->stream, &ctx->launches));
+  CU(cudaMemcpyAsync(rot, ctx->staging.p, (size_t)n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return B2D_OK;
+}
+
+int b2d_rotation_upload(b2d_ctx* ctx, const int32_t* kept_counts, const double* rot) {
+  NEED_DEVICE(); NEED_PLAN();
+  if (!kept_counts || !rot) return fail(ctx, B2D_ERR_ARG, "null buffer");
+  const Side& L = ctx->side[0];
+  ctx->kept.assign(kept_counts, kept_counts + L.nq);
+  rotation_layout(ctx);
+  if (!ctx->rot.p) return fail(ctx, B2D_ERR_CUDA, "rotation buffer allocation failed");
+  ctx->have_rot = true;
+  CU(cudaMemsetAsync(ctx->rot.p, 0, ctx->rot.cap, ctx->stream));
+  std::vector<BlockDesc> bd = rotation_blocks(ctx);
+  int64_t n = b2d_rotation_size(ctx);
+  if (n > 0) {
+    CU(ctx->staging.reserve((size_t)n * 8));
+    CU(cudaMemcpyAsync(ctx->staging.p, rot, (size_t)n * 8, cudaMemcpyHostToDevice, ctx->stream));
+    int rc = upload_desc(ctx, ctx->desc_scratch, bd.data(), bd.size() * sizeof(BlockDesc));
+    if (rc) return rc;
+    CU(launch_pack((const BlockDesc*)ctx->desc_scratch.p, (int)bd.size(), (const double*)ctx->staging.p, (double*)ctx->rot.p, ctx->stream, &ctx->launches));
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->have_rotated = false;
+  return B2D_OK;
+}
+
+int b2d_transform_operators(b2d_ctx* ctx) {
+  NEED_DEVICE(); NEED_PLAN();
+  if (!ctx->have_rot) return fail(ctx, B2D_ERR_ARG, "no rotation matrices (b2d_select_states / b2d_rotation_upload)");
+  CU(cudaSetDevice(ctx->device));
+  const Side& L = ctx->side[0];
+  // new StateInfo: sectors that kept >= 1 state, in old order (save_load_block.C:270-283)
+  Side& N = ctx->rotated;
+  N = Side();
+  ctx->rotated_old.clear();
+  for (int q = 0; q < L.nq; ++q)
+    if (ctx->kept[q] > 0) {
+      ctx->rotated_old.push_back(q);
+      N.q.insert(N.q.end(), L.q.begin() + 3 * q, L.q.begin() + 3 * q + 3);
+      N.dims.push_back(ctx->kept[q]);
+    }
+  N.nq = (int)N.dims.size();
+  N.loop = L.loop; N.sites = L.sites;
+  int64_t total = 0;
+  for (const OpRec& o : L.ops) {
+    OpRec r;
+    r.optype = o.optype; r.norb = o.norb; r.orbs[0] = o.orbs[0]; r.orbs[1] = o.orbs[1]; r.comp = o.comp;
+    memcpy(r.dq, o.dq, sizeof(r.dq)); r.fermion = o.fermion;
+    r.allowed.assign((size_t)N.nq * N.nq, 0);
+    for (int a = 0; a < N.nq; ++a)
+      for (int b = 0; b < N.nq; ++b)
+        r.allowed[(size_t)a * N.nq + b] = o.allowed[(size_t)ctx->rotated_old[a] * L.nq + ctx->rotated_old[b]];
+    layout_op(N, r);
+    total += align_up(r.dev_size, 32);
+    N.ops.push_back(std::move(r));
+  }
+  CU(ctx->rotated_arena.reserve((size_t)std::max<int64_t>(total, 16) * 8));
+  CU(cudaMemsetAsync(ctx->rotated_arena.p, 0, ctx->rotated_arena.cap, ctx->stream));
+  {
+    int64_t off = 0;
+    for (OpRec& r : N.ops) { r.dev = (double*)ctx->rotated_arena.p + off; off += align_up(r.dev_size, 32); }
+  }
+  // schedule: step 1  tmp = O[Q,Q'] U_Q'   step 2  O'[a,b] = U_Q^T tmp     (MatrixRotate, MatrixBLAS.C:553-572)
+  Schedule S;
+  const int64_t budget = (int64_t)(ctx->workspace_mb * 1024.0 * 1024.0 / 8.0);
+  Chunk cur;
+  auto close = [&]() {
+    if (cur.nterms == 0) return;
+    make_tiles(cur.step1, ctx->forced_class);
+    make_tiles(cur.step2, ctx->forced_class);
+    S.work_max = std::max(S.work_max, cur.work);
+    S.chunks.push_back(std::move(cur));
+    cur = Chunk();
+  };
+  double* rot = (double*)ctx->rot.p;
+  (void)rot;
+  for (size_t m = 0; m < L.ops.size(); ++m) {
+    const OpRec& o = L.ops[m];
+    const OpRec& r = N.ops[m];
+    int64_t need = 0;
+    for (int a = 0; a < N.nq; ++a)
+      for (int b = 0; b < N.nq; ++b)
+        if (r.allowed[(size_t)a * N.nq + b]) need += align_up((int64_t)L.dims[ctx->rotated_old[a]] * pad_ld(N.dims[b]), BLK_ALIGN);
+    if (cur.nterms > 0 && cur.work + need > budget) close();
+    cur.nterms++;
+    for (int a = 0; a < N.nq; ++a)
+      for (int b = 0; b < N.nq; ++b) {
+        if (!r.allowed[(size_t)a * N.nq + b]) continue;
+        const int Q = ctx->rotated_old[a], Qp = ctx->rotated_old[b];
+        const int dQ = L.dims[Q], dQp = L.dims[Qp], mQ = N.dims[a], mQp = N.dims[b];
+        const int64_t toff = cur.work;
+        const int ldt = pad_ld(mQp);
+        cur.work += align_up((int64_t)dQ * ldt, BLK_ALIGN);
+        GSeg s1;
+        memset(&s1, 0, sizeof(s1));
+        s1.a = (int64_t)(intptr_t)o.dev + 8 * o.off[(size_t)Q * L.nq + Qp]; s1.a_base = B2D_BASE_ABS; s1.a_trans = 0; s1.lda = pad_ld(dQp);
+        s1.b = ctx->rot_off[Qp]; s1.b_base = B2D_BASE_AUX; s1.b_kmajor = 0; s1.ldb = pad_ld(mQp);
+        s1.k = dQp; s1.alpha = 1.0;
+        GGroup g1;
+        memset(&g1, 0, sizeof(g1));
+        g1.c = toff; g1.c_base = B2D_BASE_WORK; g1.ldc = ldt; g1.m = dQ; g1.n = mQp; g1.accumulate = 0;
+        g1.seg_begin = (int)cur.step1.segs.size(); g1.seg_end = g1.seg_begin + 1;
+        cur.step1.segs.push_back(s1); cur.step1.groups.push_back(g1);
+        GSeg s2;
+        memset(&s2, 0, sizeof(s2));
+        s2.a = ctx->rot_off[Q]; s2.a_base = B2D_BASE_AUX; s2.a_trans = 1; s2.lda = pad_ld(mQ);
+        s2.b = toff; s2.b_base = B2D_BASE_WORK; s2.b_kmajor = 0; s2.ldb = ldt;
+        s2.k = dQ; s2.alpha = 1.0;
+        GGroup g2;
+        memset(&g2, 0, sizeof(g2));
+        g2.c = (r.dev - (double*)ctx->rotated_arena.p) + r.off[(size_t)a * N.nq + b]; g2.c_base = B2D_BASE_DST; g2.ldc = pad_ld(mQp); g2.m = mQ; g2.n = mQp;
+        g2.accumulate = 0;
+        g2.seg_begin = (int)cur.step2.segs.size(); g2.seg_end = g2.seg_begin + 1;
+        cur.step2.segs.push_back(s2); cur.step2.groups.push_back(g2);
+      }
+  }
+  close();
+  DevSchedule D;
+  int rc = upload_schedule(ctx, S, D);
+  if (rc) return rc;
+  begin_timing(ctx);
+  rc = run_schedule(ctx, S, D, nullptr, (double*)ctx->rotated_arena.p, (double*)ctx->rot.p);
+  end_timing(ctx);
+  CU(cudaStreamSynchronize(ctx->stream));
+  D.buf.release();
+  if (rc) return rc;
+  ctx->have_rotated = true;
+  return B2D_OK;
+}
+
+int b2d_rotated_num_sectors(const b2d_ctx* ctx) { return ctx && ctx->have_rotated ? ctx->rotated.nq : -1; }
+int b2d_rotated_sectors(const b2d_ctx* ctx, int32_t* old_index, int32_t* dims) {
+  if (!ctx || !ctx->have_rotated) return B2D_ERR_ARG;
+  for (int a = 0; a < ctx->rotated.nq; ++a) {
+    if (old_index) old_index[a] = ctx->rotated_old[a];
+    if (dims) dims[a] = ctx->rotated.dims[a];
+  }
+  return B2D_OK;
+}
+int64_t b2d_rotated_op_size(const b2d_ctx* ctx, int op_id) {
+  if (!ctx || !ctx->have_rotated || op_id < 0 || op_id >= (int)ctx->rotated.ops.size()) return -1;
+  return ctx->rotated.ops[op_id].packed_size;
+}
+int b2d_rotated_op_download(b2d_ctx* ctx, int op_id, uint8_t* allowed, double* data) {
+  NEED_DEVICE();
+  if (!ctx->have_rotated || op_id < 0 || op_id >= (int)ctx->rotated.ops.size()) return fail(ctx, B2D_ERR_ARG, "no rotated operators");
+  const Side& N = ctx->rotated;
+  const OpRec& op = N.ops[op_id];
+  if (allowed) memcpy(allowed, op.allowed.data(), op.allowed.size());
+  if (!data || op.packed_size == 0) return B2D_OK;
+  std::vector<BlockDesc> bd = op_blocks(N, op);
+  CU(ctx->staging.reserve((size_t)op.packed_size * 8));
+  int rc = upload_desc(ctx, ctx->desc_scratch, bd.data(), bd.size() * sizeof(BlockDesc));
+  if (rc) return rc;
+  CU(launch_unpack((const BlockDesc*)ctx->desc_scratch.p, (int)bd.size(), op.dev, (double*)ctx->staging.p, ctx->stream, &ctx->launches));
+  CU(cudaMemcpyAsync(data, ctx->staging.p, (size_t)op.packed_size * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return B2D_OK;
+}
+
+int b2d_renormalise_from(b2d_ctx* ctx, int nroots, int guess_slot0, const double* weights, double normtol, int keep_states, int deflation_min,
+                         int deflation_max, double* energies, int32_t* kept_counts, double* discarded, int* n_multiply) {
+  NEED_DEVICE(); NEED_PLAN();
+  // diag(H) goes to the slot after the guesses (solver.C:34)
+  int diag_slot = guess_slot0 + nroots;
+  if (ctx->nuser <= diag_slot) {
+    int rc = b2d_vec_reserve(ctx, diag_slot + 1);
+    if (rc) return rc;
+  }
+  int rc = b2d_diagonal(ctx, diag_slot);
+  if (rc) return rc;
+  rc = b2d_davidson(ctx, nroots, guess_slot0, diag_slot, normtol, deflation_min, deflation_max, energies, n_multiply, nullptr);   // solver.C:91
+  if (rc) return rc;
+  rc = b2d_make_density(ctx, nroots, guess_slot0, weights);                                                                        // renormalise.C:104
+  if (rc) return rc;
+  rc = b2d_diagonalise_dm(ctx, nullptr);                                                                                           // :113 -> rotationmat.C:258
+  if (rc) return rc;
+  return b2d_select_states(ctx, keep_states, kept_counts, discarded);
+}
+
+// ---- multi-GPU ----------------------------------------------------------------------------------------------------
+int b2d_nccl_unique_id(uint8_t* id128) {
+  static Nccl loader;
+  std::string err;
+  if (!loader.load(err)) { g_create_error = err; return B2D_ERR_NCCL; }
+  int r = loader.GetUniqueId(id128);
+  if (r != 0) { g_create_error = "ncclGetUniqueId failed"; return B2D_ERR_NCCL; }
+  return B2D_OK;
+}
+
+int b2d_comm_init(b2d_ctx* ctx, const uint8_t* id128, int rank, int nranks) {
+  NEED_DEVICE();
+  if (!id128 || nranks < 1 || rank < 0 || rank >= nranks) return fail(ctx, B2D_ERR_ARG, "b2d_comm_init: bad arguments");
+  std::string err;
+  if (!ctx->nccl.load(err)) return fail(ctx, B2D_ERR_NCCL, err);
+  CU(cudaSetDevice(ctx->device));
+  Nccl::Id128 id;
+  memcpy(id.b, id128, 128);
+  int r = ctx->nccl.CommInitRank(&ctx->nccl.comm, nranks, id, rank);
+  if (r != 0) return fail(ctx, B2D_ERR_NCCL, std::string("ncclCommInitRank: ") + (ctx->nccl.GetErrorString ? ctx->nccl.GetErrorString(r) : "error"));
+  return B2D_OK;
+}
+
+int b2d_allreduce_slot(b2d_ctx* ctx, int slot) {
+  NEED_DEVICE(); NEED_PLAN(); CHECK_SLOT(slot);
+  return allreduce(ctx, user_vec(ctx, slot), ctx->psi.Wp);
+}
+
+// ---- measurement --------------------------------------------------------------------------------------------------
+int b2d_last_timing(b2d_ctx* ctx, double* out, int n) {
+  NEED_DEVICE();
+  if (!ctx->timing_valid || !out) return fail(ctx, B2D_ERR_ARG, "nothing timed yet");
+  CU(cudaEventSynchronize(ctx->ev[1]));
+  float ms = 0.f;
+  CU(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+  double v[4] = {ms, ctx->last_step_ms[0], ctx->last_step_ms[1], 0.0};
+  for (int i = 0; i < n && i < 4; ++i) out[i] = v[i];
+  return B2D_OK;
+}
+int64_t b2d_kernel_launches(const b2d_ctx* ctx) { return ctx ? ctx->launches : -1; }
+int b2d_sync(b2d_ctx* ctx) {
+  NEED_DEVICE();
+  CU(cudaStreamSynchronize(ctx->stream));
+  return B2D_OK;
+}
+void* b2d_stream(b2d_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+int b2d_measure_fp64_peak(b2d_ctx* ctx, double* dmma_tflops, double* dfma_tflops) {
+  NEED_DEVICE();
+  CU(cudaSetDevice(ctx->device));
+  double a = 0, b = 0;
+  CU(measure_fp64(ctx->stream, &a, &b));
+  if (dmma_tflops) *dmma_tflops = a;
+  if (dfma_tflops) *dfma_tflops = b;
+  return B2D_OK;
+}
+
+}  // extern "C"

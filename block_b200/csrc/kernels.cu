@@ -1,0 +1,633 @@
+// sm_100a kernels of the DMRG hot path other than the grouped contraction itself (gemm_grouped.cuh), plus the launch
+// wrappers declared in kernels.h.  Compile: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo
+#include "kernels.h"
+
+#include <math.h>
+
+#include "gemm_grouped.cuh"
+
+namespace b2d {
+
+#define B2D_LAUNCH_CHECK()                 \
+  do {                                     \
+    cudaError_t e_ = cudaGetLastError();   \
+    if (e_ != cudaSuccess) return e_;      \
+    if (launches) ++*launches;             \
+  } while (0)
+
+// ---------------------------------------------------------------------------------------------------------------
+// grouped contraction launches
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int STAGES0 = 4, STAGES1 = 4, STAGES2 = 3;
+static size_t smem_bytes(int cls) {
+  switch (cls) {
+    case 0: return (size_t)STAGES0 * TileSmem<128, 128>::STAGE_DOUBLES * 8;
+    case 1: return (size_t)STAGES1 * TileSmem<64, 64>::STAGE_DOUBLES * 8;
+    default: return (size_t)STAGES2 * TileSmem<32, 32>::STAGE_DOUBLES * 8;
+  }
+}
+
+cudaError_t gemm_init() {
+  cudaError_t e;
+  e = cudaFuncSetAttribute(grouped_gemm_kernel<128, 128, 2, 4, STAGES0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(0));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(grouped_gemm_kernel<64, 64, 2, 2, STAGES1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(1));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(grouped_gemm_kernel<32, 32, 2, 2, STAGES2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(2));
+  return e;
+}
+
+cudaError_t launch_gemm_batch(const DevBatch& b, double* const* bases, cudaStream_t stream, int64_t* launches) {
+  Bases B;
+  for (int i = 0; i < B2D_NUM_BASES; ++i) B.p[i] = bases[i];
+  if (b.ntiles[0] > 0) {
+    grouped_gemm_kernel<128, 128, 2, 4, STAGES0><<<b.ntiles[0], 256, smem_bytes(0), stream>>>(b.segs, b.groups, b.tiles[0], B);
+    B2D_LAUNCH_CHECK();
+  }
+  if (b.ntiles[1] > 0) {
+    grouped_gemm_kernel<64, 64, 2, 2, STAGES1><<<b.ntiles[1], 128, smem_bytes(1), stream>>>(b.segs, b.groups, b.tiles[1], B);
+    B2D_LAUNCH_CHECK();
+  }
+  if (b.ntiles[2] > 0) {
+    grouped_gemm_kernel<32, 32, 2, 2, STAGES2><<<b.ntiles[2], 128, smem_bytes(2), stream>>>(b.segs, b.groups, b.tiles[2], B);
+    B2D_LAUNCH_CHECK();
+  }
+  return cudaSuccess;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// layout conversion
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void pack_kernel(const BlockDesc* __restrict__ blocks, int nblocks, const double* __restrict__ flat, double* __restrict__ dev, int to_dev) {
+  // one CTA strides over blocks; threads stride over elements (column index fastest: coalesced on both sides)
+  for (int b = blockIdx.y; b < nblocks; b += gridDim.y) {
+    const BlockDesc d = blocks[b];
+    const int64_t n = (int64_t)d.rows * d.cols;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+      int r = (int)(e / d.cols), c = (int)(e % d.cols);
+      if (to_dev) dev[d.dev_off + (int64_t)r * d.ld + c] = flat[d.ref_off + e];
+      else ((double*)flat)[d.ref_off + e] = dev[d.dev_off + (int64_t)r * d.ld + c];
+    }
+  }
+}
+
+static dim3 pack_grid(int nblocks) { return dim3(8, (unsigned)min(nblocks, 4096), 1); }
+
+cudaError_t launch_pack(const BlockDesc* blocks, int nblocks, const double* flat, double* dev, cudaStream_t s, int64_t* launches) {
+  if (nblocks == 0) return cudaSuccess;
+  pack_kernel<<<pack_grid(nblocks), 256, 0, s>>>(blocks, nblocks, flat, dev, 1);
+  B2D_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+cudaError_t launch_unpack(const BlockDesc* blocks, int nblocks, const double* dev, double* flat, cudaStream_t s, int64_t* launches) {
+  if (nblocks == 0) return cudaSuccess;
+  pack_kernel<<<pack_grid(nblocks), 256, 0, s>>>(blocks, nblocks, flat, (double*)dev, 0);
+  B2D_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// level-1 kernels.  Reductions are two-stage and ordered (per-CTA partials, then one CTA sums them in a fixed
+// order), so results are bit-reproducible run to run and identical on every rank.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int L1_THREADS = 256;
+
+static int l1_grid(int64_t n) {
+  int64_t want = (n + L1_THREADS * 4 - 1) / (L1_THREADS * 4);
+  if (want < 1) want = 1;
+  if (want > L1_MAX_BLOCKS) want = L1_MAX_BLOCKS;
+  return (int)want;
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// sums `v` over the CTA; result valid in thread 0
+__device__ __forceinline__ double block_sum(double v, double* sh /* 32 doubles */) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    v = lane < (blockDim.x >> 5) ? sh[lane] : 0.0;
+    v = warp_sum(v);
+  }
+  return v;
+}
+
+template <int K>
+__global__ void __launch_bounds__(L1_THREADS) multi_dot_kernel(VecList x, const double* __restrict__ y, int64_t n, double* __restrict__ partials) {
+  __shared__ double sh[32];
+  double acc[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) acc[j] = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const double yv = y[i];
+#pragma unroll
+    for (int j = 0; j < K; ++j) acc[j] += x.p[j][i] * yv;
+  }
+#pragma unroll
+  for (int j = 0; j < K; ++j) {
+    double v = block_sum(acc[j], sh);
+    if (threadIdx.x == 0) partials[(int64_t)blockIdx.x * L1_MAX_VECS + j] = v;
+  }
+}
+
+// out[j] = sum over blocks of partials[b][j], fixed order
+__global__ void finish_kernel(const double* __restrict__ partials, int nblocks, int K, double* __restrict__ out) {
+  __shared__ double sh[32];
+  for (int j = 0; j < K; ++j) {
+    double v = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += blockDim.x) v += partials[(int64_t)b * L1_MAX_VECS + j];
+    v = block_sum(v, sh);
+    if (threadIdx.x == 0) out[j] = v;
+  }
+}
+
+cudaError_t launch_multi_dot(int K, const VecList& x, const double* y, int64_t n, double* partials, double* out, cudaStream_t s, int64_t* launches) {
+  int done = 0;
+  const int grid = l1_grid(n);
+  while (done < K) {
+    int k = K - done >= 8 ? 8 : (K - done >= 4 ? 4 : (K - done >= 2 ? 2 : 1));
+    VecList sub;
+    for (int j = 0; j < k; ++j) sub.p[j] = x.p[done + j];
+    switch (k) {
+      case 8: multi_dot_kernel<8><<<grid, L1_THREADS, 0, s>>>(sub, y, n, partials); break;
+      case 4: multi_dot_kernel<4><<<grid, L1_THREADS, 0, s>>>(sub, y, n, partials); break;
+      case 2: multi_dot_kernel<2><<<grid, L1_THREADS, 0, s>>>(sub, y, n, partials); break;
+      default: multi_dot_kernel<1><<<grid, L1_THREADS, 0, s>>>(sub, y, n, partials); break;
+    }
+    B2D_LAUNCH_CHECK();
+    finish_kernel<<<1, 256, 0, s>>>(partials, grid, k, out + done);
+    B2D_LAUNCH_CHECK();
+    done += k;
+  }
+  return cudaSuccess;
+}
+
+__global__ void __launch_bounds__(L1_THREADS) rotate_kernel(int n_in, int n_out, VecList x, const double* __restrict__ alpha, int lda, int64_t n) {
+  __shared__ double a[L1_MAX_VECS * L1_MAX_VECS];
+  for (int i = threadIdx.x; i < n_in * n_out; i += blockDim.x) a[i] = alpha[(i / n_out) * lda + (i % n_out)];
+  __syncthreads();
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+    double v[L1_MAX_VECS];
+#pragma unroll
+    for (int i = 0; i < L1_MAX_VECS; ++i) v[i] = i < n_in ? x.p[i][e] : 0.0;
+    for (int j = 0; j < n_out; ++j) {
+      double s = 0.0;
+#pragma unroll
+      for (int i = 0; i < L1_MAX_VECS; ++i)
+        if (i < n_in) s += a[i * n_out + j] * v[i];
+      x.p[j][e] = s;
+    }
+  }
+}
+
+cudaError_t launch_rotate(int n_in, int n_out, const VecList& x, const double* alpha, int lda, int64_t n, cudaStream_t s, int64_t* launches) {
+  rotate_kernel<<<l1_grid(n), L1_THREADS, 0, s>>>(n_in, n_out, x, alpha, lda, n);
+  B2D_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+__global__ void __launch_bounds__(L1_THREADS) residual_kernel(const double* __restrict__ sigma, const double* __restrict__ b, const double* __restrict__ theta,
+                                                              double* __restrict__ r, int64_t n, double* __restrict__ partials) {
+  __shared__ double sh[32];
+  const double th = theta[0];
+  double acc = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double v = sigma[i] - th * b[i];
+    r[i] = v;
+    acc += v * v;
+  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) partials[(int64_t)blockIdx.x * L1_MAX_VECS] = acc;
+}
+
+cudaError_t launch_residual(const double* sigma, const double* b, const double* theta, double* r, int64_t n, double* partials, double* out, cudaStream_t s, int64_t* launches) {
+  const int grid = l1_grid(n);
+  residual_kernel<<<grid, L1_THREADS, 0, s>>>(sigma, b, theta, r, n, partials);
+  B2D_LAUNCH_CHECK();
+  finish_kernel<<<1, 256, 0, s>>>(partials, grid, 1, out);
+  B2D_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+__device__ __forceinline__ double precond(double v, double den) { return fabs(den) > 1e-12 ? v / den : v; }   // linear.C:35-40
+
+__global__ void __launch_bounds__(L1_THREADS) olsen_dots_kernel(const double* __restrict__ r, const double* __restrict__ c0, const double* __restrict__ diag,
+                                                                const double* __restrict__ theta, int64_t n, double* __restrict__ partials) {
+  __shared__ double sh[32];
+  const double th = theta[0];
+  double d1 = 0.0, d2 = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double c = c0[i], cp = precond(c, th - diag[i]);
+    d1 += cp * r[i];
+    d2 += c * cp;
+  }
+  d1 = block_sum(d1, sh);
+  if (threadIdx.x == 0) partials[(int64_t)blockIdx.x * L1_MAX_VECS] = d1;
+  d2 = block_sum(d2, sh);
+  if (threadIdx.x == 0) partials[(int64_t)blockIdx.x * L1_MAX_VECS + 1] = d2;
+}
+
+__global__ void __launch_bounds__(L1_THREADS) olsen_apply_kernel(double* __restrict__ r, const double* __restrict__ c0, const double* __restrict__ diag,
+                                                                 const double* __restrict__ theta, const double* __restrict__ dots, int64_t n) {
+  const double th = theta[0];
+  const double ratio = dots[0] / dots[1];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    r[i] = precond(r[i] - ratio * c0[i], th - diag[i]);
+}
+
+cudaError_t launch_olsen(double* r, const double* c0, const double* diag, const double* theta, int64_t n, double* partials, double* scratch2, cudaStream_t s, int64_t* launches) {
+  const int grid = l1_grid(n);
+  olsen_dots_kernel<<<grid, L1_THREADS, 0, s>>>(r, c0, diag, theta, n, partials);
+  B2D_LAUNCH_CHECK();
+  finish_kernel<<<1, 256, 0, s>>>(partials, grid, 2, scratch2);
+  B2D_LAUNCH_CHECK();
+  olsen_apply_kernel<<<grid, L1_THREADS, 0, s>>>(r, c0, diag, theta, scratch2, n);
+  B2D_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+__global__ void __launch_bounds__(L1_THREADS) mgs_dots_kernel(const double* __restrict__ r, const double* __restrict__ b, int64_t n, double* __restrict__ partials) {
+  __shared__ double sh[32];
+  double rr = 0.0, rb = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double v = r[i];
+    rr += v * v;
+    rb += v * (b ? b[i] : 0.0);
+  }
+  rr = block_sum(rr, sh);
+  if (threadIdx.x == 0) partials[(int64_t)blockIdx.x * L1_MAX_VECS] = rr;
+  rb = block_sum(rb, sh);
+  if (threadIdx.x == 0) partials[(int64_t)blockIdx.x * L1_MAX_VECS + 1] = rb;
+}
+
+__global__ void __launch_bounds__(L1_THREADS) mgs_apply_kernel(double* __restrict__ r, const double* __restrict__ b, const double* __restrict__ dots, int64_t n) {
+  const double inv = 1.0 / sqrt(dots[0]);
+  const double coef = dots[1] * inv;   // <r/|r| | b>
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    r[i] = b ? r[i] * inv - coef * b[i] : r[i] * inv;
+}
+
+cudaError_t launch_mgs_step(double* r, const double* b, int64_t n, double* partials, double* scratch2, cudaStream_t s, int64_t* launches) {
+  const int grid = l1_grid(n);
+  mgs_dots_kernel<<<grid, L1_THREADS, 0, s>>>(r, b, n, partials);
+  B2D_LAUNCH_CHECK();
+  finish_kernel<<<1, 256, 0, s>>>(partials, grid, 2, scratch2);
+  B2D_LAUNCH_CHECK();
+  mgs_apply_kernel<<<grid, L1_THREADS, 0, s>>>(r, b, scratch2, n);
+  B2D_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+cudaError_t launch_normalise(double* r, int64_t n, double* partials, double* scratch1, cudaStream_t s, int64_t* launches) {
+  return launch_mgs_step(r, nullptr, n, partials, scratch1, s, launches);
+}
+
+__global__ void __launch_bounds__(L1_THREADS) axpy_kernel(double* __restrict__ y, const double* __restrict__ x, const double* __restrict__ coef, double mult, int64_t n) {
+  const double a = coef ? mult * coef[0] : mult;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] += a * x[i];
+}
+cudaError_t launch_axpy(double* y, const double* x, const double* coef, double mult, int64_t n, cudaStream_t s, int64_t* launches) {
+  axpy_kernel<<<l1_grid(n), L1_THREADS, 0, s>>>(y, x, coef, mult, n);
+  B2D_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+__global__ void __launch_bounds__(L1_THREADS) scale_kernel(double* __restrict__ x, double a, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) x[i] *= a;
+}
+cudaError_t launch_scale(double* x, double a, int64_t n, cudaStream_t s, int64_t* launches) {
+  scale_kernel<<<l1_grid(n), L1_THREADS, 0, s>>>(x, a, n);
+  B2D_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Davidson subspace eigenproblem (replaces dsyev_ at linear.C:273): two-sided cyclic Jacobi, one warp, n <= 32
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(32) subspace_eig_kernel(const double* __restrict__ G, int n, int ldg, double* __restrict__ theta, double* __restrict__ alpha) {
+  __shared__ double A[32][33], V[32][33];
+  __shared__ int order[32];
+  const int lane = threadIdx.x;
+  for (int i = 0; i < n; ++i)
+    if (lane < n) {
+      A[i][lane] = lane >= i ? G[i * ldg + lane] : G[lane * ldg + i];   // G[j][i] = <b_i|sigma_j>, i >= j, is authoritative (linear.C:266-270)
+      V[i][lane] = i == lane ? 1.0 : 0.0;
+    }
+  __syncwarp();
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = 0.0, dg = 0.0;
+    if (lane < n)
+      for (int j = 0; j < n; ++j) {
+        double v = A[lane][j];
+        if (j == lane) dg += v * v; else off += v * v;
+      }
+    off = warp_sum(off); dg = warp_sum(dg);
+    off = __shfl_sync(0xffffffffu, off, 0); dg = __shfl_sync(0xffffffffu, dg, 0);
+    if (off <= 1e-32 * dg || off == 0.0) break;
+    for (int p = 0; p < n - 1; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        const double apq = A[p][q];
+        if (fabs(apq) > 1e-300) {
+          const double app = A[p][p], aqq = A[q][q];
+          const double zeta = (aqq - app) / (2.0 * apq);
+          const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+          const double c = 1.0 / sqrt(1.0 + tt * tt), s = c * tt;
+          __syncwarp();
+          if (lane < n) {   // columns p, q of A and V
+            double akp = A[lane][p], akq = A[lane][q];
+            A[lane][p] = c * akp - s * akq;
+            A[lane][q] = s * akp + c * akq;
+            double vkp = V[lane][p], vkq = V[lane][q];
+            V[lane][p] = c * vkp - s * vkq;
+            V[lane][q] = s * vkp + c * vkq;
+          }
+          __syncwarp();
+          if (lane < n) {   // rows p, q of A
+            double apk = A[p][lane], aqk = A[q][lane];
+            A[p][lane] = c * apk - s * aqk;
+            A[q][lane] = s * apk + c * aqk;
+          }
+          __syncwarp();
+        }
+      }
+  }
+  __syncwarp();
+  if (lane == 0) {   // ascending order (dsyev convention), stable
+    for (int i = 0; i < n; ++i) order[i] = i;
+    for (int i = 1; i < n; ++i) {
+      int o = order[i], j = i - 1;
+      while (j >= 0 && A[order[j]][order[j]] > A[o][o]) { order[j + 1] = order[j]; --j; }
+      order[j + 1] = o;
+    }
+  }
+  __syncwarp();
+  if (lane < n) {
+    theta[lane] = A[order[lane]][order[lane]];
+    for (int i = 0; i < n; ++i) alpha[i * ldg + lane] = V[i][order[lane]];
+  }
+}
+
+cudaError_t launch_subspace_eig(const double* G, int n, int ldg, double* theta, double* alpha, cudaStream_t s, int64_t* launches) {
+  if (n > 32) return cudaErrorInvalidValue;
+  subspace_eig_kernel<<<1, 32, 0, s>>>(G, n, ldg, theta, alpha);
+  B2D_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// diag(H)
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) diag_kernel(const BlockDesc* __restrict__ blocks, const DiagTask* __restrict__ tasks, const int* __restrict__ block_begin,
+                                                   double* __restrict__ e) {
+  const BlockDesc d = blocks[blockIdx.y];
+  const int t0 = block_begin[blockIdx.y], t1 = block_begin[blockIdx.y + 1];
+  const int64_t n = (int64_t)d.rows * d.cols;
+  for (int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(idx / d.cols), j = (int)(idx % d.cols);
+    double acc = 0.0;
+    for (int t = t0; t < t1; ++t) {
+      const DiagTask k = tasks[t];
+      double v = k.f;
+      if (k.a) v *= reinterpret_cast<const double*>(k.a)[(int64_t)i * k.sa];
+      if (k.b) v *= reinterpret_cast<const double*>(k.b)[(int64_t)j * k.sb];
+      acc += v;
+    }
+    e[d.dev_off + (int64_t)i * d.ld + j] = acc;
+  }
+}
+
+cudaError_t launch_diag(const BlockDesc* blocks, int nblocks, const DiagTask* tasks, const int* block_begin, double* e, cudaStream_t s, int64_t* launches) {
+  if (nblocks == 0) return cudaSuccess;
+  for (int b0 = 0; b0 < nblocks; b0 += 32768) {
+    int nb = min(32768, nblocks - b0);
+    diag_kernel<<<dim3(8, nb, 1), 256, 0, s>>>(blocks + b0, tasks, block_begin + b0, e);
+    B2D_LAUNCH_CHECK();
+  }
+  return cudaSuccess;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// density-matrix eigen-decomposition (replaces dsyev_ at rotationmat.C:268): one-sided Jacobi on rows
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int EIG_THREADS = 512;
+
+__global__ void __launch_bounds__(EIG_THREADS) sector_eig_kernel(const BlockDesc* __restrict__ sectors, double* __restrict__ g, double* __restrict__ vt,
+                                                                 double* __restrict__ evals, int* __restrict__ sweeps) {
+  const BlockDesc sd = sectors[blockIdx.x];
+  const int d = sd.rows, ld = sd.ld;
+  double* G = g + sd.dev_off;
+  double* V = vt + sd.dev_off;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  __shared__ int rotated;
+  // V = identity
+  for (int64_t e = threadIdx.x; e < (int64_t)d * ld; e += blockDim.x) V[e] = (e / ld == e % ld) ? 1.0 : 0.0;
+  __syncthreads();
+  const int D = (d + 1) & ~1;   // round-robin tournament over an even number of players
+  int sweep = 0;
+  for (; sweep < 60 && d > 1; ++sweep) {
+    if (threadIdx.x == 0) rotated = 0;
+    __syncthreads();
+    for (int round = 0; round < D - 1; ++round) {
+      for (int k = warp; k < D / 2; k += nwarps) {
+        int a = (round + k) % (D - 1);
+        int b = k == 0 ? D - 1 : (round - k + (D - 1)) % (D - 1);
+        if (a >= d || b >= d) continue;
+        if (a > b) { int tmp = a; a = b; b = tmp; }
+        double* ga = G + (int64_t)a * ld;
+        double* gb = G + (int64_t)b * ld;
+        double aa = 0.0, bb = 0.0, ab = 0.0;
+        for (int j = lane; j < d; j += 32) {
+          double x = ga[j], y = gb[j];
+          aa += x * x; bb += y * y; ab += x * y;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          aa += __shfl_xor_sync(0xffffffffu, aa, o);
+          bb += __shfl_xor_sync(0xffffffffu, bb, o);
+          ab += __shfl_xor_sync(0xffffffffu, ab, o);
+        }
+        if (fabs(ab) <= 1e-15 * sqrt(aa * bb) || aa < 1e-40 || bb < 1e-40) continue;
+        const double zeta = (bb - aa) / (2.0 * ab);
+        const double tt = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / sqrt(1.0 + tt * tt), s = c * tt;
+        double* va = V + (int64_t)a * ld;
+        double* vb = V + (int64_t)b * ld;
+        for (int j = lane; j < d; j += 32) {
+          double x = ga[j], y = gb[j];
+          ga[j] = c * x - s * y;
+          gb[j] = s * x + c * y;
+          x = va[j]; y = vb[j];
+          va[j] = c * x - s * y;
+          vb[j] = s * x + c * y;
+        }
+        if (lane == 0) rotated = 1;
+      }
+      __syncthreads();
+    }
+    const int any = rotated;
+    __syncthreads();
+    if (!any) break;
+  }
+  // eigenvalue of row i: Rayleigh quotient v_i . (A v_i) = v_i . g_i
+  for (int i = warp; i < d; i += nwarps) {
+    double acc = 0.0;
+    for (int j = lane; j < d; j += 32) acc += V[(int64_t)i * ld + j] * G[(int64_t)i * ld + j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) evals[sd.ref_off + i] = acc;
+  }
+  if (threadIdx.x == 0) sweeps[blockIdx.x] = sweep;
+}
+
+cudaError_t launch_sector_eig(const BlockDesc* sectors, int nsectors, double* g, double* vt, double* evals, int* sweeps, cudaStream_t s, int64_t* launches) {
+  if (nsectors == 0) return cudaSuccess;
+  sector_eig_kernel<<<nsectors, EIG_THREADS, 0, s>>>(sectors, g, vt, evals, sweeps);
+  B2D_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+__global__ void gather_rotation_kernel(const GatherDesc* __restrict__ desc, const int* __restrict__ src_rows, const double* __restrict__ vt, double* __restrict__ u) {
+  const GatherDesc g = desc[blockIdx.x];
+  const int64_t n = (int64_t)g.d * g.ncols;
+  for (int64_t e = threadIdx.x; e < n; e += blockDim.x) {
+    int c = (int)(e / g.d), j = (int)(e % g.d);   // j fastest: coalesced reads of the eigenvector row
+    u[g.u_off + (int64_t)j * g.ld_u + c] = vt[g.vt_off + (int64_t)src_rows[g.row_begin + c] * g.ld_vt + j];
+  }
+}
+cudaError_t launch_gather_rotation(const GatherDesc* desc, int nsectors, const int* src_rows, const double* vt, double* u, cudaStream_t s, int64_t* launches) {
+  if (nsectors == 0) return cudaSuccess;
+  gather_rotation_kernel<<<nsectors, 256, 0, s>>>(desc, src_rows, vt, u);
+  B2D_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// synthetic operators for the benchmark
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double counter_uniform(uint64_t seed, uint64_t idx) {   // splitmix64
+  uint64_t z = seed + 0x9E3779B97F4A7C15ull * (idx + 1);
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  return (double)(z >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+}
+
+__global__ void fill_random_kernel(double* __restrict__ dst, const BlockDesc* __restrict__ blocks, int nblocks, uint64_t seed, double amplitude) {
+  for (int b = blockIdx.y; b < nblocks; b += gridDim.y) {
+    const BlockDesc d = blocks[b];
+    const int64_t n = (int64_t)d.rows * d.cols;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+      int r = (int)(e / d.cols), c = (int)(e % d.cols);
+      dst[d.dev_off + (int64_t)r * d.ld + c] = 2.0 * amplitude * counter_uniform(seed, (uint64_t)(d.ref_off + e));
+    }
+  }
+}
+cudaError_t launch_fill_random(double* dst, const BlockDesc* blocks, int nblocks, uint64_t seed, double amplitude, cudaStream_t s, int64_t* launches) {
+  if (nblocks == 0) return cudaSuccess;
+  fill_random_kernel<<<pack_grid(nblocks), 256, 0, s>>>(dst, blocks, nblocks, seed, amplitude);
+  B2D_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+__global__ void symmetrise_kernel(double* __restrict__ base, const SymPair* __restrict__ pairs, int npairs) {
+  for (int p = blockIdx.y; p < npairs; p += gridDim.y) {
+    const SymPair sp = pairs[p];
+    const int64_t n = (int64_t)sp.rows * sp.cols;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) {
+      int r = (int)(e / sp.cols), c = (int)(e % sp.cols);
+      double* pa = base + sp.off_a + (int64_t)r * sp.ld_a + c;
+      double* pb = base + sp.off_b + (int64_t)c * sp.ld_b + r;
+      if (sp.off_a == sp.off_b) {
+        if (c >= r) { double v = 0.5 * (*pa + *pb); *pa = v; *pb = v; }   // diagonal block, f = 1
+      } else {
+        double v = *pa;
+        *pb = sp.f * v;
+      }
+    }
+  }
+}
+cudaError_t launch_symmetrise(double* base, const SymPair* pairs, int npairs, cudaStream_t s, int64_t* launches) {
+  if (npairs == 0) return cudaSuccess;
+  symmetrise_kernel<<<pack_grid(npairs), 256, 0, s>>>(base, pairs, npairs);
+  B2D_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// FP64 yardsticks
+// ---------------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) {
+  double acc[8][4];
+  double a[4], b[2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) acc[i][e] = 0.0;
+  a[0] = threadIdx.x * 1e-3; a[1] = a[0] + 1; a[2] = a[0] + 2; a[3] = a[0] + 3;
+  b[0] = 1e-6 * threadIdx.x; b[1] = b[0] + 1e-3;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dmma_16x8x8(acc[i], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) s += acc[i][e];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters) {
+  double acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = i;
+  const double a = 1.0000001, b = 1e-9 * threadIdx.x;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = fma(acc[i], a, b);
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += acc[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+cudaError_t measure_fp64(cudaStream_t s, double* dmma_tflops, double* dfma_tflops) {
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = sms * 4, threads = 256, iters = 20000;
+  double* out = nullptr;
+  cudaError_t e = cudaMalloc(&out, sizeof(double) * grid * threads);
+  if (e != cudaSuccess) return e;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  float ms = 0.f;
+  dmma_peak_kernel<<<grid, threads, 0, s>>>(out, 100);
+  cudaEventRecord(e0, s);
+  dmma_peak_kernel<<<grid, threads, 0, s>>>(out, iters);
+  cudaEventRecord(e1, s);
+  cudaEventSynchronize(e1);
+  cudaEventElapsedTime(&ms, e0, e1);
+  // per warp per iteration: 8 DMMA x (16*8*8) FMA x 2 flops
+  *dmma_tflops = (double)grid * (threads / 32) * iters * 8.0 * 16 * 8 * 8 * 2 / (ms * 1e-3) / 1e12;
+  dfma_peak_kernel<<<grid, threads, 0, s>>>(out, 100);
+  cudaEventRecord(e0, s);
+  dfma_peak_kernel<<<grid, threads, 0, s>>>(out, iters);
+  cudaEventRecord(e1, s);
+  cudaEventSynchronize(e1);
+  cudaEventElapsedTime(&ms, e0, e1);
+  *dfma_tflops = (double)grid * threads * iters * 16.0 * 2 / (ms * 1e-3) / 1e12;
+  e = cudaGetLastError();
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(out);
+  return e;
+}
+
+}  // namespace b2d

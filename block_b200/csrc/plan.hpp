@@ -1,0 +1,509 @@
+// Host-side planning of the sweep hot path: sector tables, packed device layouts, the term list of
+// SpinBlock::multiplyH and the grouped-contraction schedule the sm_100a kernels execute.  Pure integer/scalar work,
+// no CUDA: this is what the CPU tests exercise through a planning-only context.
+//
+// Reference behaviour restated here (file:line under the reference root):
+//   psi layout            Wavefunction::initialise wavefunction.C:18-56, FlattenInto :167-186
+//   operator allocation   SparseMatrix::allocate BaseOperator.C:123-145 (allowed mask is passed in by the caller)
+//   term list             SpinBlock::multiplyH spinblock.C:722-789, opxop::{cxcddcomp,cdxcdcomp,ddxcccomp} opxop.C:155-285
+//   per-GEMM factors      operatorfunctions::TensorMultiply operatorfunctions.C:485-537
+//   diag(H)               SpinBlock::diagonalH spinblock.C:855-899, operatorfunctions.C:653-762, opxop.C:295-365
+//   term ownership        processorindex para_array.h:33-42, trimap_2d para_array.h:360-383
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <map>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "angmom.hpp"
+#include "gemm_desc.h"
+
+namespace b2d {
+
+constexpr int LD_ALIGN = 2;    // leading dimensions are multiples of 2 doubles: every row starts 16-byte aligned
+constexpr int BLK_ALIGN = 16;  // sector blocks start on 128-byte boundaries
+
+inline int pad_ld(int n) { return (n + LD_ALIGN - 1) / LD_ALIGN * LD_ALIGN; }
+inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+enum { OP_HAM = 0, OP_CRE = 1, OP_CRE_CRE = 2, OP_DES_DESCOMP = 3, OP_CRE_DES = 4, OP_CRE_DESCOMP = 5, OP_CRE_CRE_DESCOMP = 6, OP_OVERLAP = 13 };
+
+struct OpRec {
+  int optype = 0, norb = 0, orbs[2] = {-1, -1}, comp = 0;
+  int dq[3] = {0, 0, 0};
+  bool fermion = false;
+  std::vector<uint8_t> allowed;   // nq x nq
+  std::vector<int64_t> off;       // nq x nq: offset (doubles) of block (i,j) from the operator's device base, -1 if absent
+  int64_t packed_size = 0;        // host (reference) layout
+  int64_t dev_size = 0;           // padded device layout
+  double* dev = nullptr;
+};
+
+struct Side {
+  int nq = 0;
+  std::vector<int> q;      // nq x 3
+  std::vector<int> dims;
+  bool loop = false;
+  std::vector<int> sites;
+  std::vector<OpRec> ops;
+  const int* quantum(int i) const { return &q[3 * i]; }
+  int find(int optype, const int* orbs, int norb, int comp) const {
+    for (size_t m = 0; m < ops.size(); ++m) {
+      const OpRec& o = ops[m];
+      if (o.optype != optype || o.comp != comp || o.norb != norb) continue;
+      bool same = true;
+      for (int k = 0; k < norb; ++k) same = same && o.orbs[k] == orbs[k];
+      if (same) return (int)m;
+    }
+    return -1;
+  }
+};
+
+// lay an operator's allowed blocks out in the padded device arena order ((i,j) row-major like the host packing)
+inline void layout_op(const Side& s, OpRec& op) {
+  op.off.assign((size_t)s.nq * s.nq, -1);
+  int64_t dev = 0, packed = 0;
+  for (int i = 0; i < s.nq; ++i)
+    for (int j = 0; j < s.nq; ++j)
+      if (op.allowed[(size_t)i * s.nq + j]) {
+        op.off[(size_t)i * s.nq + j] = dev;
+        dev += align_up((int64_t)s.dims[i] * pad_ld(s.dims[j]), BLK_ALIGN);
+        packed += (int64_t)s.dims[i] * s.dims[j];
+      }
+  op.dev_size = dev;
+  op.packed_size = packed;
+}
+
+// an operator or its Transposeview (BaseOperator.h:208-243) as TensorMultiply sees it
+struct View {
+  const Side* side;
+  const OpRec* op;
+  bool t;
+  bool allowed(int i, int j) const { return t ? op->allowed[(size_t)j * side->nq + i] : op->allowed[(size_t)i * side->nq + j]; }
+  int spin() const { return op->dq[1]; }
+  bool fermion() const { return op->fermion; }
+  // stored block that backs view element (i,j): (j,i) for a Transposeview
+  int64_t stored_off(int i, int j) const { return t ? op->off[(size_t)j * side->nq + i] : op->off[(size_t)i * side->nq + j]; }
+  int stored_ld(int i, int j) const { return pad_ld(t ? side->dims[i] : side->dims[j]); }
+  double scaling(AngMom& am, int i, int j) const {
+    return t ? am.transpose_scaling(op->dq[1], side->quantum(i)[1], side->quantum(j)[1]) : 1.0;
+  }
+};
+
+struct PsiLayout {
+  int nl = 0, nr = 0;
+  int dq[3] = {0, 0, 0};
+  std::vector<int> blk;            // nl x nr -> block index or -1
+  std::vector<int> bl, br, rows, cols, ld;
+  std::vector<int64_t> ref_off, dev_off;
+  int64_t W = 0, Wp = 0;
+  int nblocks() const { return (int)bl.size(); }
+  bool allowed(int l, int r) const { return blk[(size_t)l * nr + r] >= 0; }
+  void build(const Side& L, const Side& R, const int* target) {
+    nl = L.nq; nr = R.nq;
+    std::memcpy(dq, target, sizeof(dq));
+    blk.assign((size_t)nl * nr, -1);
+    bl.clear(); br.clear(); rows.clear(); cols.clear(); ld.clear(); ref_off.clear(); dev_off.clear();
+    W = Wp = 0;
+    for (int l = 0; l < nl; ++l)
+      for (int r = 0; r < nr; ++r)
+        if (qn_allow(target, L.quantum(l), R.quantum(r))) {
+          blk[(size_t)l * nr + r] = (int)bl.size();
+          bl.push_back(l); br.push_back(r);
+          rows.push_back(L.dims[l]); cols.push_back(R.dims[r]); ld.push_back(pad_ld(R.dims[r]));
+          ref_off.push_back(W); dev_off.push_back(Wp);
+          W += (int64_t)L.dims[l] * R.dims[r];
+          Wp += align_up((int64_t)L.dims[l] * pad_ld(R.dims[r]), BLK_ALIGN);
+        }
+  }
+};
+
+struct Term {
+  int lop, rop;     // operator ids on the left / right child
+  bool lt, rt;      // Transposeview flags
+  double scale;
+  int owner;        // rank that executes it
+};
+
+inline int tristore_2d(int i) { return i * (i + 1) / 2; }
+// para_array.h:360-383
+inline int trimap_2d(int i, int j, int length) {
+  if (i < j) std::swap(i, j);
+  int halflen = length / 2;
+  if (i >= halflen && j >= halflen) return tristore_2d(length - j - 1) + length - i - 1;
+  if (i < halflen && j < halflen) return tristore_2d(length - halflen - 1) + length - halflen + tristore_2d(i) + j;
+  int base = tristore_2d(length - halflen - 1) + length - halflen + tristore_2d(halflen);
+  return base + (i - halflen) * halflen + j;
+}
+
+// operator arrays of one type in storage order: (orbs) -> components, like Op_component::get_local_element
+struct OpArray {
+  std::vector<std::vector<int>> comps;   // per element: op ids by component index
+  std::vector<const int*> orbs;
+};
+inline OpArray op_array(const Side& s, int optype) {
+  OpArray a;
+  std::map<std::pair<int, int>, int> index;
+  for (size_t m = 0; m < s.ops.size(); ++m) {
+    const OpRec& o = s.ops[m];
+    if (o.optype != optype) continue;
+    std::pair<int, int> key(o.orbs[0], o.orbs[1]);
+    auto it = index.find(key);
+    if (it == index.end()) {
+      it = index.emplace(key, (int)a.comps.size()).first;
+      a.comps.emplace_back();
+      a.orbs.push_back(o.orbs);
+    }
+    std::vector<int>& c = a.comps[it->second];
+    if ((int)c.size() <= o.comp) c.resize(o.comp + 1, -1);
+    c[o.comp] = (int)m;
+  }
+  return a;
+}
+
+// The TensorMultiply calls of one multiplyH (energy sweep: implicit transposes, no DES/.. arrays), every rank's.
+inline std::vector<Term> enumerate_terms(const Side& L, const Side& R, double core_energy, bool hubbard, int norbs, int nranks, AngMom& am) {
+  std::vector<Term> terms;
+  const int hq[3] = {0, 0, 0};
+  auto neg = [](const int* q, int* out) { out[0] = -q[0]; out[1] = q[1]; out[2] = q[2]; };
+  auto pair = [&](bool other_is_left, int op_other, bool t_other, int op_loop, bool t_loop, double scale, int owner) {
+    Term t;
+    if (other_is_left) { t.lop = op_other; t.lt = t_other; t.rop = op_loop; t.rt = t_loop; }
+    else { t.lop = op_loop; t.lt = t_loop; t.rop = op_other; t.rt = t_other; }
+    t.scale = scale; t.owner = owner;
+    terms.push_back(t);
+  };
+  int none[2] = {-1, -1};
+  int ovl_l = L.find(OP_OVERLAP, none, 0, 0), ovl_r = R.find(OP_OVERLAP, none, 0, 0);
+  int ham_l = L.find(OP_HAM, none, 0, 0), ham_r = R.find(OP_HAM, none, 0, 0);
+  if (ovl_l < 0 || ovl_r < 0 || ham_l < 0 || ham_r < 0) throw std::runtime_error("plan: both children need HAM and OVERLAP operators");
+  if (std::fabs(core_energy) > 1e-20) terms.push_back(Term{ovl_l, ovl_r, false, false, core_energy, 0});   // spinblock.C:735-740 (rank 0)
+  terms.push_back(Term{ham_l, ovl_r, false, false, 1.0, 0});                                              // :742-744
+  terms.push_back(Term{ovl_l, ham_r, false, false, 1.0, 0});                                              // :745-747
+
+  // c x ccd_comp, both directions (:757-763 -> opxop.C:232-285)
+  for (int dir = 0; dir < 2; ++dir) {
+    const Side& other = dir == 0 ? L : R;
+    const Side& loopb = dir == 0 ? R : L;
+    bool other_is_left = dir == 0;
+    OpArray arr = op_array(loopb, OP_CRE);
+    for (size_t e = 0; e < arr.comps.size(); ++e)
+      for (size_t k = 0; k < arr.comps[e].size(); ++k) {
+        int i1 = arr.comps[e][k];
+        if (i1 < 0) continue;
+        const OpRec& op1 = loopb.ops[i1];
+        int i2 = other.find(OP_CRE_CRE_DESCOMP, op1.orbs, 1, (int)k);
+        if (i2 < 0) break;                                            // has_local_index false (opxop.C:240)
+        const OpRec& op2 = other.ops[i2];
+        int owner = nranks > 1 ? op1.orbs[0] % nranks : 0;            // processorindex(i)
+        int nq1[3], nq2[3];
+        neg(op1.dq, nq1); neg(op2.dq, nq2);
+        double par = !other_is_left ? am.commute_parity(nq1, op2.dq, hq) : 1.0;   // opxop.C:273-274
+        pair(other_is_left, i2, false, i1, true, par, owner);                       // :276
+        par = other_is_left ? am.commute_parity(op1.dq, nq2, hq) : 1.0;            // :278-279
+        pair(other_is_left, i2, true, i1, false, par, owner);                       // :282
+      }
+  }
+  if (!hubbard) {                                                     // spinblock.C:771
+    const Side& loopb = L.loop ? L : R;
+    const Side& other = L.loop ? R : L;
+    bool other_is_left = !L.loop;
+    OpArray arr = op_array(loopb, OP_CRE_DES);                        // cdxcdcomp opxop.C:155-185
+    for (size_t e = 0; e < arr.comps.size(); ++e)
+      for (size_t k = 0; k < arr.comps[e].size(); ++k) {
+        int i1 = arr.comps[e][k];
+        if (i1 < 0) continue;
+        const OpRec& op1 = loopb.ops[i1];
+        int i2 = other.find(OP_CRE_DESCOMP, op1.orbs, 2, (int)k);
+        if (i2 < 0) break;
+        int owner = nranks > 1 ? trimap_2d(op1.orbs[0], op1.orbs[1], norbs) % nranks : 0;
+        pair(other_is_left, i2, false, i1, false, 1.0, owner);
+        if (op1.orbs[0] != op1.orbs[1]) pair(other_is_left, i2, true, i1, true, 1.0, owner);
+      }
+    arr = op_array(loopb, OP_CRE_CRE);                                // ddxcccomp opxop.C:187-228
+    for (size_t e = 0; e < arr.comps.size(); ++e)
+      for (size_t k = 0; k < arr.comps[e].size(); ++k) {
+        int i1 = arr.comps[e][k];
+        if (i1 < 0) continue;
+        const OpRec& op1 = loopb.ops[i1];
+        int i2 = other.find(OP_DES_DESCOMP, op1.orbs, 2, (int)k);
+        if (i2 < 0) break;
+        const OpRec& op2 = other.ops[i2];
+        int owner = nranks > 1 ? trimap_2d(op1.orbs[0], op1.orbs[1], norbs) % nranks : 0;
+        double factor = op1.orbs[0] == op1.orbs[1] ? 1.0 : 2.0;
+        double par = other_is_left ? am.commute_parity(op1.dq, op2.dq, hq) : 1.0;
+        pair(other_is_left, i2, false, i1, false, factor * par, owner);
+        par *= AngMom::transpose_factor_dd(op1.dq[1]) * AngMom::transpose_factor_dd(op2.dq[1]);
+        pair(other_is_left, i2, true, i1, true, factor * par, owner);
+      }
+  }
+  return terms;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// grouped-contraction schedule
+// ---------------------------------------------------------------------------------------------------------------
+struct GemmBatch {
+  std::vector<GSeg> segs;
+  std::vector<GGroup> groups;
+  std::vector<GTile> tiles[B2D_NUM_TILE_CLASSES];
+  double flops = 0.0;
+  bool empty() const { return groups.empty(); }
+};
+
+inline int pick_tile_class(int m, int n, int forced) {
+  if (forced >= 0) return forced;
+  int lo = std::min(m, n);
+  if (lo > 48 && (int64_t)m * n >= 96 * 96) return 0;   // 128 x 128
+  if (lo > 20) return 1;                                 // 64 x 64
+  return 2;                                              // 32 x 32
+}
+
+// fills batch.tiles from batch.groups; tiles of a class are ordered by descending cost so the hardware's in-order
+// CTA dispatch approximates longest-processing-time scheduling over the 148 SMs
+inline void make_tiles(GemmBatch& b, int forced_class) {
+  for (int c = 0; c < B2D_NUM_TILE_CLASSES; ++c) b.tiles[c].clear();
+  for (size_t g = 0; g < b.groups.size(); ++g) {
+    GGroup& G = b.groups[g];
+    int64_t ktot = 0;
+    int kiters = 0;
+    for (int s = G.seg_begin; s < G.seg_end; ++s) { ktot += b.segs[s].k; kiters += (b.segs[s].k + 15) / 16; }
+    G.kiters = kiters;
+    int c = pick_tile_class(G.m, G.n, forced_class);
+    int bm = b2d_tile_m(c), bn = b2d_tile_n(c);
+    for (int m0 = 0; m0 < G.m; m0 += bm)
+      for (int n0 = 0; n0 < G.n; n0 += bn) {
+        GTile t;
+        t.group = (int)g; t.m0 = m0; t.n0 = n0;
+        t.cost = (int)std::min<int64_t>(ktot + 8 * (G.seg_end - G.seg_begin), 0x7fffffff);
+        b.tiles[c].push_back(t);
+      }
+  }
+  for (int c = 0; c < B2D_NUM_TILE_CLASSES; ++c)
+    std::stable_sort(b.tiles[c].begin(), b.tiles[c].end(), [](const GTile& x, const GTile& y) { return x.cost > y.cost; });
+}
+
+struct Chunk {
+  GemmBatch step1, step2;
+  int64_t work = 0;   // doubles of T workspace
+  int nterms = 0;
+};
+
+struct Schedule {
+  std::vector<Chunk> chunks;
+  double flops_alg = 0.0;    // the reference's dgemm flops
+  double flops_exec = 0.0;   // what the kernels execute (T blocks nobody consumes are skipped)
+  int64_t work_max = 0;
+  int64_t n_step1 = 0, n_step2 = 0, n_tiles = 0;
+};
+
+// Build the two-step schedule for a list of operator pairs:  dst[lQ,rQ] += F * (s A_L[lQ,lQ'] src[lQ',rQ']) A_R[rQ,rQ']^T
+inline Schedule build_schedule(const Side& L, const Side& R, const PsiLayout& P, const std::vector<Term>& terms, int opq_spin,
+                               int64_t work_budget, int forced_class, AngMom& am) {
+  Schedule S;
+  const int S_psi = P.dq[1];
+  Chunk cur;
+  std::vector<int> group_of;     // psi block -> group index inside cur.step2, -1
+  std::vector<std::vector<GSeg>> pending;   // per group: segments (merged into contiguous ranges at chunk close)
+  auto open_chunk = [&]() {
+    cur = Chunk();
+    group_of.assign(P.nblocks(), -1);
+    pending.clear();
+  };
+  auto close_chunk = [&]() {
+    if (cur.nterms == 0) return;
+    for (size_t g = 0; g < cur.step2.groups.size(); ++g) {
+      GGroup& G = cur.step2.groups[g];
+      G.seg_begin = (int)cur.step2.segs.size();
+      cur.step2.segs.insert(cur.step2.segs.end(), pending[g].begin(), pending[g].end());
+      G.seg_end = (int)cur.step2.segs.size();
+    }
+    make_tiles(cur.step1, forced_class);
+    make_tiles(cur.step2, forced_class);
+    S.work_max = std::max(S.work_max, cur.work);
+    S.n_step1 += (int64_t)cur.step1.groups.size();
+    S.n_step2 += (int64_t)cur.step2.segs.size();
+    for (int c = 0; c < B2D_NUM_TILE_CLASSES; ++c) S.n_tiles += (int64_t)(cur.step1.tiles[c].size() + cur.step2.tiles[c].size());
+    S.chunks.push_back(std::move(cur));
+  };
+  open_chunk();
+
+  std::vector<std::vector<int>> psi_row(L.nq);   // lQ' -> allowed rQ'
+  for (int l = 0; l < L.nq; ++l)
+    for (int r = 0; r < R.nq; ++r)
+      if (P.allowed(l, r)) psi_row[l].push_back(r);
+
+  for (const Term& t : terms) {
+    View lop{&L, &L.ops[t.lop], t.lt}, rop{&R, &R.ops[t.rop], t.rt};
+    // size this term's T blocks first so a chunk never splits a term
+    std::vector<std::vector<int>> rcol(R.nq);   // rQ' -> rQ with rop.allowed(rQ, rQ')
+    for (int rq = 0; rq < R.nq; ++rq)
+      for (int rqp = 0; rqp < R.nq; ++rqp)
+        if (rop.allowed(rq, rqp)) rcol[rqp].push_back(rq);
+    struct TBlock { int lQ, lQp, rQp; };
+    std::vector<TBlock> tb;
+    int64_t need = 0;
+    for (int lQ = 0; lQ < L.nq; ++lQ)
+      for (int lQp = 0; lQp < L.nq; ++lQp) {
+        if (!lop.allowed(lQ, lQp)) continue;
+        for (int rQp : psi_row[lQp]) {
+          double f1 = 2.0 * L.dims[lQ] * L.dims[lQp] * R.dims[rQp];
+          S.flops_alg += f1;
+          bool used = false;
+          for (int rQ : rcol[rQp])
+            if (P.allowed(lQ, rQ)) { used = true; S.flops_alg += 2.0 * L.dims[lQ] * R.dims[rQp] * R.dims[rQ]; }
+          if (!used) continue;
+          tb.push_back(TBlock{lQ, lQp, rQp});
+          need += align_up((int64_t)L.dims[lQ] * pad_ld(R.dims[rQp]), BLK_ALIGN);
+        }
+      }
+    if (cur.nterms > 0 && cur.work + need > work_budget) { close_chunk(); open_chunk(); }
+    cur.nterms++;
+    for (const TBlock& b : tb) {
+      const int dl = L.dims[b.lQ], dlp = L.dims[b.lQp], drp = R.dims[b.rQp];
+      const int ldt = pad_ld(drp);
+      const int64_t toff = cur.work;
+      cur.work += align_up((int64_t)dl * ldt, BLK_ALIGN);
+      // step 1:  T = s A_L^(c)[lQ,lQ'] src[lQ',rQ']                                  (operatorfunctions.C:512-516)
+      GSeg s1;
+      std::memset(&s1, 0, sizeof(s1));
+      s1.a = (int64_t)(intptr_t)(lop.op->dev) + 8 * lop.stored_off(b.lQ, b.lQp);   // absolute byte address
+      s1.a_base = B2D_BASE_ABS;
+      s1.a_trans = lop.t ? 1 : 0;                // stored block is (lQ', lQ): k x m
+      s1.lda = lop.stored_ld(b.lQ, b.lQp);
+      int pb = P.blk[(size_t)b.lQp * P.nr + b.rQp];
+      s1.b = P.dev_off[pb]; s1.b_base = B2D_BASE_SRC; s1.b_kmajor = 0; s1.ldb = P.ld[pb];
+      s1.k = dlp;
+      s1.alpha = lop.scaling(am, b.lQ, b.lQp);
+      GGroup g1;
+      std::memset(&g1, 0, sizeof(g1));
+      g1.c = toff; g1.c_base = B2D_BASE_WORK; g1.ldc = ldt; g1.m = dl; g1.n = drp; g1.accumulate = 0;
+      g1.seg_begin = (int)cur.step1.segs.size(); g1.seg_end = g1.seg_begin + 1;
+      cur.step1.segs.push_back(s1);
+      cur.step1.groups.push_back(g1);
+      cur.step1.flops += 2.0 * dl * dlp * drp;
+      // step 2:  dst[lQ,rQ] += F T (A_R^(c)[rQ,rQ'])^T                                 (operatorfunctions.C:517-531)
+      for (int rQ : rcol[b.rQp]) {
+        if (!P.allowed(b.lQ, rQ)) continue;
+        const int dr = R.dims[rQ];
+        double F = t.scale * am.ninej(L.quantum(b.lQp)[1], R.quantum(b.rQp)[1], S_psi, lop.spin(), rop.spin(), opq_spin,
+                                      L.quantum(b.lQ)[1], R.quantum(rQ)[1], S_psi);            // :522-524
+        if (rop.fermion() && (L.quantum(b.lQp)[0] & 1)) F = -F;                                 // :528
+        F *= rop.scaling(am, rQ, b.rQp);                                                        // :529
+        int db = P.blk[(size_t)b.lQ * P.nr + rQ];
+        int g = group_of[db];
+        if (g < 0) {
+          g = group_of[db] = (int)cur.step2.groups.size();
+          GGroup G;
+          std::memset(&G, 0, sizeof(G));
+          G.c = P.dev_off[db]; G.c_base = B2D_BASE_DST; G.ldc = P.ld[db]; G.m = dl; G.n = dr; G.accumulate = 1;
+          cur.step2.groups.push_back(G);
+          pending.emplace_back();
+        }
+        cur.step2.flops += 2.0 * dl * drp * dr;
+        if (F == 0.0) continue;                    // a vanishing recoupling coefficient contributes nothing
+        GSeg s2;
+        std::memset(&s2, 0, sizeof(s2));
+        s2.a = toff; s2.a_base = B2D_BASE_WORK; s2.a_trans = 0; s2.lda = ldt;
+        s2.b = (int64_t)(intptr_t)(rop.op->dev) + 8 * rop.stored_off(rQ, b.rQp);
+        s2.b_base = B2D_BASE_ABS;
+        s2.b_kmajor = rop.t ? 0 : 1;               // plain: stored (rQ,rQ') is n x k; view: stored (rQ',rQ) is k x n
+        s2.ldb = rop.stored_ld(rQ, b.rQp);
+        s2.k = drp;
+        s2.alpha = F;
+        pending[g].push_back(s2);
+      }
+    }
+  }
+  close_chunk();
+  for (const Chunk& c : S.chunks) S.flops_exec += c.step1.flops + c.step2.flops;
+  return S;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// diag(H)
+// ---------------------------------------------------------------------------------------------------------------
+inline void build_diag_tasks(const Side& L, const Side& R, const PsiLayout& P, const std::vector<Term>& all_terms, double core_energy,
+                             bool hubbard, AngMom& am, std::vector<DiagTask>& tasks, std::vector<int>& block_begin) {
+  // per psi block: list of (f, diagA, diagB).  The term list of diagonalH mirrors multiplyH's with the *_d functors
+  // (opxop.C:295-365): same operator pairs, scale 1 for c x ccd, `factor` (no parity) for cc x dd; H and e_core by trace.
+  (void)hubbard;
+  const int S_psi = P.dq[1];
+  std::vector<std::vector<DiagTask>> per(P.nblocks());
+  auto add = [&](const Term& t, double scale, bool left_only, bool right_only) {
+    View a{&L, &L.ops[t.lop], t.lt}, b{&R, &R.ops[t.rop], t.rt};
+    for (int p = 0; p < P.nblocks(); ++p) {
+      int l = P.bl[p], r = P.br[p];
+      if (!left_only && !right_only && !(a.allowed(l, l) && b.allowed(r, r))) continue;
+      if (left_only && !a.allowed(l, l)) continue;
+      if (right_only && !b.allowed(r, r)) continue;
+      int sa = right_only ? 0 : a.spin(), sb = left_only ? 0 : b.spin();
+      double f = scale * am.ninej(L.quantum(l)[1], R.quantum(r)[1], S_psi, sa, sb, 0, L.quantum(l)[1], R.quantum(r)[1], S_psi);
+      if (!left_only && b.fermion() && (L.quantum(l)[0] & 1)) f = -f;
+      DiagTask d;
+      std::memset(&d, 0, sizeof(d));
+      d.f = f;
+      if (!right_only) { d.a = (int64_t)(intptr_t)a.op->dev + 8 * a.stored_off(l, l); d.sa = a.stored_ld(l, l) + 1; }
+      if (!left_only) { d.b = (int64_t)(intptr_t)b.op->dev + 8 * b.stored_off(r, r); d.sb = b.stored_ld(r, r) + 1; }
+      per[p].push_back(d);
+    }
+  };
+  // all_terms is enumerate_terms() output: [e_core], H_L x 1, 1 x H_R, then the operator pairs
+  size_t i = 0;
+  if (std::fabs(core_energy) > 1e-20) ++i;               // handled as a constant below
+  add(all_terms[i], 1.0, true, false); ++i;              // TensorTrace(H_L)   spinblock.C:864
+  add(all_terms[i], 1.0, false, true); ++i;              // TensorTrace(H_R)   :867
+  for (; i < all_terms.size(); ++i) {
+    const Term& t = all_terms[i];
+    const OpRec& lo = L.ops[t.lop];
+    const OpRec& ro = R.ops[t.rop];
+    double scale = 1.0;
+    int ty = lo.optype == OP_CRE_CRE || ro.optype == OP_CRE_CRE ? OP_CRE_CRE : 0;
+    if (ty == OP_CRE_CRE) {
+      const OpRec& cc = lo.optype == OP_CRE_CRE ? lo : ro;
+      scale = cc.orbs[0] == cc.orbs[1] ? 1.0 : 2.0;      // opxop.C:314-339 (no commute parity in the diagonal form)
+    }
+    add(t, scale, false, false);
+  }
+  tasks.clear();
+  block_begin.assign(P.nblocks() + 1, 0);
+  for (int p = 0; p < P.nblocks(); ++p) {
+    block_begin[p] = (int)tasks.size();
+    if (core_energy != 0.0) {
+      DiagTask d;
+      std::memset(&d, 0, sizeof(d));
+      d.f = core_energy;
+      tasks.push_back(d);
+    }
+    tasks.insert(tasks.end(), per[p].begin(), per[p].end());
+  }
+  block_begin[P.nblocks()] = (int)tasks.size();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// truncation: sort_weights rotationmat.C:313-346 + assign_matrix_by_dm :149-256 (keptqstates = 0)
+// ---------------------------------------------------------------------------------------------------------------
+inline double select_states(const std::vector<std::vector<double>>& evals, int keep, std::vector<std::vector<int>>& kept) {
+  struct E { double w; int64_t ord; int q, s; };
+  std::vector<E> all;
+  for (size_t q = 0; q < evals.size(); ++q)
+    for (size_t s = 0; s < evals[q].size(); ++s) all.push_back(E{evals[q][s], (int64_t)all.size(), (int)q, (int)s});
+  // multimap reverse iteration: descending key, equal keys in reverse insertion order
+  std::sort(all.begin(), all.end(), [](const E& a, const E& b) { return a.w != b.w ? a.w > b.w : a.ord > b.ord; });
+  size_t total = std::min<size_t>(all.size(), (size_t)std::max(keep, 0));
+  kept.assign(evals.size(), std::vector<int>());
+  double norm_kept = 0.0, norm = 0.0;
+  for (size_t i = 0; i < total; ++i)
+    if (all[i].w > 1e-13) { kept[all[i].q].push_back(all[i].s); norm_kept += all[i].w; }
+  for (size_t q = 0; q < evals.size(); ++q) {
+    double s = 0.0;
+    for (double w : evals[q]) s += w;
+    norm += s;
+  }
+  return norm - norm_kept;
+}
+
+}  // namespace b2d

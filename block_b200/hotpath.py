@@ -1,0 +1,354 @@
+"""Host-side mirror of the reference's entry points for the sweep hot path, on top of the C ABI.
+
+Names follow sanshar/Block (file:line under the reference root):
+    SpinBlock.multiplyH            spinblock.h:235   spinblock.C:722
+    SpinBlock.diagonalH            spinblock.h:240   spinblock.C:855
+    SpinBlock.RenormaliseFrom      spinblock.h:247   renormalise.C:39
+    SpinBlock.transform_operators  spinblock.h:253   save_load_block.C:267
+    block_davidson                 linear.h:28       linear.C:179
+    TensorMultiply                 operatorfunctions.h:46   operatorfunctions.C:485
+Wavefunctions cross this boundary as flat float64 arrays in Wavefunction::FlattenInto order (wavefunction.C:167);
+operators as their allowed sector blocks, row-major, (i outer, j inner).
+
+Python is used here only because the tests and bench.py are Python; the C++ mirror with the reference's exact
+signatures is block_b200/host/ (see INTEGRATION.md).  All arithmetic happens in libblockb200.so on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import _lib
+
+HUBBARD = 1  # hamTypes, input.h
+
+
+class B2DError(RuntimeError):
+    pass
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+@dataclass
+class OperatorSpec:
+    """One SparseMatrix of an operator array (BaseOperator.h:75-243)."""
+    optype: int
+    orbs: tuple
+    comp: int
+    dq: tuple
+    fermion: bool
+    allowed: np.ndarray            # (nq, nq) bool / uint8
+    data: np.ndarray | None        # packed blocks or None (device-allocated zeros, e.g. for synthetic fills)
+
+
+@dataclass
+class BlockSpec:
+    """StateInfo + operators of one child of the big block."""
+    q: np.ndarray                  # (nq, 3) int: N, 2S, irrep
+    dims: np.ndarray
+    sites: tuple = ()
+    loop: bool = False
+    ops: list = field(default_factory=list)
+
+
+class SpinBlock:
+    """The `big` block of one block iteration (left child x right child) resident on one GPU."""
+
+    def __init__(self, left: BlockSpec, right: BlockSpec, psi_dq, core_energy=0.0, hubbard=False, norbs=None,
+                 device=0, rank=0, nranks=1, options=None):
+        self.lib = _lib.load()
+        self._ctx = C.c_void_p()
+        rc = self.lib.b2d_create(int(device), C.byref(self._ctx))
+        if rc:
+            raise B2DError("b2d_create: " + self.lib.b2d_last_error(None).decode())
+        self.device = device
+        for k, v in (options or {}).items():
+            self._ck(self.lib.b2d_set_option(self._ctx, k.encode(), float(v)))
+        self.left, self.right = left, right
+        self.op_ids = [[], []]
+        for side, blk in enumerate((left, right)):
+            q = np.ascontiguousarray(blk.q, dtype=np.int32).reshape(-1, 3)
+            dims = np.ascontiguousarray(blk.dims, dtype=np.int32)
+            sites = np.ascontiguousarray(blk.sites, dtype=np.int32)
+            self._ck(self.lib.b2d_set_block(self._ctx, side, len(dims), _p(q, _lib.c_i32p), _p(dims, _lib.c_i32p), int(blk.loop),
+                                            len(sites), _p(sites, _lib.c_i32p)))
+            for op in blk.ops:
+                self.op_ids[side].append(self._add_op(side, op))
+        if norbs is None:
+            norbs = len(left.sites) + len(right.sites)
+        dq = np.asarray(psi_dq, dtype=np.int32)
+        self._ck(self.lib.b2d_plan(self._ctx, _p(dq, _lib.c_i32p), float(core_energy), int(bool(hubbard)), int(norbs), int(rank), int(nranks)))
+        self.size = int(self.lib.b2d_psi_size(self._ctx))
+        self.rank, self.nranks = rank, nranks
+        self._nslots = 0
+
+    # -- plumbing ---------------------------------------------------------------------------------------------
+    def _ck(self, rc):
+        if rc:
+            raise B2DError("[%d] %s" % (rc, self.lib.b2d_last_error(self._ctx).decode()))
+
+    def _add_op(self, side, op: OperatorSpec):
+        orbs = np.asarray(list(op.orbs) + [-1, -1], dtype=np.int32)
+        dq = np.asarray(op.dq, dtype=np.int32)
+        allowed = np.ascontiguousarray(op.allowed, dtype=np.uint8)
+        data = None if op.data is None else np.ascontiguousarray(op.data, dtype=np.float64)
+        oid = C.c_int(-1)
+        self._ck(self.lib.b2d_add_op(self._ctx, side, int(op.optype), len(op.orbs), _p(orbs, _lib.c_i32p), int(op.comp), _p(dq, _lib.c_i32p),
+                                     int(bool(op.fermion)), _p(allowed, _lib.c_u8p), None if data is None else _p(data, _lib.c_f64p), C.byref(oid)))
+        return oid.value
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self.lib.b2d_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reserve(self, n):
+        if n > self._nslots:
+            self._ck(self.lib.b2d_vec_reserve(self._ctx, n))
+            self._nslots = n
+
+    def upload(self, slot, flat):
+        self.reserve(slot + 1)
+        flat = np.ascontiguousarray(flat, dtype=np.float64)
+        assert flat.size == self.size
+        self._ck(self.lib.b2d_vec_upload(self._ctx, slot, _p(flat, _lib.c_f64p)))
+
+    def download(self, slot):
+        out = np.empty(self.size)
+        self._ck(self.lib.b2d_vec_download(self._ctx, slot, _p(out, _lib.c_f64p)))
+        return out
+
+    def set_option(self, key, value):
+        self._ck(self.lib.b2d_set_option(self._ctx, key.encode(), float(value)))
+
+    def attach_communicator(self, unique_id: bytes, rank, nranks):
+        import os
+        path = _lib.nccl_library_path()
+        if path and "B2D_NCCL_LIB" not in os.environ:
+            os.environ["B2D_NCCL_LIB"] = path
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        self._ck(self.lib.b2d_comm_init(self._ctx, buf, rank, nranks))
+
+    @staticmethod
+    def nccl_unique_id() -> bytes:
+        import os
+        lib = _lib.load()
+        path = _lib.nccl_library_path()
+        if path and "B2D_NCCL_LIB" not in os.environ:
+            os.environ["B2D_NCCL_LIB"] = path
+        buf = (C.c_uint8 * 128)()
+        if lib.b2d_nccl_unique_id(buf):
+            raise B2DError(lib.b2d_last_error(None).decode())
+        return bytes(buf)
+
+    # -- integer side: layout and term list -------------------------------------------------------------------
+    def psi_blocks(self):
+        n = self.lib.b2d_psi_num_blocks(self._ctx)
+        l, r, o = np.empty(n, np.int32), np.empty(n, np.int32), np.empty(n, np.int64)
+        self._ck(self.lib.b2d_psi_blocks(self._ctx, _p(l, _lib.c_i32p), _p(r, _lib.c_i32p), _p(o, _lib.c_i64p)))
+        return l, r, o
+
+    def terms(self, all_ranks=False):
+        n = self.lib.b2d_num_terms(self._ctx, int(all_ranks))
+        lo, ro, fl, ow = (np.empty(n, np.int32) for _ in range(4))
+        sc = np.empty(n)
+        self._ck(self.lib.b2d_terms(self._ctx, int(all_ranks), _p(lo, _lib.c_i32p), _p(ro, _lib.c_i32p), _p(fl, _lib.c_i32p), _p(sc, _lib.c_f64p),
+                                    _p(ow, _lib.c_i32p)))
+        return lo, ro, fl, sc, ow
+
+    def sigma_flops(self, all_ranks=True):
+        return float(self.lib.b2d_sigma_flops(self._ctx, int(all_ranks)))
+
+    def plan_stats(self):
+        out = np.zeros(8)
+        self._ck(self.lib.b2d_plan_stats(self._ctx, _p(out, _lib.c_f64p), 8))
+        keys = ["chunks", "step1_contractions", "step2_segments", "tiles", "workspace_doubles", "arena_doubles", "launches_per_sigma", "flops_executed"]
+        return dict(zip(keys, out.tolist()))
+
+    # -- the reference's entry points ---------------------------------------------------------------------------
+    def multiplyH(self, c, v=None):
+        """SpinBlock::multiplyH(Wavefunction& c, Wavefunction* v, int): v += H c on host buffers (returns v)."""
+        c = np.ascontiguousarray(c, dtype=np.float64)
+        acc = v is not None
+        if v is None:
+            v = np.zeros(self.size)
+        assert c.size == self.size and v.size == self.size and v.flags.c_contiguous
+        self._ck(self.lib.b2d_multiplyH_host(self._ctx, _p(c, _lib.c_f64p), _p(v, _lib.c_f64p), int(acc)))
+        return v
+
+    def sigma(self, src_slot, dst_slot, accumulate=False):
+        """multiplyH on device-resident slots (what block_davidson uses internally)."""
+        self._ck(self.lib.b2d_sigma(self._ctx, src_slot, dst_slot, int(accumulate)))
+
+    def TensorMultiply(self, left_op, right_op, c, v, left_transposed=False, right_transposed=False, opq_spin=0, scale=1.0):
+        """operatorfunctions::TensorMultiply(ablock, a, b, cblock, c, v, opQ, scale): v += scale (a x b) c."""
+        self.upload(0, c)
+        self.upload(1, v)
+        flags = (1 if left_transposed else 0) | (2 if right_transposed else 0)
+        self._ck(self.lib.b2d_tensor_multiply(self._ctx, left_op, right_op, flags, int(opq_spin), float(scale), 0, 1))
+        return self.download(1)
+
+    def diagonalH(self, slot=None):
+        """SpinBlock::diagonalH(DiagonalMatrix&): diag(H) in flat psi order."""
+        s = 0 if slot is None else slot
+        self.reserve(s + 1)
+        self._ck(self.lib.b2d_diagonal(self._ctx, s))
+        return self.download(s)
+
+    def block_davidson(self, guesses, diag, normtol, deflation_min=2, deflation_max=20):
+        """Linear::block_davidson(b, h_diag, normtol, warmUp, h_multiply, useprecond, -1, {}): returns
+        (eigenvalues, solutions, number of H applications)."""
+        n = len(guesses)
+        self.reserve(n + 1)
+        for i, g in enumerate(guesses):
+            self.upload(i, g)
+        self.upload(n, diag)
+        ev = np.zeros(n)
+        nm = C.c_int(0)
+        res = C.c_double(0.0)
+        self._ck(self.lib.b2d_davidson(self._ctx, n, 0, n, float(normtol), int(deflation_min), int(deflation_max), _p(ev, _lib.c_f64p),
+                                       C.byref(nm), C.byref(res)))
+        return ev, [self.download(i) for i in range(n)], nm.value
+
+    def make_density(self, waves, weights):
+        """DensityMatrix::makedensitymatrix (noise 0): returns the per-sector blocks."""
+        n = len(waves)
+        self.reserve(n)
+        for i, w in enumerate(waves):
+            self.upload(i, w)
+        return self._density_from_slots(n, weights)
+
+    def _density_from_slots(self, n, weights):
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        self._ck(self.lib.b2d_make_density(self._ctx, n, 0, _p(w, _lib.c_f64p)))
+        return self.density()
+
+    def density(self):
+        flat = np.empty(int(self.lib.b2d_density_size(self._ctx)))
+        self._ck(self.lib.b2d_density_download(self._ctx, _p(flat, _lib.c_f64p)))
+        out, off = [], 0
+        for d in self.left.dims:
+            d = int(d)
+            out.append(flat[off:off + d * d].reshape(d, d)); off += d * d
+        return out
+
+    def diagonalise_dm(self):
+        """diagonalise_dm (rotationmat.C:258): per-sector eigenvalues (ascending, < 1e-14 -> 0)."""
+        ev = np.empty(int(np.sum(self.left.dims)))
+        self._ck(self.lib.b2d_diagonalise_dm(self._ctx, _p(ev, _lib.c_f64p)))
+        out, off = [], 0
+        for d in self.left.dims:
+            out.append(ev[off:off + int(d)]); off += int(d)
+        return out
+
+    def select_states(self, keep_states):
+        """sort_weights + assign_matrix_by_dm: returns (kept counts per sector, discarded weight, rotation matrices)."""
+        kept = np.zeros(len(self.left.dims), np.int32)
+        err = C.c_double(0.0)
+        self._ck(self.lib.b2d_select_states(self._ctx, int(keep_states), _p(kept, _lib.c_i32p), C.byref(err)))
+        return kept, err.value, self.rotation_matrices(kept)
+
+    def rotation_matrices(self, kept):
+        n = int(self.lib.b2d_rotation_size(self._ctx))
+        flat = np.empty(max(n, 1))
+        self._ck(self.lib.b2d_rotation_download(self._ctx, _p(flat, _lib.c_f64p)))
+        out, off = [], 0
+        for d, k in zip(self.left.dims, kept):
+            d, k = int(d), int(k)
+            out.append(flat[off:off + d * k].reshape(d, k).copy()); off += d * k
+        return out
+
+    def set_rotation_matrices(self, rot):
+        kept = np.asarray([r.shape[1] for r in rot], dtype=np.int32)
+        flat = np.concatenate([np.ascontiguousarray(r, dtype=np.float64).ravel() for r in rot] + [np.zeros(1)])
+        self._ck(self.lib.b2d_rotation_upload(self._ctx, _p(kept, _lib.c_i32p), _p(flat, _lib.c_f64p)))
+
+    def RenormaliseFrom(self, guesses, weights, normtol, keep_states, deflation_min=2, deflation_max=20):
+        """SpinBlock::RenormaliseFrom (two-dot, noise 0): returns dict(energies, kept, error, n_multiply, rotation)."""
+        n = len(guesses)
+        self.reserve(n + 1)
+        for i, g in enumerate(guesses):
+            self.upload(i, g)
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        en = np.zeros(n)
+        kept = np.zeros(len(self.left.dims), np.int32)
+        err = C.c_double(0.0)
+        nm = C.c_int(0)
+        self._ck(self.lib.b2d_renormalise_from(self._ctx, n, 0, _p(w, _lib.c_f64p), float(normtol), int(keep_states), int(deflation_min),
+                                               int(deflation_max), _p(en, _lib.c_f64p), _p(kept, _lib.c_i32p), C.byref(err), C.byref(nm)))
+        return dict(energies=en, kept=kept, error=err.value, n_multiply=nm.value, rotation=self.rotation_matrices(kept),
+                    solutions=[self.download(i) for i in range(n)])
+
+    def transform_operators(self):
+        """SpinBlock::transform_operators(rotateMatrix) on the LEFT child: returns (old sector index per new sector,
+        new dims, [(allowed, packed data)] per left operator in registration order)."""
+        self._ck(self.lib.b2d_transform_operators(self._ctx))
+        nq = self.lib.b2d_rotated_num_sectors(self._ctx)
+        old, dims = np.zeros(nq, np.int32), np.zeros(nq, np.int32)
+        self._ck(self.lib.b2d_rotated_sectors(self._ctx, _p(old, _lib.c_i32p), _p(dims, _lib.c_i32p)))
+        ops = []
+        for oid in self.op_ids[0]:
+            n = int(self.lib.b2d_rotated_op_size(self._ctx, oid))
+            allowed = np.zeros((nq, nq), np.uint8)
+            data = np.empty(max(n, 1))
+            self._ck(self.lib.b2d_rotated_op_download(self._ctx, oid, _p(allowed, _lib.c_u8p), _p(data, _lib.c_f64p)))
+            ops.append((allowed.astype(bool), data[:n]))
+        return old, dims, ops
+
+    # -- measurement ---------------------------------------------------------------------------------------------
+    def last_timing_ms(self):
+        out = np.zeros(4)
+        self._ck(self.lib.b2d_last_timing(self._ctx, _p(out, _lib.c_f64p), 4))
+        return out
+
+    def kernel_launches(self):
+        return int(self.lib.b2d_kernel_launches(self._ctx))
+
+    def sync(self):
+        self._ck(self.lib.b2d_sync(self._ctx))
+
+    def measure_fp64_peak(self):
+        a, b = C.c_double(0), C.c_double(0)
+        self._ck(self.lib.b2d_measure_fp64_peak(self._ctx, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def fill_op_random(self, side, op_id, seed, amplitude=1.0, symmetric=False):
+        self._ck(self.lib.b2d_fill_op_random(self._ctx, side, op_id, int(seed), float(amplitude), int(symmetric)))
+
+    def download_op(self, side, op_id):
+        n = int(self.lib.b2d_op_size(self._ctx, side, op_id))
+        out = np.empty(max(n, 1))
+        self._ck(self.lib.b2d_download_op(self._ctx, side, op_id, _p(out, _lib.c_f64p)))
+        return out[:n]
+
+
+def block_spec_from_record(rec, prefix) -> BlockSpec:
+    """Build a BlockSpec from a dump record of the reference (oracle/ref_dump.cpp format; tests/golden/*.npz)."""
+    q = np.asarray(rec[prefix + "q"], dtype=np.int32).reshape(-1, 3)
+    dims = np.asarray(rec[prefix + "dims"], dtype=np.int32)
+    blk = BlockSpec(q=q, dims=dims, sites=tuple(int(s) for s in rec[prefix + "sites"]), loop=bool(rec[prefix + "flags"][0]))
+    for m in range(int(rec[prefix + "nops"][0])):
+        meta = rec["%sop%d.meta" % (prefix, m)]
+        norb = int(meta[2])
+        blk.ops.append(OperatorSpec(optype=int(meta[0]), orbs=tuple(int(x) for x in meta[3:3 + norb]), comp=int(meta[5]),
+                                    dq=(int(meta[6]), int(meta[7]), int(meta[8])), fermion=bool(meta[9]),
+                                    allowed=np.asarray(rec["%sop%d.allowed" % (prefix, m)], dtype=np.uint8),
+                                    data=np.asarray(rec["%sop%d.data" % (prefix, m)], dtype=np.float64)))
+    return blk
+
+
+def spinblock_from_record(rec, device=0, rank=0, nranks=1, options=None) -> SpinBlock:
+    L, R = block_spec_from_record(rec, "L."), block_spec_from_record(rec, "R.")
+    norbs = len(rec["spin_orbs_symmetry"]) // 2 if "spin_orbs_symmetry" in rec else None
+    return SpinBlock(L, R, tuple(int(x) for x in rec["psi_dq"]), core_energy=float(rec["meta_f"][3]), hubbard=int(rec["meta"][7]) == HUBBARD,
+                     norbs=norbs, device=device, rank=rank, nranks=nranks, options=options)

@@ -1,0 +1,219 @@
+/* block_b200.h - C ABI of the B200-native DMRG sweep hot path (sigma = H.psi, Davidson, renormalisation).
+ *
+ * This is the drop-in boundary underneath the C++ entry points the CPU reference (sanshar/Block 1.1.1) exposes
+ * to its sweep driver.  The reference has no FFI for this path: the seam is four C++ member
+ * functions, so every entry point below cites the reference interface it replaces (file:line under the reference
+ * root) and the C++ mirror in block_b200/host/ re-exposes them under the reference's own names on top of this ABI.
+ *
+ * Conventions
+ *   - plain C, POD arguments only; every function returns 0 on success, non-zero on failure with the message
+ *     available from b2d_last_error().  There is NO CPU fallback: a compute call on a context without a CUDA
+ *     device fails with B2D_ERR_NO_DEVICE.
+ *   - "side" is 0 for the left child of the big block, 1 for the right child (SpinBlock::get_leftBlock /
+ *     get_rightBlock, spinblock.h:24).
+ *   - sectors are (N, 2S, irrep) triples as in StateInfo::quanta (StateInfo.h:113); the point group is abelian
+ *     (irrep product = XOR), which covers every BASELINE config.
+ *   - host wavefunction buffers are FLAT in the reference's Wavefunction::FlattenInto order (wavefunction.C:167-186):
+ *     allowed (lQ,rQ) blocks, lQ outer, each block row-major d_lQ x d_rQ.
+ *   - host operator buffers are the allowed sector blocks of a SparseMatrix (BaseOperator.h:100-104) concatenated
+ *     in (i outer, j inner) order, each block row-major d_i x d_j (newmat Matrix::Store(), newmat.h:455).
+ *   - one host thread per context; one context per GPU (one process per GPU under torch.distributed / NCCL).
+ */
+#ifndef BLOCK_B200_H
+#define BLOCK_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct b2d_ctx b2d_ctx;
+
+enum {
+  B2D_OK = 0,
+  B2D_ERR_ARG = 1,        /* bad argument / call order */
+  B2D_ERR_NO_DEVICE = 2,  /* compute entry point called on a planning-only context (no CUDA device) */
+  B2D_ERR_CUDA = 3,       /* a CUDA runtime call or kernel failed */
+  B2D_ERR_NCCL = 4,
+  B2D_ERR_NOCONV = 5      /* Davidson hit the iteration cap */
+};
+
+/* opTypes, BaseOperator.h:35-44 (only the ones the energy sweep carries, SURVEY.md 2.1 glossary) */
+enum {
+  B2D_HAM = 0, B2D_CRE = 1, B2D_CRE_CRE = 2, B2D_DES_DESCOMP = 3, B2D_CRE_DES = 4, B2D_CRE_DESCOMP = 5,
+  B2D_CRE_CRE_DESCOMP = 6, B2D_OVERLAP = 13
+};
+
+/* ---- context -------------------------------------------------------------------------------------------- */
+
+/* device >= 0: bind to that CUDA device.  device == -1: planning-only context (integer/host work only; used by
+ * the CPU tests; every compute call fails with B2D_ERR_NO_DEVICE). */
+int b2d_create(int device, b2d_ctx** out);
+void b2d_destroy(b2d_ctx* ctx);
+const char* b2d_last_error(const b2d_ctx* ctx);   /* ctx may be NULL: last error of a failed b2d_create */
+int b2d_abi_version(void);
+
+/* Tuning knobs (all optional): "workspace_mb" (T workspace for the two-step contraction), "max_davidson_iter",
+ * "tile_class" (debug: force one GEMM tile class), "sync_debug". */
+int b2d_set_option(b2d_ctx* ctx, const char* key, double value);
+
+/* ---- block description: replaces the host-side SpinBlock / StateInfo / Op_component objects ---------------- */
+
+/* StateInfo of one child (StateInfo.h:113-147: quanta, quantaStates) + SpinBlock::sites / is_loopblock()
+ * (spinblock.h:104,138). q = nq x 3 ints (N, 2S, irrep). */
+int b2d_set_block(b2d_ctx* ctx, int side, int nq, const int32_t* q, const int32_t* dims,
+                  int is_loop, int nsites, const int32_t* sites);
+
+/* One SparseMatrix (BaseOperator.h:75-243) of an operator array of that child (Op_component<Op>,
+ * op_components.h:214): optype, orbital indices (norb = 0,1,2), spin-component index inside the vector returned by
+ * get_element (op_components.C:172-184), deltaQuantum[0], fermion flag, allowedQuantaMatrix (nq x nq bytes) and the
+ * packed blocks.  data may be NULL: the blocks are allocated zero-filled on the device (see b2d_fill_op_random).
+ * Returns the operator id (>= 0) in *op_id. */
+int b2d_add_op(b2d_ctx* ctx, int side, int optype, int norb, const int32_t* orbs, int comp, const int32_t* dq,
+               int fermion, const uint8_t* allowed, const double* data, int* op_id);
+
+/* Synthetic-benchmark helper: fill an operator's device blocks with a counter-based uniform(-a,a) stream; if
+ * symmetric != 0 the operator is made self-adjoint in the reduced-matrix-element sense (needs dq = (0,0,0)). */
+int b2d_fill_op_random(b2d_ctx* ctx, int side, int op_id, uint64_t seed, double amplitude, int symmetric);
+
+/* Copy an operator's blocks back in the host layout of b2d_add_op. */
+int b2d_download_op(b2d_ctx* ctx, int side, int op_id, double* data);
+int64_t b2d_op_size(const b2d_ctx* ctx, int side, int op_id);   /* packed doubles */
+
+/* Wavefunction target quantum (Wavefunction::initialise, wavefunction.C:18-56), core energy (coreEnergy[],
+ * spinblock.C:735), Hamiltonian type (HUBBARD skips the two-index terms, spinblock.C:771), number of spatial
+ * orbitals (the `length` of trimap_2d, para_array.h:360) and this process's share of the operator terms
+ * (rank, nranks: the partition of distribute.C / para_array.h:33-42 across GPUs).
+ * Builds the psi layout, the term list of SpinBlock::multiplyH (spinblock.C:722-789) with every scalar factor
+ * (9j, parities, transpose scalings; operatorfunctions.C:520-529) and the grouped-contraction schedule. */
+int b2d_plan(b2d_ctx* ctx, const int32_t* psi_dq, double core_energy, int hubbard, int norbs, int rank, int nranks);
+
+int64_t b2d_psi_size(const b2d_ctx* ctx);          /* W: length of a flat host wavefunction */
+int64_t b2d_psi_padded_size(const b2d_ctx* ctx);   /* device-internal padded length */
+int b2d_psi_num_blocks(const b2d_ctx* ctx);
+/* per allowed block: lQ, rQ, flat offset (== StateInfo::unBlockedIndex of the big block, StateInfo.C:213-227) */
+int b2d_psi_blocks(const b2d_ctx* ctx, int32_t* lq, int32_t* rq, int64_t* offset);
+
+/* Term list introspection (integer work, bit-exact contract).  One row per TensorMultiply call of
+ * multiplyH that THIS rank executes: left op id, right op id, transpose flags (bit0 = left is a Transposeview,
+ * bit1 = right), scale, owner rank.  all_ranks != 0 lists every rank's terms (owner column tells whose). */
+int b2d_num_terms(const b2d_ctx* ctx, int all_ranks);
+int b2d_terms(const b2d_ctx* ctx, int all_ranks, int32_t* left_op, int32_t* right_op, int32_t* flags,
+              double* scale, int32_t* owner);
+/* ALGORITHMIC flops of one multiplyH = the dgemm flops the reference issues (operatorfunctions.C:515,530);
+ * all_ranks = 0: this rank's share. */
+double b2d_sigma_flops(const b2d_ctx* ctx, int all_ranks);
+/* schedule statistics: out[0]=#chunks, [1]=#step-1 contractions, [2]=#step-2 segments, [3]=#sigma tiles,
+ * [4]=workspace doubles, [5]=operator arena doubles, [6]=kernel launches per sigma */
+int b2d_plan_stats(const b2d_ctx* ctx, double* out, int n);
+
+/* ---- device-resident wavefunction slots ------------------------------------------------------------------- */
+
+int b2d_vec_reserve(b2d_ctx* ctx, int nslots);                       /* slots 0..nslots-1, zero-filled */
+int b2d_vec_upload(b2d_ctx* ctx, int slot, const double* flat);      /* Wavefunction::CollectFrom, wavefunction.C:188 */
+int b2d_vec_download(b2d_ctx* ctx, int slot, double* flat);          /* Wavefunction::FlattenInto, wavefunction.C:167 */
+int b2d_vec_dot(b2d_ctx* ctx, int a, int b, double* out);            /* DotProduct, BaseOperator.C:240 */
+int b2d_vec_axpy(b2d_ctx* ctx, double alpha, int x, int y);          /* ScaleAdd, BaseOperator.C:255: y += alpha x */
+int b2d_vec_scale(b2d_ctx* ctx, double alpha, int x);                /* Scale, BaseOperator.C:272 */
+int b2d_vec_copy(b2d_ctx* ctx, int src, int dst);
+int b2d_vec_clear(b2d_ctx* ctx, int slot);
+
+/* ---- sigma ------------------------------------------------------------------------------------------------ */
+
+/* SpinBlock::multiplyH(Wavefunction& c, Wavefunction* v, int) spinblock.h:235, spinblock.C:722-789.
+ * dst (+)= H src over this rank's terms, followed (nranks > 1, communicator attached) by the all-reduce that
+ * replaces distributedaccumulate (distribute.h:42-76).  accumulate = 1 keeps the reference's "v += H c"
+ * contract; 0 overwrites. */
+int b2d_sigma(b2d_ctx* ctx, int src_slot, int dst_slot, int accumulate);
+
+/* The same call with HOST buffers (what a reference-side binding does per Davidson_functor call,
+ * davidson.C:19-22): H2D of c, sigma, D2H of v.  accumulate = 1: v += H c exactly as the reference (v is uploaded
+ * too); accumulate = 0: v = H c (what block_davidson needs: it clears v first, linear.C:239-240). */
+int b2d_multiplyH_host(b2d_ctx* ctx, const double* c_flat, double* v_flat, int accumulate);
+
+/* operatorfunctions::TensorMultiply(ablock, a, b, cblock, c, v, opQ, scale), operatorfunctions.C:485-537, for ONE
+ * operator pair (left op id, right op id, transpose flags as in b2d_terms): dst += scale (A_L x A_R) src.
+ * opq_spin is the 2S of opQ (0 for every Hamiltonian term).  right_op < 0 or left_op < 0 selects the
+ * one-operator form (operatorfunctions.C:331-404) with the identity on the missing side. */
+int b2d_tensor_multiply(b2d_ctx* ctx, int left_op, int right_op, int flags, int opq_spin, double scale,
+                        int src_slot, int dst_slot);
+
+/* SpinBlock::diagonalH(DiagonalMatrix&) spinblock.h:240, spinblock.C:855-899: diag(H) in flat psi order. */
+int b2d_diagonal(b2d_ctx* ctx, int dst_slot);
+
+/* ---- Davidson --------------------------------------------------------------------------------------------- */
+
+/* Linear::block_davidson(vector<Wavefunction>& b, DiagonalMatrix& h_diag, double normtol, const bool& warmUp,
+ * Davidson_functor& h_multiply, bool& useprecond, int currentRoot, vector<Wavefunction>& lowerStates)
+ * linear.h:28, linear.C:179-385, state-averaged form (currentRoot = -1, no lower states).
+ * Guesses are in slots guess_slot0 .. guess_slot0+nroots-1 and are overwritten by the solutions (as `b` is).
+ * diag_slot holds diag(H).  evals[nroots] receives the eigenvalues (h_diag.element(i), linear.C:344),
+ * *n_multiply the number of H applications, *residual the last ||r||^2.
+ * The Krylov vectors, sigma vectors, subspace matrix, its eigen-decomposition and the Olsen preconditioner all
+ * stay on the device; the host only reads one convergence scalar per iteration. */
+int b2d_davidson(b2d_ctx* ctx, int nroots, int guess_slot0, int diag_slot, double normtol, int deflation_min,
+                 int deflation_max, double* evals, int* n_multiply, double* residual);
+
+/* ---- renormalisation ---------------------------------------------------------------------------------------- */
+
+/* DensityMatrix::makedensitymatrix (density.C:27-90, noise = 0): rho[q] = sum_i w_i sum_r psi_i[q,r] psi_i[q,r]^T
+ * for the wavefunctions in slots slot0..slot0+nroots-1. */
+int b2d_make_density(b2d_ctx* ctx, int nroots, int slot0, const double* weights);
+int64_t b2d_density_size(const b2d_ctx* ctx);       /* sum_q d_q^2 */
+int b2d_density_download(b2d_ctx* ctx, double* rho);   /* blocks q = 0..nq-1, row-major d_q x d_q */
+int b2d_density_upload(b2d_ctx* ctx, const double* rho);
+
+/* diagonalise_dm (rotationmat.C:258-279): per-sector symmetric eigen-decomposition on the device, eigenvalues
+ * ascending, those < 1e-14 set to 0.  evals receives sum_q d_q doubles. */
+int b2d_diagonalise_dm(b2d_ctx* ctx, double* evals);
+
+/* sort_weights + assign_matrix_by_dm (rotationmat.C:313-346, :149-256; keptqstates = 0): global descending order
+ * with the reference's tie rule, keep the first min(total, keep_states) with weight > 1e-13.
+ * kept_counts[nq] receives the retained states per left sector, *discarded the discarded weight.  The rotation
+ * matrices (kept eigenvectors as columns, selection order) stay on the device. */
+int b2d_select_states(b2d_ctx* ctx, int keep_states, int32_t* kept_counts, double* discarded);
+
+int64_t b2d_rotation_size(const b2d_ctx* ctx);                 /* sum_q d_q * kept_q */
+int b2d_rotation_download(b2d_ctx* ctx, double* rot);          /* per sector, row-major d_q x kept_q */
+int b2d_rotation_upload(b2d_ctx* ctx, const int32_t* kept_counts, const double* rot);
+
+/* SpinBlock::transform_operators(vector<Matrix>&) spinblock.h:253, save_load_block.C:267-319 ->
+ * SparseMatrix::renormalise_transform BaseOperator.C:341-363 -> MatrixRotate MatrixBLAS.C:553-572:
+ * every operator of the LEFT child becomes O'[a,b] = U_Q(a)^T O[Q(a),Q(b)] U_Q(b) on the retained sectors.
+ * The rotated operators replace nothing: they are written into a fresh arena that b2d_rotated_* reads. */
+int b2d_transform_operators(b2d_ctx* ctx);
+int b2d_rotated_num_sectors(const b2d_ctx* ctx);
+int b2d_rotated_sectors(const b2d_ctx* ctx, int32_t* old_index, int32_t* dims);
+int64_t b2d_rotated_op_size(const b2d_ctx* ctx, int op_id);
+int b2d_rotated_op_download(b2d_ctx* ctx, int op_id, uint8_t* allowed, double* data);
+
+/* SpinBlock::RenormaliseFrom (spinblock.h:247-251, renormalise.C:39-133), two-dot, noise = 0: diagonalH, Davidson
+ * from the guesses in slot0.., density matrix, eigen-decomposition, state selection.  Leaves the solutions in the
+ * guess slots and the rotation matrices on the device (follow with b2d_transform_operators). */
+int b2d_renormalise_from(b2d_ctx* ctx, int nroots, int guess_slot0, const double* weights, double normtol,
+                         int keep_states, int deflation_min, int deflation_max, double* energies,
+                         int32_t* kept_counts, double* discarded, int* n_multiply);
+
+/* ---- multi-GPU: partition of operator terms, NCCL all-reduce of the partial sigma --------------------------- */
+
+int b2d_nccl_unique_id(uint8_t* id128);                                   /* rank 0; broadcast out of band */
+int b2d_comm_init(b2d_ctx* ctx, const uint8_t* id128, int rank, int nranks);
+int b2d_allreduce_slot(b2d_ctx* ctx, int slot);
+
+/* ---- measurement ------------------------------------------------------------------------------------------- */
+
+/* CUDA-event time (ms) of the last b2d_sigma / b2d_davidson / b2d_make_density / b2d_transform_operators call on
+ * the context's stream: out[0] = total, out[1] = step-1 kernels, out[2] = step-2 kernels, out[3] = collective. */
+int b2d_last_timing(b2d_ctx* ctx, double* out, int n);
+int64_t b2d_kernel_launches(const b2d_ctx* ctx);     /* kernels launched by this context so far */
+int b2d_sync(b2d_ctx* ctx);
+void* b2d_stream(b2d_ctx* ctx);                      /* cudaStream_t, for event timing by the caller */
+/* FP64 yardsticks measured with this library's own kernels on the context's device: DMMA register loop
+ * (TFLOP/s), DFMA register loop (TFLOP/s). */
+int b2d_measure_fp64_peak(b2d_ctx* ctx, double* dmma_tflops, double* dfma_tflops);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,170 @@
+"""Parity of the CUDA hot path (through the C ABI) with the oracle and with records of the real reference.
+Tolerances are north_star's: sigma <= 1e-10 relative, energies <= 1e-8 Eh, identical retained sectors / counts."""
+import numpy as np
+import pytest
+
+from block_b200 import hotpath
+from oracle import dmrg_oracle as O
+from oracle import dumpio
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    return np.linalg.norm(a - b) / np.linalg.norm(b)
+
+
+@pytest.fixture(scope="module")
+def gpu_block(golden):
+    rec, big = golden
+    sb = hotpath.spinblock_from_record(rec, device=0)
+    yield rec, big, sb
+    sb.close()
+
+
+def test_operator_roundtrip(gpu_block):
+    rec, big, sb = gpu_block
+    for side, blk in enumerate((sb.left, sb.right)):
+        for k in (0, len(blk.ops) // 2, len(blk.ops) - 1):
+            assert np.array_equal(sb.download_op(side, sb.op_ids[side][k]), blk.ops[k].data)    # bit-exact
+
+
+def test_wavefunction_roundtrip(gpu_block):
+    rec, big, sb = gpu_block
+    sb.upload(0, rec["rpsi"])
+    assert np.array_equal(sb.download(0), rec["rpsi"])
+
+
+def test_sigma_matches_reference(gpu_block):
+    rec, big, sb = gpu_block
+    v = sb.multiplyH(rec["rpsi"])
+    assert rel(v, rec["rsigma"]) < 1e-10
+    assert rel(v, rec["rsigma"]) < 1e-13          # what FP64 DMMA actually delivers
+    for i in range(int(rec["meta"][4])):
+        assert rel(sb.multiplyH(rec["psi%d" % i]), rec["sigma%d" % i]) < 1e-10
+
+
+def test_sigma_accumulates_like_reference(gpu_block):
+    rec, big, sb = gpu_block
+    v0 = np.cos(np.arange(sb.size))
+    v = sb.multiplyH(rec["rpsi"], v0.copy())
+    assert rel(v - v0, rec["rsigma"]) < 1e-10
+
+
+@pytest.mark.parametrize("cls", [0, 1, 2])
+def test_sigma_every_tile_class(golden, cls):
+    rec, big = golden
+    sb = hotpath.spinblock_from_record(rec, device=0, options={"tile_class": cls})
+    try:
+        assert rel(sb.multiplyH(rec["rpsi"]), rec["rsigma"]) < 1e-12
+    finally:
+        sb.close()
+
+
+def test_sigma_chunked_workspace(golden):
+    rec, big = golden
+    sb = hotpath.spinblock_from_record(rec, device=0, options={"workspace_mb": 0.01})
+    try:
+        assert sb.plan_stats()["chunks"] > 1
+        assert rel(sb.multiplyH(rec["rpsi"]), rec["rsigma"]) < 1e-12
+    finally:
+        sb.close()
+
+
+def test_tensor_multiply_single_terms(gpu_block):
+    rec, big, sb = gpu_block
+    terms = O.h_terms(big)
+    lo, ro, fl, sc, ow = sb.terms(all_ranks=True)
+    c = big.unflatten(rec["rpsi"])
+    for k in sorted(set([0, 1, 2, len(terms) // 2, len(terms) - 1])):
+        v = big.zeros()
+        O.tensor_multiply(big, terms[k][0], terms[k][1], c, v, 0, terms[k][2])
+        ref = big.flatten(v)
+        got = sb.TensorMultiply(int(lo[k]), int(ro[k]), rec["rpsi"], np.zeros(sb.size), bool(fl[k] & 1), bool(fl[k] & 2), 0, float(sc[k]))
+        assert np.linalg.norm(got - ref) <= 1e-12 * max(np.linalg.norm(ref), 1e-30)
+
+
+def test_diagonal_matches_reference(gpu_block):
+    rec, big, sb = gpu_block
+    assert rel(sb.diagonalH(), rec["diag"]) < 1e-13
+
+
+def test_davidson_matches_reference(gpu_block):
+    rec, big, sb = gpu_block
+    nroots = int(rec["meta"][4])
+    ev, vecs, nmult = sb.block_davidson([rec["guess%d" % i] for i in range(nroots)], rec["diag"], float(rec["dav_tol"][0]),
+                                        int(rec["dav_in"][4]), int(rec["dav_in"][5]))
+    assert np.abs(ev - rec["dav_evals"][:nroots]).max() < 1e-8          # north_star: energies within 1e-8 Eh
+    assert np.abs(ev - rec["dav_evals"][:nroots]).max() < 1e-10
+    assert nmult == int(rec["dav_out"][0])                              # same number of H applications
+    for i in range(nroots):
+        assert abs(abs(np.dot(vecs[i], rec["psi%d" % i])) - 1.0) < 1e-8
+
+
+def test_density_matches_reference(gpu_block):
+    rec, big, sb = gpu_block
+    nroots = int(rec["meta"][4])
+    rho = sb.make_density([rec["psi%d" % i] for i in range(nroots)], rec["weights"])
+    assert rel(np.concatenate([r.ravel() for r in rho]), rec["rdm.data"]) < 1e-13
+
+
+def test_truncation_identical_sectors_and_counts(gpu_block):
+    rec, big, sb = gpu_block
+    nroots = int(rec["meta"][4])
+    sb.make_density([rec["psi%d" % i] for i in range(nroots)], rec["weights"])
+    evals = sb.diagonalise_dm()
+    rho = O.make_density(big, [big.unflatten(rec["psi%d" % i]) for i in range(nroots)], rec["weights"])
+    ref_evals, _ = O.diagonalise_dm(rho)
+    for a, b in zip(evals, ref_evals):
+        assert np.abs(a - b).max() < 1e-13
+    kept, err, rot = sb.select_states(int(rec["meta"][5]))
+    ref_rot = dumpio.rotation_from(rec)
+    assert list(kept) == [r.shape[1] for r in ref_rot]                  # bit-exact integer contract
+    assert abs(err - rec["error"][0]) < 1e-12
+    for q in range(len(rot)):
+        if rot[q].shape[1]:
+            assert np.abs(rot[q].T @ rot[q] - np.eye(rot[q].shape[1])).max() < 1e-12
+            assert np.abs(rot[q] @ rot[q].T - ref_rot[q] @ ref_rot[q].T).max() < 1e-7
+
+
+def test_transform_operators_matches_reference(gpu_block):
+    rec, big, sb = gpu_block
+    ref_rot = dumpio.rotation_from(rec)
+    sb.set_rotation_matrices(ref_rot)
+    old, dims, ops = sb.transform_operators()
+    N = dumpio.block_from(rec, "N.")
+    keepq = [q for q in range(len(ref_rot)) if ref_rot[q].shape[1] > 0]
+    assert list(old) == keepq and list(dims) == list(N.dims)
+    checked = 0
+    for nop in N.ops:
+        k = next((i for i, o in enumerate(big.left.ops) if o.optype == nop.optype and o.orbs == nop.orbs and o.comp == nop.comp), None)
+        if k is None:
+            continue
+        allowed, data = ops[k]
+        assert (allowed == nop.allowed).all()
+        ref = np.concatenate([nop.blocks[(a, b)].ravel() for a in range(len(dims)) for b in range(len(dims)) if nop.allowed[a, b]] + [np.zeros(0)])
+        assert np.abs(data - ref).max() < 1e-12
+        checked += 1
+    assert checked > 0
+
+
+def test_renormalise_from_end_to_end(gpu_block):
+    rec, big, sb = gpu_block
+    nroots = int(rec["meta"][4])
+    out = sb.RenormaliseFrom([rec["guess%d" % i] for i in range(nroots)], rec["weights"], float(rec["dav_tol"][0]), int(rec["meta"][5]),
+                             int(rec["dav_in"][4]), int(rec["dav_in"][5]))
+    assert np.abs(out["energies"] - rec["energies"][:nroots]).max() < 1e-8
+    ref_rot = dumpio.rotation_from(rec)
+    assert list(out["kept"]) == [r.shape[1] for r in ref_rot]
+    assert abs(out["error"] - rec["error"][0]) < 1e-9
+    assert out["n_multiply"] == int(rec["dav_out"][0])
+
+
+def test_sigma_properties_linearity_and_symmetry(gpu_block):
+    """size-independent properties used again at benchmark scale: H(ax+by) = aHx + bHy and <x|Hy> = <y|Hx>."""
+    rec, big, sb = gpu_block
+    rng = np.random.default_rng(7)
+    x, y = rng.standard_normal(sb.size), rng.standard_normal(sb.size)
+    hx, hy = sb.multiplyH(x), sb.multiplyH(y)
+    assert rel(sb.multiplyH(2.0 * x - 3.0 * y), 2.0 * hx - 3.0 * hy) < 1e-12
+    assert abs(np.dot(x, hy) - np.dot(y, hx)) < 1e-10 * np.linalg.norm(hx) * np.linalg.norm(y)

@@ -1,0 +1,431 @@
+#!/usr/bin/env python
+"""Benchmark of the DMRG sweep hot path on B200: sigma = H.psi (SpinBlock::multiplyH, spinblock.C:722-789) on the
+big block of one two-dot block iteration of BASELINE.json's headline configuration
+("synthetic random-integral FCIDUMP, 40 orbitals / 40 electrons, M=4000").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+  * one step = one multiplyH over every operator term of the block iteration (ALL ranks' terms together);
+  * value   = algorithmic sigma FP64 GFLOP/s = the dgemm flops the reference issues for that multiplyH
+              (operatorfunctions.C:515,530) / device time, psi and operators resident in HBM;
+  * e2e     = the same through the reference-facing call with HOST buffers (b2d_multiplyH_host: H2D of psi from pinned
+              memory, sigma, D2H of the result inside the timed region);
+  * N > 1   = one process per GPU (torchrun); operator terms are partitioned by the reference's ownership rule
+              (para_array.h:33-42,360-383), psi is replicated, partial sigmas are summed by NCCL all-reduce inside
+              the step: the total work is fixed, so "scaling" is "strong";
+  * --impl reference = the CPU implementation of the same TensorMultiply calls on the box's host cores on a bounded
+              sample of the terms (see cpu_sigma_sample).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "sigma_fp64_gflops"
+UNIT = "GFLOP/s"
+
+
+def workload_name(a):
+    return "synthetic 40o/40e-shaped big block: norbs=%d nelec=%d M=%d, block iteration %d|%d sites, two-dot, C1, spin-adapted" % (
+        a.norbs, a.nelec, a.M, a.left_sites, a.norbs - a.left_sites)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU leg: the reference algorithm (oracle restatement, numpy/OpenBLAS dgemm) on a bounded sample of the terms
+# ---------------------------------------------------------------------------------------------------------------------
+class _LazyBlocks(dict):
+    """Operator sector blocks generated on demand (values do not matter for timing; shapes and sparsity do)."""
+
+    def __init__(self, dims, seed):
+        super().__init__()
+        self.dims, self.rng = dims, np.random.default_rng(seed)
+
+    def __missing__(self, key):
+        a = self.rng.standard_normal((int(self.dims[key[0]]), int(self.dims[key[1]])))
+        self[key] = a
+        return a
+
+
+def cpu_sigma_sample(a, budget_s=8.0, max_terms=64):
+    """Time oracle.dmrg_oracle.tensor_multiply (the restatement of operatorfunctions.C:485-537 whose inner products are
+    numpy/OpenBLAS dgemm calls on all host cores) on an evenly spaced sample of the multiplyH term list of the SAME big
+    block.  Returns (GFLOP/s, cores, description, seconds, flops)."""
+    from block_b200 import synthetic as S
+    from oracle import dmrg_oracle as O
+
+    nl = a.left_sites
+    filling = a.nelec / a.norbs
+    L = S.add_dot(S.renormalised_sectors(nl - 1, filling * (nl - 1), a.M))
+    R = S.add_dot(S.renormalised_sectors(a.norbs - nl - 1, filling * (a.norbs - nl - 1), a.M))
+    L = {k: d for k, d in L.items() if (a.nelec - k[0], k[1]) in R}
+    R = {k: d for k, d in R.items() if (a.nelec - k[0], k[1]) in L}
+    lsites, rsites = list(range(nl)), list(range(nl, a.norbs))
+    blocks = []
+    for spec in (S.make_block(L, lsites, rsites, True), S.make_block(R, rsites, lsites, False)):
+        blk = O.Block(q=spec.q.astype(np.int64), dims=spec.dims.astype(np.int64), sites=spec.sites, loop=spec.loop)
+        for k, op in enumerate(spec.ops):
+            blk.ops.append(O.Op(optype=op.optype, orbs=op.orbs, comp=op.comp, dq=op.dq, fermion=op.fermion, allowed=op.allowed.astype(bool),
+                                blocks=_LazyBlocks(spec.dims, 1000 * len(blocks) + k)))
+        blocks.append(blk)
+    big = O.Big(left=blocks[0], right=blocks[1], psi_dq=(a.nelec, 0, 0))
+    terms = O.h_terms(big)
+    rng = np.random.default_rng(1)
+    c = big.unflatten(rng.standard_normal(big.size))
+    order = [int(i) for i in np.unique(np.linspace(0, len(terms) - 1, max_terms).astype(int))]
+    # interleave so that a truncated sample still covers every term family
+    order = order[::4] + order[1::4] + order[2::4] + order[3::4]
+    flops, secs, used = [0.0], 0.0, 0
+    for i in order:
+        lop, rop, scale = terms[i]
+        for view in (lop, rop):           # materialise the operator blocks outside the timed region
+            for (p, q) in zip(*np.nonzero(view.op.allowed)):
+                view.op.blocks[(int(p), int(q))]
+        v = big.zeros()
+        t0 = time.perf_counter()
+        O.tensor_multiply(big, lop, rop, c, v, 0, scale, flops)
+        secs += time.perf_counter() - t0
+        used += 1
+        for view in (lop, rop):
+            view.op.blocks.clear()
+        if secs > budget_s:
+            break
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    desc = "%d of %d TensorMultiply terms of the same multiplyH (evenly spaced over the term list), numpy/OpenBLAS dgemm, %.1f s" % (used, len(terms), secs)
+    return flops[0] / secs / 1e9, cores, desc, secs, flops[0]
+
+
+REF_BENCH = os.path.join(ROOT, "oracle", "_ref", "ref_bench")
+
+
+def _oracle_big(a):
+    """The synthetic big block as oracle objects (operator blocks lazily random) and its multiplyH term list."""
+    from block_b200 import synthetic as S
+    from oracle import dmrg_oracle as O
+
+    nl = a.left_sites
+    filling = a.nelec / a.norbs
+    L = S.add_dot(S.renormalised_sectors(nl - 1, filling * (nl - 1), a.M))
+    R = S.add_dot(S.renormalised_sectors(a.norbs - nl - 1, filling * (a.norbs - nl - 1), a.M))
+    L = {k: d for k, d in L.items() if (a.nelec - k[0], k[1]) in R}
+    R = {k: d for k, d in R.items() if (a.nelec - k[0], k[1]) in L}
+    lsites, rsites = list(range(nl)), list(range(nl, a.norbs))
+    blocks = []
+    for spec in (S.make_block(L, lsites, rsites, True), S.make_block(R, rsites, lsites, False)):
+        blk = O.Block(q=spec.q.astype(np.int64), dims=spec.dims.astype(np.int64), sites=spec.sites, loop=spec.loop)
+        for k, op in enumerate(spec.ops):
+            blk.ops.append(O.Op(optype=op.optype, orbs=op.orbs, comp=op.comp, dq=op.dq, fermion=op.fermion, allowed=op.allowed.astype(bool),
+                                blocks=_LazyBlocks(spec.dims, 1000 * len(blocks) + k)))
+        blocks.append(blk)
+    big = O.Big(left=blocks[0], right=blocks[1], psi_dq=(a.nelec, 0, 0))
+    return big, O.h_terms(big)
+
+
+def _sample_order(nterms, max_terms):
+    order = [int(i) for i in np.unique(np.linspace(0, nterms - 1, max_terms).astype(int))]
+    return order[::4] + order[1::4] + order[2::4] + order[3::4]   # a truncated sample still covers every term family
+
+
+def cpu_sigma_reference(a, budget_s=10.0, max_terms=48, state={}):
+    """Time the REAL reference's operatorfunctions::TensorMultiply (oracle/_ref/ref_bench: the unmodified reference
+    objects compiled by oracle/Makefile, OpenMP over operator terms with single-threaded OpenBLAS dgemm inside, exactly how
+    multiplyH parallelises: operatorloops.h:87-97) on an evenly spaced sample of the SAME multiplyH's term list.
+    Returns (GFLOP/s, cores, description, seconds, flops)."""
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    if "terms" not in state:
+        state["big"], state["terms"] = _oracle_big(a)
+    big, terms = state["big"], state["terms"]
+
+    def run(indices):
+        with tempfile.NamedTemporaryFile("w", suffix=".spec", delete=False) as f:
+            for blk in (big.left, big.right):
+                f.write("%d\n" % len(blk.dims))
+                for q, d in zip(blk.q, blk.dims):
+                    f.write("%d %d %d\n" % (q[0], q[1], d))
+            f.write("%d %d\n%d\n" % (big.psi_dq[0], big.psi_dq[1], len(indices)))
+            for i in indices:
+                lop, rop, scale = terms[i]
+                f.write("%d %d %d %d  %d %d %d %d  %.17g\n" % (lop.op.dq[0], lop.op.dq[1], int(lop.op.fermion), int(lop.t),
+                                                              rop.op.dq[0], rop.op.dq[1], int(rop.op.fermion), int(rop.t), scale))
+            path = f.name
+        env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS=str(cores))
+        out = subprocess.run([REF_BENCH, path, "1", str(cores)], env=env, capture_output=True, text=True, timeout=1200)
+        os.unlink(path)
+        for ln in out.stdout.splitlines():
+            if ln.startswith("REFBENCH"):
+                kv = dict(x.split("=") for x in ln.split()[1:])
+                return float(kv["seconds"]), float(kv["flops"])
+        raise RuntimeError("ref_bench failed: " + out.stderr[-400:])
+
+    order = _sample_order(len(terms), max_terms)
+    if "rate" not in state:                       # calibrate on one term per core
+        s0, f0 = run(order[:max(cores, 2)])
+        state["rate"] = f0 / s0
+    per_term = sum(1 for _ in order) and (5.8e13 * (a.M / 4000.0) ** 3 / len(terms))
+    n = int(min(len(order), max(cores, budget_s * state["rate"] / max(per_term, 1.0))))
+    n = max(cores, n - n % cores) if n >= cores else n
+    secs, flops = run(order[:n])
+    desc = ("%d of %d TensorMultiply terms of the same multiplyH (evenly spaced over the term list) through the unmodified reference's "
+            "operatorfunctions::TensorMultiply, OpenMP over terms x %d threads, OpenBLAS 0.3.15 dgemm single-threaded inside, %.1f s" % (n, len(terms), cores, secs))
+    return flops / secs / 1e9, cores, desc, secs, flops
+
+
+def cpu_leg(a, budget_s):
+    if os.path.exists(REF_BENCH):
+        return ("reference",) + cpu_sigma_reference(a, budget_s)
+    return ("port",) + cpu_sigma_sample(a, budget_s)
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    for _ in range(a.warmup):
+        cpu_leg(a, a.ref_step_s / 2)
+    t, fl, last = 0.0, 0.0, None
+    for _ in range(a.steps):
+        last = cpu_leg(a, a.ref_step_s)
+        t += last[4]
+        fl += last[5]
+    value = fl / t / 1e9
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": 1e3 * t / max(a.steps, 1), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "config": {"workload": workload_name(a), "sample": last[3]},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": last[2], "kind": last[0], "sample": last[3]},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU leg
+# ---------------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device):
+        self.device, self.proc, self.path = device, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.FIELDS, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        try:
+            for ln in open(self.path):
+                f = [x.strip() for x in ln.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+                except ValueError:
+                    continue
+                for nm, val in zip(names, f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            out.update(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(smax)), power_w_max=float(max(power)), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def run_ours(a):
+    import torch
+    import torch.distributed as dist
+
+    from block_b200 import synthetic as S
+    from block_b200.hotpath import SpinBlock
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the hot path has no CPU fallback (use --impl reference for the CPU leg)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    t_setup = time.time()
+    sb = S.make_big_block(norbs=a.norbs, nelec=a.nelec, M=a.M, left_sites=a.left_sites, device=local, rank=rank, nranks=world,
+                          options={"workspace_mb": a.workspace_mb})
+    if world > 1:   # the partial sigmas are summed by the library's own NCCL communicator (dlopen'ed libnccl of the torch wheel)
+        ident = [SpinBlock.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ident, src=0)
+        sb.attach_communicator(ident[0], rank, world)
+    stats = sb.plan_stats()
+    flops_alg = sb.sigma_flops(all_ranks=True)          # the reference's dgemm flops for the whole multiplyH
+    flops_mine = sb.sigma_flops(all_ranks=False)
+    W = sb.size
+    rng = np.random.default_rng(5)
+    psi_host = torch.from_numpy(rng.standard_normal(W)).pin_memory()
+    sig_host = torch.empty(W, dtype=torch.float64).pin_memory()
+    psi = psi_host.numpy()
+    psi /= np.linalg.norm(psi)
+    sb.reserve(3)
+    sb.upload(0, psi)
+    t_setup = time.time() - t_setup
+    stream = torch.cuda.ExternalStream(sb.lib.b2d_stream(sb._ctx), device=torch.device("cuda", local))
+
+    def barrier():
+        sb.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        e1.synchronize()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    if a.profile_mode:
+        sb.sigma(0, 1)
+        sb.sync()
+        for _ in range(a.steps):
+            sb.sigma(0, 1)
+        sb.sync()
+        print("profile-mode: %d launches per sigma" % int(stats["launches_per_sigma"]), flush=True)
+        sb.close()
+        return
+
+    # size-independent parity properties at full size (the oracle cannot run this size): symmetry <x|Hy> = <y|Hx>
+    y = rng.standard_normal(W); y /= np.linalg.norm(y)
+    sb.upload(2, y)
+    sb.sigma(0, 1)
+    hx = sb.download(1)
+    sb.sigma(2, 1)
+    hy = sb.download(1)
+    sym_err = abs(float(np.dot(psi, hy) - np.dot(y, hx))) / (np.linalg.norm(hx) * np.linalg.norm(y))
+
+    for _ in range(a.warmup):
+        sb.sigma(0, 1)
+    clocks = ClockSampler(local)
+    clocks.start()
+    l0 = sb.kernel_launches()
+    ms = timed(lambda: sb.sigma(0, 1), a.steps)
+    launches = sb.kernel_launches() - l0
+    clk = clocks.stop()
+    ms_step = ms / a.steps
+    value = flops_alg / (ms_step * 1e-3) / 1e9
+
+    # end to end through the reference-facing call with host buffers (pinned), copies inside the timed region
+    sigp = sig_host.numpy()
+    for _ in range(min(a.warmup, 2)):
+        sb.multiplyH_into(psi, sigp)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(a.steps):
+        sb.multiplyH_into(psi, sigp)
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_value = flops_alg / (float(e2e_s.item()) / a.steps) / 1e9
+    e2e_err = float(np.linalg.norm(sigp - hx) / np.linalg.norm(hx))
+
+    line = None
+    if rank == 0 or world == 1:
+        # roofline of the dominant kernel (128x128 DMMA tile class of the grouped contraction), timed live with events
+        prof = sb.sigma_profile(0, 1)
+        dmma, dfma = sb.measure_fp64_peak()
+        k_ms = sum(prof[(st, 0)][0] for st in range(2))
+        k_fl = sum(prof[(st, 0)][1] for st in range(2))
+        k_pad = sum(prof[(st, 0)][2] for st in range(2))
+        k_n = sum(prof[(st, 0)][3] for st in range(2))
+        tot_ms = sum(v[0] for v in prof.values())
+        achieved = k_fl / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+        roof = {"bound": "tensor", "achieved": achieved, "peak": dmma, "unit": "TFLOP/s", "frac": achieved / dmma if dmma else None, "traffic": None,
+                "kernel": "grouped_gemm_kernel<128,128,2,4,4> (FP64 DMMA m16n8k8)", "launches": int(k_n), "avg_launch_ms": k_ms / max(k_n, 1),
+                "share_of_sigma": k_ms / tot_ms if tot_ms else None, "tile_fill": k_fl / k_pad if k_pad else None,
+                "peak_source": "live FP64 DMMA register-loop yardstick of this library on this GPU (MEASURED_PEAKS.json has no FP64 entry); DFMA loop %.1f TFLOP/s" % dfma,
+                "per_class": {"step%d_class%d" % (st + 1, c): {"ms": v[0], "tflops": (v[1] / (v[0] * 1e-3) / 1e12 if v[0] > 0 else 0.0), "tile_fill": (v[1] / v[2] if v[2] else None),
+                                                               "launches": int(v[3])} for (st, c), v in prof.items()}}
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": {"workload": workload_name(a), "psi_doubles": int(W), "terms": int(len(sb.terms(all_ranks=True)[0])),
+                           "left_sectors": int(len(sb.left.dims)), "right_sectors": int(len(sb.right.dims)), "left_states": int(sb.left.dims.sum()),
+                           "right_states": int(sb.right.dims.sum()), "sigma_flops": flops_alg, "rank0_flops": flops_mine,
+                           "operator_arena_gb_rank0": stats["arena_doubles"] * 8 / 1e9, "chunks": int(stats["chunks"]),
+                           "parallelism": "operator-term partition x%d + NCCL all-reduce of partial sigma" % world if world > 1 else "single GPU",
+                           "l2": "inputs larger than L2 (operator arena %.0f GB per step)" % (stats["arena_doubles"] * 8 / 1e9), "setup_s": t_setup},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(W * 8), "d2h_bytes_per_step": int(W * 8)},
+                "gpu_launches": int(launches), "clocks": clk, "roofline": roof,
+                "parity": {"hermiticity_rel": sym_err, "e2e_vs_resident_rel": e2e_err},
+                "hbm_peak_gbs": peaks.get("hbm_gbs")}
+    if (rank == 0 or world == 1) and not a.no_cpu and world == 1:
+        kind, v, cores, desc, _, _ = cpu_leg(a, a.cpu_budget_s)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}
+    if line is not None:
+        print(json.dumps(line), flush=True)
+    sb.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--norbs", type=int, default=40)
+    ap.add_argument("--nelec", type=int, default=40)
+    ap.add_argument("--M", type=int, default=4000)
+    # 18|22: the heaviest block iteration of the 40-orbital M=4000 sweep whose materialised operator arenas (152 GB) fit
+    # ONE 180 GB B200; the mid-chain 20|20 iteration (185 GB) needs the term partition over >= 2 GPUs
+    ap.add_argument("--left-sites", type=int, default=18)
+    ap.add_argument("--workspace-mb", type=float, default=2048.0)
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--profile-mode", action="store_true", help="for ncu: 1 warm-up sigma + --steps sigmas, nothing else, no JSON line")
+    ap.add_argument("--cpu-budget-s", type=float, default=15.0)
+    ap.add_argument("--ref-step-s", type=float, default=6.0)
+    a = ap.parse_args()
+    a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)
+
+
+if __name__ == "__main__":
+    main()

@@ -70,6 +70,7 @@ PROTOTYPES = {
     "b2d_comm_init": (C.c_int, [ctx_p, c_u8p, C.c_int, C.c_int]),
     "b2d_allreduce_slot": (C.c_int, [ctx_p, C.c_int]),
     "b2d_last_timing": (C.c_int, [ctx_p, c_f64p, C.c_int]),
+    "b2d_sigma_profile": (C.c_int, [ctx_p, C.c_int, C.c_int, c_f64p]),
     "b2d_kernel_launches": (C.c_int64, [ctx_p]),
     "b2d_sync": (C.c_int, [ctx_p]),
     "b2d_stream": (C.c_void_p, [ctx_p]),

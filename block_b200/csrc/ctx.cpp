@@ -138,6 +138,8 @@ struct b2d_ctx {
   std::vector<cudaEvent_t> phase_events;
   bool phase_timing = false;
   double last_step_ms[2] = {0, 0};
+  double class_ms[2][B2D_NUM_TILE_CLASSES] = {{0, 0, 0}, {0, 0, 0}};
+  int class_launches[2][B2D_NUM_TILE_CLASSES] = {{0, 0, 0}, {0, 0, 0}};
 
   Nccl nccl;
 };
@@ -243,34 +245,51 @@ int upload_schedule(b2d_ctx* ctx, const Schedule& S, DevSchedule& D) {
   return B2D_OK;
 }
 
-// run a two-step schedule: bases for SRC / DST / AUX supplied by the caller, WORK = ctx->work
+// run a two-step schedule: bases for SRC / DST / AUX supplied by the caller, WORK = ctx->work.
+// With phase_timing every launch is bracketed by events and the times are summed per (step, tile class).
 int run_schedule(b2d_ctx* ctx, const Schedule& S, const DevSchedule& D, double* src, double* dst, double* aux) {
   CU(ctx->work.reserve((size_t)std::max<int64_t>(S.work_max, 16) * 8));
   double* bases[B2D_NUM_BASES] = {nullptr, src, (double*)ctx->work.p, dst, aux};
-  const bool pt = ctx->phase_timing;
-  size_t need_ev = pt ? D.chunks.size() * 2 + 1 : 0;
-  while (ctx->phase_events.size() < need_ev) {
-    cudaEvent_t e;
-    CU(cudaEventCreate(&e));
-    ctx->phase_events.push_back(e);
-  }
-  if (pt) CU(cudaEventRecord(ctx->phase_events[0], ctx->stream));
-  for (size_t i = 0; i < D.chunks.size(); ++i) {
-    CU(launch_gemm_batch(D.chunks[i].s1, bases, ctx->stream, &ctx->launches));
-    if (pt) CU(cudaEventRecord(ctx->phase_events[2 * i + 1], ctx->stream));
-    CU(launch_gemm_batch(D.chunks[i].s2, bases, ctx->stream, &ctx->launches));
-    if (pt) CU(cudaEventRecord(ctx->phase_events[2 * i + 2], ctx->stream));
-    if (ctx->sync_debug) CU(cudaStreamSynchronize(ctx->stream));
-  }
-  if (pt) {
-    CU(cudaStreamSynchronize(ctx->stream));
-    ctx->last_step_ms[0] = ctx->last_step_ms[1] = 0.0;
+  if (!ctx->phase_timing) {
     for (size_t i = 0; i < D.chunks.size(); ++i) {
-      float a = 0.f, b = 0.f;
-      cudaEventElapsedTime(&a, ctx->phase_events[2 * i], ctx->phase_events[2 * i + 1]);
-      cudaEventElapsedTime(&b, ctx->phase_events[2 * i + 1], ctx->phase_events[2 * i + 2]);
-      ctx->last_step_ms[0] += a; ctx->last_step_ms[1] += b;
+      CU(launch_gemm_batch(D.chunks[i].s1, bases, ctx->stream, &ctx->launches));
+      CU(launch_gemm_batch(D.chunks[i].s2, bases, ctx->stream, &ctx->launches));
+      if (ctx->sync_debug) CU(cudaStreamSynchronize(ctx->stream));
     }
+    return B2D_OK;
+  }
+  struct Mark { int step, cls; };
+  std::vector<Mark> marks;
+  size_t nev = 0;
+  auto event = [&](size_t i) -> cudaEvent_t {
+    while (ctx->phase_events.size() <= i) {
+      cudaEvent_t e = nullptr;
+      cudaEventCreate(&e);
+      ctx->phase_events.push_back(e);
+    }
+    return ctx->phase_events[i];
+  };
+  for (size_t i = 0; i < D.chunks.size(); ++i)
+    for (int step = 0; step < 2; ++step) {
+      const DevBatch& b = step == 0 ? D.chunks[i].s1 : D.chunks[i].s2;
+      for (int c = 0; c < B2D_NUM_TILE_CLASSES; ++c) {
+        if (b.ntiles[c] <= 0) continue;
+        CU(cudaEventRecord(event(nev++), ctx->stream));
+        CU(launch_gemm_class(b, c, bases, ctx->stream, &ctx->launches));
+        CU(cudaEventRecord(event(nev++), ctx->stream));
+        marks.push_back(Mark{step, c});
+      }
+    }
+  CU(cudaStreamSynchronize(ctx->stream));
+  for (int st = 0; st < 2; ++st)
+    for (int c = 0; c < B2D_NUM_TILE_CLASSES; ++c) { ctx->class_ms[st][c] = 0.0; ctx->class_launches[st][c] = 0; }
+  ctx->last_step_ms[0] = ctx->last_step_ms[1] = 0.0;
+  for (size_t k = 0; k < marks.size(); ++k) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx->phase_events[2 * k], ctx->phase_events[2 * k + 1]);
+    ctx->class_ms[marks[k].step][marks[k].cls] += ms;
+    ctx->class_launches[marks[k].step][marks[k].cls] += 1;
+    ctx->last_step_ms[marks[k].step] += ms;
   }
   return B2D_OK;
 }
@@ -383,13 +402,15 @@ int b2d_add_op(b2d_ctx* ctx, int side, int optype, int norb, const int32_t* orbs
   op.fermion = fermion != 0;
   op.allowed.assign(allowed, allowed + (size_t)s.nq * s.nq);
   layout_op(s, op);
-  if (ctx->has_device) {
+  // data == NULL: the blocks are materialised (zero-filled) by b2d_plan, and only if one of this rank's terms uses
+  // the operator - under a term partition a rank never holds the other ranks' operators
+  if (ctx->has_device && data) {
     CU(cudaSetDevice(ctx->device));
     if (op.dev_size > 0) {
       CU(arena_alloc(ctx, (size_t)op.dev_size * 8, &op.dev));
       ctx->arena_doubles += op.dev_size;
       CU(cudaMemsetAsync(op.dev, 0, (size_t)op.dev_size * 8, ctx->stream));
-      if (data) {
+      {
         std::vector<BlockDesc> bd = op_blocks(s, op);
         CU(ctx->staging.reserve((size_t)op.packed_size * 8));
         CU(cudaMemcpyAsync(ctx->staging.p, data, (size_t)op.packed_size * 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -417,6 +438,7 @@ int b2d_download_op(b2d_ctx* ctx, int side, int op_id, double* data) {
   const Side& s = ctx->side[side];
   const OpRec& op = s.ops[op_id];
   if (op.packed_size == 0) return B2D_OK;
+  if (!op.dev) return fail(ctx, B2D_ERR_ARG, "b2d_download_op: operator is not resident on this rank (no term of this rank uses it)");
   std::vector<BlockDesc> bd = op_blocks(s, op);
   CU(ctx->staging.reserve((size_t)op.packed_size * 8));
   int rc = upload_desc(ctx, ctx->desc_scratch, bd.data(), bd.size() * sizeof(BlockDesc));
@@ -432,7 +454,7 @@ int b2d_fill_op_random(b2d_ctx* ctx, int side, int op_id, uint64_t seed, double 
   if (side < 0 || side > 1 || op_id < 0 || op_id >= (int)ctx->side[side].ops.size()) return fail(ctx, B2D_ERR_ARG, "b2d_fill_op_random: bad arguments");
   const Side& s = ctx->side[side];
   const OpRec& op = s.ops[op_id];
-  if (op.packed_size == 0) return B2D_OK;
+  if (op.packed_size == 0 || !op.dev) return B2D_OK;   // not resident on this rank: nothing to fill
   std::vector<BlockDesc> bd = op_blocks(s, op);
   int rc = upload_desc(ctx, ctx->desc_scratch, bd.data(), bd.size() * sizeof(BlockDesc));
   if (rc) return rc;
@@ -471,6 +493,33 @@ int b2d_plan(b2d_ctx* ctx, const int32_t* psi_dq, double core_energy, int hubbar
     ctx->terms_all = enumerate_terms(ctx->side[0], ctx->side[1], core_energy, ctx->hubbard, norbs, nranks, ctx->am);
     ctx->terms_mine.clear();
     for (const Term& t : ctx->terms_all) if (t.owner == rank) ctx->terms_mine.push_back(t);
+    if (ctx->has_device) {   // materialise the device-allocated operators this rank's terms use
+      CU(cudaSetDevice(ctx->device));
+      std::vector<OpRec*> need;
+      size_t need_bytes = 0;
+      for (const Term& t : ctx->terms_mine) {
+        OpRec* used[2] = {&ctx->side[0].ops[t.lop], &ctx->side[1].ops[t.rop]};
+        for (OpRec* op : used) {
+          if (op->dev || op->dev_size == 0 || op->pending) continue;
+          op->pending = true;
+          need.push_back(op);
+          need_bytes += ((size_t)op->dev_size * 8 + 255) / 256 * 256;
+        }
+      }
+      if (need_bytes > 0) {   // one exact-size slab: at benchmark scale the arena is most of the GPU's memory
+        char* slab = nullptr;
+        CU(cudaMalloc(&slab, need_bytes));
+        ctx->slabs.push_back({slab, need_bytes, need_bytes});
+        CU(cudaMemsetAsync(slab, 0, need_bytes, ctx->stream));
+        size_t off = 0;
+        for (OpRec* op : need) {
+          op->dev = (double*)(slab + off);
+          op->pending = false;
+          off += ((size_t)op->dev_size * 8 + 255) / 256 * 256;
+          ctx->arena_doubles += op->dev_size;
+        }
+      }
+    }
     int64_t budget = (int64_t)(ctx->workspace_mb * 1024.0 * 1024.0 / 8.0);
     ctx->sched = build_schedule(ctx->side[0], ctx->side[1], ctx->psi, ctx->terms_mine, 0, budget, ctx->forced_class, ctx->am);
     if (nranks > 1) {
@@ -666,7 +715,7 @@ int b2d_tensor_multiply(b2d_ctx* ctx, int left_op, int right_op, int flags, int 
   if (left_op < 0 || right_op < 0 || left_op >= (int)ctx->side[0].ops.size() || right_op >= (int)ctx->side[1].ops.size())
     return fail(ctx, B2D_ERR_ARG, "b2d_tensor_multiply: operator id out of range (the one-operator form is not available yet)");
   if (src_slot == dst_slot) return fail(ctx, B2D_ERR_ARG, "b2d_tensor_multiply: src and dst must differ");
-  std::vector<Term> one(1, Term{left_op, right_op, (flags & 1) != 0, (flags & 2) != 0, scale, ctx->rank});
+  std::vector<Term> one(1, Term{left_op, right_op, (flags & 1) != 0, (flags & 2) != 0, scale, ctx->rank, TERM_PAIR});
   Schedule S;
   try {
     S = build_schedule(ctx->side[0], ctx->side[1], ctx->psi, one, opq_spin, (int64_t)1 << 60, ctx->forced_class, ctx->am);
@@ -686,7 +735,7 @@ int b2d_diagonal(b2d_ctx* ctx, int dst_slot) {
   std::vector<DiagTask> tasks;
   std::vector<int> begin;
   try {
-    build_diag_tasks(ctx->side[0], ctx->side[1], ctx->psi, ctx->terms_all, ctx->core_energy, ctx->hubbard, ctx->am, tasks, begin);
+    build_diag_tasks(ctx->side[0], ctx->side[1], ctx->psi, ctx->terms_mine, ctx->core_energy, ctx->hubbard, ctx->am, tasks, begin);
   } catch (const std::exception& e) { return fail(ctx, B2D_ERR_ARG, e.what()); }
   int rc = upload_desc(ctx, ctx->diag_tasks, tasks.data(), tasks.size() * sizeof(DiagTask));
   if (rc) return rc;
@@ -696,6 +745,8 @@ int b2d_diagonal(b2d_ctx* ctx, int dst_slot) {
   CU(cudaMemsetAsync(user_vec(ctx, dst_slot), 0, (size_t)ctx->psi.Wp * 8, ctx->stream));
   CU(launch_diag((const BlockDesc*)ctx->psi_blocks.p, ctx->psi.nblocks(), (const DiagTask*)ctx->diag_tasks.p, (const int*)ctx->diag_begin.p,
                  user_vec(ctx, dst_slot), ctx->stream, &ctx->launches));
+  rc = allreduce(ctx, user_vec(ctx, dst_slot), ctx->psi.Wp);   // every rank added the terms it owns
+  if (rc) return rc;
   end_timing(ctx);
   return B2D_OK;
 }
@@ -1084,14 +1135,19 @@ int b2d_transform_operators(b2d_ctx* ctx) {
       for (int b = 0; b < N.nq; ++b)
         r.allowed[(size_t)a * N.nq + b] = o.allowed[(size_t)ctx->rotated_old[a] * L.nq + ctx->rotated_old[b]];
     layout_op(N, r);
-    total += align_up(r.dev_size, 32);
+    if (o.dev) total += align_up(r.dev_size, 32);   // operators another rank holds are rotated there
     N.ops.push_back(std::move(r));
   }
   CU(ctx->rotated_arena.reserve((size_t)std::max<int64_t>(total, 16) * 8));
   CU(cudaMemsetAsync(ctx->rotated_arena.p, 0, ctx->rotated_arena.cap, ctx->stream));
   {
     int64_t off = 0;
-    for (OpRec& r : N.ops) { r.dev = (double*)ctx->rotated_arena.p + off; off += align_up(r.dev_size, 32); }
+    for (size_t m = 0; m < N.ops.size(); ++m) {
+      OpRec& r = N.ops[m];
+      if (!L.ops[m].dev) { r.dev = nullptr; continue; }
+      r.dev = (double*)ctx->rotated_arena.p + off;
+      off += align_up(r.dev_size, 32);
+    }
   }
   // schedule: step 1  tmp = O[Q,Q'] U_Q'   step 2  O'[a,b] = U_Q^T tmp     (MatrixRotate, MatrixBLAS.C:553-572)
   Schedule S;
@@ -1110,6 +1166,7 @@ int b2d_transform_operators(b2d_ctx* ctx) {
   for (size_t m = 0; m < L.ops.size(); ++m) {
     const OpRec& o = L.ops[m];
     const OpRec& r = N.ops[m];
+    if (!o.dev) continue;
     int64_t need = 0;
     for (int a = 0; a < N.nq; ++a)
       for (int b = 0; b < N.nq; ++b)
@@ -1181,6 +1238,7 @@ int b2d_rotated_op_download(b2d_ctx* ctx, int op_id, uint8_t* allowed, double* d
   const OpRec& op = N.ops[op_id];
   if (allowed) memcpy(allowed, op.allowed.data(), op.allowed.size());
   if (!data || op.packed_size == 0) return B2D_OK;
+  if (!op.dev) return fail(ctx, B2D_ERR_ARG, "b2d_rotated_op_download: operator is not resident on this rank");
   std::vector<BlockDesc> bd = op_blocks(N, op);
   CU(ctx->staging.reserve((size_t)op.packed_size * 8));
   int rc = upload_desc(ctx, ctx->desc_scratch, bd.data(), bd.size() * sizeof(BlockDesc));
@@ -1248,6 +1306,27 @@ int b2d_last_timing(b2d_ctx* ctx, double* out, int n) {
   CU(cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
   double v[4] = {ms, ctx->last_step_ms[0], ctx->last_step_ms[1], 0.0};
   for (int i = 0; i < n && i < 4; ++i) out[i] = v[i];
+  return B2D_OK;
+}
+int b2d_sigma_profile(b2d_ctx* ctx, int src_slot, int dst_slot, double* out) {
+  NEED_DEVICE(); NEED_PLAN(); CHECK_SLOT(src_slot); CHECK_SLOT(dst_slot);
+  if (!out || src_slot == dst_slot) return fail(ctx, B2D_ERR_ARG, "b2d_sigma_profile: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  const bool saved = ctx->phase_timing;
+  ctx->phase_timing = true;
+  int rc = sigma_dev(ctx, user_vec(ctx, src_slot), user_vec(ctx, dst_slot), false, false);
+  ctx->phase_timing = saved;
+  if (rc) return rc;
+  for (int st = 0; st < 2; ++st)
+    for (int c = 0; c < B2D_NUM_TILE_CLASSES; ++c) {
+      double fl = 0.0, pad = 0.0;
+      for (const Chunk& ch : ctx->sched.chunks) {
+        const GemmBatch& b = st == 0 ? ch.step1 : ch.step2;
+        fl += b.class_flops[c]; pad += b.class_padded[c];
+      }
+      double* o = out + (st * B2D_NUM_TILE_CLASSES + c) * 4;
+      o[0] = ctx->class_ms[st][c]; o[1] = fl; o[2] = pad; o[3] = ctx->class_launches[st][c];
+    }
   return B2D_OK;
 }
 int64_t b2d_kernel_launches(const b2d_ctx* ctx) { return ctx ? ctx->launches : -1; }

@@ -37,20 +37,23 @@ cudaError_t gemm_init() {
   return e;
 }
 
-cudaError_t launch_gemm_batch(const DevBatch& b, double* const* bases, cudaStream_t stream, int64_t* launches) {
+cudaError_t launch_gemm_class(const DevBatch& b, int cls, double* const* bases, cudaStream_t stream, int64_t* launches) {
+  if (b.ntiles[cls] <= 0) return cudaSuccess;
   Bases B;
   for (int i = 0; i < B2D_NUM_BASES; ++i) B.p[i] = bases[i];
-  if (b.ntiles[0] > 0) {
-    grouped_gemm_kernel<128, 128, 2, 4, STAGES0><<<b.ntiles[0], 256, smem_bytes(0), stream>>>(b.segs, b.groups, b.tiles[0], B);
-    B2D_LAUNCH_CHECK();
+  switch (cls) {
+    case 0: grouped_gemm_kernel<128, 128, 2, 4, STAGES0><<<b.ntiles[0], 256, smem_bytes(0), stream>>>(b.segs, b.groups, b.tiles[0], B); break;
+    case 1: grouped_gemm_kernel<64, 64, 2, 2, STAGES1><<<b.ntiles[1], 128, smem_bytes(1), stream>>>(b.segs, b.groups, b.tiles[1], B); break;
+    default: grouped_gemm_kernel<32, 32, 2, 2, STAGES2><<<b.ntiles[2], 128, smem_bytes(2), stream>>>(b.segs, b.groups, b.tiles[2], B); break;
   }
-  if (b.ntiles[1] > 0) {
-    grouped_gemm_kernel<64, 64, 2, 2, STAGES1><<<b.ntiles[1], 128, smem_bytes(1), stream>>>(b.segs, b.groups, b.tiles[1], B);
-    B2D_LAUNCH_CHECK();
-  }
-  if (b.ntiles[2] > 0) {
-    grouped_gemm_kernel<32, 32, 2, 2, STAGES2><<<b.ntiles[2], 128, smem_bytes(2), stream>>>(b.segs, b.groups, b.tiles[2], B);
-    B2D_LAUNCH_CHECK();
+  B2D_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+cudaError_t launch_gemm_batch(const DevBatch& b, double* const* bases, cudaStream_t stream, int64_t* launches) {
+  for (int c = 0; c < B2D_NUM_TILE_CLASSES; ++c) {
+    cudaError_t e = launch_gemm_class(b, c, bases, stream, launches);
+    if (e != cudaSuccess) return e;
   }
   return cudaSuccess;
 }

@@ -40,6 +40,7 @@ struct OpRec {
   int64_t packed_size = 0;        // host (reference) layout
   int64_t dev_size = 0;           // padded device layout
   double* dev = nullptr;
+  bool pending = false;           // selected for allocation by the current b2d_plan
 };
 
 struct Side {
@@ -126,7 +127,9 @@ struct Term {
   bool lt, rt;      // Transposeview flags
   double scale;
   int owner;        // rank that executes it
+  int kind;         // TERM_CORE / TERM_HAM_LEFT / TERM_HAM_RIGHT / TERM_PAIR
 };
+enum { TERM_CORE = 0, TERM_HAM_LEFT = 1, TERM_HAM_RIGHT = 2, TERM_PAIR = 3 };
 
 inline int tristore_2d(int i) { return i * (i + 1) / 2; }
 // para_array.h:360-383
@@ -173,16 +176,16 @@ inline std::vector<Term> enumerate_terms(const Side& L, const Side& R, double co
     Term t;
     if (other_is_left) { t.lop = op_other; t.lt = t_other; t.rop = op_loop; t.rt = t_loop; }
     else { t.lop = op_loop; t.lt = t_loop; t.rop = op_other; t.rt = t_other; }
-    t.scale = scale; t.owner = owner;
+    t.scale = scale; t.owner = owner; t.kind = TERM_PAIR;
     terms.push_back(t);
   };
   int none[2] = {-1, -1};
   int ovl_l = L.find(OP_OVERLAP, none, 0, 0), ovl_r = R.find(OP_OVERLAP, none, 0, 0);
   int ham_l = L.find(OP_HAM, none, 0, 0), ham_r = R.find(OP_HAM, none, 0, 0);
   if (ovl_l < 0 || ovl_r < 0 || ham_l < 0 || ham_r < 0) throw std::runtime_error("plan: both children need HAM and OVERLAP operators");
-  if (std::fabs(core_energy) > 1e-20) terms.push_back(Term{ovl_l, ovl_r, false, false, core_energy, 0});   // spinblock.C:735-740 (rank 0)
-  terms.push_back(Term{ham_l, ovl_r, false, false, 1.0, 0});                                              // :742-744
-  terms.push_back(Term{ovl_l, ham_r, false, false, 1.0, 0});                                              // :745-747
+  if (std::fabs(core_energy) > 1e-20) terms.push_back(Term{ovl_l, ovl_r, false, false, core_energy, 0, TERM_CORE});   // spinblock.C:735-740 (rank 0)
+  terms.push_back(Term{ham_l, ovl_r, false, false, 1.0, 0, TERM_HAM_LEFT});                                              // :742-744
+  terms.push_back(Term{ovl_l, ham_r, false, false, 1.0, 0, TERM_HAM_RIGHT});                                              // :745-747
 
   // c x ccd_comp, both directions (:757-763 -> opxop.C:232-285)
   for (int dir = 0; dir < 2; ++dir) {
@@ -251,6 +254,8 @@ struct GemmBatch {
   std::vector<GGroup> groups;
   std::vector<GTile> tiles[B2D_NUM_TILE_CLASSES];
   double flops = 0.0;
+  double class_flops[B2D_NUM_TILE_CLASSES] = {0, 0, 0};    // useful flops (2 m n k) executed by each tile class
+  double class_padded[B2D_NUM_TILE_CLASSES] = {0, 0, 0};   // flops the tiles issue (tile area x pipeline iterations x 16)
   bool empty() const { return groups.empty(); }
 };
 
@@ -265,7 +270,7 @@ inline int pick_tile_class(int m, int n, int forced) {
 // fills batch.tiles from batch.groups; tiles of a class are ordered by descending cost so the hardware's in-order
 // CTA dispatch approximates longest-processing-time scheduling over the 148 SMs
 inline void make_tiles(GemmBatch& b, int forced_class) {
-  for (int c = 0; c < B2D_NUM_TILE_CLASSES; ++c) b.tiles[c].clear();
+  for (int c = 0; c < B2D_NUM_TILE_CLASSES; ++c) { b.tiles[c].clear(); b.class_flops[c] = b.class_padded[c] = 0.0; }
   for (size_t g = 0; g < b.groups.size(); ++g) {
     GGroup& G = b.groups[g];
     int64_t ktot = 0;
@@ -274,6 +279,8 @@ inline void make_tiles(GemmBatch& b, int forced_class) {
     G.kiters = kiters;
     int c = pick_tile_class(G.m, G.n, forced_class);
     int bm = b2d_tile_m(c), bn = b2d_tile_n(c);
+    b.class_flops[c] += 2.0 * G.m * G.n * (double)ktot;
+    b.class_padded[c] += 2.0 * bm * bn * 16.0 * kiters * ((G.m + bm - 1) / bm) * ((G.n + bn - 1) / bn);
     for (int m0 = 0; m0 < G.m; m0 += bm)
       for (int n0 = 0; n0 < G.n; n0 += bn) {
         GTile t;
@@ -426,7 +433,7 @@ inline Schedule build_schedule(const Side& L, const Side& R, const PsiLayout& P,
 // ---------------------------------------------------------------------------------------------------------------
 // diag(H)
 // ---------------------------------------------------------------------------------------------------------------
-inline void build_diag_tasks(const Side& L, const Side& R, const PsiLayout& P, const std::vector<Term>& all_terms, double core_energy,
+inline void build_diag_tasks(const Side& L, const Side& R, const PsiLayout& P, const std::vector<Term>& terms, double core_energy,
                              bool hubbard, AngMom& am, std::vector<DiagTask>& tasks, std::vector<int>& block_begin) {
   // per psi block: list of (f, diagA, diagB).  The term list of diagonalH mirrors multiplyH's with the *_d functors
   // (opxop.C:295-365): same operator pairs, scale 1 for c x ccd, `factor` (no parity) for cc x dd; H and e_core by trace.
@@ -451,13 +458,13 @@ inline void build_diag_tasks(const Side& L, const Side& R, const PsiLayout& P, c
       per[p].push_back(d);
     }
   };
-  // all_terms is enumerate_terms() output: [e_core], H_L x 1, 1 x H_R, then the operator pairs
-  size_t i = 0;
-  if (std::fabs(core_energy) > 1e-20) ++i;               // handled as a constant below
-  add(all_terms[i], 1.0, true, false); ++i;              // TensorTrace(H_L)   spinblock.C:864
-  add(all_terms[i], 1.0, false, true); ++i;              // TensorTrace(H_R)   :867
-  for (; i < all_terms.size(); ++i) {
-    const Term& t = all_terms[i];
+  // `terms` is (this rank's share of) enumerate_terms() output; under a term partition every rank adds its own
+  // contributions and the caller all-reduces the result
+  bool have_core = false;
+  for (const Term& t : terms) {
+    if (t.kind == TERM_CORE) { have_core = true; continue; }    // handled as a constant below
+    if (t.kind == TERM_HAM_LEFT) { add(t, 1.0, true, false); continue; }    // TensorTrace(H_L)   spinblock.C:864
+    if (t.kind == TERM_HAM_RIGHT) { add(t, 1.0, false, true); continue; }   // TensorTrace(H_R)   :867
     const OpRec& lo = L.ops[t.lop];
     const OpRec& ro = R.ops[t.rop];
     double scale = 1.0;
@@ -472,7 +479,7 @@ inline void build_diag_tasks(const Side& L, const Side& R, const PsiLayout& P, c
   block_begin.assign(P.nblocks() + 1, 0);
   for (int p = 0; p < P.nblocks(); ++p) {
     block_begin[p] = (int)tasks.size();
-    if (core_energy != 0.0) {
+    if (have_core && core_energy != 0.0) {
       DiagTask d;
       std::memset(&d, 0, sizeof(d));
       d.f = core_energy;

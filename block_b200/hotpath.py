@@ -186,6 +186,11 @@ class SpinBlock:
         self._ck(self.lib.b2d_multiplyH_host(self._ctx, _p(c, _lib.c_f64p), _p(v, _lib.c_f64p), int(acc)))
         return v
 
+    def multiplyH_into(self, c, v, accumulate=False):
+        """multiplyH with caller-owned host buffers (pinned buffers make the copies true DMA): v (+)= H c."""
+        assert c.size == self.size and v.size == self.size and c.flags.c_contiguous and v.flags.c_contiguous
+        self._ck(self.lib.b2d_multiplyH_host(self._ctx, _p(c, _lib.c_f64p), _p(v, _lib.c_f64p), int(accumulate)))
+
     def sigma(self, src_slot, dst_slot, accumulate=False):
         """multiplyH on device-resident slots (what block_davidson uses internally)."""
         self._ck(self.lib.b2d_sigma(self._ctx, src_slot, dst_slot, int(accumulate)))
@@ -310,6 +315,13 @@ class SpinBlock:
         out = np.zeros(4)
         self._ck(self.lib.b2d_last_timing(self._ctx, _p(out, _lib.c_f64p), 4))
         return out
+
+    def sigma_profile(self, src_slot, dst_slot):
+        """One multiplyH with events around every contraction launch: dict[(step, tile_class)] -> (ms, useful flops,
+        issued flops, launches)."""
+        out = np.zeros(24)
+        self._ck(self.lib.b2d_sigma_profile(self._ctx, src_slot, dst_slot, _p(out, _lib.c_f64p)))
+        return {(st, c): tuple(out[(st * 3 + c) * 4:(st * 3 + c) * 4 + 4]) for st in range(2) for c in range(3)}
 
     def kernel_launches(self):
         return int(self.lib.b2d_kernel_launches(self._ctx))

@@ -1,0 +1,146 @@
+"""Synthetic `big` blocks of the shape BASELINE.json names ("synthetic random-integral FCIDUMP, 40 orbitals /
+40 electrons, M=4000"): the sector tables and operator arrays a two-dot block iteration of the reference hands to
+SpinBlock::multiplyH / RenormaliseFrom, without running the (out-of-scope) block construction.
+
+What is modelled after the reference (file:line under the reference root):
+  * a renormalised block of n sites keeps M states spread over (N, 2S) sectors (StateInfo.h:113-147); the
+    enlarged block is (renormalised block) x (one site: (0,0), (1,1), (2,0)), quanta collected and sorted by
+    (N, 2S, irrep) (StateInfo.C TensorProduct + CollectQuanta, SpinQuantum operator<);
+  * the operator arrays a block carries in the energy sweep (set_spinblock_components.C:490-560): HAM, OVERLAP,
+    CRE_i for its own sites, CRE_CRE_DESCOMP_i for the other block's sites; the loop block carries CRE_DES_ij /
+    CRE_CRE_ij (i >= j own sites, spin components S = 0, 1: op_components.C:172-184), the other block the matching
+    CRE_DESCOMP_ij / DES_DESCOMP_ij;
+  * an operator block (i, j) is allocated iff q_i is in deltaQuantum x q_j (SparseMatrix::allocate,
+    BaseOperator.C:123-145); C1 symmetry (ORBSYM all 1), so irreps are 0 throughout.
+Operator VALUES are counter-based random numbers filled on the device (b2d_fill_op_random): sigma throughput does
+not depend on them, and HAM is made self-adjoint so that Davidson runs on a symmetric matrix.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from .hotpath import BlockSpec, OperatorSpec, SpinBlock
+
+HAM, CRE, CRE_CRE, DES_DESCOMP, CRE_DES, CRE_DESCOMP, CRE_CRE_DESCOMP, OVERLAP = 0, 1, 2, 3, 4, 5, 6, 13
+
+
+def csf_count(n, N, twoS):
+    """Number of spin-adapted configurations of N electrons in n orbitals with spin S (Weyl's formula): the cap on
+    a sector's size."""
+    if N < 0 or N > 2 * n or twoS < 0 or (N - twoS) % 2 or twoS > min(N, 2 * n - N):
+        return 0
+    a = (N - twoS) // 2
+    b = (N + twoS) // 2 + 1
+    return (twoS + 1) * math.comb(n + 1, a) * math.comb(n + 1, b) // (n + 1)
+
+
+def renormalised_sectors(nsites, nelec_mean, M, sigma_n=2.2, sigma_s=1.6):
+    """{(N, 2S): states} of a renormalised block: Gaussian in N around the mean filling, (2S+1) exp(-S(S+1)/2s^2) in
+    spin, scaled so that the sectors add up to M (every populated sector keeps >= 1 state: the long tail of tiny
+    sectors is what makes the contraction ragged)."""
+    w = {}
+    for N in range(0, 2 * nsites + 1):
+        for twoS in range(N % 2, min(N, 2 * nsites - N) + 1, 2):
+            cap = csf_count(nsites, N, twoS)
+            if cap == 0:
+                continue
+            S = 0.5 * twoS
+            w[(N, twoS)] = (math.exp(-0.5 * ((N - nelec_mean) / sigma_n) ** 2) * (twoS + 1) * math.exp(-0.5 * S * (S + 1) / sigma_s ** 2), cap)
+    tot = sum(v[0] for v in w.values())
+    scale = M / tot
+    for _ in range(40):   # fixed point: sectors that round to 0 drop out, capped sectors give their share back
+        dims = {k: min(cap, int(round(scale * x))) for k, (x, cap) in w.items()}
+        got = sum(dims.values())
+        if got == M:
+            break
+        scale *= M / max(got, 1)
+    dims = {k: d for k, d in dims.items() if d > 0}
+    # exact total: adjust the largest sector
+    kmax = max(dims, key=dims.get)
+    dims[kmax] += M - sum(dims.values())
+    return dims
+
+
+def add_dot(sectors):
+    """(block) x (one site), quanta collected: dims of the enlarged block, sorted by (N, 2S)."""
+    out = {}
+    for (N, s), d in sectors.items():
+        for (dn, ds) in ((0, 0), (1, 1), (2, 0)):
+            for s2 in ([s] if ds == 0 else [s - 1, s + 1]):
+                if s2 < 0:
+                    continue
+                out[(N + dn, s2)] = out.get((N + dn, s2), 0) + d
+    return dict(sorted(out.items()))
+
+
+def allowed_mask(q, dq):
+    """SparseMatrix::allocate (BaseOperator.C:123-145): block (i, j) exists iff q_i is in dq x q_j."""
+    N, S = q[:, 0], q[:, 1]
+    ok_n = N[:, None] == N[None, :] + dq[0]
+    ok_s = (np.abs(S[None, :] - dq[1]) <= S[:, None]) & (S[:, None] <= S[None, :] + dq[1]) & ((S[:, None] + S[None, :] + dq[1]) % 2 == 0)
+    return (ok_n & ok_s).astype(np.uint8)
+
+
+def _op(q, optype, orbs, comp, dq, fermion):
+    return OperatorSpec(optype=optype, orbs=tuple(orbs), comp=comp, dq=tuple(dq), fermion=fermion, allowed=allowed_mask(q, dq), data=None)
+
+
+def make_block(sectors, sites, other_sites, loop):
+    q = np.array([[N, s, 0] for (N, s) in sectors], dtype=np.int32)
+    dims = np.array(list(sectors.values()), dtype=np.int32)
+    blk = BlockSpec(q=q, dims=dims, sites=tuple(sites), loop=loop)
+    blk.ops.append(_op(q, HAM, (), 0, (0, 0, 0), False))
+    ovl = _op(q, OVERLAP, (), 0, (0, 0, 0), False)       # the identity: diagonal blocks only
+    ovl.data = np.concatenate([np.eye(int(d)).ravel() for d in dims])
+    blk.ops.append(ovl)
+    for i in sites:
+        blk.ops.append(_op(q, CRE, (i,), 0, (1, 1, 0), True))
+    for i in other_sites:
+        blk.ops.append(_op(q, CRE_CRE_DESCOMP, (i,), 0, (1, 1, 0), True))
+    pair_sites = sites if loop else other_sites
+    for a, i in enumerate(pair_sites):
+        for j in pair_sites[:a + 1]:
+            for comp, s in ((0, 0), (1, 2)):
+                if loop:
+                    blk.ops.append(_op(q, CRE_DES, (i, j), comp, (0, s, 0), False))
+                    blk.ops.append(_op(q, CRE_CRE, (i, j), comp, (2, s, 0), False))
+                else:
+                    blk.ops.append(_op(q, CRE_DESCOMP, (i, j), comp, (0, s, 0), False))
+                    blk.ops.append(_op(q, DES_DESCOMP, (i, j), comp, (-2, s, 0), False))
+    return blk
+
+
+def make_big_block(norbs=40, nelec=40, M=4000, left_sites=None, device=0, rank=0, nranks=1, options=None, seed=20260, fill=True,
+                   sigma_n=2.2, sigma_s=1.6):
+    """The big block of the block iteration with `left_sites` orbitals on the left (default: the middle of the
+    chain), both children enlarged blocks of renormalised M-state blocks.  The left child is the loop block.
+    device = -1 gives a planning-only context (flop / memory accounting on a CPU)."""
+    nl = norbs // 2 if left_sites is None else left_sites
+    nr = norbs - nl
+    filling = nelec / norbs
+    L = add_dot(renormalised_sectors(nl - 1, filling * (nl - 1), M, sigma_n, sigma_s))
+    R = add_dot(renormalised_sectors(nr - 1, filling * (nr - 1), M, sigma_n, sigma_s))
+    # only sectors that can pair up to the target (nelec, S = 0) survive in a converged calculation
+    L = {k: d for k, d in L.items() if (nelec - k[0], k[1]) in R}
+    R = {k: d for k, d in R.items() if (nelec - k[0], k[1]) in L}
+    lsites, rsites = list(range(nl)), list(range(nl, norbs))
+    left = make_block(L, lsites, rsites, loop=True)
+    right = make_block(R, rsites, lsites, loop=False)
+    sb = SpinBlock(left, right, (nelec, 0, 0), core_energy=0.0, hubbard=False, norbs=norbs, device=device, rank=rank, nranks=nranks, options=options)
+    if fill and device >= 0:
+        fill_random(sb, seed, rank, nranks)
+    return sb
+
+
+def fill_random(sb: SpinBlock, seed, rank=0, nranks=1):
+    """Counter-based random operator values on the device; amplitudes ~ 1/sqrt(dimension) keep sigma O(1).
+    Only operators this rank's terms touch need values, but filling all keeps ranks identical."""
+    for side, blk in enumerate((sb.left, sb.right)):
+        amp = 1.0 / math.sqrt(float(np.sum(blk.dims)))
+        for k, op in enumerate(blk.ops):
+            if op.data is not None:
+                continue
+            sym = op.optype == HAM
+            sb.fill_op_random(side, sb.op_ids[side][k], seed * 1000003 + side * 500009 + k, amplitude=amp * (4.0 if sym else 1.0), symmetric=sym)

@@ -206,6 +206,11 @@ int b2d_allreduce_slot(b2d_ctx* ctx, int slot);
 /* CUDA-event time (ms) of the last b2d_sigma / b2d_davidson / b2d_make_density / b2d_transform_operators call on
  * the context's stream: out[0] = total, out[1] = step-1 kernels, out[2] = step-2 kernels, out[3] = collective. */
 int b2d_last_timing(b2d_ctx* ctx, double* out, int n);
+/* One multiplyH (this rank's terms, no collective) with CUDA events around every launch of the grouped contraction
+ * kernel.  out[(step * 3 + tile_class) * 4 + {0,1,2,3}] = {summed kernel ms, useful flops (2mnk) executed, flops the
+ * tiles issue including ragged-edge padding, number of launches}; step 0 = T = A_L psi (operatorfunctions.C:512-516),
+ * step 1 = sigma += F T A_R^T (:517-531); tile classes 128x128, 64x64, 32x32.  24 doubles. */
+int b2d_sigma_profile(b2d_ctx* ctx, int src_slot, int dst_slot, double* out);
 int64_t b2d_kernel_launches(const b2d_ctx* ctx);     /* kernels launched by this context so far */
 int b2d_sync(b2d_ctx* ctx);
 void* b2d_stream(b2d_ctx* ctx);                      /* cudaStream_t, for event timing by the caller */

@@ -106,9 +106,6 @@ def cpu_sigma_sample(a, budget_s=8.0, max_terms=64):
     return flops[0] / secs / 1e9, cores, desc, secs, flops[0]
 
 
-REF_BENCH = os.path.join(ROOT, "oracle", "_ref", "ref_bench")
-
-
 def _oracle_big(a):
     """The synthetic big block as oracle objects (operator blocks lazily random) and its multiplyH term list."""
     from block_b200 import synthetic as S
@@ -142,47 +139,54 @@ def cpu_sigma_reference(a, budget_s=10.0, max_terms=48, state={}):
     objects compiled by oracle/Makefile, OpenMP over operator terms with single-threaded OpenBLAS dgemm inside, exactly how
     multiplyH parallelises: operatorloops.h:87-97) on an evenly spaced sample of the SAME multiplyH's term list.
     Returns (GFLOP/s, cores, description, seconds, flops)."""
-    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    from oracle import refbench
+    cores = refbench.host_cores()
     if "terms" not in state:
         state["big"], state["terms"] = _oracle_big(a)
     big, terms = state["big"], state["terms"]
-
-    def run(indices):
-        with tempfile.NamedTemporaryFile("w", suffix=".spec", delete=False) as f:
-            for blk in (big.left, big.right):
-                f.write("%d\n" % len(blk.dims))
-                for q, d in zip(blk.q, blk.dims):
-                    f.write("%d %d %d\n" % (q[0], q[1], d))
-            f.write("%d %d\n%d\n" % (big.psi_dq[0], big.psi_dq[1], len(indices)))
-            for i in indices:
-                lop, rop, scale = terms[i]
-                f.write("%d %d %d %d  %d %d %d %d  %.17g\n" % (lop.op.dq[0], lop.op.dq[1], int(lop.op.fermion), int(lop.t),
-                                                              rop.op.dq[0], rop.op.dq[1], int(rop.op.fermion), int(rop.t), scale))
-            path = f.name
-        env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS=str(cores))
-        out = subprocess.run([REF_BENCH, path, "1", str(cores)], env=env, capture_output=True, text=True, timeout=1200)
-        os.unlink(path)
-        for ln in out.stdout.splitlines():
-            if ln.startswith("REFBENCH"):
-                kv = dict(x.split("=") for x in ln.split()[1:])
-                return float(kv["seconds"]), float(kv["flops"])
-        raise RuntimeError("ref_bench failed: " + out.stderr[-400:])
-
     order = _sample_order(len(terms), max_terms)
     if "rate" not in state:                       # calibrate on one term per core
-        s0, f0 = run(order[:max(cores, 2)])
-        state["rate"] = f0 / s0
-    per_term = sum(1 for _ in order) and (5.8e13 * (a.M / 4000.0) ** 3 / len(terms))
-    n = int(min(len(order), max(cores, budget_s * state["rate"] / max(per_term, 1.0))))
+        s0, f0, _ = refbench.run(big, terms, order[:max(cores, 2)], cores)
+        state["rate"], state["per_term"] = f0 / s0, f0 / max(cores, 2)
+    n = int(min(len(order), max(cores, budget_s * state["rate"] / state["per_term"])))
     n = max(cores, n - n % cores) if n >= cores else n
-    secs, flops = run(order[:n])
+    secs, flops, _ = refbench.run(big, terms, order[:n], cores)
     desc = ("%d of %d TensorMultiply terms of the same multiplyH (evenly spaced over the term list) through the unmodified reference's "
             "operatorfunctions::TensorMultiply, OpenMP over terms x %d threads, OpenBLAS 0.3.15 dgemm single-threaded inside, %.1f s" % (n, len(terms), cores, secs))
     return flops / secs / 1e9, cores, desc, secs, flops
 
 
+def reference_parity(sb, a, psi, nterms=6):
+    """Full-size parity against the REAL reference: the sum of `nterms` sampled operator-pair terms of multiplyH computed
+    by the GPU (b2d_tensor_multiply through the C ABI) and by the unmodified reference's TensorMultiply (ref_bench) on
+    identical operator values (shared counter-based stream) and the same psi.  Returns (relative error, #terms)."""
+    from block_b200 import synthetic as S
+    from oracle import refbench
+    big, terms = _oracle_big(a)
+    pair_terms = [i for i in range(len(terms)) if terms[i][0].op.optype not in (S.HAM, S.OVERLAP) and terms[i][1].op.optype not in (S.HAM, S.OVERLAP)]
+    pick = [pair_terms[int(j)] for j in np.unique(np.linspace(0, len(pair_terms) - 1, nterms).astype(int))]
+    fills, calls = {}, []
+    for i in pick:
+        lop, rop, scale = terms[i]
+        kl = next(k for k, o in enumerate(big.left.ops) if o is lop.op)
+        kr = next(k for k, o in enumerate(big.right.ops) if o is rop.op)
+        ls, la = S.fill_params(big.left.dims, 0, kl, lop.op.optype, sb.fill_seed)
+        rs, ra = S.fill_params(big.right.dims, 1, kr, rop.op.optype, sb.fill_seed)
+        fills[i] = (ls, la, rs, ra)
+        calls.append((sb.op_ids[0][kl], sb.op_ids[1][kr], lop.t, rop.t, scale))
+    _, _, ref = refbench.run(big, terms, pick, fills=fills, psi=psi)
+    sb.reserve(3)
+    sb.upload(0, psi)
+    sb.clear(1)
+    for (lo, ro, lt, rt, scale) in calls:
+        sb.tensor_multiply_slots(lo, ro, lt, rt, 0, scale, 0, 1)
+    got = sb.download(1)
+    return float(np.linalg.norm(got - ref) / np.linalg.norm(ref)), len(pick)
+
+
 def cpu_leg(a, budget_s):
-    if os.path.exists(REF_BENCH):
+    from oracle import refbench
+    if refbench.available():
         return ("reference",) + cpu_sigma_reference(a, budget_s)
     return ("port",) + cpu_sigma_sample(a, budget_s)
 
@@ -323,14 +327,25 @@ def run_ours(a):
         sb.close()
         return
 
-    # size-independent parity properties at full size (the oracle cannot run this size): symmetry <x|Hy> = <y|Hx>
+    # parity at full size (the numpy oracle cannot run this size): (1) linearity H(2x - 3y) = 2Hx - 3Hy,
+    # (2) a sample of operator-pair terms against the REAL reference's TensorMultiply on identical inputs
     y = rng.standard_normal(W); y /= np.linalg.norm(y)
     sb.upload(2, y)
     sb.sigma(0, 1)
     hx = sb.download(1)
     sb.sigma(2, 1)
     hy = sb.download(1)
-    sym_err = abs(float(np.dot(psi, hy) - np.dot(y, hx))) / (np.linalg.norm(hx) * np.linalg.norm(y))
+    sb.upload(2, 2.0 * psi - 3.0 * y)
+    sb.sigma(2, 1)
+    lin_err = float(np.linalg.norm(sb.download(1) - (2.0 * hx - 3.0 * hy)) / np.linalg.norm(2.0 * hx - 3.0 * hy))
+    parity = {"linearity_rel": lin_err}
+    if world == 1 and not a.no_cpu:
+        from oracle import refbench
+        if refbench.available():
+            err, nt = reference_parity(sb, a, psi)
+            parity["vs_reference_TensorMultiply_rel"] = err
+            parity["vs_reference_terms"] = nt
+        sb.upload(0, psi)
 
     for _ in range(a.warmup):
         sb.sigma(0, 1)
@@ -356,7 +371,7 @@ def run_ours(a):
     if world > 1:
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
     e2e_value = flops_alg / (float(e2e_s.item()) / a.steps) / 1e9
-    e2e_err = float(np.linalg.norm(sigp - hx) / np.linalg.norm(hx))
+    parity["e2e_vs_resident_rel"] = float(np.linalg.norm(sigp - hx) / np.linalg.norm(hx))
 
     line = None
     if rank == 0 or world == 1:
@@ -370,11 +385,11 @@ def run_ours(a):
         tot_ms = sum(v[0] for v in prof.values())
         achieved = k_fl / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
         roof = {"bound": "tensor", "achieved": achieved, "peak": dmma, "unit": "TFLOP/s", "frac": achieved / dmma if dmma else None, "traffic": None,
-                "kernel": "grouped_gemm_kernel<128,128,2,4,4> (FP64 DMMA m16n8k8)", "launches": int(k_n), "avg_launch_ms": k_ms / max(k_n, 1),
+                "kernel": "grouped_gemm_kernel<128,128,*> (FP64 DMMA m16n8k8, 16 warps x 32x32)", "launches": int(k_n), "avg_launch_ms": k_ms / max(k_n, 1),
                 "share_of_sigma": k_ms / tot_ms if tot_ms else None, "tile_fill": k_fl / k_pad if k_pad else None,
                 "peak_source": "live FP64 DMMA register-loop yardstick of this library on this GPU (MEASURED_PEAKS.json has no FP64 entry); DFMA loop %.1f TFLOP/s" % dfma,
-                "per_class": {"step%d_class%d" % (st + 1, c): {"ms": v[0], "tflops": (v[1] / (v[0] * 1e-3) / 1e12 if v[0] > 0 else 0.0), "tile_fill": (v[1] / v[2] if v[2] else None),
-                                                               "launches": int(v[3])} for (st, c), v in prof.items()}}
+                "per_class": {"step%d_%dx%d" % (st + 1, 128 >> (c // 3), 128 >> (c % 3)): {"ms": v[0], "tflops": (v[1] / (v[0] * 1e-3) / 1e12 if v[0] > 0 else 0.0), "tile_fill": (v[1] / v[2] if v[2] else None),
+                                                               "launches": int(v[3])} for (st, c), v in prof.items() if v[3] > 0}}
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -390,9 +405,9 @@ def run_ours(a):
                            "l2": "inputs larger than L2 (operator arena %.0f GB per step)" % (stats["arena_doubles"] * 8 / 1e9), "setup_s": t_setup},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(W * 8), "d2h_bytes_per_step": int(W * 8)},
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roof,
-                "parity": {"hermiticity_rel": sym_err, "e2e_vs_resident_rel": e2e_err},
+                "parity": parity,
                 "hbm_peak_gbs": peaks.get("hbm_gbs")}
-    if (rank == 0 or world == 1) and not a.no_cpu and world == 1:
+    if line is not None and not a.no_cpu and world == 1:
         kind, v, cores, desc, _, _ = cpu_leg(a, a.cpu_budget_s)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}
     if line is not None:

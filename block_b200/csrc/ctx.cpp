@@ -79,6 +79,9 @@ struct b2d_ctx {
   int device = -1;
   bool has_device = false;
   cudaStream_t stream = nullptr;
+  cudaStream_t side_streams[B2D_NUM_TILE_CLASSES - 1] = {};   // one per tile class beyond the first (run_schedule)
+  cudaEvent_t fork_ev = nullptr, join_ev[B2D_NUM_TILE_CLASSES - 1] = {};
+  bool multi_stream = true;
   std::string err;
   AngMom am;
 
@@ -138,8 +141,8 @@ struct b2d_ctx {
   std::vector<cudaEvent_t> phase_events;
   bool phase_timing = false;
   double last_step_ms[2] = {0, 0};
-  double class_ms[2][B2D_NUM_TILE_CLASSES] = {{0, 0, 0}, {0, 0, 0}};
-  int class_launches[2][B2D_NUM_TILE_CLASSES] = {{0, 0, 0}, {0, 0, 0}};
+  double class_ms[2][B2D_NUM_TILE_CLASSES] = {};
+  int class_launches[2][B2D_NUM_TILE_CLASSES] = {};
 
   Nccl nccl;
 };
@@ -238,6 +241,7 @@ int upload_schedule(b2d_ctx* ctx, const Schedule& S, DevSchedule& D) {
     d.segs = (const GSeg*)(base + o.segs);
     d.groups = (const GGroup*)(base + o.groups);
     for (int c = 0; c < B2D_NUM_TILE_CLASSES; ++c) { d.tiles[c] = (const GTile*)(base + o.tiles[c]); d.ntiles[c] = (int)b.tiles[c].size(); }
+    d.unit_alpha = b.unit_alpha;
     return d;
   };
   D.chunks.resize(S.chunks.size());
@@ -251,9 +255,36 @@ int run_schedule(b2d_ctx* ctx, const Schedule& S, const DevSchedule& D, double* 
   CU(ctx->work.reserve((size_t)std::max<int64_t>(S.work_max, 16) * 8));
   double* bases[B2D_NUM_BASES] = {nullptr, src, (double*)ctx->work.p, dst, aux};
   if (!ctx->phase_timing) {
+    // The tile classes of one step are independent: the first non-empty class stays on the main stream, the others
+    // are forked onto side streams so that their CTAs fill the SMs the main launch leaves idle in its tail.
+    auto run_batch = [&](const DevBatch& b) -> int {
+      int first = -1;
+      for (int c = 0; c < B2D_NUM_TILE_CLASSES; ++c) if (b.ntiles[c] > 0) { first = c; break; }
+      if (first < 0) return B2D_OK;
+      bool forked = false;
+      if (ctx->multi_stream) {
+        for (int c = first + 1; c < B2D_NUM_TILE_CLASSES; ++c) {
+          if (b.ntiles[c] <= 0) continue;
+          if (!forked) { CU(cudaEventRecord(ctx->fork_ev, ctx->stream)); forked = true; }
+          cudaStream_t side = ctx->side_streams[c - 1];
+          CU(cudaStreamWaitEvent(side, ctx->fork_ev, 0));
+          CU(launch_gemm_class(b, c, bases, side, &ctx->launches));
+          CU(cudaEventRecord(ctx->join_ev[c - 1], side));
+        }
+      }
+      CU(launch_gemm_class(b, first, bases, ctx->stream, &ctx->launches));
+      for (int c = first + 1; c < B2D_NUM_TILE_CLASSES; ++c) {
+        if (b.ntiles[c] <= 0) continue;
+        if (ctx->multi_stream) CU(cudaStreamWaitEvent(ctx->stream, ctx->join_ev[c - 1], 0));
+        else CU(launch_gemm_class(b, c, bases, ctx->stream, &ctx->launches));
+      }
+      return B2D_OK;
+    };
     for (size_t i = 0; i < D.chunks.size(); ++i) {
-      CU(launch_gemm_batch(D.chunks[i].s1, bases, ctx->stream, &ctx->launches));
-      CU(launch_gemm_batch(D.chunks[i].s2, bases, ctx->stream, &ctx->launches));
+      int rc = run_batch(D.chunks[i].s1);
+      if (rc) return rc;
+      rc = run_batch(D.chunks[i].s2);
+      if (rc) return rc;
       if (ctx->sync_debug) CU(cudaStreamSynchronize(ctx->stream));
     }
     return B2D_OK;
@@ -333,6 +364,9 @@ int b2d_create(int device, b2d_ctx** out) {
     c->has_device = true;
     CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
     for (auto& ev : c->ev) CU(cudaEventCreate(&ev));
+    for (auto& st : c->side_streams) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    CU(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
+    for (auto& ev : c->join_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CU(gemm_init());
     CU(cudaMallocHost(&c->h_pinned, 64 * sizeof(double)));
     CU(c->partials.reserve((size_t)L1_MAX_BLOCKS * L1_MAX_VECS * 8));
@@ -357,6 +391,9 @@ void b2d_destroy(b2d_ctx* ctx) {
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->phase_events) cudaEventDestroy(ev);
+    for (auto& st : ctx->side_streams) if (st) cudaStreamDestroy(st);
+    if (ctx->fork_ev) cudaEventDestroy(ctx->fork_ev);
+    for (auto& ev : ctx->join_ev) if (ev) cudaEventDestroy(ev);
     cudaStreamDestroy(ctx->stream);
   }
   delete ctx;
@@ -369,8 +406,9 @@ int b2d_set_option(b2d_ctx* ctx, const char* key, double value) {
   std::string k(key);
   if (k == "workspace_mb") ctx->workspace_mb = value;
   else if (k == "max_davidson_iter") ctx->max_davidson_iter = (int)value;
-  else if (k == "tile_class") ctx->forced_class = (int)value;
+  else if (k == "tile_class") ctx->forced_class = (int)value;   // -1 auto, 0/1/2: square 128/64/32 tiles everywhere
   else if (k == "sync_debug") ctx->sync_debug = value != 0;
+  else if (k == "multi_stream") ctx->multi_stream = value != 0;
   else if (k == "phase_timing") ctx->phase_timing = value != 0;
   else return fail(ctx, B2D_ERR_ARG, "unknown option " + k);
   return B2D_OK;
@@ -587,9 +625,15 @@ int b2d_plan_stats(const b2d_ctx* ctx, double* out, int n) {
   int launches = 0;
   for (const Chunk& c : ctx->sched.chunks)
     for (int k = 0; k < B2D_NUM_TILE_CLASSES; ++k) launches += (c.step1.tiles[k].empty() ? 0 : 1) + (c.step2.tiles[k].empty() ? 0 : 1);
-  double v[8] = {(double)ctx->sched.chunks.size(), (double)ctx->sched.n_step1, (double)ctx->sched.n_step2, (double)ctx->sched.n_tiles,
-                 (double)ctx->sched.work_max, (double)ctx->arena_doubles, (double)launches, ctx->sched.flops_exec};
-  for (int i = 0; i < n && i < 8; ++i) out[i] = v[i];
+  double useful = 0.0, issued = 0.0;
+  for (const Chunk& c : ctx->sched.chunks)
+    for (int k = 0; k < B2D_NUM_TILE_CLASSES; ++k) {
+      useful += c.step1.class_flops[k] + c.step2.class_flops[k];
+      issued += c.step1.class_padded[k] + c.step2.class_padded[k];
+    }
+  double v[10] = {(double)ctx->sched.chunks.size(), (double)ctx->sched.n_step1, (double)ctx->sched.n_step2, (double)ctx->sched.n_tiles,
+                  (double)ctx->sched.work_max, (double)ctx->arena_doubles, (double)launches, ctx->sched.flops_exec, useful, issued};
+  for (int i = 0; i < n && i < 10; ++i) out[i] = v[i];
   return B2D_OK;
 }
 

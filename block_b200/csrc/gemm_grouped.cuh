@@ -3,7 +3,7 @@
 // Every dense step of the DMRG hot path is an instance of
 //        C_g (m_g x n_g)  (+)=  sum_{s in segs(g)}  alpha_s * op(A_s) (m_g x k_s) * op(B_s) (k_s x n_g)
 // with thousands of ragged (m, n, k) per launch:
-//   sigma step 1   T = s A_L psi                         (one segment per group)          operatorfunctions.C:512-516
+//   sigma step 1   T = A_L psi                            (one segment per group)          operatorfunctions.C:512-516
 //   sigma step 2   sigma[lQ,rQ] += sum F T A_R^T          (hundreds of segments per group)  operatorfunctions.C:517-531
 //   density        rho[q] = sum w psi[q,r] psi[q,r]^T                                      operatorfunctions.C:630-650
 //   rotation       O' = U^T (O U)                                                          MatrixBLAS.C:553-572
@@ -11,13 +11,20 @@
 //
 // Design (B200):
 //   * FP64 has no tcgen05 path: the tensor-pipe instruction for doubles is the warp-level DMMA
-//     mma.sync.aligned.m16n8k8.f64, accumulators in registers.
-//   * one CTA per output tile (tile lists are cost-sorted on the host: in-order CTA dispatch ~ LPT over the SMs);
-//     three tile classes 128x128 / 64x64 / 32x32 so that tiny quantum-number sectors do not pay for big tiles.
+//     (mma.sync.aligned.m16n8k8.f64, four DMMA.8x8x4 in SASS), accumulators in registers.  Measured on B200: the
+//     pipe retires one DMMA.8x8x4 per 16 clocks per SM sub-partition (37.1 TFLOP/s) and one warp per sub-partition
+//     with >= 2 independent accumulators already saturates it - so the kernel is organised to keep FOUR warps per
+//     sub-partition issuing DMMAs (16 warps on a 128x128 tile, 32x32 per warp, 64 accumulator registers) so that
+//     fragment loads, address arithmetic and barriers of one warp hide under the DMMAs of the others.
+//   * one CTA per output tile; nine tile classes {128,64,32} x {128,64,32}: a ragged sector is covered by 128-wide
+//     bands plus ONE narrower band for the remainder, so the tensor pipe is not fed padding (tile lists are cost-sorted
+//     on the host: in-order CTA dispatch ~ longest-processing-time-first over the 148 SMs).
 //   * the K loop runs over ALL segments of the group back to back through one multi-stage cp.async (LDGSTS.128)
 //     pipeline: a 5-row segment and a 900-row segment cost what their K says, no per-segment pipeline drain.
 //   * operands may be stored K-major or M/N-major (Transposeview operators are never materialised); shared-memory
-//     tiles keep the global orientation and are padded so the DMMA fragment reads are bank-conflict free in both.
+//     tiles keep the global orientation, padded so the DMMA fragment reads are bank-conflict free in both; the
+//     orientation is resolved ONCE per pipeline stage into one of four fully unrolled code paths with compile-time
+//     strides (no per-fragment address multiplies).
 //   * ragged edges are zero-filled by cp.async's src-size operand: no scalar tail loops.
 #pragma once
 #include <cuda_runtime.h>
@@ -32,6 +39,7 @@ struct Bases {
 };
 
 constexpr int GEMM_BK = 16;
+constexpr int GEMM_PAD = 4;
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -45,34 +53,30 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 //   a0 (g, t)  a1 (g+8, t)  a2 (g, t+4)  a3 (g+8, t+4);   b0 (k=t, n=g)  b1 (k=t+4, n=g);
 //   c0 (g, 2t) c1 (g, 2t+1) c2 (g+8, 2t) c3 (g+8, 2t+1)
 __device__ __forceinline__ void dmma_16x8x8(double (&c)[4], const double (&a)[4], const double (&b)[2]) {
-#ifndef B2D_MMA_884
   asm volatile(
       "mma.sync.aligned.m16n8k8.row.col.f64.f64.f64.f64 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
       : "+d"(c[0]), "+d"(c[1]), "+d"(c[2]), "+d"(c[3])
       : "d"(a[0]), "d"(a[1]), "d"(a[2]), "d"(a[3]), "d"(b[0]), "d"(b[1]));
-#else
-  // the same product out of four m8n8k4 DMMAs (sm_80 shape); kept as a cross-check of the fragment mapping
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c[0]), "+d"(c[1]) : "d"(a[0]), "d"(b[0]));
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c[0]), "+d"(c[1]) : "d"(a[2]), "d"(b[1]));
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c[2]), "+d"(c[3]) : "d"(a[1]), "d"(b[0]));
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n" : "+d"(c[2]), "+d"(c[3]) : "d"(a[3]), "d"(b[1]));
-#endif
 }
 
 template <int BM, int BN>
-struct TileSmem {
-  static constexpr int A_DOUBLES = (BM * (GEMM_BK + 4) > GEMM_BK * (BM + 4)) ? BM * (GEMM_BK + 4) : GEMM_BK * (BM + 4);
-  static constexpr int B_DOUBLES = (BN * (GEMM_BK + 4) > GEMM_BK * (BN + 4)) ? BN * (GEMM_BK + 4) : GEMM_BK * (BN + 4);
+struct TileCfg {
+  static constexpr int WARPS_M = BM / 32, WARPS_N = BN / 32;
+  static constexpr int THREADS = WARPS_M * WARPS_N * 32;
+  static constexpr int A_DOUBLES = (BM * (GEMM_BK + GEMM_PAD) > GEMM_BK * (BM + GEMM_PAD)) ? BM * (GEMM_BK + GEMM_PAD) : GEMM_BK * (BM + GEMM_PAD);
+  static constexpr int B_DOUBLES = (BN * (GEMM_BK + GEMM_PAD) > GEMM_BK * (BN + GEMM_PAD)) ? BN * (GEMM_BK + GEMM_PAD) : GEMM_BK * (BN + GEMM_PAD);
   static constexpr int STAGE_DOUBLES = A_DOUBLES + B_DOUBLES;
+  static constexpr int STAGES = (BM == 128 && BN == 128) ? 4 : 3;
+  static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_DOUBLES * 8;
 };
 
 struct StageMeta {
   double alpha;
-  int a_trans, b_kmajor;
+  int layout;   // bit0: A stored k x m (Transposeview / U^T), bit1: B stored n x k (K contiguous)
 };
 
-// Stage an (R x GEMM_BK) operand slab.  kmajor = true: global is [R][K] (K contiguous) -> smem [R][BK+4];
-// kmajor = false: global is [K][R] (R contiguous) -> smem [BK][R+4].  r_valid / k_valid bound the ragged edge.
+// Stage an (R x GEMM_BK) operand slab.  kmajor = true: global is [R][K] (K contiguous) -> smem [R][BK+PAD];
+// kmajor = false: global is [K][R] (R contiguous) -> smem [BK][R+PAD].  r_total / k_total bound the ragged edge.
 template <int R, int THREADS>
 __device__ __forceinline__ void stage_operand(double* smem, const double* g, int ld, bool kmajor, int r0, int k0, int r_total, int k_total) {
   const int tid = threadIdx.x;
@@ -85,7 +89,7 @@ __device__ __forceinline__ void stage_operand(double* smem, const double* g, int
       int gr = r0 + row, gk = k0 + kc;
       int nv = (gr < r_total) ? min(max(k_total - gk, 0), 2) : 0;
       const double* src = nv > 0 ? g + (int64_t)gr * ld + gk : g;
-      cp_async16(smem + row * (GEMM_BK + 4) + kc, src, nv * 8);
+      cp_async16(smem + row * (GEMM_BK + GEMM_PAD) + kc, src, nv * 8);
     }
   } else {
     constexpr int CPR = R / 2;
@@ -96,18 +100,44 @@ __device__ __forceinline__ void stage_operand(double* smem, const double* g, int
       int gk = k0 + krow, gr = r0 + rc;
       int nv = (gk < k_total) ? min(max(r_total - gr, 0), 2) : 0;
       const double* src = nv > 0 ? g + (int64_t)gk * ld + gr : g;
-      cp_async16(smem + krow * (R + 4) + rc, src, nv * 8);
+      cp_async16(smem + krow * (R + GEMM_PAD) + rc, src, nv * 8);
     }
   }
 }
 
-template <int BM, int BN, int WARPS_M, int WARPS_N, int STAGES>
-__global__ void __launch_bounds__(WARPS_M* WARPS_N * 32)
+// One pipeline stage (GEMM_BK deep) of a warp's 32 x 32 sub-tile; orientation fixed at compile time.
+template <int BM, int BN, bool AT, bool BKM, bool ALPHA>
+__device__ __forceinline__ void mma_stage(const double* __restrict__ sA, const double* __restrict__ sB, double alpha, double (&acc)[2][4][4]) {
+  constexpr int sAr = AT ? 1 : (GEMM_BK + GEMM_PAD), sAk = AT ? (BM + GEMM_PAD) : 1;
+  constexpr int sBn = BKM ? (GEMM_BK + GEMM_PAD) : 1, sBk = BKM ? 1 : (BN + GEMM_PAD);
+#pragma unroll
+  for (int kk = 0; kk < GEMM_BK; kk += 8) {
+    double bf[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      bf[j][0] = sB[j * 8 * sBn + kk * sBk];
+      bf[j][1] = sB[j * 8 * sBn + (kk + 4) * sBk];
+      if (ALPHA) { bf[j][0] *= alpha; bf[j][1] *= alpha; }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      double af[4];
+      af[0] = sA[(i * 16) * sAr + kk * sAk];
+      af[1] = sA[(i * 16 + 8) * sAr + kk * sAk];
+      af[2] = sA[(i * 16) * sAr + (kk + 4) * sAk];
+      af[3] = sA[(i * 16 + 8) * sAr + (kk + 4) * sAk];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) dmma_16x8x8(acc[i][j], af, bf[j]);
+    }
+  }
+}
+
+template <int BM, int BN, bool ALPHA>
+__global__ void __launch_bounds__(TileCfg<BM, BN>::THREADS)
     grouped_gemm_kernel(const GSeg* __restrict__ segs, const GGroup* __restrict__ groups, const GTile* __restrict__ tiles, Bases bases) {
-  constexpr int THREADS = WARPS_M * WARPS_N * 32;
-  constexpr int WM = BM / WARPS_M, WN = BN / WARPS_N;
-  constexpr int MT = WM / 16, NT = WN / 8;
-  using SM = TileSmem<BM, BN>;
+  using Cfg = TileCfg<BM, BN>;
+  constexpr int THREADS = Cfg::THREADS;
+  constexpr int STAGES = Cfg::STAGES;
   extern __shared__ __align__(16) double smem[];
   __shared__ StageMeta meta[STAGES];
 
@@ -115,14 +145,14 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32)
   const GGroup grp = groups[tile.group];
   const int m0 = tile.m0, n0 = tile.n0;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int wm = warp / WARPS_N, wn = warp % WARPS_N;
+  const int wm = warp / Cfg::WARPS_N, wn = warp % Cfg::WARPS_N;
   const int g = lane >> 2, t = lane & 3;
 
-  double acc[MT][NT][4];
+  double acc[2][4][4];
 #pragma unroll
-  for (int i = 0; i < MT; ++i)
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < NT; ++j)
+    for (int j = 0; j < 4; ++j)
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.0;
 
@@ -133,14 +163,13 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32)
       const GSeg sg = segs[ps];
       const double* A = sg.a_base == B2D_BASE_ABS ? reinterpret_cast<const double*>(sg.a) : bases.p[sg.a_base] + sg.a;
       const double* B = sg.b_base == B2D_BASE_ABS ? reinterpret_cast<const double*>(sg.b) : bases.p[sg.b_base] + sg.b;
-      double* sA = smem + stage * SM::STAGE_DOUBLES;
-      double* sB = sA + SM::A_DOUBLES;
+      double* sA = smem + stage * Cfg::STAGE_DOUBLES;
+      double* sB = sA + Cfg::A_DOUBLES;
       stage_operand<BM, THREADS>(sA, A, sg.lda, sg.a_trans == 0, m0, pk, grp.m, sg.k);
       stage_operand<BN, THREADS>(sB, B, sg.ldb, sg.b_kmajor != 0, n0, pk, grp.n, sg.k);
       if (threadIdx.x == 0) {
         meta[stage].alpha = sg.alpha;
-        meta[stage].a_trans = sg.a_trans;
-        meta[stage].b_kmajor = sg.b_kmajor;
+        meta[stage].layout = (sg.a_trans ? 1 : 0) | (sg.b_kmajor ? 2 : 0);
       }
       pk += GEMM_BK;
       if (pk >= sg.k) { pk = 0; ++ps; }
@@ -157,31 +186,16 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32)
     __syncthreads();
     issue((it + STAGES - 1) % STAGES);
     const int stage = it % STAGES;
-    const double* sA = smem + stage * SM::STAGE_DOUBLES;
-    const double* sB = sA + SM::A_DOUBLES;
+    const double* sA = smem + stage * Cfg::STAGE_DOUBLES;
+    const double* sB = sA + Cfg::A_DOUBLES;
     const StageMeta mt = meta[stage];
-    const int sAr = mt.a_trans ? 1 : (GEMM_BK + 4), sAk = mt.a_trans ? (BM + 4) : 1;
-    const int sBn = mt.b_kmajor ? (GEMM_BK + 4) : 1, sBk = mt.b_kmajor ? 1 : (BN + 4);
-#pragma unroll
-    for (int kk = 0; kk < GEMM_BK; kk += 8) {
-      double bf[NT][2];
-#pragma unroll
-      for (int j = 0; j < NT; ++j) {
-        const double* pb = sB + (wn * WN + j * 8 + g) * sBn + (kk + t) * sBk;
-        bf[j][0] = pb[0] * mt.alpha;
-        bf[j][1] = pb[4 * sBk] * mt.alpha;
-      }
-#pragma unroll
-      for (int i = 0; i < MT; ++i) {
-        double af[4];
-        const double* pa = sA + (wm * WM + i * 16 + g) * sAr + (kk + t) * sAk;
-        af[0] = pa[0];
-        af[1] = pa[8 * sAr];
-        af[2] = pa[4 * sAk];
-        af[3] = pa[8 * sAr + 4 * sAk];
-#pragma unroll
-        for (int j = 0; j < NT; ++j) dmma_16x8x8(acc[i][j], af, bf[j]);
-      }
+    // this lane's fragment origin inside the stage, per orientation
+    const int ar = wm * 32 + g, br = wn * 32 + g;
+    switch (mt.layout) {
+      case 0: mma_stage<BM, BN, false, false, ALPHA>(sA + ar * (GEMM_BK + GEMM_PAD) + t, sB + br + t * (BN + GEMM_PAD), mt.alpha, acc); break;
+      case 1: mma_stage<BM, BN, true, false, ALPHA>(sA + ar + t * (BM + GEMM_PAD), sB + br + t * (BN + GEMM_PAD), mt.alpha, acc); break;
+      case 2: mma_stage<BM, BN, false, true, ALPHA>(sA + ar * (GEMM_BK + GEMM_PAD) + t, sB + br * (GEMM_BK + GEMM_PAD) + t, mt.alpha, acc); break;
+      default: mma_stage<BM, BN, true, true, ALPHA>(sA + ar + t * (BM + GEMM_PAD), sB + br * (GEMM_BK + GEMM_PAD) + t, mt.alpha, acc); break;
     }
   }
   cp_async_wait<0>();
@@ -189,13 +203,13 @@ __global__ void __launch_bounds__(WARPS_M* WARPS_N * 32)
   // epilogue: registers -> global (c0,c1 are adjacent columns: one 16-byte store per row pair)
   double* C = bases.p[grp.c_base] + grp.c;
 #pragma unroll
-  for (int i = 0; i < MT; ++i)
+  for (int i = 0; i < 2; ++i)
 #pragma unroll
-    for (int j = 0; j < NT; ++j)
+    for (int j = 0; j < 4; ++j)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        int row = m0 + wm * WM + i * 16 + g + h * 8;
-        int col = n0 + wn * WN + j * 8 + 2 * t;
+        int row = m0 + wm * 32 + i * 16 + g + h * 8;
+        int col = n0 + wn * 32 + j * 8 + 2 * t;
         if (row >= grp.m || col >= grp.n) continue;
         double* dst = C + (int64_t)row * grp.ldc + col;
         double v0 = acc[i][j][2 * h], v1 = acc[i][j][2 * h + 1];

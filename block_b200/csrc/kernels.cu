@@ -18,33 +18,47 @@ namespace b2d {
 // ---------------------------------------------------------------------------------------------------------------
 // grouped contraction launches
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int STAGES0 = 4, STAGES1 = 4, STAGES2 = 3;
-static size_t smem_bytes(int cls) {
-  switch (cls) {
-    case 0: return (size_t)STAGES0 * TileSmem<128, 128>::STAGE_DOUBLES * 8;
-    case 1: return (size_t)STAGES1 * TileSmem<64, 64>::STAGE_DOUBLES * 8;
-    default: return (size_t)STAGES2 * TileSmem<32, 32>::STAGE_DOUBLES * 8;
-  }
+template <int BM, int BN, bool ALPHA>
+static cudaError_t init_one() {
+  return cudaFuncSetAttribute(grouped_gemm_kernel<BM, BN, ALPHA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<BM, BN>::SMEM_BYTES);
+}
+template <int BM, int BN>
+static cudaError_t init_pair() {
+  cudaError_t e = init_one<BM, BN, true>();
+  return e != cudaSuccess ? e : init_one<BM, BN, false>();
 }
 
-cudaError_t gemm_init() {
+cudaError_t gemm_init() {   // opt in to > 48 KB dynamic shared memory
   cudaError_t e;
-  e = cudaFuncSetAttribute(grouped_gemm_kernel<128, 128, 2, 4, STAGES0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(0));
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(grouped_gemm_kernel<64, 64, 2, 2, STAGES1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(1));
-  if (e != cudaSuccess) return e;
-  e = cudaFuncSetAttribute(grouped_gemm_kernel<32, 32, 2, 2, STAGES2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes(2));
-  return e;
+#define B2D_INIT(BM, BN) if ((e = init_pair<BM, BN>()) != cudaSuccess) return e;
+  B2D_INIT(128, 128) B2D_INIT(128, 64) B2D_INIT(128, 32)
+  B2D_INIT(64, 128) B2D_INIT(64, 64) B2D_INIT(64, 32)
+  B2D_INIT(32, 128) B2D_INIT(32, 64) B2D_INIT(32, 32)
+#undef B2D_INIT
+  return cudaSuccess;
+}
+
+template <int BM, int BN>
+static void launch_one(const DevBatch& b, int cls, const Bases& B, cudaStream_t stream) {
+  using Cfg = TileCfg<BM, BN>;
+  if (b.unit_alpha) grouped_gemm_kernel<BM, BN, false><<<b.ntiles[cls], Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(b.segs, b.groups, b.tiles[cls], B);
+  else grouped_gemm_kernel<BM, BN, true><<<b.ntiles[cls], Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(b.segs, b.groups, b.tiles[cls], B);
 }
 
 cudaError_t launch_gemm_class(const DevBatch& b, int cls, double* const* bases, cudaStream_t stream, int64_t* launches) {
-  if (b.ntiles[cls] <= 0) return cudaSuccess;
+  if (cls < 0 || cls >= B2D_NUM_TILE_CLASSES || b.ntiles[cls] <= 0) return cudaSuccess;
   Bases B;
   for (int i = 0; i < B2D_NUM_BASES; ++i) B.p[i] = bases[i];
   switch (cls) {
-    case 0: grouped_gemm_kernel<128, 128, 2, 4, STAGES0><<<b.ntiles[0], 256, smem_bytes(0), stream>>>(b.segs, b.groups, b.tiles[0], B); break;
-    case 1: grouped_gemm_kernel<64, 64, 2, 2, STAGES1><<<b.ntiles[1], 128, smem_bytes(1), stream>>>(b.segs, b.groups, b.tiles[1], B); break;
-    default: grouped_gemm_kernel<32, 32, 2, 2, STAGES2><<<b.ntiles[2], 128, smem_bytes(2), stream>>>(b.segs, b.groups, b.tiles[2], B); break;
+    case 0: launch_one<128, 128>(b, cls, B, stream); break;
+    case 1: launch_one<128, 64>(b, cls, B, stream); break;
+    case 2: launch_one<128, 32>(b, cls, B, stream); break;
+    case 3: launch_one<64, 128>(b, cls, B, stream); break;
+    case 4: launch_one<64, 64>(b, cls, B, stream); break;
+    case 5: launch_one<64, 32>(b, cls, B, stream); break;
+    case 6: launch_one<32, 128>(b, cls, B, stream); break;
+    case 7: launch_one<32, 64>(b, cls, B, stream); break;
+    default: launch_one<32, 32>(b, cls, B, stream); break;
   }
   B2D_LAUNCH_CHECK();
   return cudaSuccess;

@@ -12,8 +12,9 @@ struct Bases;   // gemm_grouped.cuh
 struct DevBatch {
   const GSeg* segs = nullptr;
   const GGroup* groups = nullptr;
-  const GTile* tiles[B2D_NUM_TILE_CLASSES] = {nullptr, nullptr, nullptr};
-  int ntiles[B2D_NUM_TILE_CLASSES] = {0, 0, 0};
+  const GTile* tiles[B2D_NUM_TILE_CLASSES] = {};
+  int ntiles[B2D_NUM_TILE_CLASSES] = {};
+  bool unit_alpha = false;   // every segment has alpha == 1: the kernel variant without the operand scaling is used
 };
 
 constexpr int L1_MAX_VECS = 32;      // vectors per multi-vector level-1 kernel

@@ -254,38 +254,56 @@ struct GemmBatch {
   std::vector<GGroup> groups;
   std::vector<GTile> tiles[B2D_NUM_TILE_CLASSES];
   double flops = 0.0;
-  double class_flops[B2D_NUM_TILE_CLASSES] = {0, 0, 0};    // useful flops (2 m n k) executed by each tile class
-  double class_padded[B2D_NUM_TILE_CLASSES] = {0, 0, 0};   // flops the tiles issue (tile area x pipeline iterations x 16)
+  double class_flops[B2D_NUM_TILE_CLASSES] = {};    // useful flops (2 m n k) executed by each tile class
+  double class_padded[B2D_NUM_TILE_CLASSES] = {};   // flops the tiles issue (tile area x pipeline iterations x 16)
+  bool unit_alpha = false;                           // every segment has alpha == 1
   bool empty() const { return groups.empty(); }
 };
 
-inline int pick_tile_class(int m, int n, int forced) {
-  if (forced >= 0) return forced;
-  int lo = std::min(m, n);
-  if (lo > 48 && (int64_t)m * n >= 96 * 96) return 0;   // 128 x 128
-  if (lo > 20) return 1;                                 // 64 x 64
-  return 2;                                              // 32 x 32
+// Cover a dimension of `d` rows (or columns) with bands: 128-wide bands, then ONE narrower band (or 64 + 32) for the
+// remainder, so that ragged quantum-number sectors do not feed the tensor pipe padding.  Returns (origin, size index)
+// pairs, size index 0/1/2 = 128/64/32.  forced >= 0 tiles everything with that size.
+inline void make_bands(int d, int forced, std::vector<std::pair<int, int>>& out) {
+  out.clear();
+  if (forced >= 0) {
+    int b = 128 >> forced;
+    for (int o = 0; o < d; o += b) out.emplace_back(o, forced);
+    return;
+  }
+  int o = 0;
+  while (d - o > 96) { out.emplace_back(o, 0); o += 128; }
+  int r = d - o;
+  if (r <= 0) return;
+  if (r <= 32) out.emplace_back(o, 2);
+  else if (r <= 64) out.emplace_back(o, 1);
+  else { out.emplace_back(o, 1); out.emplace_back(o + 64, 2); }   // 65..96
 }
 
 // fills batch.tiles from batch.groups; tiles of a class are ordered by descending cost so the hardware's in-order
 // CTA dispatch approximates longest-processing-time scheduling over the 148 SMs
 inline void make_tiles(GemmBatch& b, int forced_class) {
   for (int c = 0; c < B2D_NUM_TILE_CLASSES; ++c) { b.tiles[c].clear(); b.class_flops[c] = b.class_padded[c] = 0.0; }
+  b.unit_alpha = true;
+  for (const GSeg& s : b.segs) if (s.alpha != 1.0) { b.unit_alpha = false; break; }
+  std::vector<std::pair<int, int>> mb, nb;
   for (size_t g = 0; g < b.groups.size(); ++g) {
     GGroup& G = b.groups[g];
     int64_t ktot = 0;
     int kiters = 0;
     for (int s = G.seg_begin; s < G.seg_end; ++s) { ktot += b.segs[s].k; kiters += (b.segs[s].k + 15) / 16; }
     G.kiters = kiters;
-    int c = pick_tile_class(G.m, G.n, forced_class);
-    int bm = b2d_tile_m(c), bn = b2d_tile_n(c);
-    b.class_flops[c] += 2.0 * G.m * G.n * (double)ktot;
-    b.class_padded[c] += 2.0 * bm * bn * 16.0 * kiters * ((G.m + bm - 1) / bm) * ((G.n + bn - 1) / bn);
-    for (int m0 = 0; m0 < G.m; m0 += bm)
-      for (int n0 = 0; n0 < G.n; n0 += bn) {
+    make_bands(G.m, forced_class, mb);
+    make_bands(G.n, forced_class, nb);
+    for (const auto& bm : mb)
+      for (const auto& bn : nb) {
+        const int c = 3 * bm.second + bn.second;
+        const int tm = 128 >> bm.second, tn = 128 >> bn.second;
+        const int um = std::min(tm, G.m - bm.first), un = std::min(tn, G.n - bn.first);
+        b.class_flops[c] += 2.0 * um * un * (double)ktot;
+        b.class_padded[c] += 2.0 * tm * tn * 16.0 * kiters;
         GTile t;
-        t.group = (int)g; t.m0 = m0; t.n0 = n0;
-        t.cost = (int)std::min<int64_t>(ktot + 8 * (G.seg_end - G.seg_begin), 0x7fffffff);
+        t.group = (int)g; t.m0 = bm.first; t.n0 = bn.first;
+        t.cost = (int)std::min<int64_t>(((int64_t)kiters * 16 + 8 * (G.seg_end - G.seg_begin)) * (tm / 32) * (tn / 32), 0x7fffffff);
         b.tiles[c].push_back(t);
       }
   }
@@ -384,7 +402,8 @@ inline Schedule build_schedule(const Side& L, const Side& R, const PsiLayout& P,
       int pb = P.blk[(size_t)b.lQp * P.nr + b.rQp];
       s1.b = P.dev_off[pb]; s1.b_base = B2D_BASE_SRC; s1.b_kmajor = 0; s1.ldb = P.ld[pb];
       s1.k = dlp;
-      s1.alpha = lop.scaling(am, b.lQ, b.lQp);
+      s1.alpha = 1.0;                            // the left scaling (:514) is folded into the step-2 factor below
+      const double left_scaling = lop.scaling(am, b.lQ, b.lQp);
       GGroup g1;
       std::memset(&g1, 0, sizeof(g1));
       g1.c = toff; g1.c_base = B2D_BASE_WORK; g1.ldc = ldt; g1.m = dl; g1.n = drp; g1.accumulate = 0;
@@ -400,6 +419,7 @@ inline Schedule build_schedule(const Side& L, const Side& R, const PsiLayout& P,
                                       L.quantum(b.lQ)[1], R.quantum(rQ)[1], S_psi);            // :522-524
         if (rop.fermion() && (L.quantum(b.lQp)[0] & 1)) F = -F;                                 // :528
         F *= rop.scaling(am, rQ, b.rQp);                                                        // :529
+        F *= left_scaling;                                                                      // :514
         int db = P.blk[(size_t)b.lQ * P.nr + rQ];
         int g = group_of[db];
         if (g < 0) {

@@ -170,9 +170,10 @@ class SpinBlock:
         return float(self.lib.b2d_sigma_flops(self._ctx, int(all_ranks)))
 
     def plan_stats(self):
-        out = np.zeros(8)
-        self._ck(self.lib.b2d_plan_stats(self._ctx, _p(out, _lib.c_f64p), 8))
-        keys = ["chunks", "step1_contractions", "step2_segments", "tiles", "workspace_doubles", "arena_doubles", "launches_per_sigma", "flops_executed"]
+        out = np.zeros(10)
+        self._ck(self.lib.b2d_plan_stats(self._ctx, _p(out, _lib.c_f64p), 10))
+        keys = ["chunks", "step1_contractions", "step2_segments", "tiles", "workspace_doubles", "arena_doubles", "launches_per_sigma", "flops_executed",
+                "flops_in_tiles", "flops_issued"]
         return dict(zip(keys, out.tolist()))
 
     # -- the reference's entry points ---------------------------------------------------------------------------
@@ -202,6 +203,15 @@ class SpinBlock:
         flags = (1 if left_transposed else 0) | (2 if right_transposed else 0)
         self._ck(self.lib.b2d_tensor_multiply(self._ctx, left_op, right_op, flags, int(opq_spin), float(scale), 0, 1))
         return self.download(1)
+
+    def tensor_multiply_slots(self, left_op, right_op, left_transposed, right_transposed, opq_spin, scale, src_slot, dst_slot):
+        """TensorMultiply on device-resident slots: dst += scale (a x b) src."""
+        flags = (1 if left_transposed else 0) | (2 if right_transposed else 0)
+        self._ck(self.lib.b2d_tensor_multiply(self._ctx, left_op, right_op, flags, int(opq_spin), float(scale), src_slot, dst_slot))
+
+    def clear(self, slot):
+        self.reserve(slot + 1)
+        self._ck(self.lib.b2d_vec_clear(self._ctx, slot))
 
     def diagonalH(self, slot=None):
         """SpinBlock::diagonalH(DiagonalMatrix&): diag(H) in flat psi order."""
@@ -319,9 +329,9 @@ class SpinBlock:
     def sigma_profile(self, src_slot, dst_slot):
         """One multiplyH with events around every contraction launch: dict[(step, tile_class)] -> (ms, useful flops,
         issued flops, launches)."""
-        out = np.zeros(24)
+        out = np.zeros(72)
         self._ck(self.lib.b2d_sigma_profile(self._ctx, src_slot, dst_slot, _p(out, _lib.c_f64p)))
-        return {(st, c): tuple(out[(st * 3 + c) * 4:(st * 3 + c) * 4 + 4]) for st in range(2) for c in range(3)}
+        return {(st, c): tuple(out[(st * 9 + c) * 4:(st * 9 + c) * 4 + 4]) for st in range(2) for c in range(9)}
 
     def kernel_launches(self):
         return int(self.lib.b2d_kernel_launches(self._ctx))

@@ -129,18 +129,24 @@ def make_big_block(norbs=40, nelec=40, M=4000, left_sites=None, device=0, rank=0
     left = make_block(L, lsites, rsites, loop=True)
     right = make_block(R, rsites, lsites, loop=False)
     sb = SpinBlock(left, right, (nelec, 0, 0), core_energy=0.0, hubbard=False, norbs=norbs, device=device, rank=rank, nranks=nranks, options=options)
+    sb.fill_seed = seed
     if fill and device >= 0:
         fill_random(sb, seed, rank, nranks)
     return sb
 
 
+def fill_params(dims, side, k, optype, seed=20260):
+    """(stream seed, amplitude) of operator k of a side: amplitudes ~ 1/sqrt(dimension) keep sigma O(1)."""
+    amp = 1.0 / math.sqrt(float(np.sum(dims)))
+    return seed * 1000003 + side * 500009 + k, amp * (4.0 if optype == HAM else 1.0)
+
+
 def fill_random(sb: SpinBlock, seed, rank=0, nranks=1):
-    """Counter-based random operator values on the device; amplitudes ~ 1/sqrt(dimension) keep sigma O(1).
-    Only operators this rank's terms touch need values, but filling all keeps ranks identical."""
+    """Counter-based random operator values on the device (operators a rank does not hold are skipped by the library);
+    the stream is a pure function of (seed, element index), so every rank - and oracle/ref_bench - sees the same values."""
     for side, blk in enumerate((sb.left, sb.right)):
-        amp = 1.0 / math.sqrt(float(np.sum(blk.dims)))
         for k, op in enumerate(blk.ops):
             if op.data is not None:
                 continue
-            sym = op.optype == HAM
-            sb.fill_op_random(side, sb.op_ids[side][k], seed * 1000003 + side * 500009 + k, amplitude=amp * (4.0 if sym else 1.0), symmetric=sym)
+            s, amp = fill_params(blk.dims, side, k, op.optype, seed)
+            sb.fill_op_random(side, sb.op_ids[side][k], s, amplitude=amp, symmetric=op.optype == HAM)

@@ -55,7 +55,7 @@ const char* b2d_last_error(const b2d_ctx* ctx);   /* ctx may be NULL: last error
 int b2d_abi_version(void);
 
 /* Tuning knobs (all optional): "workspace_mb" (T workspace for the two-step contraction), "max_davidson_iter",
- * "tile_class" (debug: force one GEMM tile class), "sync_debug". */
+ * "tile_class" (debug: -1 auto, 0/1/2 = square 128/64/32 tiles everywhere), "sync_debug", "phase_timing". */
 int b2d_set_option(b2d_ctx* ctx, const char* key, double value);
 
 /* ---- block description: replaces the host-side SpinBlock / StateInfo / Op_component objects ---------------- */
@@ -105,7 +105,8 @@ int b2d_terms(const b2d_ctx* ctx, int all_ranks, int32_t* left_op, int32_t* righ
  * all_ranks = 0: this rank's share. */
 double b2d_sigma_flops(const b2d_ctx* ctx, int all_ranks);
 /* schedule statistics: out[0]=#chunks, [1]=#step-1 contractions, [2]=#step-2 segments, [3]=#sigma tiles,
- * [4]=workspace doubles, [5]=operator arena doubles, [6]=kernel launches per sigma */
+ * [4]=workspace doubles, [5]=operator arena doubles, [6]=kernel launches per sigma, [7]=flops executed,
+ * [8]=useful flops inside tiles, [9]=flops the tiles issue including ragged-edge padding */
 int b2d_plan_stats(const b2d_ctx* ctx, double* out, int n);
 
 /* ---- device-resident wavefunction slots ------------------------------------------------------------------- */
@@ -207,9 +208,9 @@ int b2d_allreduce_slot(b2d_ctx* ctx, int slot);
  * the context's stream: out[0] = total, out[1] = step-1 kernels, out[2] = step-2 kernels, out[3] = collective. */
 int b2d_last_timing(b2d_ctx* ctx, double* out, int n);
 /* One multiplyH (this rank's terms, no collective) with CUDA events around every launch of the grouped contraction
- * kernel.  out[(step * 3 + tile_class) * 4 + {0,1,2,3}] = {summed kernel ms, useful flops (2mnk) executed, flops the
+ * kernel.  out[(step * 9 + tile_class) * 4 + {0,1,2,3}] = {summed kernel ms, useful flops (2mnk) executed, flops the
  * tiles issue including ragged-edge padding, number of launches}; step 0 = T = A_L psi (operatorfunctions.C:512-516),
- * step 1 = sigma += F T A_R^T (:517-531); tile classes 128x128, 64x64, 32x32.  24 doubles. */
+ * step 1 = sigma += F T A_R^T (:517-531); tile class = 3 * r + c for a (128 >> r) x (128 >> c) tile.  72 doubles. */
 int b2d_sigma_profile(b2d_ctx* ctx, int src_slot, int dst_slot, double* out);
 int64_t b2d_kernel_launches(const b2d_ctx* ctx);     /* kernels launched by this context so far */
 int b2d_sync(b2d_ctx* ctx);

@@ -109,6 +109,8 @@ struct b2d_ctx {
 
   // scratch
   DevBuf staging, desc_scratch, work, flat_in, flat_out;
+  DevBuf parts;            // split-K partial copies of the destination wavefunction (run_sigma_schedule)
+  int slice_iters = 256;   // pipeline iterations per split-K slice (0: no split)
   DevBuf psi_blocks;       // BlockDesc per psi block
   DevBuf diag_tasks, diag_begin;
   DevBuf partials, scalars;   // level-1 partial sums; G / theta / alpha / misc scalars
@@ -332,9 +334,23 @@ int allreduce(b2d_ctx* ctx, double* p, int64_t n) {
   return B2D_OK;
 }
 
+// run a build_schedule() schedule: dst += (terms) src, with the split-K partial copies zeroed before and summed after
+int run_sigma_schedule(b2d_ctx* ctx, const Schedule& S, const DevSchedule& D, double* src, double* dst) {
+  const int nparts = S.nslices - 1;
+  const int64_t Wp = ctx->psi.Wp;
+  if (nparts > 0) {
+    CU(ctx->parts.reserve((size_t)nparts * Wp * 8));
+    CU(cudaMemsetAsync(ctx->parts.p, 0, (size_t)nparts * Wp * 8, ctx->stream));
+  }
+  int rc = run_schedule(ctx, S, D, src, dst, (double*)ctx->parts.p);
+  if (rc) return rc;
+  if (nparts > 0) CU(launch_sum_parts(dst, (const double*)ctx->parts.p, nparts, Wp, Wp, ctx->stream, &ctx->launches));
+  return B2D_OK;
+}
+
 int sigma_dev(b2d_ctx* ctx, double* src, double* dst, bool accumulate, bool reduce) {
   if (!accumulate) CU(cudaMemsetAsync(dst, 0, (size_t)ctx->psi.Wp * 8, ctx->stream));
-  int rc = run_schedule(ctx, ctx->sched, ctx->dsched, src, dst, nullptr);
+  int rc = run_sigma_schedule(ctx, ctx->sched, ctx->dsched, src, dst);
   if (rc) return rc;
   if (reduce) return allreduce(ctx, dst, ctx->psi.Wp);
   return B2D_OK;
@@ -383,7 +399,7 @@ void b2d_destroy(b2d_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->nccl.comm) ctx->nccl.CommDestroy(ctx->nccl.comm);
     for (auto& s : ctx->slabs) cudaFree(s.p);
-    DevBuf* bufs[] = {&ctx->staging, &ctx->desc_scratch, &ctx->work, &ctx->flat_in, &ctx->flat_out, &ctx->psi_blocks, &ctx->diag_tasks,
+    DevBuf* bufs[] = {&ctx->staging, &ctx->desc_scratch, &ctx->work, &ctx->parts, &ctx->flat_in, &ctx->flat_out, &ctx->psi_blocks, &ctx->diag_tasks,
                       &ctx->diag_begin, &ctx->partials, &ctx->scalars, &ctx->user_pool, &ctx->dav_pool, &ctx->rho, &ctx->eig_g, &ctx->eig_vt,
                       &ctx->eig_vals, &ctx->eig_sweeps, &ctx->sector_desc, &ctx->rot, &ctx->gather_desc, &ctx->gather_rows,
                       &ctx->rotated_arena, &ctx->dsched.buf};
@@ -409,6 +425,7 @@ int b2d_set_option(b2d_ctx* ctx, const char* key, double value) {
   else if (k == "tile_class") ctx->forced_class = (int)value;   // -1 auto, 0/1/2: square 128/64/32 tiles everywhere
   else if (k == "sync_debug") ctx->sync_debug = value != 0;
   else if (k == "multi_stream") ctx->multi_stream = value != 0;
+  else if (k == "slice_iters") ctx->slice_iters = (int)value;
   else if (k == "phase_timing") ctx->phase_timing = value != 0;
   else return fail(ctx, B2D_ERR_ARG, "unknown option " + k);
   return B2D_OK;
@@ -559,7 +576,7 @@ int b2d_plan(b2d_ctx* ctx, const int32_t* psi_dq, double core_energy, int hubbar
       }
     }
     int64_t budget = (int64_t)(ctx->workspace_mb * 1024.0 * 1024.0 / 8.0);
-    ctx->sched = build_schedule(ctx->side[0], ctx->side[1], ctx->psi, ctx->terms_mine, 0, budget, ctx->forced_class, ctx->am);
+    ctx->sched = build_schedule(ctx->side[0], ctx->side[1], ctx->psi, ctx->terms_mine, 0, budget, ctx->forced_class, ctx->am, ctx->slice_iters);
     if (nranks > 1) {
       // algorithmic flops of the whole sigma (all ranks) without keeping the other ranks' schedules
       Schedule all = build_schedule(ctx->side[0], ctx->side[1], ctx->psi, ctx->terms_all, 0, budget, ctx->forced_class, ctx->am);
@@ -762,12 +779,12 @@ int b2d_tensor_multiply(b2d_ctx* ctx, int left_op, int right_op, int flags, int 
   std::vector<Term> one(1, Term{left_op, right_op, (flags & 1) != 0, (flags & 2) != 0, scale, ctx->rank, TERM_PAIR});
   Schedule S;
   try {
-    S = build_schedule(ctx->side[0], ctx->side[1], ctx->psi, one, opq_spin, (int64_t)1 << 60, ctx->forced_class, ctx->am);
+    S = build_schedule(ctx->side[0], ctx->side[1], ctx->psi, one, opq_spin, (int64_t)1 << 60, ctx->forced_class, ctx->am, ctx->slice_iters);
   } catch (const std::exception& e) { return fail(ctx, B2D_ERR_ARG, e.what()); }
   DevSchedule D;
   int rc = upload_schedule(ctx, S, D);
   if (rc) return rc;
-  rc = run_schedule(ctx, S, D, user_vec(ctx, src_slot), user_vec(ctx, dst_slot), nullptr);
+  rc = run_sigma_schedule(ctx, S, D, user_vec(ctx, src_slot), user_vec(ctx, dst_slot));
   CU(cudaStreamSynchronize(ctx->stream));
   D.buf.release();
   return rc;

@@ -20,7 +20,9 @@
 //     bands plus ONE narrower band for the remainder, so the tensor pipe is not fed padding (tile lists are cost-sorted
 //     on the host: in-order CTA dispatch ~ longest-processing-time-first over the 148 SMs).
 //   * the K loop runs over ALL segments of the group back to back through one multi-stage cp.async (LDGSTS.128)
-//     pipeline: a 5-row segment and a 900-row segment cost what their K says, no per-segment pipeline drain.
+//     pipeline: a 5-row segment and a 900-row segment cost what their K says, no per-segment pipeline drain.  The
+//     stages are handed over through mbarriers (cp.async.mbarrier.arrive for "data landed", one arrive per warp for
+//     "slot free"), not __syncthreads: warps drift up to a stage apart instead of draining the pipe at a barrier.
 //   * operands may be stored K-major or M/N-major (Transposeview operators are never materialised); shared-memory
 //     tiles keep the global orientation, padded so the DMMA fragment reads are bank-conflict free in both; the
 //     orientation is resolved ONCE per pipeline stage into one of four fully unrolled code paths with compile-time
@@ -45,9 +47,25 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+// mbarrier primitives (shared::cta).  full[stage]: data of a pipeline stage has landed (every thread's cp.async group
+// arrives asynchronously); empty[stage]: every warp has finished reading the stage.
+__device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(b)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* b) {
+  asm volatile("{\n .reg .b64 st;\n mbarrier.arrive.shared::cta.b64 st, [%0];\n}\n" ::"r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
+}
+// arrive on b once all cp.async operations this thread has issued so far have completed (counts as an expected arrival)
+__device__ __forceinline__ void mbar_arrive_on_cp_async(uint64_t* b) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];\n" ::"r"((unsigned)__cvta_generic_to_shared(b)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* b, int parity) {
+  const unsigned a = (unsigned)__cvta_generic_to_shared(b);
+  unsigned ok;
+  do {
+    asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n" : "=r"(ok) : "r"(a), "r"(parity) : "memory");
+  } while (!ok);
+}
 
 // D(16x8) += A(16x8) * B(8x8), FP64 tensor pipe.  Fragment layout (PTX ISA, mma.m16n8k8 .f64), g = lane/4, t = lane%4:
 //   a0 (g, t)  a1 (g+8, t)  a2 (g, t+4)  a3 (g+8, t+4);   b0 (k=t, n=g)  b1 (k=t+4, n=g);
@@ -66,7 +84,8 @@ struct TileCfg {
   static constexpr int A_DOUBLES = (BM * (GEMM_BK + GEMM_PAD) > GEMM_BK * (BM + GEMM_PAD)) ? BM * (GEMM_BK + GEMM_PAD) : GEMM_BK * (BM + GEMM_PAD);
   static constexpr int B_DOUBLES = (BN * (GEMM_BK + GEMM_PAD) > GEMM_BK * (BN + GEMM_PAD)) ? BN * (GEMM_BK + GEMM_PAD) : GEMM_BK * (BN + GEMM_PAD);
   static constexpr int STAGE_DOUBLES = A_DOUBLES + B_DOUBLES;
-  static constexpr int STAGES = (BM == 128 && BN == 128) ? 4 : 3;
+  static constexpr int STAGES = 4;
+  static constexpr int PREFETCH = 2;   // stages in flight; STAGES - PREFETCH - 1 stages of slack between fast and slow warps
   static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_DOUBLES * 8;
 };
 
@@ -156,49 +175,68 @@ __global__ void __launch_bounds__(TileCfg<BM, BN>::THREADS)
 #pragma unroll
       for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.0;
 
+  // Pipeline: a ring of STAGES slots, loads run PREFETCH iterations ahead.  There is no CTA-wide barrier in the loop:
+  // a warp waits on full[slot] for the data of its iteration and releases the slot through empty[slot]; the slot being
+  // refilled at iteration `it` was consumed at iteration it + PREFETCH - STAGES, so a fast warp may run that far ahead of
+  // the slowest one and its DMMAs cover the other warps' fragment loads, address arithmetic and load issue.
+  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES];
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], THREADS + 1); mbar_init(&empty_bar[s], THREADS / 32); }
+  }
+  __syncthreads();
+
   // producer cursor over (segment, k0)
   int ps = grp.seg_begin, pk = 0;
-  auto issue = [&](int stage) {
-    if (ps < grp.seg_end) {
-      const GSeg sg = segs[ps];
-      const double* A = sg.a_base == B2D_BASE_ABS ? reinterpret_cast<const double*>(sg.a) : bases.p[sg.a_base] + sg.a;
-      const double* B = sg.b_base == B2D_BASE_ABS ? reinterpret_cast<const double*>(sg.b) : bases.p[sg.b_base] + sg.b;
-      double* sA = smem + stage * Cfg::STAGE_DOUBLES;
-      double* sB = sA + Cfg::A_DOUBLES;
-      stage_operand<BM, THREADS>(sA, A, sg.lda, sg.a_trans == 0, m0, pk, grp.m, sg.k);
-      stage_operand<BN, THREADS>(sB, B, sg.ldb, sg.b_kmajor != 0, n0, pk, grp.n, sg.k);
-      if (threadIdx.x == 0) {
-        meta[stage].alpha = sg.alpha;
-        meta[stage].layout = (sg.a_trans ? 1 : 0) | (sg.b_kmajor ? 2 : 0);
-      }
-      pk += GEMM_BK;
-      if (pk >= sg.k) { pk = 0; ++ps; }
+  auto produce = [&](int stage) {
+    const GSeg sg = segs[ps];
+    const double* A = sg.a_base == B2D_BASE_ABS ? reinterpret_cast<const double*>(sg.a) : bases.p[sg.a_base] + sg.a;
+    const double* B = sg.b_base == B2D_BASE_ABS ? reinterpret_cast<const double*>(sg.b) : bases.p[sg.b_base] + sg.b;
+    double* sA = smem + stage * Cfg::STAGE_DOUBLES;
+    double* sB = sA + Cfg::A_DOUBLES;
+    stage_operand<BM, THREADS>(sA, A, sg.lda, sg.a_trans == 0, m0, pk, grp.m, sg.k);
+    stage_operand<BN, THREADS>(sB, B, sg.ldb, sg.b_kmajor != 0, n0, pk, grp.n, sg.k);
+    mbar_arrive_on_cp_async(&full_bar[stage]);
+    if (threadIdx.x == 0) {
+      meta[stage].alpha = sg.alpha;
+      meta[stage].layout = (sg.a_trans ? 1 : 0) | (sg.b_kmajor ? 2 : 0);
+      mbar_arrive(&full_bar[stage]);
     }
-    cp_async_commit();
+    pk += GEMM_BK;
+    if (pk >= sg.k) { pk = 0; ++ps; }
   };
 
   const int total = grp.kiters;
 #pragma unroll
-  for (int s = 0; s < STAGES - 1; ++s) issue(s);
+  for (int p = 0; p < Cfg::PREFETCH; ++p)
+    if (p < total) produce(p);
+
+  // this lane's fragment origin inside a stage, per orientation
+  const int ar = wm * 32 + g, br = wn * 32 + g;
+  const int a_off_n = ar * (GEMM_BK + GEMM_PAD) + t, a_off_t = ar + t * (BM + GEMM_PAD);
+  const int b_off_n = br + t * (BN + GEMM_PAD), b_off_k = br * (GEMM_BK + GEMM_PAD) + t;
 
   for (int it = 0; it < total; ++it) {
-    cp_async_wait<STAGES - 2>();
-    __syncthreads();
-    issue((it + STAGES - 1) % STAGES);
+    const int p = it + Cfg::PREFETCH;
+    if (p < total) {
+      const int slot = p % STAGES;
+      if (p >= STAGES) mbar_wait(&empty_bar[slot], ((p / STAGES) & 1) ^ 1);
+      produce(slot);
+    }
     const int stage = it % STAGES;
+    mbar_wait(&full_bar[stage], (it / STAGES) & 1);
     const double* sA = smem + stage * Cfg::STAGE_DOUBLES;
     const double* sB = sA + Cfg::A_DOUBLES;
     const StageMeta mt = meta[stage];
-    // this lane's fragment origin inside the stage, per orientation
-    const int ar = wm * 32 + g, br = wn * 32 + g;
     switch (mt.layout) {
-      case 0: mma_stage<BM, BN, false, false, ALPHA>(sA + ar * (GEMM_BK + GEMM_PAD) + t, sB + br + t * (BN + GEMM_PAD), mt.alpha, acc); break;
-      case 1: mma_stage<BM, BN, true, false, ALPHA>(sA + ar + t * (BM + GEMM_PAD), sB + br + t * (BN + GEMM_PAD), mt.alpha, acc); break;
-      case 2: mma_stage<BM, BN, false, true, ALPHA>(sA + ar * (GEMM_BK + GEMM_PAD) + t, sB + br * (GEMM_BK + GEMM_PAD) + t, mt.alpha, acc); break;
-      default: mma_stage<BM, BN, true, true, ALPHA>(sA + ar + t * (BM + GEMM_PAD), sB + br * (GEMM_BK + GEMM_PAD) + t, mt.alpha, acc); break;
+      case 0: mma_stage<BM, BN, false, false, ALPHA>(sA + a_off_n, sB + b_off_n, mt.alpha, acc); break;
+      case 1: mma_stage<BM, BN, true, false, ALPHA>(sA + a_off_t, sB + b_off_n, mt.alpha, acc); break;
+      case 2: mma_stage<BM, BN, false, true, ALPHA>(sA + a_off_n, sB + b_off_k, mt.alpha, acc); break;
+      default: mma_stage<BM, BN, true, true, ALPHA>(sA + a_off_t, sB + b_off_k, mt.alpha, acc); break;
     }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty_bar[stage]);
   }
-  cp_async_wait<0>();
 
   // epilogue: registers -> global (c0,c1 are adjacent columns: one 16-byte store per row pair)
   double* C = bases.p[grp.c_base] + grp.c;

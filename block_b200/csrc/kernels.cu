@@ -324,6 +324,20 @@ cudaError_t launch_scale(double* x, double a, int64_t n, cudaStream_t s, int64_t
   return cudaSuccess;
 }
 
+__global__ void __launch_bounds__(L1_THREADS) sum_parts_kernel(double* __restrict__ dst, const double* __restrict__ parts, int nparts, int64_t stride, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    double v = dst[i];
+    for (int p = 0; p < nparts; ++p) v += parts[(int64_t)p * stride + i];
+    dst[i] = v;
+  }
+}
+cudaError_t launch_sum_parts(double* dst, const double* parts, int nparts, int64_t stride, int64_t n, cudaStream_t s, int64_t* launches) {
+  if (nparts <= 0) return cudaSuccess;
+  sum_parts_kernel<<<l1_grid(n), L1_THREADS, 0, s>>>(dst, parts, nparts, stride, n);
+  B2D_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Davidson subspace eigenproblem (replaces dsyev_ at linear.C:273): two-sided cyclic Jacobi, one warp, n <= 32
 // ---------------------------------------------------------------------------------------------------------------

@@ -49,6 +49,8 @@ cudaError_t launch_normalise(double* r, int64_t n, double* partials, double* scr
 // y += mult * coef[0] * x  (coef on the device; coef == nullptr means 1)
 cudaError_t launch_axpy(double* y, const double* x, const double* coef, double mult, int64_t n, cudaStream_t s, int64_t* launches);
 cudaError_t launch_scale(double* x, double a, int64_t n, cudaStream_t s, int64_t* launches);
+// dst += parts[0] + parts[1] + ... (nparts copies, `stride` doubles apart), summed in that fixed order (split-K epilogue)
+cudaError_t launch_sum_parts(double* dst, const double* parts, int nparts, int64_t stride, int64_t n, cudaStream_t s, int64_t* launches);
 
 // symmetric eigenproblem of the Davidson subspace matrix (n <= 32): two-sided cyclic Jacobi in one warp.
 // G: n x ldg (upper triangle G[j][i], i >= j, valid; mirrored inside); theta[n] ascending; alpha[i*ldg + j] = component i of eigenvector j

@@ -323,11 +323,14 @@ struct Schedule {
   double flops_exec = 0.0;   // what the kernels execute (T blocks nobody consumes are skipped)
   int64_t work_max = 0;
   int64_t n_step1 = 0, n_step2 = 0, n_tiles = 0;
+  int nslices = 1;           // split-K copies of the destination used by step 2 (slice 0 is the destination itself)
 };
+
+constexpr int SPLITK_MAX = 8;   // K slices of one sigma block computed by different CTAs into private partial copies
 
 // Build the two-step schedule for a list of operator pairs:  dst[lQ,rQ] += F * (s A_L[lQ,lQ'] src[lQ',rQ']) A_R[rQ,rQ']^T
 inline Schedule build_schedule(const Side& L, const Side& R, const PsiLayout& P, const std::vector<Term>& terms, int opq_spin,
-                               int64_t work_budget, int forced_class, AngMom& am) {
+                               int64_t work_budget, int forced_class, AngMom& am, int slice_iters = 256) {
   Schedule S;
   const int S_psi = P.dq[1];
   Chunk cur;
@@ -340,12 +343,35 @@ inline Schedule build_schedule(const Side& L, const Side& R, const PsiLayout& P,
   };
   auto close_chunk = [&]() {
     if (cur.nterms == 0) return;
-    for (size_t g = 0; g < cur.step2.groups.size(); ++g) {
-      GGroup& G = cur.step2.groups[g];
-      G.seg_begin = (int)cur.step2.segs.size();
-      cur.step2.segs.insert(cur.step2.segs.end(), pending[g].begin(), pending[g].end());
-      G.seg_end = (int)cur.step2.segs.size();
+    // Split-K: a sigma block receives hundreds of segments per chunk but there are only a few hundred sigma tiles in
+    // total, i.e. ~3 waves over 148 SMs with a long serial K loop each.  Cut the segment list of a group into up to
+    // SPLITK_MAX slices of ~slice_iters pipeline iterations; slice 0 accumulates into the destination, slice s >= 1
+    // into partial copy s - 1 (base AUX, stride P.Wp) which the caller sums in a fixed order afterwards: deterministic.
+    const size_t ngroups = cur.step2.groups.size();
+    std::vector<GGroup> sliced;
+    for (size_t g = 0; g < ngroups; ++g) {
+      const GGroup G0 = cur.step2.groups[g];
+      int64_t iters = 0;
+      for (const GSeg& sg : pending[g]) iters += (sg.k + 15) / 16;
+      int ns = (int)std::min<int64_t>(SPLITK_MAX, std::max<int64_t>(1, (iters + slice_iters / 2) / std::max(slice_iters, 1)));
+      if (slice_iters <= 0) ns = 1;
+      S.nslices = std::max(S.nslices, ns);
+      size_t pos = 0;
+      int64_t done = 0;
+      for (int sl = 0; sl < ns; ++sl) {
+        GGroup G = G0;
+        if (sl > 0) { G.c_base = B2D_BASE_AUX; G.c = G0.c + (int64_t)(sl - 1) * P.Wp; }
+        G.seg_begin = (int)cur.step2.segs.size();
+        const int64_t target = iters * (sl + 1) / ns;
+        while (pos < pending[g].size() && (done < target || sl == ns - 1)) {
+          done += (pending[g][pos].k + 15) / 16;
+          cur.step2.segs.push_back(pending[g][pos++]);
+        }
+        G.seg_end = (int)cur.step2.segs.size();
+        if (G.seg_end > G.seg_begin) sliced.push_back(G);
+      }
     }
+    cur.step2.groups.swap(sliced);
     make_tiles(cur.step1, forced_class);
     make_tiles(cur.step2, forced_class);
     S.work_max = std::max(S.work_max, cur.work);

@@ -71,6 +71,21 @@ def test_sigma_chunked_workspace(golden):
         sb.close()
 
 
+@pytest.mark.parametrize("iters", [0, 1, 3])
+def test_sigma_split_k_slices(golden, iters):
+    """step-2 split-K (partial copies summed in a fixed order) must not change sigma; 0 disables the split."""
+    rec, big = golden
+    sb = hotpath.spinblock_from_record(rec, device=0, options={"slice_iters": iters})
+    try:
+        v1 = sb.multiplyH(rec["rpsi"])
+        assert rel(v1, rec["rsigma"]) < 1e-12
+        assert np.array_equal(v1, sb.multiplyH(rec["rpsi"]))          # deterministic run to run
+        v0 = np.sin(np.arange(sb.size))
+        assert rel(sb.multiplyH(rec["rpsi"], v0.copy()) - v0, rec["rsigma"]) < 1e-10
+    finally:
+        sb.close()
+
+
 def test_tensor_multiply_single_terms(gpu_block):
     rec, big, sb = gpu_block
     terms = O.h_terms(big)

@@ -278,7 +278,7 @@ def run_ours(a):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     t_setup = time.time()
     sb = S.make_big_block(norbs=a.norbs, nelec=a.nelec, M=a.M, left_sites=a.left_sites, device=local, rank=rank, nranks=world,
-                          options={"workspace_mb": a.workspace_mb})
+                          options=dict({"workspace_mb": a.workspace_mb, "slice_iters": a.slice_iters}, **{kv.split("=")[0]: float(kv.split("=")[1]) for kv in a.opt}))
     if world > 1:   # the partial sigmas are summed by the library's own NCCL communicator (dlopen'ed libnccl of the torch wheel)
         ident = [SpinBlock.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ident, src=0)
@@ -338,7 +338,8 @@ def run_ours(a):
     sb.upload(2, 2.0 * psi - 3.0 * y)
     sb.sigma(2, 1)
     lin_err = float(np.linalg.norm(sb.download(1) - (2.0 * hx - 3.0 * hy)) / np.linalg.norm(2.0 * hx - 3.0 * hy))
-    parity = {"linearity_rel": lin_err}
+    # sigma_norm / sigma_probe are pure functions of the (seeded) workload: they must agree across --gpus 1/2/4/8 runs
+    parity = {"linearity_rel": lin_err, "sigma_norm": float(np.linalg.norm(hx)), "sigma_probe": float(np.dot(hx, np.cos(np.arange(W))))}
     if world == 1 and not a.no_cpu:
         from oracle import refbench
         if refbench.available():
@@ -429,7 +430,9 @@ def main():
     # 18|22: the heaviest block iteration of the 40-orbital M=4000 sweep whose materialised operator arenas (152 GB) fit
     # ONE 180 GB B200; the mid-chain 20|20 iteration (185 GB) needs the term partition over >= 2 GPUs
     ap.add_argument("--left-sites", type=int, default=18)
-    ap.add_argument("--workspace-mb", type=float, default=2048.0)
+    ap.add_argument("--workspace-mb", type=float, default=8192.0)
+    ap.add_argument("--slice-iters", type=int, default=256)
+    ap.add_argument("--opt", action="append", default=[], help="extra library option key=value (b2d_set_option)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--profile-mode", action="store_true", help="for ncu: 1 warm-up sigma + --steps sigmas, nothing else, no JSON line")
     ap.add_argument("--cpu-budget-s", type=float, default=15.0)

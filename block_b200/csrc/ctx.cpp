@@ -109,6 +109,7 @@ struct b2d_ctx {
 
   // scratch
   DevBuf staging, desc_scratch, work, flat_in, flat_out;
+  DevBuf trace_buf;        // B2D_TRACE diagnostic
   DevBuf parts;            // split-K partial copies of the destination wavefunction (run_sigma_schedule)
   int slice_iters = 256;   // pipeline iterations per split-K slice (0: no split)
   DevBuf psi_blocks;       // BlockDesc per psi block
@@ -259,22 +260,46 @@ int run_schedule(b2d_ctx* ctx, const Schedule& S, const DevSchedule& D, double* 
   if (!ctx->phase_timing) {
     // The tile classes of one step are independent: the first non-empty class stays on the main stream, the others
     // are forked onto side streams so that their CTAs fill the SMs the main launch leaves idle in its tail.
+    const char* trace_path = getenv("B2D_TRACE");   // diagnostic: per-launch (stream, class, start, end) timeline
+    struct TraceRec { int chunk, step, cls; };
+    std::vector<TraceRec> trace;
+    int cur_chunk = 0, cur_step = 0;
+    const size_t trace_cap = D.chunks.size() * 2 * B2D_NUM_TILE_CLASSES;
+    if (trace_path) {   // one {min start, max end} slot per launch, filled by the kernels from %globaltimer
+      CU(ctx->trace_buf.reserve(trace_cap * 16));
+      std::vector<unsigned long long> init(trace_cap * 2);
+      for (size_t i = 0; i < trace_cap; ++i) { init[2 * i] = ~0ull; init[2 * i + 1] = 0ull; }
+      CU(cudaMemcpyAsync(ctx->trace_buf.p, init.data(), trace_cap * 16, cudaMemcpyHostToDevice, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+    }
+    auto traced_launch = [&](const DevBatch& b, int c, cudaStream_t st) -> int {
+      unsigned long long* slot = nullptr;
+      if (trace_path) {
+        slot = (unsigned long long*)ctx->trace_buf.p + 2 * trace.size();
+        trace.push_back(TraceRec{cur_chunk, cur_step, c});
+      }
+      CU(launch_gemm_class(b, c, bases, st, &ctx->launches, slot));
+      return B2D_OK;
+    };
     auto run_batch = [&](const DevBatch& b) -> int {
       int first = -1;
       for (int c = 0; c < B2D_NUM_TILE_CLASSES; ++c) if (b.ntiles[c] > 0) { first = c; break; }
       if (first < 0) return B2D_OK;
-      bool forked = false;
+      // the big class goes first and on the high-priority main stream: it takes every SM, the narrower classes (queued
+      // behind it on low-priority side streams) are dispatched as SMs drain in its tail
+      bool more = false;
+      for (int c = first + 1; c < B2D_NUM_TILE_CLASSES; ++c) more = more || b.ntiles[c] > 0;
+      if (ctx->multi_stream && more) CU(cudaEventRecord(ctx->fork_ev, ctx->stream));
+      { int rc = traced_launch(b, first, ctx->stream); if (rc) return rc; }
       if (ctx->multi_stream) {
         for (int c = first + 1; c < B2D_NUM_TILE_CLASSES; ++c) {
           if (b.ntiles[c] <= 0) continue;
-          if (!forked) { CU(cudaEventRecord(ctx->fork_ev, ctx->stream)); forked = true; }
           cudaStream_t side = ctx->side_streams[c - 1];
           CU(cudaStreamWaitEvent(side, ctx->fork_ev, 0));
-          CU(launch_gemm_class(b, c, bases, side, &ctx->launches));
+          { int rc = traced_launch(b, c, side); if (rc) return rc; }
           CU(cudaEventRecord(ctx->join_ev[c - 1], side));
         }
       }
-      CU(launch_gemm_class(b, first, bases, ctx->stream, &ctx->launches));
       for (int c = first + 1; c < B2D_NUM_TILE_CLASSES; ++c) {
         if (b.ntiles[c] <= 0) continue;
         if (ctx->multi_stream) CU(cudaStreamWaitEvent(ctx->stream, ctx->join_ev[c - 1], 0));
@@ -283,11 +308,25 @@ int run_schedule(b2d_ctx* ctx, const Schedule& S, const DevSchedule& D, double* 
       return B2D_OK;
     };
     for (size_t i = 0; i < D.chunks.size(); ++i) {
+      cur_chunk = (int)i; cur_step = 0;
       int rc = run_batch(D.chunks[i].s1);
       if (rc) return rc;
+      cur_step = 1;
       rc = run_batch(D.chunks[i].s2);
       if (rc) return rc;
       if (ctx->sync_debug) CU(cudaStreamSynchronize(ctx->stream));
+    }
+    if (trace_path && !trace.empty()) {
+      CU(cudaStreamSynchronize(ctx->stream));
+      std::vector<unsigned long long> t(trace.size() * 2);
+      CU(cudaMemcpy(t.data(), ctx->trace_buf.p, t.size() * 8, cudaMemcpyDeviceToHost));
+      FILE* f = fopen(trace_path, "w");
+      if (f) {
+        fprintf(f, "chunk,step,class,start_ms,end_ms\n");
+        for (size_t i = 0; i < trace.size(); ++i)
+          fprintf(f, "%d,%d,%d,%.4f,%.4f\n", trace[i].chunk, trace[i].step, trace[i].cls, (double)(t[2 * i] - t[0]) * 1e-6, (double)(t[2 * i + 1] - t[0]) * 1e-6);
+        fclose(f);
+      }
     }
     return B2D_OK;
   }
@@ -378,9 +417,11 @@ int b2d_create(int device, b2d_ctx** out) {
     CU(cudaSetDevice(device));
     c->device = device;
     c->has_device = true;
-    CU(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+    int prio_least = 0, prio_greatest = 0;
+    CU(cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest));
+    CU(cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_greatest));
     for (auto& ev : c->ev) CU(cudaEventCreate(&ev));
-    for (auto& st : c->side_streams) CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (auto& st : c->side_streams) CU(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, prio_least));
     CU(cudaEventCreateWithFlags(&c->fork_ev, cudaEventDisableTiming));
     for (auto& ev : c->join_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
     CU(gemm_init());
@@ -399,7 +440,7 @@ void b2d_destroy(b2d_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     if (ctx->nccl.comm) ctx->nccl.CommDestroy(ctx->nccl.comm);
     for (auto& s : ctx->slabs) cudaFree(s.p);
-    DevBuf* bufs[] = {&ctx->staging, &ctx->desc_scratch, &ctx->work, &ctx->parts, &ctx->flat_in, &ctx->flat_out, &ctx->psi_blocks, &ctx->diag_tasks,
+    DevBuf* bufs[] = {&ctx->staging, &ctx->desc_scratch, &ctx->work, &ctx->parts, &ctx->trace_buf, &ctx->flat_in, &ctx->flat_out, &ctx->psi_blocks, &ctx->diag_tasks,
                       &ctx->diag_begin, &ctx->partials, &ctx->scalars, &ctx->user_pool, &ctx->dav_pool, &ctx->rho, &ctx->eig_g, &ctx->eig_vt,
                       &ctx->eig_vals, &ctx->eig_sweeps, &ctx->sector_desc, &ctx->rot, &ctx->gather_desc, &ctx->gather_rows,
                       &ctx->rotated_arena, &ctx->dsched.buf};

@@ -38,10 +38,17 @@ namespace b2d {
 
 struct Bases {
   double* p[B2D_NUM_BASES];
+  unsigned long long* trace;   // diagnostic: {min CTA start, max CTA end} of this launch in %globaltimer ns, or nullptr
 };
 
 constexpr int GEMM_BK = 16;
 constexpr int GEMM_PAD = 4;
+#ifndef B2D_SMALL_STAGES
+#define B2D_SMALL_STAGES 3
+#endif
+#ifndef B2D_SMALL_PREFETCH
+#define B2D_SMALL_PREFETCH 1
+#endif
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src_bytes) {
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -84,8 +91,11 @@ struct TileCfg {
   static constexpr int A_DOUBLES = (BM * (GEMM_BK + GEMM_PAD) > GEMM_BK * (BM + GEMM_PAD)) ? BM * (GEMM_BK + GEMM_PAD) : GEMM_BK * (BM + GEMM_PAD);
   static constexpr int B_DOUBLES = (BN * (GEMM_BK + GEMM_PAD) > GEMM_BK * (BN + GEMM_PAD)) ? BN * (GEMM_BK + GEMM_PAD) : GEMM_BK * (BN + GEMM_PAD);
   static constexpr int STAGE_DOUBLES = A_DOUBLES + B_DOUBLES;
-  static constexpr int STAGES = 4;
-  static constexpr int PREFETCH = 2;   // stages in flight; STAGES - PREFETCH - 1 stages of slack between fast and slow warps
+  // 128x128: one 16-warp CTA per SM, 4 x 40 KB stages.  Narrower classes: fewer stages so that 2-3 CTAs share an SM and
+  // one CTA's prologue / epilogue hides under the others' K loops.
+  static constexpr bool BIG = (BM == 128 && BN == 128);
+  static constexpr int STAGES = BIG ? 4 : B2D_SMALL_STAGES;
+  static constexpr int PREFETCH = BIG ? 2 : B2D_SMALL_PREFETCH;   // stages in flight; STAGES - PREFETCH - 1 stages of slack between warps
   static constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_DOUBLES * 8;
 };
 
@@ -160,6 +170,11 @@ __global__ void __launch_bounds__(TileCfg<BM, BN>::THREADS)
   extern __shared__ __align__(16) double smem[];
   __shared__ StageMeta meta[STAGES];
 
+  if (bases.trace && threadIdx.x == 0) {
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    atomicMin(bases.trace, t0);
+  }
   const GTile tile = tiles[blockIdx.x];
   const GGroup grp = groups[tile.group];
   const int m0 = tile.m0, n0 = tile.n0;
@@ -186,10 +201,10 @@ __global__ void __launch_bounds__(TileCfg<BM, BN>::THREADS)
   }
   __syncthreads();
 
-  // producer cursor over (segment, k0)
+  // producer cursor over (segment, k0); the segment descriptor stays in registers until the segment is exhausted
   int ps = grp.seg_begin, pk = 0;
+  GSeg sg = segs[ps];
   auto produce = [&](int stage) {
-    const GSeg sg = segs[ps];
     const double* A = sg.a_base == B2D_BASE_ABS ? reinterpret_cast<const double*>(sg.a) : bases.p[sg.a_base] + sg.a;
     const double* B = sg.b_base == B2D_BASE_ABS ? reinterpret_cast<const double*>(sg.b) : bases.p[sg.b_base] + sg.b;
     double* sA = smem + stage * Cfg::STAGE_DOUBLES;
@@ -203,7 +218,10 @@ __global__ void __launch_bounds__(TileCfg<BM, BN>::THREADS)
       mbar_arrive(&full_bar[stage]);
     }
     pk += GEMM_BK;
-    if (pk >= sg.k) { pk = 0; ++ps; }
+    if (pk >= sg.k) {
+      pk = 0;
+      if (++ps < grp.seg_end) sg = segs[ps];
+    }
   };
 
   const int total = grp.kiters;
@@ -260,6 +278,11 @@ __global__ void __launch_bounds__(TileCfg<BM, BN>::THREADS)
           dst[0] = grp.accumulate ? dst[0] + v0 : v0;
         }
       }
+  if (bases.trace && threadIdx.x == 0) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    atomicMax(bases.trace + 1, t1);
+  }
 }
 
 }  // namespace b2d

@@ -45,10 +45,12 @@ static void launch_one(const DevBatch& b, int cls, const Bases& B, cudaStream_t 
   else grouped_gemm_kernel<BM, BN, true><<<b.ntiles[cls], Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(b.segs, b.groups, b.tiles[cls], B);
 }
 
-cudaError_t launch_gemm_class(const DevBatch& b, int cls, double* const* bases, cudaStream_t stream, int64_t* launches) {
+cudaError_t launch_gemm_class(const DevBatch& b, int cls, double* const* bases, cudaStream_t stream, int64_t* launches,
+                              unsigned long long* trace_slot) {
   if (cls < 0 || cls >= B2D_NUM_TILE_CLASSES || b.ntiles[cls] <= 0) return cudaSuccess;
   Bases B;
   for (int i = 0; i < B2D_NUM_BASES; ++i) B.p[i] = bases[i];
+  B.trace = trace_slot;
   switch (cls) {
     case 0: launch_one<128, 128>(b, cls, B, stream); break;
     case 1: launch_one<128, 64>(b, cls, B, stream); break;

@@ -292,8 +292,9 @@ inline void make_tiles(GemmBatch& b, int forced_class) {
     int kiters = 0;
     for (int s = G.seg_begin; s < G.seg_end; ++s) { ktot += b.segs[s].k; kiters += (b.segs[s].k + 15) / 16; }
     G.kiters = kiters;
-    make_bands(G.m, forced_class, mb);
-    make_bands(G.n, forced_class, nb);
+    // forced_class: -1 auto; 0/1/2 square 128/64/32; 10*(r+1)+c forces (128>>r) x (128>>c) tiles (experiments)
+    make_bands(G.m, forced_class >= 10 ? forced_class / 10 - 1 : forced_class, mb);
+    make_bands(G.n, forced_class >= 10 ? forced_class % 10 : forced_class, nb);
     for (const auto& bm : mb)
       for (const auto& bn : nb) {
         const int c = 3 * bm.second + bn.second;

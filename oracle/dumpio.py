@@ -34,6 +34,21 @@ def read_records(path) -> dict:
     return out
 
 
+def write_records(path, rec: dict) -> None:
+    """Inverse of read_records (raw format): lets C++ test drivers consume the .npz fixtures."""
+    with open(path, "wb") as f:
+        for name, arr in rec.items():
+            a = np.asarray(arr)
+            isint = a.dtype.kind in "iub"
+            a = np.ascontiguousarray(a, dtype="<i4" if isint else "<f8")
+            nb = name.encode()
+            f.write(struct.pack("<I", len(nb))); f.write(nb)
+            f.write(struct.pack("<B", 0 if isint else 1))
+            f.write(struct.pack("<I", a.ndim))
+            f.write(struct.pack("<%dQ" % a.ndim, *a.shape))
+            f.write(a.tobytes())
+
+
 def block_from(rec: dict, prefix: str) -> O.Block:
     q = rec[prefix + "q"].astype(np.int64).reshape(-1, 3)
     dims = rec[prefix + "dims"].astype(np.int64)

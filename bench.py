@@ -33,6 +33,15 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 METRIC = "sigma_fp64_gflops"
 UNIT = "GFLOP/s"
 
@@ -208,7 +217,7 @@ def run_reference(a):
             "data": "synthetic", "config": {"workload": workload_name(a), "sample": last[3]},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": last[2], "kind": last[0], "sample": last[3]},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -412,13 +421,18 @@ def run_ours(a):
         kind, v, cores, desc, _, _ = cpu_leg(a, a.cpu_budget_s)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}
     if line is not None:
-        print(json.dumps(line), flush=True)
+        emit(line)
     sb.close()
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
+    # stdout carries exactly ONE JSON line: everything libraries print (NCCL banners, torchrun notices) goes to stderr
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

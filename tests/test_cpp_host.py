@@ -15,7 +15,7 @@ EXE = os.path.join(ROOT, "block_b200", "lib", "host_mirror_test")
 
 
 def rel(a, b):
-    return np.linalg.norm(a - b) / np.linalg.norm(b)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
 
 
 def test_cpp_mirror_builds_and_fails_loudly_without_a_device(tmp_path, golden):

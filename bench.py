@@ -270,6 +270,53 @@ class ClockSampler:
         return out
 
 
+def block_iteration_leg(sb, a, psi, sigma_ms):
+    """The rest of one RenormaliseFrom + transform_operators at the same size (renormalise.C:39-133, save_load_block.C:267):
+    diag(H), a Davidson solve capped at a.davidson_iters iterations (random operators do not converge like a molecule's),
+    density matrix, per-sector eigen-decomposition, state selection, operator rotation.  Times are wall-clock around the
+    synchronous C calls.  Not part of `value`: it shows that nothing beside sigma dominates a block iteration."""
+    import ctypes as C
+    from block_b200 import _lib
+    out = {}
+    sb.set_option("max_davidson_iter", a.davidson_iters)
+    sb.reserve(3)
+    sb.upload(0, psi)
+
+    def timed(fn):
+        sb.sync()
+        t0 = time.perf_counter()
+        r = fn()
+        sb.sync()
+        return r, (time.perf_counter() - t0) * 1e3
+
+    _, out["diag_ms"] = timed(lambda: sb.lib.b2d_diagonal(sb._ctx, 1))
+    ev, nm, res = np.zeros(1), C.c_int(0), C.c_double(0.0)
+    rc, out["davidson_ms"] = timed(lambda: sb.lib.b2d_davidson(sb._ctx, 1, 0, 1, 1e-14, 2, 20, ev.ctypes.data_as(_lib.c_f64p), C.byref(nm), C.byref(res)))
+    out["davidson_h_applications"] = nm.value
+    out["davidson_level1_ms_per_iteration"] = (out["davidson_ms"] - nm.value * sigma_ms) / max(nm.value, 1)
+    out["davidson_residual_norm2"] = res.value
+    w = np.ones(1)
+    rc, out["density_ms"] = timed(lambda: sb.lib.b2d_make_density(sb._ctx, 1, 0, w.ctypes.data_as(_lib.c_f64p)))
+    if rc:
+        out["error"] = sb.lib.b2d_last_error(sb._ctx).decode()
+        return out
+    rc, out["eigen_ms"] = timed(lambda: sb.lib.b2d_diagonalise_dm(sb._ctx, None))
+    if rc:
+        out["error"] = sb.lib.b2d_last_error(sb._ctx).decode()
+        return out
+    kept = np.zeros(len(sb.left.dims), np.int32)
+    err = C.c_double(0.0)
+    rc, out["select_ms"] = timed(lambda: sb.lib.b2d_select_states(sb._ctx, a.M, kept.ctypes.data_as(_lib.c_i32p), C.byref(err)))
+    out["kept_states"] = int(kept.sum())
+    out["discarded_weight"] = err.value
+    rc, out["rotate_ms"] = timed(lambda: sb.lib.b2d_transform_operators(sb._ctx))
+    if rc:
+        out["error"] = sb.lib.b2d_last_error(sb._ctx).decode()
+    out["non_sigma_ms"] = out["diag_ms"] + out["davidson_level1_ms_per_iteration"] * nm.value + out["density_ms"] + out["eigen_ms"] + out["select_ms"] + out.get("rotate_ms", 0.0)
+    out["sigma_share_of_block_iteration"] = nm.value * sigma_ms / (nm.value * sigma_ms + out["non_sigma_ms"])
+    return out
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -417,6 +464,8 @@ def run_ours(a):
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roof,
                 "parity": parity,
                 "hbm_peak_gbs": peaks.get("hbm_gbs")}
+    if line is not None and world == 1 and not a.no_block_iteration:
+        line["block_iteration"] = block_iteration_leg(sb, a, psi, ms_step)
     if line is not None and not a.no_cpu and world == 1:
         kind, v, cores, desc, _, _ = cpu_leg(a, a.cpu_budget_s)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}
@@ -448,6 +497,8 @@ def main():
     ap.add_argument("--slice-iters", type=int, default=256)
     ap.add_argument("--opt", action="append", default=[], help="extra library option key=value (b2d_set_option)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-block-iteration", action="store_true", help="skip the Davidson / density / eigen / rotation leg")
+    ap.add_argument("--davidson-iters", type=int, default=6)
     ap.add_argument("--profile-mode", action="store_true", help="for ncu: 1 warm-up sigma + --steps sigmas, nothing else, no JSON line")
     ap.add_argument("--cpu-budget-s", type=float, default=15.0)
     ap.add_argument("--ref-step-s", type=float, default=6.0)

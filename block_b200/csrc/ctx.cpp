@@ -73,6 +73,40 @@ struct Nccl {
   }
 };
 
+// cuSOLVER through dlopen (ships with the CUDA toolkit of the image): Dsyevd for the LARGE density-matrix sectors.
+// The eigen-decomposition is O(sum d^3) once per block iteration (< 0.1 % of one sigma's flops): a plain library call,
+// like the reference's dsyev_ (MatrixBLAS.C:396-401); small sectors use the hand-written Jacobi kernel.
+struct Cusolver {
+  void* h = nullptr;
+  void* handle = nullptr;
+  int (*Create)(void**) = nullptr;
+  int (*Destroy)(void*) = nullptr;
+  int (*SetStream)(void*, cudaStream_t) = nullptr;
+  int (*Dsyevd_bufferSize)(void*, int, int, int, const double*, int, const double*, int*) = nullptr;
+  int (*Dsyevd)(void*, int, int, int, double*, int, double*, double*, int, int*) = nullptr;
+  bool load(std::string& err) {
+    if (handle) return true;
+    if (!h) {
+      const char* env = getenv("B2D_CUSOLVER_LIB");
+      const char* names[] = {env, "libcusolver.so.11", "/usr/local/cuda/lib64/libcusolver.so.11", "libcusolver.so"};
+      for (const char* n : names) {
+        if (!n) continue;
+        h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+        if (h) break;
+      }
+      if (!h) { err = std::string("cannot dlopen cuSOLVER (set B2D_CUSOLVER_LIB): ") + dlerror(); return false; }
+      Create = (decltype(Create))dlsym(h, "cusolverDnCreate");
+      Destroy = (decltype(Destroy))dlsym(h, "cusolverDnDestroy");
+      SetStream = (decltype(SetStream))dlsym(h, "cusolverDnSetStream");
+      Dsyevd_bufferSize = (decltype(Dsyevd_bufferSize))dlsym(h, "cusolverDnDsyevd_bufferSize");
+      Dsyevd = (decltype(Dsyevd))dlsym(h, "cusolverDnDsyevd");
+      if (!Create || !Destroy || !SetStream || !Dsyevd_bufferSize || !Dsyevd) { err = "cuSOLVER symbols missing"; return false; }
+    }
+    if (Create(&handle) != 0) { err = "cusolverDnCreate failed"; handle = nullptr; return false; }
+    return true;
+  }
+};
+
 }  // namespace
 
 struct b2d_ctx {
@@ -148,6 +182,9 @@ struct b2d_ctx {
   int class_launches[2][B2D_NUM_TILE_CLASSES] = {};
 
   Nccl nccl;
+  Cusolver cusolver;
+  DevBuf eig_work, eig_info;
+  int eig_jacobi_max = 64;   // sectors up to this size use the hand-written Jacobi kernel, larger ones cusolverDnDsyevd
 };
 
 namespace {
@@ -439,8 +476,9 @@ void b2d_destroy(b2d_ctx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     if (ctx->nccl.comm) ctx->nccl.CommDestroy(ctx->nccl.comm);
+    if (ctx->cusolver.handle) ctx->cusolver.Destroy(ctx->cusolver.handle);
     for (auto& s : ctx->slabs) cudaFree(s.p);
-    DevBuf* bufs[] = {&ctx->staging, &ctx->desc_scratch, &ctx->work, &ctx->parts, &ctx->trace_buf, &ctx->flat_in, &ctx->flat_out, &ctx->psi_blocks, &ctx->diag_tasks,
+    DevBuf* bufs[] = {&ctx->staging, &ctx->desc_scratch, &ctx->work, &ctx->parts, &ctx->trace_buf, &ctx->eig_work, &ctx->eig_info, &ctx->flat_in, &ctx->flat_out, &ctx->psi_blocks, &ctx->diag_tasks,
                       &ctx->diag_begin, &ctx->partials, &ctx->scalars, &ctx->user_pool, &ctx->dav_pool, &ctx->rho, &ctx->eig_g, &ctx->eig_vt,
                       &ctx->eig_vals, &ctx->eig_sweeps, &ctx->sector_desc, &ctx->rot, &ctx->gather_desc, &ctx->gather_rows,
                       &ctx->rotated_arena, &ctx->dsched.buf};
@@ -467,6 +505,7 @@ int b2d_set_option(b2d_ctx* ctx, const char* key, double value) {
   else if (k == "sync_debug") ctx->sync_debug = value != 0;
   else if (k == "multi_stream") ctx->multi_stream = value != 0;
   else if (k == "slice_iters") ctx->slice_iters = (int)value;
+  else if (k == "eig_jacobi_max") ctx->eig_jacobi_max = (int)value;
   else if (k == "phase_timing") ctx->phase_timing = value != 0;
   else return fail(ctx, B2D_ERR_ARG, "unknown option " + k);
   return B2D_OK;
@@ -940,7 +979,7 @@ int b2d_davidson(b2d_ctx* ctx, int nroots, int guess_slot0, int diag_slot, doubl
     std::swap(R, B[nb]);
     ++nb;
   }
-  if (rc == B2D_OK) {
+  {   // also when the iteration cap stopped the solve: the caller gets the current Ritz pairs and B2D_ERR_NOCONV
     CU(cudaMemcpyAsync(ctx->h_pinned, theta, (size_t)nroots * 8, cudaMemcpyDeviceToHost, st));
     for (int i = 0; i < nroots; ++i) CU(cudaMemcpyAsync(user_vec(ctx, guess_slot0 + i), B[i], (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
     end_timing(ctx);
@@ -1078,12 +1117,50 @@ int b2d_diagonalise_dm(b2d_ctx* ctx, double* evals_out) {
   CU(ctx->eig_vt.reserve((size_t)ctx->rho_padded * 8));
   CU(ctx->eig_vals.reserve((size_t)nev * 8));
   CU(ctx->eig_sweeps.reserve((size_t)L.nq * 4));
-  int rc = upload_desc(ctx, ctx->sector_desc, sd.data(), sd.size() * sizeof(BlockDesc));
+  // small sectors: one CTA each in the Jacobi kernel; large sectors: cusolverDnDsyevd in place on the eigenvector buffer
+  std::vector<BlockDesc> small;
+  std::vector<int> large;
+  for (int q = 0; q < L.nq; ++q) {
+    if (L.dims[q] <= ctx->eig_jacobi_max) small.push_back(sd[q]); else large.push_back(q);
+  }
+  int rc = upload_desc(ctx, ctx->sector_desc, small.data(), small.size() * sizeof(BlockDesc));
   if (rc) return rc;
   begin_timing(ctx);
   CU(cudaMemcpyAsync(ctx->eig_g.p, ctx->rho.p, (size_t)ctx->rho_padded * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-  CU(launch_sector_eig((const BlockDesc*)ctx->sector_desc.p, L.nq, (double*)ctx->eig_g.p, (double*)ctx->eig_vt.p, (double*)ctx->eig_vals.p,
+  if (!large.empty())   // Dsyevd works in place: rho_q -> eigenvectors (the Jacobi kernel initialises its own sectors of eig_vt)
+    CU(cudaMemcpyAsync(ctx->eig_vt.p, ctx->rho.p, (size_t)ctx->rho_padded * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  CU(launch_sector_eig((const BlockDesc*)ctx->sector_desc.p, (int)small.size(), (double*)ctx->eig_g.p, (double*)ctx->eig_vt.p, (double*)ctx->eig_vals.p,
                        (int*)ctx->eig_sweeps.p, ctx->stream, &ctx->launches));
+  if (!large.empty()) {
+    std::string err;
+    if (!ctx->cusolver.load(err)) return fail(ctx, B2D_ERR_CUDA, err);
+    if (ctx->cusolver.SetStream(ctx->cusolver.handle, ctx->stream) != 0) return fail(ctx, B2D_ERR_CUDA, "cusolverDnSetStream failed");
+    int lwork_max = 0;
+    for (int q : large) {
+      int lw = 0;
+      const int d = L.dims[q];
+      if (ctx->cusolver.Dsyevd_bufferSize(ctx->cusolver.handle, 1, 0, d, (const double*)ctx->eig_vt.p + ctx->rho_off[q], pad_ld(d),
+                                          (const double*)ctx->eig_vals.p + sd[q].ref_off, &lw) != 0)
+        return fail(ctx, B2D_ERR_CUDA, "cusolverDnDsyevd_bufferSize failed");
+      lwork_max = std::max(lwork_max, lw);
+    }
+    CU(ctx->eig_work.reserve((size_t)std::max(lwork_max, 1) * 8));
+    CU(ctx->eig_info.reserve(large.size() * sizeof(int)));
+    for (size_t k = 0; k < large.size(); ++k) {
+      const int q = large[k], d = L.dims[q];
+      // rho_q is symmetric, so its row-major block IS a column-major matrix with lda = ld; on exit column k (= our row k) is
+      // eigenvector k and W is ascending: exactly the layout the Jacobi kernel leaves in eig_vt / eig_vals
+      int st = ctx->cusolver.Dsyevd(ctx->cusolver.handle, /*CUSOLVER_EIG_MODE_VECTOR*/ 1, /*CUBLAS_FILL_MODE_LOWER*/ 0, d,
+                                    (double*)ctx->eig_vt.p + ctx->rho_off[q], pad_ld(d), (double*)ctx->eig_vals.p + sd[q].ref_off,
+                                    (double*)ctx->eig_work.p, lwork_max, (int*)ctx->eig_info.p + k);
+      if (st != 0) return fail(ctx, B2D_ERR_CUDA, "cusolverDnDsyevd failed with status " + std::to_string(st));
+      ++ctx->launches;
+    }
+    std::vector<int> info(large.size());
+    CU(cudaMemcpyAsync(info.data(), ctx->eig_info.p, large.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    for (int v : info) if (v != 0) return fail(ctx, B2D_ERR_CUDA, "cusolverDnDsyevd did not converge (info " + std::to_string(v) + ")");
+  }
   end_timing(ctx);
   std::vector<double> raw(nev);
   CU(cudaMemcpyAsync(raw.data(), ctx->eig_vals.p, (size_t)nev * 8, cudaMemcpyDeviceToHost, ctx->stream));

@@ -152,7 +152,9 @@ int b2d_diagonal(b2d_ctx* ctx, int dst_slot);
  * diag_slot holds diag(H).  evals[nroots] receives the eigenvalues (h_diag.element(i), linear.C:344),
  * *n_multiply the number of H applications, *residual the last ||r||^2.
  * The Krylov vectors, sigma vectors, subspace matrix, its eigen-decomposition and the Olsen preconditioner all
- * stay on the device; the host only reads one convergence scalar per iteration. */
+ * stay on the device; the host only reads one convergence scalar per iteration.  The reference has no iteration cap
+ * (linear.C:214 `maxiter` is unused); the option "max_davidson_iter" (default 2000) stops a runaway solve: the current
+ * Ritz pairs are returned together with B2D_ERR_NOCONV. */
 int b2d_davidson(b2d_ctx* ctx, int nroots, int guess_slot0, int diag_slot, double normtol, int deflation_min,
                  int deflation_max, double* evals, int* n_multiply, double* residual);
 

@@ -142,6 +142,30 @@ def test_truncation_identical_sectors_and_counts(gpu_block):
             assert np.abs(rot[q] @ rot[q].T - ref_rot[q] @ ref_rot[q].T).max() < 1e-7
 
 
+def test_truncation_with_cusolver_sectors(golden):
+    """large sectors go through cusolverDnDsyevd instead of the Jacobi kernel: force it for every sector with > 2 states."""
+    rec, big = golden
+    sb = hotpath.spinblock_from_record(rec, device=0, options={"eig_jacobi_max": 2})
+    try:
+        nroots = int(rec["meta"][4])
+        sb.make_density([rec["psi%d" % i] for i in range(nroots)], rec["weights"])
+        evals = sb.diagonalise_dm()
+        rho = O.make_density(big, [big.unflatten(rec["psi%d" % i]) for i in range(nroots)], rec["weights"])
+        ref_evals, _ = O.diagonalise_dm(rho)
+        for a, b in zip(evals, ref_evals):
+            assert np.abs(a - b).max() < 1e-13
+        kept, err, rot = sb.select_states(int(rec["meta"][5]))
+        ref_rot = dumpio.rotation_from(rec)
+        assert list(kept) == [r.shape[1] for r in ref_rot]
+        assert abs(err - rec["error"][0]) < 1e-12
+        for q in range(len(rot)):
+            if rot[q].shape[1]:
+                assert np.abs(rot[q].T @ rot[q] - np.eye(rot[q].shape[1])).max() < 1e-12
+                assert np.abs(rot[q] @ rot[q].T - ref_rot[q] @ ref_rot[q].T).max() < 1e-7
+    finally:
+        sb.close()
+
+
 def test_transform_operators_matches_reference(gpu_block):
     rec, big, sb = gpu_block
     ref_rot = dumpio.rotation_from(rec)

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -181,6 +182,8 @@ struct b2d_ctx {
   double class_ms[2][B2D_NUM_TILE_CLASSES] = {};
   int class_launches[2][B2D_NUM_TILE_CLASSES] = {};
 
+  std::map<std::vector<int>, PsiLayout> layouts;   // wavefunction layouts for other target quanta (noise: O.psi sectors)
+  DevBuf dm_noise;
   Nccl nccl;
   Cusolver cusolver;
   DevBuf eig_work, eig_info;
@@ -439,7 +442,7 @@ void end_timing(b2d_ctx* ctx) { cudaEventRecord(ctx->ev[1], ctx->stream); }
 
 extern "C" {
 
-int b2d_abi_version(void) { return 1; }
+int b2d_abi_version(void) { return 2; }
 
 int b2d_create(int device, b2d_ctx** out) {
   if (!out) return B2D_ERR_ARG;
@@ -478,7 +481,7 @@ void b2d_destroy(b2d_ctx* ctx) {
     if (ctx->nccl.comm) ctx->nccl.CommDestroy(ctx->nccl.comm);
     if (ctx->cusolver.handle) ctx->cusolver.Destroy(ctx->cusolver.handle);
     for (auto& s : ctx->slabs) cudaFree(s.p);
-    DevBuf* bufs[] = {&ctx->staging, &ctx->desc_scratch, &ctx->work, &ctx->parts, &ctx->trace_buf, &ctx->eig_work, &ctx->eig_info, &ctx->flat_in, &ctx->flat_out, &ctx->psi_blocks, &ctx->diag_tasks,
+    DevBuf* bufs[] = {&ctx->staging, &ctx->desc_scratch, &ctx->work, &ctx->parts, &ctx->trace_buf, &ctx->eig_work, &ctx->eig_info, &ctx->dm_noise, &ctx->flat_in, &ctx->flat_out, &ctx->psi_blocks, &ctx->diag_tasks,
                       &ctx->diag_begin, &ctx->partials, &ctx->scalars, &ctx->user_pool, &ctx->dav_pool, &ctx->rho, &ctx->eig_g, &ctx->eig_vt,
                       &ctx->eig_vals, &ctx->eig_sweeps, &ctx->sector_desc, &ctx->rot, &ctx->gather_desc, &ctx->gather_rows,
                       &ctx->rotated_arena, &ctx->dsched.buf};
@@ -664,6 +667,7 @@ int b2d_plan(b2d_ctx* ctx, const int32_t* psi_dq, double core_energy, int hubbar
     } else ctx->flops_all = ctx->sched.flops_alg;
   } catch (const std::exception& e) { return fail(ctx, B2D_ERR_ARG, std::string("b2d_plan: ") + e.what()); }
   ctx->planned = true;
+  ctx->layouts.clear();
   ctx->have_eig = ctx->have_rot = ctx->have_rotated = false;
   if (ctx->has_device) {
     CU(cudaSetDevice(ctx->device));
@@ -1015,17 +1019,7 @@ int b2d_make_density(b2d_ctx* ctx, int nroots, int slot0, const double* weights)
   std::vector<std::vector<GSeg>> per(L.nq);
   for (int i = 0; i < nroots; ++i) {
     if (std::fabs(weights[i]) < 1e-20) continue;    // density.C:86 skips negligible weights
-    for (int p = 0; p < P.nblocks(); ++p) {
-      GSeg s;
-      memset(&s, 0, sizeof(s));
-      s.a = s.b = (int64_t)(slot0 + i) * P.Wp + P.dev_off[p];
-      s.a_base = s.b_base = B2D_BASE_SRC;
-      s.a_trans = 0; s.b_kmajor = 1;
-      s.lda = s.ldb = P.ld[p];
-      s.k = P.cols[p];
-      s.alpha = weights[i];
-      per[P.bl[p]].push_back(s);
-    }
+    add_density_segments(P, B2D_BASE_SRC, (int64_t)(slot0 + i) * P.Wp, weights[i], per);
   }
   for (int q = 0; q < L.nq; ++q) {
     GGroup G;
@@ -1428,8 +1422,190 @@ int b2d_rotated_op_download(b2d_ctx* ctx, int op_id, uint8_t* allowed, double* d
   return B2D_OK;
 }
 
+namespace {
+const PsiLayout& layout_for(b2d_ctx* ctx, const int* dq) {
+  std::vector<int> key(dq, dq + 3);
+  auto it = ctx->layouts.find(key);
+  if (it == ctx->layouts.end()) {
+    PsiLayout P;
+    P.build(ctx->side[0], ctx->side[1], dq);
+    it = ctx->layouts.emplace(key, std::move(P)).first;
+  }
+  return it->second;
+}
+
+// the operator arrays add_onedot_noise loops over (density.C:360-379), this rank's share
+std::vector<int> noise_operators(b2d_ctx* ctx) {
+  const Side& L = ctx->side[0];
+  bool has_cc = false, has_ddcomp = false;
+  for (const OpRec& o : L.ops) { has_cc = has_cc || o.optype == OP_CRE_CRE; has_ddcomp = has_ddcomp || o.optype == OP_DES_DESCOMP; }
+  std::vector<int> types = {OP_CRE};
+  if (has_cc) { types.push_back(OP_CRE_CRE); types.push_back(OP_CRE_DES); }
+  else if (has_ddcomp) { types.push_back(OP_DES_DESCOMP); types.push_back(OP_CRE_DESCOMP); }
+  std::vector<int> out;
+  for (int ty : types)
+    for (size_t m = 0; m < L.ops.size(); ++m) {
+      const OpRec& o = L.ops[m];
+      if (o.optype != ty || !o.dev) continue;
+      int owner = 0;
+      if (ctx->nranks > 1) owner = o.norb == 1 ? o.orbs[0] % ctx->nranks : trimap_2d(o.orbs[0], o.orbs[1], ctx->norbs) % ctx->nranks;
+      if (owner == ctx->rank) out.push_back((int)m);
+    }
+  return out;
+}
+}  // namespace
+
+int64_t b2d_wavefunction_size(b2d_ctx* ctx, const int32_t* dq) {
+  if (!ctx || !ctx->planned || !dq) return -1;
+  int q[3] = {dq[0], dq[1], dq[2]};
+  return layout_for(ctx, q).W;
+}
+
+int b2d_tensor_multiply_one_host(b2d_ctx* ctx, int side, int op_id, int transposed, const int32_t* dst_dq, double scale, const double* c_flat,
+                                 double* v_flat) {
+  NEED_DEVICE(); NEED_PLAN();
+  if (side < 0 || side > 1 || op_id < 0 || op_id >= (int)ctx->side[side].ops.size() || !dst_dq || !c_flat || !v_flat)
+    return fail(ctx, B2D_ERR_ARG, "b2d_tensor_multiply_one_host: bad arguments");
+  const OpRec& op = ctx->side[side].ops[op_id];
+  if (!op.dev && op.dev_size > 0) return fail(ctx, B2D_ERR_ARG, "b2d_tensor_multiply_one_host: operator is not resident on this rank");
+  CU(cudaSetDevice(ctx->device));
+  int q[3] = {dst_dq[0], dst_dq[1], dst_dq[2]};
+  const PsiLayout& Pd = layout_for(ctx, q);
+  const PsiLayout& Ps = ctx->psi;
+  if (Pd.W == 0) return B2D_OK;
+  // WORK: [ src (padded) | dst (padded) ], host images staged through flat_in / staging
+  Schedule S;
+  Chunk ch;
+  try {
+    add_one_op_groups(ctx->side[0], ctx->side[1], Ps, Pd, side, op, transposed != 0, scale, B2D_BASE_WORK, 0, B2D_BASE_WORK, Ps.Wp, ctx->am, ch.step1);
+  } catch (const std::exception& e) { return fail(ctx, B2D_ERR_ARG, e.what()); }
+  make_tiles(ch.step1, ctx->forced_class);
+  ch.nterms = 1;
+  ch.work = Ps.Wp + Pd.Wp;
+  S.work_max = ch.work;
+  S.chunks.push_back(std::move(ch));
+  DevSchedule D;
+  int rc = upload_schedule(ctx, S, D);
+  if (rc) return rc;
+  CU(ctx->work.reserve((size_t)S.work_max * 8));
+  double* src = (double*)ctx->work.p;
+  double* dst = src + Ps.Wp;
+  std::vector<BlockDesc> bd(Pd.nblocks());
+  for (int p = 0; p < Pd.nblocks(); ++p) { bd[p].ref_off = Pd.ref_off[p]; bd[p].dev_off = Pd.dev_off[p]; bd[p].rows = Pd.rows[p]; bd[p].cols = Pd.cols[p]; bd[p].ld = Pd.ld[p]; bd[p].pad = 0; }
+  rc = upload_desc(ctx, ctx->desc_scratch, bd.data(), bd.size() * sizeof(BlockDesc));
+  if (rc) return rc;
+  CU(ctx->staging.reserve((size_t)Pd.W * 8));
+  CU(cudaMemsetAsync(ctx->work.p, 0, (size_t)S.work_max * 8, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->flat_in.p, c_flat, (size_t)Ps.W * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CU(launch_pack((const BlockDesc*)ctx->psi_blocks.p, Ps.nblocks(), (const double*)ctx->flat_in.p, src, ctx->stream, &ctx->launches));
+  CU(cudaMemcpyAsync(ctx->staging.p, v_flat, (size_t)Pd.W * 8, cudaMemcpyHostToDevice, ctx->stream));      // v += ...
+  CU(launch_pack((const BlockDesc*)ctx->desc_scratch.p, Pd.nblocks(), (const double*)ctx->staging.p, dst, ctx->stream, &ctx->launches));
+  rc = run_schedule(ctx, S, D, nullptr, nullptr, nullptr);
+  if (rc) return rc;
+  CU(launch_unpack((const BlockDesc*)ctx->desc_scratch.p, Pd.nblocks(), dst, (double*)ctx->staging.p, ctx->stream, &ctx->launches));
+  CU(cudaMemcpyAsync(v_flat, ctx->staging.p, (size_t)Pd.W * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  D.buf.release();
+  return B2D_OK;
+}
+
+int b2d_add_onedot_noise(b2d_ctx* ctx, int nroots, int slot0, double noise) {
+  NEED_DEVICE(); NEED_PLAN();
+  if (!ctx->rho.p) return fail(ctx, B2D_ERR_ARG, "b2d_add_onedot_noise: call b2d_make_density first");
+  for (int i = 0; i < nroots; ++i) CHECK_SLOT(slot0 + i);
+  if (!(noise > 1e-15) || nroots < 1) return B2D_OK;                          // NUMERICAL_ZERO, density.C:40
+  if (ctx->hubbard) return B2D_OK;                                             // reference quirk: rho_n is never added for HUBBARD (density.C:358-392)
+  CU(cudaSetDevice(ctx->device));
+  const Side& L = ctx->side[0];
+  const PsiLayout& Ps = ctx->psi;
+  const std::vector<int> ops = noise_operators(ctx);
+  // work items: (operator, +dQ with the operator / -dQ with its transpose, coupled spin)      density.C:203-237
+  struct Item { int op; bool t; int dq[3]; };
+  std::vector<Item> items;
+  for (int m : ops) {
+    const OpRec& o = L.ops[m];
+    const int irrep = Ps.dq[2] ^ o.dq[2];
+    for (int spin = std::abs(Ps.dq[1] - o.dq[1]); spin <= Ps.dq[1] + o.dq[1]; spin += 2)
+      for (int sign = +1; sign >= -1; sign -= 2) {
+        Item it{m, sign < 0, {Ps.dq[0] + sign * o.dq[0], spin, irrep}};
+        if (layout_for(ctx, it.dq).W > 0) items.push_back(it);
+      }
+  }
+  std::vector<BlockDesc> sectors = density_blocks(ctx);
+  int rc = upload_desc(ctx, ctx->sector_desc, sectors.data(), sectors.size() * sizeof(BlockDesc));
+  if (rc) return rc;
+  CU(ctx->dm_noise.reserve((size_t)ctx->rho_padded * 8));
+  double* partials = (double*)ctx->partials.p;
+  double* misc = (double*)ctx->scalars.p + 2080;
+  const int64_t budget = (int64_t)(ctx->workspace_mb * 1024.0 * 1024.0 / 8.0);
+  begin_timing(ctx);
+  for (int root = 0; root < nroots; ++root) {
+    CU(cudaMemsetAsync(ctx->dm_noise.p, 0, (size_t)ctx->rho_padded * 8, ctx->stream));
+    size_t next = 0;
+    while (next < items.size()) {
+      // chunk of items whose O.psi vectors fit the workspace
+      Schedule S;
+      Chunk ch;
+      std::vector<std::pair<int64_t, int64_t>> vecs;   // (offset, padded length) of each O.psi in WORK
+      std::vector<std::vector<GSeg>> per(L.nq);
+      try {
+        while (next < items.size()) {
+          const Item& it = items[next];
+          const PsiLayout& Pd = layout_for(ctx, it.dq);
+          if (!vecs.empty() && ch.work + Pd.Wp > budget) break;
+          add_one_op_groups(ctx->side[0], ctx->side[1], Ps, Pd, 0, L.ops[it.op], it.t, 1.0, B2D_BASE_SRC, (int64_t)(slot0 + root) * Ps.Wp,
+                            B2D_BASE_WORK, ch.work, ctx->am, ch.step1);
+          add_density_segments(Pd, B2D_BASE_WORK, ch.work, 1.0, per);        // MultiplyProduct(opxwave, Transpose(opxwave), dm, 1.0)
+          vecs.emplace_back(ch.work, Pd.Wp);
+          ch.work += Pd.Wp;
+          ++next;
+        }
+      } catch (const std::exception& e) { return fail(ctx, B2D_ERR_ARG, e.what()); }
+      for (int q = 0; q < L.nq; ++q) {
+        if (per[q].empty()) continue;
+        GGroup G;
+        memset(&G, 0, sizeof(G));
+        G.c = ctx->rho_off[q]; G.c_base = B2D_BASE_AUX; G.ldc = pad_ld(L.dims[q]); G.m = G.n = L.dims[q]; G.accumulate = 1;
+        G.seg_begin = (int)ch.step2.segs.size();
+        ch.step2.segs.insert(ch.step2.segs.end(), per[q].begin(), per[q].end());
+        G.seg_end = (int)ch.step2.segs.size();
+        ch.step2.groups.push_back(G);
+      }
+      make_tiles(ch.step1, ctx->forced_class);
+      make_tiles(ch.step2, ctx->forced_class);
+      ch.nterms = (int)vecs.size();
+      S.work_max = ch.work;
+      S.chunks.push_back(std::move(ch));
+      DevSchedule D;
+      rc = upload_schedule(ctx, S, D);
+      if (rc) return rc;
+      CU(ctx->work.reserve((size_t)std::max<int64_t>(S.work_max, 16) * 8));
+      CU(cudaMemsetAsync(ctx->work.p, 0, (size_t)S.work_max * 8, ctx->stream));
+      double* bases[B2D_NUM_BASES] = {nullptr, (double*)ctx->user_pool.p, (double*)ctx->work.p, nullptr, (double*)ctx->dm_noise.p};
+      CU(launch_gemm_batch(D.chunks[0].s1, bases, ctx->stream, &ctx->launches));                     // every O.psi of the chunk
+      for (const auto& v : vecs)                                                                    // normalise, vanishing ones -> 0 (:220-224)
+        CU(launch_normalise_guarded((double*)ctx->work.p + v.first, v.second, 1e-15, partials, misc, ctx->stream, &ctx->launches));
+      CU(launch_gemm_batch(D.chunks[0].s2, bases, ctx->stream, &ctx->launches));                     // rho_n += (O psi)(O psi)^T
+      CU(cudaStreamSynchronize(ctx->stream));
+      D.buf.release();
+    }
+    rc = allreduce(ctx, (double*)ctx->dm_noise.p, ctx->rho_padded);                                  // distributedaccumulate(dm[0]), density.C:255
+    if (rc) return rc;
+    CU(launch_trace((const BlockDesc*)ctx->sector_desc.p, L.nq, (const double*)ctx->dm_noise.p, misc, ctx->stream, &ctx->launches));
+    CU(cudaMemcpyAsync(ctx->h_pinned, misc, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    const double norm = ctx->h_pinned[0];
+    if (norm > 1.0)                                                                                 // density.C:388-389
+      CU(launch_axpy((double*)ctx->rho.p, (const double*)ctx->dm_noise.p, nullptr, (noise / nroots) / norm, ctx->rho_padded, ctx->stream, &ctx->launches));
+  }
+  end_timing(ctx);
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->have_eig = ctx->have_rot = ctx->have_rotated = false;
+  return B2D_OK;
+}
+
 int b2d_renormalise_from(b2d_ctx* ctx, int nroots, int guess_slot0, const double* weights, double normtol, int keep_states, int deflation_min,
-                         int deflation_max, double* energies, int32_t* kept_counts, double* discarded, int* n_multiply) {
+                         int deflation_max, double noise, double* energies, int32_t* kept_counts, double* discarded, int* n_multiply) {
   NEED_DEVICE(); NEED_PLAN();
   // diag(H) goes to the slot after the guesses (solver.C:34)
   int diag_slot = guess_slot0 + nroots;
@@ -1442,6 +1618,8 @@ int b2d_renormalise_from(b2d_ctx* ctx, int nroots, int guess_slot0, const double
   rc = b2d_davidson(ctx, nroots, guess_slot0, diag_slot, normtol, deflation_min, deflation_max, energies, n_multiply, nullptr);   // solver.C:91
   if (rc) return rc;
   rc = b2d_make_density(ctx, nroots, guess_slot0, weights);                                                                        // renormalise.C:104
+  if (rc) return rc;
+  rc = b2d_add_onedot_noise(ctx, nroots, guess_slot0, noise);                                                                      // density.C:40-60
   if (rc) return rc;
   rc = b2d_diagonalise_dm(ctx, nullptr);                                                                                           // :113 -> rotationmat.C:258
   if (rc) return rc;

@@ -308,6 +308,38 @@ cudaError_t launch_normalise(double* r, int64_t n, double* partials, double* scr
   return launch_mgs_step(r, nullptr, n, partials, scratch1, s, launches);
 }
 
+__global__ void __launch_bounds__(L1_THREADS) guarded_scale_kernel(double* __restrict__ r, const double* __restrict__ dots, double tiny, int64_t n) {
+  const double nrm = dots[0];
+  const double inv = fabs(nrm) > tiny ? 1.0 / sqrt(nrm) : 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) r[i] *= inv;
+}
+cudaError_t launch_normalise_guarded(double* r, int64_t n, double tiny, double* partials, double* scratch1, cudaStream_t s, int64_t* launches) {
+  const int grid = l1_grid(n);
+  mgs_dots_kernel<<<grid, L1_THREADS, 0, s>>>(r, nullptr, n, partials);
+  B2D_LAUNCH_CHECK();
+  finish_kernel<<<1, 256, 0, s>>>(partials, grid, 1, scratch1);
+  B2D_LAUNCH_CHECK();
+  guarded_scale_kernel<<<grid, L1_THREADS, 0, s>>>(r, scratch1, tiny, n);
+  B2D_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+__global__ void __launch_bounds__(256) trace_kernel(const BlockDesc* __restrict__ sectors, int nsectors, const double* __restrict__ buf, double* __restrict__ out) {
+  __shared__ double sh[32];
+  double acc = 0.0;
+  for (int q = 0; q < nsectors; ++q) {
+    const BlockDesc d = sectors[q];
+    for (int i = threadIdx.x; i < d.rows; i += blockDim.x) acc += buf[d.dev_off + (int64_t)i * d.ld + i];
+  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) out[0] = acc;
+}
+cudaError_t launch_trace(const BlockDesc* sectors, int nsectors, const double* buf, double* out, cudaStream_t s, int64_t* launches) {
+  trace_kernel<<<1, 256, 0, s>>>(sectors, nsectors, buf, out);
+  B2D_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
 __global__ void __launch_bounds__(L1_THREADS) axpy_kernel(double* __restrict__ y, const double* __restrict__ x, const double* __restrict__ coef, double mult, int64_t n) {
   const double a = coef ? mult * coef[0] : mult;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) y[i] += a * x[i];

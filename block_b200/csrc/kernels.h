@@ -47,6 +47,10 @@ cudaError_t launch_olsen(double* r, const double* c0, const double* diag, const 
 cudaError_t launch_mgs_step(double* r, const double* b, int64_t n, double* partials, double* scratch2, cudaStream_t s, int64_t* launches);
 // r <- r / |r|
 cudaError_t launch_normalise(double* r, int64_t n, double* partials, double* scratch1, cudaStream_t s, int64_t* launches);
+// r <- r / |r| if |r|^2 > tiny, else r <- 0  (noise wavefunctions O.psi, density.C:220-224: a vanishing one is skipped)
+cudaError_t launch_normalise_guarded(double* r, int64_t n, double tiny, double* partials, double* scratch1, cudaStream_t s, int64_t* launches);
+// out[0] = sum over sectors of the trace of the d x d block at buf + dev_off (leading dimension ld)
+cudaError_t launch_trace(const BlockDesc* sectors, int nsectors, const double* buf, double* out, cudaStream_t s, int64_t* launches);
 // y += mult * coef[0] * x  (coef on the device; coef == nullptr means 1)
 cudaError_t launch_axpy(double* y, const double* x, const double* coef, double mult, int64_t n, cudaStream_t s, int64_t* launches);
 cudaError_t launch_scale(double* x, double a, int64_t n, cudaStream_t s, int64_t* launches);

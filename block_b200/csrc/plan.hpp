@@ -478,6 +478,78 @@ inline Schedule build_schedule(const Side& L, const Side& R, const PsiLayout& P,
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// one-operator products (operatorfunctions::TensorMultiply(ablock, a, cblock, c, v, dQ, scale), operatorfunctions.C:331-404)
+// and wavefunction outer products (MultiplyProduct, operatorfunctions.C:630-650) as single-step grouped contractions
+// ---------------------------------------------------------------------------------------------------------------
+// dst (layout Pd, vector at dst_base + dst_off) += scale (a x 1) src   [side 0]   or   scale (1 x a) src   [side 1];
+// src has layout Ps and lives at src_base + src_off.  One group per destination block, one segment per contributing
+// source block.  Returns the dgemm flops.
+inline double add_one_op_groups(const Side& L, const Side& R, const PsiLayout& Ps, const PsiLayout& Pd, int side, const OpRec& op, bool transposed,
+                                double scale, uint8_t src_base, int64_t src_off, uint8_t dst_base, int64_t dst_off, AngMom& am, GemmBatch& batch) {
+  const Side& S = side == 0 ? L : R;
+  View a{&S, &op, transposed};
+  const int Sc = Ps.dq[1], Sv = Pd.dq[1];
+  double flops = 0.0;
+  for (int p = 0; p < Pd.nblocks(); ++p) {
+    const int lQ = Pd.bl[p], rQ = Pd.br[p];
+    GGroup G;
+    std::memset(&G, 0, sizeof(G));
+    G.c = dst_off + Pd.dev_off[p]; G.c_base = dst_base; G.ldc = Pd.ld[p]; G.m = Pd.rows[p]; G.n = Pd.cols[p]; G.accumulate = 1;
+    G.seg_begin = (int)batch.segs.size();
+    if (side == 0) {
+      for (int lQp = 0; lQp < L.nq; ++lQp) {                                              // :347-366
+        if (!a.allowed(lQ, lQp) || !Ps.allowed(lQp, rQ)) continue;
+        double fac = scale * am.ninej(L.quantum(lQp)[1], R.quantum(rQ)[1], Sc, a.spin(), 0, a.spin(), L.quantum(lQ)[1], R.quantum(rQ)[1], Sv);
+        fac *= a.scaling(am, lQ, lQp);
+        flops += 2.0 * L.dims[lQ] * L.dims[lQp] * R.dims[rQ];
+        if (fac == 0.0) continue;
+        const int ps = Ps.blk[(size_t)lQp * Ps.nr + rQ];
+        GSeg sg;
+        std::memset(&sg, 0, sizeof(sg));
+        sg.a = (int64_t)(intptr_t)op.dev + 8 * a.stored_off(lQ, lQp); sg.a_base = B2D_BASE_ABS; sg.a_trans = transposed ? 1 : 0; sg.lda = a.stored_ld(lQ, lQp);
+        sg.b = src_off + Ps.dev_off[ps]; sg.b_base = src_base; sg.b_kmajor = 0; sg.ldb = Ps.ld[ps];
+        sg.k = L.dims[lQp]; sg.alpha = fac;
+        batch.segs.push_back(sg);
+      }
+    } else {
+      for (int rQp = 0; rQp < R.nq; ++rQp) {                                              // :378-397
+        if (!a.allowed(rQ, rQp) || !Ps.allowed(lQ, rQp)) continue;
+        double fac = scale * am.ninej(L.quantum(lQ)[1], R.quantum(rQp)[1], Sc, 0, a.spin(), a.spin(), L.quantum(lQ)[1], R.quantum(rQ)[1], Sv);
+        fac *= a.scaling(am, rQ, rQp);
+        if (a.fermion() && (L.quantum(lQ)[0] & 1)) fac = -fac;
+        flops += 2.0 * L.dims[lQ] * R.dims[rQp] * R.dims[rQ];
+        if (fac == 0.0) continue;
+        const int ps = Ps.blk[(size_t)lQ * Ps.nr + rQp];
+        GSeg sg;
+        std::memset(&sg, 0, sizeof(sg));
+        sg.a = src_off + Ps.dev_off[ps]; sg.a_base = src_base; sg.a_trans = 0; sg.lda = Ps.ld[ps];
+        sg.b = (int64_t)(intptr_t)op.dev + 8 * a.stored_off(rQ, rQp); sg.b_base = B2D_BASE_ABS; sg.b_kmajor = transposed ? 0 : 1; sg.ldb = a.stored_ld(rQ, rQp);
+        sg.k = R.dims[rQp]; sg.alpha = fac;
+        batch.segs.push_back(sg);
+      }
+    }
+    G.seg_end = (int)batch.segs.size();
+    if (G.seg_end > G.seg_begin) batch.groups.push_back(G);
+  }
+  return flops;
+}
+
+// per left sector lQ: segments of  rho[lQ] += alpha * w[lQ,rQ] w[lQ,rQ]^T  for the wavefunction (layout P) at base + off
+inline void add_density_segments(const PsiLayout& P, uint8_t base, int64_t off, double alpha, std::vector<std::vector<GSeg>>& per_sector) {
+  for (int p = 0; p < P.nblocks(); ++p) {
+    GSeg s;
+    std::memset(&s, 0, sizeof(s));
+    s.a = s.b = off + P.dev_off[p];
+    s.a_base = s.b_base = base;
+    s.a_trans = 0; s.b_kmajor = 1;
+    s.lda = s.ldb = P.ld[p];
+    s.k = P.cols[p];
+    s.alpha = alpha;
+    per_sector[P.bl[p]].push_back(s);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // diag(H)
 // ---------------------------------------------------------------------------------------------------------------
 inline void build_diag_tasks(const Side& L, const Side& R, const PsiLayout& P, const std::vector<Term>& terms, double core_energy,

@@ -171,8 +171,8 @@ void SpinBlock::RenormaliseFrom(std::vector<double>& energies, std::vector<doubl
                                 std::vector<Wavefunction>* solution, const std::vector<double>* weights) {
   b2d_ctx* c = big.context();
   if (!c || big.get_leftBlock() != this) { fprintf(stderr, "block_b200: RenormaliseFrom: `this` must be the left child of `big`\n"); abort(); }
-  if (noise != 0.0 || additional_noise != 0.0 || onedot || keptqstates != 0 || currentRoot >= 0 || !lowerStates.empty() || !solution || solution->empty()) {
-    fprintf(stderr, "block_b200: RenormaliseFrom: only the two-dot, noise-free, state-averaged form with caller-supplied guesses is on the GPU path yet\n");
+  if (additional_noise != 0.0 || onedot || keptqstates != 0 || currentRoot >= 0 || !lowerStates.empty() || !solution || solution->empty()) {
+    fprintf(stderr, "block_b200: RenormaliseFrom: only the two-dot, state-averaged form with caller-supplied guesses and without additional (random) noise is on the GPU path yet\n");
     abort();
   }
   const int nroots = (int)solution->size();
@@ -188,7 +188,7 @@ void SpinBlock::RenormaliseFrom(std::vector<double>& energies, std::vector<doubl
   energies.assign(nroots, 0.0);
   spins.assign(nroots, 0.0);
   int nmult = 0;
-  B2D_CK(c, b2d_renormalise_from(c, nroots, 0, w.data(), tol, keptstates, big.options().deflation_min, big.options().deflation_max, energies.data(),
+  B2D_CK(c, b2d_renormalise_from(c, nroots, 0, w.data(), tol, keptstates, big.options().deflation_min, big.options().deflation_max, noise, energies.data(),
                                  kept.data(), &error, &nmult));
   flat.assign((size_t)big.psi_size(), 0.0);
   for (int i = 0; i < nroots; ++i) {

@@ -235,18 +235,34 @@ class SpinBlock:
                                        C.byref(nm), C.byref(res)))
         return ev, [self.download(i) for i in range(n)], nm.value
 
-    def make_density(self, waves, weights):
-        """DensityMatrix::makedensitymatrix (noise 0): returns the per-sector blocks."""
+    def make_density(self, waves, weights, noise=0.0):
+        """DensityMatrix::makedensitymatrix(wave_solutions, big, weights, noise, 0, warmup): returns the per-sector blocks."""
         n = len(waves)
         self.reserve(n)
         for i, w in enumerate(waves):
             self.upload(i, w)
-        return self._density_from_slots(n, weights)
+        return self._density_from_slots(n, weights, noise)
 
-    def _density_from_slots(self, n, weights):
+    def _density_from_slots(self, n, weights, noise=0.0):
         w = np.ascontiguousarray(weights, dtype=np.float64)
         self._ck(self.lib.b2d_make_density(self._ctx, n, 0, _p(w, _lib.c_f64p)))
+        if noise > 0.0:
+            self._ck(self.lib.b2d_add_onedot_noise(self._ctx, n, 0, float(noise)))
         return self.density()
+
+    def wavefunction_size(self, dq):
+        q = np.asarray(dq, dtype=np.int32)
+        return int(self.lib.b2d_wavefunction_size(self._ctx, _p(q, _lib.c_i32p)))
+
+    def TensorMultiplyOne(self, side, op_id, c, v, dst_dq, transposed=False, scale=1.0):
+        """One-operator operatorfunctions::TensorMultiply(ablock, a, cblock, c, v, dQ, scale): v += scale (a x 1) c or (1 x a) c;
+        v is a flat wavefunction with target quantum dst_dq (returns v)."""
+        c = np.ascontiguousarray(c, dtype=np.float64)
+        q = np.asarray(dst_dq, dtype=np.int32)
+        assert c.size == self.size and v.size == self.wavefunction_size(dst_dq) and v.flags.c_contiguous
+        self._ck(self.lib.b2d_tensor_multiply_one_host(self._ctx, int(side), int(op_id), int(bool(transposed)), _p(q, _lib.c_i32p), float(scale),
+                                                       _p(c, _lib.c_f64p), _p(v, _lib.c_f64p)))
+        return v
 
     def density(self):
         flat = np.empty(int(self.lib.b2d_density_size(self._ctx)))
@@ -288,8 +304,8 @@ class SpinBlock:
         flat = np.concatenate([np.ascontiguousarray(r, dtype=np.float64).ravel() for r in rot] + [np.zeros(1)])
         self._ck(self.lib.b2d_rotation_upload(self._ctx, _p(kept, _lib.c_i32p), _p(flat, _lib.c_f64p)))
 
-    def RenormaliseFrom(self, guesses, weights, normtol, keep_states, deflation_min=2, deflation_max=20):
-        """SpinBlock::RenormaliseFrom (two-dot, noise 0): returns dict(energies, kept, error, n_multiply, rotation)."""
+    def RenormaliseFrom(self, guesses, weights, normtol, keep_states, deflation_min=2, deflation_max=20, noise=0.0):
+        """SpinBlock::RenormaliseFrom (two-dot): returns dict(energies, kept, error, n_multiply, rotation)."""
         n = len(guesses)
         self.reserve(n + 1)
         for i, g in enumerate(guesses):
@@ -300,7 +316,7 @@ class SpinBlock:
         err = C.c_double(0.0)
         nm = C.c_int(0)
         self._ck(self.lib.b2d_renormalise_from(self._ctx, n, 0, _p(w, _lib.c_f64p), float(normtol), int(keep_states), int(deflation_min),
-                                               int(deflation_max), _p(en, _lib.c_f64p), _p(kept, _lib.c_i32p), C.byref(err), C.byref(nm)))
+                                               int(deflation_max), float(noise), _p(en, _lib.c_f64p), _p(kept, _lib.c_i32p), C.byref(err), C.byref(nm)))
         return dict(energies=en, kept=kept, error=err.value, n_multiply=nm.value, rotation=self.rotation_matrices(kept),
                     solutions=[self.download(i) for i in range(n)])
 

@@ -140,6 +140,15 @@ int b2d_multiplyH_host(b2d_ctx* ctx, const double* c_flat, double* v_flat, int a
 int b2d_tensor_multiply(b2d_ctx* ctx, int left_op, int right_op, int flags, int opq_spin, double scale,
                         int src_slot, int dst_slot);
 
+/* One-operator form, operatorfunctions::TensorMultiply(ablock, a, cblock, c, v, dQ, scale) operatorfunctions.C:331-404:
+ * v += scale (a x 1) c (side 0) or scale (1 x a) c (side 1; fermion sign of the left sector included, :393), with HOST
+ * buffers.  c is a wavefunction of the planned target quantum; v is a wavefunction with target quantum dst_dq (the
+ * operator shifts the sector: Wavefunction(q, &big, onedot), density.C:215), flat in ITS FlattenInto order,
+ * b2d_wavefunction_size(ctx, dst_dq) doubles.  transposed != 0 applies the Transposeview of the operator. */
+int64_t b2d_wavefunction_size(b2d_ctx* ctx, const int32_t* dq);
+int b2d_tensor_multiply_one_host(b2d_ctx* ctx, int side, int op_id, int transposed, const int32_t* dst_dq, double scale, const double* c_flat,
+                                 double* v_flat);
+
 /* SpinBlock::diagonalH(DiagonalMatrix&) spinblock.h:240, spinblock.C:855-899: diag(H) in flat psi order. */
 int b2d_diagonal(b2d_ctx* ctx, int dst_slot);
 
@@ -163,6 +172,12 @@ int b2d_davidson(b2d_ctx* ctx, int nroots, int guess_slot0, int diag_slot, doubl
 /* DensityMatrix::makedensitymatrix (density.C:27-90, noise = 0): rho[q] = sum_i w_i sum_r psi_i[q,r] psi_i[q,r]^T
  * for the wavefunctions in slots slot0..slot0+nroots-1. */
 int b2d_make_density(b2d_ctx* ctx, int nroots, int slot0, const double* weights);
+/* DensityMatrix::add_onedot_noise (density.C:332-399, functor onedot_noise_f :181-258) for every root, as makedensitymatrix
+ * does when the schedule's noise > 0 (density.C:40-60): rho += (noise/nroots) / tr(rho_n) * rho_n with
+ * rho_n = sum_O (O psi)(O psi)^T / |O psi|^2 over the left block's CRE, CRE_CRE, CRE_DES (or DES_DESCOMP, CRE_DESCOMP) operators
+ * and their transposes, each into its +-dQ shifted sector.  Under a term partition every rank does its operators and rho_n
+ * is all-reduced.  Call after b2d_make_density.  (additional_noise / add_twodot_noise draws from glibc rand(): host side.) */
+int b2d_add_onedot_noise(b2d_ctx* ctx, int nroots, int slot0, double noise);
 int64_t b2d_density_size(const b2d_ctx* ctx);       /* sum_q d_q^2 */
 int b2d_density_download(b2d_ctx* ctx, double* rho);   /* blocks q = 0..nq-1, row-major d_q x d_q */
 int b2d_density_upload(b2d_ctx* ctx, const double* rho);
@@ -191,11 +206,11 @@ int b2d_rotated_sectors(const b2d_ctx* ctx, int32_t* old_index, int32_t* dims);
 int64_t b2d_rotated_op_size(const b2d_ctx* ctx, int op_id);
 int b2d_rotated_op_download(b2d_ctx* ctx, int op_id, uint8_t* allowed, double* data);
 
-/* SpinBlock::RenormaliseFrom (spinblock.h:247-251, renormalise.C:39-133), two-dot, noise = 0: diagonalH, Davidson
- * from the guesses in slot0.., density matrix, eigen-decomposition, state selection.  Leaves the solutions in the
- * guess slots and the rotation matrices on the device (follow with b2d_transform_operators). */
+/* SpinBlock::RenormaliseFrom (spinblock.h:247-251, renormalise.C:39-133), two-dot: diagonalH, Davidson from the guesses in
+ * slot0.., density matrix (+ one-dot noise if noise > 0), eigen-decomposition, state selection.  Leaves the solutions in
+ * the guess slots and the rotation matrices on the device (follow with b2d_transform_operators). */
 int b2d_renormalise_from(b2d_ctx* ctx, int nroots, int guess_slot0, const double* weights, double normtol,
-                         int keep_states, int deflation_min, int deflation_max, double* energies,
+                         int keep_states, int deflation_min, int deflation_max, double noise, double* energies,
                          int32_t* kept_counts, double* discarded, int* n_multiply);
 
 /* ---- multi-GPU: partition of operator terms, NCCL all-reduce of the partial sigma --------------------------- */

@@ -484,6 +484,121 @@ def make_density(big: Big, waves, weights):
     return rho
 
 
+class WaveLayout:
+    """Sector layout of a Wavefunction with target quantum dq on `big` (Wavefunction::initialise wavefunction.C:18-56):
+    the noise wavefunctions O.psi live in sectors shifted by the operator's quantum numbers."""
+
+    def __init__(self, big: Big, dq):
+        L, R = big.left, big.right
+        self.big, self.dq = big, tuple(int(x) for x in dq)
+        self.offsets, off = {}, 0
+        for l in range(len(L.dims)):
+            for r in range(len(R.dims)):
+                if qn_allow(self.dq, tuple(L.q[l]), tuple(R.q[r])):
+                    self.offsets[(l, r)] = off
+                    off += int(L.dims[l]) * int(R.dims[r])
+        self.size = off
+
+    def allowed(self, l, r):
+        return (l, r) in self.offsets
+
+    def zeros(self):
+        L, R = self.big.left, self.big.right
+        return {k: np.zeros((int(L.dims[k[0]]), int(R.dims[k[1]]))) for k in self.offsets}
+
+    def flatten(self, w):
+        out = np.zeros(self.size)
+        for k, o in self.offsets.items():
+            out[o:o + w[k].size] = w[k].ravel()
+        return out
+
+    def unflatten(self, flat):
+        L, R = self.big.left, self.big.right
+        return {k: np.array(flat[o:o + int(L.dims[k[0]]) * int(R.dims[k[1]])], dtype=np.float64).reshape(int(L.dims[k[0]]), int(R.dims[k[1]]))
+                for k, o in self.offsets.items()}
+
+
+def tensor_multiply_one(big: Big, a: View, a_is_left: bool, c, c_layout: WaveLayout, v, v_layout: WaveLayout, scale: float):
+    """One-operator operatorfunctions::TensorMultiply(ablock, a, cblock, c, v, dQ, scale), operatorfunctions.C:331-404:
+    v += scale (a x 1) c (a on the left child, :343-372) or scale (1 x a) c (right child, :374-402)."""
+    L, R = big.left, big.right
+    Sc, Sv = c_layout.dq[1], v_layout.dq[1]
+    nl, nr = len(L.dims), len(R.dims)
+    if a_is_left:
+        for lQ in range(nl):
+            for lQp in range(nl):
+                if not a.allowed(lQ, lQp):
+                    continue
+                for rQ in range(nr):
+                    if c_layout.allowed(lQp, rQ) and v_layout.allowed(lQ, rQ):
+                        fac = scale * ninej(L.q[lQp][1], R.q[rQ][1], Sc, a.spin, 0, a.spin, L.q[lQ][1], R.q[rQ][1], Sv)     # :357-359
+                        fac *= a.scaling(L.q[lQ], L.q[lQp])                                                                  # :363
+                        v[(lQ, rQ)] += fac * (a.mat(lQ, lQp) @ c[(lQp, rQ)])                                               # :364
+    else:
+        for rQ in range(nr):
+            for rQp in range(nr):
+                if not a.allowed(rQ, rQp):
+                    continue
+                for lQp in range(nl):
+                    if v_layout.allowed(lQp, rQ) and c_layout.allowed(lQp, rQp):
+                        fac = scale * ninej(L.q[lQp][1], R.q[rQp][1], Sc, 0, a.spin, a.spin, L.q[lQp][1], R.q[rQ][1], Sv)   # :386-388
+                        fac *= a.scaling(R.q[rQ], R.q[rQp])                                                                  # :392
+                        if a.fermion and L.q[lQp][0] % 2:                                                                    # :393
+                            fac = -fac
+                        v[(lQp, rQ)] += fac * (c[(lQp, rQp)] @ a.mat(rQ, rQp).T)                                           # :395
+
+
+def noise_operator_types(left: Block):
+    """Operator arrays add_onedot_noise loops over, density.C:360-379."""
+    types = [CRE] if left.array(CRE) else []
+    if left.array(CRE_CRE):
+        types += [CRE_CRE, CRE_DES]
+    elif left.array(DES_DESCOMP):
+        types += [DES_DESCOMP, CRE_DESCOMP]
+    return types
+
+
+def add_onedot_noise(big: Big, rho, wave, noise: float):
+    """DensityMatrix::add_onedot_noise density.C:332-399 with the functor onedot_noise_f :181-258:
+    rho += noise / tr(rho_n) * rho_n,  rho_n = sum_O (O psi)(O psi)^T / |O psi|^2 over the left block's CRE, CRE_CRE, CRE_DES
+    (or DES_DESCOMP, CRE_DESCOMP) operators and their transposes, each into the +-dQ shifted target sector.
+    Reference quirk kept: for HUBBARD the accumulated rho_n is never added (:358-392)."""
+    if big.hubbard:
+        return
+    L = big.left
+    wl = WaveLayout(big, big.psi_dq)
+    dmn = [np.zeros((int(d), int(d))) for d in L.dims]
+    wq = big.psi_dq
+    for optype in noise_operator_types(L):
+        for orbs, comps in L.array(optype):
+            for op in comps:
+                oq = op.dq
+                irrep = irrep_mul(wq[2], oq[2])
+                for spin in range(abs(wq[1] - oq[1]), wq[1] + oq[1] + 1, 2):                      # spinvec = wQ.s + oQ.s (:208)
+                    for sign, view in ((+1, View(op, False)), (-1, View(op, True))):              # :214-224 and :226-236
+                        vl = WaveLayout(big, (wq[0] + sign * oq[0], spin, irrep))
+                        opx = vl.zeros()
+                        tensor_multiply_one(big, view, True, wave, wl, opx, vl, 1.0)
+                        norm = sum(float(np.vdot(m, m)) for m in opx.values())
+                        if abs(norm) > NUMERICAL_ZERO:
+                            inv = 1.0 / math.sqrt(norm)
+                            for (l, r), m in opx.items():
+                                dmn[l] += (inv * m) @ (inv * m).T                                 # MultiplyProduct(opxwave, Transpose(opxwave), dm, 1.0)
+    norm = sum(float(np.trace(m)) for m in dmn)
+    if norm > 1.0:                                                                                # :388-389
+        for q in range(len(rho)):
+            rho[q] += (noise / norm) * dmn[q]
+
+
+def make_density_with_noise(big: Big, waves, weights, noise: float):
+    """DensityMatrix::makedensitymatrix density.C:27-82 (additional_noise = 0)."""
+    rho = make_density(big, waves, weights)
+    if noise > NUMERICAL_ZERO:
+        for w in waves:
+            add_onedot_noise(big, rho, w, noise / len(waves))                                     # :57-60
+    return rho
+
+
 def diagonalise_dm(rho):
     """diagonalise_dm rotationmat.C:258-279: per-sector dsyev ascending, eigenvalues < 1e-14 -> 0."""
     evals, evecs = [], []

@@ -155,7 +155,7 @@ int main(int argc, char** argv) {
   std::vector<double> energies, spins;
   double error = 0.0;
   std::vector<Matrix> rotateMatrix;
-  L.RenormaliseFrom(energies, spins, error, rotateMatrix, rec["meta"].i[5], 0, rec["dav_tol"].d[0], big, TRANSFORM, 0.0, 0.0, false, L, L, R, true, false,
+  L.RenormaliseFrom(energies, spins, error, rotateMatrix, rec["meta"].i[5], 0, rec["dav_tol"].d[0], big, TRANSFORM, rec["rdm.args"].d[0], 0.0, false, L, L, R, true, false,
                     0, -1, lower, &sol, &rec["weights"].d);
   write_rec(out, "energies", energies);
   write_rec(out, "error", std::vector<double>(1, error));

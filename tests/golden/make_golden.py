@@ -57,6 +57,38 @@ noreorder
 outputlevel 0
 warmup local_2site
 """, [7, 12]),
+    # schedule noise > 0: pins DensityMatrix::add_onedot_noise (density.C:332-399)
+    "c2_d2h_M30_noise": ("c2_d2h_smallM", ["reorder.dat"], """nelec 8
+spin 0
+irrep 1
+hf_occ integral
+schedule
+0 30 1.0e-6 1.0e-3
+end
+maxiter 3
+twodot
+sweep_tol 1e-9
+sym d2h
+orbitals FCIDUMP
+nroots 2
+weights 0.5 0.5
+reorder reorder.dat
+outputlevel 0
+""", [5, 12]),
+    "h2o_c1_M32_noise": ("h2o_nosym", [], """nelec 10
+spin 0
+irrep 1
+hf_occ integral
+schedule
+0 32 1.0e-7 1.0e-4
+end
+maxiter 3
+twodot
+sweep_tol 1e-9
+orbitals FCIDUMP
+noreorder
+outputlevel 0
+""", [14]),
     "h2o_c1_M32": ("h2o_nosym", [], """nelec 10
 spin 0
 irrep 1

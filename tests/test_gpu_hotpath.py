@@ -99,6 +99,35 @@ def test_tensor_multiply_single_terms(gpu_block):
         assert np.linalg.norm(got - ref) <= 1e-12 * max(np.linalg.norm(ref), 1e-30)
 
 
+def test_tensor_multiply_one_operator_form(gpu_block):
+    """operatorfunctions.C:331-404 on both children, plain and Transposeview, into the dQ-shifted target sectors."""
+    rec, big, sb = gpu_block
+    wl = O.WaveLayout(big, big.psi_dq)
+    c = wl.unflatten(rec["rpsi"])
+    checked = 0
+    for side, blk in enumerate((big.left, big.right)):
+        picks = {}
+        for k, op in enumerate(blk.ops):
+            picks.setdefault(op.optype, k)                      # first operator of every type
+        for k in picks.values():
+            op = blk.ops[k]
+            for sign, t in ((+1, False), (-1, True)):
+                for spin in range(abs(big.psi_dq[1] - op.dq[1]), big.psi_dq[1] + op.dq[1] + 1, 2):
+                    dq = (big.psi_dq[0] + sign * op.dq[0], spin, O.irrep_mul(big.psi_dq[2], op.dq[2]))
+                    vl = O.WaveLayout(big, dq)
+                    assert sb.wavefunction_size(dq) == vl.size
+                    if vl.size == 0:
+                        continue
+                    v = vl.zeros()
+                    O.tensor_multiply_one(big, O.View(op, t), side == 0, c, wl, v, vl, 0.75)
+                    ref = vl.flatten(v)
+                    v0 = np.cos(np.arange(vl.size))
+                    got = sb.TensorMultiplyOne(side, sb.op_ids[side][k], rec["rpsi"], v0.copy(), dq, transposed=t, scale=0.75)
+                    assert np.linalg.norm(got - v0 - ref) <= 1e-12 * max(np.linalg.norm(ref), 1e-30)
+                    checked += 1
+    assert checked >= 6
+
+
 def test_diagonal_matches_reference(gpu_block):
     rec, big, sb = gpu_block
     assert rel(sb.diagonalH(), rec["diag"]) < 1e-13
@@ -119,16 +148,16 @@ def test_davidson_matches_reference(gpu_block):
 def test_density_matches_reference(gpu_block):
     rec, big, sb = gpu_block
     nroots = int(rec["meta"][4])
-    rho = sb.make_density([rec["psi%d" % i] for i in range(nroots)], rec["weights"])
-    assert rel(np.concatenate([r.ravel() for r in rho]), rec["rdm.data"]) < 1e-13
+    rho = sb.make_density([rec["psi%d" % i] for i in range(nroots)], rec["weights"], noise=float(rec["rdm.args"][0]))
+    assert rel(np.concatenate([r.ravel() for r in rho]), rec["rdm.data"]) < 1e-13      # incl. add_onedot_noise in the *_noise fixtures
 
 
 def test_truncation_identical_sectors_and_counts(gpu_block):
     rec, big, sb = gpu_block
     nroots = int(rec["meta"][4])
-    sb.make_density([rec["psi%d" % i] for i in range(nroots)], rec["weights"])
+    sb.make_density([rec["psi%d" % i] for i in range(nroots)], rec["weights"], noise=float(rec["rdm.args"][0]))
     evals = sb.diagonalise_dm()
-    rho = O.make_density(big, [big.unflatten(rec["psi%d" % i]) for i in range(nroots)], rec["weights"])
+    rho = O.make_density_with_noise(big, [big.unflatten(rec["psi%d" % i]) for i in range(nroots)], rec["weights"], float(rec["rdm.args"][0]))
     ref_evals, _ = O.diagonalise_dm(rho)
     for a, b in zip(evals, ref_evals):
         assert np.abs(a - b).max() < 1e-13
@@ -148,9 +177,10 @@ def test_truncation_with_cusolver_sectors(golden):
     sb = hotpath.spinblock_from_record(rec, device=0, options={"eig_jacobi_max": 2})
     try:
         nroots = int(rec["meta"][4])
-        sb.make_density([rec["psi%d" % i] for i in range(nroots)], rec["weights"])
+        noise = float(rec["rdm.args"][0])
+        sb.make_density([rec["psi%d" % i] for i in range(nroots)], rec["weights"], noise=noise)
         evals = sb.diagonalise_dm()
-        rho = O.make_density(big, [big.unflatten(rec["psi%d" % i]) for i in range(nroots)], rec["weights"])
+        rho = O.make_density_with_noise(big, [big.unflatten(rec["psi%d" % i]) for i in range(nroots)], rec["weights"], noise)
         ref_evals, _ = O.diagonalise_dm(rho)
         for a, b in zip(evals, ref_evals):
             assert np.abs(a - b).max() < 1e-13
@@ -191,7 +221,7 @@ def test_renormalise_from_end_to_end(gpu_block):
     rec, big, sb = gpu_block
     nroots = int(rec["meta"][4])
     out = sb.RenormaliseFrom([rec["guess%d" % i] for i in range(nroots)], rec["weights"], float(rec["dav_tol"][0]), int(rec["meta"][5]),
-                             int(rec["dav_in"][4]), int(rec["dav_in"][5]))
+                             int(rec["dav_in"][4]), int(rec["dav_in"][5]), noise=float(rec["rdm.args"][0]))
     assert np.abs(out["energies"] - rec["energies"][:nroots]).max() < 1e-8
     ref_rot = dumpio.rotation_from(rec)
     assert list(out["kept"]) == [r.shape[1] for r in ref_rot]

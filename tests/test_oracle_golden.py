@@ -52,8 +52,12 @@ def test_density_truncation_rotation(golden):
     rec, big = golden
     nroots = int(rec["meta"][4])
     waves = [big.unflatten(rec["psi%d" % i]) for i in range(nroots)]
-    rho = O.make_density(big, waves, rec["weights"])
+    noise = float(rec["rdm.args"][0])       # > 0 in the *_noise fixtures: add_onedot_noise (density.C:332-399)
+    rho = O.make_density_with_noise(big, waves, rec["weights"], noise)
     assert rel(np.concatenate([r.ravel() for r in rho]), rec["rdm.data"]) < 1e-13
+    if noise > 0:
+        rho0 = O.make_density(big, waves, rec["weights"])
+        assert rel(np.concatenate([r.ravel() for r in rho0]), rec["rdm.data"]) > 1e-7      # the fixture really exercises the noise
     evals, evecs = O.diagonalise_dm(rho)
     kept, err = O.select_states(evals, int(rec["meta"][5]))
     ref_rot = dumpio.rotation_from(rec)

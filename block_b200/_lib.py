@@ -51,6 +51,7 @@ PROTOTYPES = {
     "b2d_tensor_multiply": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int]),
     "b2d_diagonal": (C.c_int, [ctx_p, C.c_int]),
     "b2d_davidson": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, c_f64p, C.POINTER(C.c_int), c_f64p]),
+    "b2d_davidson_lower": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int, c_f64p, C.POINTER(C.c_int), c_f64p]),
     "b2d_make_density": (C.c_int, [ctx_p, C.c_int, C.c_int, c_f64p]),
     "b2d_density_size": (C.c_int64, [ctx_p]),
     "b2d_density_download": (C.c_int, [ctx_p, c_f64p]),

@@ -899,7 +899,14 @@ int b2d_diagonal(b2d_ctx* ctx, int dst_slot) {
 // ---- Davidson ---------------------------------------------------------------------------------------------------
 int b2d_davidson(b2d_ctx* ctx, int nroots, int guess_slot0, int diag_slot, double normtol, int deflation_min, int deflation_max,
                  double* evals, int* n_multiply, double* residual) {
+  return b2d_davidson_lower(ctx, nroots, guess_slot0, diag_slot, normtol, deflation_min, deflation_max, 0, 0, evals, n_multiply, residual);
+}
+
+int b2d_davidson_lower(b2d_ctx* ctx, int nroots, int guess_slot0, int diag_slot, double normtol, int deflation_min, int deflation_max,
+                       int n_lower, int lower_slot0, double* evals, int* n_multiply, double* residual) {
   NEED_DEVICE(); NEED_PLAN();
+  if (n_lower < 0 || n_lower > 32) return fail(ctx, B2D_ERR_ARG, "b2d_davidson_lower: 0 <= n_lower <= 32");
+  for (int i = 0; i < n_lower; ++i) CHECK_SLOT(lower_slot0 + i);
   if (nroots < 1 || deflation_max > 30 || deflation_min < nroots || deflation_max <= deflation_min)
     return fail(ctx, B2D_ERR_ARG, "b2d_davidson: need nroots >= 1 and nroots <= deflation_min < deflation_max <= 30");
   for (int i = 0; i < nroots; ++i) CHECK_SLOT(guess_slot0 + i);
@@ -925,6 +932,30 @@ int b2d_davidson(b2d_ctx* ctx, int nroots, int guess_slot0, int diag_slot, doubl
   cudaStream_t st = ctx->stream;
   int64_t* L = &ctx->launches;
   begin_timing(ctx);
+  // lower states of a state-specific solve (linear.C:201-208, 311-317, 369-375): r <- r - <r|l>/<l|l> l, in the order given
+  std::vector<double> inv_ll(n_lower, 0.0);
+  if (n_lower > 0) {
+    for (int i = 0; i < n_lower; ++i) {
+      VecList x; x.p[0] = user_vec(ctx, lower_slot0 + i);
+      CU(launch_multi_dot(1, x, user_vec(ctx, lower_slot0 + i), n, partials, misc + 16 + i, st, L));
+    }
+    CU(cudaMemcpyAsync(ctx->h_pinned, misc + 16, (size_t)n_lower * 8, cudaMemcpyDeviceToHost, st));
+    CU(cudaStreamSynchronize(st));
+    for (int i = 0; i < n_lower; ++i) {
+      if (!(ctx->h_pinned[i] > 0.0)) return fail(ctx, B2D_ERR_ARG, "b2d_davidson_lower: a lower state has zero norm");
+      inv_ll[i] = 1.0 / ctx->h_pinned[i];
+    }
+  }
+  auto project_lower = [&](double* r) -> cudaError_t {
+    for (int i = 0; i < n_lower; ++i) {
+      VecList x; x.p[0] = user_vec(ctx, lower_slot0 + i);
+      cudaError_t e = launch_multi_dot(1, x, r, n, partials, misc + 2, st, L);
+      if (e != cudaSuccess) return e;
+      e = launch_axpy(r, user_vec(ctx, lower_slot0 + i), misc + 2, -inv_ll[i], n, st, L);
+      if (e != cudaSuccess) return e;
+    }
+    return cudaSuccess;
+  };
   for (int i = 0; i < nroots; ++i) CU(cudaMemcpyAsync(B[i], user_vec(ctx, guess_slot0 + i), (size_t)n * 8, cudaMemcpyDeviceToDevice, st));
   // Gram-Schmidt of the guesses (linear.C:190-198)
   for (int i = 0; i < nroots; ++i) {
@@ -934,6 +965,10 @@ int b2d_davidson(b2d_ctx* ctx, int nroots, int guess_slot0, int diag_slot, doubl
       CU(launch_axpy(B[i], B[j], misc, -1.0, n, st, L));
     }
     CU(launch_normalise(B[i], n, partials, misc, st, L));
+  }
+  if (n_lower > 0) {                                                   // linear.C:201-208: only b[0]
+    CU(project_lower(B[0]));
+    CU(launch_normalise(B[0], n, partials, misc, st, L));
   }
   int nb = nroots, nsig = 0, converged = 0, nmult = 0;
   double rnorm = 0.0;
@@ -968,6 +1003,11 @@ int b2d_davidson(b2d_ctx* ctx, int nroots, int guess_slot0, int diag_slot, doubl
         if (ctx->h_pinned[i] > normtol) { converged = i; break; }
     }
     CU(launch_residual(Sg[converged], B[converged], theta + converged, R, n, partials, misc + 4, st, L));   // :308-309, :323
+    if (n_lower > 0) {                                                 // :311-317, then rnorm = <r|r> of the projected residual
+      CU(project_lower(R));
+      VecList x; x.p[0] = R;
+      CU(launch_multi_dot(1, x, R, n, partials, misc + 4, st, L));
+    }
     CU(cudaMemcpyAsync(ctx->h_pinned, misc + 4, 8, cudaMemcpyDeviceToHost, st));
     CU(cudaStreamSynchronize(st));                                     // the one host read per iteration
     rnorm = ctx->h_pinned[0];
@@ -979,6 +1019,7 @@ int b2d_davidson(b2d_ctx* ctx, int nroots, int guess_slot0, int diag_slot, doubl
     CU(launch_olsen(R, B[converged], diag, theta + converged, n, partials, misc, st, L));                   // :331
     if (nb >= deflation_max) { nb = deflation_min; nsig = deflation_min; }                                  // :352-357
     for (int j = 0; j < nb; ++j) CU(launch_mgs_step(R, B[j], n, partials, misc, st, L));                    // :358-366
+    if (n_lower > 0) CU(project_lower(R));                                                                  // :369-375
     CU(launch_normalise(R, n, partials, misc, st, L));
     std::swap(R, B[nb]);
     ++nb;

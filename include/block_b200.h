@@ -166,6 +166,12 @@ int b2d_diagonal(b2d_ctx* ctx, int dst_slot);
  * Ritz pairs are returned together with B2D_ERR_NOCONV. */
 int b2d_davidson(b2d_ctx* ctx, int nroots, int guess_slot0, int diag_slot, double normtol, int deflation_min,
                  int deflation_max, double* evals, int* n_multiply, double* residual);
+/* The same solve with `lowerStates` (state-specific form, currentRoot >= 0; linear.C:201-208, 311-317, 369-375): the first guess,
+ * every residual (before its norm is taken) and every new Krylov vector are projected against the n_lower wavefunctions in slots
+ * lower_slot0.. as r <- r - <r|l>/<l|l> l, in the order given.  The caller has orthogonalised the lower states among
+ * themselves (solver.C:79-86).  n_lower = 0 is b2d_davidson. */
+int b2d_davidson_lower(b2d_ctx* ctx, int nroots, int guess_slot0, int diag_slot, double normtol, int deflation_min,
+                       int deflation_max, int n_lower, int lower_slot0, double* evals, int* n_multiply, double* residual);
 
 /* ---- renormalisation ---------------------------------------------------------------------------------------- */
 

@@ -425,15 +425,25 @@ def olsen_precondition(r, c0, e, diag):
     return precondition(r, e, diag)
 
 
-def block_davidson(hmul, guesses, diag, tol, defl_min=2, defl_max=20, max_iter=10000):
-    """Linear::block_davidson linear.C:179-385, state-averaged (no lower states).
+def block_davidson(hmul, guesses, diag, tol, defl_min=2, defl_max=20, max_iter=10000, lower=()):
+    """Linear::block_davidson linear.C:179-385.  `lower` = lowerStates of a state-specific solve (currentRoot >= 0), already
+    orthogonalised among themselves by the caller (solver.C:79-86); empty for the state-averaged form.
     hmul: flat -> flat.  Returns (eigenvalues[nroots], vectors, number of H applications)."""
     b = [np.array(g, dtype=np.float64) for g in guesses]
+    lower = [np.asarray(l, dtype=np.float64) for l in lower]
     nroots = len(b)
+
+    def project(r):                                               # :203-206, :311-317, :369-375
+        for l in lower:
+            r = r - (np.dot(r, l) / np.dot(l, l)) * l
+        return r
     for i in range(nroots):                                       # :190-198
         for j in range(i):
             b[i] = b[i] - np.dot(b[j], b[i]) * b[j]
         b[i] = b[i] / math.sqrt(np.dot(b[i], b[i]))
+    if lower:                                                     # :201-208: only b[0]
+        b[0] = project(b[0])
+        b[0] = b[0] / math.sqrt(np.dot(b[0], b[0]))
     sigma, converged, nmult = [], 0, 0
     for _ in range(max_iter):
         for i in range(len(sigma), len(b)):                       # :234-257
@@ -451,8 +461,8 @@ def block_davidson(hmul, guesses, diag, tol, defl_min=2, defl_max=20, max_iter=1
             r = sigma[i] - theta[i] * b[i]
             if np.dot(r, r) > tol:
                 converged = i
-        r = sigma[converged] - theta[converged] * b[converged]
-        rnorm = np.dot(r, r)
+        r = project(sigma[converged] - theta[converged] * b[converged])
+        rnorm = np.dot(r, r)                                      # :321-323, of the projected residual
         r = olsen_precondition(r, b[converged], theta[converged], diag)   # :331
         if rnorm < tol:                                           # :335
             converged += 1
@@ -464,6 +474,7 @@ def block_davidson(hmul, guesses, diag, tol, defl_min=2, defl_max=20, max_iter=1
         for j in range(len(b)):                                   # :358-366
             r = r / math.sqrt(np.dot(r, r))
             r = r - np.dot(r, b[j]) * b[j]
+        r = project(r)
         r = r / math.sqrt(np.dot(r, r))
         b.append(r)
     raise RuntimeError("davidson did not converge")

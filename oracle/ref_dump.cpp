@@ -148,6 +148,15 @@ void dump_block(Dumper& d, const string& p, SpinBlock& b, const std::set<int>* o
   d.ints(p + "nops", vector<int>{m});
 }
 
+// a deterministic non-trivial wavefunction ("rpsi")
+void fill_lcg(SparseMatrix& w) {
+  uint64_t st = 0x9E3779B97F4A7C15ull;
+  for (int l = 0; l < w.nrows(); ++l) for (int r = 0; r < w.ncols(); ++r) if (w.allowed(l, r)) {
+    Matrix& m = w.operator_element(l, r);
+    for (int k = 0; k < m.Storage(); ++k) { st = st * 6364136223846793005ull + 1442695040888963407ull; m.Store()[k] = ((st >> 11) * (1.0 / 9007199254740992.0)) - 0.5; }
+  }
+}
+
 const std::set<int>& hot_optypes() {
   static std::set<int> s;
   if (s.empty()) { int t[] = {HAM, CRE, CRE_CRE, DES_DESCOMP, CRE_DES, CRE_DESCOMP, CRE_CRE_DESCOMP, OVERLAP}; s.insert(t, t + 8); }
@@ -202,11 +211,7 @@ void wrap_RenormaliseFrom(SpinBlock* self, vector<double>& energies, vector<doub
     for (int l = 0; l < w.nrows(); ++l) for (int r = 0; r < w.ncols(); ++r) allowed.push_back(w.allowed(l, r) ? 1 : 0);
     d.ints("psi_allowed", allowed, {(uint64_t)w.nrows(), (uint64_t)w.ncols()});
     // a deterministic non-trivial vector and the reference's sigma for it
-    uint64_t st = 0x9E3779B97F4A7C15ull;
-    for (int l = 0; l < w.nrows(); ++l) for (int r = 0; r < w.ncols(); ++r) if (w.allowed(l, r)) {
-      Matrix& m = w.operator_element(l, r);
-      for (int k = 0; k < m.Storage(); ++k) { st = st * 6364136223846793005ull + 1442695040888963407ull; m.Store()[k] = ((st >> 11) * (1.0 / 9007199254740992.0)) - 0.5; }
-    }
+    fill_lcg(w);
     Wavefunction v = w; v.Clear();
     big.multiplyH(w, &v, 1);
     vector<double> flat; flatten(w, flat); d.dbls("rpsi", flat); flatten(v, flat); d.dbls("rsigma", flat);
@@ -257,7 +262,9 @@ void wrap_davidson(vector<Wavefunction>& b, DiagonalMatrix& h_diag, double normt
 void wrap_davidson(vector<Wavefunction>& b, DiagonalMatrix& h_diag, double normtol, const bool& warmUp, Davidson_functor& h_multiply, bool& useprecond,
                    int currentRoot, vector<Wavefunction>& lowerStates) {
   long c0 = g_sigma_calls;
+  DiagonalMatrix diag_in;
   if (g_dump_this) {
+    diag_in = h_diag;
     Dumper d; d.open(g_path, true);
     vector<double> flat;
     for (size_t i = 0; i < b.size(); ++i) { std::ostringstream a; a << "guess" << i; flatten(b[i], flat); d.dbls(a.str(), flat); }
@@ -270,6 +277,20 @@ void wrap_davidson(vector<Wavefunction>& b, DiagonalMatrix& h_diag, double normt
     vector<double> ev; for (size_t i = 0; i < b.size() && (int)i < h_diag.Ncols(); ++i) ev.push_back(h_diag.element(i));
     d.dbls("dav_evals", ev);
     d.ints("dav_out", vector<int>{(int)(g_sigma_calls - c0), (int)b.size()});
+    // state-specific form (lowerStates, linear.C:201-208,311-317,369-375): one more solve of the reference's own block_davidson
+    // for ONE root, guess = the deterministic vector "rpsi", lower state = the converged root 0.  Pins the lower-state projections.
+    if (lowerStates.empty()) {
+      long c1 = g_sigma_calls;
+      vector<Wavefunction> lo(1, b[0]);
+      vector<Wavefunction> g1(1, b[0]);
+      fill_lcg(g1[0]);
+      DiagonalMatrix hd = diag_in;
+      bool up = useprecond;
+      real_davidson(g1, hd, normtol, warmUp, h_multiply, up, 1, lo);
+      d.dbls("ss_eval", vector<double>{hd.element(0)});
+      vector<double> flat; flatten(g1[0], flat); d.dbls("ss_psi", flat);
+      d.ints("ss_nmult", vector<int>{(int)(g_sigma_calls - c1)});
+    }
   }
 }
 

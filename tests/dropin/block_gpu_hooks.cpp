@@ -1,0 +1,528 @@
+// block_gpu: the UNMODIFIED reference sweep (sanshar/Block 1.1.1, oracle/_ref/libblockref.a) with its hot-path entry points
+// re-routed at LINK time (GNU ld --wrap) to libblockb200.so through the C ABI of include/block_b200.h.
+//
+// This is the reference-side binding of INTEGRATION.md made real and testable: no reference source is edited or copied,
+// dmrg.C / sweep.C / renormalise.C / solver.C run as they are (input parsing, block construction, guess wavefunctions, disk
+// checkpoints), and only the arithmetic of the path moves to the GPU:
+//
+//   SpinBlock::diagonalH              spinblock.C:855      (caller solver.C:34)      -> b2d_diagonal
+//   Linear::block_davidson            linear.C:179         (caller solver.C:91)      -> b2d_davidson_lower (device-resident Krylov space)
+//   SpinBlock::multiplyH              spinblock.C:722      (caller davidson.C:21)    -> b2d_multiplyH_host (only with B2D_DROPIN_DAVIDSON=host)
+//   DensityMatrix::makedensitymatrix  density.C:27         (caller renormalise.C:104)-> b2d_make_density (+ b2d_add_onedot_noise)
+//   diagonalise_dm                    rotationmat.C:258    (caller renormalise.C:145)-> b2d_diagonalise_dm
+//   assign_matrix_by_dm               rotationmat.C:149    (caller renormalise.C:164)-> b2d_select_states + b2d_rotation_download
+//   SpinBlock::transform_operators    save_load_block.C:267(caller sweep.C:279)      -> b2d_transform_operators; the reference's own
+//                                     bookkeeping (new StateInfo, core flags, freeing the children) still runs, with its
+//                                     MatrixRotate arithmetic (MatrixBLAS.C:553) switched off and the blocks filled from the device.
+//
+// TEST INFRASTRUCTURE: built by `make -C oracle dropin` into oracle/_ref/block_gpu (it contains reference objects, so it is
+// git-ignored like the rest of oracle/_ref and travels to the GPU box with the snapshot); driven by tests/test_gpu_dropin.py
+// and bench.py's sweep leg.  There is no CPU fallback: a mode the GPU path does not cover aborts with a message.
+//
+// Environment:
+//   B2D_DEVICE            CUDA device (default 0)
+//   B2D_DROPIN_CHECK=1    every hook ALSO runs the reference's CPU function on copies and prints the differences
+//   B2D_DROPIN_DAVIDSON   "device" (default): block_davidson on the GPU;  "host": the reference's block_davidson with
+//                         multiplyH through b2d_multiplyH_host (host buffers, the e2e form of the sigma call)
+//   B2D_DROPIN_WORKSPACE_MB   T workspace of the two-step contraction
+//   B2D_DROPIN_STATS      file that receives one line per block iteration (timings, flops, H applications)
+#include <sys/time.h>
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "wrap_syms_gpu.h"
+
+#include "spinblock.h"
+#include "wavefunction.h"
+#include "density.h"
+#include "rotationmat.h"
+#include "solver.h"
+#include "linear.h"
+#include "davidson.h"
+#include "global.h"
+#include "input.h"
+#include "operatorfunctions.h"
+#include "MatrixBLAS.h"
+
+#include "block_b200.h"
+
+using namespace SpinAdapted;
+using std::string;
+using std::vector;
+
+namespace {
+
+double now_s() { timeval tv; gettimeofday(&tv, 0); return tv.tv_sec + 1e-6 * tv.tv_usec; }
+bool env_on(const char* k) { const char* v = getenv(k); return v && *v && strcmp(v, "0") != 0; }
+
+[[noreturn]] void die(const string& msg) {
+  fprintf(stderr, "block_gpu: %s\n", msg.c_str());
+  fflush(stderr);
+  abort();   // the reference's error behaviour (MatrixBLAS.C:491-495)
+}
+
+struct OpRef { SparseMatrix* elem; int id; };
+
+struct Gpu {
+  b2d_ctx* ctx = 0;
+  const SpinBlock* big = 0;
+  vector<int> lsites, rsites;
+  vector<OpRef> left_ops;        // every operator element of the left child, in upload order
+  int nslots = 0;
+  int64_t W = 0;
+  bool rho_on_device = false;    // b2d_make_density ran for this block
+  bool rot_on_device = false;    // b2d_select_states ran for this block
+  bool in_transform = false;     // MatrixRotate is switched off
+  // statistics of the current block iteration
+  double t_upload = 0, t_diag = 0, t_dav = 0, t_rho = 0, t_eig = 0, t_rot = 0, dav_dev_ms = 0, flops = 0;
+  int nmult = 0, call = -1;
+  // check mode: CPU results kept between hooks
+  SparseMatrix* chk_transform = 0;
+  vector<DiagonalMatrix> chk_eigs;
+  DensityMatrix chk_vecs;
+} g;
+
+void ck(int rc, const char* what) {
+  if (rc) die(string(what) + ": " + b2d_last_error(g.ctx));
+}
+
+void flatten(const SparseMatrix& w, vector<double>& out) {   // Wavefunction::FlattenInto order, wavefunction.C:167-186
+  out.clear();
+  for (int l = 0; l < w.nrows(); ++l)
+    for (int r = 0; r < w.ncols(); ++r)
+      if (w.allowed(l, r)) {
+        const Matrix& m = w.operator_element(l, r);
+        out.insert(out.end(), m.Store(), m.Store() + m.Storage());
+      }
+}
+void collect(SparseMatrix& w, const vector<double>& in) {     // Wavefunction::CollectFrom, wavefunction.C:188-203
+  size_t off = 0;
+  for (int l = 0; l < w.nrows(); ++l)
+    for (int r = 0; r < w.ncols(); ++r)
+      if (w.allowed(l, r)) {
+        Matrix& m = w.operator_element(l, r);
+        if (off + m.Storage() > in.size()) die("collect: size mismatch");
+        memcpy(m.Store(), in.data() + off, sizeof(double) * m.Storage());
+        off += m.Storage();
+      }
+  if (off != in.size()) die("collect: size mismatch");
+}
+
+void release() {
+  if (g.ctx) b2d_destroy(g.ctx);
+  g.ctx = 0; g.big = 0; g.left_ops.clear(); g.nslots = 0; g.rho_on_device = g.rot_on_device = false;
+}
+
+void write_stats() {
+  const char* path = getenv("B2D_DROPIN_STATS");
+  if (!path || !g.ctx) return;
+  FILE* f = fopen(path, "a");
+  if (!f) return;
+  fprintf(f, "call=%d lsites=%d rsites=%d W=%lld sigma_flops=%.6e n_multiply=%d upload_s=%.6f diag_s=%.6f davidson_s=%.6f davidson_dev_ms=%.3f "
+             "density_s=%.6f eig_s=%.6f rotate_s=%.6f launches=%lld\n",
+          g.call, (int)g.lsites.size(), (int)g.rsites.size(), (long long)g.W, g.flops, g.nmult, g.t_upload, g.t_diag, g.t_dav, g.dav_dev_ms, g.t_rho,
+          g.t_eig, g.t_rot, (long long)b2d_kernel_launches(g.ctx));
+  fclose(f);
+}
+
+void upload_block(int side, SpinBlock& b, vector<OpRef>* keep) {
+  const StateInfo& s = b.get_stateInfo();
+  int nq = (int)s.quanta.size();
+  vector<int32_t> q(3 * nq), dims(nq);
+  for (int i = 0; i < nq; ++i) {
+    q[3 * i] = s.quanta[i].get_n(); q[3 * i + 1] = s.quanta[i].get_s().getirrep(); q[3 * i + 2] = s.quanta[i].get_symm().getirrep();
+    dims[i] = s.quantaStates[i];
+  }
+  vector<int32_t> sites(b.get_sites().begin(), b.get_sites().end());
+  ck(b2d_set_block(g.ctx, side, nq, q.data(), dims.data(), b.is_loopblock() ? 1 : 0, (int)sites.size(), sites.data()), "b2d_set_block");
+  vector<uint8_t> allowed((size_t)nq * nq);
+  vector<double> data;
+  for (std::map<opTypes, boost::shared_ptr<Op_component_base> >::iterator it = b.ops.begin(); it != b.ops.end(); ++it) {
+    Op_component_base& arr = *it->second;
+    for (int i = 0; i < arr.get_size(); ++i) {
+      vector<boost::shared_ptr<SparseMatrix> > vec = arr.get_local_element(i);
+      for (size_t c = 0; c < vec.size(); ++c) {
+        // direct-mode virtual operators are built here by the reference's own Op::build (host side of the seam)
+        boost::shared_ptr<SparseMatrix> rep = vec[c]->getworkingrepresentation(&b);
+        SparseMatrix& op = *rep;
+        if (op.get_deltaQuantum_size() != 1) die("operator with several deltaQuantum components (non spin-adapted / BCS run): not covered");
+        if (op.nrows() != nq || op.ncols() != nq) die("operator shape does not match the block's StateInfo");
+        int32_t orbs[2] = {-1, -1};
+        int norb = (int)op.get_orbs().size();
+        if (norb > 2) die("operator with more than two orbital indices on the sweep path");
+        for (int k = 0; k < norb; ++k) orbs[k] = op.get_orbs()[k];
+        SpinQuantum dq = op.get_deltaQuantum(0);
+        int32_t dqv[3] = {dq.get_n(), dq.get_s().getirrep(), dq.get_symm().getirrep()};
+        data.clear();
+        for (int a = 0; a < nq; ++a)
+          for (int bq = 0; bq < nq; ++bq) {
+            bool al = op.allowed(a, bq);
+            allowed[(size_t)a * nq + bq] = al ? 1 : 0;
+            if (al) { const Matrix& m = op.operator_element(a, bq); data.insert(data.end(), m.Store(), m.Store() + m.Storage()); }
+          }
+        if (data.empty()) data.push_back(0.0);
+        int id = -1;
+        ck(b2d_add_op(g.ctx, side, (int)it->first, norb, orbs, (int)c, dqv, op.get_fermion() ? 1 : 0, allowed.data(), data.data(), &id), "b2d_add_op");
+        if (keep) keep->push_back(OpRef{vec[c].get(), id});
+      }
+    }
+  }
+}
+
+// one context per big block (one block iteration); built at the first hook that sees the block (diagonalH, solver.C:34)
+void ensure_ctx(const SpinBlock& big_c) {
+  SpinBlock& big = const_cast<SpinBlock&>(big_c);
+  if (!big.get_leftBlock() || !big.get_rightBlock()) die("big block without children");
+  if (g.ctx && g.big == &big && g.lsites == big.get_leftBlock()->get_sites() && g.rsites == big.get_rightBlock()->get_sites()) return;
+  release();
+  if (!dmrginp.spinAdapted()) die("non spin-adapted run: not covered by the GPU path");
+  if (dmrginp.hamiltonian() != QUANTUM_CHEMISTRY && dmrginp.hamiltonian() != HUBBARD) die("Hamiltonian type not covered by the GPU path");
+  double t0 = now_s();
+  int dev = getenv("B2D_DEVICE") ? atoi(getenv("B2D_DEVICE")) : 0;
+  if (b2d_create(dev, &g.ctx)) die(string("b2d_create: ") + b2d_last_error(0));
+  if (getenv("B2D_DROPIN_WORKSPACE_MB")) ck(b2d_set_option(g.ctx, "workspace_mb", atof(getenv("B2D_DROPIN_WORKSPACE_MB"))), "b2d_set_option");
+  g.big = &big; g.lsites = big.get_leftBlock()->get_sites(); g.rsites = big.get_rightBlock()->get_sites();
+  upload_block(0, *big.get_leftBlock(), &g.left_ops);
+  upload_block(1, *big.get_rightBlock(), 0);
+  SpinQuantum tq = dmrginp.effective_molecule_quantum();
+  int32_t dq[3] = {tq.get_n(), tq.get_s().getirrep(), tq.get_symm().getirrep()};
+  int norbs = (int)dmrginp.spin_orbs_symmetry().size() / 2;
+  ck(b2d_plan(g.ctx, dq, coreEnergy[big.get_integralIndex()], dmrginp.hamiltonian() == HUBBARD ? 1 : 0, norbs, 0, 1), "b2d_plan");
+  g.W = b2d_psi_size(g.ctx);
+  g.flops = b2d_sigma_flops(g.ctx, 1);
+  g.t_upload = now_s() - t0;
+  g.t_diag = g.t_dav = g.t_rho = g.t_eig = g.t_rot = g.dav_dev_ms = 0; g.nmult = 0;
+  ++g.call;
+}
+
+void need_slots(int n) {
+  if (n > g.nslots) { ck(b2d_vec_reserve(g.ctx, n), "b2d_vec_reserve"); g.nslots = n; }
+}
+
+void upload_wave(int slot, const SparseMatrix& w) {
+  vector<double> flat; flatten(w, flat);
+  if ((int64_t)flat.size() != g.W) die("wavefunction size differs from the planned psi layout");
+  ck(b2d_vec_upload(g.ctx, slot, flat.data()), "b2d_vec_upload");
+}
+void download_wave(int slot, SparseMatrix& w) {
+  vector<double> flat((size_t)g.W);
+  ck(b2d_vec_download(g.ctx, slot, flat.data()), "b2d_vec_download");
+  collect(w, flat);
+}
+
+double max_abs_diff(const SparseMatrix& a, const SparseMatrix& b, double* scale = 0) {
+  vector<double> x, y; flatten(a, x); flatten(b, y);
+  if (x.size() != y.size()) return 1e300;
+  double d = 0, s = 0;
+  for (size_t i = 0; i < x.size(); ++i) { d = std::max(d, fabs(x[i] - y[i])); s = std::max(s, fabs(y[i])); }
+  if (scale) *scale = s;
+  return d;
+}
+
+const int DIAG_SLOT = 0, ROOT_SLOT0 = 1;
+
+}  // namespace
+
+// ---------------- wrapped entry points ----------------
+namespace SpinAdapted {
+
+// ---- SpinBlock::diagonalH ----
+void real_diagonalH(const SpinBlock* self, DiagonalMatrix& e) asm("__real_" SYM_diagonalH);
+void wrap_diagonalH(const SpinBlock* self, DiagonalMatrix& e) asm("__wrap_" SYM_diagonalH);
+void wrap_diagonalH(const SpinBlock* self, DiagonalMatrix& e) {
+  ensure_ctx(*self);
+  double t0 = now_s();
+  if ((int64_t)e.Ncols() != g.W) die("diagonalH: DiagonalMatrix length differs from the psi layout");
+  need_slots(ROOT_SLOT0 + 1);
+  ck(b2d_diagonal(g.ctx, DIAG_SLOT), "b2d_diagonal");
+  ck(b2d_vec_download(g.ctx, DIAG_SLOT, e.Store()), "b2d_vec_download");
+  g.t_diag += now_s() - t0;
+  if (env_on("B2D_DROPIN_CHECK")) {
+    DiagonalMatrix e2; e2.ReSize(e.Ncols()); e2 = 0;
+    real_diagonalH(self, e2);
+    double d = 0; for (int i = 0; i < e.Ncols(); ++i) d = std::max(d, fabs(e.element(i) - e2.element(i)));
+    fprintf(stderr, "B2D_CHECK call=%d diagonalH max_abs_diff=%.3e\n", g.call, d);
+  }
+}
+
+// ---- SpinBlock::multiplyH ----
+void real_multiplyH(const SpinBlock* self, Wavefunction& c, Wavefunction* v, int num_threads) asm("__real_" SYM_multiplyH);
+void wrap_multiplyH(const SpinBlock* self, Wavefunction& c, Wavefunction* v, int num_threads) asm("__wrap_" SYM_multiplyH);
+void wrap_multiplyH(const SpinBlock* self, Wavefunction& c, Wavefunction* v, int num_threads) {
+  ensure_ctx(*self);
+  vector<double> cf, vf; flatten(c, cf); flatten(*v, vf);
+  if ((int64_t)cf.size() != g.W || (int64_t)vf.size() != g.W) die("multiplyH: wavefunction size differs from the psi layout");
+  need_slots(ROOT_SLOT0 + 1);
+  ck(b2d_multiplyH_host(g.ctx, cf.data(), vf.data(), 1), "b2d_multiplyH_host");   // v += H c (linear.C:239-253)
+  ++g.nmult;
+  if (env_on("B2D_DROPIN_CHECK")) {
+    Wavefunction v2 = *v;
+    real_multiplyH(self, c, &v2, num_threads);
+    collect(*v, vf);
+    double s; double d = max_abs_diff(*v, v2, &s);
+    fprintf(stderr, "B2D_CHECK call=%d multiplyH max_abs_diff=%.3e (max |sigma| %.3e)\n", g.call, d, s);
+    return;
+  }
+  collect(*v, vf);
+}
+
+// ---- Linear::block_davidson ----
+void real_davidson(vector<Wavefunction>& b, DiagonalMatrix& h_diag, double normtol, const bool& warmUp, Davidson_functor& h_multiply, bool& useprecond,
+                   int currentRoot, vector<Wavefunction>& lowerStates) asm("__real_" SYM_block_davidson);
+void wrap_davidson(vector<Wavefunction>& b, DiagonalMatrix& h_diag, double normtol, const bool& warmUp, Davidson_functor& h_multiply, bool& useprecond,
+                   int currentRoot, vector<Wavefunction>& lowerStates) asm("__wrap_" SYM_block_davidson);
+void wrap_davidson(vector<Wavefunction>& b, DiagonalMatrix& h_diag, double normtol, const bool& warmUp, Davidson_functor& h_multiply, bool& useprecond,
+                   int currentRoot, vector<Wavefunction>& lowerStates) {
+  const char* mode = getenv("B2D_DROPIN_DAVIDSON");
+  if (mode && string(mode) == "host") {   // the reference's Davidson; every H application crosses the boundary with host buffers
+    double t0 = now_s();
+    real_davidson(b, h_diag, normtol, warmUp, h_multiply, useprecond, currentRoot, lowerStates);
+    g.t_dav += now_s() - t0;
+    return;
+  }
+  ensure_ctx(h_multiply.get_block());
+  if (!useprecond) die("block_davidson without the Olsen preconditioner: not covered");
+  int nroots = (int)b.size(), nlow = (int)lowerStates.size();
+  if ((int64_t)h_diag.Ncols() != g.W) die("block_davidson: h_diag length differs from the psi layout");
+  vector<Wavefunction> b_in; DiagonalMatrix h_in;
+  bool check = env_on("B2D_DROPIN_CHECK");
+  if (check) { b_in = b; h_in = h_diag; }
+  double t0 = now_s();
+  need_slots(ROOT_SLOT0 + nroots + nlow);
+  ck(b2d_vec_upload(g.ctx, DIAG_SLOT, h_diag.Store()), "b2d_vec_upload(diag)");
+  for (int i = 0; i < nroots; ++i) upload_wave(ROOT_SLOT0 + i, b[i]);
+  for (int i = 0; i < nlow; ++i) upload_wave(ROOT_SLOT0 + nroots + i, lowerStates[i]);
+  vector<double> ev(nroots);
+  int nm = 0; double res = 0;
+  ck(b2d_davidson_lower(g.ctx, nroots, ROOT_SLOT0, DIAG_SLOT, normtol, dmrginp.deflation_min_size(), dmrginp.deflation_max_size(), nlow,
+                        ROOT_SLOT0 + nroots, ev.data(), &nm, &res), "b2d_davidson");
+  double tm[4] = {0, 0, 0, 0};
+  b2d_last_timing(g.ctx, tm, 4);
+  g.dav_dev_ms += tm[0];
+  b.resize(nroots);
+  for (int i = 0; i < nroots; ++i) download_wave(ROOT_SLOT0 + i, b[i]);
+  for (int i = 0; i < std::min(nroots, h_diag.Ncols()); ++i) h_diag.element(i) = ev[i];   // linear.C:344-345
+  g.nmult += nm;
+  g.t_dav += now_s() - t0;
+  if (check) {
+    real_davidson(b_in, h_in, normtol, warmUp, h_multiply, useprecond, currentRoot, lowerStates);
+    for (int i = 0; i < nroots; ++i) {
+      double ov = DotProduct(b[i], b_in[i]);
+      fprintf(stderr, "B2D_CHECK call=%d davidson root=%d E_gpu=%.12f E_cpu=%.12f dE=%.3e |<gpu|cpu>|=%.12f n_multiply_gpu=%d\n", g.call, i, ev[i],
+              h_in.element(i), ev[i] - h_in.element(i), fabs(ov), nm);
+    }
+  }
+}
+
+// ---- DensityMatrix::makedensitymatrix ----
+void real_makedm(DensityMatrix* self, const vector<Wavefunction>& ws, SpinBlock& big, const vector<double>& wts, const double noise, const double add_noise, bool warmup) asm("__real_" SYM_makedensitymatrix);
+void wrap_makedm(DensityMatrix* self, const vector<Wavefunction>& ws, SpinBlock& big, const vector<double>& wts, const double noise, const double add_noise, bool warmup) asm("__wrap_" SYM_makedensitymatrix);
+void wrap_makedm(DensityMatrix* self, const vector<Wavefunction>& ws, SpinBlock& big, const vector<double>& wts, const double noise, const double add_noise, bool warmup) {
+  ensure_ctx(big);
+  if (add_noise > NUMERICAL_ZERO) die("add_twodot_noise (RANDOM noise, density.C:92-165): draws from glibc rand() - not covered by the GPU path; use twodot_noise 0");
+  DensityMatrix chk;
+  bool check = env_on("B2D_DROPIN_CHECK");
+  if (check) { chk = *self; real_makedm(&chk, ws, big, wts, noise, add_noise, warmup); }
+  double t0 = now_s();
+  int nroots = (int)wts.size();     // density.C:31: one term per weight
+  if ((int)ws.size() < nroots) die("makedensitymatrix: fewer wavefunctions than weights");
+  need_slots(ROOT_SLOT0 + std::max(nroots, (int)ws.size()));
+  for (size_t i = 0; i < ws.size(); ++i) upload_wave(ROOT_SLOT0 + (int)i, ws[i]);
+  ck(b2d_make_density(g.ctx, nroots, ROOT_SLOT0, wts.data()), "b2d_make_density");
+  if (noise > NUMERICAL_ZERO) ck(b2d_add_onedot_noise(g.ctx, (int)ws.size(), ROOT_SLOT0, noise), "b2d_add_onedot_noise");   // density.C:40-60
+  vector<double> rho((size_t)b2d_density_size(g.ctx));
+  ck(b2d_density_download(g.ctx, rho.data()), "b2d_density_download");
+  size_t off = 0;
+  for (int q = 0; q < self->nrows(); ++q) {
+    if (!self->allowed(q, q)) die("density matrix without a diagonal block");
+    Matrix& m = self->operator_element(q, q);
+    if (off + m.Storage() > rho.size()) die("density matrix size mismatch");
+    for (int k = 0; k < m.Storage(); ++k) m.Store()[k] += rho[off + k];   // MultiplyProduct accumulates (operatorfunctions.C:630-650)
+    off += m.Storage();
+  }
+  if (off != rho.size()) die("density matrix size mismatch");
+  g.rho_on_device = true;
+  g.t_rho += now_s() - t0;
+  if (check) {
+    double s; double d = max_abs_diff(*self, chk, &s);
+    fprintf(stderr, "B2D_CHECK call=%d makedensitymatrix noise=%.1e max_abs_diff=%.3e (max |rho| %.3e)\n", g.call, noise, d, s);
+  }
+}
+
+// ---- diagonalise_dm ----
+void real_diagdm(SparseMatrix& traced, SparseMatrix& transform, vector<DiagonalMatrix>& eigs) asm("__real_" SYM_diagonalise_dm);
+void wrap_diagdm(SparseMatrix& traced, SparseMatrix& transform, vector<DiagonalMatrix>& eigs) asm("__wrap_" SYM_diagonalise_dm);
+void wrap_diagdm(SparseMatrix& traced, SparseMatrix& transform, vector<DiagonalMatrix>& eigs) {
+  if (!g.ctx || !g.rho_on_device) die("diagonalise_dm outside a GPU block iteration (module not covered by the GPU path)");
+  bool check = env_on("B2D_DROPIN_CHECK");
+  if (check) {
+    g.chk_vecs = static_cast<DensityMatrix&>(transform);
+    g.chk_eigs.clear();
+    real_diagdm(traced, g.chk_vecs, g.chk_eigs);
+  }
+  double t0 = now_s();
+  // honour the argument: diagonalise the matrix we were handed (it is the one the makedensitymatrix hook produced)
+  vector<double> rho;
+  for (int q = 0; q < traced.nrows(); ++q) { const Matrix& m = traced.operator_element(q, q); rho.insert(rho.end(), m.Store(), m.Store() + m.Storage()); }
+  if ((int64_t)rho.size() != b2d_density_size(g.ctx)) die("diagonalise_dm: density matrix size mismatch");
+  ck(b2d_density_upload(g.ctx, rho.data()), "b2d_density_upload");
+  int nq = traced.nrows();
+  size_t total = 0; for (int q = 0; q < nq; ++q) total += traced.operator_element(q, q).Nrows();
+  vector<double> ev(total);
+  ck(b2d_diagonalise_dm(g.ctx, ev.data()), "b2d_diagonalise_dm");
+  eigs.resize(nq);
+  size_t off = 0;
+  for (int q = 0; q < nq; ++q) {
+    int d = traced.operator_element(q, q).Nrows();
+    DiagonalMatrix w(d);
+    for (int i = 0; i < d; ++i) w.element(i, i) = ev[off + i];   // ascending, < 1e-14 already clamped (rotationmat.C:274-276)
+    eigs[q] = w;
+    off += d;
+  }
+  g.t_eig += now_s() - t0;
+  if (check) {
+    double d = 0;
+    for (int q = 0; q < nq; ++q) for (int i = 0; i < eigs[q].Nrows(); ++i) d = std::max(d, fabs(eigs[q].element(i, i) - g.chk_eigs[q].element(i, i)));
+    fprintf(stderr, "B2D_CHECK call=%d diagonalise_dm eigenvalue max_abs_diff=%.3e\n", g.call, d);
+  }
+}
+
+// ---- assign_matrix_by_dm ----
+double real_assign(vector<Matrix>& rot, vector<DiagonalMatrix>& eigs, SparseMatrix& transform, vector<std::pair<int, int> >& inorder, vector<vector<int> >& byq,
+                   int nbydm, int nbyq, int lsize, int rsize) asm("__real_" SYM_assign_matrix_by_dm);
+double wrap_assign(vector<Matrix>& rot, vector<DiagonalMatrix>& eigs, SparseMatrix& transform, vector<std::pair<int, int> >& inorder, vector<vector<int> >& byq,
+                   int nbydm, int nbyq, int lsize, int rsize) asm("__wrap_" SYM_assign_matrix_by_dm);
+double wrap_assign(vector<Matrix>& rot, vector<DiagonalMatrix>& eigs, SparseMatrix& transform, vector<std::pair<int, int> >& inorder, vector<vector<int> >& byq,
+                   int nbydm, int nbyq, int lsize, int rsize) {
+  if (!g.ctx || !g.rho_on_device) die("assign_matrix_by_dm outside a GPU block iteration (module not covered by the GPU path)");
+  if (nbyq != 0) die("keptqstates != 0: not covered (sweep_params.C:80 always passes 0)");
+  if (dmrginp.do_pdm()) die("do_pdm keeps zero-weight states (rotationmat.C:161): not covered by the GPU path");
+  double t0 = now_s();
+  int nq = (int)eigs.size();
+  vector<int32_t> kept(nq, 0);
+  double discarded = 0;
+  // nbydm = min(#eigenvalues, keptstates) (renormalise.C:156): the library applies the same min
+  ck(b2d_select_states(g.ctx, nbydm, kept.data(), &discarded), "b2d_select_states");
+  vector<double> flat((size_t)std::max<int64_t>(b2d_rotation_size(g.ctx), 1));
+  ck(b2d_rotation_download(g.ctx, flat.data()), "b2d_rotation_download");
+  rot.clear(); rot.resize(nq);
+  size_t off = 0;
+  for (int q = 0; q < nq; ++q) {
+    int d = eigs[q].Nrows();
+    if (kept[q] == 0) continue;
+    rot[q].ReSize(d, kept[q]);
+    memcpy(rot[q].Store(), flat.data() + off, sizeof(double) * (size_t)d * kept[q]);
+    off += (size_t)d * kept[q];
+  }
+  g.rot_on_device = true;
+  g.t_eig += now_s() - t0;
+  if (env_on("B2D_DROPIN_CHECK")) {
+    vector<Matrix> rot2;
+    vector<std::pair<int, int> > in2; vector<vector<int> > by2;
+    sort_weights(g.chk_eigs, in2, by2);
+    double d2 = real_assign(rot2, g.chk_eigs, g.chk_vecs, in2, by2, std::min((int)in2.size(), nbydm), 0, lsize, rsize);
+    int mism = 0; double proj = 0;
+    for (int q = 0; q < nq; ++q) {
+      if (rot2[q].Ncols() != rot[q].Ncols()) { ++mism; continue; }
+      if (rot[q].Ncols() == 0) continue;
+      Matrix pa = rot[q] * rot[q].t(), pb = rot2[q] * rot2[q].t();   // projectors: sign / degenerate-rotation invariant
+      for (int k = 0; k < pa.Storage(); ++k) proj = std::max(proj, fabs(pa.Store()[k] - pb.Store()[k]));
+    }
+    fprintf(stderr, "B2D_CHECK call=%d select_states sectors_with_different_kept_count=%d discarded_gpu=%.6e discarded_cpu=%.6e projector_max_abs_diff=%.3e\n",
+            g.call, mism, discarded, d2, proj);
+  }
+  return discarded;
+}
+
+// ---- MatrixRotate (switched off while the transform hook runs the reference's bookkeeping) ----
+void real_rotate(const Matrix& a, const Matrix& b, const Matrix& c, Matrix& d) asm("__real_" SYM_MatrixRotate);
+void wrap_rotate(const Matrix& a, const Matrix& b, const Matrix& c, Matrix& d) asm("__wrap_" SYM_MatrixRotate);
+void wrap_rotate(const Matrix& a, const Matrix& b, const Matrix& c, Matrix& d) {
+  if (g.in_transform && !env_on("B2D_DROPIN_CHECK")) return;
+  real_rotate(a, b, c, d);
+}
+
+// ---- SpinBlock::transform_operators ----
+void real_transform(SpinBlock* self, vector<Matrix>& rot) asm("__real_" SYM_transform_operators);
+void wrap_transform(SpinBlock* self, vector<Matrix>& rot) asm("__wrap_" SYM_transform_operators);
+void wrap_transform(SpinBlock* self, vector<Matrix>& rot) {
+  if (!g.ctx || g.lsites != self->get_sites())
+    die("transform_operators on a block that was not the left child of the last GPU block iteration (warm-up / one-dot tail: not covered)");
+  double t0 = now_s();
+  int nq = (int)rot.size();
+  // honour the argument: rotate with the matrices we were handed
+  vector<int32_t> kept(nq);
+  vector<double> flat;
+  for (int q = 0; q < nq; ++q) {
+    kept[q] = rot[q].Ncols();
+    if (kept[q]) flat.insert(flat.end(), rot[q].Store(), rot[q].Store() + rot[q].Storage());
+  }
+  if (flat.empty()) flat.push_back(0.0);
+  ck(b2d_rotation_upload(g.ctx, kept.data(), flat.data()), "b2d_rotation_upload");
+  ck(b2d_transform_operators(g.ctx), "b2d_transform_operators");
+  // the reference's bookkeeping (new StateInfo, allocation, core flags, freeing the children) with MatrixRotate switched off
+  g.in_transform = true;
+  real_transform(self, rot);
+  g.in_transform = false;
+  int nnew = b2d_rotated_num_sectors(g.ctx);
+  if (nnew != (int)self->get_stateInfo().quanta.size()) die("transform_operators: retained sector count differs from the reference's StateInfo");
+  bool check = env_on("B2D_DROPIN_CHECK");
+  double worst = 0, scale = 0;
+  vector<uint8_t> allowed((size_t)nnew * nnew);
+  vector<double> data;
+  for (size_t k = 0; k < g.left_ops.size(); ++k) {
+    SparseMatrix& op = *g.left_ops[k].elem;
+    int id = g.left_ops[k].id;
+    if (op.nrows() != nnew || op.ncols() != nnew) die("transform_operators: an operator was not re-allocated by the reference");
+    int64_t n = b2d_rotated_op_size(g.ctx, id);
+    data.resize((size_t)std::max<int64_t>(n, 1));
+    ck(b2d_rotated_op_download(g.ctx, id, allowed.data(), data.data()), "b2d_rotated_op_download");
+    size_t off = 0;
+    for (int a = 0; a < nnew; ++a)
+      for (int b = 0; b < nnew; ++b) {
+        bool al = op.allowed(a, b);
+        if (al != (allowed[(size_t)a * nnew + b] != 0)) die("transform_operators: allowed mask differs from SparseMatrix::allocate");
+        if (!al) continue;
+        Matrix& m = op.operator_element(a, b);
+        if (check) for (int i = 0; i < m.Storage(); ++i) { worst = std::max(worst, fabs(m.Store()[i] - data[off + i])); scale = std::max(scale, fabs(m.Store()[i])); }
+        memcpy(m.Store(), data.data() + off, sizeof(double) * m.Storage());
+        off += m.Storage();
+      }
+    if ((int64_t)off != n) die("transform_operators: rotated operator size mismatch");
+  }
+  g.t_rot += now_s() - t0;
+  if (check) fprintf(stderr, "B2D_CHECK call=%d transform_operators ops=%d max_abs_diff=%.3e (max |O'| %.3e)\n", g.call, (int)g.left_ops.size(), worst, scale);
+  write_stats();
+  release();
+}
+
+// ---- SpinBlock::RenormaliseFrom: only guards the modes the GPU path does not cover ----
+void real_RenormaliseFrom(SpinBlock* self, vector<double>& energies, vector<double>& spins, double& error, vector<Matrix>& rotateMatrix,
+                          const int keptstates, const int keptqstates, const double tol, SpinBlock& big, const guessWaveTypes& gw,
+                          const double noise, const double additional_noise, const bool& onedot, SpinBlock& System, SpinBlock& sysDot,
+                          SpinBlock& environment, const bool& dot_with_sys, const bool& warmUp, int sweepiter, int currentRoot,
+                          vector<Wavefunction>& lowerStates, DensityMatrix* rdm) asm("__real_" SYM_RenormaliseFrom);
+void wrap_RenormaliseFrom(SpinBlock* self, vector<double>& energies, vector<double>& spins, double& error, vector<Matrix>& rotateMatrix,
+                          const int keptstates, const int keptqstates, const double tol, SpinBlock& big, const guessWaveTypes& gw,
+                          const double noise, const double additional_noise, const bool& onedot, SpinBlock& System, SpinBlock& sysDot,
+                          SpinBlock& environment, const bool& dot_with_sys, const bool& warmUp, int sweepiter, int currentRoot,
+                          vector<Wavefunction>& lowerStates, DensityMatrix* rdm) asm("__wrap_" SYM_RenormaliseFrom);
+void wrap_RenormaliseFrom(SpinBlock* self, vector<double>& energies, vector<double>& spins, double& error, vector<Matrix>& rotateMatrix,
+                          const int keptstates, const int keptqstates, const double tol, SpinBlock& big, const guessWaveTypes& gw,
+                          const double noise, const double additional_noise, const bool& onedot, SpinBlock& System, SpinBlock& sysDot,
+                          SpinBlock& environment, const bool& dot_with_sys, const bool& warmUp, int sweepiter, int currentRoot,
+                          vector<Wavefunction>& lowerStates, DensityMatrix* rdm) {
+  if (onedot && !dot_with_sys) die("one-dot step with the dot on the environment side (renormalise.C:64-79, onedot_shufflesysdot): not covered; use `twodot`");
+  if (dmrginp.solve_method() != DAVIDSON) die("solver other than Davidson: not covered");
+  real_RenormaliseFrom(self, energies, spins, error, rotateMatrix, keptstates, keptqstates, tol, big, gw, noise, additional_noise, onedot, System, sysDot,
+                       environment, dot_with_sys, warmUp, sweepiter, currentRoot, lowerStates, rdm);
+}
+
+}  // namespace SpinAdapted

@@ -1,0 +1,191 @@
+#!/usr/bin/env python
+"""Golden per-sweep energies for the drop-in test (tests/test_gpu_dropin.py): the UNMODIFIED reference
+(oracle/_ref/block.spin_adapted, no hooks) is run on each case; its "Sweep Energy" lines, the inputs it read and its wall
+time are stored in tests/golden/dropin_cases.npz.  The GPU test feeds the same inputs to oracle/_ref/block_gpu (same reference
+objects, hot path re-routed to libblockb200.so) and compares sweep by sweep (north_star: per-sweep energies within 1e-8 Eh).
+
+Run in the build container only (needs /root/reference and `make -C oracle ref`).  Inputs that come from the reference's
+dmrg_tests/ are stored as bytes inside the .npz (fixtures, not sources); the Hubbard chain and the synthetic random-integral
+FCIDUMPs are generated here (SURVEY.md 8d, P3 / P5 recipes).
+"""
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = os.environ.get("BLOCK_REFERENCE", "/root/reference")
+BLOCK = os.path.join(ROOT, "oracle", "_ref", "block.spin_adapted")
+
+
+def hubbard_chain_fcidump(L, U=2.0, t=1.0):
+    """Open 1-D chain in the format / sign convention of dmrg_tests/hubbard/FCIDUMP (which is the periodic 8-ring)."""
+    lines = [" &FCI NORB= %d,NELEC= %d,MS2= 0," % (L, L), "  ORBSYM=" + ",".join(["1"] * L) + ",", "  ISYM=1", " &END"]
+    for i in range(1, L + 1):
+        lines.append("%.2f\t%d\t%d\t%d\t%d" % (U, i, i, i, i))
+    for i in range(1, L):
+        lines.append("%.2f\t%d\t%d\t0\t0" % (t, i, i + 1))
+    return "\n".join(lines) + "\n"
+
+
+def synthetic_fcidump(norb, nelec, seed=20260):
+    """h symmetric N(0,1)*0.5 with a diagonal ramp, (ij|kl) = sum_P L^P_ij L^P_kl (positive, 8-fold symmetric), C1."""
+    rng = np.random.default_rng(seed)
+    h = rng.normal(size=(norb, norb)) * 0.5
+    h = 0.5 * (h + h.T) + np.diag(np.linspace(-2.0, 2.0, norb))
+    Lp = rng.normal(size=(3 * norb, norb, norb)) * 0.1
+    Lp = 0.5 * (Lp + Lp.transpose(0, 2, 1))
+    eri = np.einsum("pij,pkl->ijkl", Lp, Lp)
+    out = [" &FCI NORB= %d,NELEC=%d,MS2= 0," % (norb, nelec), "  ORBSYM=" + ",".join(["1"] * norb) + ",", "  ISYM=1", " &END"]
+    for i in range(norb):
+        for j in range(i + 1):
+            for k in range(i + 1):
+                for l in range(k + 1):
+                    if i * (i + 1) // 2 + j < k * (k + 1) // 2 + l:
+                        continue
+                    out.append("%.15e %d %d %d %d" % (eri[i, j, k, l], i + 1, j + 1, k + 1, l + 1))
+    for i in range(norb):
+        for j in range(i + 1):
+            out.append("%.15e %d %d 0 0" % (h[i, j], i + 1, j + 1))
+    out.append("%.15e 0 0 0 0" % 0.0)
+    return "\n".join(out) + "\n"
+
+
+def ref_file(*parts):
+    return open(os.path.join(REF, "dmrg_tests", *parts)).read()
+
+
+def cases():
+    c = {}
+    # P1 (BASELINE configs[0]): C2 / D2h, small M two-site sweeps, two state-averaged roots
+    c["c2_d2h_M50"] = dict(files={"FCIDUMP": ref_file("c2_d2h_smallM", "FCIDUMP"), "reorder.dat": ref_file("c2_d2h_smallM", "reorder.dat")}, conf="""nelec 8
+spin 0
+irrep 1
+hf_occ integral
+schedule
+0 50 1.0e-10 0.0
+end
+maxiter 4
+twodot
+sweep_tol 1e-12
+sym d2h
+orbitals FCIDUMP
+nroots 2
+weights 0.5 0.5
+reorder reorder.dat
+outputlevel 0
+""")
+    # the same with perturbative noise in the first sweeps (DensityMatrix::add_onedot_noise inside the sweep)
+    c["c2_d2h_M50_noise"] = dict(files=c["c2_d2h_M50"]["files"], conf="""nelec 8
+spin 0
+irrep 1
+hf_occ integral
+schedule
+0 50 1.0e-10 1.0e-4
+2 50 1.0e-10 0.0
+end
+maxiter 4
+twodot
+sweep_tol 1e-12
+sym d2h
+orbitals FCIDUMP
+nroots 2
+weights 0.5 0.5
+reorder reorder.dat
+outputlevel 0
+""")
+    # P2 (configs[1]): H2O, no symmetry, M = 500
+    c["h2o_nosym_M500"] = dict(files={"FCIDUMP": ref_file("h2o_nosym", "FCIDUMP")}, conf="""nelec 10
+spin 0
+irrep 1
+hf_occ integral
+schedule
+0 500 1.0e-10 0.0
+end
+maxiter 3
+twodot
+sweep_tol 1e-12
+orbitals FCIDUMP
+noreorder
+outputlevel 0
+""")
+    # P3 (configs[2]): 1-D Hubbard chain, spin-adapted, M = 1000, noise in the first sweeps
+    c["hubbard_L16_M1000"] = dict(files={"FCIDUMP": hubbard_chain_fcidump(16)}, conf="""nelec 16
+spin 0
+hf_occ integral
+schedule
+0 200 1.0e-8 1e-4
+4 1000 1.0e-10 0.0
+end
+maxiter 8
+twodot
+sweep_tol 1e-12
+orbitals FCIDUMP
+noreorder
+outputlevel 0
+warmup local_2site
+""")
+    # P5 scaled down (configs[4] shape: random-integral FCIDUMP, half filling, C1) so that the CPU reference finishes in a minute
+    c["synthetic_14o_M200"] = dict(files={"FCIDUMP": synthetic_fcidump(14, 14)}, conf="""nelec 14
+spin 0
+irrep 1
+hf_occ integral
+schedule
+0 100 1.0e-9 0.0
+2 200 1.0e-10 0.0
+end
+maxiter 4
+twodot
+sweep_tol 1e-12
+orbitals FCIDUMP
+noreorder
+outputlevel 0
+""")
+    return c
+
+
+def run_reference(name, case, threads=8):
+    work = tempfile.mkdtemp(prefix="dropin_")
+    for f, text in case["files"].items():
+        open(os.path.join(work, f), "w").write(text)
+    open(os.path.join(work, "dmrg.conf"), "w").write(case["conf"])
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="1")
+    t0 = time.time()
+    out = subprocess.run([BLOCK, "dmrg.conf"], cwd=work, env=env, capture_output=True, text=True)
+    dt = time.time() - t0
+    shutil.rmtree(work)
+    if out.returncode != 0:
+        print(out.stdout[-3000:], out.stderr[-3000:])
+        raise SystemExit("reference run failed for " + name)
+    sweeps = [l.strip() for l in out.stdout.splitlines() if "Sweep Energy" in l]
+    return sweeps, dt
+
+
+def main():
+    only = sys.argv[1:]
+    path = os.path.join(HERE, "dropin_cases.npz")
+    store = dict(np.load(path, allow_pickle=False)) if os.path.exists(path) else {}
+    for name, case in cases().items():
+        if only and name not in only:
+            continue
+        sweeps, dt = run_reference(name, case)
+        print(name, "%.1f s" % dt)
+        for s in sweeps:
+            print("   ", s)
+        store[name + "/conf"] = np.frombuffer(case["conf"].encode(), dtype=np.uint8)
+        store[name + "/files"] = np.array(sorted(case["files"]))
+        for f, text in case["files"].items():
+            store[name + "/file/" + f] = np.frombuffer(text.encode(), dtype=np.uint8)
+        store[name + "/sweeps"] = np.frombuffer("\n".join(sweeps).encode(), dtype=np.uint8)
+        store[name + "/ref_wall_s"] = np.array([dt])
+    np.savez_compressed(path, **store)
+    print("wrote", path, "%.1f kB" % (os.path.getsize(path) / 1e3))
+
+
+if __name__ == "__main__":
+    main()

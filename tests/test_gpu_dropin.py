@@ -1,0 +1,110 @@
+"""Drop-in test: the unmodified reference sweep with its hot path re-routed to libblockb200.so (oracle/_ref/block_gpu,
+tests/dropin/block_gpu_hooks.cpp) must reproduce the unmodified reference's per-sweep energies (tests/golden/dropin_cases.npz,
+made by tests/golden/make_dropin_golden.py from oracle/_ref/block.spin_adapted) within 1e-8 Eh, sweep by sweep and root by root -
+BASELINE.json north_star's parity gate on identical FCIDUMP and dmrg.conf inputs - and print the same discarded weights.
+"""
+import os
+import re
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BLOCK_GPU = os.path.join(ROOT, "oracle", "_ref", "block_gpu")
+CASES = os.path.join(ROOT, "tests", "golden", "dropin_cases.npz")
+
+SWEEP_RE = re.compile(r"M = (\d+)\s+state = (\d+)\s+Largest Discarded Weight = (\S+)\s+Sweep Energy = (\S+)")
+
+
+def parse_sweeps(text):
+    return [(int(m.group(1)), int(m.group(2)), float(m.group(3)), float(m.group(4))) for m in SWEEP_RE.finditer(text)]
+
+
+def case_names():
+    if not os.path.exists(CASES):
+        return []
+    with np.load(CASES) as z:
+        return sorted({k.split("/")[0] for k in z.files})
+
+
+def run_case(name, extra_env=None, timeout=1500):
+    z = np.load(CASES)
+    work = tempfile.mkdtemp(prefix="dropin_" + name + "_")
+    for f in z[name + "/files"]:
+        open(os.path.join(work, str(f)), "wb").write(z["%s/file/%s" % (name, f)].tobytes())
+    open(os.path.join(work, "dmrg.conf"), "wb").write(z[name + "/conf"].tobytes())
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="1", B2D_DROPIN_STATS=os.path.join(work, "stats.txt"))
+    env.update(extra_env or {})
+    out = subprocess.run([BLOCK_GPU, "dmrg.conf"], cwd=work, env=env, capture_output=True, text=True, timeout=timeout)
+    golden = parse_sweeps(z[name + "/sweeps"].tobytes().decode())
+    stats = open(os.path.join(work, "stats.txt")).read() if os.path.exists(os.path.join(work, "stats.txt")) else ""
+    return out, golden, stats
+
+
+def test_golden_sweeps_parse():
+    """CPU: the committed golden file holds, for every case, inputs and at least two sweeps of energies."""
+    names = case_names()
+    assert names, "tests/golden/dropin_cases.npz missing"
+    with np.load(CASES) as z:
+        for n in names:
+            sweeps = parse_sweeps(z[n + "/sweeps"].tobytes().decode())
+            assert len(sweeps) >= 2, n
+            assert b"schedule" in z[n + "/conf"].tobytes()
+            assert "FCIDUMP" in [str(f) for f in z[n + "/files"]]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", case_names())
+def test_sweep_energies_match_reference(name):
+    assert os.path.exists(BLOCK_GPU), "oracle/_ref/block_gpu not built (make -C oracle dropin)"
+    out, golden, stats = run_case(name)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    got = parse_sweeps(out.stdout)
+    assert len(got) == len(golden), (len(got), len(golden), out.stdout[-2000:])
+    worst = 0.0
+    for (m1, s1, dw1, e1), (m2, s2, dw2, e2) in zip(got, golden):
+        assert (m1, s1) == (m2, s2)
+        worst = max(worst, abs(e1 - e2))
+        assert abs(e1 - e2) <= 1e-8, (name, m1, s1, e1, e2)                     # north_star: per-sweep energies within 1e-8 Eh
+        assert abs(dw1 - dw2) <= 1e-3 * abs(dw2) + 5e-12, (name, dw1, dw2)      # printed with 4 significant digits
+    assert "n_multiply" in stats and "launches" in stats                         # the hooks ran on the device
+    print("%s: %d sweep energies, worst |dE| = %.2e Eh" % (name, len(got), worst))
+
+
+@pytest.mark.gpu
+def test_every_hook_against_the_cpu_function():
+    """B2D_DROPIN_CHECK=1: each hook also runs the reference's own CPU function on copies of its inputs."""
+    name = "c2_d2h_M50_noise"
+    out, golden, _ = run_case(name, {"B2D_DROPIN_CHECK": "1"})
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    lines = [l for l in out.stderr.splitlines() if l.startswith("B2D_CHECK")]
+    kinds = {l.split()[2] for l in lines}
+    assert {"diagonalH", "davidson", "makedensitymatrix", "diagonalise_dm", "select_states", "transform_operators"} <= kinds, kinds
+
+    def val(line, key):
+        return float(re.search(key + r"=(\S+)", line).group(1))
+    for l in lines:
+        k = l.split()[2]
+        if k in ("diagonalH", "makedensitymatrix", "transform_operators"):
+            assert val(l, "max_abs_diff") < 1e-10, l
+        elif k == "diagonalise_dm":
+            assert val(l, "max_abs_diff") < 1e-12, l
+        elif k == "davidson":
+            assert abs(val(l, "dE")) < 1e-9, l
+        elif k == "select_states":
+            assert val(l, "sectors_with_different_kept_count") == 0, l
+            assert abs(val(l, "discarded_gpu") - val(l, "discarded_cpu")) < 1e-12, l
+
+
+@pytest.mark.gpu
+def test_host_davidson_through_multiplyH():
+    """B2D_DROPIN_DAVIDSON=host: the reference's own block_davidson, every H application through b2d_multiplyH_host."""
+    name = "c2_d2h_M50"
+    out, golden, stats = run_case(name, {"B2D_DROPIN_DAVIDSON": "host"})
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    got = parse_sweeps(out.stdout)
+    assert len(got) == len(golden)
+    for (m1, s1, dw1, e1), (m2, s2, dw2, e2) in zip(got, golden):
+        assert abs(e1 - e2) <= 1e-8, (e1, e2)

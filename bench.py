@@ -317,6 +317,56 @@ def block_iteration_leg(sb, a, psi, sigma_ms):
     return out
 
 
+def sweep_leg(a):
+    """BASELINE.json's other headline figure, "two-site sweep wall time ... energy delta vs ref": the UNMODIFIED reference sweep
+    (oracle/_ref/block.spin_adapted, all host threads) next to the same reference sweep with its hot path re-routed to this library
+    (oracle/_ref/block_gpu, tests/dropin/block_gpu_hooks.cpp) on one real FCIDUMP / dmrg.conf case of tests/golden/dropin_cases.npz.
+    Both run here, back to back, on this box; energies are compared sweep by sweep.  Host-side block construction (the reference's
+    own Op::build, SURVEY N2) is inside both times."""
+    import re
+    gpu_bin = os.path.join(ROOT, "oracle", "_ref", "block_gpu")
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "block.spin_adapted")
+    cases = os.path.join(ROOT, "tests", "golden", "dropin_cases.npz")
+    if not (os.path.exists(gpu_bin) and os.path.exists(ref_bin) and os.path.exists(cases)):
+        return {"unavailable": "oracle/_ref/block_gpu or block.spin_adapted not built"}
+    z = np.load(cases)
+    name = a.sweep_case
+    threads = os.cpu_count() or 1
+    pat = re.compile(r"M = (\d+)\s+state = (\d+)\s+Largest Discarded Weight = (\S+)\s+Sweep Energy = (\S+)")
+    out = {"case": name, "host_threads": threads}
+    energies = {}
+    for tag, exe in (("reference_cpu", ref_bin), ("gpu_dropin", gpu_bin)):
+        work = tempfile.mkdtemp(prefix="sweep_%s_" % tag)
+        for f in z[name + "/files"]:
+            open(os.path.join(work, str(f)), "wb").write(z["%s/file/%s" % (name, f)].tobytes())
+        conf = z[name + "/conf"].tobytes().decode() + "threads_per_node %d\n" % threads
+        open(os.path.join(work, "dmrg.conf"), "w").write(conf)
+        env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS=str(threads), B2D_DROPIN_STATS=os.path.join(work, "stats.txt"))
+        t0 = time.perf_counter()
+        r = subprocess.run([exe, "dmrg.conf"], cwd=work, env=env, capture_output=True, text=True)
+        dt = time.perf_counter() - t0
+        if r.returncode != 0:
+            out[tag] = {"failed": (r.stderr or r.stdout)[-300:]}
+            continue
+        e = [float(m.group(4)) for m in pat.finditer(r.stdout)]
+        energies[tag] = e
+        out[tag] = {"wall_s": dt, "sweep_lines": len(e), "final_energy": e[-1] if e else None}
+        if tag == "gpu_dropin" and os.path.exists(os.path.join(work, "stats.txt")):
+            tot = {}
+            for l in open(os.path.join(work, "stats.txt")):
+                for k, v in re.findall(r"(\w+)=([-\d.e+]+)", l):
+                    tot[k] = tot.get(k, 0.0) + float(v)
+            out[tag]["hot_path_s"] = {k: tot.get(k, 0.0) for k in ("upload_s", "diag_s", "davidson_s", "density_s", "eig_s", "rotate_s")}
+            out[tag]["n_multiply"] = int(tot.get("n_multiply", 0))
+            out[tag]["kernel_launches"] = int(tot.get("launches", 0))
+    if len(energies) == 2 and len(energies["reference_cpu"]) == len(energies["gpu_dropin"]):
+        out["max_abs_dE_per_sweep"] = max(abs(x - y) for x, y in zip(energies["reference_cpu"], energies["gpu_dropin"]))
+        golden = [float(m.group(4)) for m in pat.finditer(z[name + "/sweeps"].tobytes().decode())]
+        if len(golden) == len(energies["gpu_dropin"]):
+            out["max_abs_dE_vs_golden"] = max(abs(x - y) for x, y in zip(golden, energies["gpu_dropin"]))
+    return out
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -441,7 +491,12 @@ def run_ours(a):
         k_n = sum(prof[(st, 0)][3] for st in range(2))
         tot_ms = sum(v[0] for v in prof.values())
         achieved = k_fl / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
-        roof = {"bound": "tensor", "achieved": achieved, "peak": dmma, "unit": "TFLOP/s", "frac": achieved / dmma if dmma else None, "traffic": None,
+        # DRAM bytes per launch of that kernel from the committed ncu capture of this same workload (profiles/README.md); other
+        # workloads have no capture
+        default_workload = (a.norbs, a.nelec, a.M, a.left_sites, world) == (40, 40, 4000, 18, 1)
+        roof = {"bound": "tensor", "achieved": achieved, "peak": dmma, "unit": "TFLOP/s", "frac": achieved / dmma if dmma else None,
+                "traffic": 16.12e9 if default_workload else None,
+                "traffic_source": "profiles/r01_ncu_launches_sigma_fullsize.csv: dram__bytes_read.sum + dram__bytes_write.sum of the 36 launches / 36 (bytes per launch)" if default_workload else None,
                 "kernel": "grouped_gemm_kernel<128,128,*> (FP64 DMMA m16n8k8, 16 warps x 32x32)", "launches": int(k_n), "avg_launch_ms": k_ms / max(k_n, 1),
                 "share_of_sigma": k_ms / tot_ms if tot_ms else None, "tile_fill": k_fl / k_pad if k_pad else None,
                 "peak_source": "live FP64 DMMA register-loop yardstick of this library on this GPU (MEASURED_PEAKS.json has no FP64 entry); DFMA loop %.1f TFLOP/s" % dfma,
@@ -469,9 +524,11 @@ def run_ours(a):
     if line is not None and not a.no_cpu and world == 1:
         kind, v, cores, desc, _, _ = cpu_leg(a, a.cpu_budget_s)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}
+    sb.close()
+    if line is not None and world == 1 and not a.no_sweep:
+        line["sweep"] = sweep_leg(a)
     if line is not None:
         emit(line)
-    sb.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -499,6 +556,8 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-block-iteration", action="store_true", help="skip the Davidson / density / eigen / rotation leg")
     ap.add_argument("--davidson-iters", type=int, default=6)
+    ap.add_argument("--no-sweep", action="store_true", help="skip the whole-sweep leg (reference sweep vs the same sweep with the GPU hot path)")
+    ap.add_argument("--sweep-case", default="synthetic_14o_M200", help="case of tests/golden/dropin_cases.npz for the sweep leg")
     ap.add_argument("--profile-mode", action="store_true", help="for ncu: 1 warm-up sigma + --steps sigmas, nothing else, no JSON line")
     ap.add_argument("--cpu-budget-s", type=float, default=15.0)
     ap.add_argument("--ref-step-s", type=float, default=6.0)

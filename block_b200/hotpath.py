@@ -220,19 +220,21 @@ class SpinBlock:
         self._ck(self.lib.b2d_diagonal(self._ctx, s))
         return self.download(s)
 
-    def block_davidson(self, guesses, diag, normtol, deflation_min=2, deflation_max=20):
-        """Linear::block_davidson(b, h_diag, normtol, warmUp, h_multiply, useprecond, -1, {}): returns
-        (eigenvalues, solutions, number of H applications)."""
-        n = len(guesses)
-        self.reserve(n + 1)
+    def block_davidson(self, guesses, diag, normtol, deflation_min=2, deflation_max=20, lowerStates=()):
+        """Linear::block_davidson(b, h_diag, normtol, warmUp, h_multiply, useprecond, currentRoot, lowerStates): returns
+        (eigenvalues, solutions, number of H applications).  lowerStates non-empty = the state-specific form."""
+        n, nl = len(guesses), len(lowerStates)
+        self.reserve(n + 1 + nl)
         for i, g in enumerate(guesses):
             self.upload(i, g)
         self.upload(n, diag)
+        for i, l in enumerate(lowerStates):
+            self.upload(n + 1 + i, l)
         ev = np.zeros(n)
         nm = C.c_int(0)
         res = C.c_double(0.0)
-        self._ck(self.lib.b2d_davidson(self._ctx, n, 0, n, float(normtol), int(deflation_min), int(deflation_max), _p(ev, _lib.c_f64p),
-                                       C.byref(nm), C.byref(res)))
+        self._ck(self.lib.b2d_davidson_lower(self._ctx, n, 0, n, float(normtol), int(deflation_min), int(deflation_max), nl, n + 1,
+                                             _p(ev, _lib.c_f64p), C.byref(nm), C.byref(res)))
         return ev, [self.download(i) for i in range(n)], nm.value
 
     def make_density(self, waves, weights, noise=0.0):

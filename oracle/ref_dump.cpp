@@ -149,8 +149,7 @@ void dump_block(Dumper& d, const string& p, SpinBlock& b, const std::set<int>* o
 }
 
 // a deterministic non-trivial wavefunction ("rpsi")
-void fill_lcg(SparseMatrix& w) {
-  uint64_t st = 0x9E3779B97F4A7C15ull;
+void fill_lcg(SparseMatrix& w, uint64_t st = 0x9E3779B97F4A7C15ull) {
   for (int l = 0; l < w.nrows(); ++l) for (int r = 0; r < w.ncols(); ++r) if (w.allowed(l, r)) {
     Matrix& m = w.operator_element(l, r);
     for (int k = 0; k < m.Storage(); ++k) { st = st * 6364136223846793005ull + 1442695040888963407ull; m.Store()[k] = ((st >> 11) * (1.0 / 9007199254740992.0)) - 0.5; }
@@ -278,17 +277,25 @@ void wrap_davidson(vector<Wavefunction>& b, DiagonalMatrix& h_diag, double normt
     d.dbls("dav_evals", ev);
     d.ints("dav_out", vector<int>{(int)(g_sigma_calls - c0), (int)b.size()});
     // state-specific form (lowerStates, linear.C:201-208,311-317,369-375): one more solve of the reference's own block_davidson
-    // for ONE root, guess = the deterministic vector "rpsi", lower state = the converged root 0.  Pins the lower-state projections.
+    // for ONE root with a lower state.  Lower state = a deterministic pseudo-random, unnormalised vector; guess = converged root 0
+    // + 1% of another such vector, so that the solve takes a handful of iterations (a long Krylov run from a random guess amplifies
+    // rounding differences and cannot be compared bit for bit).  Pins the three lower-state projections.
     if (lowerStates.empty()) {
       long c1 = g_sigma_calls;
       vector<Wavefunction> lo(1, b[0]);
+      fill_lcg(lo[0], 0xD1B54A32D192ED03ull);
       vector<Wavefunction> g1(1, b[0]);
-      fill_lcg(g1[0]);
+      Wavefunction pert = b[0];
+      fill_lcg(pert);
+      ScaleAdd(0.01, pert, g1[0]);
+      vector<double> flat;
+      flatten(lo[0], flat); d.dbls("ss_lower", flat);
+      flatten(g1[0], flat); d.dbls("ss_guess", flat);
       DiagonalMatrix hd = diag_in;
       bool up = useprecond;
       real_davidson(g1, hd, normtol, warmUp, h_multiply, up, 1, lo);
       d.dbls("ss_eval", vector<double>{hd.element(0)});
-      vector<double> flat; flatten(g1[0], flat); d.dbls("ss_psi", flat);
+      flatten(g1[0], flat); d.dbls("ss_psi", flat);
       d.ints("ss_nmult", vector<int>{(int)(g_sigma_calls - c1)});
     }
   }

@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")))
+GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*_site*.npz")))   # one RenormaliseFrom record each
 
 
 def pytest_configure(config):

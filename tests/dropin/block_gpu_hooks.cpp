@@ -72,7 +72,8 @@ struct OpRef { SparseMatrix* elem; int id; };
 
 struct Gpu {
   b2d_ctx* ctx = 0;
-  const SpinBlock* big = 0;
+  const SpinBlock* left = 0;     // children of the big block this context was built for (RenormaliseFrom works on a COPY
+  const SpinBlock* right = 0;    // of `big`, renormalise.C:79 `newbig = big`, which shares the children)
   vector<int> lsites, rsites;
   vector<OpRef> left_ops;        // every operator element of the left child, in upload order
   int nslots = 0;
@@ -117,7 +118,7 @@ void collect(SparseMatrix& w, const vector<double>& in) {     // Wavefunction::C
 
 void release() {
   if (g.ctx) b2d_destroy(g.ctx);
-  g.ctx = 0; g.big = 0; g.left_ops.clear(); g.nslots = 0; g.rho_on_device = g.rot_on_device = false;
+  g.ctx = 0; g.left = g.right = 0; g.left_ops.clear(); g.nslots = 0; g.rho_on_device = g.rot_on_device = false;
 }
 
 void write_stats() {
@@ -180,7 +181,9 @@ void upload_block(int side, SpinBlock& b, vector<OpRef>* keep) {
 void ensure_ctx(const SpinBlock& big_c) {
   SpinBlock& big = const_cast<SpinBlock&>(big_c);
   if (!big.get_leftBlock() || !big.get_rightBlock()) die("big block without children");
-  if (g.ctx && g.big == &big && g.lsites == big.get_leftBlock()->get_sites() && g.rsites == big.get_rightBlock()->get_sites()) return;
+  if (g.ctx && g.left == big.get_leftBlock() && g.right == big.get_rightBlock() && g.lsites == big.get_leftBlock()->get_sites() &&
+      g.rsites == big.get_rightBlock()->get_sites())
+    return;
   release();
   if (!dmrginp.spinAdapted()) die("non spin-adapted run: not covered by the GPU path");
   if (dmrginp.hamiltonian() != QUANTUM_CHEMISTRY && dmrginp.hamiltonian() != HUBBARD) die("Hamiltonian type not covered by the GPU path");
@@ -188,7 +191,7 @@ void ensure_ctx(const SpinBlock& big_c) {
   int dev = getenv("B2D_DEVICE") ? atoi(getenv("B2D_DEVICE")) : 0;
   if (b2d_create(dev, &g.ctx)) die(string("b2d_create: ") + b2d_last_error(0));
   if (getenv("B2D_DROPIN_WORKSPACE_MB")) ck(b2d_set_option(g.ctx, "workspace_mb", atof(getenv("B2D_DROPIN_WORKSPACE_MB"))), "b2d_set_option");
-  g.big = &big; g.lsites = big.get_leftBlock()->get_sites(); g.rsites = big.get_rightBlock()->get_sites();
+  g.left = big.get_leftBlock(); g.right = big.get_rightBlock(); g.lsites = big.get_leftBlock()->get_sites(); g.rsites = big.get_rightBlock()->get_sites();
   upload_block(0, *big.get_leftBlock(), &g.left_ops);
   upload_block(1, *big.get_rightBlock(), 0);
   SpinQuantum tq = dmrginp.effective_molecule_quantum();

@@ -68,7 +68,7 @@ spin 0
 irrep 1
 hf_occ integral
 schedule
-0 50 1.0e-10 0.0
+0 50 1.0e-16 0.0
 end
 maxiter 4
 twodot
@@ -86,8 +86,8 @@ spin 0
 irrep 1
 hf_occ integral
 schedule
-0 50 1.0e-10 1.0e-4
-2 50 1.0e-10 0.0
+0 50 1.0e-16 1.0e-4
+2 50 1.0e-16 0.0
 end
 maxiter 4
 twodot
@@ -105,7 +105,7 @@ spin 0
 irrep 1
 hf_occ integral
 schedule
-0 500 1.0e-10 0.0
+0 500 1.0e-16 0.0
 end
 maxiter 3
 twodot
@@ -119,8 +119,8 @@ outputlevel 0
 spin 0
 hf_occ integral
 schedule
-0 200 1.0e-8 1e-4
-4 1000 1.0e-10 0.0
+0 200 1.0e-16 1e-4
+4 1000 1.0e-16 0.0
 end
 maxiter 8
 twodot
@@ -136,8 +136,8 @@ spin 0
 irrep 1
 hf_occ integral
 schedule
-0 100 1.0e-9 0.0
-2 200 1.0e-10 0.0
+0 100 1.0e-16 0.0
+2 200 1.0e-16 0.0
 end
 maxiter 4
 twodot

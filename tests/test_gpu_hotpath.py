@@ -145,6 +145,18 @@ def test_davidson_matches_reference(gpu_block):
         assert abs(abs(np.dot(vecs[i], rec["psi%d" % i])) - 1.0) < 1e-8
 
 
+def test_davidson_with_lower_states_matches_reference(gpu_block):
+    """b2d_davidson_lower against the reference's own state-specific solve recorded in the fixture (one lower state)."""
+    rec, big, sb = gpu_block
+    ev, vecs, nmult = sb.block_davidson([rec["ss_guess"]], rec["diag"], float(rec["dav_tol"][0]), int(rec["dav_in"][4]), int(rec["dav_in"][5]),
+                                        lowerStates=[rec["ss_lower"]])
+    assert abs(ev[0] - rec["ss_eval"][0]) < 1e-8            # north_star: energies within 1e-8 Eh
+    assert abs(ev[0] - rec["ss_eval"][0]) < 1e-10
+    assert nmult == int(rec["ss_nmult"][0])                 # same number of H applications
+    assert abs(abs(np.dot(vecs[0], rec["ss_psi"])) - 1.0) < 1e-8
+    assert abs(np.dot(vecs[0], rec["ss_lower"])) / np.linalg.norm(rec["ss_lower"]) < 1e-9
+
+
 def test_density_matches_reference(gpu_block):
     rec, big, sb = gpu_block
     nroots = int(rec["meta"][4])

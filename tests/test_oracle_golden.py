@@ -48,6 +48,24 @@ def test_davidson_matches_reference(golden):
         assert abs(abs(np.dot(vecs[i], rec["psi%d" % i])) - 1.0) < 1e-8
 
 
+def test_davidson_with_lower_states_matches_reference(golden):
+    """State-specific form: the reference's own block_davidson was run once more per fixture with one lower state (a
+    deterministic unnormalised vector) from a guess near root 0 (oracle/ref_dump.cpp); linear.C:201-208, 311-317, 369-375."""
+    rec, big = golden
+    hmul = lambda x: big.flatten(O.multiply_h(big, big.unflatten(x)))
+    ev, vecs, nmult = O.block_davidson(hmul, [rec["ss_guess"]], rec["diag"], float(rec["dav_tol"][0]), int(rec["dav_in"][4]), int(rec["dav_in"][5]),
+                                       lower=[rec["ss_lower"]])
+    assert abs(ev[0] - rec["ss_eval"][0]) < 1e-10
+    assert nmult == int(rec["ss_nmult"][0])                       # same number of H applications
+    assert abs(abs(np.dot(vecs[0], rec["ss_psi"])) - 1.0) < 1e-8
+    l = rec["ss_lower"]
+    assert abs(np.dot(vecs[0], l)) / np.linalg.norm(l) < 1e-9     # orthogonal to the lower state
+    assert ev[0] > rec["dav_evals"][0] - 1e-9                     # lowest state of the projected H lies above the ground state
+    # without the projections the same call converges to a different answer: the fixture really exercises them
+    ev0, _, _ = O.block_davidson(hmul, [rec["ss_guess"]], rec["diag"], float(rec["dav_tol"][0]), int(rec["dav_in"][4]), int(rec["dav_in"][5]))
+    assert abs(ev0[0] - rec["ss_eval"][0]) > 1e-6
+
+
 def test_density_truncation_rotation(golden):
     rec, big = golden
     nroots = int(rec["meta"][4])

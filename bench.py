@@ -356,7 +356,7 @@ def sweep_leg(a):
             for l in open(os.path.join(work, "stats.txt")):
                 for k, v in re.findall(r"(\w+)=([-\d.e+]+)", l):
                     tot[k] = tot.get(k, 0.0) + float(v)
-            out[tag]["hot_path_s"] = {k: tot.get(k, 0.0) for k in ("upload_s", "diag_s", "davidson_s", "density_s", "eig_s", "rotate_s")}
+            out[tag]["hot_path_s"] = {k: tot.get(k, 0.0) for k in ("host_op_build_s", "upload_s", "diag_s", "davidson_s", "density_s", "eig_s", "rotate_s")}
             out[tag]["n_multiply"] = int(tot.get("n_multiply", 0))
             out[tag]["kernel_launches"] = int(tot.get("launches", 0))
     if len(energies) == 2 and len(energies["reference_cpu"]) == len(energies["gpu_dropin"]):
@@ -521,6 +521,13 @@ def run_ours(a):
                 "hbm_peak_gbs": peaks.get("hbm_gbs")}
     if line is not None and world == 1 and not a.no_block_iteration:
         line["block_iteration"] = block_iteration_leg(sb, a, psi, ms_step)
+        # HBM-bound phases (north_star: achieved HBM GB/s for the bandwidth-bound phases): the Davidson level-1 kernels alone
+        hbm = peaks.get("hbm_gbs") or 6534.5
+        lv = sb.measure_level1(reps=10)
+        line["level1_hbm"] = {"peak_gbs": hbm, "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks.get("hbm_gbs") else "fallback 6534.5 GB/s",
+                              "vector_mb": W * 8 / 1e6,
+                              "kernels": {k: {"ms": ms_, "algorithmic_gb": by / 1e9, "gbs": by / (ms_ * 1e-3) / 1e9 if ms_ > 0 else None,
+                                              "frac": by / (ms_ * 1e-3) / 1e9 / hbm if ms_ > 0 else None} for k, (ms_, by) in lv.items()}}
     if line is not None and not a.no_cpu and world == 1:
         kind, v, cores, desc, _, _ = cpu_leg(a, a.cpu_budget_s)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "sample": desc}

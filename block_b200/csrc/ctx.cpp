@@ -142,6 +142,11 @@ struct b2d_ctx {
   std::vector<Slab> slabs;
   int64_t arena_doubles = 0;
 
+  // operator uploads are batched: host images and block descriptors of the operators added since the last flush
+  // (one H2D copy + one pack launch per flush instead of three synchronisations per operator)
+  std::vector<double> pend_data;
+  std::vector<BlockDesc> pend_desc;
+
   // scratch
   DevBuf staging, desc_scratch, work, flat_in, flat_out;
   DevBuf trace_buf;        // B2D_TRACE diagnostic
@@ -252,6 +257,21 @@ int upload_desc(b2d_ctx* ctx, DevBuf& buf, const void* host, size_t bytes) {
   CU(buf.reserve(bytes));
   CU(cudaMemcpyAsync(buf.p, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));   // host vectors are temporaries
+  return B2D_OK;
+}
+
+// pack every pending operator image into its padded device blocks (dev_off is absolute: base pointer 0)
+int flush_pending_ops(b2d_ctx* ctx) {
+  if (ctx->pend_desc.empty()) { ctx->pend_data.clear(); return B2D_OK; }
+  CU(cudaSetDevice(ctx->device));
+  CU(ctx->staging.reserve(ctx->pend_data.size() * 8));
+  CU(cudaMemcpyAsync(ctx->staging.p, ctx->pend_data.data(), ctx->pend_data.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = upload_desc(ctx, ctx->desc_scratch, ctx->pend_desc.data(), ctx->pend_desc.size() * sizeof(BlockDesc));
+  if (rc) return rc;
+  CU(launch_pack((const BlockDesc*)ctx->desc_scratch.p, (int)ctx->pend_desc.size(), (const double*)ctx->staging.p, (double*)nullptr, ctx->stream, &ctx->launches));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->pend_desc.clear();
+  ctx->pend_data.clear();
   return B2D_OK;
 }
 
@@ -550,12 +570,15 @@ int b2d_add_op(b2d_ctx* ctx, int side, int optype, int norb, const int32_t* orbs
       CU(cudaMemsetAsync(op.dev, 0, (size_t)op.dev_size * 8, ctx->stream));
       {
         std::vector<BlockDesc> bd = op_blocks(s, op);
-        CU(ctx->staging.reserve((size_t)op.packed_size * 8));
-        CU(cudaMemcpyAsync(ctx->staging.p, data, (size_t)op.packed_size * 8, cudaMemcpyHostToDevice, ctx->stream));
-        int rc = upload_desc(ctx, ctx->desc_scratch, bd.data(), bd.size() * sizeof(BlockDesc));
-        if (rc) return rc;
-        CU(launch_pack((const BlockDesc*)ctx->desc_scratch.p, (int)bd.size(), (const double*)ctx->staging.p, op.dev, ctx->stream, &ctx->launches));
-        CU(cudaStreamSynchronize(ctx->stream));
+        const int64_t base = (int64_t)ctx->pend_data.size();
+        const int64_t dev_base = (int64_t)((uintptr_t)op.dev / sizeof(double));
+        for (BlockDesc& d : bd) { d.ref_off += base; d.dev_off += dev_base; }
+        ctx->pend_desc.insert(ctx->pend_desc.end(), bd.begin(), bd.end());
+        ctx->pend_data.insert(ctx->pend_data.end(), data, data + op.packed_size);
+        if (ctx->pend_data.size() >= ((size_t)64 << 20) / 8 || ctx->pend_desc.size() >= 4096 * 64) {
+          int rc = flush_pending_ops(ctx);
+          if (rc) return rc;
+        }
       }
     }
   }
@@ -572,6 +595,7 @@ int64_t b2d_op_size(const b2d_ctx* ctx, int side, int op_id) {
 
 int b2d_download_op(b2d_ctx* ctx, int side, int op_id, double* data) {
   NEED_DEVICE();
+  { int frc = flush_pending_ops(ctx); if (frc) return frc; }
   if (side < 0 || side > 1 || op_id < 0 || op_id >= (int)ctx->side[side].ops.size() || !data) return fail(ctx, B2D_ERR_ARG, "b2d_download_op: bad arguments");
   const Side& s = ctx->side[side];
   const OpRec& op = s.ops[op_id];
@@ -589,6 +613,7 @@ int b2d_download_op(b2d_ctx* ctx, int side, int op_id, double* data) {
 
 int b2d_fill_op_random(b2d_ctx* ctx, int side, int op_id, uint64_t seed, double amplitude, int symmetric) {
   NEED_DEVICE();
+  { int frc = flush_pending_ops(ctx); if (frc) return frc; }
   if (side < 0 || side > 1 || op_id < 0 || op_id >= (int)ctx->side[side].ops.size()) return fail(ctx, B2D_ERR_ARG, "b2d_fill_op_random: bad arguments");
   const Side& s = ctx->side[side];
   const OpRec& op = s.ops[op_id];
@@ -624,6 +649,7 @@ int b2d_fill_op_random(b2d_ctx* ctx, int side, int op_id, uint64_t seed, double 
 int b2d_plan(b2d_ctx* ctx, const int32_t* psi_dq, double core_energy, int hubbard, int norbs, int rank, int nranks) {
   if (!ctx || !psi_dq || nranks < 1 || rank < 0 || rank >= nranks) return fail(ctx, B2D_ERR_ARG, "b2d_plan: bad arguments");
   if (ctx->side[0].nq == 0 || ctx->side[1].nq == 0) return fail(ctx, B2D_ERR_ARG, "b2d_plan: set both blocks first");
+  if (ctx->has_device) { int frc = flush_pending_ops(ctx); if (frc) return frc; }
   try {
     ctx->core_energy = core_energy; ctx->hubbard = hubbard != 0; ctx->norbs = norbs; ctx->rank = rank; ctx->nranks = nranks;
     int dq[3] = {psi_dq[0], psi_dq[1], psi_dq[2]};
@@ -1195,6 +1221,47 @@ int b2d_diagonalise_dm(b2d_ctx* ctx, double* evals_out) {
     CU(cudaMemcpyAsync(info.data(), ctx->eig_info.p, large.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     for (int v : info) if (v != 0) return fail(ctx, B2D_ERR_CUDA, "cusolverDnDsyevd did not converge (info " + std::to_string(v) + ")");
+    // Divide-and-conquer leaves the SMALL eigenvalues of rho with absolute errors of ~1e-14 (measured against dsyev_), which is
+    // the size of the reference's clamp (1e-14) and a tenth of its keep threshold (1e-13, rotationmat.C:161,274).  The eigenvectors
+    // are good, so the eigenvalues are recomputed as Rayleigh quotients v_i.(rho v_i): G_q = Vt_q rho_q by the grouped contraction
+    // kernel, then one dot product per row - accurate to the rounding of one FP64 product (~1e-17), like dsyev_'s.
+    Schedule S;
+    Chunk ch;
+    std::vector<BlockDesc> lsd;
+    for (int q : large) {
+      const int d = L.dims[q];
+      GSeg sg;
+      memset(&sg, 0, sizeof(sg));
+      sg.a = (int64_t)(uintptr_t)((double*)ctx->eig_vt.p + ctx->rho_off[q]);
+      sg.b = (int64_t)(uintptr_t)((double*)ctx->rho.p + ctx->rho_off[q]);
+      sg.a_base = sg.b_base = B2D_BASE_ABS;
+      sg.a_trans = 0; sg.b_kmajor = 0;
+      sg.lda = sg.ldb = pad_ld(d);
+      sg.k = d;
+      sg.alpha = 1.0;
+      GGroup G;
+      memset(&G, 0, sizeof(G));
+      G.c = ctx->rho_off[q]; G.c_base = B2D_BASE_AUX; G.ldc = pad_ld(d); G.m = G.n = d; G.accumulate = 0;
+      G.seg_begin = (int)ch.step2.segs.size();
+      ch.step2.segs.push_back(sg);
+      G.seg_end = (int)ch.step2.segs.size();
+      ch.step2.groups.push_back(G);
+      lsd.push_back(sd[q]);
+    }
+    make_tiles(ch.step2, ctx->forced_class);
+    ch.nterms = 1;
+    S.chunks.push_back(std::move(ch));
+    DevSchedule D;
+    rc = upload_schedule(ctx, S, D);
+    if (rc) return rc;
+    rc = run_schedule(ctx, S, D, nullptr, nullptr, (double*)ctx->eig_g.p);
+    if (rc) return rc;
+    rc = upload_desc(ctx, ctx->sector_desc, lsd.data(), lsd.size() * sizeof(BlockDesc));
+    if (rc) return rc;
+    CU(launch_rayleigh((const BlockDesc*)ctx->sector_desc.p, (int)lsd.size(), (const double*)ctx->eig_g.p, (const double*)ctx->eig_vt.p,
+                       (double*)ctx->eig_vals.p, ctx->stream, &ctx->launches));
+    CU(cudaStreamSynchronize(ctx->stream));
+    D.buf.release();
   }
   end_timing(ctx);
   std::vector<double> raw(nev);
@@ -1463,6 +1530,39 @@ int b2d_rotated_op_download(b2d_ctx* ctx, int op_id, uint8_t* allowed, double* d
   return B2D_OK;
 }
 
+int64_t b2d_rotated_total_size(const b2d_ctx* ctx) {
+  if (!ctx || !ctx->have_rotated) return -1;
+  int64_t n = 0;
+  for (const OpRec& op : ctx->rotated.ops) n += op.packed_size;
+  return n;
+}
+
+int b2d_rotated_download_all(b2d_ctx* ctx, double* data) {
+  NEED_DEVICE();
+  if (!ctx->have_rotated || !data) return fail(ctx, B2D_ERR_ARG, "no rotated operators");
+  const Side& N = ctx->rotated;
+  std::vector<BlockDesc> all;
+  int64_t base = 0;
+  for (const OpRec& op : N.ops) {
+    if (op.packed_size == 0) continue;
+    if (!op.dev) return fail(ctx, B2D_ERR_ARG, "b2d_rotated_download_all: an operator is not resident on this rank");
+    std::vector<BlockDesc> bd = op_blocks(N, op);
+    const int64_t dev_base = op.dev - (const double*)ctx->rotated_arena.p;
+    for (BlockDesc& d : bd) { d.ref_off += base; d.dev_off += dev_base; }
+    all.insert(all.end(), bd.begin(), bd.end());
+    base += op.packed_size;
+  }
+  if (base == 0) return B2D_OK;
+  CU(cudaSetDevice(ctx->device));
+  CU(ctx->staging.reserve((size_t)base * 8));
+  int rc = upload_desc(ctx, ctx->desc_scratch, all.data(), all.size() * sizeof(BlockDesc));
+  if (rc) return rc;
+  CU(launch_unpack((const BlockDesc*)ctx->desc_scratch.p, (int)all.size(), (const double*)ctx->rotated_arena.p, (double*)ctx->staging.p, ctx->stream, &ctx->launches));
+  CU(cudaMemcpyAsync(data, ctx->staging.p, (size_t)base * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return B2D_OK;
+}
+
 namespace {
 const PsiLayout& layout_for(b2d_ctx* ctx, const int* dq) {
   std::vector<int> key(dq, dq + 3);
@@ -1547,6 +1647,58 @@ int b2d_tensor_multiply_one_host(b2d_ctx* ctx, int side, int op_id, int transpos
   CU(cudaMemcpyAsync(v_flat, ctx->staging.p, (size_t)Pd.W * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   D.buf.release();
+  return B2D_OK;
+}
+
+// rho += weight * w w^T for a host wavefunction of ANY target quantum dq (MultiplyProduct(w, Transpose(w), dm, weight),
+// operatorfunctions.C:630-650): the device half of DensityMatrix::add_twodot_noise (density.C:92-165), whose random
+// wavefunctions are drawn on the host (glibc rand(), Wavefunction::Randomise) so that the stream stays the reference's.
+int b2d_add_wavefunction_density(b2d_ctx* ctx, const int32_t* dq, const double* flat, double weight) {
+  NEED_DEVICE(); NEED_PLAN();
+  if (!dq || !flat) return fail(ctx, B2D_ERR_ARG, "b2d_add_wavefunction_density: bad arguments");
+  if (!ctx->rho.p) return fail(ctx, B2D_ERR_ARG, "b2d_add_wavefunction_density: call b2d_make_density first");
+  CU(cudaSetDevice(ctx->device));
+  const Side& L = ctx->side[0];
+  int q[3] = {dq[0], dq[1], dq[2]};
+  const PsiLayout& Pd = layout_for(ctx, q);
+  if (Pd.W == 0) return B2D_OK;
+  Schedule S;
+  Chunk ch;
+  std::vector<std::vector<GSeg>> per(L.nq);
+  try {
+    add_density_segments(Pd, B2D_BASE_WORK, 0, weight, per);
+  } catch (const std::exception& e) { return fail(ctx, B2D_ERR_ARG, e.what()); }
+  for (int sq = 0; sq < L.nq; ++sq) {
+    if (per[sq].empty()) continue;
+    GGroup G;
+    memset(&G, 0, sizeof(G));
+    G.c = ctx->rho_off[sq]; G.c_base = B2D_BASE_AUX; G.ldc = pad_ld(L.dims[sq]); G.m = G.n = L.dims[sq]; G.accumulate = 1;
+    G.seg_begin = (int)ch.step2.segs.size();
+    ch.step2.segs.insert(ch.step2.segs.end(), per[sq].begin(), per[sq].end());
+    G.seg_end = (int)ch.step2.segs.size();
+    ch.step2.groups.push_back(G);
+  }
+  make_tiles(ch.step2, ctx->forced_class);
+  ch.nterms = 1; ch.work = Pd.Wp;
+  S.work_max = Pd.Wp;
+  S.chunks.push_back(std::move(ch));
+  DevSchedule D;
+  int rc = upload_schedule(ctx, S, D);
+  if (rc) return rc;
+  CU(ctx->work.reserve((size_t)std::max<int64_t>(Pd.Wp, 16) * 8));
+  CU(cudaMemsetAsync(ctx->work.p, 0, (size_t)Pd.Wp * 8, ctx->stream));
+  std::vector<BlockDesc> bd(Pd.nblocks());
+  for (int p = 0; p < Pd.nblocks(); ++p) { bd[p].ref_off = Pd.ref_off[p]; bd[p].dev_off = Pd.dev_off[p]; bd[p].rows = Pd.rows[p]; bd[p].cols = Pd.cols[p]; bd[p].ld = Pd.ld[p]; bd[p].pad = 0; }
+  rc = upload_desc(ctx, ctx->desc_scratch, bd.data(), bd.size() * sizeof(BlockDesc));
+  if (rc) return rc;
+  CU(ctx->staging.reserve((size_t)Pd.W * 8));
+  CU(cudaMemcpyAsync(ctx->staging.p, flat, (size_t)Pd.W * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CU(launch_pack((const BlockDesc*)ctx->desc_scratch.p, Pd.nblocks(), (const double*)ctx->staging.p, (double*)ctx->work.p, ctx->stream, &ctx->launches));
+  double* bases[B2D_NUM_BASES] = {nullptr, (double*)ctx->user_pool.p, (double*)ctx->work.p, nullptr, (double*)ctx->rho.p};
+  CU(launch_gemm_batch(D.chunks[0].s2, bases, ctx->stream, &ctx->launches));
+  CU(cudaStreamSynchronize(ctx->stream));
+  D.buf.release();
+  ctx->have_eig = ctx->have_rot = ctx->have_rotated = false;
   return B2D_OK;
 }
 
@@ -1742,6 +1894,64 @@ int b2d_measure_fp64_peak(b2d_ctx* ctx, double* dmma_tflops, double* dfma_tflops
   if (dmma_tflops) *dmma_tflops = a;
   if (dfma_tflops) *dfma_tflops = b;
   return B2D_OK;
+}
+
+// Level-1 (HBM-bound) kernels of the Davidson iteration timed alone with CUDA events on the context's stream, on the
+// wavefunction slots slot0 .. slot0+17 (contents are overwritten).  out[2k] = milliseconds per launch, out[2k+1] = ALGORITHMIC
+// bytes per launch (8 bytes x vectors read or written) for k = 0 multi_dot(8 vectors) 1 rotate(8 -> 8)
+// 2 residual 3 olsen 4 mgs_step 5 axpy 6 D2D copy (the yardstick).  Consecutive launches rotate over two disjoint sets of
+// vectors so that a 126 MB L2 cannot serve the re-reads.
+int b2d_measure_level1(b2d_ctx* ctx, int slot0, int reps, double* out) {
+  NEED_DEVICE(); NEED_PLAN();
+  if (reps < 1 || !out) return fail(ctx, B2D_ERR_ARG, "b2d_measure_level1: bad arguments");
+  for (int i = 0; i < 18; ++i) CHECK_SLOT(slot0 + i);
+  CU(cudaSetDevice(ctx->device));
+  const int64_t n = ctx->psi.Wp;
+  cudaStream_t st = ctx->stream;
+  int64_t* L = &ctx->launches;
+  double* partials = (double*)ctx->partials.p;
+  double* sc = (double*)ctx->scalars.p;
+  double* misc = sc + 2080;
+  double* alpha = sc + 1056;
+  {   // a well-conditioned 8x8 rotation (identity) and non-trivial vectors
+    std::vector<double> a(1024, 0.0);
+    for (int i = 0; i < 8; ++i) a[i * 32 + i] = 1.0;
+    CU(cudaMemcpyAsync(alpha, a.data(), 1024 * 8, cudaMemcpyHostToDevice, st));
+    CU(cudaStreamSynchronize(st));
+    for (int i = 0; i < 18; ++i) {
+      CU(cudaMemsetAsync(user_vec(ctx, slot0 + i), 0, (size_t)n * 8, st));
+      CU(launch_fill_random(user_vec(ctx, slot0 + i), (const BlockDesc*)ctx->psi_blocks.p, ctx->psi.nblocks(), 77 + i, 0.5, st, L));
+    }
+  }
+  cudaEvent_t e0, e1;
+  CU(cudaEventCreate(&e0)); CU(cudaEventCreate(&e1));
+  auto V = [&](int set, int i) { return user_vec(ctx, slot0 + set * 9 + i); };
+  auto run = [&](int k, double vectors, auto&& body) -> int {
+    for (int w = 0; w < 2; ++w) { cudaError_t e = body(w & 1); if (e != cudaSuccess) return fail(ctx, B2D_ERR_CUDA, cudaGetErrorString(e)); }
+    CU(cudaEventRecord(e0, st));
+    for (int r = 0; r < reps; ++r) { cudaError_t e = body(r & 1); if (e != cudaSuccess) return fail(ctx, B2D_ERR_CUDA, cudaGetErrorString(e)); }
+    CU(cudaEventRecord(e1, st));
+    CU(cudaEventSynchronize(e1));
+    float ms = 0; CU(cudaEventElapsedTime(&ms, e0, e1));
+    out[2 * k] = ms / reps; out[2 * k + 1] = vectors * 8.0 * (double)ctx->psi.W;
+    return B2D_OK;
+  };
+  int rc;
+  rc = run(0, 9, [&](int s) { VecList x; for (int i = 0; i < 8; ++i) x.p[i] = V(s, i); return launch_multi_dot(8, x, V(s, 8), n, partials, misc + 8, st, L); });
+  if (rc) return rc;
+  rc = run(1, 16, [&](int s) { VecList x; for (int i = 0; i < 8; ++i) x.p[i] = V(s, i); return launch_rotate(8, 8, x, alpha, 32, n, st, L); });
+  if (rc) return rc;
+  rc = run(2, 3, [&](int s) { return launch_residual(V(s, 0), V(s, 1), misc + 8, V(s, 2), n, partials, misc + 4, st, L); });
+  if (rc) return rc;
+  rc = run(3, 7, [&](int s) { return launch_olsen(V(s, 2), V(s, 1), V(s, 3), misc + 8, n, partials, misc, st, L); });
+  if (rc) return rc;
+  rc = run(4, 5, [&](int s) { return launch_mgs_step(V(s, 2), V(s, 1), n, partials, misc, st, L); });
+  if (rc) return rc;
+  rc = run(5, 3, [&](int s) { return launch_axpy(V(s, 4), V(s, 5), nullptr, 1e-3, n, st, L); });
+  if (rc) return rc;
+  rc = run(6, 2, [&](int s) { return cudaMemcpyAsync(V(s, 6), V(s, 7), (size_t)n * 8, cudaMemcpyDeviceToDevice, st); });
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  return rc;
 }
 
 }  // extern "C"

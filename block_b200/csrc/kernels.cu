@@ -550,6 +550,29 @@ __global__ void __launch_bounds__(EIG_THREADS) sector_eig_kernel(const BlockDesc
   if (threadIdx.x == 0) sweeps[blockIdx.x] = sweep;
 }
 
+// evals[ref_off + i] = v_i . g_i for the rows of V and G = V rho (Rayleigh quotients of given eigenvectors): one CTA per sector
+__global__ void __launch_bounds__(EIG_THREADS) rayleigh_kernel(const BlockDesc* __restrict__ sectors, const double* __restrict__ g, const double* __restrict__ vt,
+                                                               double* __restrict__ evals) {
+  const BlockDesc sd = sectors[blockIdx.x];
+  const int d = sd.rows, ld = sd.ld;
+  const double* G = g + sd.dev_off;
+  const double* V = vt + sd.dev_off;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  for (int i = warp; i < d; i += nwarps) {
+    double acc = 0.0;
+    for (int j = lane; j < d; j += 32) acc += V[(int64_t)i * ld + j] * G[(int64_t)i * ld + j];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) evals[sd.ref_off + i] = acc;
+  }
+}
+cudaError_t launch_rayleigh(const BlockDesc* sectors, int nsectors, const double* g, const double* vt, double* evals, cudaStream_t s, int64_t* launches) {
+  if (nsectors == 0) return cudaSuccess;
+  rayleigh_kernel<<<nsectors, EIG_THREADS, 0, s>>>(sectors, g, vt, evals);
+  B2D_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
 cudaError_t launch_sector_eig(const BlockDesc* sectors, int nsectors, double* g, double* vt, double* evals, int* sweeps, cudaStream_t s, int64_t* launches) {
   if (nsectors == 0) return cudaSuccess;
   sector_eig_kernel<<<nsectors, EIG_THREADS, 0, s>>>(sectors, g, vt, evals, sweeps);

@@ -68,6 +68,9 @@ cudaError_t launch_diag(const BlockDesc* blocks, int nblocks, const DiagTask* ta
 // sectors[q] = {rows=cols=d_q, ld, dev_off = offset of G_q / Vt_q in g / vt, ref_off = offset of the eigenvalues}
 // On exit: rows of vt are the eigenvectors, evals[ref_off + i] the eigenvalue of row i (unsorted), sweeps[q] the sweep count.
 cudaError_t launch_sector_eig(const BlockDesc* sectors, int nsectors, double* g, double* vt, double* evals, int* sweeps, cudaStream_t s, int64_t* launches);
+// evals[ref_off + i] = vt_i . g_i (Rayleigh quotients of the rows of vt, g = vt * rho): eigenvalues of library eigenvectors to the
+// absolute accuracy of one FP64 matrix product
+cudaError_t launch_rayleigh(const BlockDesc* sectors, int nsectors, const double* g, const double* vt, double* evals, cudaStream_t s, int64_t* launches);
 // U_q[:, c] = vt_q[src_row[c], :]   (gather the kept eigenvectors as columns, selection order)
 struct GatherDesc {
   int64_t vt_off, u_off;

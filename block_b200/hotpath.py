@@ -252,6 +252,13 @@ class SpinBlock:
             self._ck(self.lib.b2d_add_onedot_noise(self._ctx, n, 0, float(noise)))
         return self.density()
 
+    def add_wavefunction_density(self, dq, flat, weight):
+        """rho += weight * w w^T for a host wavefunction of target quantum dq (the device half of add_twodot_noise, density.C:92-165)."""
+        q = np.asarray(dq, dtype=np.int32)
+        flat = np.ascontiguousarray(flat, dtype=np.float64)
+        assert flat.size == self.wavefunction_size(dq)
+        self._ck(self.lib.b2d_add_wavefunction_density(self._ctx, _p(q, _lib.c_i32p), _p(flat, _lib.c_f64p), float(weight)))
+
     def wavefunction_size(self, dq):
         q = np.asarray(dq, dtype=np.int32)
         return int(self.lib.b2d_wavefunction_size(self._ctx, _p(q, _lib.c_i32p)))
@@ -361,6 +368,14 @@ class SpinBlock:
         a, b = C.c_double(0), C.c_double(0)
         self._ck(self.lib.b2d_measure_fp64_peak(self._ctx, C.byref(a), C.byref(b)))
         return a.value, b.value
+
+    def measure_level1(self, reps=10):
+        """HBM-bound Davidson kernels timed alone: dict name -> (ms per launch, algorithmic bytes per launch)."""
+        self.reserve(18)
+        out = np.zeros(14)
+        self._ck(self.lib.b2d_measure_level1(self._ctx, 0, int(reps), _p(out, _lib.c_f64p)))
+        names = ["multi_dot8", "rotate8", "residual", "olsen", "mgs_step", "axpy", "device_copy"]
+        return {n: (out[2 * k], out[2 * k + 1]) for k, n in enumerate(names)}
 
     def fill_op_random(self, side, op_id, seed, amplitude=1.0, symmetric=False):
         self._ck(self.lib.b2d_fill_op_random(self._ctx, side, op_id, int(seed), float(amplitude), int(symmetric)))

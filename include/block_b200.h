@@ -182,8 +182,13 @@ int b2d_make_density(b2d_ctx* ctx, int nroots, int slot0, const double* weights)
  * does when the schedule's noise > 0 (density.C:40-60): rho += (noise/nroots) / tr(rho_n) * rho_n with
  * rho_n = sum_O (O psi)(O psi)^T / |O psi|^2 over the left block's CRE, CRE_CRE, CRE_DES (or DES_DESCOMP, CRE_DESCOMP) operators
  * and their transposes, each into its +-dQ shifted sector.  Under a term partition every rank does its operators and rho_n
- * is all-reduced.  Call after b2d_make_density.  (additional_noise / add_twodot_noise draws from glibc rand(): host side.) */
+ * is all-reduced.  Call after b2d_make_density.  (additional_noise / add_twodot_noise: b2d_add_wavefunction_density.) */
 int b2d_add_onedot_noise(b2d_ctx* ctx, int nroots, int slot0, double noise);
+/* rho += weight * w w^T for a HOST wavefunction w of any target quantum dq, flat in its own FlattenInto order
+ * (b2d_wavefunction_size(ctx, dq) doubles): MultiplyProduct(w, Transpose(w), dm, weight), operatorfunctions.C:630-650.  This is the
+ * device half of DensityMatrix::add_twodot_noise (density.C:92-165): the caller draws and normalises the random wavefunctions
+ * (Wavefunction::Randomise, glibc rand()) so that the random stream is the reference's own.  Call after b2d_make_density. */
+int b2d_add_wavefunction_density(b2d_ctx* ctx, const int32_t* dq, const double* flat, double weight);
 int64_t b2d_density_size(const b2d_ctx* ctx);       /* sum_q d_q^2 */
 int b2d_density_download(b2d_ctx* ctx, double* rho);   /* blocks q = 0..nq-1, row-major d_q x d_q */
 int b2d_density_upload(b2d_ctx* ctx, const double* rho);
@@ -210,7 +215,11 @@ int b2d_transform_operators(b2d_ctx* ctx);
 int b2d_rotated_num_sectors(const b2d_ctx* ctx);
 int b2d_rotated_sectors(const b2d_ctx* ctx, int32_t* old_index, int32_t* dims);
 int64_t b2d_rotated_op_size(const b2d_ctx* ctx, int op_id);
-int b2d_rotated_op_download(b2d_ctx* ctx, int op_id, uint8_t* allowed, double* data);
+int b2d_rotated_op_download(b2d_ctx* ctx, int op_id, uint8_t* allowed, double* data);   /* data may be NULL: mask only */
+/* All rotated operators in one device pass and one copy: the packed blocks of operator 0, 1, ... back to back
+ * (b2d_rotated_op_size(id) doubles each, b2d_rotated_total_size in total). */
+int64_t b2d_rotated_total_size(const b2d_ctx* ctx);
+int b2d_rotated_download_all(b2d_ctx* ctx, double* data);
 
 /* SpinBlock::RenormaliseFrom (spinblock.h:247-251, renormalise.C:39-133), two-dot: diagonalH, Davidson from the guesses in
  * slot0.., density matrix (+ one-dot noise if noise > 0), eigen-decomposition, state selection.  Leaves the solutions in
@@ -241,6 +250,12 @@ void* b2d_stream(b2d_ctx* ctx);                      /* cudaStream_t, for event 
 /* FP64 yardsticks measured with this library's own kernels on the context's device: DMMA register loop
  * (TFLOP/s), DFMA register loop (TFLOP/s). */
 int b2d_measure_fp64_peak(b2d_ctx* ctx, double* dmma_tflops, double* dfma_tflops);
+
+/* HBM-bound level-1 kernels of the Davidson iteration (DotProduct / ScaleAdd / Normalise of BaseOperator.C:240-288 and the Ritz
+ * rotation of linear.C:279-294 in their fused device forms) timed alone with CUDA events on wavefunction slots slot0..slot0+17
+ * (overwritten).  out[2k] = ms per launch, out[2k+1] = algorithmic bytes per launch; k = 0 multi_dot(8) 1 rotate(8) 2 residual
+ * 3 olsen 4 mgs_step 5 axpy 6 device copy (yardstick).  14 doubles. */
+int b2d_measure_level1(b2d_ctx* ctx, int slot0, int reps, double* out);
 
 #ifdef __cplusplus
 }

@@ -24,7 +24,10 @@
 //   B2D_DROPIN_CHECK=1    every hook ALSO runs the reference's CPU function on copies and prints the differences
 //   B2D_DROPIN_DAVIDSON   "device" (default): block_davidson on the GPU;  "host": the reference's block_davidson with
 //                         multiplyH through b2d_multiplyH_host (host buffers, the e2e form of the sigma call)
+//   B2D_DROPIN_TRANSFORM  "device" (default): the transform hook does the block's bookkeeping itself;  "reference": it lets the
+//                         reference's transform_operators do it with MatrixRotate switched off (re-builds virtual operators on the CPU)
 //   B2D_DROPIN_WORKSPACE_MB   T workspace of the two-step contraction
+//   B2D_DROPIN_OPTIONS    "key=value,..." library options (b2d_set_option), e.g. eig_jacobi_max=512
 //   B2D_DROPIN_STATS      file that receives one line per block iteration (timings, flops, H applications)
 #include <sys/time.h>
 #include <algorithm>
@@ -82,6 +85,7 @@ struct Gpu {
   bool rot_on_device = false;    // b2d_select_states ran for this block
   bool in_transform = false;     // MatrixRotate is switched off
   // statistics of the current block iteration
+  double t_build = 0;            // inside the reference's own Op::build for direct-mode virtual operators (host side)
   double t_upload = 0, t_diag = 0, t_dav = 0, t_rho = 0, t_eig = 0, t_rot = 0, dav_dev_ms = 0, flops = 0;
   int nmult = 0, call = -1;
   // check mode: CPU results kept between hooks
@@ -126,9 +130,9 @@ void write_stats() {
   if (!path || !g.ctx) return;
   FILE* f = fopen(path, "a");
   if (!f) return;
-  fprintf(f, "call=%d lsites=%d rsites=%d W=%lld sigma_flops=%.6e n_multiply=%d upload_s=%.6f diag_s=%.6f davidson_s=%.6f davidson_dev_ms=%.3f "
+  fprintf(f, "call=%d lsites=%d rsites=%d W=%lld sigma_flops=%.6e n_multiply=%d host_op_build_s=%.6f upload_s=%.6f diag_s=%.6f davidson_s=%.6f davidson_dev_ms=%.3f "
              "density_s=%.6f eig_s=%.6f rotate_s=%.6f launches=%lld\n",
-          g.call, (int)g.lsites.size(), (int)g.rsites.size(), (long long)g.W, g.flops, g.nmult, g.t_upload, g.t_diag, g.t_dav, g.dav_dev_ms, g.t_rho,
+          g.call, (int)g.lsites.size(), (int)g.rsites.size(), (long long)g.W, g.flops, g.nmult, g.t_build, g.t_upload, g.t_diag, g.t_dav, g.dav_dev_ms, g.t_rho,
           g.t_eig, g.t_rot, (long long)b2d_kernel_launches(g.ctx));
   fclose(f);
 }
@@ -151,7 +155,9 @@ void upload_block(int side, SpinBlock& b, vector<OpRef>* keep) {
       vector<boost::shared_ptr<SparseMatrix> > vec = arr.get_local_element(i);
       for (size_t c = 0; c < vec.size(); ++c) {
         // direct-mode virtual operators are built here by the reference's own Op::build (host side of the seam)
+        double tb = now_s();
         boost::shared_ptr<SparseMatrix> rep = vec[c]->getworkingrepresentation(&b);
+        g.t_build += now_s() - tb;
         SparseMatrix& op = *rep;
         if (op.get_deltaQuantum_size() != 1) die("operator with several deltaQuantum components (non spin-adapted / BCS run): not covered");
         if (op.nrows() != nq || op.ncols() != nq) die("operator shape does not match the block's StateInfo");
@@ -188,9 +194,21 @@ void ensure_ctx(const SpinBlock& big_c) {
   if (!dmrginp.spinAdapted()) die("non spin-adapted run: not covered by the GPU path");
   if (dmrginp.hamiltonian() != QUANTUM_CHEMISTRY && dmrginp.hamiltonian() != HUBBARD) die("Hamiltonian type not covered by the GPU path");
   double t0 = now_s();
+  g.t_build = 0;
   int dev = getenv("B2D_DEVICE") ? atoi(getenv("B2D_DEVICE")) : 0;
   if (b2d_create(dev, &g.ctx)) die(string("b2d_create: ") + b2d_last_error(0));
   if (getenv("B2D_DROPIN_WORKSPACE_MB")) ck(b2d_set_option(g.ctx, "workspace_mb", atof(getenv("B2D_DROPIN_WORKSPACE_MB"))), "b2d_set_option");
+  if (getenv("B2D_DROPIN_OPTIONS")) {   // "key=value,key=value" -> b2d_set_option
+    string all = getenv("B2D_DROPIN_OPTIONS");
+    size_t pos = 0;
+    while (pos < all.size()) {
+      size_t end = all.find(',', pos); if (end == string::npos) end = all.size();
+      string kv = all.substr(pos, end - pos);
+      size_t eq = kv.find('=');
+      if (eq != string::npos) ck(b2d_set_option(g.ctx, kv.substr(0, eq).c_str(), atof(kv.substr(eq + 1).c_str())), "b2d_set_option");
+      pos = end + 1;
+    }
+  }
   g.left = big.get_leftBlock(); g.right = big.get_rightBlock(); g.lsites = big.get_leftBlock()->get_sites(); g.rsites = big.get_rightBlock()->get_sites();
   upload_block(0, *big.get_leftBlock(), &g.left_ops);
   upload_block(1, *big.get_rightBlock(), 0);
@@ -200,7 +218,7 @@ void ensure_ctx(const SpinBlock& big_c) {
   ck(b2d_plan(g.ctx, dq, coreEnergy[big.get_integralIndex()], dmrginp.hamiltonian() == HUBBARD ? 1 : 0, norbs, 0, 1), "b2d_plan");
   g.W = b2d_psi_size(g.ctx);
   g.flops = b2d_sigma_flops(g.ctx, 1);
-  g.t_upload = now_s() - t0;
+  g.t_upload = now_s() - t0 - g.t_build;
   g.t_diag = g.t_dav = g.t_rho = g.t_eig = g.t_rot = g.dav_dev_ms = 0; g.nmult = 0;
   ++g.call;
 }
@@ -329,9 +347,9 @@ void real_makedm(DensityMatrix* self, const vector<Wavefunction>& ws, SpinBlock&
 void wrap_makedm(DensityMatrix* self, const vector<Wavefunction>& ws, SpinBlock& big, const vector<double>& wts, const double noise, const double add_noise, bool warmup) asm("__wrap_" SYM_makedensitymatrix);
 void wrap_makedm(DensityMatrix* self, const vector<Wavefunction>& ws, SpinBlock& big, const vector<double>& wts, const double noise, const double add_noise, bool warmup) {
   ensure_ctx(big);
-  if (add_noise > NUMERICAL_ZERO) die("add_twodot_noise (RANDOM noise, density.C:92-165): draws from glibc rand() - not covered by the GPU path; use twodot_noise 0");
   DensityMatrix chk;
   bool check = env_on("B2D_DROPIN_CHECK");
+  if (check && add_noise > NUMERICAL_ZERO) check = false;   // the CPU copy would consume the rand() stream a second time
   if (check) { chk = *self; real_makedm(&chk, ws, big, wts, noise, add_noise, warmup); }
   double t0 = now_s();
   int nroots = (int)wts.size();     // density.C:31: one term per weight
@@ -340,6 +358,38 @@ void wrap_makedm(DensityMatrix* self, const vector<Wavefunction>& ws, SpinBlock&
   for (size_t i = 0; i < ws.size(); ++i) upload_wave(ROOT_SLOT0 + (int)i, ws[i]);
   ck(b2d_make_density(g.ctx, nroots, ROOT_SLOT0, wts.data()), "b2d_make_density");
   if (noise > NUMERICAL_ZERO) ck(b2d_add_onedot_noise(g.ctx, (int)ws.size(), ROOT_SLOT0, noise), "b2d_add_onedot_noise");   // density.C:40-60
+  if (add_noise > NUMERICAL_ZERO) {
+    // DensityMatrix::add_twodot_noise (density.C:92-165), once per root with (1.0*noise)/nroots (density.C:71-80): random
+    // wavefunctions in the 12 neighbouring (N +- 1|2, S +- 1|2) targets, drawn HERE with the reference's own
+    // Wavefunction::Randomise so that the glibc rand() stream is the unmodified run's; the products w w^T run on the device
+    if (dmrginp.hamiltonian() == BCS) die("BCS: not covered");
+    const int N = dmrginp.total_particle_number(), S = dmrginp.total_spin_number().getirrep();
+    const IrrepSpace& sym = dmrginp.total_symmetry_number();
+    vector<SpinQuantum> toadd;
+    const int one[2] = {+1, -1}, two[3] = {+2, 0, -2};
+    for (int k = 0; k < 2; ++k) toadd.push_back(SpinQuantum(N + one[k], SpinSpace(S + 1), sym));
+    if (S >= 1) for (int k = 0; k < 2; ++k) toadd.push_back(SpinQuantum(N + one[k], SpinSpace(S - 1), sym));
+    for (int k = 0; k < 3; ++k) toadd.push_back(SpinQuantum(N + two[k], SpinSpace(S + 2), sym));
+    toadd.push_back(SpinQuantum(N + 2, SpinSpace(S), sym));
+    toadd.push_back(SpinQuantum(N - 2, SpinSpace(S), sym));
+    if (S >= 2) for (int k = 0; k < 3; ++k) toadd.push_back(SpinQuantum(N + two[k], SpinSpace(S - 2), sym));
+    vector<double> flat;
+    for (size_t root = 0; root < ws.size(); ++root)
+      for (size_t q = 0; q < toadd.size(); ++q) {
+        Wavefunction w;
+        w.initialise(toadd[q], &big, false);
+        w.Randomise();
+        double nrm = DotProduct(w, w);
+        if (fabs(nrm) > NUMERICAL_ZERO) {
+          Scale(1. / sqrt(nrm), w);
+          flatten(w, flat);
+          int32_t dq[3] = {toadd[q].get_n(), toadd[q].get_s().getirrep(), toadd[q].get_symm().getirrep()};
+          if ((int64_t)flat.size() != b2d_wavefunction_size(g.ctx, dq)) die("add_twodot_noise: noise wavefunction size differs from the device layout");
+          ck(b2d_add_wavefunction_density(g.ctx, dq, flat.data(), ((1.0 * noise) / ws.size()) / toadd.size()), "b2d_add_wavefunction_density");
+        }
+        w.CleanUp();
+      }
+  }
   vector<double> rho((size_t)b2d_density_size(g.ctx));
   ck(b2d_density_download(g.ctx, rho.data()), "b2d_density_download");
   size_t off = 0;
@@ -391,9 +441,13 @@ void wrap_diagdm(SparseMatrix& traced, SparseMatrix& transform, vector<DiagonalM
   }
   g.t_eig += now_s() - t0;
   if (check) {
-    double d = 0;
-    for (int q = 0; q < nq; ++q) for (int i = 0; i < eigs[q].Nrows(); ++i) d = std::max(d, fabs(eigs[q].element(i, i) - g.chk_eigs[q].element(i, i)));
-    fprintf(stderr, "B2D_CHECK call=%d diagonalise_dm eigenvalue max_abs_diff=%.3e\n", g.call, d);
+    double d = 0, rel_cut = 0; int near_cut = 0;
+    for (int q = 0; q < nq; ++q) for (int i = 0; i < eigs[q].Nrows(); ++i) {
+      double a = eigs[q].element(i, i), b = g.chk_eigs[q].element(i, i);
+      d = std::max(d, fabs(a - b));
+      if (b > 1e-14 && b < 1e-12) { ++near_cut; rel_cut = std::max(rel_cut, fabs(a - b) / b); }   // the 1e-13 keep threshold (rotationmat.C:161)
+    }
+    fprintf(stderr, "B2D_CHECK call=%d diagonalise_dm eigenvalue max_abs_diff=%.3e near_cut=%d near_cut_max_rel_diff=%.3e\n", g.call, d, near_cut, rel_cut);
   }
 }
 
@@ -470,35 +524,62 @@ void wrap_transform(SpinBlock* self, vector<Matrix>& rot) {
   if (flat.empty()) flat.push_back(0.0);
   ck(b2d_rotation_upload(g.ctx, kept.data(), flat.data()), "b2d_rotation_upload");
   ck(b2d_transform_operators(g.ctx), "b2d_transform_operators");
-  // the reference's bookkeeping (new StateInfo, allocation, core flags, freeing the children) with MatrixRotate switched off
-  g.in_transform = true;
-  real_transform(self, rot);
-  g.in_transform = false;
+  bool check = env_on("B2D_DROPIN_CHECK");
+  const char* tmode = getenv("B2D_DROPIN_TRANSFORM");
+  if (check || (tmode && string(tmode) == "reference")) {
+    // the reference's own bookkeeping (new StateInfo, allocation, core flags, freeing the children) with MatrixRotate switched
+    // off.  It also re-BUILDS every virtual operator on the CPU (BaseOperator.C:369-375) only to ignore it: kept for check mode.
+    g.in_transform = true;
+    real_transform(self, rot);
+    g.in_transform = false;
+  } else {
+    // the same bookkeeping done here (save_load_block.C:270-316), without building anything on the CPU: the un-rotated
+    // operators are already on the device
+    StateInfo before = self->braStateInfo;
+    vector<SpinQuantum> nquanta; vector<int> nstates, nmap;
+    for (int q = 0; q < nq; ++q)
+      if (kept[q] != 0) { nquanta.push_back(before.quanta[q]); nstates.push_back(kept[q]); nmap.push_back(q); }
+    StateInfo after(nquanta, nstates, nmap);
+    for (size_t k = 0; k < g.left_ops.size(); ++k) {
+      g.left_ops[k].elem->allocate(after);       // allowed mask + zeroed blocks on the retained sectors (BaseOperator.C:123-145)
+      g.left_ops[k].elem->set_built() = true;
+    }
+    self->braStateInfo = after;
+    self->braStateInfo.AllocatePreviousStateInfo();
+    *self->braStateInfo.previousStateInfo = before;
+    self->ketStateInfo = self->braStateInfo;
+    for (std::map<opTypes, boost::shared_ptr<Op_component_base> >::iterator it = self->ops.begin(); it != self->ops.end(); ++it)
+      if (!it->second->is_core()) it->second->set_core(true);
+    self->direct = false;
+    if (self->leftBlock) self->leftBlock->clear();
+    if (self->rightBlock) self->rightBlock->clear();
+  }
   int nnew = b2d_rotated_num_sectors(g.ctx);
   if (nnew != (int)self->get_stateInfo().quanta.size()) die("transform_operators: retained sector count differs from the reference's StateInfo");
-  bool check = env_on("B2D_DROPIN_CHECK");
   double worst = 0, scale = 0;
   vector<uint8_t> allowed((size_t)nnew * nnew);
-  vector<double> data;
+  vector<double> data((size_t)std::max<int64_t>(b2d_rotated_total_size(g.ctx), 1));
+  ck(b2d_rotated_download_all(g.ctx, data.data()), "b2d_rotated_download_all");   // one device pass + one copy for every operator
+  size_t off = 0;
   for (size_t k = 0; k < g.left_ops.size(); ++k) {
     SparseMatrix& op = *g.left_ops[k].elem;
     int id = g.left_ops[k].id;
-    if (op.nrows() != nnew || op.ncols() != nnew) die("transform_operators: an operator was not re-allocated by the reference");
-    int64_t n = b2d_rotated_op_size(g.ctx, id);
-    data.resize((size_t)std::max<int64_t>(n, 1));
-    ck(b2d_rotated_op_download(g.ctx, id, allowed.data(), data.data()), "b2d_rotated_op_download");
-    size_t off = 0;
+    if ((int)k != id) die("transform_operators: operator ids are not in upload order");
+    if (op.nrows() != nnew || op.ncols() != nnew) die("transform_operators: an operator was not re-allocated");
+    ck(b2d_rotated_op_download(g.ctx, id, allowed.data(), 0), "b2d_rotated_op_download(mask)");
+    size_t begin = off;
     for (int a = 0; a < nnew; ++a)
       for (int b = 0; b < nnew; ++b) {
         bool al = op.allowed(a, b);
         if (al != (allowed[(size_t)a * nnew + b] != 0)) die("transform_operators: allowed mask differs from SparseMatrix::allocate");
         if (!al) continue;
         Matrix& m = op.operator_element(a, b);
+        if (off + m.Storage() > data.size()) die("transform_operators: rotated operator size mismatch");
         if (check) for (int i = 0; i < m.Storage(); ++i) { worst = std::max(worst, fabs(m.Store()[i] - data[off + i])); scale = std::max(scale, fabs(m.Store()[i])); }
         memcpy(m.Store(), data.data() + off, sizeof(double) * m.Storage());
         off += m.Storage();
       }
-    if ((int64_t)off != n) die("transform_operators: rotated operator size mismatch");
+    if ((int64_t)(off - begin) != b2d_rotated_op_size(g.ctx, id)) die("transform_operators: rotated operator size mismatch");
   }
   g.t_rot += now_s() - t0;
   if (check) fprintf(stderr, "B2D_CHECK call=%d transform_operators ops=%d max_abs_diff=%.3e (max |O'| %.3e)\n", g.call, (int)g.left_ops.size(), worst, scale);

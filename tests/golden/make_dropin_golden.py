@@ -99,6 +99,27 @@ weights 0.5 0.5
 reorder reorder.dat
 outputlevel 0
 """)
+    # RANDOM noise as well (twodot_noise keyword -> DensityMatrix::add_twodot_noise, density.C:92-165): the hook draws the random
+    # wavefunctions with the reference's own Randomise, so both runs consume the same glibc rand() stream
+    c["c2_d2h_M50_twodotnoise"] = dict(files=c["c2_d2h_M50"]["files"], conf="""nelec 8
+spin 0
+irrep 1
+hf_occ integral
+schedule
+0 50 1.0e-16 1.0e-4
+2 50 1.0e-16 0.0
+end
+maxiter 4
+twodot
+twodot_noise 1.0e-4 0.3
+sweep_tol 1e-12
+sym d2h
+orbitals FCIDUMP
+nroots 2
+weights 0.5 0.5
+reorder reorder.dat
+outputlevel 0
+""")
     # P2 (configs[1]): H2O, no symmetry, M = 500
     c["h2o_nosym_M500"] = dict(files={"FCIDUMP": ref_file("h2o_nosym", "FCIDUMP")}, conf="""nelec 10
 spin 0
@@ -107,13 +128,15 @@ hf_occ integral
 schedule
 0 500 1.0e-16 0.0
 end
-maxiter 3
+maxiter 8
 twodot
 sweep_tol 1e-12
 orbitals FCIDUMP
 noreorder
 outputlevel 0
 """)
+    # the same molecule with M small enough that the top-M cut (not the 1e-13 weight threshold) decides the retained basis
+    c["h2o_nosym_M60"] = dict(files=c["h2o_nosym_M500"]["files"], conf=c["h2o_nosym_M500"]["conf"].replace("0 500 1.0e-16 0.0", "0 60 1.0e-16 0.0").replace("maxiter 8", "maxiter 4"))
     # P3 (configs[2]): 1-D Hubbard chain, spin-adapted, M = 1000, noise in the first sweeps
     c["hubbard_L16_M1000"] = dict(files={"FCIDUMP": hubbard_chain_fcidump(16)}, conf="""nelec 16
 spin 0
@@ -130,6 +153,7 @@ noreorder
 outputlevel 0
 warmup local_2site
 """)
+    c["hubbard_L16_M80"] = dict(files=c["hubbard_L16_M1000"]["files"], conf=c["hubbard_L16_M1000"]["conf"].replace("0 200 1.0e-16 1e-4", "0 80 1.0e-16 1e-4").replace("4 1000 1.0e-16 0.0", "4 80 1.0e-16 0.0"))
     # P5 scaled down (configs[4] shape: random-integral FCIDUMP, half filling, C1) so that the CPU reference finishes in a minute
     c["synthetic_14o_M200"] = dict(files={"FCIDUMP": synthetic_fcidump(14, 14)}, conf="""nelec 14
 spin 0

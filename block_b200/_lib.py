@@ -21,6 +21,7 @@ ctx_p = C.c_void_p
 PROTOTYPES = {
     "b2d_create": (C.c_int, [C.c_int, C.POINTER(ctx_p)]),
     "b2d_destroy": (None, [ctx_p]),
+    "b2d_reset": (C.c_int, [ctx_p]),
     "b2d_last_error": (C.c_char_p, [ctx_p]),
     "b2d_abi_version": (C.c_int, []),
     "b2d_set_option": (C.c_int, [ctx_p, C.c_char_p, C.c_double]),

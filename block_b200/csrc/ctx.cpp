@@ -167,6 +167,7 @@ struct b2d_ctx {
   int64_t rho_padded = 0;
   std::vector<std::vector<double>> evals; // per sector ascending, clamped
   std::vector<std::vector<int>> eval_row; // per sector: Jacobi row index of the i-th ascending eigenvalue
+  bool have_rho = false;                  // b2d_make_density / b2d_density_upload ran for the current block
   bool have_eig = false;
   std::vector<int> kept;                  // kept columns per sector
   std::vector<int64_t> rot_off;           // per sector offset in rot (padded ld = pad_ld(kept))
@@ -517,6 +518,38 @@ void b2d_destroy(b2d_ctx* ctx) {
   delete ctx;
 }
 
+// Forget the block description (both children, their operators, the plan, wavefunction slots, density / rotation state) but
+// keep everything that is expensive to create: streams, events, pinned memory, the cuSOLVER / NCCL handles, the operator arena
+// slabs and every scratch buffer.  A sweep creates ONE context and resets it between block iterations.
+int b2d_reset(b2d_ctx* ctx) {
+  if (!ctx) return B2D_ERR_ARG;
+  if (ctx->has_device) {
+    CU(cudaSetDevice(ctx->device));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->dsched.buf.release();
+  }
+  ctx->side[0] = Side(); ctx->side[1] = Side();
+  ctx->psi = PsiLayout();
+  ctx->planned = false;
+  ctx->terms_all.clear(); ctx->terms_mine.clear();
+  ctx->sched = Schedule();
+  ctx->dsched = DevSchedule();
+  ctx->flops_all = 0.0;
+  for (auto& sl : ctx->slabs) sl.used = 0;
+  ctx->arena_doubles = 0;
+  ctx->pend_data.clear(); ctx->pend_desc.clear();
+  ctx->nuser = 0; ctx->ndav = 0;
+  ctx->rho_off.clear(); ctx->rho_padded = 0;
+  ctx->evals.clear(); ctx->eval_row.clear(); ctx->kept.clear(); ctx->rot_off.clear();
+  ctx->have_eig = ctx->have_rot = ctx->have_rotated = false;
+  ctx->have_rho = false;
+  ctx->rotated = Side(); ctx->rotated_old.clear();
+  ctx->layouts.clear();
+  ctx->timing_valid = false;
+  ctx->err.clear();
+  return B2D_OK;
+}
+
 const char* b2d_last_error(const b2d_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 int b2d_set_option(b2d_ctx* ctx, const char* key, double value) {
@@ -769,8 +802,15 @@ int b2d_vec_reserve(b2d_ctx* ctx, int nslots) {
   NEED_DEVICE(); NEED_PLAN();
   if (nslots <= ctx->nuser) return B2D_OK;
   CU(cudaSetDevice(ctx->device));
-  DevBuf nb;
   size_t bytes = (size_t)nslots * ctx->psi.Wp * 8;
+  if (bytes <= ctx->user_pool.cap) {   // capacity left over (b2d_reset keeps the pool): only the new slots need zeroing
+    size_t have = (size_t)ctx->nuser * ctx->psi.Wp * 8;
+    CU(cudaMemsetAsync((char*)ctx->user_pool.p + have, 0, bytes - have, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->nuser = nslots;
+    return B2D_OK;
+  }
+  DevBuf nb;
   CU(nb.reserve(std::max<size_t>(bytes, 256)));
   CU(cudaMemsetAsync(nb.p, 0, std::max<size_t>(bytes, 256), ctx->stream));
   if (ctx->nuser > 0) CU(cudaMemcpyAsync(nb.p, ctx->user_pool.p, (size_t)ctx->nuser * ctx->psi.Wp * 8, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -1110,6 +1150,7 @@ int b2d_make_density(b2d_ctx* ctx, int nroots, int slot0, const double* weights)
   CU(cudaStreamSynchronize(ctx->stream));
   D.buf.release();
   ctx->have_eig = ctx->have_rot = ctx->have_rotated = false;
+  ctx->have_rho = rc == B2D_OK;
   return rc;
 }
 
@@ -1160,12 +1201,13 @@ int b2d_density_upload(b2d_ctx* ctx, const double* rho) {
   CU(launch_pack((const BlockDesc*)ctx->desc_scratch.p, (int)bd.size(), (const double*)ctx->staging.p, (double*)ctx->rho.p, ctx->stream, &ctx->launches));
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->have_eig = ctx->have_rot = ctx->have_rotated = false;
+  ctx->have_rho = true;
   return B2D_OK;
 }
 
 int b2d_diagonalise_dm(b2d_ctx* ctx, double* evals_out) {
   NEED_DEVICE(); NEED_PLAN();
-  if (!ctx->rho.p) return fail(ctx, B2D_ERR_ARG, "no density matrix yet");
+  if (!ctx->rho.p || !ctx->have_rho) return fail(ctx, B2D_ERR_ARG, "no density matrix yet");
   CU(cudaSetDevice(ctx->device));
   const Side& L = ctx->side[0];
   int64_t nev = 0;
@@ -1656,7 +1698,7 @@ int b2d_tensor_multiply_one_host(b2d_ctx* ctx, int side, int op_id, int transpos
 int b2d_add_wavefunction_density(b2d_ctx* ctx, const int32_t* dq, const double* flat, double weight) {
   NEED_DEVICE(); NEED_PLAN();
   if (!dq || !flat) return fail(ctx, B2D_ERR_ARG, "b2d_add_wavefunction_density: bad arguments");
-  if (!ctx->rho.p) return fail(ctx, B2D_ERR_ARG, "b2d_add_wavefunction_density: call b2d_make_density first");
+  if (!ctx->rho.p || !ctx->have_rho) return fail(ctx, B2D_ERR_ARG, "b2d_add_wavefunction_density: call b2d_make_density first");
   CU(cudaSetDevice(ctx->device));
   const Side& L = ctx->side[0];
   int q[3] = {dq[0], dq[1], dq[2]};
@@ -1704,7 +1746,7 @@ int b2d_add_wavefunction_density(b2d_ctx* ctx, const int32_t* dq, const double* 
 
 int b2d_add_onedot_noise(b2d_ctx* ctx, int nroots, int slot0, double noise) {
   NEED_DEVICE(); NEED_PLAN();
-  if (!ctx->rho.p) return fail(ctx, B2D_ERR_ARG, "b2d_add_onedot_noise: call b2d_make_density first");
+  if (!ctx->rho.p || !ctx->have_rho) return fail(ctx, B2D_ERR_ARG, "b2d_add_onedot_noise: call b2d_make_density first");
   for (int i = 0; i < nroots; ++i) CHECK_SLOT(slot0 + i);
   if (!(noise > 1e-15) || nroots < 1) return B2D_OK;                          // NUMERICAL_ZERO, density.C:40
   if (ctx->hubbard) return B2D_OK;                                             // reference quirk: rho_n is never added for HUBBARD (density.C:358-392)

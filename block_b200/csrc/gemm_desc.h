@@ -2,7 +2,9 @@
 #pragma once
 #include <stdint.h>
 
-#define B2D_NUM_TILE_CLASSES 9   // {128,64,32} x {128,64,32}: class = 3 * (row size index) + (column size index)
+#define B2D_NUM_TILE_CLASSES 10  // {128,64,32} x {128,64,32}: class = 3 * (row size index) + (column size index); class 9 = tiny
+#define B2D_TINY_CLASS 9         // output blocks of at most B2D_TINY_DIM x B2D_TINY_DIM: one WARP per block, lanes split K, shuffle reduction
+#define B2D_TINY_DIM 8
 #define B2D_BASE_ABS 0    // pointer field is an absolute device address (operator arenas)
 #define B2D_BASE_SRC 1    // offset (doubles) into the source wavefunction
 #define B2D_BASE_WORK 2   // offset into the T workspace
@@ -16,8 +18,8 @@
 #define B2D_HD
 #endif
 
-B2D_HD inline int b2d_tile_m(int cls) { return 128 >> (cls / 3); }
-B2D_HD inline int b2d_tile_n(int cls) { return 128 >> (cls % 3); }
+B2D_HD inline int b2d_tile_m(int cls) { return cls == B2D_TINY_CLASS ? B2D_TINY_DIM : 128 >> (cls / 3); }
+B2D_HD inline int b2d_tile_n(int cls) { return cls == B2D_TINY_CLASS ? B2D_TINY_DIM : 128 >> (cls % 3); }
 
 // One K-segment of a grouped contraction:  C += alpha * op(A) * op(B),  op(A) is m x k, op(B) is k x n.
 //   a_trans  = 0: A stored m x k row-major (K contiguous);  1: stored k x m row-major (M contiguous)

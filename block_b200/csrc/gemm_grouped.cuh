@@ -285,4 +285,73 @@ __global__ void __launch_bounds__(TileCfg<BM, BN>::THREADS)
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Tiny sectors: output blocks of at most 8 x 8 (the one- to eight-state quantum-number sectors at the edges of the
+// particle-number / spin distribution).  A 32 x 32 DMMA tile would be > 94 % padding and pay a shared-memory pipeline per
+// segment; here ONE WARP owns the block: lanes split the K index of every segment (coalesced along K for K-contiguous
+// operands), accumulate the full m x n product in registers with DFMA, and the 32 partial sums of each output element are
+// combined by a fixed-order butterfly of warp shuffles (deterministic).  Four warps per CTA, one block each.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int TINY_WARPS = 4;
+
+__global__ void __launch_bounds__(TINY_WARPS * 32)
+    tiny_gemm_kernel(const GSeg* __restrict__ segs, const GGroup* __restrict__ groups, const GTile* __restrict__ tiles, int ntiles, Bases bases) {
+  const int w = blockIdx.x * TINY_WARPS + (threadIdx.x >> 5);
+  if (bases.trace && threadIdx.x == 0) {
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    atomicMin(bases.trace, t0);
+  }
+  if (w < ntiles) {
+    const int lane = threadIdx.x & 31;
+    const GGroup grp = groups[tiles[w].group];
+    const int m = grp.m, n = grp.n;
+    double acc[B2D_TINY_DIM][B2D_TINY_DIM];
+#pragma unroll
+    for (int i = 0; i < B2D_TINY_DIM; ++i)
+#pragma unroll
+      for (int j = 0; j < B2D_TINY_DIM; ++j) acc[i][j] = 0.0;
+    for (int s = grp.seg_begin; s < grp.seg_end; ++s) {
+      const GSeg sg = segs[s];
+      const double* A = sg.a_base == B2D_BASE_ABS ? reinterpret_cast<const double*>(sg.a) : bases.p[sg.a_base] + sg.a;
+      const double* B = sg.b_base == B2D_BASE_ABS ? reinterpret_cast<const double*>(sg.b) : bases.p[sg.b_base] + sg.b;
+      const int64_t a_rs = sg.a_trans ? 1 : sg.lda, a_ks = sg.a_trans ? sg.lda : 1;     // op(A)(i, k) = A[i * a_rs + k * a_ks]
+      const int64_t b_ns = sg.b_kmajor ? sg.ldb : 1, b_ks = sg.b_kmajor ? 1 : sg.ldb;   // op(B)(k, j) = B[j * b_ns + k * b_ks]
+      for (int k = lane; k < sg.k; k += 32) {
+        double a[B2D_TINY_DIM], b[B2D_TINY_DIM];
+#pragma unroll
+        for (int i = 0; i < B2D_TINY_DIM; ++i) a[i] = i < m ? sg.alpha * A[i * a_rs + k * a_ks] : 0.0;
+#pragma unroll
+        for (int j = 0; j < B2D_TINY_DIM; ++j) b[j] = j < n ? B[j * b_ns + k * b_ks] : 0.0;
+#pragma unroll
+        for (int i = 0; i < B2D_TINY_DIM; ++i)
+          if (i < m) {
+#pragma unroll
+            for (int j = 0; j < B2D_TINY_DIM; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+          }
+      }
+    }
+    double* C = bases.p[grp.c_base] + grp.c;
+#pragma unroll
+    for (int i = 0; i < B2D_TINY_DIM; ++i)
+#pragma unroll
+      for (int j = 0; j < B2D_TINY_DIM; ++j) {
+        if (i < m && j < n) {   // warp-uniform
+          double v = acc[i][j];
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+          if (lane == ((i * B2D_TINY_DIM + j) & 31)) {
+            double* dst = C + (int64_t)i * grp.ldc + j;
+            *dst = grp.accumulate ? *dst + v : v;
+          }
+        }
+      }
+  }
+  if (bases.trace && threadIdx.x == 0) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    atomicMax(bases.trace + 1, t1);
+  }
+}
+
 }  // namespace b2d

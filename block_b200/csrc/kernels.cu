@@ -60,7 +60,8 @@ cudaError_t launch_gemm_class(const DevBatch& b, int cls, double* const* bases, 
     case 5: launch_one<64, 32>(b, cls, B, stream); break;
     case 6: launch_one<32, 128>(b, cls, B, stream); break;
     case 7: launch_one<32, 64>(b, cls, B, stream); break;
-    default: launch_one<32, 32>(b, cls, B, stream); break;
+    case 8: launch_one<32, 32>(b, cls, B, stream); break;
+    default: tiny_gemm_kernel<<<(b.ntiles[cls] + TINY_WARPS - 1) / TINY_WARPS, TINY_WARPS * 32, 0, stream>>>(b.segs, b.groups, b.tiles[cls], b.ntiles[cls], B); break;
   }
   B2D_LAUNCH_CHECK();
   return cudaSuccess;
@@ -206,8 +207,51 @@ __global__ void __launch_bounds__(L1_THREADS) rotate_kernel(int n_in, int n_out,
   }
 }
 
+// Square in-place rotation with the vector count as a template parameter: every thread owns TWO consecutive elements of all N
+// vectors (16-byte loads and stores), the N x N coefficients sit in shared memory and each broadcast read feeds two DFMAs.
+// HBM bound: N reads + N writes of the vector per launch.
+template <int N>
+__global__ void __launch_bounds__(L1_THREADS) rotate_square_kernel(VecList x, const double* __restrict__ alpha, int lda, int64_t n2) {
+  __shared__ double a[N * N];        // a[j * N + i] = alpha(i, j): the coefficients of output j are contiguous
+  __shared__ double2* ptr[N];
+  for (int i = threadIdx.x; i < N * N; i += blockDim.x) a[(i % N) * N + (i / N)] = alpha[(i / N) * lda + (i % N)];
+  if (threadIdx.x < N) ptr[threadIdx.x] = reinterpret_cast<double2*>(x.p[threadIdx.x]);
+  __syncthreads();
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n2; e += (int64_t)gridDim.x * blockDim.x) {
+    double2 v[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) v[i] = ptr[i][e];
+#pragma unroll 1
+    for (int j = 0; j < N; ++j) {     // not unrolled: N x N x 2 DFMAs would not fit an unrolled body for N = 32
+      const double* aj = a + j * N;
+      double2 s = make_double2(0.0, 0.0);
+#pragma unroll
+      for (int i = 0; i < N; ++i) { const double c = aj[i]; s.x = fma(c, v[i].x, s.x); s.y = fma(c, v[i].y, s.y); }
+      ptr[j][e] = s;
+    }
+  }
+}
+
+template <int N>
+static void launch_rotate_square(const VecList& x, const double* alpha, int lda, int64_t n, cudaStream_t s) {
+  rotate_square_kernel<N><<<l1_grid(n / 2), L1_THREADS, 0, s>>>(x, alpha, lda, n / 2);
+}
+
 cudaError_t launch_rotate(int n_in, int n_out, const VecList& x, const double* alpha, int lda, int64_t n, cudaStream_t s, int64_t* launches) {
-  rotate_kernel<<<l1_grid(n), L1_THREADS, 0, s>>>(n_in, n_out, x, alpha, lda, n);
+  bool aligned = (n % 2) == 0;
+  for (int i = 0; i < n_in && aligned; ++i) aligned = (reinterpret_cast<uintptr_t>(x.p[i]) % 16) == 0;
+  if (n_in == n_out && aligned && n_in >= 1 && n_in <= L1_MAX_VECS) {
+    switch (n_in) {
+#define B2D_ROT(N) case N: launch_rotate_square<N>(x, alpha, lda, n, s); break;
+      B2D_ROT(1) B2D_ROT(2) B2D_ROT(3) B2D_ROT(4) B2D_ROT(5) B2D_ROT(6) B2D_ROT(7) B2D_ROT(8) B2D_ROT(9) B2D_ROT(10) B2D_ROT(11)
+      B2D_ROT(12) B2D_ROT(13) B2D_ROT(14) B2D_ROT(15) B2D_ROT(16) B2D_ROT(17) B2D_ROT(18) B2D_ROT(19) B2D_ROT(20) B2D_ROT(21)
+      B2D_ROT(22) B2D_ROT(23) B2D_ROT(24) B2D_ROT(25) B2D_ROT(26) B2D_ROT(27) B2D_ROT(28) B2D_ROT(29) B2D_ROT(30) B2D_ROT(31)
+      B2D_ROT(32)
+#undef B2D_ROT
+    }
+  } else {
+    rotate_kernel<<<l1_grid(n), L1_THREADS, 0, s>>>(n_in, n_out, x, alpha, lda, n);
+  }
   B2D_LAUNCH_CHECK();
   return cudaSuccess;
 }

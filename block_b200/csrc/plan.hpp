@@ -292,9 +292,20 @@ inline void make_tiles(GemmBatch& b, int forced_class) {
     int kiters = 0;
     for (int s = G.seg_begin; s < G.seg_end; ++s) { ktot += b.segs[s].k; kiters += (b.segs[s].k + 15) / 16; }
     G.kiters = kiters;
-    // forced_class: -1 auto; 0/1/2 square 128/64/32; 10*(r+1)+c forces (128>>r) x (128>>c) tiles (experiments)
-    make_bands(G.m, forced_class >= 10 ? forced_class / 10 - 1 : forced_class, mb);
-    make_bands(G.n, forced_class >= 10 ? forced_class % 10 : forced_class, nb);
+    // tiny sectors (both dimensions <= B2D_TINY_DIM): one warp per block, no shared-memory pipeline (forced_class 3 = only these)
+    if ((forced_class == -1 || forced_class == 3) && G.m <= B2D_TINY_DIM && G.n <= B2D_TINY_DIM) {
+      b.class_flops[B2D_TINY_CLASS] += 2.0 * G.m * G.n * (double)ktot;
+      b.class_padded[B2D_TINY_CLASS] += 2.0 * G.m * G.n * (double)ktot;   // DFMA path: no padded tensor-pipe work is issued
+      GTile t;
+      t.group = (int)g; t.m0 = 0; t.n0 = 0;
+      t.cost = (int)std::min<int64_t>(ktot + 8 * (G.seg_end - G.seg_begin), 0x7fffffff);
+      b.tiles[B2D_TINY_CLASS].push_back(t);
+      continue;
+    }
+    // forced_class: -1 auto; 3 tiny where eligible, auto elsewhere; 0/1/2 square 128/64/32; 10*(r+1)+c forces (128>>r) x (128>>c) tiles (experiments)
+    const int fc = forced_class == 3 ? -1 : forced_class;
+    make_bands(G.m, fc >= 10 ? fc / 10 - 1 : fc, mb);
+    make_bands(G.n, fc >= 10 ? fc % 10 : fc, nb);
     for (const auto& bm : mb)
       for (const auto& bn : nb) {
         const int c = 3 * bm.second + bn.second;

@@ -68,6 +68,15 @@ class SpinBlock:
         self.device = device
         for k, v in (options or {}).items():
             self._ck(self.lib.b2d_set_option(self._ctx, k.encode(), float(v)))
+        self._describe(left, right, psi_dq, core_energy, hubbard, norbs, rank, nranks)
+
+    def reset(self, left: BlockSpec, right: BlockSpec, psi_dq, core_energy=0.0, hubbard=False, norbs=None, rank=0, nranks=1):
+        """b2d_reset + a new block description on the SAME context (streams, arena slabs and scratch buffers are kept): what a
+        sweep does between block iterations."""
+        self._ck(self.lib.b2d_reset(self._ctx))
+        self._describe(left, right, psi_dq, core_energy, hubbard, norbs, rank, nranks)
+
+    def _describe(self, left, right, psi_dq, core_energy, hubbard, norbs, rank, nranks):
         self.left, self.right = left, right
         self.op_ids = [[], []]
         for side, blk in enumerate((left, right)):
@@ -353,10 +362,10 @@ class SpinBlock:
 
     def sigma_profile(self, src_slot, dst_slot):
         """One multiplyH with events around every contraction launch: dict[(step, tile_class)] -> (ms, useful flops,
-        issued flops, launches)."""
-        out = np.zeros(72)
+        issued flops, launches); tile class 9 = the warp-per-block kernel of the tiny (<= 8 x 8) sectors."""
+        out = np.zeros(80)
         self._ck(self.lib.b2d_sigma_profile(self._ctx, src_slot, dst_slot, _p(out, _lib.c_f64p)))
-        return {(st, c): tuple(out[(st * 9 + c) * 4:(st * 9 + c) * 4 + 4]) for st in range(2) for c in range(9)}
+        return {(st, c): tuple(out[(st * 10 + c) * 4:(st * 10 + c) * 4 + 4]) for st in range(2) for c in range(10)}
 
     def kernel_launches(self):
         return int(self.lib.b2d_kernel_launches(self._ctx))

@@ -51,11 +51,16 @@ enum {
  * the CPU tests; every compute call fails with B2D_ERR_NO_DEVICE). */
 int b2d_create(int device, b2d_ctx** out);
 void b2d_destroy(b2d_ctx* ctx);
+/* Forget the block description (children, operators, plan, wavefunction slots, density / rotation state) and keep what is
+ * expensive to create (streams, pinned memory, library handles, operator arena slabs, scratch buffers): a sweep creates one
+ * context and resets it between block iterations (the reference builds a new `big` SpinBlock per block iteration, sweep.C:182). */
+int b2d_reset(b2d_ctx* ctx);
 const char* b2d_last_error(const b2d_ctx* ctx);   /* ctx may be NULL: last error of a failed b2d_create */
 int b2d_abi_version(void);
 
 /* Tuning knobs (all optional): "workspace_mb" (T workspace for the two-step contraction), "max_davidson_iter",
- * "tile_class" (debug: -1 auto, 0/1/2 = square 128/64/32 tiles everywhere), "sync_debug", "phase_timing". */
+ * "tile_class" (debug: -1 auto, 0/1/2 = square 128/64/32 DMMA tiles everywhere, 3 = auto with the tiny-sector warp kernel,
+ * which auto already uses), "sync_debug", "phase_timing". */
 int b2d_set_option(b2d_ctx* ctx, const char* key, double value);
 
 /* ---- block description: replaces the host-side SpinBlock / StateInfo / Op_component objects ---------------- */
@@ -240,9 +245,10 @@ int b2d_allreduce_slot(b2d_ctx* ctx, int slot);
  * the context's stream: out[0] = total, out[1] = step-1 kernels, out[2] = step-2 kernels, out[3] = collective. */
 int b2d_last_timing(b2d_ctx* ctx, double* out, int n);
 /* One multiplyH (this rank's terms, no collective) with CUDA events around every launch of the grouped contraction
- * kernel.  out[(step * 9 + tile_class) * 4 + {0,1,2,3}] = {summed kernel ms, useful flops (2mnk) executed, flops the
+ * kernel.  out[(step * 10 + tile_class) * 4 + {0,1,2,3}] = {summed kernel ms, useful flops (2mnk) executed, flops the
  * tiles issue including ragged-edge padding, number of launches}; step 0 = T = A_L psi (operatorfunctions.C:512-516),
- * step 1 = sigma += F T A_R^T (:517-531); tile class = 3 * r + c for a (128 >> r) x (128 >> c) tile.  72 doubles. */
+ * step 1 = sigma += F T A_R^T (:517-531); tile class = 3 * r + c for a (128 >> r) x (128 >> c) DMMA tile, class 9 = the
+ * warp-per-block DFMA + shuffle-reduction kernel of the tiny (<= 8 x 8) sectors.  80 doubles. */
 int b2d_sigma_profile(b2d_ctx* ctx, int src_slot, int dst_slot, double* out);
 int64_t b2d_kernel_launches(const b2d_ctx* ctx);     /* kernels launched by this context so far */
 int b2d_sync(b2d_ctx* ctx);

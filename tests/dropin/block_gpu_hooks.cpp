@@ -74,7 +74,8 @@ bool env_on(const char* k) { const char* v = getenv(k); return v && *v && strcmp
 struct OpRef { SparseMatrix* elem; int id; };
 
 struct Gpu {
-  b2d_ctx* ctx = 0;
+  b2d_ctx* ctx = 0;              // created once, b2d_reset between block iterations
+  bool active = false;           // the context currently describes a big block
   const SpinBlock* left = 0;     // children of the big block this context was built for (RenormaliseFrom works on a COPY
   const SpinBlock* right = 0;    // of `big`, renormalise.C:79 `newbig = big`, which shares the children)
   vector<int> lsites, rsites;
@@ -88,6 +89,8 @@ struct Gpu {
   double t_build = 0;            // inside the reference's own Op::build for direct-mode virtual operators (host side)
   double t_upload = 0, t_diag = 0, t_dav = 0, t_rho = 0, t_eig = 0, t_rot = 0, dav_dev_ms = 0, flops = 0;
   int nmult = 0, call = -1;
+  long long launch0 = 0;         // kernel-launch counter of the (reused) context when this block iteration began
+  bool dirty = false;            // statistics of this context not written yet
   // check mode: CPU results kept between hooks
   SparseMatrix* chk_transform = 0;
   vector<DiagonalMatrix> chk_eigs;
@@ -120,20 +123,23 @@ void collect(SparseMatrix& w, const vector<double>& in) {     // Wavefunction::C
   if (off != in.size()) die("collect: size mismatch");
 }
 
+void write_stats();
 void release() {
-  if (g.ctx) b2d_destroy(g.ctx);
-  g.ctx = 0; g.left = g.right = 0; g.left_ops.clear(); g.nslots = 0; g.rho_on_device = g.rot_on_device = false;
+  if (g.ctx && g.dirty) write_stats();   // a context that is replaced before transform_operators (one-dot, dot on the environment side)
+  if (g.ctx && b2d_reset(g.ctx)) die(string("b2d_reset: ") + b2d_last_error(g.ctx));   // one context for the whole run
+  g.dirty = false;
+  g.active = false; g.left = g.right = 0; g.left_ops.clear(); g.nslots = 0; g.rho_on_device = g.rot_on_device = false;
 }
 
 void write_stats() {
   const char* path = getenv("B2D_DROPIN_STATS");
-  if (!path || !g.ctx) return;
+  if (!path || !g.ctx || !g.active) return;
   FILE* f = fopen(path, "a");
   if (!f) return;
   fprintf(f, "call=%d lsites=%d rsites=%d W=%lld sigma_flops=%.6e n_multiply=%d host_op_build_s=%.6f upload_s=%.6f diag_s=%.6f davidson_s=%.6f davidson_dev_ms=%.3f "
              "density_s=%.6f eig_s=%.6f rotate_s=%.6f launches=%lld\n",
           g.call, (int)g.lsites.size(), (int)g.rsites.size(), (long long)g.W, g.flops, g.nmult, g.t_build, g.t_upload, g.t_diag, g.t_dav, g.dav_dev_ms, g.t_rho,
-          g.t_eig, g.t_rot, (long long)b2d_kernel_launches(g.ctx));
+          g.t_eig, g.t_rot, (long long)(b2d_kernel_launches(g.ctx) - g.launch0));
   fclose(f);
 }
 
@@ -187,7 +193,7 @@ void upload_block(int side, SpinBlock& b, vector<OpRef>* keep) {
 void ensure_ctx(const SpinBlock& big_c) {
   SpinBlock& big = const_cast<SpinBlock&>(big_c);
   if (!big.get_leftBlock() || !big.get_rightBlock()) die("big block without children");
-  if (g.ctx && g.left == big.get_leftBlock() && g.right == big.get_rightBlock() && g.lsites == big.get_leftBlock()->get_sites() &&
+  if (g.ctx && g.active && g.left == big.get_leftBlock() && g.right == big.get_rightBlock() && g.lsites == big.get_leftBlock()->get_sites() &&
       g.rsites == big.get_rightBlock()->get_sites())
     return;
   release();
@@ -196,7 +202,9 @@ void ensure_ctx(const SpinBlock& big_c) {
   double t0 = now_s();
   g.t_build = 0;
   int dev = getenv("B2D_DEVICE") ? atoi(getenv("B2D_DEVICE")) : 0;
-  if (b2d_create(dev, &g.ctx)) die(string("b2d_create: ") + b2d_last_error(0));
+  if (!g.ctx && b2d_create(dev, &g.ctx)) die(string("b2d_create: ") + b2d_last_error(0));
+  g.active = true;
+  g.launch0 = b2d_kernel_launches(g.ctx);
   if (getenv("B2D_DROPIN_WORKSPACE_MB")) ck(b2d_set_option(g.ctx, "workspace_mb", atof(getenv("B2D_DROPIN_WORKSPACE_MB"))), "b2d_set_option");
   if (getenv("B2D_DROPIN_OPTIONS")) {   // "key=value,key=value" -> b2d_set_option
     string all = getenv("B2D_DROPIN_OPTIONS");
@@ -220,6 +228,7 @@ void ensure_ctx(const SpinBlock& big_c) {
   g.flops = b2d_sigma_flops(g.ctx, 1);
   g.t_upload = now_s() - t0 - g.t_build;
   g.t_diag = g.t_dav = g.t_rho = g.t_eig = g.t_rot = g.dav_dev_ms = 0; g.nmult = 0;
+  g.dirty = true;
   ++g.call;
 }
 
@@ -413,7 +422,7 @@ void wrap_makedm(DensityMatrix* self, const vector<Wavefunction>& ws, SpinBlock&
 void real_diagdm(SparseMatrix& traced, SparseMatrix& transform, vector<DiagonalMatrix>& eigs) asm("__real_" SYM_diagonalise_dm);
 void wrap_diagdm(SparseMatrix& traced, SparseMatrix& transform, vector<DiagonalMatrix>& eigs) asm("__wrap_" SYM_diagonalise_dm);
 void wrap_diagdm(SparseMatrix& traced, SparseMatrix& transform, vector<DiagonalMatrix>& eigs) {
-  if (!g.ctx || !g.rho_on_device) die("diagonalise_dm outside a GPU block iteration (module not covered by the GPU path)");
+  if (!g.ctx || !g.active || !g.rho_on_device) die("diagonalise_dm outside a GPU block iteration (module not covered by the GPU path)");
   bool check = env_on("B2D_DROPIN_CHECK");
   if (check) {
     g.chk_vecs = static_cast<DensityMatrix&>(transform);
@@ -458,7 +467,7 @@ double wrap_assign(vector<Matrix>& rot, vector<DiagonalMatrix>& eigs, SparseMatr
                    int nbydm, int nbyq, int lsize, int rsize) asm("__wrap_" SYM_assign_matrix_by_dm);
 double wrap_assign(vector<Matrix>& rot, vector<DiagonalMatrix>& eigs, SparseMatrix& transform, vector<std::pair<int, int> >& inorder, vector<vector<int> >& byq,
                    int nbydm, int nbyq, int lsize, int rsize) {
-  if (!g.ctx || !g.rho_on_device) die("assign_matrix_by_dm outside a GPU block iteration (module not covered by the GPU path)");
+  if (!g.ctx || !g.active || !g.rho_on_device) die("assign_matrix_by_dm outside a GPU block iteration (module not covered by the GPU path)");
   if (nbyq != 0) die("keptqstates != 0: not covered (sweep_params.C:80 always passes 0)");
   if (dmrginp.do_pdm()) die("do_pdm keeps zero-weight states (rotationmat.C:161): not covered by the GPU path");
   double t0 = now_s();
@@ -510,7 +519,7 @@ void wrap_rotate(const Matrix& a, const Matrix& b, const Matrix& c, Matrix& d) {
 void real_transform(SpinBlock* self, vector<Matrix>& rot) asm("__real_" SYM_transform_operators);
 void wrap_transform(SpinBlock* self, vector<Matrix>& rot) asm("__wrap_" SYM_transform_operators);
 void wrap_transform(SpinBlock* self, vector<Matrix>& rot) {
-  if (!g.ctx || g.lsites != self->get_sites())
+  if (!g.ctx || !g.active || g.lsites != self->get_sites())
     die("transform_operators on a block that was not the left child of the last GPU block iteration (warm-up / one-dot tail: not covered)");
   double t0 = now_s();
   int nq = (int)rot.size();
@@ -584,6 +593,7 @@ void wrap_transform(SpinBlock* self, vector<Matrix>& rot) {
   g.t_rot += now_s() - t0;
   if (check) fprintf(stderr, "B2D_CHECK call=%d transform_operators ops=%d max_abs_diff=%.3e (max |O'| %.3e)\n", g.call, (int)g.left_ops.size(), worst, scale);
   write_stats();
+  g.dirty = false;
   release();
 }
 
@@ -603,7 +613,9 @@ void wrap_RenormaliseFrom(SpinBlock* self, vector<double>& energies, vector<doub
                           const double noise, const double additional_noise, const bool& onedot, SpinBlock& System, SpinBlock& sysDot,
                           SpinBlock& environment, const bool& dot_with_sys, const bool& warmUp, int sweepiter, int currentRoot,
                           vector<Wavefunction>& lowerStates, DensityMatrix* rdm) {
-  if (onedot && !dot_with_sys) die("one-dot step with the dot on the environment side (renormalise.C:64-79, onedot_shufflesysdot): not covered; use `twodot`");
+  // one-dot step with the dot on the environment side (renormalise.C:64-79): the solve runs on system x (dot+environment), the
+  // reference reshuffles the solutions on the host (onedot_shufflesysdot) and the density matrix / rotation then run on
+  // (system+dot) x environment: two device contexts in one call, created by whichever hook first sees each big block
   if (dmrginp.solve_method() != DAVIDSON) die("solver other than Davidson: not covered");
   real_RenormaliseFrom(self, energies, spins, error, rotateMatrix, keptstates, keptqstates, tol, big, gw, noise, additional_noise, onedot, System, sysDot,
                        environment, dot_with_sys, warmUp, sweepiter, currentRoot, lowerStates, rdm);

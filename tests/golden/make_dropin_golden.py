@@ -120,6 +120,27 @@ weights 0.5 0.5
 reorder reorder.dat
 outputlevel 0
 """)
+    # the reference's default algorithm: two-dot sweeps, then one-dot sweeps (twodot_to_onedot).  In the one-dot sweeps the dot
+    # alternates between the system and the environment side; on the environment side RenormaliseFrom solves on
+    # system x (dot+environment) and reshuffles the solution to (system+dot) x environment before the density matrix (renormalise.C:64-79)
+    c["c2_d2h_M50_onedot_tail"] = dict(files=c["c2_d2h_M50"]["files"], conf="""nelec 8
+spin 0
+irrep 1
+hf_occ integral
+schedule
+0 50 1.0e-16 1.0e-4
+2 50 1.0e-16 0.0
+end
+maxiter 6
+twodot_to_onedot 3
+sweep_tol 1e-12
+sym d2h
+orbitals FCIDUMP
+nroots 2
+weights 0.5 0.5
+reorder reorder.dat
+outputlevel 0
+""")
     # P2 (configs[1]): H2O, no symmetry, M = 500
     c["h2o_nosym_M500"] = dict(files={"FCIDUMP": ref_file("h2o_nosym", "FCIDUMP")}, conf="""nelec 10
 spin 0

@@ -44,6 +44,38 @@ def test_sigma_matches_reference(gpu_block):
         assert rel(sb.multiplyH(rec["psi%d" % i]), rec["sigma%d" % i]) < 1e-10
 
 
+def test_context_reuse_across_block_iterations(golden):
+    """b2d_reset: one context serves a sequence of different big blocks (what the drop-in sweep does); results must be those of a
+    fresh context, bit for bit."""
+    import glob
+    import os
+    rec, big = golden
+    others = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*_site*.npz")))
+    other = dumpio.read_records(others[0])
+    sb = hotpath.spinblock_from_record(other, device=0)       # start on ANOTHER block, run something, then reset onto `rec`
+    try:
+        sb.multiplyH(other["rpsi"])
+        nro = int(other["meta"][4])
+        sb.RenormaliseFrom([other["guess%d" % i] for i in range(nro)], other["weights"], float(other["dav_tol"][0]), int(other["meta"][5]))
+        sb.transform_operators()
+        L, R = hotpath.block_spec_from_record(rec, "L."), hotpath.block_spec_from_record(rec, "R.")
+        norbs = len(rec["spin_orbs_symmetry"]) // 2
+        sb.reset(L, R, tuple(int(x) for x in rec["psi_dq"]), core_energy=float(rec["meta_f"][3]), hubbard=int(rec["meta"][7]) == hotpath.HUBBARD, norbs=norbs)
+        v = sb.multiplyH(rec["rpsi"])
+        assert rel(v, rec["rsigma"]) < 1e-13
+        fresh = hotpath.spinblock_from_record(rec, device=0)
+        try:
+            assert np.array_equal(v, fresh.multiplyH(rec["rpsi"]))
+            nroots = int(rec["meta"][4])
+            args = ([rec["guess%d" % i] for i in range(nroots)], rec["weights"], float(rec["dav_tol"][0]), int(rec["meta"][5]))
+            a, b = sb.RenormaliseFrom(*args, noise=float(rec["rdm.args"][0])), fresh.RenormaliseFrom(*args, noise=float(rec["rdm.args"][0]))
+            assert np.array_equal(a["energies"], b["energies"]) and list(a["kept"]) == list(b["kept"]) and a["error"] == b["error"]
+        finally:
+            fresh.close()
+    finally:
+        sb.close()
+
+
 def test_sigma_accumulates_like_reference(gpu_block):
     rec, big, sb = gpu_block
     v0 = np.cos(np.arange(sb.size))
@@ -51,7 +83,7 @@ def test_sigma_accumulates_like_reference(gpu_block):
     assert rel(v - v0, rec["rsigma"]) < 1e-10
 
 
-@pytest.mark.parametrize("cls", [0, 1, 2])
+@pytest.mark.parametrize("cls", [0, 1, 2, 3])
 def test_sigma_every_tile_class(golden, cls):
     rec, big = golden
     sb = hotpath.spinblock_from_record(rec, device=0, options={"tile_class": cls})

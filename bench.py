@@ -361,8 +361,8 @@ def sweep_leg(a):
             out[tag]["kernel_launches"] = int(tot.get("launches", 0))
     if len(energies) == 2 and len(energies["reference_cpu"]) == len(energies["gpu_dropin"]):
         out["max_abs_dE_per_sweep"] = max(abs(x - y) for x, y in zip(energies["reference_cpu"], energies["gpu_dropin"]))
-        golden = [float(m.group(4)) for m in pat.finditer(z[name + "/sweeps"].tobytes().decode())]
-        if len(golden) == len(energies["gpu_dropin"]):
+        golden = [float(m.group(4)) for m in pat.finditer(z[name + "/sweeps"].tobytes().decode())] if name + "/sweeps" in z.files else []
+        if golden and len(golden) == len(energies["gpu_dropin"]):
             out["max_abs_dE_vs_golden"] = max(abs(x - y) for x, y in zip(golden, energies["gpu_dropin"]))
     return out
 
@@ -522,6 +522,12 @@ def run_ours(a):
                 "parity": parity,
                 "hbm_peak_gbs": peaks.get("hbm_gbs")}
     if line is not None and world == 1 and not a.no_block_iteration:
+        # a first pass with ONE Davidson iteration loads every kernel of the leg (CUDA loads modules lazily: the first launch of
+        # a kernel costs tens of milliseconds) and sizes the scratch buffers; the second pass is the one reported
+        iters = a.davidson_iters
+        a.davidson_iters = 1
+        block_iteration_leg(sb, a, psi, ms_step)
+        a.davidson_iters = iters
         line["block_iteration"] = block_iteration_leg(sb, a, psi, ms_step)
         # HBM-bound phases (north_star: achieved HBM GB/s for the bandwidth-bound phases): the Davidson level-1 kernels alone
         hbm = peaks.get("hbm_gbs") or 6534.5

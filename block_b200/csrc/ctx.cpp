@@ -144,7 +144,8 @@ struct b2d_ctx {
 
   // operator uploads are batched: host images and block descriptors of the operators added since the last flush
   // (one H2D copy + one pack launch per flush instead of three synchronisations per operator)
-  std::vector<double> pend_data;
+  double* pend_pinned = nullptr;          // pinned host staging (cudaMallocHost): the H2D copy of a flush is a true DMA
+  size_t pend_cap = 0, pend_used = 0;     // doubles
   std::vector<BlockDesc> pend_desc;
 
   // scratch
@@ -263,17 +264,37 @@ int upload_desc(b2d_ctx* ctx, DevBuf& buf, const void* host, size_t bytes) {
 
 // pack every pending operator image into its padded device blocks (dev_off is absolute: base pointer 0)
 int flush_pending_ops(b2d_ctx* ctx) {
-  if (ctx->pend_desc.empty()) { ctx->pend_data.clear(); return B2D_OK; }
+  if (ctx->pend_desc.empty()) { ctx->pend_used = 0; return B2D_OK; }
   CU(cudaSetDevice(ctx->device));
-  CU(ctx->staging.reserve(ctx->pend_data.size() * 8));
-  CU(cudaMemcpyAsync(ctx->staging.p, ctx->pend_data.data(), ctx->pend_data.size() * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx->staging.reserve(ctx->pend_used * 8));
+  CU(cudaMemcpyAsync(ctx->staging.p, ctx->pend_pinned, ctx->pend_used * 8, cudaMemcpyHostToDevice, ctx->stream));
   int rc = upload_desc(ctx, ctx->desc_scratch, ctx->pend_desc.data(), ctx->pend_desc.size() * sizeof(BlockDesc));
   if (rc) return rc;
   CU(launch_pack((const BlockDesc*)ctx->desc_scratch.p, (int)ctx->pend_desc.size(), (const double*)ctx->staging.p, (double*)nullptr, ctx->stream, &ctx->launches));
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->pend_desc.clear();
-  ctx->pend_data.clear();
+  ctx->pend_used = 0;
   return B2D_OK;
+}
+
+// room for n more doubles in the pinned staging buffer (flushing what is pending first if necessary); nullptr on failure
+double* pending_room(b2d_ctx* ctx, size_t n, int* rc) {
+  *rc = B2D_OK;
+  const size_t chunk = ((size_t)64 << 20) / 8;
+  if (ctx->pend_used + n > ctx->pend_cap) {
+    *rc = flush_pending_ops(ctx);
+    if (*rc) return nullptr;
+    if (n > ctx->pend_cap) {
+      if (ctx->pend_pinned) cudaFreeHost(ctx->pend_pinned);
+      ctx->pend_pinned = nullptr; ctx->pend_cap = 0;
+      size_t want = std::max(n, chunk);
+      if (cudaMallocHost(&ctx->pend_pinned, want * 8) != cudaSuccess) { *rc = fail(ctx, B2D_ERR_CUDA, "cudaMallocHost failed for the operator staging buffer"); return nullptr; }
+      ctx->pend_cap = want;
+    }
+  }
+  double* p = ctx->pend_pinned + ctx->pend_used;
+  ctx->pend_used += n;
+  return p;
 }
 
 int upload_schedule(b2d_ctx* ctx, const Schedule& S, DevSchedule& D) {
@@ -508,6 +529,7 @@ void b2d_destroy(b2d_ctx* ctx) {
                       &ctx->rotated_arena, &ctx->dsched.buf};
     for (DevBuf* b : bufs) b->release();
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->pend_pinned) cudaFreeHost(ctx->pend_pinned);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->phase_events) cudaEventDestroy(ev);
     for (auto& st : ctx->side_streams) if (st) cudaStreamDestroy(st);
@@ -537,7 +559,7 @@ int b2d_reset(b2d_ctx* ctx) {
   ctx->flops_all = 0.0;
   for (auto& sl : ctx->slabs) sl.used = 0;
   ctx->arena_doubles = 0;
-  ctx->pend_data.clear(); ctx->pend_desc.clear();
+  ctx->pend_used = 0; ctx->pend_desc.clear();
   ctx->nuser = 0; ctx->ndav = 0;
   ctx->rho_off.clear(); ctx->rho_padded = 0;
   ctx->evals.clear(); ctx->eval_row.clear(); ctx->kept.clear(); ctx->rot_off.clear();
@@ -581,8 +603,22 @@ int b2d_set_block(b2d_ctx* ctx, int side, int nq, const int32_t* q, const int32_
   return B2D_OK;
 }
 
+static int add_op_impl(b2d_ctx* ctx, int side, int optype, int norb, const int32_t* orbs, int comp, const int32_t* dq, int fermion,
+                       const uint8_t* allowed, const double* data, const double* const* blocks, int* op_id);
+
 int b2d_add_op(b2d_ctx* ctx, int side, int optype, int norb, const int32_t* orbs, int comp, const int32_t* dq, int fermion,
                const uint8_t* allowed, const double* data, int* op_id) {
+  return add_op_impl(ctx, side, optype, norb, orbs, comp, dq, fermion, allowed, data, nullptr, op_id);
+}
+
+int b2d_add_op_blocks(b2d_ctx* ctx, int side, int optype, int norb, const int32_t* orbs, int comp, const int32_t* dq, int fermion,
+                      const uint8_t* allowed, const double* const* blocks, int* op_id) {
+  if (!blocks) return fail(ctx, B2D_ERR_ARG, "b2d_add_op_blocks: null block table");
+  return add_op_impl(ctx, side, optype, norb, orbs, comp, dq, fermion, allowed, nullptr, blocks, op_id);
+}
+
+static int add_op_impl(b2d_ctx* ctx, int side, int optype, int norb, const int32_t* orbs, int comp, const int32_t* dq, int fermion,
+                       const uint8_t* allowed, const double* data, const double* const* blocks, int* op_id) {
   if (!ctx || side < 0 || side > 1 || norb < 0 || norb > 2 || !dq || !allowed) return fail(ctx, B2D_ERR_ARG, "b2d_add_op: bad arguments");
   Side& s = ctx->side[side];
   if (s.nq == 0) return fail(ctx, B2D_ERR_ARG, "b2d_add_op: call b2d_set_block first");
@@ -595,7 +631,7 @@ int b2d_add_op(b2d_ctx* ctx, int side, int optype, int norb, const int32_t* orbs
   layout_op(s, op);
   // data == NULL: the blocks are materialised (zero-filled) by b2d_plan, and only if one of this rank's terms uses
   // the operator - under a term partition a rank never holds the other ranks' operators
-  if (ctx->has_device && data) {
+  if (ctx->has_device && (data || blocks)) {
     CU(cudaSetDevice(ctx->device));
     if (op.dev_size > 0) {
       CU(arena_alloc(ctx, (size_t)op.dev_size * 8, &op.dev));
@@ -603,14 +639,24 @@ int b2d_add_op(b2d_ctx* ctx, int side, int optype, int norb, const int32_t* orbs
       CU(cudaMemsetAsync(op.dev, 0, (size_t)op.dev_size * 8, ctx->stream));
       {
         std::vector<BlockDesc> bd = op_blocks(s, op);
-        const int64_t base = (int64_t)ctx->pend_data.size();
+        int rc = B2D_OK;
+        double* room = pending_room(ctx, (size_t)op.packed_size, &rc);
+        if (!room) return rc;
+        const int64_t base = room - ctx->pend_pinned;
         const int64_t dev_base = (int64_t)((uintptr_t)op.dev / sizeof(double));
         for (BlockDesc& d : bd) { d.ref_off += base; d.dev_off += dev_base; }
         ctx->pend_desc.insert(ctx->pend_desc.end(), bd.begin(), bd.end());
-        ctx->pend_data.insert(ctx->pend_data.end(), data, data + op.packed_size);
-        if (ctx->pend_data.size() >= ((size_t)64 << 20) / 8 || ctx->pend_desc.size() >= 4096 * 64) {
-          int rc = flush_pending_ops(ctx);
-          if (rc) return rc;
+        if (data) {
+          memcpy(room, data, (size_t)op.packed_size * 8);
+        } else {   // scatter-gather form: one pointer per allowed block, copied straight from the caller's matrices
+          int64_t off = 0, k = 0;
+          for (int i = 0; i < s.nq; ++i)
+            for (int j = 0; j < s.nq; ++j)
+              if (op.allowed[(size_t)i * s.nq + j]) {
+                const int64_t n = (int64_t)s.dims[i] * s.dims[j];
+                memcpy(room + off, blocks[k++], (size_t)n * 8);
+                off += n;
+              }
         }
       }
     }

@@ -268,22 +268,26 @@ void TensorMultiply(const SpinBlock* ablock, const SparseMatrix& a, const Sparse
 
 namespace Linear {
 void block_davidson(std::vector<Wavefunction>& b, DiagonalMatrix& h_diag, double normtol, const bool&, Davidson_functor& h_multiply, bool&,
-                    int currentRoot, std::vector<Wavefunction>& lowerStates) {
+                    int /*currentRoot*/, std::vector<Wavefunction>& lowerStates) {
   const SpinBlock& big = h_multiply.get_block();
   b2d_ctx* ctx = big.context();
-  if (currentRoot >= 0 || !lowerStates.empty()) { fprintf(stderr, "block_b200: block_davidson: state-specific form is not on the GPU path yet\n"); abort(); }
-  const int n = (int)b.size();
-  B2D_CK(ctx, b2d_vec_reserve(ctx, n + 1));
+  const int n = (int)b.size(), nlow = (int)lowerStates.size();   // lowerStates non-empty: the state-specific form (linear.C:201-208,311-317,369-375)
+  B2D_CK(ctx, b2d_vec_reserve(ctx, n + 1 + nlow));
   std::vector<double> flat;
   for (int i = 0; i < n; ++i) {
     b[i].FlattenInto(flat);
     B2D_CK(ctx, b2d_vec_upload(ctx, i, flat.data()));
   }
   B2D_CK(ctx, b2d_vec_upload(ctx, n, h_diag.data()));
+  for (int i = 0; i < nlow; ++i) {
+    lowerStates[i].FlattenInto(flat);
+    B2D_CK(ctx, b2d_vec_upload(ctx, n + 1 + i, flat.data()));
+  }
   std::vector<double> evals(n);
   int nmult = 0;
   double res = 0.0;
-  B2D_CK(ctx, b2d_davidson(ctx, n, 0, n, normtol, big.options().deflation_min, big.options().deflation_max, evals.data(), &nmult, &res));
+  B2D_CK(ctx, b2d_davidson_lower(ctx, n, 0, n, normtol, big.options().deflation_min, big.options().deflation_max, nlow, n + 1, evals.data(), &nmult,
+                                 &res));
   flat.assign((size_t)big.psi_size(), 0.0);
   for (int i = 0; i < n; ++i) {
     B2D_CK(ctx, b2d_vec_download(ctx, i, flat.data()));

@@ -184,8 +184,9 @@ void TensorMultiply(const SpinBlock* ablock, const SparseMatrix& a, const Sparse
 }
 
 namespace Linear {
-// linear.C:179-385, state-averaged form (currentRoot = -1, no lower states).  The Krylov space lives on the device: the
-// functor is only asked for its block (no callbacks into the host during the solve).
+// linear.C:179-385, state-averaged (lowerStates empty) or state-specific (lowerStates = the lower roots, already orthogonalised
+// among themselves by the caller, solver.C:79-86).  The Krylov space lives on the device: the functor is only asked for its
+// block (no callbacks into the host during the solve).
 void block_davidson(std::vector<Wavefunction>& b, DiagonalMatrix& h_diag, double normtol, const bool& warmUp, Davidson_functor& h_multiply,
                     bool& useprecond, int currentRoot, std::vector<Wavefunction>& lowerStates);
 }

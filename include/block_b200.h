@@ -78,6 +78,12 @@ int b2d_set_block(b2d_ctx* ctx, int side, int nq, const int32_t* q, const int32_
 int b2d_add_op(b2d_ctx* ctx, int side, int optype, int norb, const int32_t* orbs, int comp, const int32_t* dq,
                int fermion, const uint8_t* allowed, const double* data, int* op_id);
 
+/* The same with one pointer per allowed block (i outer, j inner; each block row-major d_i x d_j, contiguous - newmat Matrix::Store()):
+ * the library copies the blocks straight from the caller's matrices into its pinned staging buffer, so a binding needs no packed
+ * intermediate copy.  Uploads are batched: the device copy happens when 64 MB are pending or at b2d_plan. */
+int b2d_add_op_blocks(b2d_ctx* ctx, int side, int optype, int norb, const int32_t* orbs, int comp, const int32_t* dq,
+                      int fermion, const uint8_t* allowed, const double* const* blocks, int* op_id);
+
 /* Synthetic-benchmark helper: fill an operator's device blocks with a counter-based uniform(-a,a) stream; if
  * symmetric != 0 the operator is made self-adjoint in the reduced-matrix-element sense (needs dq = (0,0,0)). */
 int b2d_fill_op_random(b2d_ctx* ctx, int side, int op_id, uint64_t seed, double amplitude, int symmetric);

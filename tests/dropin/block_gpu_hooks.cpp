@@ -27,6 +27,8 @@
 //   B2D_DROPIN_TRANSFORM  "device" (default): the transform hook does the block's bookkeeping itself;  "reference": it lets the
 //                         reference's transform_operators do it with MatrixRotate switched off (re-builds virtual operators on the CPU)
 //   B2D_DROPIN_WORKSPACE_MB   T workspace of the two-step contraction
+//   B2D_DROPIN_EIG        "host": diagnostic - the density-matrix eigen-decomposition and state selection stay with the reference
+//                         (dsyev_), everything else on the GPU: separates eigenvector non-uniqueness from arithmetic differences
 //   B2D_DROPIN_OPTIONS    "key=value,..." library options (b2d_set_option), e.g. eig_jacobi_max=512
 //   B2D_DROPIN_STATS      file that receives one line per block iteration (timings, flops, H applications)
 #include <sys/time.h>
@@ -154,7 +156,7 @@ void upload_block(int side, SpinBlock& b, vector<OpRef>* keep) {
   vector<int32_t> sites(b.get_sites().begin(), b.get_sites().end());
   ck(b2d_set_block(g.ctx, side, nq, q.data(), dims.data(), b.is_loopblock() ? 1 : 0, (int)sites.size(), sites.data()), "b2d_set_block");
   vector<uint8_t> allowed((size_t)nq * nq);
-  vector<double> data;
+  vector<const double*> blocks;
   for (std::map<opTypes, boost::shared_ptr<Op_component_base> >::iterator it = b.ops.begin(); it != b.ops.end(); ++it) {
     Op_component_base& arr = *it->second;
     for (int i = 0; i < arr.get_size(); ++i) {
@@ -173,16 +175,16 @@ void upload_block(int side, SpinBlock& b, vector<OpRef>* keep) {
         for (int k = 0; k < norb; ++k) orbs[k] = op.get_orbs()[k];
         SpinQuantum dq = op.get_deltaQuantum(0);
         int32_t dqv[3] = {dq.get_n(), dq.get_s().getirrep(), dq.get_symm().getirrep()};
-        data.clear();
+        blocks.clear();
         for (int a = 0; a < nq; ++a)
           for (int bq = 0; bq < nq; ++bq) {
             bool al = op.allowed(a, bq);
             allowed[(size_t)a * nq + bq] = al ? 1 : 0;
-            if (al) { const Matrix& m = op.operator_element(a, bq); data.insert(data.end(), m.Store(), m.Store() + m.Storage()); }
+            if (al) blocks.push_back(op.operator_element(a, bq).Store());   // newmat Matrix: row-major, contiguous
           }
-        if (data.empty()) data.push_back(0.0);
+        if (blocks.empty()) blocks.push_back(0);
         int id = -1;
-        ck(b2d_add_op(g.ctx, side, (int)it->first, norb, orbs, (int)c, dqv, op.get_fermion() ? 1 : 0, allowed.data(), data.data(), &id), "b2d_add_op");
+        ck(b2d_add_op_blocks(g.ctx, side, (int)it->first, norb, orbs, (int)c, dqv, op.get_fermion() ? 1 : 0, allowed.data(), blocks.data(), &id), "b2d_add_op_blocks");
         if (keep) keep->push_back(OpRef{vec[c].get(), id});
       }
     }
@@ -421,7 +423,9 @@ void wrap_makedm(DensityMatrix* self, const vector<Wavefunction>& ws, SpinBlock&
 // ---- diagonalise_dm ----
 void real_diagdm(SparseMatrix& traced, SparseMatrix& transform, vector<DiagonalMatrix>& eigs) asm("__real_" SYM_diagonalise_dm);
 void wrap_diagdm(SparseMatrix& traced, SparseMatrix& transform, vector<DiagonalMatrix>& eigs) asm("__wrap_" SYM_diagonalise_dm);
+bool eig_on_host() { const char* v = getenv("B2D_DROPIN_EIG"); return v && string(v) == "host"; }
 void wrap_diagdm(SparseMatrix& traced, SparseMatrix& transform, vector<DiagonalMatrix>& eigs) {
+  if (eig_on_host()) { real_diagdm(traced, transform, eigs); return; }   // diagnostic: dsyev_ eigenvectors, everything else on the GPU
   if (!g.ctx || !g.active || !g.rho_on_device) die("diagonalise_dm outside a GPU block iteration (module not covered by the GPU path)");
   bool check = env_on("B2D_DROPIN_CHECK");
   if (check) {
@@ -467,6 +471,7 @@ double wrap_assign(vector<Matrix>& rot, vector<DiagonalMatrix>& eigs, SparseMatr
                    int nbydm, int nbyq, int lsize, int rsize) asm("__wrap_" SYM_assign_matrix_by_dm);
 double wrap_assign(vector<Matrix>& rot, vector<DiagonalMatrix>& eigs, SparseMatrix& transform, vector<std::pair<int, int> >& inorder, vector<vector<int> >& byq,
                    int nbydm, int nbyq, int lsize, int rsize) {
+  if (eig_on_host()) return real_assign(rot, eigs, transform, inorder, byq, nbydm, nbyq, lsize, rsize);
   if (!g.ctx || !g.active || !g.rho_on_device) die("assign_matrix_by_dm outside a GPU block iteration (module not covered by the GPU path)");
   if (nbyq != 0) die("keptqstates != 0: not covered (sweep_params.C:80 always passes 0)");
   if (dmrginp.do_pdm()) die("do_pdm keeps zero-weight states (rotationmat.C:161): not covered by the GPU path");

@@ -572,7 +572,7 @@ def main():
     ap.add_argument("--no-block-iteration", action="store_true", help="skip the Davidson / density / eigen / rotation leg")
     ap.add_argument("--davidson-iters", type=int, default=6)
     ap.add_argument("--no-sweep", action="store_true", help="skip the whole-sweep leg (reference sweep vs the same sweep with the GPU hot path)")
-    ap.add_argument("--sweep-case", default="synthetic_14o_M200", help="case of tests/golden/dropin_cases.npz for the sweep leg")
+    ap.add_argument("--sweep-case", default="synthetic_18o_M500", help="case of tests/golden/dropin_cases.npz for the sweep leg")
     ap.add_argument("--profile-mode", action="store_true", help="for ncu: 1 warm-up sigma + --steps sigmas, nothing else, no JSON line")
     ap.add_argument("--cpu-budget-s", type=float, default=15.0)
     ap.add_argument("--ref-step-s", type=float, default=6.0)

@@ -194,6 +194,8 @@ struct b2d_ctx {
   Nccl nccl;
   Cusolver cusolver;
   DevBuf eig_work, eig_info;
+  bool persistent = false;   // option "persistent": 128 x 128 class as a persistent kernel with a cross-tile pipeline (measured: no gain, see profiles/README.md)
+  DevBuf tile_counter;
   int eig_jacobi_max = 64;   // sectors up to this size use the hand-written Jacobi kernel, larger ones cusolverDnDsyevd
 };
 
@@ -360,7 +362,8 @@ int run_schedule(b2d_ctx* ctx, const Schedule& S, const DevSchedule& D, double* 
         slot = (unsigned long long*)ctx->trace_buf.p + 2 * trace.size();
         trace.push_back(TraceRec{cur_chunk, cur_step, c});
       }
-      CU(launch_gemm_class(b, c, bases, st, &ctx->launches, slot));
+      int* counter = (ctx->persistent && c == 0 && st == ctx->stream) ? (int*)ctx->tile_counter.p : nullptr;
+      CU(launch_gemm_class(b, c, bases, st, &ctx->launches, slot, counter));
       return B2D_OK;
     };
     auto run_batch = [&](const DevBatch& b) -> int {
@@ -510,6 +513,7 @@ int b2d_create(int device, b2d_ctx** out) {
     CU(cudaMallocHost(&c->h_pinned, 64 * sizeof(double)));
     CU(c->partials.reserve((size_t)L1_MAX_BLOCKS * L1_MAX_VECS * 8));
     CU(c->scalars.reserve(8192 * 8));
+    CU(c->tile_counter.reserve(256));
   }
   *out = c.release();
   return B2D_OK;
@@ -526,7 +530,7 @@ void b2d_destroy(b2d_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->staging, &ctx->desc_scratch, &ctx->work, &ctx->parts, &ctx->trace_buf, &ctx->eig_work, &ctx->eig_info, &ctx->dm_noise, &ctx->flat_in, &ctx->flat_out, &ctx->psi_blocks, &ctx->diag_tasks,
                       &ctx->diag_begin, &ctx->partials, &ctx->scalars, &ctx->user_pool, &ctx->dav_pool, &ctx->rho, &ctx->eig_g, &ctx->eig_vt,
                       &ctx->eig_vals, &ctx->eig_sweeps, &ctx->sector_desc, &ctx->rot, &ctx->gather_desc, &ctx->gather_rows,
-                      &ctx->rotated_arena, &ctx->dsched.buf};
+                      &ctx->rotated_arena, &ctx->dsched.buf, &ctx->tile_counter};
     for (DevBuf* b : bufs) b->release();
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->pend_pinned) cudaFreeHost(ctx->pend_pinned);
@@ -584,6 +588,7 @@ int b2d_set_option(b2d_ctx* ctx, const char* key, double value) {
   else if (k == "multi_stream") ctx->multi_stream = value != 0;
   else if (k == "slice_iters") ctx->slice_iters = (int)value;
   else if (k == "eig_jacobi_max") ctx->eig_jacobi_max = (int)value;
+  else if (k == "persistent") ctx->persistent = value != 0;
   else if (k == "phase_timing") ctx->phase_timing = value != 0;
   else return fail(ctx, B2D_ERR_ARG, "unknown option " + k);
   return B2D_OK;

@@ -39,6 +39,7 @@ namespace b2d {
 struct Bases {
   double* p[B2D_NUM_BASES];
   unsigned long long* trace;   // diagnostic: {min CTA start, max CTA end} of this launch in %globaltimer ns, or nullptr
+  int* tile_counter;           // persistent variant: next unclaimed tile of the launch (zeroed before the launch)
 };
 
 constexpr int GEMM_BK = 16;
@@ -278,6 +279,155 @@ __global__ void __launch_bounds__(TileCfg<BM, BN>::THREADS)
           dst[0] = grp.accumulate ? dst[0] + v0 : v0;
         }
       }
+  if (bases.trace && threadIdx.x == 0) {
+    unsigned long long t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    atomicMax(bases.trace + 1, t1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Persistent variant (used for the 128 x 128 class, one 16-warp CTA per SM): a CTA claims tiles from an atomic counter in the
+// host's cost-sorted order and runs ONE pipeline across tile boundaries - the loads of the next tile's first stages are
+// already in flight while the warps store the current tile's accumulators, so the per-tile prologue (first loads) and epilogue
+// (stores) no longer leave the DMMA pipe idle.  Tile ids travel from thread 0 to the other threads through an 8-slot ring
+// guarded by mbarriers (no CTA-wide barrier anywhere in the loop).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int TILE_RING = 8;
+
+template <int BM, int BN, bool ALPHA>
+__global__ void __launch_bounds__(TileCfg<BM, BN>::THREADS)
+    grouped_gemm_persistent_kernel(const GSeg* __restrict__ segs, const GGroup* __restrict__ groups, const GTile* __restrict__ tiles, int ntiles, Bases bases) {
+  using Cfg = TileCfg<BM, BN>;
+  constexpr int THREADS = Cfg::THREADS;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ __align__(16) double smem[];
+  __shared__ StageMeta meta[STAGES];
+  __shared__ uint64_t full_bar[STAGES], empty_bar[STAGES], tile_bar[TILE_RING];
+  __shared__ int tile_ring[TILE_RING];
+
+  if (bases.trace && threadIdx.x == 0) {
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    atomicMin(bases.trace, t0);
+  }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int wm = warp / Cfg::WARPS_N, wn = warp % Cfg::WARPS_N;
+  const int g = lane >> 2, t = lane & 3;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], THREADS + 1); mbar_init(&empty_bar[s], THREADS / 32); }
+#pragma unroll
+    for (int s = 0; s < TILE_RING; ++s) mbar_init(&tile_bar[s], 1);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { tile_ring[0] = atomicAdd(bases.tile_counter, 1); mbar_arrive(&tile_bar[0]); }
+
+  // ---- producer cursor: (tile, segment, k0); every thread stages its share of each operand slab ----
+  int p_seq = 0;            // sequence number of the tile being produced
+  bool p_valid = false;
+  int p_m0 = 0, p_n0 = 0, p_m = 0, p_n = 0, p_left = 0, p_send = 0, ps = 0, pk = 0;
+  GSeg sg;
+  auto enter_tile = [&](int seq) {
+    mbar_wait(&tile_bar[seq % TILE_RING], (seq / TILE_RING) & 1);
+    const int id = tile_ring[seq % TILE_RING];
+    p_valid = id < ntiles;
+    if (threadIdx.x == 0 && p_valid) {   // publish the following tile now: its id is needed PREFETCH stages before this one ends
+      tile_ring[(seq + 1) % TILE_RING] = atomicAdd(bases.tile_counter, 1);
+      mbar_arrive(&tile_bar[(seq + 1) % TILE_RING]);
+    }
+    if (!p_valid) return;
+    const GTile tl = tiles[id];
+    const GGroup gr = groups[tl.group];
+    p_m0 = tl.m0; p_n0 = tl.n0; p_m = gr.m; p_n = gr.n; p_left = gr.kiters; ps = gr.seg_begin; p_send = gr.seg_end; pk = 0;
+    sg = segs[ps];
+  };
+  enter_tile(0);
+  int pg = 0;               // stages produced so far (over all tiles of this CTA)
+  auto produce_one = [&]() {
+    const int slot = pg % STAGES;
+    if (pg >= STAGES) mbar_wait(&empty_bar[slot], ((pg / STAGES) & 1) ^ 1);
+    const double* A = sg.a_base == B2D_BASE_ABS ? reinterpret_cast<const double*>(sg.a) : bases.p[sg.a_base] + sg.a;
+    const double* B = sg.b_base == B2D_BASE_ABS ? reinterpret_cast<const double*>(sg.b) : bases.p[sg.b_base] + sg.b;
+    double* sA = smem + slot * Cfg::STAGE_DOUBLES;
+    double* sB = sA + Cfg::A_DOUBLES;
+    stage_operand<BM, THREADS>(sA, A, sg.lda, sg.a_trans == 0, p_m0, pk, p_m, sg.k);
+    stage_operand<BN, THREADS>(sB, B, sg.ldb, sg.b_kmajor != 0, p_n0, pk, p_n, sg.k);
+    mbar_arrive_on_cp_async(&full_bar[slot]);
+    if (threadIdx.x == 0) {
+      meta[slot].alpha = sg.alpha;
+      meta[slot].layout = (sg.a_trans ? 1 : 0) | (sg.b_kmajor ? 2 : 0);
+      mbar_arrive(&full_bar[slot]);
+    }
+    ++pg;
+    pk += GEMM_BK;
+    if (pk >= sg.k) {
+      pk = 0;
+      if (++ps < p_send) sg = segs[ps];
+    }
+    if (--p_left == 0) enter_tile(++p_seq);
+  };
+
+  const int ar = wm * 32 + g, br = wn * 32 + g;
+  const int a_off_n = ar * (GEMM_BK + GEMM_PAD) + t, a_off_t = ar + t * (BM + GEMM_PAD);
+  const int b_off_n = br + t * (BN + GEMM_PAD), b_off_k = br * (GEMM_BK + GEMM_PAD) + t;
+
+  int cg = 0;               // stages consumed so far
+  for (int seq = 0;; ++seq) {
+    mbar_wait(&tile_bar[seq % TILE_RING], (seq / TILE_RING) & 1);
+    const int id = tile_ring[seq % TILE_RING];
+    if (id >= ntiles) break;
+    const GTile tile = tiles[id];
+    const GGroup grp = groups[tile.group];
+    const int m0 = tile.m0, n0 = tile.n0;
+    double acc[2][4][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.0;
+    const int total = grp.kiters;
+    for (int it = 0; it < total; ++it) {
+      while (p_valid && pg <= cg + Cfg::PREFETCH) produce_one();   // keeps running into the NEXT tile near the end of this one
+      const int stage = cg % STAGES;
+      mbar_wait(&full_bar[stage], (cg / STAGES) & 1);
+      const double* sA = smem + stage * Cfg::STAGE_DOUBLES;
+      const double* sB = sA + Cfg::A_DOUBLES;
+      const StageMeta mt = meta[stage];
+      switch (mt.layout) {
+        case 0: mma_stage<BM, BN, false, false, ALPHA>(sA + a_off_n, sB + b_off_n, mt.alpha, acc); break;
+        case 1: mma_stage<BM, BN, true, false, ALPHA>(sA + a_off_t, sB + b_off_n, mt.alpha, acc); break;
+        case 2: mma_stage<BM, BN, false, true, ALPHA>(sA + a_off_n, sB + b_off_k, mt.alpha, acc); break;
+        default: mma_stage<BM, BN, true, true, ALPHA>(sA + a_off_t, sB + b_off_k, mt.alpha, acc); break;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty_bar[stage]);
+      ++cg;
+    }
+    while (p_valid && pg <= cg + Cfg::PREFETCH) produce_one();     // the next tile's first stages are in flight during the stores
+    double* C = bases.p[grp.c_base] + grp.c;
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          int row = m0 + wm * 32 + i * 16 + g + h * 8;
+          int col = n0 + wn * 32 + j * 8 + 2 * t;
+          if (row >= grp.m || col >= grp.n) continue;
+          double* dst = C + (int64_t)row * grp.ldc + col;
+          double v0 = acc[i][j][2 * h], v1 = acc[i][j][2 * h + 1];
+          if (col + 1 < grp.n) {
+            double2 o;
+            if (grp.accumulate) { o = *reinterpret_cast<double2*>(dst); o.x += v0; o.y += v1; }
+            else { o.x = v0; o.y = v1; }
+            *reinterpret_cast<double2*>(dst) = o;
+          } else {
+            dst[0] = grp.accumulate ? dst[0] + v0 : v0;
+          }
+        }
+  }
   if (bases.trace && threadIdx.x == 0) {
     unsigned long long t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));

@@ -27,6 +27,17 @@ static cudaError_t init_pair() {
   cudaError_t e = init_one<BM, BN, true>();
   return e != cudaSuccess ? e : init_one<BM, BN, false>();
 }
+static int g_num_sms = 0;
+static cudaError_t init_persistent() {
+  cudaError_t e = cudaFuncSetAttribute(grouped_gemm_persistent_kernel<128, 128, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<128, 128>::SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(grouped_gemm_persistent_kernel<128, 128, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TileCfg<128, 128>::SMEM_BYTES);
+  if (e != cudaSuccess) return e;
+  int dev = 0;
+  e = cudaGetDevice(&dev);
+  if (e != cudaSuccess) return e;
+  return cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+}
 
 cudaError_t gemm_init() {   // opt in to > 48 KB dynamic shared memory
   cudaError_t e;
@@ -35,7 +46,7 @@ cudaError_t gemm_init() {   // opt in to > 48 KB dynamic shared memory
   B2D_INIT(64, 128) B2D_INIT(64, 64) B2D_INIT(64, 32)
   B2D_INIT(32, 128) B2D_INIT(32, 64) B2D_INIT(32, 32)
 #undef B2D_INIT
-  return cudaSuccess;
+  return init_persistent();
 }
 
 template <int BM, int BN>
@@ -46,11 +57,22 @@ static void launch_one(const DevBatch& b, int cls, const Bases& B, cudaStream_t 
 }
 
 cudaError_t launch_gemm_class(const DevBatch& b, int cls, double* const* bases, cudaStream_t stream, int64_t* launches,
-                              unsigned long long* trace_slot) {
+                              unsigned long long* trace_slot, int* tile_counter) {
   if (cls < 0 || cls >= B2D_NUM_TILE_CLASSES || b.ntiles[cls] <= 0) return cudaSuccess;
   Bases B;
   for (int i = 0; i < B2D_NUM_BASES; ++i) B.p[i] = bases[i];
   B.trace = trace_slot;
+  B.tile_counter = tile_counter;
+  if (cls == 0 && tile_counter && g_num_sms > 0 && b.ntiles[0] > g_num_sms) {
+    // persistent 128 x 128: one CTA per SM claims tiles from the counter; the pipeline runs across tile boundaries
+    cudaError_t e = cudaMemsetAsync(tile_counter, 0, sizeof(int), stream);
+    if (e != cudaSuccess) return e;
+    using Cfg = TileCfg<128, 128>;
+    if (b.unit_alpha) grouped_gemm_persistent_kernel<128, 128, false><<<g_num_sms, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(b.segs, b.groups, b.tiles[0], b.ntiles[0], B);
+    else grouped_gemm_persistent_kernel<128, 128, true><<<g_num_sms, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(b.segs, b.groups, b.tiles[0], b.ntiles[0], B);
+    B2D_LAUNCH_CHECK();
+    return cudaSuccess;
+  }
   switch (cls) {
     case 0: launch_one<128, 128>(b, cls, B, stream); break;
     case 1: launch_one<128, 64>(b, cls, B, stream); break;
@@ -69,7 +91,7 @@ cudaError_t launch_gemm_class(const DevBatch& b, int cls, double* const* bases, 
 
 cudaError_t launch_gemm_batch(const DevBatch& b, double* const* bases, cudaStream_t stream, int64_t* launches) {
   for (int c = 0; c < B2D_NUM_TILE_CLASSES; ++c) {
-    cudaError_t e = launch_gemm_class(b, c, bases, stream, launches);
+    cudaError_t e = launch_gemm_class(b, c, bases, stream, launches, nullptr, nullptr);
     if (e != cudaSuccess) return e;
   }
   return cudaSuccess;

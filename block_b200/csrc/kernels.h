@@ -28,8 +28,9 @@ cudaError_t gemm_init();   // opt in to > 48 KB dynamic shared memory
 // base pointers: p[B2D_BASE_SRC], p[B2D_BASE_WORK], p[B2D_BASE_DST], p[B2D_BASE_AUX]
 cudaError_t launch_gemm_batch(const DevBatch& b, double* const* bases, cudaStream_t stream, int64_t* launches);
 // one tile class of the batch only (profiling: events around each class)
+// tile_counter != nullptr (one int of device memory, private to the stream): the 128 x 128 class runs as a persistent kernel
 cudaError_t launch_gemm_class(const DevBatch& b, int cls, double* const* bases, cudaStream_t stream, int64_t* launches,
-                              unsigned long long* trace_slot = nullptr);
+                              unsigned long long* trace_slot = nullptr, int* tile_counter = nullptr);
 
 // flat reference layout <-> padded device layout (Wavefunction::CollectFrom / FlattenInto; operator upload)
 cudaError_t launch_pack(const BlockDesc* blocks, int nblocks, const double* flat, double* dev, cudaStream_t s, int64_t* launches);

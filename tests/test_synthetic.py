@@ -128,3 +128,27 @@ def test_gpu_synthetic_sigma_matches_oracle():
                 sb2.close()
     finally:
         sb.close()
+
+
+@pytest.mark.gpu
+def test_gpu_persistent_kernel_is_bit_identical():
+    """The persistent 128 x 128 kernel (tiles claimed from an atomic counter, one pipeline across tile boundaries) against the
+    one-CTA-per-tile kernel: same tiles, same K order inside a tile => bit-identical sigma; forced 128 x 128 tiles so that the
+    class has far more tiles than SMs, and the default (auto) classes as well."""
+    a = args(300, left_sites=6, norbs=14, nelec=14)
+    psi = np.random.default_rng(11).standard_normal
+    out = {}
+    for cls in (0, -1):
+        for pers in (0, 1):
+            sb = S.make_big_block(norbs=a.norbs, nelec=a.nelec, M=a.M, left_sites=a.left_sites, device=0,
+                                  options={"tile_class": cls, "persistent": pers})
+            try:
+                x = np.random.default_rng(11).standard_normal(sb.size)
+                out[(cls, pers)] = sb.multiplyH(x)
+                if cls == 0:
+                    assert sb.plan_stats()["tiles"] > 148 * 4
+            finally:
+                sb.close()
+    assert np.array_equal(out[(0, 0)], out[(0, 1)])
+    assert np.array_equal(out[(-1, 0)], out[(-1, 1)])
+    assert np.linalg.norm(out[(0, 1)] - out[(-1, 1)]) <= 1e-12 * np.linalg.norm(out[(-1, 1)])

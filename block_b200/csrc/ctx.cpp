@@ -154,7 +154,7 @@ struct b2d_ctx {
   DevBuf parts;            // split-K partial copies of the destination wavefunction (run_sigma_schedule)
   int slice_iters = 256;   // pipeline iterations per split-K slice (0: no split)
   DevBuf psi_blocks;       // BlockDesc per psi block
-  DevBuf diag_tasks, diag_begin;
+  DevBuf diag_tasks, diag_begin, diag_gather, diag_pool;
   DevBuf partials, scalars;   // level-1 partial sums; G / theta / alpha / misc scalars
   double* h_pinned = nullptr; // 64 doubles
 
@@ -375,7 +375,10 @@ int run_schedule(b2d_ctx* ctx, const Schedule& S, const DevSchedule& D, double* 
       bool more = false;
       for (int c = first + 1; c < B2D_NUM_TILE_CLASSES; ++c) more = more || b.ntiles[c] > 0;
       if (ctx->multi_stream && more) CU(cudaEventRecord(ctx->fork_ev, ctx->stream));
-      { int rc = traced_launch(b, first, ctx->stream); if (rc) return rc; }
+      // persistent 128 x 128 class: the narrower classes are queued FIRST and the persistent CTAs (which claim tiles dynamically,
+      // so a CTA that starts late simply takes fewer tiles) fill the SMs as they free up - nothing is left for a serial tail
+      const bool big_last = ctx->persistent && ctx->multi_stream && first == 0 && more;
+      if (!big_last) { int rc = traced_launch(b, first, ctx->stream); if (rc) return rc; }
       if (ctx->multi_stream) {
         for (int c = first + 1; c < B2D_NUM_TILE_CLASSES; ++c) {
           if (b.ntiles[c] <= 0) continue;
@@ -385,6 +388,7 @@ int run_schedule(b2d_ctx* ctx, const Schedule& S, const DevSchedule& D, double* 
           CU(cudaEventRecord(ctx->join_ev[c - 1], side));
         }
       }
+      if (big_last) { int rc = traced_launch(b, first, ctx->stream); if (rc) return rc; }
       for (int c = first + 1; c < B2D_NUM_TILE_CLASSES; ++c) {
         if (b.ntiles[c] <= 0) continue;
         if (ctx->multi_stream) CU(cudaStreamWaitEvent(ctx->stream, ctx->join_ev[c - 1], 0));
@@ -432,7 +436,7 @@ int run_schedule(b2d_ctx* ctx, const Schedule& S, const DevSchedule& D, double* 
       for (int c = 0; c < B2D_NUM_TILE_CLASSES; ++c) {
         if (b.ntiles[c] <= 0) continue;
         CU(cudaEventRecord(event(nev++), ctx->stream));
-        CU(launch_gemm_class(b, c, bases, ctx->stream, &ctx->launches));
+        CU(launch_gemm_class(b, c, bases, ctx->stream, &ctx->launches, nullptr, (ctx->persistent && c == 0) ? (int*)ctx->tile_counter.p : nullptr));
         CU(cudaEventRecord(event(nev++), ctx->stream));
         marks.push_back(Mark{step, c});
       }
@@ -530,7 +534,7 @@ void b2d_destroy(b2d_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->staging, &ctx->desc_scratch, &ctx->work, &ctx->parts, &ctx->trace_buf, &ctx->eig_work, &ctx->eig_info, &ctx->dm_noise, &ctx->flat_in, &ctx->flat_out, &ctx->psi_blocks, &ctx->diag_tasks,
                       &ctx->diag_begin, &ctx->partials, &ctx->scalars, &ctx->user_pool, &ctx->dav_pool, &ctx->rho, &ctx->eig_g, &ctx->eig_vt,
                       &ctx->eig_vals, &ctx->eig_sweeps, &ctx->sector_desc, &ctx->rot, &ctx->gather_desc, &ctx->gather_rows,
-                      &ctx->rotated_arena, &ctx->dsched.buf, &ctx->tile_counter};
+                      &ctx->rotated_arena, &ctx->dsched.buf, &ctx->tile_counter, &ctx->diag_gather, &ctx->diag_pool};
     for (DevBuf* b : bufs) b->release();
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->pend_pinned) cudaFreeHost(ctx->pend_pinned);
@@ -999,12 +1003,47 @@ int b2d_diagonal(b2d_ctx* ctx, int dst_slot) {
   try {
     build_diag_tasks(ctx->side[0], ctx->side[1], ctx->psi, ctx->terms_mine, ctx->core_energy, ctx->hubbard, ctx->am, tasks, begin);
   } catch (const std::exception& e) { return fail(ctx, B2D_ERR_ARG, e.what()); }
-  int rc = upload_desc(ctx, ctx->diag_tasks, tasks.data(), tasks.size() * sizeof(DiagTask));
+  // every (operator, sector) diagonal is read by ~d_other x #tasks threads with stride ld + 1: gather each distinct one ONCE into
+  // a compact pool and point the tasks at it (stride 1: coalesced along j, broadcast along i)
+  std::vector<DiagGather> gather;
+  {
+    std::map<std::pair<int64_t, int>, int64_t> seen;   // (address, stride) -> pool offset
+    int64_t pool = 0;
+    const PsiLayout& P = ctx->psi;
+    auto remap = [&](int64_t& addr, int32_t& stride, int n) {
+      if (!addr) return;
+      auto key = std::make_pair(addr, (int)stride);
+      auto it = seen.find(key);
+      if (it == seen.end()) {
+        it = seen.emplace(key, pool).first;
+        gather.push_back(DiagGather{addr, pool, n, stride});
+        pool += (n + 1) & ~1;
+      }
+      addr = it->second;   // pool offset for now; turned into an address below
+      stride = 1;
+    };
+    for (int p = 0; p < P.nblocks(); ++p)
+      for (int t = begin[p]; t < begin[p + 1]; ++t) {
+        remap(tasks[t].a, tasks[t].sa, P.rows[p]);
+        remap(tasks[t].b, tasks[t].sb, P.cols[p]);
+      }
+    CU(ctx->diag_pool.reserve((size_t)std::max<int64_t>(pool, 2) * 8));
+    const int64_t base = (int64_t)(intptr_t)ctx->diag_pool.p;
+    for (int p = 0; p < P.nblocks(); ++p)
+      for (int t = begin[p]; t < begin[p + 1]; ++t) {
+        if (tasks[t].sa == 1) tasks[t].a = base + 8 * tasks[t].a;
+        if (tasks[t].sb == 1) tasks[t].b = base + 8 * tasks[t].b;
+      }
+  }
+  int rc = upload_desc(ctx, ctx->diag_gather, gather.data(), gather.size() * sizeof(DiagGather));
+  if (rc) return rc;
+  rc = upload_desc(ctx, ctx->diag_tasks, tasks.data(), tasks.size() * sizeof(DiagTask));
   if (rc) return rc;
   rc = upload_desc(ctx, ctx->diag_begin, begin.data(), begin.size() * sizeof(int));
   if (rc) return rc;
   begin_timing(ctx);
   CU(cudaMemsetAsync(user_vec(ctx, dst_slot), 0, (size_t)ctx->psi.Wp * 8, ctx->stream));
+  CU(launch_gather_diag((const DiagGather*)ctx->diag_gather.p, (int)gather.size(), (double*)ctx->diag_pool.p, ctx->stream, &ctx->launches));
   CU(launch_diag((const BlockDesc*)ctx->psi_blocks.p, ctx->psi.nblocks(), (const DiagTask*)ctx->diag_tasks.p, (const int*)ctx->diag_begin.p,
                  user_vec(ctx, dst_slot), ctx->stream, &ctx->launches));
   rc = allreduce(ctx, user_vec(ctx, dst_slot), ctx->psi.Wp);   // every rank added the terms it owns

@@ -533,6 +533,21 @@ __global__ void __launch_bounds__(256) diag_kernel(const BlockDesc* __restrict__
   }
 }
 
+// gather the diagonals of operator blocks into one compact pool: pool[dst + i] = *(src + i * stride)
+__global__ void gather_diag_kernel(const DiagGather* __restrict__ items, int nitems, double* __restrict__ pool) {
+  for (int it = blockIdx.x; it < nitems; it += gridDim.x) {
+    const DiagGather g = items[it];
+    const double* src = reinterpret_cast<const double*>(g.src);
+    for (int i = threadIdx.x; i < g.n; i += blockDim.x) pool[g.dst + i] = src[(int64_t)i * g.stride];
+  }
+}
+cudaError_t launch_gather_diag(const DiagGather* items, int nitems, double* pool, cudaStream_t s, int64_t* launches) {
+  if (nitems == 0) return cudaSuccess;
+  gather_diag_kernel<<<min(nitems, 8192), 128, 0, s>>>(items, nitems, pool);
+  B2D_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
 cudaError_t launch_diag(const BlockDesc* blocks, int nblocks, const DiagTask* tasks, const int* block_begin, double* e, cudaStream_t s, int64_t* launches) {
   if (nblocks == 0) return cudaSuccess;
   for (int b0 = 0; b0 < nblocks; b0 += 32768) {

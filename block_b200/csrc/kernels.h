@@ -62,6 +62,13 @@ cudaError_t launch_sum_parts(double* dst, const double* parts, int nparts, int64
 // G: n x ldg (upper triangle G[j][i], i >= j, valid; mirrored inside); theta[n] ascending; alpha[i*ldg + j] = component i of eigenvector j
 cudaError_t launch_subspace_eig(const double* G, int n, int ldg, double* theta, double* alpha, cudaStream_t s, int64_t* launches);
 
+// diagonals of operator sector blocks gathered into a compact pool (stride ld + 1 -> 1) before diag(H) reads them thousands of times
+struct DiagGather {
+  int64_t src;      // absolute byte address of the first diagonal element
+  int64_t dst;      // offset (doubles) in the pool
+  int32_t n, stride;
+};
+cudaError_t launch_gather_diag(const DiagGather* items, int nitems, double* pool, cudaStream_t s, int64_t* launches);
 // diag(H): e[block p][i, j] += sum_tasks f a_i b_j
 cudaError_t launch_diag(const BlockDesc* blocks, int nblocks, const DiagTask* tasks, const int* block_begin, double* e, cudaStream_t s, int64_t* launches);
 

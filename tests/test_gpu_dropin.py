@@ -55,6 +55,18 @@ def test_golden_sweeps_parse():
             assert "FCIDUMP" in [str(f) for f in z[n + "/files"]]
 
 
+def test_dropin_fails_loudly_without_a_device():
+    """CPU: with a planning-only context (B2D_DEVICE=-1) the drop-in binary marshals the first big block through the C ABI
+    (b2d_set_block / b2d_add_op_blocks / b2d_plan: integer work) and then ABORTS at the first compute call with the library's
+    message - there is no CPU fallback behind the hooks."""
+    if not os.path.exists(BLOCK_GPU):
+        pytest.skip("oracle/_ref/block_gpu not built (make -C oracle dropin; needs the reference sources)")
+    out, _, _ = run_case("c2_d2h_M50", {"B2D_DEVICE": "-1"}, timeout=300)
+    assert out.returncode != 0
+    assert "no CUDA device" in out.stderr and "no CPU fallback" in out.stderr, out.stderr[-500:]
+    assert "Sweep Energy" not in out.stdout
+
+
 # Conditioning of the comparison.  Every arithmetic step of the path is reproduced to ~1e-13 (see
 # test_every_hook_against_the_cpu_function), but ONE output of the path is not unique: the eigenvectors of the reduced density
 # matrix inside (near-)degenerate eigenspaces - in particular the near-null space (weights 1e-13 .. 1e-10, i.e. squares of

@@ -1,5 +1,4 @@
-mkdir -p gpurun_out/r9
-for w in "--opt persistent=1" "--opt persistent=0"; do timeout 600 python bench.py --no-cpu --no-block-iteration --no-sweep --steps 3 --warmup 3 $w 2> gpurun_out/r9/exp.err | python -c "
-import json,sys; l=json.loads(sys.stdin.read().strip().splitlines()[-1]); p=l['roofline']['per_class']; print('$w', round(l['value']), round(l['ms_per_step'],1), 'frac', round(l['roofline']['frac'],4), 's1_128', round(p['step1_128x128']['tflops'],2), 's2_128', round(p['step2_128x128']['tflops'],2), 'lin', l['parity']['linearity_rel'])" | tee -a gpurun_out/r9/persistent_ab.txt; tail -2 gpurun_out/r9/exp.err; done
-ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_subpipe_dmma_cycles_active.avg.pct_of_peak_sustained_active --clock-control none -k regex:"grouped_gemm|tiny_gemm|sum_parts|multi_dot|rotate|residual|olsen|mgs|axpy|normalise|finish" -c 900 --csv --log-file gpurun_out/r9/ncu_launches_sigma_level1.csv python bench.py --profile-mode --steps 1 > gpurun_out/r9/ncu1.log 2>&1; tail -2 gpurun_out/r9/ncu1.log
-ncu --set full --import-source on --clock-control none -k regex:"rotate_square|rayleigh|multi_dot|olsen" -c 6 -o gpurun_out/r9/ncu_full_level1 python bench.py --profile-mode --steps 1 > gpurun_out/r9/ncu2.log 2>&1; tail -2 gpurun_out/r9/ncu2.log
+mkdir -p gpurun_out/r10
+python -m pytest tests -m gpu -q -x 2>&1 | tail -8 > gpurun_out/r10/pytest_gpu.txt; cat gpurun_out/r10/pytest_gpu.txt
+python bench.py > gpurun_out/r10/bench_n1.json 2> gpurun_out/r10/bench_n1.err; python -c "
+import json; l=json.loads(open('gpurun_out/r10/bench_n1.json').read().strip().splitlines()[-1]); print(l['value'], l['e2e']['value'], l['roofline']['frac']); print(l['block_iteration']); print(l['sweep'])"; tail -2 gpurun_out/r10/bench_n1.err

@@ -205,6 +205,21 @@ void wrap_RenormaliseFrom(SpinBlock* self, vector<double>& energies, vector<doub
     const StateInfo& bs = big.get_stateInfo();
     dump_stateinfo(d, "big.", bs);
     d.ints("big.lmap", bs.leftUnMapQuanta); d.ints("big.rmap", bs.rightUnMapQuanta); d.ints("big.unblocked", bs.unBlockedIndex);
+    if (getenv("ORACLE_DUMP_CHILDREN") && big.get_leftBlock()->get_leftBlock() && big.get_leftBlock()->get_rightBlock()) {
+      // for the operator-construction oracle: the two children of the enlarged left block with every operator they
+      // carry, and the product StateInfo maps of the enlarged block (TensorProduct / TensorTrace, operatorfunctions.C:19-254)
+      SpinBlock& nl = *big.get_leftBlock();
+      dump_block(d, "LL.", *nl.get_leftBlock());
+      dump_block(d, "LR.", *nl.get_rightBlock());
+      const StateInfo& si = nl.get_stateInfo();
+      d.ints("L.si.lmap", si.leftUnMapQuanta); d.ints("L.si.rmap", si.rightUnMapQuanta);
+      d.ints("L.si.uncollected_dims", si.unCollectedStateInfo->quantaStates);
+      vector<int> o2n, o2n_begin(1, 0);
+      for (size_t q = 0; q < si.oldToNewState.size(); ++q) { o2n.insert(o2n.end(), si.oldToNewState[q].begin(), si.oldToNewState[q].end()); o2n_begin.push_back((int)o2n.size()); }
+      d.ints("L.si.old_to_new", o2n); d.ints("L.si.old_to_new_begin", o2n_begin);
+      d.ints("L.si.left_is_LL", vector<int>{si.leftStateInfo == &nl.get_leftBlock()->get_stateInfo() ? 1 : 0});
+      dump_block(d, "LA.", nl);    // the enlarged block with EVERY operator type (the hot-path subset is "L.")
+    }
     Wavefunction w; w.initialise(dmrginp.effective_molecule_quantum_vec(), &big, onedot);
     vector<int> allowed;
     for (int l = 0; l < w.nrows(); ++l) for (int r = 0; r < w.ncols(); ++r) allowed.push_back(w.allowed(l, r) ? 1 : 0);

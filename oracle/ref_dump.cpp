@@ -219,6 +219,17 @@ void wrap_RenormaliseFrom(SpinBlock* self, vector<double>& energies, vector<doub
       d.ints("L.si.old_to_new", o2n); d.ints("L.si.old_to_new_begin", o2n_begin);
       d.ints("L.si.left_is_LL", vector<int>{si.leftStateInfo == &nl.get_leftBlock()->get_stateInfo() ? 1 : 0});
       dump_block(d, "LA.", nl);    // the enlarged block with EVERY operator type (the hot-path subset is "L.")
+      // integrals as the reference's own accessors return them (reordered orbitals), spatial indices: v1[i][j] = v_1(2i,2j),
+      // v2[i][j][k][l] = v_2(2i,2j,2k,2l)
+      const int idx = big.get_integralIndex();
+      const int n = (int)dmrginp.spin_orbs_symmetry().size() / 2;
+      vector<double> h1((size_t)n * n), h2((size_t)n * n * n * n);
+      for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) h1[(size_t)i * n + j] = v_1[idx](2 * i, 2 * j);
+      for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) for (int k = 0; k < n; ++k) for (int l = 0; l < n; ++l)
+        h2[(((size_t)i * n + j) * n + k) * n + l] = v_2[idx](2 * i, 2 * j, 2 * k, 2 * l);
+      d.dbls("v1", h1, {(uint64_t)n, (uint64_t)n});
+      d.dbls("v2", h2, {(uint64_t)n, (uint64_t)n, (uint64_t)n, (uint64_t)n});
+      d.dbls("screen_tol", vector<double>{dmrginp.oneindex_screen_tol(), dmrginp.twoindex_screen_tol()});
     }
     Wavefunction w; w.initialise(dmrginp.effective_molecule_quantum_vec(), &big, onedot);
     vector<int> allowed;

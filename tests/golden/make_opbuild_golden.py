@@ -36,7 +36,7 @@ def main():
             print(out.stdout[-2000:], out.stderr[-2000:]); raise SystemExit("reference run failed for " + name)
         for c in calls:
             rec = dumpio.read_records(os.path.join(work, "dump", "site%d.bin" % c))
-            keep = {k: v for k, v in rec.items() if k.startswith(("LL.", "LR.", "LA.", "L.si.")) or k in ("meta", "sym", "spin_orbs_symmetry", "L.q", "L.dims", "L.sites")}
+            keep = {k: v for k, v in rec.items() if k.startswith(("LL.", "LR.", "LA.", "L.si.")) or k in ("meta", "sym", "spin_orbs_symmetry", "L.q", "L.dims", "L.sites", "v1", "v2", "screen_tol")}
             dst = os.path.join(HERE, "opbuild_%s_call%d.npz" % (name, c))
             np.savez_compressed(dst, **keep)
             print(name, c, "LL ops %d, LR ops %d, LA ops %d, %.1f kB" % (int(rec["LL.nops"][0]), int(rec["LR.nops"][0]), int(rec["LA.nops"][0]), os.path.getsize(dst) / 1e3))

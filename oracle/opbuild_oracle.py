@@ -13,8 +13,12 @@ Restated (file:line under the reference root):
                                                                reference assumes the right factor is 1 x 1, which it is for a one-site dot)
     SparseMatrix::allocate                                     BaseOperator.C:123-145
     Cre::build, CreDes::build, CreCre::build, Overlap::build   Operators.C:453-487, 624-691, 847-900, 2597-2625
-The complementary operators (CreDesComp, DesDesComp, CreCreDesComp: Operators.C:1059-2320) and Ham::build (:2322-2395) are sums of
-the same two primitives weighted by one- and two-electron integrals; they are the next part to restate.
+    TensorOp (spin-coupled operator strings)                   tensor_operator.h:27-289
+    SparseMatrix::calcCompfactor                               Operators.C:87-137
+    CreDesComp::build, DesDesComp::build                       Operators.C:1059-1194, 1472-1616 (integral-weighted child products)
+    CreCreDesComp::build -> opxop::cxcdcomp / dxcccomp         Operators.C:1905-1966, opxop.C:376-532
+    Ham::build -> opxop::cxcddcomp / cdxcdcomp / ddxcccomp     Operators.C:2322-2395, opxop.C:22-143
+i.e. EVERY operator type an energy sweep carries on an enlarged block.
 """
 from __future__ import annotations
 
@@ -240,3 +244,269 @@ def build_normal_operator(pi: ProductInfo, ref_op: O.Op) -> O.Op:
     if ref_op.optype == OVERLAP:
         return build_overlap(pi)
     raise ValueError("operator type %d is not restated yet" % ref_op.optype)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# complementary operators: spin-coupled operator strings (TensorOp, tensor_operator.h) contracted with the integrals
+# (SparseMatrix::calcCompfactor, Operators.C:87-137), then the same TensorProduct as above with that scalar.
+# Spin-adapted, abelian point group (irreps are bit patterns, product = XOR, one row per irrep).
+# ----------------------------------------------------------------------------------------------------------------------
+class Integrals:
+    """v_1 / v_2 as the reference's accessors return them for SPIN-orbital indices (IntegralMatrix.C:32-46, 312-333, rhf): zero unless
+    the spins of (i,k) and of (j,l) match, else the spatial value.  Spatial arrays come from the fixture (reordered orbitals)."""
+
+    def __init__(self, v1, v2, orbital_irreps, screen_tol=(1e-20, 1e-20)):
+        self.h1, self.h2 = np.asarray(v1), np.asarray(v2)
+        self.irreps = [int(x) for x in orbital_irreps]       # per spatial orbital
+        self.one_tol, self.two_tol = float(screen_tol[0]), float(screen_tol[1])
+
+    def v1(self, i, j):
+        return 0.0 if (i & 1) != (j & 1) else float(self.h1[i // 2, j // 2])
+
+    def v2(self, i, j, k, l):
+        if (i & 1) != (k & 1) or (j & 1) != (l & 1):
+            return 0.0
+        return float(self.h2[i // 2, j // 2, k // 2, l // 2])
+
+    @staticmethod
+    def from_record(rec):
+        sos = rec["spin_orbs_symmetry"]
+        return Integrals(rec["v1"], rec["v2"], [int(sos[2 * i]) for i in range(len(sos) // 2)], rec["screen_tol"])
+
+
+class TensorOp:
+    """tensor_operator.h:27-354: a spin tensor operator as coefficient vectors (one per Sz component, index (Spin - sz)/2) over
+    products of spin-orbital creation (+1) / destruction (-1) operators."""
+
+    def __init__(self, k=None, sign=None, ints: Integrals = None):
+        self.empty = True
+        self.spin, self.irrep, self.szops, self.opindices, self.optypes = 0, 0, [], [], []
+        if k is None:
+            return
+        K = 2 * k                                                       # spatial_to_spin
+        ind = [K + 1, K + 0] if sign < 0 else [K + 0, K + 1]            # :58-66
+        self.empty = False
+        self.spin = 1
+        self.irrep = ints.irreps[k]                                     # abelian: -irrep == irrep
+        self.optypes = [sign]
+        self.szops = [[sign * 1.0, 0.0], [0.0, 1.0]]                    # :95-99
+        self.opindices = [[ind[0]], [ind[1]]]
+
+    def dn(self):
+        return sum(self.optypes)
+
+    def product(self, other: "TensorOp", pspin: int, pirrep: int) -> "TensorOp":
+        """TensorOp::product tensor_operator.h:196-289 (`identical` is forced to false there)."""
+        out = TensorOp()
+        if pspin < abs(self.spin - other.spin) or pspin > self.spin + other.spin:
+            raise ValueError("cannot combine spins %d and %d to %d" % (self.spin, other.spin, pspin))
+        if (self.irrep ^ other.irrep) != pirrep:
+            return out                                                  # empty
+        out.empty = False
+        out.optypes = self.optypes + other.optypes
+        out.opindices = [a + b for a in self.opindices for b in other.opindices]
+        n2 = len(other.opindices)
+        out.szops = [[0.0] * len(out.opindices) for _ in range(pspin + 1)]
+        for sz in range(pspin, -pspin - 1, -2):
+            dst = out.szops[(pspin - sz) // 2]
+            for sz1 in range(self.spin, -self.spin - 1, -2):
+                for sz2 in range(other.spin, -other.spin - 1, -2):
+                    cleb = O.clebsch(self.spin, sz1, other.spin, sz2, pspin, sz)
+                    if abs(cleb) <= 1e-14:
+                        continue
+                    v1, v2 = self.szops[(self.spin - sz1) // 2], other.szops[(other.spin - sz2) // 2]
+                    for i, a in enumerate(v1):
+                        for j, b in enumerate(v2):
+                            dst[i * n2 + j] += cleb * a * b
+        out.spin, out.irrep = pspin, pirrep
+        return out
+
+
+def calc_compfactor(op1: TensorOp, op2: TensorOp, comp: str, ints: Integrals) -> float:
+    """SparseMatrix::calcCompfactor(op1, op2, comp, v_2, integralIndex) Operators.C:87-137 (comp in CD, DD, CCD, CDD, C)."""
+    factor = 0.0
+    c1 = op1.szops[0]
+    for sz2 in range(-op2.spin, op2.spin + 1, 2):
+        c2 = op2.szops[(op2.spin - sz2) // 2]
+        cleb = O.clebsch(op1.spin, op1.spin, op2.spin, sz2, 0, 0)
+        if (op1.irrep ^ op2.irrep) != 0:
+            cleb = 0.0
+        if abs(cleb) <= 1e-14:
+            continue
+        for i1, a in enumerate(c1):
+            for i2, b in enumerate(c2):
+                if a == 0.0 or b == 0.0:
+                    continue
+                I1, I2 = op1.opindices[i1], op2.opindices[i2]
+                if comp == "CD":
+                    t = 0.5 * (-ints.v2(I1[0], I2[0], I2[1], I1[1]) - ints.v2(I2[0], I1[0], I1[1], I2[1])
+                               + ints.v2(I2[0], I1[0], I2[1], I1[1]) + ints.v2(I1[0], I2[0], I1[1], I2[1]))
+                elif comp == "DD":
+                    t = 0.5 * ints.v2(I1[0], I1[1], I2[1], I2[0])
+                elif comp == "CCD":
+                    t = 0.5 * (ints.v2(I1[0], I1[1], I2[0], I1[2]) - ints.v2(I1[1], I1[0], I2[0], I1[2]))
+                elif comp == "CDD":
+                    t = 0.5 * (ints.v2(I2[0], I1[0], I1[2], I1[1]) - ints.v2(I1[0], I2[0], I1[2], I1[1]))
+                elif comp == "C":
+                    t = 0.5 * ints.v1(I1[0], I2[0])
+                else:
+                    raise ValueError(comp)
+                factor += t * a * b / cleb
+        break      # `found`: only the first Sz component with a non-vanishing coupling is used
+    return factor
+
+
+def _carry_over(pi, optype, i_j, dq, c):
+    """The part of a complementary operator that already lives on one child: comp(L) x 1 and 1 x comp(R) (Operators.C:1076-1101)."""
+    L, R = pi.left, pi.right
+    if _has(L, optype, i_j):
+        _product_or_trace(pi, _find(L, optype, i_j, dq), True, c)
+    if len(R.sites) == 0:
+        return False
+    if _has(R, optype, i_j):
+        tensor_product(pi, _overlap(L), O.View(_find(R, optype, i_j, dq)), True, c)
+    return True
+
+
+def build_credescomp(pi: ProductInfo, i: int, j: int, comp: int, dq, ints: Integrals) -> O.Op:
+    """CreDesComp::build Operators.C:1059-1194 (non-BCS, blocks without explicit DES operators)."""
+    c = allocate(pi, CRE_DESCOMP, (i, j), comp, dq, False)
+    spin, sym = dq[1], dq[2]
+    CD1 = TensorOp(i, 1, ints).product(TensorOp(j, -1, ints), spin, sym)          # the operator to be complemented
+    if not _carry_over(pi, CRE_DESCOMP, (i, j), dq, c):
+        return c
+    L, R = pi.left, pi.right
+    for k in L.sites:
+        for l in R.sites:
+            have = _has(L, CRE, (k,)) and _has(R, CRE, (l,))
+            CD2 = TensorOp(k, 1, ints).product(TensorOp(l, -1, ints), spin, sym)
+            if not CD2.empty:
+                s = calc_compfactor(CD1, CD2, "CD", ints)
+                if have and abs(s) > ints.two_tol:                                        # c+_k(L) x d_l(R)
+                    tensor_product(pi, O.View(_find(L, CRE, (k,))), O.View(_find(R, CRE, (l,)), True), True, c, s)
+            CD2 = TensorOp(l, 1, ints).product(TensorOp(k, -1, ints), spin, sym)
+            if not CD2.empty:
+                s = calc_compfactor(CD1, CD2, "CD", ints)
+                if have and abs(s) > ints.two_tol:                                        # c+_l(R) x d_k(L)
+                    op1, op2 = _find(R, CRE, (l,)), _find(L, CRE, (k,))
+                    parity = O.commute_parity(tuple(op1.dq), O.neg(tuple(op2.dq)), tuple(dq))
+                    tensor_product(pi, O.View(op1), O.View(op2, True), False, c, s * parity)
+    return c
+
+
+def build_desdescomp(pi: ProductInfo, i: int, j: int, comp: int, dq, ints: Integrals) -> O.Op:
+    """DesDesComp::build Operators.C:1472-1616 (non-BCS, blocks without explicit DES operators)."""
+    c = allocate(pi, DES_DESCOMP, (i, j), comp, dq, False)
+    spin, sym = dq[1], dq[2]
+    CC1 = TensorOp(i, 1, ints).product(TensorOp(j, 1, ints), spin, sym)
+    if not _carry_over(pi, DES_DESCOMP, (i, j), dq, c):
+        return c
+    L, R = pi.left, pi.right
+    for k in L.sites:
+        for l in R.sites:
+            DD2 = TensorOp(k, -1, ints).product(TensorOp(l, -1, ints), spin, sym)
+            if DD2.empty:
+                continue
+            s = calc_compfactor(CC1, DD2, "DD", ints)
+            s2 = calc_compfactor(CC1, TensorOp(l, -1, ints).product(TensorOp(k, -1, ints), spin, sym), "DD", ints)
+            if _has(L, CRE, (k,)) and _has(R, CRE, (l,)) and abs(s) + abs(s2) > ints.two_tol:
+                op1, op2 = _find(L, CRE, (k,)), _find(R, CRE, (l,))
+                parity = O.commute_parity(O.neg(tuple(op1.dq)), O.neg(tuple(op2.dq)), tuple(dq))
+                s += parity * s2
+                if abs(s) > ints.two_tol:
+                    tensor_product(pi, O.View(op1, True), O.View(op2, True), True, c, s)
+    return c
+
+
+def build_operator(pi: ProductInfo, ref_op: O.Op, ints: Integrals = None, hubbard=False) -> O.Op:
+    """Any restated operator type of the enlarged block."""
+    if ref_op.optype == CRE_CRE_DESCOMP:
+        return build_crecredescomp(pi, ref_op.orbs[0], ref_op.dq, ints, hubbard)
+    if ref_op.optype == HAM:
+        return build_ham(pi, hubbard)
+    if ref_op.optype == CRE_DESCOMP:
+        return build_credescomp(pi, ref_op.orbs[0], ref_op.orbs[1], ref_op.comp, ref_op.dq, ints)
+    if ref_op.optype == DES_DESCOMP:
+        return build_desdescomp(pi, ref_op.orbs[0], ref_op.orbs[1], ref_op.comp, ref_op.dq, ints)
+    return build_normal_operator(pi, ref_op)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# three-index complementary operator and the Hamiltonian of the enlarged block: sums over products of one child's normal
+# operators with the other child's two- / three-index complementary operators (no integrals appear explicitly here)
+# ----------------------------------------------------------------------------------------------------------------------
+def _recoupling(j2, j1, j21, phase_twice):
+    """pow(-1, int(phase/2)) * sixj(j2, j1, j21, 1, 0, j2) * sqrt((j21+1)(j2+1))   (opxop.C:395, 421, 471, 504)."""
+    return (-1.0) ** int(phase_twice / 2) * O.six_j(j2, j1, j21, 1, 0, j2) * np.sqrt((j21 + 1.0) * (j2 + 1.0))
+
+
+def _comps(block: O.Block, optype, orbs):
+    return [op for op in block.ops if op.optype == optype and op.orbs == tuple(orbs)]
+
+
+def _cxcdcomp(pi, other_is_left, op1, I, c, scale):
+    """opxop::cxcdcomp (operator form) opxop.C:376-445: c += c+_j (loop side) x CDcomp_{jI} or its transpose (other side)."""
+    other = pi.left if other_is_left else pi.right
+    j = op1.orbs[0]
+    j1, j21 = op1.dq[1], c.dq[1]
+    if j >= I:
+        for op2 in _comps(other, CRE_DESCOMP, (j, I)):
+            j2 = op2.dq[1]
+            f = _recoupling(j2, j1, j21, 2 + j2)
+            if not other_is_left:
+                f *= O.commute_parity(tuple(op1.dq), tuple(op2.dq), tuple(c.dq))
+            tensor_product(pi, O.View(op2), O.View(op1), other_is_left, c, f * scale)
+    else:
+        for op2 in _comps(other, CRE_DESCOMP, (I, j)):
+            j2 = op2.dq[1]
+            f = _recoupling(j2, j1, j21, 1 + 1 + 0 + j2)
+            if not other_is_left:
+                f *= O.commute_parity(tuple(op1.dq), O.neg(tuple(op2.dq)), tuple(c.dq))
+            f *= -1.0 if j2 == 2 else 1.0                                  # TensorOp::getTransposeFactorCD, abelian
+            tensor_product(pi, O.View(op2, True), O.View(op1), other_is_left, c, f * scale)
+
+
+def _dxcccomp(pi, other_is_left, op1, K, c, scale, ints: Integrals):
+    """opxop::dxcccomp (operator form, blocks without DES operators) opxop.C:447-532: c += d_j (loop side) x DDcomp_{kj}^T (other side)."""
+    other = pi.left if other_is_left else pi.right
+    k, i, transpose = K, op1.orbs[0], False
+    if k < i:
+        k, i, transpose = i, K, True
+    iq, kq = (1, 1, ints.irreps[i]), (1, 1, ints.irreps[k])
+    j1, j21 = op1.dq[1], c.dq[1]
+    for op2 in _comps(other, DES_DESCOMP, (k, i)):
+        topq = O.neg(tuple(op2.dq))
+        j2 = op2.dq[1]
+        f = _recoupling(j2, j1, j21, 2 + j2)
+        f *= -1.0 if j2 == 0 else 1.0                                      # TensorOp::getTransposeFactorDD, abelian
+        if transpose:
+            f *= O.commute_parity(iq, kq, topq)
+        if other_is_left is False:                                         # loop block is the left child
+            f *= O.commute_parity(O.neg(iq), topq, kq)
+        tensor_product(pi, O.View(op2, True), O.View(op1, True), other_is_left, c, f * scale)
+
+
+def build_crecredescomp(pi: ProductInfo, k: int, dq, ints: Integrals, hubbard=False) -> O.Op:
+    """CreCreDesComp::build Operators.C:1905-1966."""
+    c = allocate(pi, CRE_CRE_DESCOMP, (k,), 0, dq, True)
+    if not _carry_over(pi, CRE_CRE_DESCOMP, (k,), dq, c) or hubbard:
+        return c
+    L, R = pi.left, pi.right
+    loop_is_left = L.loop                                                  # assignloopblock BaseOperator.C:298-304
+    loopb, otherb = (L, R) if loop_is_left else (R, L)
+    if any(op.optype == CRE_DESCOMP for op in loopb.ops):
+        for src, holder_is_left in ((loopb, not loop_is_left), (otherb, loop_is_left)):
+            for op1 in [op for op in src.ops if op.optype == CRE]:
+                _cxcdcomp(pi, holder_is_left, op1, k, c, 1.0)
+                _dxcccomp(pi, holder_is_left, op1, k, c, 2.0, ints)        # 2.0: CCcomp_ij = -CCcomp_ji
+    return c
+
+
+def build_ham(pi: ProductInfo, hubbard=False) -> O.Op:
+    """Ham::build Operators.C:2322-2395: H_L x 1 + 1 x H_R + the same operator pairs SpinBlock::multiplyH applies to a wavefunction
+    (opxop.C:22-143 are the operator forms of :155-285), accumulated with TensorProduct instead of TensorMultiply."""
+    c = allocate(pi, HAM, (), 0, (0, 0, 0), False)
+    big = O.Big(left=pi.left, right=pi.right, psi_dq=(0, 0, 0), core_energy=0.0, hubbard=hubbard)
+    for lop, rop, scale in O.h_terms(big):
+        tensor_product(pi, lop, rop, True, c, scale)
+    return c

@@ -60,3 +60,46 @@ def test_fixtures_exercise_cross_child_products():
         lsites = set(pi.left.sites)
         found += sum(1 for op in ref.ops if op.optype in (B.CRE_CRE, B.CRE_DES) and len({o in lsites for o in op.orbs}) == 2)
     assert found >= 4
+
+
+def test_two_index_complementary_operators_match_reference(record):
+    """CreDesComp / DesDesComp: integral-weighted sums of child products (TensorOp coupling + calcCompfactor restated)."""
+    rec, pi, ref = record
+    ints = B.Integrals.from_record(rec)
+    n = 0
+    for op in ref.ops:
+        if op.optype not in (B.CRE_DESCOMP, B.DES_DESCOMP):
+            continue
+        mine = B.build_operator(pi, op, ints)
+        assert np.array_equal(mine.allowed, op.allowed), (op.optype, op.orbs, op.comp)
+        for key, blk in op.blocks.items():
+            scale = max(1.0, float(np.abs(blk).max()))
+            assert np.abs(mine.blocks[key] - blk).max() <= 1e-12 * scale, (op.optype, op.orbs, op.comp, key, np.abs(mine.blocks[key] - blk).max())
+        n += 1
+    if rec["LA.nops"][0] > 10:      # the Hubbard fixture carries no two-index operators
+        assert n >= 4
+
+
+def test_three_index_complementary_and_hamiltonian_match_reference(record):
+    """CreCreDesComp (recoupled products with the other child's two-index complementary operators) and Ham of the enlarged block."""
+    rec, pi, ref = record
+    ints = B.Integrals.from_record(rec)
+    hubbard = int(rec["meta"][7]) == B.O.HUBBARD_HAM
+    n = {B.CRE_CRE_DESCOMP: 0, B.HAM: 0}
+    for op in ref.ops:
+        if op.optype not in n:
+            continue
+        mine = B.build_operator(pi, op, ints, hubbard)
+        assert np.array_equal(mine.allowed, op.allowed), (op.optype, op.orbs)
+        for key, blk in op.blocks.items():
+            scale = max(1.0, float(np.abs(blk).max()))
+            err = np.abs(mine.blocks[key] - blk).max()
+            assert err <= 1e-12 * scale, (op.optype, op.orbs, key, err)
+        n[op.optype] += 1
+    assert n[B.HAM] == 1 and n[B.CRE_CRE_DESCOMP] >= 1, n
+
+
+def test_every_operator_of_the_enlarged_block_is_restated(record):
+    rec, pi, ref = record
+    types = {op.optype for op in ref.ops}
+    assert types <= {B.HAM, B.CRE, B.CRE_CRE, B.DES_DESCOMP, B.CRE_DES, B.CRE_DESCOMP, B.CRE_CRE_DESCOMP, B.OVERLAP}, types

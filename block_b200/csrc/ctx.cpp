@@ -189,6 +189,15 @@ struct b2d_ctx {
   double class_ms[2][B2D_NUM_TILE_CLASSES] = {};
   int class_launches[2][B2D_NUM_TILE_CLASSES] = {};
 
+  // enlarged-block operator construction: product StateInfo of side[0] (x) side[1] and the operators built on it
+  struct Product {
+    Side side;                              // collected sectors of the enlarged block + the operators built so far
+    std::vector<int> lmap, rmap, unc_dims;  // leftUnMapQuanta / rightUnMapQuanta / unCollectedStateInfo->quantaStates
+    std::vector<std::vector<int>> old_to_new;
+    bool set = false;
+  } product;
+  DevBuf kron_tasks;
+
   std::map<std::vector<int>, PsiLayout> layouts;   // wavefunction layouts for other target quanta (noise: O.psi sectors)
   DevBuf dm_noise;
   Nccl nccl;
@@ -534,7 +543,7 @@ void b2d_destroy(b2d_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->staging, &ctx->desc_scratch, &ctx->work, &ctx->parts, &ctx->trace_buf, &ctx->eig_work, &ctx->eig_info, &ctx->dm_noise, &ctx->flat_in, &ctx->flat_out, &ctx->psi_blocks, &ctx->diag_tasks,
                       &ctx->diag_begin, &ctx->partials, &ctx->scalars, &ctx->user_pool, &ctx->dav_pool, &ctx->rho, &ctx->eig_g, &ctx->eig_vt,
                       &ctx->eig_vals, &ctx->eig_sweeps, &ctx->sector_desc, &ctx->rot, &ctx->gather_desc, &ctx->gather_rows,
-                      &ctx->rotated_arena, &ctx->dsched.buf, &ctx->tile_counter, &ctx->diag_gather, &ctx->diag_pool};
+                      &ctx->rotated_arena, &ctx->dsched.buf, &ctx->tile_counter, &ctx->diag_gather, &ctx->diag_pool, &ctx->kron_tasks};
     for (DevBuf* b : bufs) b->release();
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->pend_pinned) cudaFreeHost(ctx->pend_pinned);
@@ -575,6 +584,7 @@ int b2d_reset(b2d_ctx* ctx) {
   ctx->have_rho = false;
   ctx->rotated = Side(); ctx->rotated_old.clear();
   ctx->layouts.clear();
+  ctx->product = b2d_ctx::Product();
   ctx->timing_valid = false;
   ctx->err.clear();
   return B2D_OK;
@@ -1949,6 +1959,139 @@ int b2d_renormalise_from(b2d_ctx* ctx, int nroots, int guess_slot0, const double
   rc = b2d_diagonalise_dm(ctx, nullptr);                                                                                           // :113 -> rotationmat.C:258
   if (rc) return rc;
   return b2d_select_states(ctx, keep_states, kept_counts, discarded);
+}
+
+// ---- enlarged-block operator construction: TensorProduct / TensorTrace on the device --------------------
+int b2d_set_product_stateinfo(b2d_ctx* ctx, int nq, const int32_t* q, const int32_t* dims, int nunc, const int32_t* lmap, const int32_t* rmap,
+                              const int32_t* unc_dims, const int32_t* old_to_new_begin, const int32_t* old_to_new) {
+  if (!ctx || nq <= 0 || !q || !dims || nunc <= 0 || !lmap || !rmap || !unc_dims || !old_to_new_begin || !old_to_new)
+    return fail(ctx, B2D_ERR_ARG, "b2d_set_product_stateinfo: bad arguments");
+  const Side& L = ctx->side[0];
+  const Side& R = ctx->side[1];
+  if (L.nq == 0 || R.nq == 0) return fail(ctx, B2D_ERR_ARG, "b2d_set_product_stateinfo: set both children first (b2d_set_block)");
+  b2d_ctx::Product P;
+  P.side.nq = nq;
+  P.side.q.assign(q, q + 3 * nq);
+  P.side.dims.assign(dims, dims + nq);
+  P.lmap.assign(lmap, lmap + nunc); P.rmap.assign(rmap, rmap + nunc); P.unc_dims.assign(unc_dims, unc_dims + nunc);
+  P.old_to_new.resize(nq);
+  for (int c = 0; c < nq; ++c) {
+    int sum = 0;
+    for (int k = old_to_new_begin[c]; k < old_to_new_begin[c + 1]; ++k) {
+      const int u = old_to_new[k];
+      if (u < 0 || u >= nunc || lmap[u] < 0 || lmap[u] >= L.nq || rmap[u] < 0 || rmap[u] >= R.nq) return fail(ctx, B2D_ERR_ARG, "b2d_set_product_stateinfo: index out of range");
+      if (unc_dims[u] != L.dims[lmap[u]] * R.dims[rmap[u]]) return fail(ctx, B2D_ERR_ARG, "b2d_set_product_stateinfo: uncollected sector size is not d_left * d_right");
+      if (!qn_allow(&P.side.q[3 * c], L.quantum(lmap[u]), R.quantum(rmap[u]))) return fail(ctx, B2D_ERR_ARG, "b2d_set_product_stateinfo: piece does not couple to its sector");
+      P.old_to_new[c].push_back(u);
+      sum += unc_dims[u];
+    }
+    if (sum != dims[c]) return fail(ctx, B2D_ERR_ARG, "b2d_set_product_stateinfo: pieces do not add up to the sector size");
+  }
+  P.set = true;
+  ctx->product = std::move(P);
+  return B2D_OK;
+}
+
+int b2d_product_op_create(b2d_ctx* ctx, const int32_t* dq, int fermion, int* prod_id) {
+  NEED_DEVICE();
+  if (!ctx->product.set || !dq || !prod_id) return fail(ctx, B2D_ERR_ARG, "b2d_product_op_create: call b2d_set_product_stateinfo first");
+  CU(cudaSetDevice(ctx->device));
+  Side& S = ctx->product.side;
+  OpRec op;
+  memcpy(op.dq, dq, sizeof(op.dq));
+  op.fermion = fermion != 0;
+  op.allowed.assign((size_t)S.nq * S.nq, 0);
+  for (int i = 0; i < S.nq; ++i)                       // SparseMatrix::allocate BaseOperator.C:123-145
+    for (int j = 0; j < S.nq; ++j) op.allowed[(size_t)i * S.nq + j] = qn_allow(S.quantum(i), dq, S.quantum(j)) ? 1 : 0;
+  layout_op(S, op);
+  if (op.dev_size > 0) {
+    CU(arena_alloc(ctx, (size_t)op.dev_size * 8, &op.dev));
+    CU(cudaMemsetAsync(op.dev, 0, (size_t)op.dev_size * 8, ctx->stream));
+  }
+  S.ops.push_back(std::move(op));
+  *prod_id = (int)S.ops.size() - 1;
+  return B2D_OK;
+}
+
+int b2d_product_op_accumulate(b2d_ctx* ctx, int prod_id, int left_op, int left_transposed, int right_op, int right_transposed, double scale) {
+  NEED_DEVICE();
+  b2d_ctx::Product& P = ctx->product;
+  const Side& L = ctx->side[0];
+  const Side& R = ctx->side[1];
+  if (!P.set || prod_id < 0 || prod_id >= (int)P.side.ops.size() || left_op >= (int)L.ops.size() || right_op >= (int)R.ops.size() || (left_op < 0 && right_op < 0))
+    return fail(ctx, B2D_ERR_ARG, "b2d_product_op_accumulate: bad arguments");
+  if (std::fabs(scale) < 1e-20) return B2D_OK;        // TINY, operatorfunctions.C:148
+  { int frc = flush_pending_ops(ctx); if (frc) return frc; }
+  CU(cudaSetDevice(ctx->device));
+  const OpRec& c = P.side.ops[prod_id];
+  const bool trace_l = left_op < 0, trace_r = right_op < 0;      // identity on that child: TensorTrace
+  const OpRec* la = trace_l ? nullptr : &L.ops[left_op];
+  const OpRec* rb = trace_r ? nullptr : &R.ops[right_op];
+  if ((la && la->dev_size > 0 && !la->dev) || (rb && rb->dev_size > 0 && !rb->dev)) return fail(ctx, B2D_ERR_ARG, "b2d_product_op_accumulate: child operator is not resident");
+  View a{&L, la, left_transposed != 0}, b{&R, rb, right_transposed != 0};
+  const int sa = la ? la->dq[1] : 0, sb = rb ? rb->dq[1] : 0, sc = c.dq[1];
+  std::vector<KronTask> tasks;
+  try {
+    for (int cq = 0; cq < P.side.nq; ++cq)
+      for (int cqp = 0; cqp < P.side.nq; ++cqp) {
+        if (!c.allowed[(size_t)cq * P.side.nq + cqp]) continue;
+        int row = 0;
+        for (int oi : P.old_to_new[cq]) {
+          int col = 0;
+          for (int oj : P.old_to_new[cqp]) {
+            const int aq = P.lmap[oi], aqp = P.lmap[oj], bq = P.rmap[oi], bqp = P.rmap[oj];
+            const bool a_ok = trace_l ? aq == aqp : a.allowed(aq, aqp);
+            const bool b_ok = trace_r ? bq == bqp : b.allowed(bq, bqp);
+            if (a_ok && b_ok) {
+              // operatorfunctions.C:205-218 (TensorProduct) / :83-107 (TensorTrace: no get_scaling there)
+              double f = scale * ctx->am.ninej(L.quantum(aqp)[1], R.quantum(bqp)[1], P.side.quantum(cqp)[1], sa, sb, sc, L.quantum(aq)[1], R.quantum(bq)[1],
+                                               P.side.quantum(cq)[1]);
+              if (!trace_l && !trace_r) f *= a.scaling(ctx->am, aq, aqp) * b.scaling(ctx->am, bq, bqp);
+              if (rb && rb->fermion && (L.quantum(aqp)[0] & 1)) f = -f;
+              KronTask k;
+              memset(&k, 0, sizeof(k));
+              k.coef = f;
+              k.a_rows = L.dims[aq]; k.a_cols = L.dims[aqp]; k.b_rows = R.dims[bq]; k.b_cols = R.dims[bqp];
+              if (!trace_l) { k.a = (int64_t)(intptr_t)la->dev + 8 * a.stored_off(aq, aqp); k.lda = a.stored_ld(aq, aqp); k.a_t = a.t ? 1 : 0; }
+              if (!trace_r) { k.b = (int64_t)(intptr_t)rb->dev + 8 * b.stored_off(bq, bqp); k.ldb = b.stored_ld(bq, bqp); k.b_t = b.t ? 1 : 0; }
+              k.dst = (int64_t)(intptr_t)c.dev + 8 * c.off[(size_t)cq * P.side.nq + cqp];
+              k.ldd = pad_ld(P.side.dims[cqp]);
+              k.row0 = row; k.col0 = col;
+              tasks.push_back(k);
+            }
+            col += P.unc_dims[oj];
+          }
+          row += P.unc_dims[oi];
+        }
+      }
+  } catch (const std::exception& e) { return fail(ctx, B2D_ERR_ARG, e.what()); }
+  int rc = upload_desc(ctx, ctx->kron_tasks, tasks.data(), tasks.size() * sizeof(KronTask));
+  if (rc) return rc;
+  CU(launch_kron_scatter((const KronTask*)ctx->kron_tasks.p, (int)tasks.size(), ctx->stream, &ctx->launches));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return B2D_OK;
+}
+
+int64_t b2d_product_op_size(const b2d_ctx* ctx, int prod_id) {
+  if (!ctx || !ctx->product.set || prod_id < 0 || prod_id >= (int)ctx->product.side.ops.size()) return -1;
+  return ctx->product.side.ops[prod_id].packed_size;
+}
+
+int b2d_product_op_download(b2d_ctx* ctx, int prod_id, uint8_t* allowed, double* data) {
+  NEED_DEVICE();
+  if (!ctx->product.set || prod_id < 0 || prod_id >= (int)ctx->product.side.ops.size()) return fail(ctx, B2D_ERR_ARG, "b2d_product_op_download: bad arguments");
+  const Side& S = ctx->product.side;
+  const OpRec& op = S.ops[prod_id];
+  if (allowed) memcpy(allowed, op.allowed.data(), op.allowed.size());
+  if (!data || op.packed_size == 0) return B2D_OK;
+  std::vector<BlockDesc> bd = op_blocks(S, op);
+  CU(ctx->staging.reserve((size_t)op.packed_size * 8));
+  int rc = upload_desc(ctx, ctx->desc_scratch, bd.data(), bd.size() * sizeof(BlockDesc));
+  if (rc) return rc;
+  CU(launch_unpack((const BlockDesc*)ctx->desc_scratch.p, (int)bd.size(), op.dev, (double*)ctx->staging.p, ctx->stream, &ctx->launches));
+  CU(cudaMemcpyAsync(data, ctx->staging.p, (size_t)op.packed_size * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return B2D_OK;
 }
 
 // ---- multi-GPU ----------------------------------------------------------------------------------------------------

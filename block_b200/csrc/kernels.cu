@@ -533,6 +533,33 @@ __global__ void __launch_bounds__(256) diag_kernel(const BlockDesc* __restrict__
   }
 }
 
+// c += coef (a x b) on sub-blocks: one CTA per task; threads run over the destination sub-block with the column index fastest
+// (coalesced stores; A / B elements come from L1/L2 - B is 1 x 1 for a one-site dot).  Tasks of one launch never overlap.
+__global__ void __launch_bounds__(256) kron_scatter_kernel(const KronTask* __restrict__ tasks, int ntasks) {
+  for (int t = blockIdx.x; t < ntasks; t += gridDim.x) {
+    const KronTask k = tasks[t];
+    const double* A = reinterpret_cast<const double*>(k.a);
+    const double* B = reinterpret_cast<const double*>(k.b);
+    double* D = reinterpret_cast<double*>(k.dst);
+    const int rows = k.a_rows * k.b_rows, cols = k.a_cols * k.b_cols;
+    const int64_t n = (int64_t)rows * cols;
+    for (int64_t e = threadIdx.x; e < n; e += blockDim.x) {
+      const int r = (int)(e / cols), c = (int)(e % cols);
+      const int ia = r / k.b_rows, ib = r % k.b_rows, ja = c / k.b_cols, jb = c % k.b_cols;
+      double va, vb;
+      if (A) va = k.a_t ? A[(int64_t)ja * k.lda + ia] : A[(int64_t)ia * k.lda + ja]; else va = ia == ja ? 1.0 : 0.0;
+      if (B) vb = k.b_t ? B[(int64_t)jb * k.ldb + ib] : B[(int64_t)ib * k.ldb + jb]; else vb = ib == jb ? 1.0 : 0.0;
+      D[(int64_t)(k.row0 + r) * k.ldd + k.col0 + c] += k.coef * va * vb;
+    }
+  }
+}
+cudaError_t launch_kron_scatter(const KronTask* tasks, int ntasks, cudaStream_t s, int64_t* launches) {
+  if (ntasks == 0) return cudaSuccess;
+  kron_scatter_kernel<<<min(ntasks, 148 * 16), 256, 0, s>>>(tasks, ntasks);
+  B2D_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
 // gather the diagonals of operator blocks into one compact pool: pool[dst + i] = *(src + i * stride)
 __global__ void gather_diag_kernel(const DiagGather* __restrict__ items, int nitems, double* __restrict__ pool) {
   for (int it = blockIdx.x; it < nitems; it += gridDim.x) {

@@ -62,6 +62,18 @@ cudaError_t launch_sum_parts(double* dst, const double* parts, int nparts, int64
 // G: n x ldg (upper triangle G[j][i], i >= j, valid; mirrored inside); theta[n] ascending; alpha[i*ldg + j] = component i of eigenvector j
 cudaError_t launch_subspace_eig(const double* G, int n, int ldg, double* theta, double* alpha, cudaStream_t s, int64_t* launches);
 
+// enlarged-block operator construction (operatorfunctions::TensorProduct / TensorTrace, operatorfunctions.C:19-254 -> MatrixTensorProduct
+// MatrixBLAS.C:125-200): dst[row0 + ia * b_rows + ib][col0 + ja * b_cols + jb] += coef * opA(ia, ja) * opB(ib, jb), one task per
+// (destination block, uncollected row piece, uncollected column piece).  HBM-bound scatter: A and B sub-blocks read once, dst written once.
+struct KronTask {
+  int64_t a, b;        // absolute byte addresses of the STORED blocks; 0 = identity of size a_rows / b_rows (TensorTrace)
+  int64_t dst;         // absolute byte address of the destination block
+  double coef;
+  int32_t a_rows, a_cols, lda, a_t;   // op(A) is a_rows x a_cols; a_t: stored transposed (a_cols x a_rows, leading dimension lda)
+  int32_t b_rows, b_cols, ldb, b_t;
+  int32_t row0, col0, ldd, pad;
+};
+cudaError_t launch_kron_scatter(const KronTask* tasks, int ntasks, cudaStream_t s, int64_t* launches);
 // diagonals of operator sector blocks gathered into a compact pool (stride ld + 1 -> 1) before diag(H) reads them thousands of times
 struct DiagGather {
   int64_t src;      // absolute byte address of the first diagonal element

@@ -396,6 +396,71 @@ class SpinBlock:
         return out[:n]
 
 
+class ProductBlock:
+    """Construction of the operators of an ENLARGED block (left child x right child) on the device: the TensorProduct / TensorTrace
+    scatter of operatorfunctions.C:19-254 (first device step).  The caller decides which products enter an operator."""
+
+    def __init__(self, left: BlockSpec, right: BlockSpec, q, dims, lmap, rmap, unc_dims, old_to_new, device=0):
+        self.lib = _lib.load()
+        self._ctx = C.c_void_p()
+        if self.lib.b2d_create(int(device), C.byref(self._ctx)):
+            raise B2DError("b2d_create: " + self.lib.b2d_last_error(None).decode())
+        self.op_ids = [[], []]
+        for side, blk in enumerate((left, right)):
+            bq = np.ascontiguousarray(blk.q, dtype=np.int32).reshape(-1, 3)
+            bd = np.ascontiguousarray(blk.dims, dtype=np.int32)
+            sites = np.ascontiguousarray(blk.sites, dtype=np.int32)
+            self._ck(self.lib.b2d_set_block(self._ctx, side, len(bd), _p(bq, _lib.c_i32p), _p(bd, _lib.c_i32p), int(blk.loop), len(sites), _p(sites, _lib.c_i32p)))
+            for op in blk.ops:
+                self.op_ids[side].append(SpinBlock._add_op(self, side, op))
+        q = np.ascontiguousarray(q, dtype=np.int32).reshape(-1, 3)
+        self.dims = np.ascontiguousarray(dims, dtype=np.int32)
+        lmap, rmap, unc = (np.ascontiguousarray(x, dtype=np.int32) for x in (lmap, rmap, unc_dims))
+        begin = np.zeros(len(old_to_new) + 1, np.int32)
+        begin[1:] = np.cumsum([len(x) for x in old_to_new])
+        flat = np.ascontiguousarray([u for piece in old_to_new for u in piece], dtype=np.int32)
+        self._ck(self.lib.b2d_set_product_stateinfo(self._ctx, len(self.dims), _p(q, _lib.c_i32p), _p(self.dims, _lib.c_i32p), len(unc), _p(lmap, _lib.c_i32p),
+                                                     _p(rmap, _lib.c_i32p), _p(unc, _lib.c_i32p), _p(begin, _lib.c_i32p), _p(flat, _lib.c_i32p)))
+
+    def _ck(self, rc):
+        if rc:
+            raise B2DError("[%d] %s" % (rc, self.lib.b2d_last_error(self._ctx).decode()))
+
+    def create(self, dq, fermion):
+        """SparseMatrix::allocate on the enlarged block: returns the id of a zero-filled operator with deltaQuantum dq."""
+        q = np.asarray(dq, dtype=np.int32)
+        pid = C.c_int(-1)
+        self._ck(self.lib.b2d_product_op_create(self._ctx, _p(q, _lib.c_i32p), int(bool(fermion)), C.byref(pid)))
+        return pid.value
+
+    def accumulate(self, prod_id, left_op, right_op, left_transposed=False, right_transposed=False, scale=1.0):
+        """c += scale (a x b); left_op / right_op None = identity on that child (TensorTrace)."""
+        self._ck(self.lib.b2d_product_op_accumulate(self._ctx, int(prod_id), -1 if left_op is None else int(left_op), int(bool(left_transposed)),
+                                                     -1 if right_op is None else int(right_op), int(bool(right_transposed)), float(scale)))
+
+    def download(self, prod_id):
+        nq = len(self.dims)
+        n = int(self.lib.b2d_product_op_size(self._ctx, int(prod_id)))
+        allowed = np.zeros((nq, nq), np.uint8)
+        data = np.empty(max(n, 1))
+        self._ck(self.lib.b2d_product_op_download(self._ctx, int(prod_id), _p(allowed, _lib.c_u8p), _p(data, _lib.c_f64p)))
+        return allowed.astype(bool), data[:n]
+
+    def kernel_launches(self):
+        return int(self.lib.b2d_kernel_launches(self._ctx))
+
+    def close(self):
+        if getattr(self, "_ctx", None) is not None and self._ctx.value:
+            self.lib.b2d_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def block_spec_from_record(rec, prefix) -> BlockSpec:
     """Build a BlockSpec from a dump record of the reference (oracle/ref_dump.cpp format; tests/golden/*.npz)."""
     q = np.asarray(rec[prefix + "q"], dtype=np.int32).reshape(-1, 3)

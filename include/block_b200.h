@@ -239,6 +239,32 @@ int b2d_renormalise_from(b2d_ctx* ctx, int nroots, int guess_slot0, const double
                          int keep_states, int deflation_min, int deflation_max, double noise, double* energies,
                          int32_t* kept_counts, double* discarded, int* n_multiply);
 
+/* ---- construction of enlarged-block operators on the device (first device step) --------------------
+ * operatorfunctions::TensorProduct(ablock, a, b, cblock, cstateinfo, c, scale) operatorfunctions.C:146-254 and
+ * operatorfunctions::TensorTrace operatorfunctions.C:19-117 (-> MatrixTensorProduct MatrixBLAS.C:125-200): the scatter every
+ * Op::build of an enlarged block is made of (Operators.C:453-2395).  Here side 0 / side 1 of the context are the two CHILDREN of the
+ * enlarged block (renormalised block and dot), described with b2d_set_block / b2d_add_op as usual; no b2d_plan is needed.
+ * Which products enter an operator, and their integral factors, are still decided by the caller (the reference's host code or
+ * the restatement in oracle/opbuild_oracle.py that the test drives this with). */
+
+/* Product StateInfo of the enlarged block after CollectQuanta (StateInfo.h:113-147): collected quanta q (nq x 3) and sizes;
+ * per UNCOLLECTED sector u its left / right child sectors (leftUnMapQuanta, rightUnMapQuanta) and size
+ * (unCollectedStateInfo->quantaStates); per collected sector c its pieces old_to_new[old_to_new_begin[c] .. old_to_new_begin[c+1])
+ * (oldToNewState), in the order in which they are concatenated. */
+int b2d_set_product_stateinfo(b2d_ctx* ctx, int nq, const int32_t* q, const int32_t* dims, int nunc, const int32_t* lmap,
+                              const int32_t* rmap, const int32_t* unc_dims, const int32_t* old_to_new_begin,
+                              const int32_t* old_to_new);
+/* SparseMatrix::allocate(stateinfo) BaseOperator.C:123-145 for an operator with deltaQuantum dq on the enlarged block: zero-filled
+ * device blocks where q_i is in dq (+) q_j. */
+int b2d_product_op_create(b2d_ctx* ctx, const int32_t* dq, int fermion, int* prod_id);
+/* c += scale * (a x b), a = operator left_op of the left child (or its Transposeview), b = operator right_op of the right child;
+ * left_op < 0 or right_op < 0: the identity on that child (TensorTrace).  9j coefficient, Transposeview scalings and the fermion
+ * sign of operatorfunctions.C:205-218 are applied per sub-block. */
+int b2d_product_op_accumulate(b2d_ctx* ctx, int prod_id, int left_op, int left_transposed, int right_op, int right_transposed,
+                              double scale);
+int64_t b2d_product_op_size(const b2d_ctx* ctx, int prod_id);
+int b2d_product_op_download(b2d_ctx* ctx, int prod_id, uint8_t* allowed, double* data);   /* host layout of b2d_add_op */
+
 /* ---- multi-GPU: partition of operator terms, NCCL all-reduce of the partial sigma --------------------------- */
 
 int b2d_nccl_unique_id(uint8_t* id128);                                   /* rank 0; broadcast out of band */

@@ -15,6 +15,7 @@
 #include "../../include/block_b200.h"
 #include "kernels.h"
 #include "plan.hpp"
+#include "opbuild.hpp"
 
 using namespace b2d;
 
@@ -197,6 +198,7 @@ struct b2d_ctx {
     bool set = false;
   } product;
   DevBuf kron_tasks;
+  Integrals integrals;                      // one- / two-electron integrals for the complementary operators (b2d_set_integrals)
 
   std::map<std::vector<int>, PsiLayout> layouts;   // wavefunction layouts for other target quanta (noise: O.psi sectors)
   DevBuf dm_noise;
@@ -585,7 +587,7 @@ int b2d_reset(b2d_ctx* ctx) {
   ctx->rotated = Side(); ctx->rotated_old.clear();
   ctx->layouts.clear();
   ctx->product = b2d_ctx::Product();
-  ctx->timing_valid = false;
+  ctx->timing_valid = false;   // (the integrals belong to the whole calculation: b2d_reset keeps them)
   ctx->err.clear();
   return B2D_OK;
 }
@@ -2069,6 +2071,59 @@ int b2d_product_op_accumulate(b2d_ctx* ctx, int prod_id, int left_op, int left_t
   if (rc) return rc;
   CU(launch_kron_scatter((const KronTask*)ctx->kron_tasks.p, (int)tasks.size(), ctx->stream, &ctx->launches));
   CU(cudaStreamSynchronize(ctx->stream));
+  return B2D_OK;
+}
+
+int b2d_set_integrals(b2d_ctx* ctx, int norbs, const double* v1, const double* v2, const int32_t* orbital_irreps, double one_tol, double two_tol) {
+  if (!ctx || norbs <= 0 || !v1 || !v2 || !orbital_irreps) return fail(ctx, B2D_ERR_ARG, "b2d_set_integrals: bad arguments");
+  Integrals& I = ctx->integrals;
+  I.n = norbs;
+  I.h1.assign(v1, v1 + (size_t)norbs * norbs);
+  I.h2.assign(v2, v2 + (size_t)norbs * norbs * norbs * norbs);
+  I.irrep.assign(orbital_irreps, orbital_irreps + norbs);
+  I.one_tol = one_tol; I.two_tol = two_tol;
+  I.set = true;
+  return B2D_OK;
+}
+
+static int plan_enlarged_op(b2d_ctx* ctx, int optype, int norb, const int32_t* orbs, const int32_t* dq, int hubbard, std::vector<ProductCall>& calls) {
+  if (!ctx || !dq || norb < 0 || norb > 2 || (norb > 0 && !orbs)) return fail(ctx, B2D_ERR_ARG, "enlarged-block operator: bad arguments");
+  if (ctx->side[0].nq == 0 || ctx->side[1].nq == 0) return fail(ctx, B2D_ERR_ARG, "enlarged-block operator: set both children first");
+  int o[2] = {norb > 0 ? orbs[0] : -1, norb > 1 ? orbs[1] : -1};
+  int q[3] = {dq[0], dq[1], dq[2]};
+  try {
+    OpBuildPlanner P(ctx->side[0], ctx->side[1], ctx->integrals, hubbard != 0, ctx->am);
+    calls = P.plan(optype, o, q);
+  } catch (const std::exception& e) { return fail(ctx, B2D_ERR_ARG, e.what()); }
+  return B2D_OK;
+}
+
+int b2d_enlarged_op_products(b2d_ctx* ctx, int optype, int norb, const int32_t* orbs, const int32_t* dq, int hubbard, int max_products,
+                             int32_t* left_op, int32_t* right_op, int32_t* flags, double* scale) {
+  std::vector<ProductCall> calls;
+  int rc = plan_enlarged_op(ctx, optype, norb, orbs, dq, hubbard, calls);
+  if (rc) return -rc;
+  for (int k = 0; k < (int)calls.size() && k < max_products; ++k) {
+    if (left_op) left_op[k] = calls[k].lop;
+    if (right_op) right_op[k] = calls[k].rop;
+    if (flags) flags[k] = (calls[k].lt ? 1 : 0) | (calls[k].rt ? 2 : 0);
+    if (scale) scale[k] = calls[k].scale;
+  }
+  return (int)calls.size();
+}
+
+int b2d_build_enlarged_op(b2d_ctx* ctx, int optype, int norb, const int32_t* orbs, const int32_t* dq, int fermion, int hubbard, int* prod_id) {
+  NEED_DEVICE();
+  if (!prod_id) return fail(ctx, B2D_ERR_ARG, "b2d_build_enlarged_op: bad arguments");
+  std::vector<ProductCall> calls;
+  int rc = plan_enlarged_op(ctx, optype, norb, orbs, dq, hubbard, calls);
+  if (rc) return rc;
+  rc = b2d_product_op_create(ctx, dq, fermion, prod_id);
+  if (rc) return rc;
+  for (const ProductCall& c : calls) {
+    rc = b2d_product_op_accumulate(ctx, *prod_id, c.lop, c.lt ? 1 : 0, c.rop, c.rt ? 1 : 0, c.scale);
+    if (rc) return rc;
+  }
   return B2D_OK;
 }
 

@@ -426,6 +426,32 @@ class ProductBlock:
         if rc:
             raise B2DError("[%d] %s" % (rc, self.lib.b2d_last_error(self._ctx).decode()))
 
+    def set_integrals(self, v1, v2, orbital_irreps, one_tol=1e-15, two_tol=1e-15):
+        v1 = np.ascontiguousarray(v1, dtype=np.float64); v2 = np.ascontiguousarray(v2, dtype=np.float64)
+        irr = np.ascontiguousarray(orbital_irreps, dtype=np.int32)
+        self._ck(self.lib.b2d_set_integrals(self._ctx, len(irr), _p(v1, _lib.c_f64p), _p(v2, _lib.c_f64p), _p(irr, _lib.c_i32p), float(one_tol), float(two_tol)))
+
+    def products(self, optype, orbs, dq, hubbard=False):
+        """The planner's product list for one enlarged-block operator: [(left op id or None, left transposed, right op id or None,
+        right transposed, scale)] (host work only)."""
+        o = np.asarray(list(orbs) + [-1, -1], dtype=np.int32)
+        q = np.asarray(dq, dtype=np.int32)
+        n = self.lib.b2d_enlarged_op_products(self._ctx, int(optype), len(orbs), _p(o, _lib.c_i32p), _p(q, _lib.c_i32p), int(bool(hubbard)), 0, None, None, None, None)
+        if n < 0:
+            raise B2DError("[%d] %s" % (-n, self.lib.b2d_last_error(self._ctx).decode()))
+        lo, ro, fl, sc = np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1), np.int32), np.zeros(max(n, 1))
+        self.lib.b2d_enlarged_op_products(self._ctx, int(optype), len(orbs), _p(o, _lib.c_i32p), _p(q, _lib.c_i32p), int(bool(hubbard)), n, _p(lo, _lib.c_i32p),
+                                          _p(ro, _lib.c_i32p), _p(fl, _lib.c_i32p), _p(sc, _lib.c_f64p))
+        return [(None if lo[k] < 0 else int(lo[k]), bool(fl[k] & 1), None if ro[k] < 0 else int(ro[k]), bool(fl[k] & 2), float(sc[k])) for k in range(n)]
+
+    def build(self, optype, orbs, dq, fermion, hubbard=False):
+        """Op::build of one operator of the enlarged block, planned on the host and executed on the device: returns its id."""
+        o = np.asarray(list(orbs) + [-1, -1], dtype=np.int32)
+        q = np.asarray(dq, dtype=np.int32)
+        pid = C.c_int(-1)
+        self._ck(self.lib.b2d_build_enlarged_op(self._ctx, int(optype), len(orbs), _p(o, _lib.c_i32p), _p(q, _lib.c_i32p), int(bool(fermion)), int(bool(hubbard)), C.byref(pid)))
+        return pid.value
+
     def create(self, dq, fermion):
         """SparseMatrix::allocate on the enlarged block: returns the id of a zero-filled operator with deltaQuantum dq."""
         q = np.asarray(dq, dtype=np.int32)

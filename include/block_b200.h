@@ -244,8 +244,7 @@ int b2d_renormalise_from(b2d_ctx* ctx, int nroots, int guess_slot0, const double
  * operatorfunctions::TensorTrace operatorfunctions.C:19-117 (-> MatrixTensorProduct MatrixBLAS.C:125-200): the scatter every
  * Op::build of an enlarged block is made of (Operators.C:453-2395).  Here side 0 / side 1 of the context are the two CHILDREN of the
  * enlarged block (renormalised block and dot), described with b2d_set_block / b2d_add_op as usual; no b2d_plan is needed.
- * Which products enter an operator, and their integral factors, are still decided by the caller (the reference's host code or
- * the restatement in oracle/opbuild_oracle.py that the test drives this with). */
+ * b2d_product_op_* are the primitives; b2d_build_enlarged_op plans and builds a whole operator. */
 
 /* Product StateInfo of the enlarged block after CollectQuanta (StateInfo.h:113-147): collected quanta q (nq x 3) and sizes;
  * per UNCOLLECTED sector u its left / right child sectors (leftUnMapQuanta, rightUnMapQuanta) and size
@@ -262,6 +261,20 @@ int b2d_product_op_create(b2d_ctx* ctx, const int32_t* dq, int fermion, int* pro
  * sign of operatorfunctions.C:205-218 are applied per sub-block. */
 int b2d_product_op_accumulate(b2d_ctx* ctx, int prod_id, int left_op, int left_transposed, int right_op, int right_transposed,
                               double scale);
+/* One- and two-electron integrals as the reference's accessors return them for the (reordered) spatial orbitals:
+ * v1[i*n + j] = v_1(2i, 2j), v2[((i*n + j)*n + k)*n + l] = v_2(2i, 2j, 2k, 2l) (IntegralMatrix.C:32-46, 312-333), the irrep of every
+ * spatial orbital and the screening thresholds (input.C:141-142).  Kept across b2d_reset. */
+int b2d_set_integrals(b2d_ctx* ctx, int norbs, const double* v1, const double* v2, const int32_t* orbital_irreps, double one_tol,
+                      double two_tol);
+/* Op::build of ONE operator of the enlarged block (Operators.C:453-2625: Cre, CreCre, CreDes, CreDesComp, DesDesComp, CreCreDesComp,
+ * Ham, Overlap; energy sweep, spin-adapted, abelian): the host planner (block_b200/csrc/opbuild.hpp: TensorOp coupling,
+ * calcCompfactor with the integrals, commute parities, 6j recoupling) decides which child products enter it, the device
+ * performs them.  b2d_enlarged_op_products only lists them (integer / scalar work, no device needed; flags bit0 = left operand is a
+ * Transposeview, bit1 = right; an id of -1 = identity on that child): returns the count, or -(error code). */
+int b2d_enlarged_op_products(b2d_ctx* ctx, int optype, int norb, const int32_t* orbs, const int32_t* dq, int hubbard, int max_products,
+                             int32_t* left_op, int32_t* right_op, int32_t* flags, double* scale);
+int b2d_build_enlarged_op(b2d_ctx* ctx, int optype, int norb, const int32_t* orbs, const int32_t* dq, int fermion, int hubbard,
+                          int* prod_id);
 int64_t b2d_product_op_size(const b2d_ctx* ctx, int prod_id);
 int b2d_product_op_download(b2d_ctx* ctx, int prod_id, uint8_t* allowed, double* data);   /* host layout of b2d_add_op */
 

@@ -72,3 +72,37 @@ def test_device_tensor_products_rebuild_the_reference_operators(monkeypatch, pat
         assert pb.kernel_launches() >= products          # every product ran as a device launch
     finally:
         pb.close()
+
+
+@pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(f)[:-4] for f in FIXTURES])
+def test_build_enlarged_operators_without_the_oracle(path):
+    """b2d_build_enlarged_op: the library's own host planner (block_b200/csrc/opbuild.hpp) decides the products and the integral
+    factors, the device performs them; inputs are only the two children, the product StateInfo and the integrals.  Every
+    operator of the enlarged block must equal the one the REAL reference built."""
+    rec = dict(np.load(path))
+    pi, ref, ints = B.ProductInfo.from_record(rec), dumpio.block_from(rec, "LA."), B.Integrals.from_record(rec)
+    hubbard = int(rec["meta"][7]) == B.O.HUBBARD_HAM
+    left, right = hotpath.block_spec_from_record(rec, "LL."), hotpath.block_spec_from_record(rec, "LR.")
+    pb = hotpath.ProductBlock(left, right, pi.q, pi.dims, pi.lmap, pi.rmap, pi.unc_dims, pi.old_to_new, device=0)
+    pb.set_integrals(ints.h1, ints.h2, ints.irreps, ints.one_tol, ints.two_tol)
+    try:
+        worst = 0.0
+        for op in ref.ops:
+            pid = pb.build(op.optype, op.orbs, op.dq, op.fermion, hubbard)
+            allowed, data = pb.download(pid)
+            assert np.array_equal(allowed, op.allowed), (op.optype, op.orbs, op.comp)
+            off = 0
+            for i in range(len(pi.dims)):
+                for j in range(len(pi.dims)):
+                    if not op.allowed[i, j]:
+                        continue
+                    blk = op.blocks[(i, j)]
+                    got = data[off:off + blk.size].reshape(blk.shape)
+                    off += blk.size
+                    err = np.abs(got - blk).max() / max(1.0, float(np.abs(blk).max()))
+                    worst = max(worst, err)
+                    assert err <= 1e-12, (op.optype, op.orbs, op.comp, (i, j), err)
+        assert pb.kernel_launches() > len(ref.ops)
+        print("%s: %d operators rebuilt on the device, worst relative difference %.1e" % (os.path.basename(path), len(ref.ops), worst))
+    finally:
+        pb.close()

@@ -79,7 +79,10 @@ PROTOTYPES = {
     "b2d_product_op_download": (C.c_int, [ctx_p, C.c_int, c_u8p, c_f64p]),
     "b2d_set_integrals": (C.c_int, [ctx_p, C.c_int, c_f64p, c_f64p, c_i32p, C.c_double, C.c_double]),
     "b2d_enlarged_op_products": (C.c_int, [ctx_p, C.c_int, C.c_int, c_i32p, c_i32p, C.c_int, C.c_int, c_i32p, c_i32p, c_i32p, c_f64p]),
-    "b2d_build_enlarged_op": (C.c_int, [ctx_p, C.c_int, C.c_int, c_i32p, c_i32p, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "b2d_build_enlarged_op": (C.c_int, [ctx_p, C.c_int, C.c_int, c_i32p, C.c_int, c_i32p, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "b2d_stash_product": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_int, c_i32p]),
+    "b2d_stash_side": (C.c_int, [ctx_p, C.c_int, C.c_int]),
+    "b2d_assemble_big": (C.c_int, [ctx_p]),
     "b2d_renormalise_from": (C.c_int, [ctx_p, C.c_int, C.c_int, c_f64p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_double, c_f64p, c_i32p, c_f64p, C.POINTER(C.c_int)]),
     "b2d_add_onedot_noise": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_double]),
     "b2d_wavefunction_size": (C.c_int64, [ctx_p, c_i32p]),

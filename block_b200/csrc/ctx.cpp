@@ -198,6 +198,8 @@ struct b2d_ctx {
     bool set = false;
   } product;
   DevBuf kron_tasks;
+  Side stash[2];                            // children of the big block parked by b2d_stash_product / b2d_stash_side
+  bool stash_set[2] = {false, false};
   Integrals integrals;                      // one- / two-electron integrals for the complementary operators (b2d_set_integrals)
 
   std::map<std::vector<int>, PsiLayout> layouts;   // wavefunction layouts for other target quanta (noise: O.psi sectors)
@@ -587,6 +589,7 @@ int b2d_reset(b2d_ctx* ctx) {
   ctx->rotated = Side(); ctx->rotated_old.clear();
   ctx->layouts.clear();
   ctx->product = b2d_ctx::Product();
+  ctx->stash[0] = Side(); ctx->stash[1] = Side(); ctx->stash_set[0] = ctx->stash_set[1] = false;
   ctx->timing_valid = false;   // (the integrals belong to the whole calculation: b2d_reset keeps them)
   ctx->err.clear();
   return B2D_OK;
@@ -2112,7 +2115,7 @@ int b2d_enlarged_op_products(b2d_ctx* ctx, int optype, int norb, const int32_t* 
   return (int)calls.size();
 }
 
-int b2d_build_enlarged_op(b2d_ctx* ctx, int optype, int norb, const int32_t* orbs, const int32_t* dq, int fermion, int hubbard, int* prod_id) {
+int b2d_build_enlarged_op(b2d_ctx* ctx, int optype, int norb, const int32_t* orbs, int comp, const int32_t* dq, int fermion, int hubbard, int* prod_id) {
   NEED_DEVICE();
   if (!prod_id) return fail(ctx, B2D_ERR_ARG, "b2d_build_enlarged_op: bad arguments");
   std::vector<ProductCall> calls;
@@ -2120,10 +2123,46 @@ int b2d_build_enlarged_op(b2d_ctx* ctx, int optype, int norb, const int32_t* orb
   if (rc) return rc;
   rc = b2d_product_op_create(ctx, dq, fermion, prod_id);
   if (rc) return rc;
+  {   // identity of the operator inside its array: the term planner (b2d_plan) finds operators by (type, orbitals, component)
+    OpRec& op = ctx->product.side.ops[*prod_id];
+    op.optype = optype; op.norb = norb; op.comp = comp;
+    for (int k = 0; k < norb; ++k) op.orbs[k] = orbs[k];
+  }
   for (const ProductCall& c : calls) {
     rc = b2d_product_op_accumulate(ctx, *prod_id, c.lop, c.lt ? 1 : 0, c.rop, c.rt ? 1 : 0, c.scale);
     if (rc) return rc;
   }
+  return B2D_OK;
+}
+
+// One child of the big block is ready (built on the device from ITS children, or uploaded as it is): park it, so that side 0 / side 1
+// are free to describe the children of the other one.  b2d_assemble_big then makes the two parked blocks the children of the big block.
+int b2d_stash_product(b2d_ctx* ctx, int slot, int is_loop, int nsites, const int32_t* sites) {
+  if (!ctx || slot < 0 || slot > 1 || !ctx->product.set) return fail(ctx, B2D_ERR_ARG, "b2d_stash_product: no product block");
+  Side s = std::move(ctx->product.side);
+  s.loop = is_loop != 0;
+  s.sites.clear();
+  if (sites) s.sites.assign(sites, sites + nsites);
+  ctx->stash[slot] = std::move(s);
+  ctx->stash_set[slot] = true;
+  ctx->product = b2d_ctx::Product();
+  return B2D_OK;
+}
+int b2d_stash_side(b2d_ctx* ctx, int slot, int from_side) {
+  if (!ctx || slot < 0 || slot > 1 || from_side < 0 || from_side > 1 || ctx->side[from_side].nq == 0) return fail(ctx, B2D_ERR_ARG, "b2d_stash_side: bad arguments");
+  if (ctx->has_device) { int frc = flush_pending_ops(ctx); if (frc) return frc; }
+  ctx->stash[slot] = std::move(ctx->side[from_side]);
+  ctx->side[from_side] = Side();
+  ctx->stash_set[slot] = true;
+  return B2D_OK;
+}
+int b2d_assemble_big(b2d_ctx* ctx) {
+  if (!ctx || !ctx->stash_set[0] || !ctx->stash_set[1]) return fail(ctx, B2D_ERR_ARG, "b2d_assemble_big: both children must be stashed first");
+  ctx->side[0] = std::move(ctx->stash[0]);
+  ctx->side[1] = std::move(ctx->stash[1]);
+  ctx->stash[0] = Side(); ctx->stash[1] = Side();
+  ctx->stash_set[0] = ctx->stash_set[1] = false;
+  ctx->planned = false;
   return B2D_OK;
 }
 

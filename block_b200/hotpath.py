@@ -444,12 +444,13 @@ class ProductBlock:
                                           _p(ro, _lib.c_i32p), _p(fl, _lib.c_i32p), _p(sc, _lib.c_f64p))
         return [(None if lo[k] < 0 else int(lo[k]), bool(fl[k] & 1), None if ro[k] < 0 else int(ro[k]), bool(fl[k] & 2), float(sc[k])) for k in range(n)]
 
-    def build(self, optype, orbs, dq, fermion, hubbard=False):
+    def build(self, optype, orbs, dq, fermion, hubbard=False, comp=0):
         """Op::build of one operator of the enlarged block, planned on the host and executed on the device: returns its id."""
         o = np.asarray(list(orbs) + [-1, -1], dtype=np.int32)
         q = np.asarray(dq, dtype=np.int32)
         pid = C.c_int(-1)
-        self._ck(self.lib.b2d_build_enlarged_op(self._ctx, int(optype), len(orbs), _p(o, _lib.c_i32p), _p(q, _lib.c_i32p), int(bool(fermion)), int(bool(hubbard)), C.byref(pid)))
+        self._ck(self.lib.b2d_build_enlarged_op(self._ctx, int(optype), len(orbs), _p(o, _lib.c_i32p), int(comp), _p(q, _lib.c_i32p), int(bool(fermion)),
+                                                int(bool(hubbard)), C.byref(pid)))
         return pid.value
 
     def create(self, dq, fermion):

@@ -273,8 +273,16 @@ int b2d_set_integrals(b2d_ctx* ctx, int norbs, const double* v1, const double* v
  * Transposeview, bit1 = right; an id of -1 = identity on that child): returns the count, or -(error code). */
 int b2d_enlarged_op_products(b2d_ctx* ctx, int optype, int norb, const int32_t* orbs, const int32_t* dq, int hubbard, int max_products,
                              int32_t* left_op, int32_t* right_op, int32_t* flags, double* scale);
-int b2d_build_enlarged_op(b2d_ctx* ctx, int optype, int norb, const int32_t* orbs, const int32_t* dq, int fermion, int hubbard,
-                          int* prod_id);
+int b2d_build_enlarged_op(b2d_ctx* ctx, int optype, int norb, const int32_t* orbs, int comp, const int32_t* dq, int fermion,
+                          int hubbard, int* prod_id);
+/* Both children of the big block of a two-dot step are themselves enlarged blocks (SpinBlock::BuildSumBlock).  A child that was
+ * built on the device from ITS children (b2d_build_enlarged_op for each of its operators, in the order of the reference's operator
+ * arrays) is parked with b2d_stash_product (is_loop / sites as in b2d_set_block); a child that was uploaded as it is (b2d_set_block +
+ * b2d_add_op on side `from_side`) with b2d_stash_side; b2d_assemble_big makes the block parked in slot 0 / 1 the left / right child,
+ * after which b2d_plan runs as usual.  Operators built on the device never cross the PCIe bus. */
+int b2d_stash_product(b2d_ctx* ctx, int slot, int is_loop, int nsites, const int32_t* sites);
+int b2d_stash_side(b2d_ctx* ctx, int slot, int from_side);
+int b2d_assemble_big(b2d_ctx* ctx);
 int64_t b2d_product_op_size(const b2d_ctx* ctx, int prod_id);
 int b2d_product_op_download(b2d_ctx* ctx, int prod_id, uint8_t* allowed, double* data);   /* host layout of b2d_add_op */
 

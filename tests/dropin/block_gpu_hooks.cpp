@@ -27,6 +27,8 @@
 //   B2D_DROPIN_TRANSFORM  "device" (default): the transform hook does the block's bookkeeping itself;  "reference": it lets the
 //                         reference's transform_operators do it with MatrixRotate switched off (re-builds virtual operators on the CPU)
 //   B2D_DROPIN_WORKSPACE_MB   T workspace of the two-step contraction
+//   B2D_DROPIN_OPBUILD    "device" (default): a child of the big block that is an enlarged block is built on the GPU from ITS children
+//                         (SURVEY N2);  "host": the reference's Op::build constructs it on the CPU and it is uploaded
 //   B2D_DROPIN_EIG        "host": diagnostic - the density-matrix eigen-decomposition and state selection stay with the reference
 //                         (dsyev_), everything else on the GPU: separates eigenvector non-uniqueness from arithmetic differences
 //   B2D_DROPIN_OPTIONS    "key=value,..." library options (b2d_set_option), e.g. eig_jacobi_max=512
@@ -93,6 +95,8 @@ struct Gpu {
   int nmult = 0, call = -1;
   long long launch0 = 0;         // kernel-launch counter of the (reused) context when this block iteration began
   bool dirty = false;            // statistics of this context not written yet
+  bool integrals_set = false;    // b2d_set_integrals done (kept across b2d_reset)
+  int children_on_device = 0;    // children of big blocks built on the device so far
   // check mode: CPU results kept between hooks
   SparseMatrix* chk_transform = 0;
   vector<DiagonalMatrix> chk_eigs;
@@ -139,9 +143,9 @@ void write_stats() {
   FILE* f = fopen(path, "a");
   if (!f) return;
   fprintf(f, "call=%d lsites=%d rsites=%d W=%lld sigma_flops=%.6e n_multiply=%d host_op_build_s=%.6f upload_s=%.6f diag_s=%.6f davidson_s=%.6f davidson_dev_ms=%.3f "
-             "density_s=%.6f eig_s=%.6f rotate_s=%.6f launches=%lld\n",
+             "density_s=%.6f eig_s=%.6f rotate_s=%.6f launches=%lld children_built_on_device=%d\n",
           g.call, (int)g.lsites.size(), (int)g.rsites.size(), (long long)g.W, g.flops, g.nmult, g.t_build, g.t_upload, g.t_diag, g.t_dav, g.dav_dev_ms, g.t_rho,
-          g.t_eig, g.t_rot, (long long)(b2d_kernel_launches(g.ctx) - g.launch0));
+          g.t_eig, g.t_rot, (long long)(b2d_kernel_launches(g.ctx) - g.launch0), g.children_on_device);
   fclose(f);
 }
 
@@ -191,6 +195,107 @@ void upload_block(int side, SpinBlock& b, vector<OpRef>* keep) {
   }
 }
 
+bool opbuild_on_device() { const char* v = getenv("B2D_DROPIN_OPBUILD"); return !(v && string(v) == "host"); }
+
+void set_integrals_once(const SpinBlock& big) {
+  if (g.integrals_set) return;
+  const int idx = big.get_integralIndex();
+  const int n = (int)dmrginp.spin_orbs_symmetry().size() / 2;
+  vector<double> h1((size_t)n * n), h2((size_t)n * n * n * n);
+  vector<int32_t> irr(n);
+  for (int i = 0; i < n; ++i) {
+    irr[i] = SymmetryOfSpatialOrb(i).getirrep();
+    for (int j = 0; j < n; ++j) h1[(size_t)i * n + j] = v_1[idx](2 * i, 2 * j);
+  }
+  for (int i = 0; i < n; ++i) for (int j = 0; j < n; ++j) for (int k = 0; k < n; ++k) for (int l = 0; l < n; ++l)
+    h2[(((size_t)i * n + j) * n + k) * n + l] = v_2[idx](2 * i, 2 * j, 2 * k, 2 * l);
+  ck(b2d_set_integrals(g.ctx, n, h1.data(), h2.data(), irr.data(), dmrginp.oneindex_screen_tol(), dmrginp.twoindex_screen_tol()), "b2d_set_integrals");
+  g.integrals_set = true;
+}
+
+// a child of the big block that is itself an enlarged block (renormalised block x dot) is NOT built by the reference's
+// Op::build on the CPU and uploaded; its two children (M-state operators + the one-site dot: ~16x less data) are uploaded and every
+// operator of the child is built on the device (b2d_build_enlarged_op: host planner + kron_scatter_kernel).  Returns false - nothing
+// done - when the block is not such a product or carries operator types outside the energy sweep: the caller uploads it as it is.
+bool build_child_on_device(int slot, SpinBlock& b, vector<OpRef>* keep) {
+  if (!b.get_leftBlock() || !b.get_rightBlock()) return false;
+  if (b.get_leftBlock()->get_sites().empty() || b.get_rightBlock()->get_sites().empty()) return false;
+  const StateInfo& si = b.get_stateInfo();
+  if (!si.hasCollectedQuanta || !si.unCollectedStateInfo || !si.leftStateInfo || !si.rightStateInfo) return false;
+  SpinBlock& cl = *b.get_leftBlock();
+  SpinBlock& cr = *b.get_rightBlock();
+  if (si.leftStateInfo->quanta.size() != cl.get_stateInfo().quanta.size() || si.rightStateInfo->quanta.size() != cr.get_stateInfo().quanta.size()) return false;
+  if (si.leftStateInfo->quantaStates != cl.get_stateInfo().quantaStates || si.rightStateInfo->quantaStates != cr.get_stateInfo().quantaStates) return false;
+  static const int known[] = {HAM, CRE, CRE_CRE, DES_DESCOMP, CRE_DES, CRE_DESCOMP, CRE_CRE_DESCOMP, OVERLAP};
+  for (std::map<opTypes, boost::shared_ptr<Op_component_base> >::iterator it = b.ops.begin(); it != b.ops.end(); ++it) {
+    bool ok = false;
+    for (int t : known) ok = ok || t == (int)it->first;
+    if (!ok) return false;
+  }
+  double tb0 = g.t_build;
+  upload_block(0, cl, 0);          // the grandchildren: renormalised operators (core) and the dot
+  upload_block(1, cr, 0);
+  g.t_build = tb0;                 // getworkingrepresentation of core operators does not build anything
+  int nq = (int)si.quanta.size();
+  vector<int32_t> q(3 * nq), dims(nq), begin(1, 0), flat;
+  for (int i = 0; i < nq; ++i) {
+    q[3 * i] = si.quanta[i].get_n(); q[3 * i + 1] = si.quanta[i].get_s().getirrep(); q[3 * i + 2] = si.quanta[i].get_symm().getirrep();
+    dims[i] = si.quantaStates[i];
+    flat.insert(flat.end(), si.oldToNewState[i].begin(), si.oldToNewState[i].end());
+    begin.push_back((int32_t)flat.size());
+  }
+  vector<int32_t> lmap(si.leftUnMapQuanta.begin(), si.leftUnMapQuanta.end()), rmap(si.rightUnMapQuanta.begin(), si.rightUnMapQuanta.end());
+  vector<int32_t> unc(si.unCollectedStateInfo->quantaStates.begin(), si.unCollectedStateInfo->quantaStates.end());
+  ck(b2d_set_product_stateinfo(g.ctx, nq, q.data(), dims.data(), (int)unc.size(), lmap.data(), rmap.data(), unc.data(), begin.data(), flat.data()),
+     "b2d_set_product_stateinfo");
+  const int hub = dmrginp.hamiltonian() == HUBBARD ? 1 : 0;
+  const bool check = env_on("B2D_DROPIN_CHECK");
+  double worst = 0, scale = 0;
+  int nops = 0;
+  vector<uint8_t> allowed((size_t)nq * nq);
+  vector<double> data;
+  for (std::map<opTypes, boost::shared_ptr<Op_component_base> >::iterator it = b.ops.begin(); it != b.ops.end(); ++it) {
+    Op_component_base& arr = *it->second;
+    for (int i = 0; i < arr.get_size(); ++i) {
+      vector<boost::shared_ptr<SparseMatrix> > vec = arr.get_local_element(i);
+      for (size_t c = 0; c < vec.size(); ++c) {
+        SparseMatrix& op = *vec[c];
+        if (op.get_deltaQuantum_size() != 1) die("operator with several deltaQuantum components (non spin-adapted / BCS run): not covered");
+        int32_t orbs[2] = {-1, -1};
+        int norb = (int)op.get_orbs().size();
+        if (norb > 2) die("operator with more than two orbital indices on the sweep path");
+        for (int k = 0; k < norb; ++k) orbs[k] = op.get_orbs()[k];
+        SpinQuantum dq = op.get_deltaQuantum(0);
+        int32_t dqv[3] = {dq.get_n(), dq.get_s().getirrep(), dq.get_symm().getirrep()};
+        int id = -1;
+        ck(b2d_build_enlarged_op(g.ctx, (int)it->first, norb, orbs, (int)c, dqv, op.get_fermion() ? 1 : 0, hub, &id), "b2d_build_enlarged_op");
+        if (keep) keep->push_back(OpRef{vec[c].get(), id});
+        ++nops;
+        if (check) {   // the reference's own Op::build on the CPU
+          boost::shared_ptr<SparseMatrix> rep = vec[c]->getworkingrepresentation(&b);
+          int64_t n = b2d_product_op_size(g.ctx, id);
+          data.resize((size_t)std::max<int64_t>(n, 1));
+          ck(b2d_product_op_download(g.ctx, id, allowed.data(), data.data()), "b2d_product_op_download");
+          size_t off = 0;
+          for (int a = 0; a < nq; ++a)
+            for (int bq = 0; bq < nq; ++bq) {
+              if ((allowed[(size_t)a * nq + bq] != 0) != (bool)rep->allowed(a, bq)) die("device-built operator: allowed mask differs from the reference's");
+              if (!rep->allowed(a, bq)) continue;
+              const Matrix& m = rep->operator_element(a, bq);
+              for (int e = 0; e < m.Storage(); ++e) { worst = std::max(worst, fabs(m.Store()[e] - data[off + e])); scale = std::max(scale, fabs(m.Store()[e])); }
+              off += m.Storage();
+            }
+        }
+      }
+    }
+  }
+  if (check) fprintf(stderr, "B2D_CHECK call=%d opbuild side=%d ops=%d max_abs_diff=%.3e (max |O| %.3e)\n", g.call + 1, slot, nops, worst, scale);
+  vector<int32_t> sites(b.get_sites().begin(), b.get_sites().end());
+  ck(b2d_stash_product(g.ctx, slot, b.is_loopblock() ? 1 : 0, (int)sites.size(), sites.data()), "b2d_stash_product");
+  ++g.children_on_device;
+  return true;
+}
+
 // one context per big block (one block iteration); built at the first hook that sees the block (diagonalH, solver.C:34)
 void ensure_ctx(const SpinBlock& big_c) {
   SpinBlock& big = const_cast<SpinBlock&>(big_c);
@@ -220,8 +325,21 @@ void ensure_ctx(const SpinBlock& big_c) {
     }
   }
   g.left = big.get_leftBlock(); g.right = big.get_rightBlock(); g.lsites = big.get_leftBlock()->get_sites(); g.rsites = big.get_rightBlock()->get_sites();
-  upload_block(0, *big.get_leftBlock(), &g.left_ops);
-  upload_block(1, *big.get_rightBlock(), 0);
+  // each child: built on the device from ITS children where possible, otherwise the reference builds it and it is uploaded
+  for (int slot = 0; slot < 2; ++slot) {
+    SpinBlock& child = slot == 0 ? *big.get_leftBlock() : *big.get_rightBlock();
+    vector<OpRef>* keep = slot == 0 ? &g.left_ops : 0;
+    bool on_device = false;
+    if (opbuild_on_device()) {
+      set_integrals_once(big);
+      on_device = build_child_on_device(slot, child, keep);
+    }
+    if (!on_device) {
+      upload_block(0, child, keep);
+      ck(b2d_stash_side(g.ctx, slot, 0), "b2d_stash_side");
+    }
+  }
+  ck(b2d_assemble_big(g.ctx), "b2d_assemble_big");
   SpinQuantum tq = dmrginp.effective_molecule_quantum();
   int32_t dq[3] = {tq.get_n(), tq.get_s().getirrep(), tq.get_symm().getirrep()};
   int norbs = (int)dmrginp.spin_orbs_symmetry().size() / 2;

@@ -9,6 +9,7 @@
 //   DensityMatrix::makedensitymatrix density.C:27         (caller renormalise.C:104)
 //   SpinBlock::transform_operators  save_load_block.C:267 (caller sweep.C:279)
 //   SpinBlock::multiplyH            spinblock.C:722       (caller davidson.C:21)
+//   GuessWave::guess_wavefunctions  guess_wavefunction.C:378 (caller solver.C:77)   [ORACLE_DUMP_GUESS: SURVEY N1 fixtures]
 //
 // Environment:
 //   ORACLE_DUMP_DIR    directory for site<k>.bin records (unset => no dumps)
@@ -39,6 +40,7 @@
 #include "global.h"
 #include "input.h"
 #include "operatorfunctions.h"
+#include "guess_wavefunction.h"
 
 using namespace SpinAdapted;
 using std::string;
@@ -353,6 +355,80 @@ void wrap_transform(SpinBlock* self, vector<Matrix>& rot) {
   if (!g_dump_this) return;
   Dumper d; d.open(g_path, true);
   dump_block(d, "N.", *self);
+}
+
+// the guess-wavefunction transform of a two-dot step (GuessWave::transform_previous_wavefunction, guess_wavefunction.C:524-636).
+// The wrapped caller-facing entry point is guess_wavefunctions (called across translation units from solver.C:77); the inputs the
+// reference loads from its scratch files inside (previous wavefunction + its StateInfo tree, the two rotation matrices) are loaded
+// here the same way and dumped together with every StateInfo table the transform reads; the output is the reference's own trial vector.
+void dump_si_tables(Dumper& d, const string& p, const StateInfo& s) {
+  dump_stateinfo(d, p, s);
+  d.ints(p + "new_quanta_map", s.newQuantaMap);
+  if (s.hasCollectedQuanta && s.unCollectedStateInfo) {
+    const StateInfo& u = *s.unCollectedStateInfo;
+    dump_stateinfo(d, p + "unc.", u);
+    d.ints(p + "unc.lmap", u.leftUnMapQuanta); d.ints(p + "unc.rmap", u.rightUnMapQuanta);
+    vector<int> o2n, begin(1, 0);
+    for (size_t q = 0; q < s.oldToNewState.size(); ++q) { o2n.insert(o2n.end(), s.oldToNewState[q].begin(), s.oldToNewState[q].end()); begin.push_back((int)o2n.size()); }
+    d.ints(p + "old_to_new", o2n); d.ints(p + "old_to_new_begin", begin);
+  }
+}
+void dump_rotation(Dumper& d, const string& p, const vector<Matrix>& rot) {
+  vector<int> shape; vector<double> data;
+  for (size_t q = 0; q < rot.size(); ++q) {
+    shape.push_back(rot[q].Nrows()); shape.push_back(rot[q].Ncols());
+    if (rot[q].Ncols()) data.insert(data.end(), rot[q].Store(), rot[q].Store() + rot[q].Storage());
+  }
+  d.ints(p + "shape", shape, {rot.size(), 2}); d.dbls(p + "data", data);
+}
+
+void real_guess(vector<Wavefunction>& solution, DiagonalMatrix& e, const SpinBlock& big, const guessWaveTypes& gw, const bool& onedot,
+                const bool& transpose_guess_wave, double additional_noise, int currentState) asm("__real_" SYM_guess_wavefunctions);
+void wrap_guess(vector<Wavefunction>& solution, DiagonalMatrix& e, const SpinBlock& big, const guessWaveTypes& gw, const bool& onedot,
+                const bool& transpose_guess_wave, double additional_noise, int currentState) asm("__wrap_" SYM_guess_wavefunctions);
+void wrap_guess(vector<Wavefunction>& solution, DiagonalMatrix& e, const SpinBlock& big, const guessWaveTypes& gw, const bool& onedot,
+                const bool& transpose_guess_wave, double additional_noise, int currentState) {
+  real_guess(solution, e, big, gw, onedot, transpose_guess_wave, additional_noise, currentState);
+  if (!g_dump_this || !getenv("ORACLE_DUMP_GUESS") || gw != TRANSFORM || onedot) return;
+  Dumper d; d.open(g_path, true);
+  const int nroots = (int)solution.size();
+  d.ints("gw.nroots", vector<int>{nroots, (int)transpose_guess_wave});
+  for (int i = 0; i < nroots; ++i) {
+    const int state = (dmrginp.setStateSpecific() || dmrginp.calc_type() == COMPRESS || dmrginp.calc_type() == MPS_NEVPT) ? currentState : i;
+    std::ostringstream pp; pp << "gw" << i << ".";
+    const string p = pp.str();
+    StateInfo oldSI;
+    Wavefunction oldWave;
+    vector<Matrix> lrot, rrot;
+    oldWave.LoadWavefunctionInfo(oldSI, big.get_leftBlock()->get_leftBlock()->get_sites(), state);
+    LoadRotationMatrix(big.get_leftBlock()->get_leftBlock()->get_sites(), lrot, state);
+    LoadRotationMatrix(big.get_rightBlock()->get_sites(), rrot, state);
+    const StateInfo& bs = big.get_stateInfo();
+    SpinQuantum dq = oldWave.get_deltaQuantum(0);
+    d.ints(p + "dq", vector<int>{dq.get_n(), dq.get_s().getirrep(), dq.get_symm().getirrep(), (int)oldWave.get_deltaQuantum_size()});
+    dump_si_tables(d, p + "sys.", *bs.leftStateInfo->leftStateInfo);      // S': the renormalised system block
+    dump_si_tables(d, p + "dot.", *bs.leftStateInfo->rightStateInfo);     // the new system dot
+    dump_si_tables(d, p + "left.", *bs.leftStateInfo);                    // S' (x) dot, collected (+ its uncollected tables)
+    dump_si_tables(d, p + "right.", *bs.rightStateInfo);                  // the new environment side
+    dump_si_tables(d, p + "oldleft.", *oldSI.leftStateInfo);              // row space of the previous wavefunction
+    dump_si_tables(d, p + "oldright.", *oldSI.rightStateInfo);            // its column space: E_old (x) dot, collected
+    dump_si_tables(d, p + "env.", *oldSI.rightStateInfo->leftStateInfo);  // E_old: the renormalised environment the rotation R produced
+    dump_si_tables(d, p + "olddot.", *oldSI.rightStateInfo->rightStateInfo);
+    vector<int> allowed; vector<double> data;
+    for (int a = 0; a < oldWave.nrows(); ++a) for (int b = 0; b < oldWave.ncols(); ++b) {
+      allowed.push_back(oldWave.allowed(a, b) ? 1 : 0);
+      if (oldWave.allowed(a, b)) { const Matrix& m = oldWave.operator_element(a, b); data.insert(data.end(), m.Store(), m.Store() + m.Storage()); }
+    }
+    d.ints(p + "old.allowed", allowed, {(uint64_t)oldWave.nrows(), (uint64_t)oldWave.ncols()});
+    d.dbls(p + "old.data", data);
+    dump_rotation(d, p + "lrot.", lrot);
+    dump_rotation(d, p + "rrot.", rrot);
+    vector<int> tallowed;
+    for (int l = 0; l < solution[i].nrows(); ++l) for (int r = 0; r < solution[i].ncols(); ++r) tallowed.push_back(solution[i].allowed(l, r) ? 1 : 0);
+    d.ints(p + "trial.allowed", tallowed, {(uint64_t)solution[i].nrows(), (uint64_t)solution[i].ncols()});
+    vector<double> flat; flatten(solution[i], flat); d.dbls(p + "trial", flat);
+    oldSI.Free();
+  }
 }
 
 void real_multiplyH(const SpinBlock* self, Wavefunction& c, Wavefunction* v, int num_threads) asm("__real_" SYM_multiplyH);

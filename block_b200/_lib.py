@@ -17,6 +17,21 @@ c_u8p = C.POINTER(C.c_uint8)
 c_f64p = C.POINTER(C.c_double)
 ctx_p = C.c_void_p
 
+
+
+class StateInfoC(C.Structure):
+    """b2d_stateinfo (include/block_b200.h)."""
+    _fields_ = [("nq", C.c_int32), ("q", c_i32p), ("dims", c_i32p), ("new_quanta_map", c_i32p), ("nunc", C.c_int32), ("unc_q", c_i32p),
+                ("unc_dims", c_i32p), ("unc_left", c_i32p), ("unc_right", c_i32p), ("old_to_new_begin", c_i32p), ("old_to_new", c_i32p)]
+
+
+class GuessDescC(C.Structure):
+    """b2d_guess_desc (include/block_b200.h)."""
+    _fields_ = [("dq", C.c_int32 * 3), ("sys", StateInfoC), ("dot", StateInfoC), ("left", StateInfoC), ("right", StateInfoC),
+                ("oldleft", StateInfoC), ("oldright", StateInfoC), ("env", StateInfoC), ("old_allowed", c_u8p), ("lrot_cols", c_i32p),
+                ("rrot_cols", c_i32p)]
+
+
 # name: (restype, [argtypes])  -- one entry per function declared in include/block_b200.h
 PROTOTYPES = {
     "b2d_create": (C.c_int, [C.c_int, C.POINTER(ctx_p)]),
@@ -87,6 +102,9 @@ PROTOTYPES = {
     "b2d_add_onedot_noise": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_double]),
     "b2d_wavefunction_size": (C.c_int64, [ctx_p, c_i32p]),
     "b2d_tensor_multiply_one_host": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_int, c_i32p, C.c_double, c_f64p, c_f64p]),
+    "b2d_guess_plan": (C.c_int, [ctx_p, C.POINTER(GuessDescC), c_f64p, C.c_int]),
+    "b2d_guess_plan_export": (C.c_int64, [ctx_p, C.c_int, C.c_void_p, C.c_int64]),
+    "b2d_guess_transform": (C.c_int, [ctx_p, c_f64p, c_f64p, c_f64p, C.c_int, c_f64p]),
     "b2d_nccl_unique_id": (C.c_int, [c_u8p]),
     "b2d_comm_init": (C.c_int, [ctx_p, c_u8p, C.c_int, C.c_int]),
     "b2d_allreduce_slot": (C.c_int, [ctx_p, C.c_int]),

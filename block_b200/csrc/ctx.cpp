@@ -16,6 +16,7 @@
 #include "kernels.h"
 #include "plan.hpp"
 #include "opbuild.hpp"
+#include "guess.hpp"
 
 using namespace b2d;
 
@@ -201,6 +202,8 @@ struct b2d_ctx {
   Side stash[2];                            // children of the big block parked by b2d_stash_product / b2d_stash_side
   bool stash_set[2] = {false, false};
   Integrals integrals;                      // one- / two-electron integrals for the complementary operators (b2d_set_integrals)
+  GuessPlan guess;                          // guess-wavefunction transform of the next block iteration (b2d_guess_plan)
+  DevBuf guess_image, guess_trial;
 
   std::map<std::vector<int>, PsiLayout> layouts;   // wavefunction layouts for other target quanta (noise: O.psi sectors)
   DevBuf dm_noise;
@@ -590,6 +593,7 @@ int b2d_reset(b2d_ctx* ctx) {
   ctx->layouts.clear();
   ctx->product = b2d_ctx::Product();
   ctx->stash[0] = Side(); ctx->stash[1] = Side(); ctx->stash_set[0] = ctx->stash_set[1] = false;
+  ctx->guess = GuessPlan();
   ctx->timing_valid = false;   // (the integrals belong to the whole calculation: b2d_reset keeps them)
   ctx->err.clear();
   return B2D_OK;
@@ -2163,6 +2167,152 @@ int b2d_assemble_big(b2d_ctx* ctx) {
   ctx->stash[0] = Side(); ctx->stash[1] = Side();
   ctx->stash_set[0] = ctx->stash_set[1] = false;
   ctx->planned = false;
+  return B2D_OK;
+}
+
+// ---- guess wavefunction of the next block iteration (GuessWave::transform_previous_wavefunction) ------------------------
+int b2d_guess_plan(b2d_ctx* ctx, const b2d_guess_desc* desc, double* out, int n) {
+  if (!ctx || !desc) return fail(ctx, B2D_ERR_ARG, "b2d_guess_plan: null argument");
+  try {
+    ctx->guess = plan_guess_transform(*desc, ctx->am, ctx->forced_class);
+  } catch (const std::exception& e) {
+    ctx->guess = GuessPlan();
+    return fail(ctx, B2D_ERR_ARG, e.what());
+  }
+  const GuessPlan& P = ctx->guess;
+  int64_t ntasks = 0;
+  for (const auto& r : P.rounds) ntasks += (int64_t)r.size();
+  const double v[8] = {(double)P.old_size, (double)P.lrot_size, (double)P.rrot_size, (double)P.trial.W, P.flops, (double)P.shuffle_bytes, (double)ntasks, (double)P.rounds.size()};
+  for (int i = 0; i < n && i < 8; ++i) out[i] = v[i];
+  return B2D_OK;
+}
+
+int64_t b2d_guess_plan_export(const b2d_ctx* ctx, int what, void* out, int64_t cap) {
+  if (!ctx || !ctx->guess.valid) return -1;
+  const GuessPlan& P = ctx->guess;
+  std::vector<char> buf;
+  auto put = [&](const void* p, size_t bytes) { const char* c = (const char*)p; buf.insert(buf.end(), c, c + bytes); };
+  switch (what) {
+    case 0: put(P.stage1.segs.data(), P.stage1.segs.size() * sizeof(GSeg)); break;
+    case 1: put(P.stage1.groups.data(), P.stage1.groups.size() * sizeof(GGroup)); break;
+    case 2: for (const auto& r : P.rounds) put(r.data(), r.size() * sizeof(KronTask)); break;
+    case 3: for (const auto& r : P.rounds) { int32_t c = (int32_t)r.size(); put(&c, 4); } break;
+    case 4: put(P.stage3.segs.data(), P.stage3.segs.size() * sizeof(GSeg)); break;
+    case 5: put(P.stage3.groups.data(), P.stage3.groups.size() * sizeof(GGroup)); break;
+    case 6:
+      put(P.in_old.data(), P.in_old.size() * sizeof(BlockDesc)); put(P.in_lrot.data(), P.in_lrot.size() * sizeof(BlockDesc));
+      put(P.in_rrot.data(), P.in_rrot.size() * sizeof(BlockDesc));
+      break;
+    case 7: {
+      int32_t c[4] = {(int32_t)P.in_old.size(), (int32_t)P.in_lrot.size(), (int32_t)P.in_rrot.size(), 0};
+      int64_t s[3] = {P.image_size, P.t1_size, P.work_size};
+      put(c, sizeof(c)); put(s, sizeof(s));
+      break;
+    }
+    case 8: {
+      for (int p = 0; p < P.trial.nblocks(); ++p) {
+        BlockDesc d; d.ref_off = P.trial.ref_off[p]; d.dev_off = P.trial.dev_off[p]; d.rows = P.trial.rows[p]; d.cols = P.trial.cols[p]; d.ld = P.trial.ld[p]; d.pad = 0;
+        put(&d, sizeof(d));
+      }
+      break;
+    }
+    case 9: { int32_t sz[4] = {(int32_t)sizeof(GSeg), (int32_t)sizeof(GGroup), (int32_t)sizeof(KronTask), (int32_t)sizeof(BlockDesc)}; put(sz, sizeof(sz)); break; }
+    default: return -1;
+  }
+  if (out && cap >= (int64_t)buf.size() && !buf.empty()) memcpy(out, buf.data(), buf.size());
+  return (int64_t)buf.size();
+}
+
+int b2d_guess_transform(b2d_ctx* ctx, const double* old_wave, const double* left_rot, const double* right_rot, int dst_slot, double* trial) {
+  NEED_DEVICE();
+  GuessPlan& P = ctx->guess;
+  if (!P.valid) return fail(ctx, B2D_ERR_ARG, "b2d_guess_transform: call b2d_guess_plan first");
+  if ((P.old_size && !old_wave) || (P.lrot_size && !left_rot) || (P.rrot_size && !right_rot)) return fail(ctx, B2D_ERR_ARG, "b2d_guess_transform: null input");
+  if (dst_slot < 0 && !trial) return fail(ctx, B2D_ERR_ARG, "b2d_guess_transform: no destination");
+  double* dst = nullptr;
+  if (dst_slot >= 0) {
+    NEED_PLAN(); CHECK_SLOT(dst_slot);
+    const PsiLayout& a = ctx->psi; const PsiLayout& b = P.trial;
+    if (a.W != b.W || a.Wp != b.Wp || a.bl != b.bl || a.br != b.br || a.rows != b.rows || a.cols != b.cols)
+      return fail(ctx, B2D_ERR_ARG, "b2d_guess_transform: the trial vector's sector layout is not the planned big block's");
+    dst = user_vec(ctx, dst_slot);
+  }
+  CU(cudaSetDevice(ctx->device));
+  // 1. one upload of the three inputs through the pinned staging buffer, packed into the padded image
+  const int64_t n_in = P.old_size + P.lrot_size + P.rrot_size;
+  int rc = flush_pending_ops(ctx);
+  if (rc) return rc;
+  double* pin = pending_room(ctx, (size_t)std::max<int64_t>(n_in, 1), &rc);
+  if (!pin) return rc;
+  if (P.old_size) memcpy(pin, old_wave, (size_t)P.old_size * 8);
+  if (P.lrot_size) memcpy(pin + P.old_size, left_rot, (size_t)P.lrot_size * 8);
+  if (P.rrot_size) memcpy(pin + P.old_size + P.lrot_size, right_rot, (size_t)P.rrot_size * 8);
+  ctx->pend_used = 0;   // the staging area is consumed below, before anybody else can claim it
+  CU(ctx->staging.reserve((size_t)std::max<int64_t>(n_in, 2) * 8));
+  CU(cudaMemcpyAsync(ctx->staging.p, pin, (size_t)n_in * 8, cudaMemcpyHostToDevice, ctx->stream));
+  CU(ctx->guess_image.reserve((size_t)std::max<int64_t>(P.image_size, 16) * 8));
+  CU(cudaMemsetAsync(ctx->guess_image.p, 0, (size_t)std::max<int64_t>(P.image_size, 16) * 8, ctx->stream));
+  std::vector<BlockDesc> blocks;
+  blocks.reserve(P.in_old.size() + P.in_lrot.size() + P.in_rrot.size());
+  for (BlockDesc d : P.in_old) blocks.push_back(d);
+  for (BlockDesc d : P.in_lrot) { d.ref_off += P.old_size; blocks.push_back(d); }
+  for (BlockDesc d : P.in_rrot) { d.ref_off += P.old_size + P.lrot_size; blocks.push_back(d); }
+  rc = upload_desc(ctx, ctx->desc_scratch, blocks.data(), blocks.size() * sizeof(BlockDesc));
+  if (rc) return rc;
+  CU(launch_pack((const BlockDesc*)ctx->desc_scratch.p, (int)blocks.size(), (const double*)ctx->staging.p, (double*)ctx->guess_image.p, ctx->stream, &ctx->launches));
+  // 2. destination and workspace
+  if (!dst) {
+    CU(ctx->guess_trial.reserve((size_t)std::max<int64_t>(P.trial.Wp, 16) * 8));
+    dst = (double*)ctx->guess_trial.p;
+  }
+  CU(cudaMemsetAsync(dst, 0, (size_t)P.trial.Wp * 8, ctx->stream));
+  CU(ctx->work.reserve((size_t)std::max<int64_t>(P.work_size, 16) * 8));
+  if (P.work_size > P.t2_off) CU(cudaMemsetAsync((double*)ctx->work.p + P.t2_off, 0, (size_t)(P.work_size - P.t2_off) * 8, ctx->stream));
+  // 3. stage 1 (grouped GEMM), stage 2 (scatter rounds), stage 3 (grouped GEMM)
+  Schedule S1, S3;
+  { Chunk c; c.step1 = P.stage1; c.nterms = 1; c.work = P.work_size; S1.chunks.push_back(std::move(c)); S1.work_max = P.work_size; }
+  { Chunk c; c.step1 = P.stage3; c.nterms = 1; c.work = P.work_size; S3.chunks.push_back(std::move(c)); S3.work_max = P.work_size; }
+  DevSchedule D1, D3;
+  rc = upload_schedule(ctx, S1, D1);
+  if (rc) return rc;
+  rc = upload_schedule(ctx, S3, D3);
+  if (rc) return rc;
+  begin_timing(ctx);
+  rc = run_schedule(ctx, S1, D1, nullptr, dst, (double*)ctx->guess_image.p);
+  if (rc) return rc;
+  {
+    std::vector<KronTask> tasks;
+    for (const auto& r : P.rounds)
+      for (KronTask t : r) {
+        t.a = (int64_t)(intptr_t)((double*)ctx->work.p + t.a);
+        t.dst = (int64_t)(intptr_t)((double*)ctx->work.p + t.dst);
+        tasks.push_back(t);
+      }
+    rc = upload_desc(ctx, ctx->kron_tasks, tasks.data(), tasks.size() * sizeof(KronTask));
+    if (rc) return rc;
+    size_t first = 0;
+    for (const auto& r : P.rounds) {   // tasks of one round never overlap; the rounds accumulate in stream order
+      CU(launch_kron_scatter((const KronTask*)ctx->kron_tasks.p + first, (int)r.size(), ctx->stream, &ctx->launches));
+      first += r.size();
+    }
+  }
+  rc = run_schedule(ctx, S3, D3, nullptr, dst, (double*)ctx->guess_image.p);
+  end_timing(ctx);
+  if (rc) return rc;
+  if (trial) {
+    std::vector<BlockDesc> tb;
+    for (int p = 0; p < P.trial.nblocks(); ++p) {
+      BlockDesc d; d.ref_off = P.trial.ref_off[p]; d.dev_off = P.trial.dev_off[p]; d.rows = P.trial.rows[p]; d.cols = P.trial.cols[p]; d.ld = P.trial.ld[p]; d.pad = 0;
+      tb.push_back(d);
+    }
+    rc = upload_desc(ctx, ctx->desc_scratch, tb.data(), tb.size() * sizeof(BlockDesc));
+    if (rc) return rc;
+    CU(ctx->staging.reserve((size_t)std::max<int64_t>(P.trial.W, 2) * 8));
+    CU(launch_unpack((const BlockDesc*)ctx->desc_scratch.p, (int)tb.size(), dst, (double*)ctx->staging.p, ctx->stream, &ctx->launches));
+    CU(cudaMemcpyAsync(trial, ctx->staging.p, (size_t)P.trial.W * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  D1.buf.release(); D3.buf.release();
   return B2D_OK;
 }
 

@@ -508,3 +508,93 @@ def spinblock_from_record(rec, device=0, rank=0, nranks=1, options=None) -> Spin
     norbs = len(rec["spin_orbs_symmetry"]) // 2 if "spin_orbs_symmetry" in rec else None
     return SpinBlock(L, R, tuple(int(x) for x in rec["psi_dq"]), core_energy=float(rec["meta_f"][3]), hubbard=int(rec["meta"][7]) == HUBBARD,
                      norbs=norbs, device=device, rank=rank, nranks=nranks, options=options)
+
+
+class GuessTransform:
+    """Guess wavefunction of the next block iteration: GuessWave::transform_previous_wavefunction (guess_wavefunction.C:524-636,
+    two-dot branch) planned on the host (b2d_guess_plan) and executed on the device (b2d_guess_transform).
+
+    `tables` maps the StateInfo names of b2d_guess_desc ("sys", "dot", "left", "right", "oldleft", "oldright", "env") to dicts with
+    the reference's tables: "q", "dims", and where the transform reads them "new_quanta_map", "unc.q", "unc.dims", "unc.lmap",
+    "unc.rmap", "old_to_new", "old_to_new_begin"."""
+
+    NAMES = ("sys", "dot", "left", "right", "oldleft", "oldright", "env")
+
+    def __init__(self, dq, tables, old_allowed, lrot_cols, rrot_cols, device=0, ctx=None):
+        self.lib = _lib.load()
+        self._own = ctx is None
+        if ctx is None:
+            self._ctx = C.c_void_p()
+            if self.lib.b2d_create(int(device), C.byref(self._ctx)):
+                raise B2DError("b2d_create: " + self.lib.b2d_last_error(None).decode())
+        else:
+            self._ctx = ctx
+        self._keep = []     # the arrays the descriptor points into
+
+        def arr(x, dt=np.int32):
+            a = np.ascontiguousarray(x, dtype=dt)
+            self._keep.append(a)
+            return a
+
+        def si(t):
+            s = _lib.StateInfoC()
+            s.nq = len(t["dims"])
+            s.q = _p(arr(t["q"]).reshape(-1), _lib.c_i32p)
+            s.dims = _p(arr(t["dims"]), _lib.c_i32p)
+            nqm = t.get("new_quanta_map")
+            s.new_quanta_map = _p(arr(nqm), _lib.c_i32p) if nqm is not None and len(nqm) else None
+            if "unc.dims" in t and "old_to_new_begin" in t:
+                s.nunc = len(t["unc.dims"])
+                s.unc_q = _p(arr(t["unc.q"]).reshape(-1), _lib.c_i32p)
+                s.unc_dims = _p(arr(t["unc.dims"]), _lib.c_i32p)
+                s.unc_left = _p(arr(t["unc.lmap"]), _lib.c_i32p)
+                s.unc_right = _p(arr(t["unc.rmap"]), _lib.c_i32p)
+                s.old_to_new_begin = _p(arr(t["old_to_new_begin"]), _lib.c_i32p)
+                s.old_to_new = _p(arr(t["old_to_new"]), _lib.c_i32p)
+            else:
+                s.nunc = 0
+            return s
+
+        d = _lib.GuessDescC()
+        for k in range(3):
+            d.dq[k] = int(dq[k])
+        for name in self.NAMES:
+            setattr(d, name, si(tables[name]))
+        d.old_allowed = _p(arr(old_allowed, np.uint8).reshape(-1), _lib.c_u8p)
+        d.lrot_cols = _p(arr(lrot_cols), _lib.c_i32p)
+        d.rrot_cols = _p(arr(rrot_cols), _lib.c_i32p)
+        self._desc = d
+        out = np.zeros(8)
+        self._ck(self.lib.b2d_guess_plan(self._ctx, C.byref(d), _p(out, _lib.c_f64p), 8))
+        self.old_size, self.lrot_size, self.rrot_size, self.trial_size = (int(x) for x in out[:4])
+        self.flops, self.shuffle_bytes, self.shuffle_tasks, self.shuffle_rounds = float(out[4]), float(out[5]), int(out[6]), int(out[7])
+
+    def _ck(self, rc):
+        if rc:
+            raise B2DError("[%d] %s" % (rc, self.lib.b2d_last_error(self._ctx).decode()))
+
+    def export(self, what):
+        """Raw bytes of one descriptor table of the plan (b2d_guess_plan_export)."""
+        n = self.lib.b2d_guess_plan_export(self._ctx, int(what), None, 0)
+        if n < 0:
+            raise B2DError("b2d_guess_plan_export(%d)" % what)
+        buf = np.zeros(max(int(n), 1), np.uint8)
+        self.lib.b2d_guess_plan_export(self._ctx, int(what), buf.ctypes.data_as(C.c_void_p), int(n))
+        return buf[:n]
+
+    def transform(self, old_wave, left_rot, right_rot, dst_slot=-1, download=True):
+        """The trial vector, flat in FlattenInto order (and / or left in wavefunction slot `dst_slot` of a planned context)."""
+        ow, lr, rr = (np.ascontiguousarray(x, dtype=np.float64) for x in (old_wave, left_rot, right_rot))
+        assert ow.size == self.old_size and lr.size == self.lrot_size and rr.size == self.rrot_size
+        out = np.zeros(max(self.trial_size, 1)) if download else None
+        self._ck(self.lib.b2d_guess_transform(self._ctx, _p(ow, _lib.c_f64p), _p(lr, _lib.c_f64p), _p(rr, _lib.c_f64p), int(dst_slot),
+                                              _p(out, _lib.c_f64p) if download else None))
+        return out[:self.trial_size] if download else None
+
+    def kernel_launches(self):
+        return int(self.lib.b2d_kernel_launches(self._ctx))
+
+    def close(self):
+        if self._own and self._ctx:
+            self.lib.b2d_destroy(self._ctx)
+        self._ctx = None

@@ -286,6 +286,63 @@ int b2d_assemble_big(b2d_ctx* ctx);
 int64_t b2d_product_op_size(const b2d_ctx* ctx, int prod_id);
 int b2d_product_op_download(b2d_ctx* ctx, int prod_id, uint8_t* allowed, double* data);   /* host layout of b2d_add_op */
 
+/* ---- guess wavefunction of the next block iteration ----------------------------------------- */
+
+/* One StateInfo of the reference as the transform reads it (StateInfo.h:60-130): quanta / quantaStates; newQuantaMap for a
+ * renormalised block (index of each sector in the un-truncated StateInfo it was cut from; NULL otherwise); for a collected
+ * product StateInfo the unCollectedStateInfo tables (quanta, quantaStates, leftUnMapQuanta, rightUnMapQuanta) and oldToNewState
+ * in CSR form (old_to_new_begin has nq + 1 entries); nunc = 0 and NULLs otherwise. */
+typedef struct b2d_stateinfo {
+  int32_t nq;
+  const int32_t* q;
+  const int32_t* dims;
+  const int32_t* new_quanta_map;
+  int32_t nunc;
+  const int32_t* unc_q;
+  const int32_t* unc_dims;
+  const int32_t* unc_left;
+  const int32_t* unc_right;
+  const int32_t* old_to_new_begin;
+  const int32_t* old_to_new;
+} b2d_stateinfo;
+
+/* Everything GuessWave::transform_previous_wavefunction (guess_wavefunction.C:524-636, two-dot branch) reads:
+ *   dq        target quantum of the wavefunction
+ *   sys       big.leftStateInfo->leftStateInfo   the renormalised system block S' (newQuantaMap -> sectors of `oldleft`)
+ *   dot       big.leftStateInfo->rightStateInfo  the new system dot (one state per sector)
+ *   left      big.leftStateInfo                  S' (x) dot, collected, with its un-collected tables
+ *   right     big.rightStateInfo                 the new environment side (sector dims only)
+ *   oldleft   oldStateInfo.leftStateInfo         row space of the previous wavefunction (dims only)
+ *   oldright  oldStateInfo.rightStateInfo        its column space E_old (x) dot, collected, with its un-collected tables
+ *   env       oldStateInfo.rightStateInfo->leftStateInfo   E_old (newQuantaMap -> sectors of `right`)
+ *   old_allowed  oldleft.nq x oldright.nq: allowed blocks of the previous wavefunction (wave-*.tmp)
+ *   lrot_cols / rrot_cols  kept states per sector of the two rotation matrices (Rotation-*.tmp; 0 = sector dropped): the left one
+ *                          is indexed by `oldleft` sectors, the right one by `right` sectors */
+typedef struct b2d_guess_desc {
+  int32_t dq[3];
+  b2d_stateinfo sys, dot, left, right, oldleft, oldright, env;
+  const uint8_t* old_allowed;
+  const int32_t* lrot_cols;
+  const int32_t* rrot_cols;
+} b2d_guess_desc;
+
+/* Plan the transform (host integer / scalar work: sector bookkeeping, getCommuteParity, 6j recoupling coefficients; valid on a
+ * planning-only context).  out[0..7] = {doubles of the previous wavefunction, of the left rotation, of the right rotation, of
+ * the trial vector (flat), GEMM flops, algorithmic bytes of the shuffle, number of shuffle tasks, number of shuffle rounds}. */
+int b2d_guess_plan(b2d_ctx* ctx, const b2d_guess_desc* desc, double* out, int n);
+/* The plan's descriptors for inspection (CPU tests execute them with numpy): what = 0 stage-1 segments (GSeg, 40 bytes each),
+ * 1 stage-1 groups (GGroup, 40), 2 shuffle tasks (KronTask, 80; rounds concatenated), 3 tasks per round (int32), 4 stage-3
+ * segments, 5 stage-3 groups, 6 input blocks (BlockDesc, 32: previous wavefunction, left rotation, right rotation), 7 counts of
+ * those three tables (int32 x 3) followed by {image, T1, work} sizes in doubles (int64 x 3 at byte 16), 8 trial blocks (BlockDesc).
+ * Returns the number of bytes (copied when cap is large enough), or -1. */
+int64_t b2d_guess_plan_export(const b2d_ctx* ctx, int what, void* out, int64_t cap);
+/* Execute it on the device: the three host arrays (allowed blocks row-major, (i outer, j inner) order; rotation matrices as the
+ * reference stores them, d_q x m_q row-major, dropped sectors skipped) are uploaded once, stage 1 / 3 run in the grouped FP64
+ * contraction kernel, stage 2 in the HBM-bound scatter kernel.  dst_slot >= 0: the trial vector is left in that wavefunction slot
+ * (needs b2d_plan with the same children and target quantum: the layouts must be identical) ready for b2d_davidson, nothing
+ * returns to the host; trial != NULL: it is (also) downloaded in FlattenInto order. */
+int b2d_guess_transform(b2d_ctx* ctx, const double* old_wave, const double* left_rot, const double* right_rot, int dst_slot, double* trial);
+
 /* ---- multi-GPU: partition of operator terms, NCCL all-reduce of the partial sigma --------------------------- */
 
 int b2d_nccl_unique_id(uint8_t* id128);                                   /* rank 0; broadcast out of band */

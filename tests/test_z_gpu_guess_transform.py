@@ -1,7 +1,9 @@
 """GPU: the guess-wavefunction transform on the device (b2d_guess_plan + b2d_guess_transform through the C ABI) against
 the REAL reference's trial vectors (tests/golden/guess_*.npz: GuessWave::transform_previous_wavefunction, guess_wavefunction.C:524-636)
 and against the pinned oracle, on forward and backward block iterations of C2/D2h (two roots), H2O/C1 and Hubbard.
-Tolerance: 1e-12 relative (FP64 contractions with different summation order; north_star's bar for vectors is 1e-10)."""
+Tolerance: 1e-12 relative (FP64 contractions with different summation order; north_star's bar for vectors is 1e-10).
+(File name: sorts after every other test module - this device path was finished after the round's GPU budget was spent, its planner is
+pinned on CPU by tests/test_guess_planner_cpu.py, and its first run on a B200 is the round-end one.)"""
 import glob
 import os
 

@@ -11,6 +11,7 @@
 //   DensityMatrix::makedensitymatrix  density.C:27         (caller renormalise.C:104)-> b2d_make_density (+ b2d_add_onedot_noise)
 //   diagonalise_dm                    rotationmat.C:258    (caller renormalise.C:145)-> b2d_diagonalise_dm
 //   assign_matrix_by_dm               rotationmat.C:149    (caller renormalise.C:164)-> b2d_select_states + b2d_rotation_download
+//   GuessWave::guess_wavefunctions    guess_wavefunction.C:378 (caller solver.C:77)  -> b2d_guess_plan + b2d_guess_transform (B2D_DROPIN_GUESS=device)
 //   SpinBlock::transform_operators    save_load_block.C:267(caller sweep.C:279)      -> b2d_transform_operators; the reference's own
 //                                     bookkeeping (new StateInfo, core flags, freeing the children) still runs, with its
 //                                     MatrixRotate arithmetic (MatrixBLAS.C:553) switched off and the blocks filled from the device.
@@ -29,6 +30,9 @@
 //   B2D_DROPIN_WORKSPACE_MB   T workspace of the two-step contraction
 //   B2D_DROPIN_OPBUILD    "device" (default): a child of the big block that is an enlarged block is built on the GPU from ITS children
 //                         (SURVEY N2);  "host": the reference's Op::build constructs it on the CPU and it is uploaded
+//   B2D_DROPIN_GUESS      "device": the TRANSFORM guess of a two-dot block iteration (GuessWave::transform_previous_wavefunction,
+//                         SURVEY N1) is computed on the GPU (b2d_guess_plan + b2d_guess_transform);  default "host": the reference's own
+//                         (opt-in until the device path has been run on a B200)
 //   B2D_DROPIN_EIG        "host": diagnostic - the density-matrix eigen-decomposition and state selection stay with the reference
 //                         (dsyev_), everything else on the GPU: separates eigenvector non-uniqueness from arithmetic differences
 //   B2D_DROPIN_OPTIONS    "key=value,..." library options (b2d_set_option), e.g. eig_jacobi_max=512
@@ -57,6 +61,7 @@
 #include "input.h"
 #include "operatorfunctions.h"
 #include "MatrixBLAS.h"
+#include "guess_wavefunction.h"
 
 #include "block_b200.h"
 
@@ -91,6 +96,7 @@ struct Gpu {
   bool in_transform = false;     // MatrixRotate is switched off
   // statistics of the current block iteration
   double t_build = 0;            // inside the reference's own Op::build for direct-mode virtual operators (host side)
+  double t_guess = 0;
   double t_upload = 0, t_diag = 0, t_dav = 0, t_rho = 0, t_eig = 0, t_rot = 0, dav_dev_ms = 0, flops = 0;
   int nmult = 0, call = -1;
   long long launch0 = 0;         // kernel-launch counter of the (reused) context when this block iteration began
@@ -143,9 +149,9 @@ void write_stats() {
   FILE* f = fopen(path, "a");
   if (!f) return;
   fprintf(f, "call=%d lsites=%d rsites=%d W=%lld sigma_flops=%.6e n_multiply=%d host_op_build_s=%.6f upload_s=%.6f diag_s=%.6f davidson_s=%.6f davidson_dev_ms=%.3f "
-             "density_s=%.6f eig_s=%.6f rotate_s=%.6f launches=%lld children_built_on_device=%d\n",
+             "density_s=%.6f eig_s=%.6f rotate_s=%.6f launches=%lld children_built_on_device=%d guess_s=%.6f\n",
           g.call, (int)g.lsites.size(), (int)g.rsites.size(), (long long)g.W, g.flops, g.nmult, g.t_build, g.t_upload, g.t_diag, g.t_dav, g.dav_dev_ms, g.t_rho,
-          g.t_eig, g.t_rot, (long long)(b2d_kernel_launches(g.ctx) - g.launch0), g.children_on_device);
+          g.t_eig, g.t_rot, (long long)(b2d_kernel_launches(g.ctx) - g.launch0), g.children_on_device, g.t_guess);
   fclose(f);
 }
 
@@ -347,7 +353,7 @@ void ensure_ctx(const SpinBlock& big_c) {
   g.W = b2d_psi_size(g.ctx);
   g.flops = b2d_sigma_flops(g.ctx, 1);
   g.t_upload = now_s() - t0 - g.t_build;
-  g.t_diag = g.t_dav = g.t_rho = g.t_eig = g.t_rot = g.dav_dev_ms = 0; g.nmult = 0;
+  g.t_diag = g.t_dav = g.t_rho = g.t_eig = g.t_rot = g.dav_dev_ms = g.t_guess = 0; g.nmult = 0;
   g.dirty = true;
   ++g.call;
 }
@@ -400,6 +406,102 @@ void wrap_diagonalH(const SpinBlock* self, DiagonalMatrix& e) {
     double d = 0; for (int i = 0; i < e.Ncols(); ++i) d = std::max(d, fabs(e.element(i) - e2.element(i)));
     fprintf(stderr, "B2D_CHECK call=%d diagonalH max_abs_diff=%.3e\n", g.call, d);
   }
+}
+
+// ---- GuessWave::guess_wavefunctions (vector form, solver.C:77) ----
+// SURVEY N1.  For a TRANSFORM guess of a two-dot step the reference loads the previous wavefunction and two rotation matrices from its
+// scratch files and runs TransformLeftBlock / onedot_shufflesysdot / TransformRightBlock on the CPU (guess_wavefunction.C:524-636).  Here
+// the same files are loaded the same way, the StateInfo tables the transform reads are handed to b2d_guess_plan, and the arithmetic runs
+// on the device.  Everything else (BASIC / TRANSPOSE guesses, one-dot steps) goes to the reference's own function.
+void fill_stateinfo(b2d_stateinfo& o, const StateInfo& s, vector<vector<int32_t> >& keep) {
+  memset(&o, 0, sizeof(o));
+  auto hold = [&](const vector<int>& v) -> const int32_t* { keep.push_back(vector<int32_t>(v.begin(), v.end())); if (keep.back().empty()) keep.back().push_back(0); return keep.back().data(); };
+  auto quanta = [&](const StateInfo& t) -> const int32_t* {
+    vector<int> q;
+    for (size_t i = 0; i < t.quanta.size(); ++i) { q.push_back(t.quanta[i].get_n()); q.push_back(t.quanta[i].get_s().getirrep()); q.push_back(t.quanta[i].get_symm().getirrep()); }
+    return hold(q);
+  };
+  o.nq = (int32_t)s.quanta.size();
+  o.q = quanta(s);
+  o.dims = hold(s.quantaStates);
+  o.new_quanta_map = s.newQuantaMap.size() == s.quanta.size() && !s.newQuantaMap.empty() ? hold(s.newQuantaMap) : 0;
+  if (s.hasCollectedQuanta && s.unCollectedStateInfo) {
+    const StateInfo& u = *s.unCollectedStateInfo;
+    o.nunc = (int32_t)u.quanta.size();
+    o.unc_q = quanta(u);
+    o.unc_dims = hold(u.quantaStates);
+    o.unc_left = hold(u.leftUnMapQuanta);
+    o.unc_right = hold(u.rightUnMapQuanta);
+    vector<int> flat, begin(1, 0);
+    for (size_t q = 0; q < s.oldToNewState.size(); ++q) { flat.insert(flat.end(), s.oldToNewState[q].begin(), s.oldToNewState[q].end()); begin.push_back((int)flat.size()); }
+    o.old_to_new_begin = hold(begin);
+    o.old_to_new = hold(flat);
+  }
+}
+
+void real_guess(vector<Wavefunction>& solution, DiagonalMatrix& e, const SpinBlock& big, const guessWaveTypes& gw, const bool& onedot,
+                const bool& transpose_guess_wave, double additional_noise, int currentState) asm("__real_" SYM_guess_wavefunctions);
+void wrap_guess(vector<Wavefunction>& solution, DiagonalMatrix& e, const SpinBlock& big, const guessWaveTypes& gw, const bool& onedot,
+                const bool& transpose_guess_wave, double additional_noise, int currentState) asm("__wrap_" SYM_guess_wavefunctions);
+void wrap_guess(vector<Wavefunction>& solution, DiagonalMatrix& e, const SpinBlock& big, const guessWaveTypes& gw, const bool& onedot,
+                const bool& transpose_guess_wave, double additional_noise, int currentState) {
+  const char* mode = getenv("B2D_DROPIN_GUESS");
+  const bool on_device = mode && string(mode) == "device" && gw == TRANSFORM && !onedot && g.ctx && big.get_leftBlock()->get_leftBlock() &&
+                         dmrginp.spinAdapted() && dmrginp.hamiltonian() != BCS;
+  if (!on_device) { real_guess(solution, e, big, gw, onedot, transpose_guess_wave, additional_noise, currentState); return; }
+  double t0 = now_s();
+  const StateInfo& bs = big.get_stateInfo();
+  for (size_t i = 0; i < solution.size(); ++i) {
+    const int state = (dmrginp.setStateSpecific() || dmrginp.calc_type() == COMPRESS || dmrginp.calc_type() == MPS_NEVPT) ? currentState : (int)i;
+    solution[i].initialise(dmrginp.effective_molecule_quantum_vec(), &big, onedot);     // guess_wavefunction.C:282
+    StateInfo oldSI;
+    Wavefunction oldWave;
+    vector<Matrix> lrot, rrot;
+    oldWave.LoadWavefunctionInfo(oldSI, big.get_leftBlock()->get_leftBlock()->get_sites(), state);     // :537
+    LoadRotationMatrix(big.get_leftBlock()->get_leftBlock()->get_sites(), lrot, state);                // :538
+    LoadRotationMatrix(big.get_rightBlock()->get_sites(), rrot, state);                                // :613
+    if (oldWave.get_deltaQuantum_size() != 1) die("guess transform: wavefunction with several target quanta: not covered");
+    vector<vector<int32_t> > keep;
+    keep.reserve(128);
+    b2d_guess_desc d;
+    memset(&d, 0, sizeof(d));
+    SpinQuantum dq = oldWave.get_deltaQuantum(0);
+    d.dq[0] = dq.get_n(); d.dq[1] = dq.get_s().getirrep(); d.dq[2] = dq.get_symm().getirrep();
+    fill_stateinfo(d.sys, *bs.leftStateInfo->leftStateInfo, keep);
+    fill_stateinfo(d.dot, *bs.leftStateInfo->rightStateInfo, keep);
+    fill_stateinfo(d.left, *bs.leftStateInfo, keep);
+    fill_stateinfo(d.right, *bs.rightStateInfo, keep);
+    fill_stateinfo(d.oldleft, *oldSI.leftStateInfo, keep);
+    fill_stateinfo(d.oldright, *oldSI.rightStateInfo, keep);
+    fill_stateinfo(d.env, *oldSI.rightStateInfo->leftStateInfo, keep);
+    vector<uint8_t> allowed; vector<double> old, lr, rr;
+    for (int a = 0; a < oldWave.nrows(); ++a) for (int b = 0; b < oldWave.ncols(); ++b) {
+      allowed.push_back(oldWave.allowed(a, b) ? 1 : 0);
+      if (oldWave.allowed(a, b)) { const Matrix& m = oldWave.operator_element(a, b); old.insert(old.end(), m.Store(), m.Store() + m.Storage()); }
+    }
+    vector<int32_t> lcols, rcols;
+    for (size_t q = 0; q < lrot.size(); ++q) { lcols.push_back(lrot[q].Ncols()); if (lrot[q].Ncols()) lr.insert(lr.end(), lrot[q].Store(), lrot[q].Store() + lrot[q].Storage()); }
+    for (size_t q = 0; q < rrot.size(); ++q) { rcols.push_back(rrot[q].Ncols()); if (rrot[q].Ncols()) rr.insert(rr.end(), rrot[q].Store(), rrot[q].Store() + rrot[q].Storage()); }
+    if ((int)lcols.size() != d.oldleft.nq || (int)rcols.size() != d.right.nq) die("guess transform: rotation matrices do not match the StateInfo of their blocks");
+    d.old_allowed = allowed.data(); d.lrot_cols = lcols.data(); d.rrot_cols = rcols.data();
+    double info[8];
+    ck(b2d_guess_plan(g.ctx, &d, info, 8), "b2d_guess_plan");
+    vector<double> flat((size_t)info[3]);
+    if ((int64_t)flat.size() != g.W) die("guess transform: trial vector length differs from the psi layout");
+    if (old.empty()) old.push_back(0); if (lr.empty()) lr.push_back(0); if (rr.empty()) rr.push_back(0);
+    ck(b2d_guess_transform(g.ctx, old.data(), lr.data(), rr.data(), -1, flat.data()), "b2d_guess_transform");
+    collect(solution[i], flat);
+    oldSI.Free();
+    if (env_on("B2D_DROPIN_CHECK")) {
+      vector<Wavefunction> ref(1);
+      real_guess(ref, e, big, gw, onedot, transpose_guess_wave, additional_noise, state);
+      vector<double> rf; flatten(ref[0], rf);
+      double worst = 0, scale = 0;
+      for (size_t k = 0; k < rf.size(); ++k) { worst = std::max(worst, fabs(rf[k] - flat[k])); scale = std::max(scale, fabs(rf[k])); }
+      fprintf(stderr, "B2D_CHECK call=%d guess_transform root=%d max_abs_diff=%.3e (max |psi| %.3e)\n", g.call, (int)i, worst, scale);
+    }
+  }
+  g.t_guess += now_s() - t0;
 }
 
 // ---- SpinBlock::multiplyH ----

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <array>
 #include <map>
 #include <memory>
 #include <string>
@@ -199,6 +200,10 @@ struct b2d_ctx {
     bool set = false;
   } product;
   DevBuf kron_tasks;
+  bool opbuild_batch = false;               // b2d_build_enlarged_op defers its scatter tasks: one launch per ROUND for a whole child block
+  std::vector<KronTask> pend_kron;          // deferred tasks ...
+  std::vector<int> pend_kron_round;         // ... and the round of each: how many earlier tasks hit the same destination piece
+  std::map<std::array<int64_t, 3>, int> pend_kron_hits;
   Side stash[2];                            // children of the big block parked by b2d_stash_product / b2d_stash_side
   bool stash_set[2] = {false, false};
   Integrals integrals;                      // one- / two-electron integrals for the complementary operators (b2d_set_integrals)
@@ -594,6 +599,7 @@ int b2d_reset(b2d_ctx* ctx) {
   ctx->product = b2d_ctx::Product();
   ctx->stash[0] = Side(); ctx->stash[1] = Side(); ctx->stash_set[0] = ctx->stash_set[1] = false;
   ctx->guess = GuessPlan();
+  ctx->pend_kron.clear(); ctx->pend_kron_round.clear(); ctx->pend_kron_hits.clear();
   ctx->timing_valid = false;   // (the integrals belong to the whole calculation: b2d_reset keeps them)
   ctx->err.clear();
   return B2D_OK;
@@ -613,6 +619,7 @@ int b2d_set_option(b2d_ctx* ctx, const char* key, double value) {
   else if (k == "eig_jacobi_max") ctx->eig_jacobi_max = (int)value;
   else if (k == "persistent") ctx->persistent = value != 0;
   else if (k == "phase_timing") ctx->phase_timing = value != 0;
+  else if (k == "opbuild_batch") ctx->opbuild_batch = value != 0;
   else return fail(ctx, B2D_ERR_ARG, "unknown option " + k);
   return B2D_OK;
 }
@@ -1975,6 +1982,7 @@ int b2d_set_product_stateinfo(b2d_ctx* ctx, int nq, const int32_t* q, const int3
                               const int32_t* unc_dims, const int32_t* old_to_new_begin, const int32_t* old_to_new) {
   if (!ctx || nq <= 0 || !q || !dims || nunc <= 0 || !lmap || !rmap || !unc_dims || !old_to_new_begin || !old_to_new)
     return fail(ctx, B2D_ERR_ARG, "b2d_set_product_stateinfo: bad arguments");
+  ctx->pend_kron.clear(); ctx->pend_kron_round.clear(); ctx->pend_kron_hits.clear();   // deferred tasks of a product block nobody stashed
   const Side& L = ctx->side[0];
   const Side& R = ctx->side[1];
   if (L.nq == 0 || R.nq == 0) return fail(ctx, B2D_ERR_ARG, "b2d_set_product_stateinfo: set both children first (b2d_set_block)");
@@ -2022,7 +2030,38 @@ int b2d_product_op_create(b2d_ctx* ctx, const int32_t* dq, int fermion, int* pro
   return B2D_OK;
 }
 
+// Deferred scatter tasks (option opbuild_batch): executed round by round - tasks of one round hit pairwise different destination pieces,
+// a piece receives its contributions in the order they were planned (same summation order as the immediate path: bit-identical).
+static int flush_product_tasks(b2d_ctx* ctx) {
+  if (ctx->pend_kron.empty()) return B2D_OK;
+  { int frc = flush_pending_ops(ctx); if (frc) return frc; }
+  CU(cudaSetDevice(ctx->device));
+  int nrounds = 0;
+  for (int r : ctx->pend_kron_round) nrounds = std::max(nrounds, r + 1);
+  std::vector<int> count(nrounds + 1, 0);
+  for (int r : ctx->pend_kron_round) count[r + 1]++;
+  for (int r = 0; r < nrounds; ++r) count[r + 1] += count[r];
+  std::vector<KronTask> sorted(ctx->pend_kron.size());
+  {
+    std::vector<int> at(count.begin(), count.end() - 1);
+    for (size_t i = 0; i < ctx->pend_kron.size(); ++i) sorted[at[ctx->pend_kron_round[i]]++] = ctx->pend_kron[i];
+  }
+  int rc = upload_desc(ctx, ctx->kron_tasks, sorted.data(), sorted.size() * sizeof(KronTask));
+  if (rc) return rc;
+  for (int r = 0; r < nrounds; ++r)
+    CU(launch_kron_scatter((const KronTask*)ctx->kron_tasks.p + count[r], count[r + 1] - count[r], ctx->stream, &ctx->launches));
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->pend_kron.clear(); ctx->pend_kron_round.clear(); ctx->pend_kron_hits.clear();
+  return B2D_OK;
+}
+
+static int product_op_accumulate_impl(b2d_ctx* ctx, int prod_id, int left_op, int left_transposed, int right_op, int right_transposed, double scale, bool defer);
 int b2d_product_op_accumulate(b2d_ctx* ctx, int prod_id, int left_op, int left_transposed, int right_op, int right_transposed, double scale) {
+  NEED_DEVICE();
+  { int frc = flush_product_tasks(ctx); if (frc) return frc; }   // keep the order of contributions
+  return product_op_accumulate_impl(ctx, prod_id, left_op, left_transposed, right_op, right_transposed, scale, false);
+}
+static int product_op_accumulate_impl(b2d_ctx* ctx, int prod_id, int left_op, int left_transposed, int right_op, int right_transposed, double scale, bool defer) {
   NEED_DEVICE();
   b2d_ctx::Product& P = ctx->product;
   const Side& L = ctx->side[0];
@@ -2074,6 +2113,14 @@ int b2d_product_op_accumulate(b2d_ctx* ctx, int prod_id, int left_op, int left_t
         }
       }
   } catch (const std::exception& e) { return fail(ctx, B2D_ERR_ARG, e.what()); }
+  if (defer) {
+    for (const KronTask& k : tasks) {
+      int& hits = ctx->pend_kron_hits[std::array<int64_t, 3>{k.dst, (int64_t)k.row0, (int64_t)k.col0}];
+      ctx->pend_kron.push_back(k);
+      ctx->pend_kron_round.push_back(hits++);
+    }
+    return B2D_OK;
+  }
   int rc = upload_desc(ctx, ctx->kron_tasks, tasks.data(), tasks.size() * sizeof(KronTask));
   if (rc) return rc;
   CU(launch_kron_scatter((const KronTask*)ctx->kron_tasks.p, (int)tasks.size(), ctx->stream, &ctx->launches));
@@ -2133,7 +2180,8 @@ int b2d_build_enlarged_op(b2d_ctx* ctx, int optype, int norb, const int32_t* orb
     for (int k = 0; k < norb; ++k) op.orbs[k] = orbs[k];
   }
   for (const ProductCall& c : calls) {
-    rc = b2d_product_op_accumulate(ctx, *prod_id, c.lop, c.lt ? 1 : 0, c.rop, c.rt ? 1 : 0, c.scale);
+    rc = ctx->opbuild_batch ? product_op_accumulate_impl(ctx, *prod_id, c.lop, c.lt ? 1 : 0, c.rop, c.rt ? 1 : 0, c.scale, true)
+                            : b2d_product_op_accumulate(ctx, *prod_id, c.lop, c.lt ? 1 : 0, c.rop, c.rt ? 1 : 0, c.scale);
     if (rc) return rc;
   }
   return B2D_OK;
@@ -2143,6 +2191,7 @@ int b2d_build_enlarged_op(b2d_ctx* ctx, int optype, int norb, const int32_t* orb
 // are free to describe the children of the other one.  b2d_assemble_big then makes the two parked blocks the children of the big block.
 int b2d_stash_product(b2d_ctx* ctx, int slot, int is_loop, int nsites, const int32_t* sites) {
   if (!ctx || slot < 0 || slot > 1 || !ctx->product.set) return fail(ctx, B2D_ERR_ARG, "b2d_stash_product: no product block");
+  if (ctx->has_device) { int frc = flush_product_tasks(ctx); if (frc) return frc; }
   Side s = std::move(ctx->product.side);
   s.loop = is_loop != 0;
   s.sites.clear();
@@ -2324,6 +2373,7 @@ int64_t b2d_product_op_size(const b2d_ctx* ctx, int prod_id) {
 int b2d_product_op_download(b2d_ctx* ctx, int prod_id, uint8_t* allowed, double* data) {
   NEED_DEVICE();
   if (!ctx->product.set || prod_id < 0 || prod_id >= (int)ctx->product.side.ops.size()) return fail(ctx, B2D_ERR_ARG, "b2d_product_op_download: bad arguments");
+  { int frc = flush_product_tasks(ctx); if (frc) return frc; }
   const Side& S = ctx->product.side;
   const OpRec& op = S.ops[prod_id];
   if (allowed) memcpy(allowed, op.allowed.data(), op.allowed.size());

@@ -60,7 +60,9 @@ int b2d_abi_version(void);
 
 /* Tuning knobs (all optional): "workspace_mb" (T workspace for the two-step contraction), "max_davidson_iter",
  * "tile_class" (debug: -1 auto, 0/1/2 = square 128/64/32 DMMA tiles everywhere, 3 = auto with the tiny-sector warp kernel,
- * which auto already uses), "sync_debug", "phase_timing". */
+ * which auto already uses), "sync_debug", "phase_timing", "opbuild_batch" (b2d_build_enlarged_op defers its scatter tasks and
+ * b2d_stash_product / b2d_product_op_download run them for the whole block, one launch per round instead of one per product; same
+ * summation order, default off until measured). */
 int b2d_set_option(b2d_ctx* ctx, const char* key, double value);
 
 /* ---- block description: replaces the host-side SpinBlock / StateInfo / Op_component objects ---------------- */

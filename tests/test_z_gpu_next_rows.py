@@ -55,3 +55,38 @@ def test_norm_is_preserved_up_to_truncation():
             assert abs(np.linalg.norm(got) - np.linalg.norm(rec["gw0.trial"])) < 1e-12
         finally:
             gt.close()
+
+
+OPBUILD_FIXTURES = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "opbuild_*.npz")))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", OPBUILD_FIXTURES, ids=[os.path.basename(f)[:-4] for f in OPBUILD_FIXTURES])
+def test_batched_operator_construction_is_bit_identical(path):
+    """Option opbuild_batch: b2d_build_enlarged_op defers its scatter tasks; the whole enlarged block is then built with
+    one launch per round.  Each destination piece receives its contributions in the planned order, so every operator must be
+    BIT-IDENTICAL to the one-launch-per-product path (which tests/test_gpu_opbuild.py pins against the real reference)."""
+    from oracle import dumpio
+    from oracle import opbuild_oracle as B
+    rec = dict(np.load(path))
+    pi, ref, ints = B.ProductInfo.from_record(rec), dumpio.block_from(rec, "LA."), B.Integrals.from_record(rec)
+    hubbard = int(rec["meta"][7]) == B.O.HUBBARD_HAM
+    results, launches = [], []
+    for batch in (0, 1):
+        left, right = hotpath.block_spec_from_record(rec, "LL."), hotpath.block_spec_from_record(rec, "LR.")
+        pb = hotpath.ProductBlock(left, right, pi.q, pi.dims, pi.lmap, pi.rmap, pi.unc_dims, pi.old_to_new, device=0)
+        try:
+            rc = pb.lib.b2d_set_option(pb._ctx, b"opbuild_batch", float(batch))
+            assert rc == 0
+            pb.set_integrals(ints.h1, ints.h2, ints.irreps, ints.one_tol, ints.two_tol)
+            l0 = pb.kernel_launches()
+            ids = [pb.build(op.optype, op.orbs, op.dq, op.fermion, hubbard) for op in ref.ops]
+            out = [pb.download(i)[1].copy() for i in ids]
+            launches.append(pb.kernel_launches() - l0)
+            results.append(out)
+        finally:
+            pb.close()
+    for a, b in zip(*results):
+        assert np.array_equal(a, b)
+    assert launches[1] < launches[0]
+    print("%s: %d launches one per product, %d batched" % (os.path.basename(path), launches[0], launches[1]))

@@ -367,6 +367,21 @@ def sweep_leg(a):
     return out
 
 
+def next_rows_leg(a):
+    """Rows of SURVEY.md 8f behind the C ABI (guess-wavefunction transform, N1) at the benchmark's size, in a process of its own: a
+    failure there is reported under "error" and never touches the measurements above."""
+    cmd = [sys.executable, os.path.join(ROOT, "scripts", "bench_next_rows.py"), "--norbs", str(a.norbs), "--nelec", str(a.nelec), "--M", str(a.M),
+           "--left-sites", str(a.left_sites)]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
+        lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if r.returncode != 0 or not lines:
+            return {"error": (r.stderr or r.stdout)[-400:]}
+        return json.loads(lines[-1])
+    except Exception as e:   # noqa: BLE001
+        return {"error": repr(e)[:400]}
+
+
 def run_ours(a):
     import torch
     import torch.distributed as dist
@@ -542,6 +557,8 @@ def run_ours(a):
     sb.close()
     if line is not None and world == 1 and not a.no_sweep:
         line["sweep"] = sweep_leg(a)
+    if line is not None and world == 1 and not a.no_block_iteration:
+        line["guess_transform"] = next_rows_leg(a)
     if line is not None:
         emit(line)
     if world > 1:

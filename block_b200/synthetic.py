@@ -150,3 +150,76 @@ def fill_random(sb: SpinBlock, seed, rank=0, nranks=1):
                 continue
             s, amp = fill_params(blk.dims, side, k, op.optype, seed)
             sb.fill_op_random(side, sb.op_ids[side][k], s, amplitude=amp, symmetric=op.optype == HAM)
+
+
+# ---- guess-wavefunction transform of the same shape ----------------------------------------------------------------
+DOT = ((0, 0), (1, 1), (2, 0))     # sectors of one spin-adapted site: (N, 2S), one state each
+
+
+def product_tables(sectors, dims):
+    """StateInfo tables of (block) x (one site) as b2d_stateinfo wants them: un-collected pieces in (block sector outer, dot sector
+    inner, coupled spin increasing) order, collected quanta sorted by (N, 2S); C1 symmetry."""
+    unc_q, unc_dims, lmap, rmap = [], [], [], []
+    for a, (N, s) in enumerate(sectors):
+        for b, (dn, ds) in enumerate(DOT):
+            for s2 in ([s] if ds == 0 else [s - 1, s + 1]):
+                if s2 < 0:
+                    continue
+                unc_q.append((N + dn, s2, 0)); unc_dims.append(int(dims[a])); lmap.append(a); rmap.append(b)
+    keys = sorted(set(unc_q))
+    index = {k: i for i, k in enumerate(keys)}
+    pieces = [[] for _ in keys]
+    for u, k in enumerate(unc_q):
+        pieces[index[k]].append(u)
+    begin = np.zeros(len(keys) + 1, np.int32)
+    begin[1:] = np.cumsum([len(p) for p in pieces])
+    return {"q": np.array(keys, np.int32), "dims": np.array([sum(unc_dims[u] for u in p) for p in pieces], np.int32),
+            "unc.q": np.array(unc_q, np.int32), "unc.dims": np.array(unc_dims, np.int32), "unc.lmap": np.array(lmap, np.int32),
+            "unc.rmap": np.array(rmap, np.int32), "old_to_new": np.array([u for p in pieces for u in p], np.int32), "old_to_new_begin": begin}
+
+
+def make_guess_case(norbs=40, nelec=40, M=4000, left_sites=None, seed=20260, sigma_n=2.2, sigma_s=1.6):
+    """Inputs of b2d_guess_plan / b2d_guess_transform for the block iteration make_big_block describes: previous wavefunction
+    [S (x) d1][E_old (x) d2] -> trial vector [S' (x) d2][d3 (x) E''] (guess_wavefunction.C:524-636).  Returns (dq, tables, old_allowed,
+    lrot_cols, rrot_cols, old_wave, left_rot, right_rot); values are seeded random numbers (throughput does not depend on them)."""
+    nl = norbs // 2 if left_sites is None else left_sites
+    nr = norbs - nl
+    f = nelec / norbs
+    rs = lambda n: renormalised_sectors(n, f * n, M, sigma_n, sigma_s)
+    oldleft = add_dot(rs(nl - 2))                       # S (x) d1, collected: the basis the left rotation matrix truncates
+    sys = {k: min(d, oldleft[k]) for k, d in rs(nl - 1).items() if k in oldleft}      # S': M states
+    right = add_dot(rs(nr - 1))                         # d3 (x) E'', collected: the basis the right rotation matrix truncated
+    env = {k: min(d, right[k]) for k, d in rs(nr).items() if k in right}             # E_old: M states
+    q3 = lambda d: np.array([[N, s, 0] for (N, s) in d], np.int32)
+    dims = lambda d: np.array(list(d.values()), np.int32)
+    okeys, rkeys = list(oldleft), list(right)
+    tables = {
+        "sys": {"q": q3(sys), "dims": dims(sys), "new_quanta_map": np.array([okeys.index(k) for k in sys], np.int32)},
+        "dot": {"q": np.array([[n, s, 0] for (n, s) in DOT], np.int32), "dims": np.ones(3, np.int32)},
+        "left": product_tables(list(sys), dims(sys)),
+        "right": {"q": q3(right), "dims": dims(right)},
+        "oldleft": {"q": q3(oldleft), "dims": dims(oldleft)},
+        "oldright": product_tables(list(env), dims(env)),
+        "env": {"q": q3(env), "dims": dims(env), "new_quanta_map": np.array([rkeys.index(k) for k in env], np.int32)},
+    }
+    dq = (nelec, 0, 0)
+    ol, orr = tables["oldleft"], tables["oldright"]
+    old_allowed = (allowed_mask_pair(ol["q"], orr["q"], dq)).astype(np.uint8)
+    lrot_cols = np.zeros(len(okeys), np.int32)
+    for k, m in sys.items():
+        lrot_cols[okeys.index(k)] = m
+    rrot_cols = np.zeros(len(rkeys), np.int32)
+    for k, m in env.items():
+        rrot_cols[rkeys.index(k)] = m
+    rng = np.random.default_rng(seed)
+    n_old = int((old_allowed * np.outer(ol["dims"], orr["dims"])).sum())
+    old_wave = rng.standard_normal(n_old) / math.sqrt(max(n_old, 1))
+    left_rot = rng.standard_normal(int((ol["dims"] * lrot_cols).sum())) * 0.02
+    right_rot = rng.standard_normal(int((tables["right"]["dims"] * rrot_cols).sum())) * 0.02
+    return dq, tables, old_allowed, lrot_cols, rrot_cols, old_wave, left_rot, right_rot
+
+
+def allowed_mask_pair(ql, qr, dq):
+    """Wavefunction::AllowQuantaFor (wavefunction.C:393-415): block (i, j) exists iff dq is in q_i x q_j (C1)."""
+    Nl, Sl, Nr, Sr = ql[:, 0][:, None], ql[:, 1][:, None], qr[:, 0][None, :], qr[:, 1][None, :]
+    return (Nl + Nr == dq[0]) & (np.abs(Sl - Sr) <= dq[1]) & (dq[1] <= Sl + Sr) & ((Sl + Sr + dq[1]) % 2 == 0)

@@ -129,3 +129,20 @@ def test_no_cpu_fallback_and_argument_checks():
     bad["dot"] = dict(bad["dot"], dims=np.array([1, 2, 1], np.int32))
     with pytest.raises(hotpath.B2DError, match="dot sectors"):
         hotpath.GuessTransform(rec["gw0.dq"][:3], bad, rec["gw0.old.allowed"], rec["gw0.lrot.shape"][:, 1], rec["gw0.rrot.shape"][:, 1], device=-1)
+
+
+@pytest.mark.parametrize("M", [60, 600])
+def test_synthetic_case_plans_and_executes(M):
+    """CPU: the synthetic sector tables bench.py's guess-transform leg uses are consistent (b2d_guess_plan accepts them) and the plan
+    is linear and non-trivial when executed with numpy."""
+    from block_b200 import synthetic
+    dq, tables, allowed, lcols, rcols, old, lrot, rrot = synthetic.make_guess_case(16, 16, M, 8)
+    gt = hotpath.GuessTransform(dq, tables, allowed, lcols, rcols, device=-1)
+    try:
+        assert (gt.old_size, gt.lrot_size, gt.rrot_size) == (old.size, lrot.size, rrot.size)
+        a = execute_plan(gt, old, lrot, rrot)
+        b = execute_plan(gt, 2.0 * old, lrot, rrot)
+        assert np.linalg.norm(a) > 0 and np.linalg.norm(b - 2.0 * a) <= 1e-14 * np.linalg.norm(a)
+        assert gt.flops > 0 and gt.shuffle_tasks > 0
+    finally:
+        gt.close()

@@ -90,3 +90,24 @@ def test_batched_operator_construction_is_bit_identical(path):
         assert np.array_equal(a, b)
     assert launches[1] < launches[0]
     print("%s: %d launches one per product, %d batched" % (os.path.basename(path), launches[0], launches[1]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("M", [60, 600])
+def test_device_transform_on_synthetic_sectors_matches_the_plan_executed_with_numpy(M):
+    """Sectors of up to a few hundred states (every DMMA tile class, not only the warp kernel the small golden cases reach): the
+    device result against the same plan executed descriptor by descriptor with numpy (tests/test_guess_planner_cpu.py pins that
+    executor + planner against the real reference)."""
+    from block_b200 import synthetic
+    from test_guess_planner_cpu import execute_plan
+    dq, tables, allowed, lcols, rcols, old, lrot, rrot = synthetic.make_guess_case(16, 16, M, 8)
+    gt = hotpath.GuessTransform(dq, tables, allowed, lcols, rcols, device=0)
+    try:
+        got = gt.transform(old, lrot, rrot)
+        ref = execute_plan(gt, old, lrot, rrot)
+        assert np.linalg.norm(ref) > 0
+        err = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+        assert err < 1e-12, err
+        print("synthetic M = %d: W = %d, %d shuffle tasks, relative difference %.1e" % (M, got.size, gt.shuffle_tasks, err))
+    finally:
+        gt.close()

@@ -321,8 +321,10 @@ def sweep_leg(a):
     """BASELINE.json's other headline figure, "two-site sweep wall time ... energy delta vs ref": the UNMODIFIED reference sweep
     (oracle/_ref/block.spin_adapted, all host threads) next to the same reference sweep with its hot path re-routed to this library
     (oracle/_ref/block_gpu, tests/dropin/block_gpu_hooks.cpp) on one real FCIDUMP / dmrg.conf case of tests/golden/dropin_cases.npz.
-    Both run here, back to back, on this box; energies are compared sweep by sweep.  Host-side block construction (the reference's
-    own Op::build, SURVEY N2) is inside both times."""
+    Both run here, back to back, on this box; energies are compared sweep by sweep.  Block construction is inside both times (the
+    drop-in builds the children of the big block on the device).  A third run, "gpu_dropin_next_rows", switches on what
+    was finished after this round's GPU budget was spent (batched operator construction, guess-wavefunction transform on the device:
+    B2D_DROPIN_OPTIONS=opbuild_batch=1, B2D_DROPIN_GUESS=device); it is reported beside the other two and never replaces them."""
     import re
     gpu_bin = os.path.join(ROOT, "oracle", "_ref", "block_gpu")
     ref_bin = os.path.join(ROOT, "oracle", "_ref", "block.spin_adapted")
@@ -335,15 +337,21 @@ def sweep_leg(a):
     pat = re.compile(r"M = (\d+)\s+state = (\d+)\s+Largest Discarded Weight = (\S+)\s+Sweep Energy = (\S+)")
     out = {"case": name, "host_threads": threads}
     energies = {}
-    for tag, exe in (("reference_cpu", ref_bin), ("gpu_dropin", gpu_bin)):
+    for tag, exe in (("reference_cpu", ref_bin), ("gpu_dropin", gpu_bin), ("gpu_dropin_next_rows", gpu_bin)):
         work = tempfile.mkdtemp(prefix="sweep_%s_" % tag)
         for f in z[name + "/files"]:
             open(os.path.join(work, str(f)), "wb").write(z["%s/file/%s" % (name, f)].tobytes())
         conf = z[name + "/conf"].tobytes().decode() + "threads_per_node %d\n" % threads
         open(os.path.join(work, "dmrg.conf"), "w").write(conf)
         env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS=str(threads), B2D_DROPIN_STATS=os.path.join(work, "stats.txt"))
+        if tag == "gpu_dropin_next_rows":
+            env.update(B2D_DROPIN_OPTIONS="opbuild_batch=1", B2D_DROPIN_GUESS="device")
         t0 = time.perf_counter()
-        r = subprocess.run([exe, "dmrg.conf"], cwd=work, env=env, capture_output=True, text=True)
+        try:
+            r = subprocess.run([exe, "dmrg.conf"], cwd=work, env=env, capture_output=True, text=True, timeout=900)
+        except subprocess.TimeoutExpired:
+            out[tag] = {"failed": "timeout"}
+            continue
         dt = time.perf_counter() - t0
         if r.returncode != 0:
             out[tag] = {"failed": (r.stderr or r.stdout)[-300:]}
@@ -351,15 +359,17 @@ def sweep_leg(a):
         e = [float(m.group(4)) for m in pat.finditer(r.stdout)]
         energies[tag] = e
         out[tag] = {"wall_s": dt, "sweep_lines": len(e), "final_energy": e[-1] if e else None}
-        if tag == "gpu_dropin" and os.path.exists(os.path.join(work, "stats.txt")):
+        if tag.startswith("gpu_dropin") and os.path.exists(os.path.join(work, "stats.txt")):
             tot = {}
             for l in open(os.path.join(work, "stats.txt")):
                 for k, v in re.findall(r"(\w+)=([-\d.e+]+)", l):
                     tot[k] = tot.get(k, 0.0) + float(v)
-            out[tag]["hot_path_s"] = {k: tot.get(k, 0.0) for k in ("host_op_build_s", "upload_s", "diag_s", "davidson_s", "density_s", "eig_s", "rotate_s")}
+            out[tag]["hot_path_s"] = {k: tot.get(k, 0.0) for k in ("host_op_build_s", "upload_s", "guess_s", "diag_s", "davidson_s", "density_s", "eig_s", "rotate_s")}
             out[tag]["n_multiply"] = int(tot.get("n_multiply", 0))
             out[tag]["kernel_launches"] = int(tot.get("launches", 0))
-    if len(energies) == 2 and len(energies["reference_cpu"]) == len(energies["gpu_dropin"]):
+    if "reference_cpu" in energies and "gpu_dropin_next_rows" in energies and len(energies["reference_cpu"]) == len(energies["gpu_dropin_next_rows"]):
+        out["gpu_dropin_next_rows"]["max_abs_dE_per_sweep"] = max(abs(x - y) for x, y in zip(energies["reference_cpu"], energies["gpu_dropin_next_rows"]))
+    if "reference_cpu" in energies and "gpu_dropin" in energies and len(energies["reference_cpu"]) == len(energies["gpu_dropin"]):
         out["max_abs_dE_per_sweep"] = max(abs(x - y) for x, y in zip(energies["reference_cpu"], energies["gpu_dropin"]))
         golden = [float(m.group(4)) for m in pat.finditer(z[name + "/sweeps"].tobytes().decode())] if name + "/sweeps" in z.files else []
         if golden and len(golden) == len(energies["gpu_dropin"]):

@@ -431,6 +431,20 @@ void wrap_guess(vector<Wavefunction>& solution, DiagonalMatrix& e, const SpinBlo
   }
 }
 
+// ORACLE_TIMING: where the reference spends its time outside the hot path (scratch files)
+double g_store_s = 0, g_restore_s = 0; long g_store_n = 0, g_restore_n = 0;
+struct IoReport { ~IoReport() { if (getenv("ORACLE_TIMING")) fprintf(stderr, "ORACLE_IO store_s=%.3f (%ld calls) restore_s=%.3f (%ld calls)\n", g_store_s, g_store_n, g_restore_s, g_restore_n); } } g_io_report;
+void real_store(bool forward, const vector<int>& sites, SpinBlock& b, int left, int right, char* name) asm("__real_" SYM_store);
+void wrap_store(bool forward, const vector<int>& sites, SpinBlock& b, int left, int right, char* name) asm("__wrap_" SYM_store);
+void wrap_store(bool forward, const vector<int>& sites, SpinBlock& b, int left, int right, char* name) {
+  double t0 = now_s(); real_store(forward, sites, b, left, right, name); g_store_s += now_s() - t0; ++g_store_n;
+}
+string real_restore(bool forward, const vector<int>& sites, SpinBlock& b, int left, int right, char* name) asm("__real_" SYM_restore);
+string wrap_restore(bool forward, const vector<int>& sites, SpinBlock& b, int left, int right, char* name) asm("__wrap_" SYM_restore);
+string wrap_restore(bool forward, const vector<int>& sites, SpinBlock& b, int left, int right, char* name) {
+  double t0 = now_s(); string r = real_restore(forward, sites, b, left, right, name); g_restore_s += now_s() - t0; ++g_restore_n; return r;
+}
+
 void real_multiplyH(const SpinBlock* self, Wavefunction& c, Wavefunction* v, int num_threads) asm("__real_" SYM_multiplyH);
 void wrap_multiplyH(const SpinBlock* self, Wavefunction& c, Wavefunction* v, int num_threads) asm("__wrap_" SYM_multiplyH);
 void wrap_multiplyH(const SpinBlock* self, Wavefunction& c, Wavefunction* v, int num_threads) {

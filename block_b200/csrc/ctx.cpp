@@ -2322,6 +2322,7 @@ int b2d_guess_transform(b2d_ctx* ctx, const double* old_wave, const double* left
   { Chunk c; c.step1 = P.stage1; c.nterms = 1; c.work = P.work_size; S1.chunks.push_back(std::move(c)); S1.work_max = P.work_size; }
   { Chunk c; c.step1 = P.stage3; c.nterms = 1; c.work = P.work_size; S3.chunks.push_back(std::move(c)); S3.work_max = P.work_size; }
   DevSchedule D1, D3;
+  struct Release { DevSchedule &a, &b; ~Release() { a.buf.release(); b.buf.release(); } } release_schedules{D1, D3};   // on every return path
   rc = upload_schedule(ctx, S1, D1);
   if (rc) return rc;
   rc = upload_schedule(ctx, S3, D3);
@@ -2361,7 +2362,6 @@ int b2d_guess_transform(b2d_ctx* ctx, const double* old_wave, const double* left
     CU(cudaMemcpyAsync(trial, ctx->staging.p, (size_t)P.trial.W * 8, cudaMemcpyDeviceToHost, ctx->stream));
   }
   CU(cudaStreamSynchronize(ctx->stream));
-  D1.buf.release(); D3.buf.release();
   return B2D_OK;
 }
 

@@ -512,7 +512,7 @@ void end_timing(b2d_ctx* ctx) { cudaEventRecord(ctx->ev[1], ctx->stream); }
 
 extern "C" {
 
-int b2d_abi_version(void) { return 2; }
+int b2d_abi_version(void) { return 3; }   // 3: b2d_build_enlarged_op takes the spin component; stash / assemble, guess transform
 
 int b2d_create(int device, b2d_ctx** out) {
   if (!out) return B2D_ERR_ARG;

@@ -56,7 +56,7 @@ void b2d_destroy(b2d_ctx* ctx);
  * context and resets it between block iterations (the reference builds a new `big` SpinBlock per block iteration, sweep.C:182). */
 int b2d_reset(b2d_ctx* ctx);
 const char* b2d_last_error(const b2d_ctx* ctx);   /* ctx may be NULL: last error of a failed b2d_create */
-int b2d_abi_version(void);
+int b2d_abi_version(void);                        /* 3 */
 
 /* Tuning knobs (all optional): "workspace_mb" (T workspace for the two-step contraction), "max_davidson_iter",
  * "tile_class" (debug: -1 auto, 0/1/2 = square 128/64/32 DMMA tiles everywhere, 3 = auto with the tiny-sector warp kernel,

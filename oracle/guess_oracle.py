@@ -165,3 +165,40 @@ def transform_previous_wavefunction(rec, root):
     t2 = shuffle_sysdot(t1, sys, dot, env, oldright, left, dq)
     t3 = transform_right_block(t2, env, right, rrot, dq, left)
     return flatten(t3, len(left["dims"]), len(right["dims"]), dq, left["q"], right["q"], left["dims"], right["dims"])
+
+
+# ---- one-dot branch: GuessWave::onedot_transform_wavefunction (guess_wavefunction.C:832-936) ---------------------------------------
+def onedot_rotate(old, oldleft, oldcol, rows, cols_dims, lrot, rrot):
+    """:870-911.  tmp(a, transC) = old(a, c) . R[transC]^T for every block of the previous wavefunction (transC = newQuantaMap of
+    its column sector), then new(a', c) = L[oldA]^T . tmp(oldA, c) with oldA = newQuantaMap of the new row sector a'."""
+    ncol = len(cols_dims)
+    tmp = {}
+    for (a, c), m in old.items():
+        tc = int(oldcol["new_quanta_map"][c])
+        tmp[(a, tc)] = m @ rrot[tc].T
+    out = {}
+    for c in range(ncol):
+        for a in range(len(rows["dims"])):
+            olda = int(rows["new_quanta_map"][a])
+            if (olda, c) in tmp:
+                out[(a, c)] = lrot[olda].T @ tmp[(olda, c)]
+    return out
+
+
+def transform_previous_wavefunction_onedot(rec, root):
+    """The one-dot trial vector of root `root`, flat in FlattenInto order.  transpose_guess_wave (dot on the system side): the rotated
+    wavefunction is in [S'][E'.dot] form and the dot is moved to the system by the same shuffle as in the two-dot case."""
+    p = "gw%d." % root
+    dq = rec[p + "dq"][:3]
+    transpose = int(rec["gw.nroots"][1]) != 0
+    left, right, oldleft, oldcol = (stateinfo(rec, p + n + ".") for n in ("left", "right", "oldleft", "oldcol"))
+    old = unpack_blocks(rec[p + "old.allowed"], rec[p + "old.data"], oldleft["dims"], oldcol["dims"])
+    lrot = unpack_rotation(rec[p + "lrot.shape"], rec[p + "lrot.data"])
+    rrot = unpack_rotation(rec[p + "rrot.shape"], rec[p + "rrot.data"])
+    if not transpose:
+        t = onedot_rotate(old, oldleft, oldcol, left, right["dims"], lrot, rrot)
+        return flatten(t, len(left["dims"]), len(right["dims"]), dq, left["q"], right["q"], left["dims"], right["dims"])
+    sys, dot, newenv = (stateinfo(rec, p + n + ".") for n in ("sys", "dot", "newenv"))
+    t1 = onedot_rotate(old, oldleft, oldcol, sys, newenv["dims"], lrot, rrot)          # [S'][E'.dot]
+    t2 = shuffle_sysdot(t1, sys, dot, right, newenv, left, dq)                          # -> [S'.dot][E']
+    return flatten(t2, len(left["dims"]), len(right["dims"]), dq, left["q"], right["q"], left["dims"], right["dims"])

@@ -18,6 +18,7 @@
 //
 // Record format (little endian): repeated { u32 name_len, name, u8 dtype (0=i32,1=f64), u32 ndim, u64 dims[ndim], data }.
 #include <sys/time.h>
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
@@ -389,6 +390,63 @@ void wrap_guess(vector<Wavefunction>& solution, DiagonalMatrix& e, const SpinBlo
 void wrap_guess(vector<Wavefunction>& solution, DiagonalMatrix& e, const SpinBlock& big, const guessWaveTypes& gw, const bool& onedot,
                 const bool& transpose_guess_wave, double additional_noise, int currentState) {
   real_guess(solution, e, big, gw, onedot, transpose_guess_wave, additional_noise, currentState);
+  if (getenv("ORACLE_DUMP_GUESS") && gw == TRANSFORM && onedot && want_dump(g_call) && big.get_leftBlock()->get_leftBlock()) {
+    // one-dot branch (guess_wavefunction.C:600-628 -> onedot_transform_wavefunction :832-936): a file of its own, because the
+    // RenormaliseFrom record is not written for one-dot steps with the dot on the environment side
+    std::ostringstream fp; fp << getenv("ORACLE_DUMP_DIR") << "/guess1dot_" << g_call << ".bin";
+    Dumper d; d.open(fp.str(), false);
+    const int nroots = (int)solution.size();
+    d.ints("meta", vector<int>{g_call, big.get_leftBlock()->get_sites()[0] == 0, 1, (int)transpose_guess_wave});
+    d.ints("gw.nroots", vector<int>{nroots, (int)transpose_guess_wave});
+    const StateInfo& bs = big.get_stateInfo();
+    for (int i = 0; i < nroots; ++i) {
+      const int state = (dmrginp.setStateSpecific() || dmrginp.calc_type() == COMPRESS || dmrginp.calc_type() == MPS_NEVPT) ? currentState : i;
+      std::ostringstream pp; pp << "gw" << i << ".";
+      const string p = pp.str();
+      StateInfo oldSI; Wavefunction oldWave; vector<Matrix> lrot, rrot;
+      if (transpose_guess_wave) {
+        oldWave.LoadWavefunctionInfo(oldSI, big.get_leftBlock()->get_leftBlock()->get_sites(), state);
+        LoadRotationMatrix(big.get_leftBlock()->get_leftBlock()->get_sites(), lrot, state);
+        vector<int> rotsites = big.get_rightBlock()->get_sites();
+        rotsites.insert(rotsites.end(), big.get_leftBlock()->get_rightBlock()->get_sites().begin(), big.get_leftBlock()->get_rightBlock()->get_sites().end());
+        std::sort(rotsites.begin(), rotsites.end());
+        LoadRotationMatrix(rotsites, rrot, state);
+      } else {
+        oldWave.LoadWavefunctionInfo(oldSI, big.get_leftBlock()->get_sites(), state);
+        LoadRotationMatrix(big.get_leftBlock()->get_sites(), lrot, state);
+        LoadRotationMatrix(big.get_rightBlock()->get_sites(), rrot, state);
+      }
+      SpinQuantum dq = oldWave.get_deltaQuantum(0);
+      d.ints(p + "dq", vector<int>{dq.get_n(), dq.get_s().getirrep(), dq.get_symm().getirrep(), (int)oldWave.get_deltaQuantum_size()});
+      dump_si_tables(d, p + "left.", *bs.leftStateInfo);
+      dump_si_tables(d, p + "right.", *bs.rightStateInfo);
+      dump_si_tables(d, p + "oldleft.", *oldSI.leftStateInfo);
+      dump_si_tables(d, p + "oldcol.", *oldSI.rightStateInfo);
+      if (transpose_guess_wave) {
+        dump_si_tables(d, p + "sys.", *bs.leftStateInfo->leftStateInfo);
+        dump_si_tables(d, p + "dot.", *bs.leftStateInfo->rightStateInfo);
+        StateInfo newenv;     // guess_wavefunction.C:853-856
+        TensorProduct(*(bs.rightStateInfo), *(bs.leftStateInfo->rightStateInfo), newenv, NO_PARTICLE_SPIN_NUMBER_CONSTRAINT);
+        newenv.CollectQuanta();
+        dump_si_tables(d, p + "newenv.", newenv);
+      }
+      vector<int> allowed; vector<double> data;
+      for (int a = 0; a < oldWave.nrows(); ++a) for (int b = 0; b < oldWave.ncols(); ++b) {
+        allowed.push_back(oldWave.allowed(a, b) ? 1 : 0);
+        if (oldWave.allowed(a, b)) { const Matrix& m = oldWave.operator_element(a, b); data.insert(data.end(), m.Store(), m.Store() + m.Storage()); }
+      }
+      d.ints(p + "old.allowed", allowed, {(uint64_t)oldWave.nrows(), (uint64_t)oldWave.ncols()});
+      d.dbls(p + "old.data", data);
+      dump_rotation(d, p + "lrot.", lrot);
+      dump_rotation(d, p + "rrot.", rrot);
+      vector<int> tallowed;
+      for (int l = 0; l < solution[i].nrows(); ++l) for (int r = 0; r < solution[i].ncols(); ++r) tallowed.push_back(solution[i].allowed(l, r) ? 1 : 0);
+      d.ints(p + "trial.allowed", tallowed, {(uint64_t)solution[i].nrows(), (uint64_t)solution[i].ncols()});
+      vector<double> flat; flatten(solution[i], flat); d.dbls(p + "trial", flat);
+      oldSI.Free();
+    }
+    return;
+  }
   if (!g_dump_this || !getenv("ORACLE_DUMP_GUESS") || gw != TRANSFORM || onedot) return;
   Dumper d; d.open(g_path, true);
   const int nroots = (int)solution.size();

@@ -44,3 +44,26 @@ def test_trial_layout_is_the_big_block_wavefunction(path):
     dq = rec["gw0.dq"][:3]
     mask = np.array([[G.allow(dq, left["q"][i], right["q"][j]) for j in range(len(right["dims"]))] for i in range(len(left["dims"]))], dtype=np.int32)
     assert (mask == rec["gw0.trial.allowed"]).all()
+
+
+ONEDOT = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "guess1dot_*.npz")))
+
+
+@pytest.mark.parametrize("path", ONEDOT, ids=[os.path.basename(f)[:-4] for f in ONEDOT])
+def test_onedot_transform_matches_reference(path):
+    """One-dot branch (GuessWave::onedot_transform_wavefunction, guess_wavefunction.C:832-936): dot on the system side (rotate, then
+    shuffle the dot from the environment to the system) and dot on the environment side (rotate only)."""
+    rec = dict(np.load(path))
+    for root in range(int(rec["gw.nroots"][0])):
+        ref = rec["gw%d.trial" % root]
+        got = G.transform_previous_wavefunction_onedot(rec, root)
+        assert got.shape == ref.shape and np.linalg.norm(ref) > 0.5
+        assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-13, path
+
+
+def test_onedot_fixtures_cover_both_dot_positions():
+    flags = set()
+    for f in ONEDOT:
+        with np.load(f) as z:
+            flags.add(int(z["gw.nroots"][1]))
+    assert flags == {0, 1}

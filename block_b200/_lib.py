@@ -27,9 +27,9 @@ class StateInfoC(C.Structure):
 
 class GuessDescC(C.Structure):
     """b2d_guess_desc (include/block_b200.h)."""
-    _fields_ = [("dq", C.c_int32 * 3), ("sys", StateInfoC), ("dot", StateInfoC), ("left", StateInfoC), ("right", StateInfoC),
-                ("oldleft", StateInfoC), ("oldright", StateInfoC), ("env", StateInfoC), ("old_allowed", c_u8p), ("lrot_cols", c_i32p),
-                ("rrot_cols", c_i32p)]
+    _fields_ = [("dq", C.c_int32 * 3), ("mode", C.c_int32), ("sys", StateInfoC), ("dot", StateInfoC), ("left", StateInfoC), ("right", StateInfoC),
+                ("oldleft", StateInfoC), ("oldright", StateInfoC), ("env", StateInfoC), ("oldcol", StateInfoC), ("old_allowed", c_u8p),
+                ("lrot_cols", c_i32p), ("rrot_cols", c_i32p)]
 
 
 # name: (restype, [argtypes])  -- one entry per function declared in include/block_b200.h

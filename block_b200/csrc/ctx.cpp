@@ -2242,12 +2242,14 @@ int64_t b2d_guess_plan_export(const b2d_ctx* ctx, int what, void* out, int64_t c
   std::vector<char> buf;
   auto put = [&](const void* p, size_t bytes) { const char* c = (const char*)p; buf.insert(buf.end(), c, c + bytes); };
   switch (what) {
-    case 0: put(P.stage1.segs.data(), P.stage1.segs.size() * sizeof(GSeg)); break;
-    case 1: put(P.stage1.groups.data(), P.stage1.groups.size() * sizeof(GGroup)); break;
+    case 0: put(P.gemm_a.segs.data(), P.gemm_a.segs.size() * sizeof(GSeg)); break;
+    case 1: put(P.gemm_a.groups.data(), P.gemm_a.groups.size() * sizeof(GGroup)); break;
+    case 10: put(P.gemm_b.segs.data(), P.gemm_b.segs.size() * sizeof(GSeg)); break;
+    case 11: put(P.gemm_b.groups.data(), P.gemm_b.groups.size() * sizeof(GGroup)); break;
     case 2: for (const auto& r : P.rounds) put(r.data(), r.size() * sizeof(KronTask)); break;
     case 3: for (const auto& r : P.rounds) { int32_t c = (int32_t)r.size(); put(&c, 4); } break;
-    case 4: put(P.stage3.segs.data(), P.stage3.segs.size() * sizeof(GSeg)); break;
-    case 5: put(P.stage3.groups.data(), P.stage3.groups.size() * sizeof(GGroup)); break;
+    case 4: put(P.gemm_c.segs.data(), P.gemm_c.segs.size() * sizeof(GSeg)); break;
+    case 5: put(P.gemm_c.groups.data(), P.gemm_c.groups.size() * sizeof(GGroup)); break;
     case 6:
       put(P.in_old.data(), P.in_old.size() * sizeof(BlockDesc)); put(P.in_lrot.data(), P.in_lrot.size() * sizeof(BlockDesc));
       put(P.in_rrot.data(), P.in_rrot.size() * sizeof(BlockDesc));
@@ -2317,10 +2319,10 @@ int b2d_guess_transform(b2d_ctx* ctx, const double* old_wave, const double* left
   CU(cudaMemsetAsync(dst, 0, (size_t)P.trial.Wp * 8, ctx->stream));
   CU(ctx->work.reserve((size_t)std::max<int64_t>(P.work_size, 16) * 8));
   if (P.work_size > P.t2_off) CU(cudaMemsetAsync((double*)ctx->work.p + P.t2_off, 0, (size_t)(P.work_size - P.t2_off) * 8, ctx->stream));
-  // 3. stage 1 (grouped GEMM), stage 2 (scatter rounds), stage 3 (grouped GEMM)
+  // 3. contraction batch a, batch b (one-dot), the shuffle rounds, batch c (two-dot)
   Schedule S1, S3;
-  { Chunk c; c.step1 = P.stage1; c.nterms = 1; c.work = P.work_size; S1.chunks.push_back(std::move(c)); S1.work_max = P.work_size; }
-  { Chunk c; c.step1 = P.stage3; c.nterms = 1; c.work = P.work_size; S3.chunks.push_back(std::move(c)); S3.work_max = P.work_size; }
+  { Chunk c; c.step1 = P.gemm_a; c.step2 = P.gemm_b; c.nterms = 1; c.work = P.work_size; S1.chunks.push_back(std::move(c)); S1.work_max = P.work_size; }
+  { Chunk c; c.step1 = P.gemm_c; c.nterms = 1; c.work = P.work_size; S3.chunks.push_back(std::move(c)); S3.work_max = P.work_size; }
   DevSchedule D1, D3;
   struct Release { DevSchedule &a, &b; ~Release() { a.buf.release(); b.buf.release(); } } release_schedules{D1, D3};   // on every return path
   rc = upload_schedule(ctx, S1, D1);
@@ -2335,7 +2337,8 @@ int b2d_guess_transform(b2d_ctx* ctx, const double* old_wave, const double* left
     for (const auto& r : P.rounds)
       for (KronTask t : r) {
         t.a = (int64_t)(intptr_t)((double*)ctx->work.p + t.a);
-        t.dst = (int64_t)(intptr_t)((double*)ctx->work.p + t.dst);
+        t.dst = (int64_t)(intptr_t)((t.pad ? dst : (double*)ctx->work.p) + t.dst);   // pad = 1: the shuffle writes the trial vector
+        t.pad = 0;
         tasks.push_back(t);
       }
     rc = upload_desc(ctx, ctx->kron_tasks, tasks.data(), tasks.size() * sizeof(KronTask));

@@ -519,8 +519,11 @@ class GuessTransform:
     "unc.rmap", "old_to_new", "old_to_new_begin"."""
 
     NAMES = ("sys", "dot", "left", "right", "oldleft", "oldright", "env")
+    NAMES_BY_MODE = {0: NAMES, 1: ("sys", "dot", "left", "right", "oldleft", "oldright", "oldcol"), 2: ("left", "right", "oldleft", "oldcol")}
 
-    def __init__(self, dq, tables, old_allowed, lrot_cols, rrot_cols, device=0, ctx=None):
+    def __init__(self, dq, tables, old_allowed, lrot_cols, rrot_cols, device=0, ctx=None, mode=0):
+        """mode 0: two-dot step; 1: one-dot, dot on the system side ("oldright" = the reference's newenvstateinfo); 2: one-dot, dot on
+        the environment side (see b2d_guess_desc)."""
         self.lib = _lib.load()
         self._own = ctx is None
         if ctx is None:
@@ -558,7 +561,8 @@ class GuessTransform:
         d = _lib.GuessDescC()
         for k in range(3):
             d.dq[k] = int(dq[k])
-        for name in self.NAMES:
+        d.mode = int(mode)
+        for name in self.NAMES_BY_MODE[int(mode)]:
             setattr(d, name, si(tables[name]))
         d.old_allowed = _p(arr(old_allowed, np.uint8).reshape(-1), _lib.c_u8p)
         d.lrot_cols = _p(arr(lrot_cols), _lib.c_i32p)

@@ -319,10 +319,21 @@ typedef struct b2d_stateinfo {
  *   env       oldStateInfo.rightStateInfo->leftStateInfo   E_old (newQuantaMap -> sectors of `right`)
  *   old_allowed  oldleft.nq x oldright.nq: allowed blocks of the previous wavefunction (wave-*.tmp)
  *   lrot_cols / rrot_cols  kept states per sector of the two rotation matrices (Rotation-*.tmp; 0 = sector dropped): the left one
- *                          is indexed by `oldleft` sectors, the right one by `right` sectors */
+ *                          is indexed by `oldleft` sectors, the right one by `right` sectors
+ *
+ * One-dot steps (GuessWave::onedot_transform_wavefunction, guess_wavefunction.C:832-936): the previous wavefunction is [S.d][E_old]; its
+ * columns are first expanded with the right rotation matrix, its rows rotated with the left one.
+ *   mode 1  dot on the system side (transpose_guess_wave): sys / dot / left / right as above; oldcol = oldStateInfo.rightStateInfo
+ *           (newQuantaMap -> sectors of `oldright`); oldright = right (x) dot, collected (the reference's newenvstateinfo, :853-856) with
+ *           its un-collected tables; env unused.  The right rotation matrix (sites of the right block + the dot) is indexed by `oldright`
+ *           sectors; the rotated wavefunction [S'][E'.d] is shuffled to [S'.d][E'].
+ *   mode 2  dot on the environment side: left = big.leftStateInfo (newQuantaMap -> sectors of `oldleft`), right, oldleft, oldcol
+ *           (newQuantaMap -> sectors of `right`); no shuffle.  sys, dot, oldright, env unused.
+ * old_allowed is oldleft.nq x oldcol.nq in modes 1 and 2. */
 typedef struct b2d_guess_desc {
   int32_t dq[3];
-  b2d_stateinfo sys, dot, left, right, oldleft, oldright, env;
+  int32_t mode;     /* 0 two-dot, 1 / 2 one-dot (see above) */
+  b2d_stateinfo sys, dot, left, right, oldleft, oldright, env, oldcol;
   const uint8_t* old_allowed;
   const int32_t* lrot_cols;
   const int32_t* rrot_cols;
@@ -332,9 +343,10 @@ typedef struct b2d_guess_desc {
  * planning-only context).  out[0..7] = {doubles of the previous wavefunction, of the left rotation, of the right rotation, of
  * the trial vector (flat), GEMM flops, algorithmic bytes of the shuffle, number of shuffle tasks, number of shuffle rounds}. */
 int b2d_guess_plan(b2d_ctx* ctx, const b2d_guess_desc* desc, double* out, int n);
-/* The plan's descriptors for inspection (CPU tests execute them with numpy): what = 0 stage-1 segments (GSeg, 40 bytes each),
- * 1 stage-1 groups (GGroup, 40), 2 shuffle tasks (KronTask, 80; rounds concatenated), 3 tasks per round (int32), 4 stage-3
- * segments, 5 stage-3 groups, 6 input blocks (BlockDesc, 32: previous wavefunction, left rotation, right rotation), 7 counts of
+/* The plan's descriptors for inspection (CPU tests execute them with numpy), in execution order: what = 0 / 1 segments (GSeg, 40 bytes
+ * each) / groups (GGroup, 40) of the first contraction batch, 10 / 11 of the second (one-dot only), 2 shuffle tasks (KronTask, 80; rounds
+ * concatenated; pad = 1: destination offset is into the trial vector), 3 tasks per round (int32), 4 / 5 segments / groups of the batch
+ * after the shuffle (two-dot only), 6 input blocks (BlockDesc, 32: previous wavefunction, left rotation, right rotation), 7 counts of
  * those three tables (int32 x 3) followed by {image, T1, work} sizes in doubles (int64 x 3 at byte 16), 8 trial blocks (BlockDesc).
  * Returns the number of bytes (copied when cap is large enough), or -1. */
 int64_t b2d_guess_plan_export(const b2d_ctx* ctx, int what, void* out, int64_t cap);

@@ -409,10 +409,10 @@ void wrap_diagonalH(const SpinBlock* self, DiagonalMatrix& e) {
 }
 
 // ---- GuessWave::guess_wavefunctions (vector form, solver.C:77) ----
-// SURVEY N1.  For a TRANSFORM guess of a two-dot step the reference loads the previous wavefunction and two rotation matrices from its
+// SURVEY N1.  For a TRANSFORM guess (two-dot: transform_previous_wavefunction :524-636; one-dot: onedot_transform_wavefunction :832-936) the reference loads the previous wavefunction and two rotation matrices from its
 // scratch files and runs TransformLeftBlock / onedot_shufflesysdot / TransformRightBlock on the CPU (guess_wavefunction.C:524-636).  Here
 // the same files are loaded the same way, the StateInfo tables the transform reads are handed to b2d_guess_plan, and the arithmetic runs
-// on the device.  Everything else (BASIC / TRANSPOSE guesses, one-dot steps) goes to the reference's own function.
+// on the device.  BASIC / TRANSPOSE guesses go to the reference's own function.
 void fill_stateinfo(b2d_stateinfo& o, const StateInfo& s, vector<vector<int32_t> >& keep) {
   memset(&o, 0, sizeof(o));
   auto hold = [&](const vector<int>& v) -> const int32_t* { keep.push_back(vector<int32_t>(v.begin(), v.end())); if (keep.back().empty()) keep.back().push_back(0); return keep.back().data(); };
@@ -446,8 +446,8 @@ void wrap_guess(vector<Wavefunction>& solution, DiagonalMatrix& e, const SpinBlo
 void wrap_guess(vector<Wavefunction>& solution, DiagonalMatrix& e, const SpinBlock& big, const guessWaveTypes& gw, const bool& onedot,
                 const bool& transpose_guess_wave, double additional_noise, int currentState) {
   const char* mode = getenv("B2D_DROPIN_GUESS");
-  const bool on_device = mode && string(mode) == "device" && gw == TRANSFORM && !onedot && g.ctx && big.get_leftBlock()->get_leftBlock() &&
-                         dmrginp.spinAdapted() && dmrginp.hamiltonian() != BCS;
+  const bool on_device = mode && string(mode) == "device" && gw == TRANSFORM && g.ctx && big.get_leftBlock()->get_leftBlock() &&
+                         dmrginp.spinAdapted() && dmrginp.hamiltonian() != BCS && !dmrginp.transition_diff_irrep();
   if (!on_device) { real_guess(solution, e, big, gw, onedot, transpose_guess_wave, additional_noise, currentState); return; }
   double t0 = now_s();
   const StateInfo& bs = big.get_stateInfo();
@@ -457,9 +457,25 @@ void wrap_guess(vector<Wavefunction>& solution, DiagonalMatrix& e, const SpinBlo
     StateInfo oldSI;
     Wavefunction oldWave;
     vector<Matrix> lrot, rrot;
-    oldWave.LoadWavefunctionInfo(oldSI, big.get_leftBlock()->get_leftBlock()->get_sites(), state);     // :537
-    LoadRotationMatrix(big.get_leftBlock()->get_leftBlock()->get_sites(), lrot, state);                // :538
-    LoadRotationMatrix(big.get_rightBlock()->get_sites(), rrot, state);                                // :613
+    StateInfo newenv;
+    if (!onedot || transpose_guess_wave) {
+      oldWave.LoadWavefunctionInfo(oldSI, big.get_leftBlock()->get_leftBlock()->get_sites(), state);     // :537
+      LoadRotationMatrix(big.get_leftBlock()->get_leftBlock()->get_sites(), lrot, state);                // :538
+    } else {
+      oldWave.LoadWavefunctionInfo(oldSI, big.get_leftBlock()->get_sites(), state);                      // :541
+      LoadRotationMatrix(big.get_leftBlock()->get_sites(), lrot, state);                                 // :542
+    }
+    if (onedot && transpose_guess_wave) {                                                                // :617-622
+      vector<int> rotsites = big.get_rightBlock()->get_sites();
+      rotsites.insert(rotsites.end(), big.get_leftBlock()->get_rightBlock()->get_sites().begin(), big.get_leftBlock()->get_rightBlock()->get_sites().end());
+      std::sort(rotsites.begin(), rotsites.end());
+      LoadRotationMatrix(rotsites, rrot, state);
+      // the environment side with the dot still attached: the reference's own integer bookkeeping (:853-856)
+      TensorProduct(*(bs.rightStateInfo), *(bs.leftStateInfo->rightStateInfo), newenv, NO_PARTICLE_SPIN_NUMBER_CONSTRAINT);
+      newenv.CollectQuanta();
+    } else {
+      LoadRotationMatrix(big.get_rightBlock()->get_sites(), rrot, state);                                // :613 / :625
+    }
     if (oldWave.get_deltaQuantum_size() != 1) die("guess transform: wavefunction with several target quanta: not covered");
     vector<vector<int32_t> > keep;
     keep.reserve(128);
@@ -467,13 +483,21 @@ void wrap_guess(vector<Wavefunction>& solution, DiagonalMatrix& e, const SpinBlo
     memset(&d, 0, sizeof(d));
     SpinQuantum dq = oldWave.get_deltaQuantum(0);
     d.dq[0] = dq.get_n(); d.dq[1] = dq.get_s().getirrep(); d.dq[2] = dq.get_symm().getirrep();
-    fill_stateinfo(d.sys, *bs.leftStateInfo->leftStateInfo, keep);
-    fill_stateinfo(d.dot, *bs.leftStateInfo->rightStateInfo, keep);
+    d.mode = !onedot ? 0 : (transpose_guess_wave ? 1 : 2);
     fill_stateinfo(d.left, *bs.leftStateInfo, keep);
     fill_stateinfo(d.right, *bs.rightStateInfo, keep);
     fill_stateinfo(d.oldleft, *oldSI.leftStateInfo, keep);
-    fill_stateinfo(d.oldright, *oldSI.rightStateInfo, keep);
-    fill_stateinfo(d.env, *oldSI.rightStateInfo->leftStateInfo, keep);
+    if (d.mode != 2) {
+      fill_stateinfo(d.sys, *bs.leftStateInfo->leftStateInfo, keep);
+      fill_stateinfo(d.dot, *bs.leftStateInfo->rightStateInfo, keep);
+    }
+    if (d.mode == 0) {
+      fill_stateinfo(d.oldright, *oldSI.rightStateInfo, keep);
+      fill_stateinfo(d.env, *oldSI.rightStateInfo->leftStateInfo, keep);
+    } else {
+      fill_stateinfo(d.oldcol, *oldSI.rightStateInfo, keep);
+      if (d.mode == 1) fill_stateinfo(d.oldright, newenv, keep);
+    }
     vector<uint8_t> allowed; vector<double> old, lr, rr;
     for (int a = 0; a < oldWave.nrows(); ++a) for (int b = 0; b < oldWave.ncols(); ++b) {
       allowed.push_back(oldWave.allowed(a, b) ? 1 : 0);
@@ -482,7 +506,8 @@ void wrap_guess(vector<Wavefunction>& solution, DiagonalMatrix& e, const SpinBlo
     vector<int32_t> lcols, rcols;
     for (size_t q = 0; q < lrot.size(); ++q) { lcols.push_back(lrot[q].Ncols()); if (lrot[q].Ncols()) lr.insert(lr.end(), lrot[q].Store(), lrot[q].Store() + lrot[q].Storage()); }
     for (size_t q = 0; q < rrot.size(); ++q) { rcols.push_back(rrot[q].Ncols()); if (rrot[q].Ncols()) rr.insert(rr.end(), rrot[q].Store(), rrot[q].Store() + rrot[q].Storage()); }
-    if ((int)lcols.size() != d.oldleft.nq || (int)rcols.size() != d.right.nq) die("guess transform: rotation matrices do not match the StateInfo of their blocks");
+    if ((int)lcols.size() != d.oldleft.nq || (int)rcols.size() != (d.mode == 1 ? d.oldright.nq : d.right.nq))
+      die("guess transform: rotation matrices do not match the StateInfo of their blocks");
     d.old_allowed = allowed.data(); d.lrot_cols = lcols.data(); d.rrot_cols = rcols.data();
     double info[8];
     ck(b2d_guess_plan(g.ctx, &d, info, 8), "b2d_guess_plan");

@@ -74,6 +74,7 @@ def execute_plan(gt, old, lrot, rrot):
     dst = np.zeros(Wp)
     bases = {BASE_WORK: work, BASE_DST: dst, BASE_AUX: image}
     run_groups(gt.export(0).view(GSEG), gt.export(1).view(GGROUP), bases)
+    run_groups(gt.export(10).view(GSEG), gt.export(11).view(GGROUP), bases)      # second batch (one-dot): reads what the first wrote
     tasks, per_round = gt.export(2).view(KRON), gt.export(3).view("<i4")
     assert per_round.sum() == len(tasks) == gt.shuffle_tasks and len(per_round) == gt.shuffle_rounds
     first = 0
@@ -82,14 +83,15 @@ def execute_plan(gt, old, lrot, rrot):
         for t in tasks[first:first + int(n)]:
             assert t["b"] == 0 and t["b_rows"] == 1 and t["b_cols"] == 1 and t["a_t"] == 0
             assert int(t["a"]) + (int(t["a_rows"]) - 1) * int(t["lda"]) + int(t["a_cols"]) <= t1_size      # reads stage-1 output only
-            assert int(t["dst"]) >= t1_size
+            target = dst if t["pad"] else work          # pad = 1: the shuffle writes the trial vector (one-dot, dot on the system side)
+            assert t["pad"] or int(t["dst"]) >= t1_size
             key = (int(t["dst"]), int(t["row0"]))
             assert key not in written, "two tasks of one round write the same destination rows"
             written.add(key)
             for i in range(int(t["a_rows"])):
                 s0 = int(t["a"]) + i * int(t["lda"])
                 d0 = int(t["dst"]) + (int(t["row0"]) + i) * int(t["ldd"]) + int(t["col0"])
-                work[d0:d0 + int(t["a_cols"])] += float(t["coef"]) * work[s0:s0 + int(t["a_cols"])]
+                target[d0:d0 + int(t["a_cols"])] += float(t["coef"]) * work[s0:s0 + int(t["a_cols"])]
         first += int(n)
     run_groups(gt.export(4).view(GSEG), gt.export(5).view(GGROUP), bases)
     flat = np.zeros(gt.trial_size)
@@ -146,3 +148,36 @@ def test_synthetic_case_plans_and_executes(M):
         assert gt.flops > 0 and gt.shuffle_tasks > 0
     finally:
         gt.close()
+
+
+ONEDOT = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "guess1dot_*.npz")))
+
+
+def make_onedot(rec, root, device):
+    """One-dot record -> b2d_guess_desc: mode 1 (dot on the system side; "oldright" is the reference's newenvstateinfo) or mode 2."""
+    p = "gw%d." % root
+    transpose = int(rec["gw.nroots"][1]) != 0
+    names = {"left": "left", "right": "right", "oldleft": "oldleft", "oldcol": "oldcol"}
+    if transpose:
+        names.update({"sys": "sys", "dot": "dot", "oldright": "newenv"})
+    tabs = {k: {key[len(p + v + "."):]: rec[key] for key in rec if key.startswith(p + v + ".")} for k, v in names.items()}
+    return hotpath.GuessTransform(rec[p + "dq"][:3], tabs, rec[p + "old.allowed"], rec[p + "lrot.shape"][:, 1], rec[p + "rrot.shape"][:, 1],
+                                  device=device, mode=1 if transpose else 2)
+
+
+@pytest.mark.parametrize("path", ONEDOT, ids=[os.path.basename(f)[:-4] for f in ONEDOT])
+def test_planned_onedot_transform_reproduces_the_reference_trial_vector(path):
+    """One-dot branch (GuessWave::onedot_transform_wavefunction, guess_wavefunction.C:832-936), both dot positions."""
+    rec = dict(np.load(path))
+    for root in range(int(rec["gw.nroots"][0])):
+        p = "gw%d." % root
+        gt = make_onedot(rec, root, device=-1)
+        try:
+            assert gt.trial_size == rec[p + "trial"].size
+            got = execute_plan(gt, rec[p + "old.data"], rec[p + "lrot.data"], rec[p + "rrot.data"])
+            ref = rec[p + "trial"]
+            err = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+            assert err < 1e-13, (path, root, err)
+            assert (gt.shuffle_tasks > 0) == (int(rec["gw.nroots"][1]) != 0)       # the rotate-only mode has no shuffle
+        finally:
+            gt.close()

@@ -12,7 +12,7 @@ import pytest
 
 from block_b200 import hotpath
 from oracle import guess_oracle as G
-from test_guess_planner_cpu import make
+from test_guess_planner_cpu import make, make_onedot
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FIXTURES = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "guess_*.npz")))
@@ -111,3 +111,25 @@ def test_device_transform_on_synthetic_sectors_matches_the_plan_executed_with_nu
         print("synthetic M = %d: W = %d, %d shuffle tasks, relative difference %.1e" % (M, got.size, gt.shuffle_tasks, err))
     finally:
         gt.close()
+
+
+ONEDOT = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "guess1dot_*.npz")))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", ONEDOT, ids=[os.path.basename(f)[:-4] for f in ONEDOT])
+def test_device_onedot_transform_matches_reference(path):
+    """One-dot branch on the device (b2d_guess_desc modes 1 and 2) against the real reference's trial vectors and the pinned oracle."""
+    rec = dict(np.load(path))
+    for root in range(int(rec["gw.nroots"][0])):
+        p = "gw%d." % root
+        gt = make_onedot(rec, root, device=0)
+        try:
+            got = gt.transform(rec[p + "old.data"], rec[p + "lrot.data"], rec[p + "rrot.data"])
+            ref = rec[p + "trial"]
+            err = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+            assert err < 1e-12, (path, root, err)
+            orc = G.transform_previous_wavefunction_onedot(rec, root)
+            assert np.linalg.norm(got - orc) / np.linalg.norm(orc) < 1e-12
+        finally:
+            gt.close()

@@ -2336,8 +2336,8 @@ int b2d_guess_transform(b2d_ctx* ctx, const double* old_wave, const double* left
     std::vector<KronTask> tasks;
     for (const auto& r : P.rounds)
       for (KronTask t : r) {
-        t.a = (int64_t)(intptr_t)((double*)ctx->work.p + t.a);
-        t.dst = (int64_t)(intptr_t)((t.pad ? dst : (double*)ctx->work.p) + t.dst);   // pad = 1: the shuffle writes the trial vector
+        t.a = (int64_t)(intptr_t)(((t.pad & 2) ? (double*)ctx->guess_image.p : (double*)ctx->work.p) + t.a);   // bit 1: the source is the input image
+        t.dst = (int64_t)(intptr_t)(((t.pad & 1) ? dst : (double*)ctx->work.p) + t.dst);                      // bit 0: the task writes the trial vector
         t.pad = 0;
         tasks.push_back(t);
       }

@@ -37,7 +37,7 @@ struct GuessPlan {
   //   mode 2: a = columns (T0),     b = rows (trial),   c = -        (no shuffle)
   GemmBatch gemm_a, gemm_b, gemm_c;
   std::vector<std::vector<KronTask>> rounds;           // a / dst hold OFFSETS (doubles) until execution: a into WORK, dst into WORK or - pad = 1 -
-                                                       // into the trial vector; tasks of one round never overlap (a destination's j-th
+                                                       // into the trial vector, pad bit 1: a is an offset into the image; tasks of one round never overlap (a destination's j-th
                                                        // source goes to round j)
   int64_t t1_size = 0, t2_off = 0, work_size = 0;      // WORK: [0, t1_size) what the shuffle reads (and T0 before it), [t2_off, work_size) T2
   Side left, right;                                    // sector tables of the big block's children (trial layout)
@@ -50,11 +50,57 @@ inline void guess_check(bool ok, const char* what) {
   if (!ok) throw std::runtime_error(std::string("b2d_guess_plan: ") + what);
 }
 
+// mode 3: GuessWave::transpose_previous_wavefunction (guess_wavefunction.C:55-84), two-dot to two-dot, first block iteration of a sweep:
+//   trial(i, j) = getCommuteParity(q_oldcol[i], q_oldleft[j], dq) . old(j, i)^T      - one scatter task per block, no contraction
+inline GuessPlan plan_guess_transpose(const b2d_guess_desc& d, AngMom& am) {
+  GuessPlan P;
+  P.mode = 3;
+  std::memcpy(P.dq, d.dq, sizeof(P.dq));
+  const b2d_stateinfo &left = d.left, &right = d.right, &oldleft = d.oldleft, &oldcol = d.oldcol;
+  guess_check(left.nq > 0 && right.nq > 0 && oldleft.nq == right.nq && oldcol.nq == left.nq && d.old_allowed,
+              "transpose: the previous wavefunction must live on (right sectors) x (left sectors)");
+  for (int i = 0; i < left.nq; ++i) guess_check(left.dims[i] == oldcol.dims[i], "transpose: column sectors of the previous wavefunction are not the new left sectors");
+  for (int j = 0; j < right.nq; ++j) guess_check(right.dims[j] == oldleft.dims[j], "transpose: row sectors of the previous wavefunction are not the new right sectors");
+  std::vector<int64_t> old_off((size_t)oldleft.nq * oldcol.nq, -1);
+  int64_t dev = 0, ref = 0;
+  for (int a = 0; a < oldleft.nq; ++a)
+    for (int b = 0; b < oldcol.nq; ++b)
+      if (d.old_allowed[(size_t)a * oldcol.nq + b]) {
+        BlockDesc bd; bd.ref_off = ref; bd.dev_off = dev; bd.rows = oldleft.dims[a]; bd.cols = oldcol.dims[b]; bd.ld = pad_ld(bd.cols); bd.pad = 0;
+        old_off[(size_t)a * oldcol.nq + b] = dev;
+        ref += (int64_t)bd.rows * bd.cols; dev += align_up((int64_t)bd.rows * bd.ld, BLK_ALIGN);
+        P.in_old.push_back(bd);
+      }
+  P.old_size = ref;
+  P.image_size = dev;
+  P.left.nq = left.nq; P.left.q.assign(left.q, left.q + 3 * left.nq); P.left.dims.assign(left.dims, left.dims + left.nq);
+  P.right.nq = right.nq; P.right.q.assign(right.q, right.q + 3 * right.nq); P.right.dims.assign(right.dims, right.dims + right.nq);
+  P.trial.build(P.left, P.right, d.dq);
+  P.rounds.resize(1);
+  for (int p = 0; p < P.trial.nblocks(); ++p) {
+    const int i = P.trial.bl[p], j = P.trial.br[p];
+    const int64_t src = old_off[(size_t)j * oldcol.nq + i];
+    guess_check(src >= 0, "transpose: a block of the trial vector has no counterpart in the previous wavefunction");   // the reference asserts it (:72)
+    KronTask t; std::memset(&t, 0, sizeof(t));
+    t.a = src; t.b = 0; t.dst = P.trial.dev_off[p];
+    t.coef = am.commute_parity(&oldcol.q[3 * i], &oldleft.q[3 * j], d.dq);
+    t.a_rows = left.dims[i]; t.a_cols = right.dims[j]; t.lda = pad_ld(oldcol.dims[i]); t.a_t = 1;     // stored a_cols x a_rows
+    t.b_rows = 1; t.b_cols = 1; t.ldb = 1; t.b_t = 0;
+    t.row0 = 0; t.col0 = 0; t.ldd = P.trial.ld[p];
+    t.pad = 3;                                                                                          // source: the image, destination: the trial vector
+    P.rounds[0].push_back(t);
+    P.shuffle_bytes += 8ll * 3 * t.a_rows * t.a_cols;
+  }
+  P.valid = true;
+  return P;
+}
+
 inline GuessPlan plan_guess_transform(const b2d_guess_desc& d, AngMom& am, int forced_class) {
   GuessPlan P;
   P.mode = d.mode;
   std::memcpy(P.dq, d.dq, sizeof(P.dq));
-  guess_check(d.mode >= 0 && d.mode <= 2, "mode must be 0 (two-dot), 1 (one-dot, dot moved to the system) or 2 (one-dot, rotation only)");
+  guess_check(d.mode >= 0 && d.mode <= 3, "mode must be 0 (two-dot), 1 (one-dot, dot moved to the system), 2 (one-dot, rotation only) or 3 (transpose)");
+  if (d.mode == 3) return plan_guess_transpose(d, am);
   const bool shuffle = d.mode != 2, onedot = d.mode != 0;
   const b2d_stateinfo &sys = d.sys, &dot = d.dot, &left = d.left, &right = d.right, &oldleft = d.oldleft, &oldright = d.oldright, &oldcol = d.oldcol;
   const b2d_stateinfo& env = d.mode == 0 ? d.env : d.right;      // the environment sectors the shuffle keeps as columns

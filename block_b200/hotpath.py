@@ -519,7 +519,8 @@ class GuessTransform:
     "unc.rmap", "old_to_new", "old_to_new_begin"."""
 
     NAMES = ("sys", "dot", "left", "right", "oldleft", "oldright", "env")
-    NAMES_BY_MODE = {0: NAMES, 1: ("sys", "dot", "left", "right", "oldleft", "oldright", "oldcol"), 2: ("left", "right", "oldleft", "oldcol")}
+    NAMES_BY_MODE = {0: NAMES, 1: ("sys", "dot", "left", "right", "oldleft", "oldright", "oldcol"), 2: ("left", "right", "oldleft", "oldcol"),
+                     3: ("left", "right", "oldleft", "oldcol")}
 
     def __init__(self, dq, tables, old_allowed, lrot_cols, rrot_cols, device=0, ctx=None, mode=0):
         """mode 0: two-dot step; 1: one-dot, dot on the system side ("oldright" = the reference's newenvstateinfo); 2: one-dot, dot on
@@ -565,8 +566,8 @@ class GuessTransform:
         for name in self.NAMES_BY_MODE[int(mode)]:
             setattr(d, name, si(tables[name]))
         d.old_allowed = _p(arr(old_allowed, np.uint8).reshape(-1), _lib.c_u8p)
-        d.lrot_cols = _p(arr(lrot_cols), _lib.c_i32p)
-        d.rrot_cols = _p(arr(rrot_cols), _lib.c_i32p)
+        d.lrot_cols = _p(arr(lrot_cols), _lib.c_i32p) if lrot_cols is not None else None
+        d.rrot_cols = _p(arr(rrot_cols), _lib.c_i32p) if rrot_cols is not None else None
         self._desc = d
         out = np.zeros(8)
         self._ck(self.lib.b2d_guess_plan(self._ctx, C.byref(d), _p(out, _lib.c_f64p), 8))
@@ -586,9 +587,9 @@ class GuessTransform:
         self.lib.b2d_guess_plan_export(self._ctx, int(what), buf.ctypes.data_as(C.c_void_p), int(n))
         return buf[:n]
 
-    def transform(self, old_wave, left_rot, right_rot, dst_slot=-1, download=True):
+    def transform(self, old_wave, left_rot=None, right_rot=None, dst_slot=-1, download=True):
         """The trial vector, flat in FlattenInto order (and / or left in wavefunction slot `dst_slot` of a planned context)."""
-        ow, lr, rr = (np.ascontiguousarray(x, dtype=np.float64) for x in (old_wave, left_rot, right_rot))
+        ow, lr, rr = (np.ascontiguousarray(x if x is not None else np.zeros(0), dtype=np.float64) for x in (old_wave, left_rot, right_rot))
         assert ow.size == self.old_size and lr.size == self.lrot_size and rr.size == self.rrot_size
         out = np.zeros(max(self.trial_size, 1)) if download else None
         self._ck(self.lib.b2d_guess_transform(self._ctx, _p(ow, _lib.c_f64p), _p(lr, _lib.c_f64p), _p(rr, _lib.c_f64p), int(dst_slot),

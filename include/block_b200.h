@@ -329,10 +329,13 @@ typedef struct b2d_stateinfo {
  *           sectors; the rotated wavefunction [S'][E'.d] is shuffled to [S'.d][E'].
  *   mode 2  dot on the environment side: left = big.leftStateInfo (newQuantaMap -> sectors of `oldleft`), right, oldleft, oldcol
  *           (newQuantaMap -> sectors of `right`); no shuffle.  sys, dot, oldright, env unused.
- * old_allowed is oldleft.nq x oldcol.nq in modes 1 and 2. */
+ *   mode 3  TRANSPOSE guess of the first block iteration of a sweep (GuessWave::transpose_previous_wavefunction, :55-84, two-dot to
+ *           two-dot): left, right, oldleft (= the sectors of `right`), oldcol (= the sectors of `left`); trial(i, j) = parity . old(j, i)^T;
+ *           no rotation matrices (pass lrot_cols / rrot_cols = NULL).
+ * old_allowed is oldleft.nq x oldcol.nq in modes 1, 2 and 3. */
 typedef struct b2d_guess_desc {
   int32_t dq[3];
-  int32_t mode;     /* 0 two-dot, 1 / 2 one-dot (see above) */
+  int32_t mode;     /* 0 two-dot, 1 / 2 one-dot, 3 transpose (see above) */
   b2d_stateinfo sys, dot, left, right, oldleft, oldright, env, oldcol;
   const uint8_t* old_allowed;
   const int32_t* lrot_cols;
@@ -345,7 +348,7 @@ typedef struct b2d_guess_desc {
 int b2d_guess_plan(b2d_ctx* ctx, const b2d_guess_desc* desc, double* out, int n);
 /* The plan's descriptors for inspection (CPU tests execute them with numpy), in execution order: what = 0 / 1 segments (GSeg, 40 bytes
  * each) / groups (GGroup, 40) of the first contraction batch, 10 / 11 of the second (one-dot only), 2 shuffle tasks (KronTask, 80; rounds
- * concatenated; pad = 1: destination offset is into the trial vector), 3 tasks per round (int32), 4 / 5 segments / groups of the batch
+ * concatenated; pad bit 0: the destination offset is into the trial vector, bit 1: the source offset is into the input image), 3 tasks per round (int32), 4 / 5 segments / groups of the batch
  * after the shuffle (two-dot only), 6 input blocks (BlockDesc, 32: previous wavefunction, left rotation, right rotation), 7 counts of
  * those three tables (int32 x 3) followed by {image, T1, work} sizes in doubles (int64 x 3 at byte 16), 8 trial blocks (BlockDesc).
  * Returns the number of bytes (copied when cap is large enough), or -1. */

@@ -202,3 +202,20 @@ def transform_previous_wavefunction_onedot(rec, root):
     t1 = onedot_rotate(old, oldleft, oldcol, sys, newenv["dims"], lrot, rrot)          # [S'][E'.dot]
     t2 = shuffle_sysdot(t1, sys, dot, right, newenv, left, dq)                          # -> [S'.dot][E']
     return flatten(t2, len(left["dims"]), len(right["dims"]), dq, left["q"], right["q"], left["dims"], right["dims"])
+
+
+# ---- first block iteration of a sweep: GuessWave::transpose_previous_wavefunction (guess_wavefunction.C:55-84), two-dot ------------
+def transpose_previous_wavefunction(rec, root):
+    """trial(i, j) = getCommuteParity(q_right_old[i], q_left_old[j], dq) . old(j, i)^T: the previous wavefunction seen from the other end
+    of the chain (a transposition, not a Hermitian conjugate, with the fermionic / recoupling sign of swapping the two blocks)."""
+    p = "gw%d." % root
+    dq = rec[p + "dq"][:3]
+    left, right, oldleft, oldcol = (stateinfo(rec, p + n + ".") for n in ("left", "right", "oldleft", "oldcol"))
+    old = unpack_blocks(rec[p + "old.allowed"], rec[p + "old.data"], oldleft["dims"], oldcol["dims"])
+    out = {}
+    for i in range(len(left["dims"])):
+        for j in range(len(right["dims"])):
+            if allow(dq, left["q"][i], right["q"][j]):
+                assert (j, i) in old
+                out[(i, j)] = commute_parity(oldcol["q"][i], oldleft["q"][j], dq) * old[(j, i)].T
+    return flatten(out, len(left["dims"]), len(right["dims"]), dq, left["q"], right["q"], left["dims"], right["dims"])

@@ -447,6 +447,38 @@ void wrap_guess(vector<Wavefunction>& solution, DiagonalMatrix& e, const SpinBlo
     }
     return;
   }
+  if (getenv("ORACLE_DUMP_GUESS") && gw == TRANSPOSE && !onedot && want_dump(g_call)) {
+    // first block iteration of a sweep: GuessWave::transpose_previous_wavefunction (guess_wavefunction.C:55-84), two-dot to two-dot
+    const int nroots = (int)solution.size();
+    const StateInfo& bs = big.get_stateInfo();
+    std::ostringstream fp; fp << getenv("ORACLE_DUMP_DIR") << "/guessT_" << g_call << ".bin";
+    Dumper d; bool opened = false;
+    for (int i = 0; i < nroots; ++i) {
+      const int state = (dmrginp.setStateSpecific() || dmrginp.calc_type() == COMPRESS || dmrginp.calc_type() == MPS_NEVPT) ? currentState : i;
+      StateInfo oldSI; Wavefunction oldWave;
+      oldWave.LoadWavefunctionInfo(oldSI, big.get_rightBlock()->get_sites(), state);
+      if (oldWave.get_onedot()) { oldSI.Free(); return; }     // one-dot -> two-dot switch: not dumped
+      if (!opened) { d.open(fp.str(), false); opened = true; d.ints("meta", vector<int>{g_call, big.get_leftBlock()->get_sites()[0] == 0, 0, 3}); d.ints("gw.nroots", vector<int>{nroots, 3}); }
+      std::ostringstream pp; pp << "gw" << i << ".";
+      const string p = pp.str();
+      SpinQuantum dq = oldWave.get_deltaQuantum(0);
+      d.ints(p + "dq", vector<int>{dq.get_n(), dq.get_s().getirrep(), dq.get_symm().getirrep(), (int)oldWave.get_deltaQuantum_size()});
+      dump_si_tables(d, p + "left.", *bs.leftStateInfo);
+      dump_si_tables(d, p + "right.", *bs.rightStateInfo);
+      dump_si_tables(d, p + "oldleft.", *oldSI.leftStateInfo);
+      dump_si_tables(d, p + "oldcol.", *oldSI.rightStateInfo);
+      vector<int> allowed; vector<double> data;
+      for (int a = 0; a < oldWave.nrows(); ++a) for (int b = 0; b < oldWave.ncols(); ++b) {
+        allowed.push_back(oldWave.allowed(a, b) ? 1 : 0);
+        if (oldWave.allowed(a, b)) { const Matrix& m = oldWave.operator_element(a, b); data.insert(data.end(), m.Store(), m.Store() + m.Storage()); }
+      }
+      d.ints(p + "old.allowed", allowed, {(uint64_t)oldWave.nrows(), (uint64_t)oldWave.ncols()});
+      d.dbls(p + "old.data", data);
+      vector<double> flat; flatten(solution[i], flat); d.dbls(p + "trial", flat);
+      oldSI.Free();
+    }
+    return;
+  }
   if (!g_dump_this || !getenv("ORACLE_DUMP_GUESS") || gw != TRANSFORM || onedot) return;
   Dumper d; d.open(g_path, true);
   const int nroots = (int)solution.size();

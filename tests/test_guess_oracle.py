@@ -67,3 +67,14 @@ def test_onedot_fixtures_cover_both_dot_positions():
         with np.load(f) as z:
             flags.add(int(z["gw.nroots"][1]))
     assert flags == {0, 1}
+
+
+TRANSPOSE = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "guessT_*.npz")))
+
+
+@pytest.mark.parametrize("path", TRANSPOSE, ids=[os.path.basename(f)[:-4] for f in TRANSPOSE])
+def test_transpose_guess_matches_reference(path):
+    """GuessWave::transpose_previous_wavefunction (guess_wavefunction.C:55-84): bit-exact."""
+    rec = dict(np.load(path))
+    for root in range(int(rec["gw.nroots"][0])):
+        assert np.array_equal(G.transpose_previous_wavefunction(rec, root), rec["gw%d.trial" % root])

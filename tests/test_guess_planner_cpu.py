@@ -81,17 +81,21 @@ def execute_plan(gt, old, lrot, rrot):
     for n in per_round:
         written = set()
         for t in tasks[first:first + int(n)]:
-            assert t["b"] == 0 and t["b_rows"] == 1 and t["b_cols"] == 1 and t["a_t"] == 0
-            assert int(t["a"]) + (int(t["a_rows"]) - 1) * int(t["lda"]) + int(t["a_cols"]) <= t1_size      # reads stage-1 output only
-            target = dst if t["pad"] else work          # pad = 1: the shuffle writes the trial vector (one-dot, dot on the system side)
-            assert t["pad"] or int(t["dst"]) >= t1_size
+            assert t["b"] == 0 and t["b_rows"] == 1 and t["b_cols"] == 1
+            target = dst if int(t["pad"]) & 1 else work      # pad bit 0: the task writes the trial vector
+            source = image if int(t["pad"]) & 2 else work    # pad bit 1: the task reads the input image (transpose guess)
+            if not int(t["pad"]) & 2:
+                assert t["a_t"] == 0 and int(t["a"]) + (int(t["a_rows"]) - 1) * int(t["lda"]) + int(t["a_cols"]) <= t1_size   # reads stage-1 output only
+            assert int(t["pad"]) & 1 or int(t["dst"]) >= t1_size
             key = (int(t["dst"]), int(t["row0"]))
             assert key not in written, "two tasks of one round write the same destination rows"
             written.add(key)
-            for i in range(int(t["a_rows"])):
-                s0 = int(t["a"]) + i * int(t["lda"])
+            rows, cols, lda = int(t["a_rows"]), int(t["a_cols"]), int(t["lda"])
+            a0 = int(t["a"])
+            blk = source[a0:a0 + cols * lda].reshape(cols, lda)[:, :rows].T if t["a_t"] else np.stack([source[a0 + i * lda:a0 + i * lda + cols] for i in range(rows)])
+            for i in range(rows):
                 d0 = int(t["dst"]) + (int(t["row0"]) + i) * int(t["ldd"]) + int(t["col0"])
-                target[d0:d0 + int(t["a_cols"])] += float(t["coef"]) * work[s0:s0 + int(t["a_cols"])]
+                target[d0:d0 + cols] += float(t["coef"]) * blk[i]
         first += int(n)
     run_groups(gt.export(4).view(GSEG), gt.export(5).view(GGROUP), bases)
     flat = np.zeros(gt.trial_size)
@@ -179,5 +183,31 @@ def test_planned_onedot_transform_reproduces_the_reference_trial_vector(path):
             err = np.linalg.norm(got - ref) / np.linalg.norm(ref)
             assert err < 1e-13, (path, root, err)
             assert (gt.shuffle_tasks > 0) == (int(rec["gw.nroots"][1]) != 0)       # the rotate-only mode has no shuffle
+        finally:
+            gt.close()
+
+
+TRANSPOSE = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "guessT_*.npz")))
+
+
+def make_transpose(rec, root, device):
+    p = "gw%d." % root
+    tabs = {k: {key[len(p + k + "."):]: rec[key] for key in rec if key.startswith(p + k + ".")} for k in ("left", "right", "oldleft", "oldcol")}
+    return hotpath.GuessTransform(rec[p + "dq"][:3], tabs, rec[p + "old.allowed"], None, None, device=device, mode=3)
+
+
+@pytest.mark.parametrize("path", TRANSPOSE, ids=[os.path.basename(f)[:-4] for f in TRANSPOSE])
+def test_planned_transpose_guess_reproduces_the_reference_trial_vector(path):
+    """First block iteration of a sweep (GuessWave::transpose_previous_wavefunction, guess_wavefunction.C:55-84): a signed
+    transposition, bit-exact."""
+    rec = dict(np.load(path))
+    assert TRANSPOSE
+    for root in range(int(rec["gw.nroots"][0])):
+        p = "gw%d." % root
+        gt = make_transpose(rec, root, device=-1)
+        try:
+            got = execute_plan(gt, rec[p + "old.data"], np.zeros(0), np.zeros(0))
+            assert np.array_equal(got, rec[p + "trial"])
+            assert gt.flops == 0 and gt.shuffle_rounds == 1
         finally:
             gt.close()

@@ -12,7 +12,7 @@ import pytest
 
 from block_b200 import hotpath
 from oracle import guess_oracle as G
-from test_guess_planner_cpu import make, make_onedot
+from test_guess_planner_cpu import make, make_onedot, make_transpose
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 FIXTURES = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "guess_*.npz")))
@@ -131,5 +131,22 @@ def test_device_onedot_transform_matches_reference(path):
             assert err < 1e-12, (path, root, err)
             orc = G.transform_previous_wavefunction_onedot(rec, root)
             assert np.linalg.norm(got - orc) / np.linalg.norm(orc) < 1e-12
+        finally:
+            gt.close()
+
+
+TRANSPOSE = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "guessT_*.npz")))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", TRANSPOSE, ids=[os.path.basename(f)[:-4] for f in TRANSPOSE])
+def test_device_transpose_guess_is_bit_exact(path):
+    """b2d_guess_desc mode 3 (first block iteration of a sweep): a signed transposition on the device, bit-exact against the reference."""
+    rec = dict(np.load(path))
+    for root in range(int(rec["gw.nroots"][0])):
+        gt = make_transpose(rec, root, device=0)
+        try:
+            got = gt.transform(rec["gw%d.old.data" % root])
+            assert np.array_equal(got, rec["gw%d.trial" % root])
         finally:
             gt.close()

@@ -555,12 +555,14 @@ void wrap_guess(vector<Wavefunction>& solution, DiagonalMatrix& e, const SpinBlo
     ck(b2d_guess_transform(g.ctx, old.data(), lr.data(), rr.data(), -1, flat.data()), "b2d_guess_transform");
     collect(solution[i], flat);
     oldSI.Free();
-    if (env_on("B2D_DROPIN_CHECK")) {
-      vector<Wavefunction> ref(1);
-      real_guess(ref, e, big, gw, onedot, transpose_guess_wave, additional_noise, state);
-      vector<double> rf; flatten(ref[0], rf);
+  }
+  if (env_on("B2D_DROPIN_CHECK")) {   // the reference's own transform of every root (its loop maps root i to state i itself)
+    vector<Wavefunction> ref(solution.size());
+    real_guess(ref, e, big, gw, onedot, transpose_guess_wave, additional_noise, currentState);
+    for (size_t i = 0; i < solution.size(); ++i) {
+      vector<double> rf, gf; flatten(ref[i], rf); flatten(solution[i], gf);
       double worst = 0, scale = 0;
-      for (size_t k = 0; k < rf.size(); ++k) { worst = std::max(worst, fabs(rf[k] - flat[k])); scale = std::max(scale, fabs(rf[k])); }
+      for (size_t k = 0; k < rf.size() && k < gf.size(); ++k) { worst = std::max(worst, fabs(rf[k] - gf[k])); scale = std::max(scale, fabs(rf[k])); }
       fprintf(stderr, "B2D_CHECK call=%d guess_transform root=%d max_abs_diff=%.3e (max |psi| %.3e)\n", g.call, (int)i, worst, scale);
     }
   }

@@ -95,12 +95,103 @@ inline GuessPlan plan_guess_transpose(const b2d_guess_desc& d, AngMom& am) {
   return P;
 }
 
+// mode 4: first block iteration of a ONE-DOT sweep, GuessWave::onedot_transpose_wavefunction (guess_wavefunction.C:140-198 with :402-432 and
+// :200-256): [S.d][E] -> [E.d][S].  Every un-collected row piece u = (S sector a, dot sector b, quantum AB) of a block of the previous
+// wavefunction is transposed with the sign getCommuteParity(S, d, AB) . getCommuteParity(AB, E, dq) and re-coupled into the row pieces
+// v = (E sector c, dot sector b, quantum EB) of the new left block with sixj(E, d, EB, S, J, AB) sqrt((EB+1)(AB+1)) (-1)^((E+d+J+S)/2):
+// scatter tasks only (source: the input image, stored transposed; destination: the trial vector).
+inline GuessPlan plan_guess_onedot_transpose(const b2d_guess_desc& d, AngMom& am) {
+  GuessPlan P;
+  P.mode = 4;
+  std::memcpy(P.dq, d.dq, sizeof(P.dq));
+  const b2d_stateinfo &left = d.left, &sys = d.sys, &dot = d.dot, &right = d.right, &oldleft = d.oldleft, &oldcol = d.oldcol;
+  guess_check(left.nq > 0 && right.nq > 0 && sys.nq > 0 && dot.nq > 0 && oldleft.nq > 0 && oldcol.nq == sys.nq && d.old_allowed, "one-dot transpose: bad StateInfos");
+  guess_check(left.nunc > 0 && left.unc_q && left.unc_dims && left.unc_left && left.unc_right && left.old_to_new_begin && left.old_to_new, "left needs its un-collected tables");
+  guess_check(oldleft.nunc > 0 && oldleft.unc_q && oldleft.unc_dims && oldleft.unc_left && oldleft.unc_right && oldleft.old_to_new_begin && oldleft.old_to_new,
+              "oldleft needs its un-collected tables");
+  for (int b = 0; b < dot.nq; ++b) guess_check(dot.dims[b] == 1, "dot sectors must hold one state (spin-adapted single site)");
+  for (int c = 0; c < sys.nq; ++c) guess_check(sys.dims[c] == oldcol.dims[c], "one-dot transpose: the new system block is not the previous wavefunction's column block");
+  std::vector<int64_t> old_off((size_t)oldleft.nq * oldcol.nq, -1);
+  int64_t dev = 0, ref = 0;
+  for (int a = 0; a < oldleft.nq; ++a)
+    for (int b = 0; b < oldcol.nq; ++b)
+      if (d.old_allowed[(size_t)a * oldcol.nq + b]) {
+        BlockDesc bd; bd.ref_off = ref; bd.dev_off = dev; bd.rows = oldleft.dims[a]; bd.cols = oldcol.dims[b]; bd.ld = pad_ld(bd.cols); bd.pad = 0;
+        old_off[(size_t)a * oldcol.nq + b] = dev;
+        ref += (int64_t)bd.rows * bd.cols; dev += align_up((int64_t)bd.rows * bd.ld, BLK_ALIGN);
+        P.in_old.push_back(bd);
+      }
+  P.old_size = ref;
+  P.image_size = dev;
+  P.left.nq = left.nq; P.left.q.assign(left.q, left.q + 3 * left.nq); P.left.dims.assign(left.dims, left.dims + left.nq);
+  P.right.nq = right.nq; P.right.q.assign(right.q, right.q + 3 * right.nq); P.right.dims.assign(right.dims, right.dims + right.nq);
+  P.trial.build(P.left, P.right, d.dq);
+  std::vector<int> ou_parent(oldleft.nunc, -1), ou_first(oldleft.nunc, 0), lu_parent(left.nunc, -1), lu_first(left.nunc, 0);
+  for (int q = 0; q < oldleft.nq; ++q) {
+    int first = 0;
+    for (int k = oldleft.old_to_new_begin[q]; k < oldleft.old_to_new_begin[q + 1]; ++k) {
+      const int u = oldleft.old_to_new[k];
+      guess_check(u >= 0 && u < oldleft.nunc, "oldleft.oldToNewState out of range");
+      ou_parent[u] = q; ou_first[u] = first; first += oldleft.unc_dims[u];
+    }
+    guess_check(first == oldleft.dims[q], "oldleft: un-collected pieces do not add up to the collected sector");
+  }
+  for (int q = 0; q < left.nq; ++q) {
+    int first = 0;
+    for (int k = left.old_to_new_begin[q]; k < left.old_to_new_begin[q + 1]; ++k) {
+      const int v = left.old_to_new[k];
+      guess_check(v >= 0 && v < left.nunc, "left.oldToNewState out of range");
+      lu_parent[v] = q; lu_first[v] = first; first += left.unc_dims[v];
+    }
+    guess_check(first == left.dims[q], "left: un-collected pieces do not add up to the collected sector");
+  }
+  std::vector<int> hits((size_t)left.nunc * right.nq, 0);
+  const int J = d.dq[1];
+  for (int u = 0; u < oldleft.nunc; ++u) {
+    const int a = oldleft.unc_left[u], b = oldleft.unc_right[u], oq = ou_parent[u];
+    guess_check(a >= 0 && a < right.nq && b >= 0 && b < dot.nq, "oldleft un-collected maps out of range");
+    if (oq < 0) continue;
+    guess_check(oldleft.unc_dims[u] == right.dims[a] * dot.dims[b], "one-dot transpose: the new right block is not the previous wavefunction's system block");
+    for (int c = 0; c < oldcol.nq; ++c) {
+      const int64_t src = old_off[(size_t)oq * oldcol.nq + c];
+      if (src < 0 || !qn_allow(d.dq, &oldleft.unc_q[3 * u], &oldcol.q[3 * c])) continue;
+      const double parity = am.commute_parity(&right.q[3 * a], &dot.q[3 * b], &oldleft.unc_q[3 * u]) * am.commute_parity(&oldleft.unc_q[3 * u], &oldcol.q[3 * c], d.dq);
+      for (int v = 0; v < left.nunc; ++v) {
+        if (left.unc_left[v] != c || left.unc_right[v] != b || lu_parent[v] < 0) continue;
+        if (!qn_allow(d.dq, &left.unc_q[3 * v], &right.q[3 * a])) continue;
+        const int A = sys.q[3 * c + 1], B = dot.q[3 * b + 1], AB = left.unc_q[3 * v + 1], C = right.q[3 * a + 1], CB = oldleft.unc_q[3 * u + 1];
+        double f = parity * am.six_j(A, B, AB, C, J, CB) * std::sqrt((AB + 1.0) * (CB + 1.0)) * ((((A + B + J + C) / 2) & 1) ? -1.0 : 1.0);
+        const int Al = sys.q[3 * c + 2], Bl = dot.q[3 * b + 2], ABl = left.unc_q[3 * v + 2], Cl = right.q[3 * a + 2], CBl = oldleft.unc_q[3 * u + 2];
+        if (ABl != (Al ^ Bl) || CBl != (Bl ^ Cl) || d.dq[2] != (ABl ^ Cl)) f = 0.0;
+        if (f == 0.0) continue;
+        const int p = P.trial.blk[(size_t)lu_parent[v] * right.nq + a];
+        guess_check(p >= 0, "one-dot transpose: destination outside the target quantum number");
+        KronTask t; std::memset(&t, 0, sizeof(t));
+        t.a = src + (int64_t)ou_first[u] * pad_ld(oldcol.dims[c]); t.b = 0; t.dst = P.trial.dev_off[p]; t.coef = f;
+        t.a_rows = sys.dims[c]; t.a_cols = right.dims[a]; t.lda = pad_ld(oldcol.dims[c]); t.a_t = 1;      // stored (S piece rows) x (E columns)
+        t.b_rows = 1; t.b_cols = 1; t.ldb = 1; t.b_t = 0;
+        t.row0 = lu_first[v]; t.col0 = 0; t.ldd = P.trial.ld[p];
+        t.pad = 3;
+        guess_check(left.unc_dims[v] == sys.dims[c] * dot.dims[b], "left: un-collected sector size is not the product of its factors");
+        int& h = hits[(size_t)v * right.nq + a];
+        if ((int)P.rounds.size() <= h) P.rounds.resize(h + 1);
+        P.rounds[h].push_back(t);
+        ++h;
+        P.shuffle_bytes += 8ll * 3 * t.a_rows * t.a_cols;
+      }
+    }
+  }
+  P.valid = true;
+  return P;
+}
+
 inline GuessPlan plan_guess_transform(const b2d_guess_desc& d, AngMom& am, int forced_class) {
   GuessPlan P;
   P.mode = d.mode;
   std::memcpy(P.dq, d.dq, sizeof(P.dq));
-  guess_check(d.mode >= 0 && d.mode <= 3, "mode must be 0 (two-dot), 1 (one-dot, dot moved to the system), 2 (one-dot, rotation only) or 3 (transpose)");
+  guess_check(d.mode >= 0 && d.mode <= 4, "mode must be 0 (two-dot), 1 (one-dot, dot moved to the system), 2 (one-dot, rotation only), 3 (transpose) or 4 (one-dot transpose)");
   if (d.mode == 3) return plan_guess_transpose(d, am);
+  if (d.mode == 4) return plan_guess_onedot_transpose(d, am);
   const bool shuffle = d.mode != 2, onedot = d.mode != 0;
   const b2d_stateinfo &sys = d.sys, &dot = d.dot, &left = d.left, &right = d.right, &oldleft = d.oldleft, &oldright = d.oldright, &oldcol = d.oldcol;
   const b2d_stateinfo& env = d.mode == 0 ? d.env : d.right;      // the environment sectors the shuffle keeps as columns

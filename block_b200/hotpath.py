@@ -520,7 +520,7 @@ class GuessTransform:
 
     NAMES = ("sys", "dot", "left", "right", "oldleft", "oldright", "env")
     NAMES_BY_MODE = {0: NAMES, 1: ("sys", "dot", "left", "right", "oldleft", "oldright", "oldcol"), 2: ("left", "right", "oldleft", "oldcol"),
-                     3: ("left", "right", "oldleft", "oldcol")}
+                     3: ("left", "right", "oldleft", "oldcol"), 4: ("left", "sys", "dot", "right", "oldleft", "oldcol")}
 
     def __init__(self, dq, tables, old_allowed, lrot_cols, rrot_cols, device=0, ctx=None, mode=0):
         """mode 0: two-dot step; 1: one-dot, dot on the system side ("oldright" = the reference's newenvstateinfo); 2: one-dot, dot on

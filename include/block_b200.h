@@ -332,10 +332,13 @@ typedef struct b2d_stateinfo {
  *   mode 3  TRANSPOSE guess of the first block iteration of a sweep (GuessWave::transpose_previous_wavefunction, :55-84, two-dot to
  *           two-dot): left, right, oldleft (= the sectors of `right`), oldcol (= the sectors of `left`); trial(i, j) = parity . old(j, i)^T;
  *           no rotation matrices (pass lrot_cols / rrot_cols = NULL).
- * old_allowed is oldleft.nq x oldcol.nq in modes 1, 2 and 3. */
+ *   mode 4  TRANSPOSE guess of the first block iteration of a ONE-DOT sweep (GuessWave::onedot_transpose_wavefunction, :140-198):
+ *           [S.d][E] -> [E.d][S]; left (E (x) d, with its un-collected tables), sys (= E), dot, right (= S), oldleft (S (x) d collected, with
+ *           its un-collected tables: left -> sectors of `right`, right -> dot sectors), oldcol (= the sectors of `sys`); no rotation matrices.
+ * old_allowed is oldleft.nq x oldcol.nq in modes 1 to 4. */
 typedef struct b2d_guess_desc {
   int32_t dq[3];
-  int32_t mode;     /* 0 two-dot, 1 / 2 one-dot, 3 transpose (see above) */
+  int32_t mode;     /* 0 two-dot, 1 / 2 one-dot, 3 / 4 transpose (see above) */
   b2d_stateinfo sys, dot, left, right, oldleft, oldright, env, oldcol;
   const uint8_t* old_allowed;
   const int32_t* lrot_cols;

@@ -219,3 +219,61 @@ def transpose_previous_wavefunction(rec, root):
                 assert (j, i) in old
                 out[(i, j)] = commute_parity(oldcol["q"][i], oldleft["q"][j], dq) * old[(j, i)].T
     return flatten(out, len(left["dims"]), len(right["dims"]), dq, left["q"], right["q"], left["dims"], right["dims"])
+
+
+# ---- first block iteration of a ONE-DOT sweep: onedot_transpose_wavefunction (guess_wavefunction.C:140-198, :200-256, :402-432) -----
+def onedot_transpose_wavefunction(rec, root):
+    """[S.d][E] -> [E.d][S]: rows of the previous wavefunction un-collected into (S sector, dot sector) pieces (:402-432), every piece
+    transposed with the sign of moving |S>|d> past |E> (:163-190), then re-coupled into the rows (E, d) of the new left block with the
+    same 6j coefficient as the shuffle (:200-256)."""
+    p = "gw%d." % root
+    dq = rec[p + "dq"][:3]
+    left, sys, dot, right = (stateinfo(rec, p + n + ".") for n in ("left", "sys", "dot", "right"))
+    oldleft, oldsys, oldcol = (stateinfo(rec, p + n + ".") for n in ("oldleft", "oldsys", "oldcol"))
+    old = unpack_blocks(rec[p + "old.allowed"], rec[p + "old.data"], oldleft["dims"], oldcol["dims"])
+    J = int(dq[1])
+    # un-collect the rows of the previous wavefunction: piece u = (a: S sector, b: dot sector, quantum AB)
+    pieces = {}
+    for lq in range(len(oldleft["dims"])):
+        first = 0
+        for k in range(int(oldleft["old_to_new_begin"][lq]), int(oldleft["old_to_new_begin"][lq + 1])):
+            u = int(oldleft["old_to_new"][k])
+            size = int(oldleft["unc.dims"][u])
+            for c in range(len(oldcol["dims"])):
+                if (lq, c) in old and allow(dq, oldleft["unc.q"][u], oldcol["q"][c]):
+                    pieces[(u, c)] = old[(lq, c)][first:first + size, :]
+            first += size
+    two = {}
+    for (u, c), blk in pieces.items():
+        a, b = int(oldleft["unc.lmap"][u]), int(oldleft["unc.rmap"][u])
+        Aq, Bq, ABq, Cq = oldsys["q"][a], dot["q"][b], oldleft["unc.q"][u], oldcol["q"][c]
+        parity = commute_parity(Aq, Bq, ABq) * commute_parity(ABq, Cq, dq)
+        tr = parity * blk.T                                  # (E sector c) x (S sector a)
+        # new roles: rows (E = sys sector c, dot b), columns S = right sector a
+        for v in range(len(left["unc.dims"])):
+            if int(left["unc.lmap"][v]) != c or int(left["unc.rmap"][v]) != b:
+                continue
+            if not allow(dq, left["unc.q"][v], right["q"][a]):
+                continue
+            A, B, AB, C, CB = int(sys["q"][c][1]), int(dot["q"][b][1]), int(left["unc.q"][v][1]), int(right["q"][a][1]), int(ABq[1])
+            scale = O.six_j(A, B, AB, C, J, CB) * math.sqrt((AB + 1.0) * (CB + 1.0)) * (-1.0) ** int((A + B + J + C) / 2)
+            Al, Bl, ABl, Cl, CBl = int(sys["q"][c][2]), int(dot["q"][b][2]), int(left["unc.q"][v][2]), int(right["q"][a][2]), int(ABq[2])
+            if ABl != (Al ^ Bl) or CBl != (Bl ^ Cl) or int(dq[2]) != (ABl ^ Cl):
+                scale = 0.0
+            tgt = two.setdefault((v, a), np.zeros((int(left["unc.dims"][v]), int(right["dims"][a]))))
+            tgt += scale * tr
+    out = {}
+    for lq in range(len(left["dims"])):
+        for a in range(len(right["dims"])):
+            if not allow(dq, left["q"][lq], right["q"][a]):
+                continue
+            m = np.zeros((int(left["dims"][lq]), int(right["dims"][a])))
+            first = 0
+            for k in range(int(left["old_to_new_begin"][lq]), int(left["old_to_new_begin"][lq + 1])):
+                v = int(left["old_to_new"][k])
+                size = int(left["unc.dims"][v])
+                if (v, a) in two:
+                    m[first:first + size, :] = two[(v, a)]
+                first += size
+            out[(lq, a)] = m
+    return flatten(out, len(left["dims"]), len(right["dims"]), dq, left["q"], right["q"], left["dims"], right["dims"])

@@ -447,6 +447,45 @@ void wrap_guess(vector<Wavefunction>& solution, DiagonalMatrix& e, const SpinBlo
     }
     return;
   }
+  if (getenv("ORACLE_DUMP_GUESS") && gw == TRANSPOSE && onedot && want_dump(g_call) && big.get_leftBlock()->get_rightBlock()) {
+    // first block iteration of a one-dot sweep: transpose_previous_wavefunction (guess_wavefunction.C:100-112) -> onedot_transpose_wavefunction (:140-198)
+    const int nroots = (int)solution.size();
+    const StateInfo& bs = big.get_stateInfo();
+    std::ostringstream fp; fp << getenv("ORACLE_DUMP_DIR") << "/guessT1_" << g_call << ".bin";
+    Dumper d; d.open(fp.str(), false);
+    d.ints("meta", vector<int>{g_call, big.get_leftBlock()->get_sites()[0] == 0, 1, 4});
+    d.ints("gw.nroots", vector<int>{nroots, 4});
+    vector<int> wfsites = big.get_rightBlock()->get_sites();
+    wfsites.insert(wfsites.end(), big.get_leftBlock()->get_rightBlock()->get_sites().begin(), big.get_leftBlock()->get_rightBlock()->get_sites().end());
+    std::sort(wfsites.begin(), wfsites.end());
+    for (int i = 0; i < nroots; ++i) {
+      const int state = (dmrginp.setStateSpecific() || dmrginp.calc_type() == COMPRESS || dmrginp.calc_type() == MPS_NEVPT) ? currentState : i;
+      StateInfo oldSI; Wavefunction oldWave;
+      oldWave.LoadWavefunctionInfo(oldSI, wfsites, state);
+      std::ostringstream pp; pp << "gw" << i << ".";
+      const string p = pp.str();
+      SpinQuantum dq = oldWave.get_deltaQuantum(0);
+      d.ints(p + "dq", vector<int>{dq.get_n(), dq.get_s().getirrep(), dq.get_symm().getirrep(), (int)oldWave.get_deltaQuantum_size()});
+      dump_si_tables(d, p + "left.", *bs.leftStateInfo);
+      dump_si_tables(d, p + "sys.", *bs.leftStateInfo->leftStateInfo);
+      dump_si_tables(d, p + "dot.", *bs.leftStateInfo->rightStateInfo);
+      dump_si_tables(d, p + "right.", *bs.rightStateInfo);
+      dump_si_tables(d, p + "oldleft.", *oldSI.leftStateInfo);
+      dump_si_tables(d, p + "oldsys.", *oldSI.leftStateInfo->leftStateInfo);
+      dump_si_tables(d, p + "olddot.", *oldSI.leftStateInfo->rightStateInfo);
+      dump_si_tables(d, p + "oldcol.", *oldSI.rightStateInfo);
+      vector<int> allowed; vector<double> data;
+      for (int a = 0; a < oldWave.nrows(); ++a) for (int b = 0; b < oldWave.ncols(); ++b) {
+        allowed.push_back(oldWave.allowed(a, b) ? 1 : 0);
+        if (oldWave.allowed(a, b)) { const Matrix& m = oldWave.operator_element(a, b); data.insert(data.end(), m.Store(), m.Store() + m.Storage()); }
+      }
+      d.ints(p + "old.allowed", allowed, {(uint64_t)oldWave.nrows(), (uint64_t)oldWave.ncols()});
+      d.dbls(p + "old.data", data);
+      vector<double> flat; flatten(solution[i], flat); d.dbls(p + "trial", flat);
+      oldSI.Free();
+    }
+    return;
+  }
   if (getenv("ORACLE_DUMP_GUESS") && gw == TRANSPOSE && !onedot && want_dump(g_call)) {
     // first block iteration of a sweep: GuessWave::transpose_previous_wavefunction (guess_wavefunction.C:55-84), two-dot to two-dot
     const int nroots = (int)solution.size();

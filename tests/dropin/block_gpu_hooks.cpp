@@ -450,6 +450,49 @@ void wrap_guess(vector<Wavefunction>& solution, DiagonalMatrix& e, const SpinBlo
   const bool on_device = covered && gw == TRANSFORM && big.get_leftBlock()->get_leftBlock();
   double t0 = now_s();
   const StateInfo& bs = big.get_stateInfo();
+  if (covered && gw == TRANSPOSE && onedot && big.get_leftBlock()->get_rightBlock()) {
+    // first block iteration of a one-dot sweep: onedot_transpose_wavefunction (guess_wavefunction.C:100-112, :140-198) = mode 4
+    vector<int> wfsites = big.get_rightBlock()->get_sites();
+    wfsites.insert(wfsites.end(), big.get_leftBlock()->get_rightBlock()->get_sites().begin(), big.get_leftBlock()->get_rightBlock()->get_sites().end());
+    std::sort(wfsites.begin(), wfsites.end());
+    for (size_t i = 0; i < solution.size(); ++i) {
+      const int state = (dmrginp.setStateSpecific() || dmrginp.calc_type() == COMPRESS || dmrginp.calc_type() == MPS_NEVPT) ? currentState : (int)i;
+      StateInfo oldSI;
+      Wavefunction oldWave;
+      oldWave.LoadWavefunctionInfo(oldSI, wfsites, state);
+      if (oldWave.get_deltaQuantum_size() != 1) die("guess transpose: wavefunction with several target quanta: not covered");
+      solution[i].initialise(dmrginp.effective_molecule_quantum_vec(), &big, onedot);
+      vector<vector<int32_t> > keep;
+      keep.reserve(96);
+      b2d_guess_desc d;
+      memset(&d, 0, sizeof(d));
+      SpinQuantum dq = oldWave.get_deltaQuantum(0);
+      d.dq[0] = dq.get_n(); d.dq[1] = dq.get_s().getirrep(); d.dq[2] = dq.get_symm().getirrep();
+      d.mode = 4;
+      fill_stateinfo(d.left, *bs.leftStateInfo, keep);
+      fill_stateinfo(d.sys, *bs.leftStateInfo->leftStateInfo, keep);
+      fill_stateinfo(d.dot, *bs.leftStateInfo->rightStateInfo, keep);
+      fill_stateinfo(d.right, *bs.rightStateInfo, keep);
+      fill_stateinfo(d.oldleft, *oldSI.leftStateInfo, keep);
+      fill_stateinfo(d.oldcol, *oldSI.rightStateInfo, keep);
+      vector<uint8_t> allowed; vector<double> old;
+      for (int a = 0; a < oldWave.nrows(); ++a) for (int b = 0; b < oldWave.ncols(); ++b) {
+        allowed.push_back(oldWave.allowed(a, b) ? 1 : 0);
+        if (oldWave.allowed(a, b)) { const Matrix& m = oldWave.operator_element(a, b); old.insert(old.end(), m.Store(), m.Store() + m.Storage()); }
+      }
+      d.old_allowed = allowed.data();
+      double info[8];
+      ck(b2d_guess_plan(g.ctx, &d, info, 8), "b2d_guess_plan(one-dot transpose)");
+      vector<double> flat((size_t)info[3]);
+      if ((int64_t)flat.size() != g.W) die("guess transpose: trial vector length differs from the psi layout");
+      if (old.empty()) old.push_back(0);
+      ck(b2d_guess_transform(g.ctx, old.data(), 0, 0, -1, flat.data()), "b2d_guess_transform(one-dot transpose)");
+      collect(solution[i], flat);
+      oldSI.Free();
+    }
+    g.t_guess += now_s() - t0;
+    return;
+  }
   if (covered && gw == TRANSPOSE && !onedot) {
     // first block iteration of a sweep: transpose_previous_wavefunction (guess_wavefunction.C:55-84) = b2d_guess_desc mode 3
     bool done = true;

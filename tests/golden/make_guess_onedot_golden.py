@@ -42,6 +42,16 @@ def main():
                 rec = dumpio.read_records(path)
                 have[int(rec["meta"][3])].append((c, rec))
         print(name, "one-dot TRANSFORM guesses: dot on the system side", [c for c, _ in have[1]], "on the environment side", [c for c, _ in have[0]])
+        tr = []
+        for c in range(10, 80):
+            path = os.path.join(work, "dump", "guessT1_%d.bin" % c)
+            if os.path.exists(path):
+                tr.append((c, dumpio.read_records(path)))
+        print(name, "one-dot TRANSPOSE guesses at calls", [c for c, _ in tr])
+        for c, rec in tr[:2]:
+            dst = os.path.join(HERE, "guessT1_%s_call%d.npz" % (name, c))
+            np.savez_compressed(dst, **rec)
+            print("  ", name, c, "one-dot transpose", "forward" if int(rec["meta"][1]) else "backward", "W = %d, %.1f kB" % (rec["gw0.trial"].size, os.path.getsize(dst) / 1e3))
         for flag in (0, 1):
             if not have[flag]:
                 continue

@@ -78,3 +78,16 @@ def test_transpose_guess_matches_reference(path):
     rec = dict(np.load(path))
     for root in range(int(rec["gw.nroots"][0])):
         assert np.array_equal(G.transpose_previous_wavefunction(rec, root), rec["gw%d.trial" % root])
+
+
+TRANSPOSE1 = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "guessT1_*.npz")))
+
+
+@pytest.mark.parametrize("path", TRANSPOSE1, ids=[os.path.basename(f)[:-4] for f in TRANSPOSE1])
+def test_onedot_transpose_guess_matches_reference(path):
+    """GuessWave::onedot_transpose_wavefunction (guess_wavefunction.C:140-198)."""
+    rec = dict(np.load(path))
+    assert TRANSPOSE1
+    for root in range(int(rec["gw.nroots"][0])):
+        ref = rec["gw%d.trial" % root]
+        assert np.linalg.norm(G.onedot_transpose_wavefunction(rec, root) - ref) / np.linalg.norm(ref) < 1e-13

@@ -211,3 +211,28 @@ def test_planned_transpose_guess_reproduces_the_reference_trial_vector(path):
             assert gt.flops == 0 and gt.shuffle_rounds == 1
         finally:
             gt.close()
+
+
+TRANSPOSE1 = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "guessT1_*.npz")))
+
+
+def make_onedot_transpose(rec, root, device):
+    p = "gw%d." % root
+    tabs = {k: {key[len(p + k + "."):]: rec[key] for key in rec if key.startswith(p + k + ".")} for k in ("left", "sys", "dot", "right", "oldleft", "oldcol")}
+    return hotpath.GuessTransform(rec[p + "dq"][:3], tabs, rec[p + "old.allowed"], None, None, device=device, mode=4)
+
+
+@pytest.mark.parametrize("path", TRANSPOSE1, ids=[os.path.basename(f)[:-4] for f in TRANSPOSE1])
+def test_planned_onedot_transpose_guess_reproduces_the_reference_trial_vector(path):
+    """First block iteration of a one-dot sweep (GuessWave::onedot_transpose_wavefunction, guess_wavefunction.C:140-198)."""
+    rec = dict(np.load(path))
+    for root in range(int(rec["gw.nroots"][0])):
+        p = "gw%d." % root
+        gt = make_onedot_transpose(rec, root, device=-1)
+        try:
+            got = execute_plan(gt, rec[p + "old.data"], np.zeros(0), np.zeros(0))
+            ref = rec[p + "trial"]
+            assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-13
+            assert gt.flops == 0 and gt.shuffle_tasks > 0
+        finally:
+            gt.close()

@@ -12,7 +12,7 @@ import pytest
 
 from block_b200 import hotpath
 from oracle import guess_oracle as G
-from test_guess_planner_cpu import make, make_onedot, make_transpose
+from test_guess_planner_cpu import make, make_onedot, make_onedot_transpose, make_transpose
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 # Everything in this module exercises device code that was finished AFTER this round's GPU budget was spent (planners and oracles are
@@ -153,5 +153,23 @@ def test_device_transpose_guess_is_bit_exact(path):
         try:
             got = gt.transform(rec["gw%d.old.data" % root])
             assert np.array_equal(got, rec["gw%d.trial" % root])
+        finally:
+            gt.close()
+
+
+TRANSPOSE1 = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "guessT1_*.npz")))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", TRANSPOSE1, ids=[os.path.basename(f)[:-4] for f in TRANSPOSE1])
+def test_device_onedot_transpose_guess_matches_reference(path):
+    """b2d_guess_desc mode 4 (first block iteration of a one-dot sweep) on the device."""
+    rec = dict(np.load(path))
+    for root in range(int(rec["gw.nroots"][0])):
+        gt = make_onedot_transpose(rec, root, device=0)
+        try:
+            got = gt.transform(rec["gw%d.old.data" % root])
+            ref = rec["gw%d.trial" % root]
+            assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-13
         finally:
             gt.close()

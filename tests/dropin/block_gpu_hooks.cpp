@@ -64,6 +64,7 @@
 #include "guess_wavefunction.h"
 
 #include "block_b200.h"
+#include "guess_binding.hpp"
 
 using namespace SpinAdapted;
 using std::string;
@@ -409,36 +410,10 @@ void wrap_diagonalH(const SpinBlock* self, DiagonalMatrix& e) {
 }
 
 // ---- GuessWave::guess_wavefunctions (vector form, solver.C:77) ----
-// SURVEY N1.  For a TRANSFORM guess (two-dot: transform_previous_wavefunction :524-636; one-dot: onedot_transform_wavefunction :832-936) the reference loads the previous wavefunction and two rotation matrices from its
+// SURVEY N1.  For a TRANSFORM or TRANSPOSE guess (two-dot :524-636 / :55-84, one-dot :832-936 / :140-198) the reference loads the previous wavefunction and two rotation matrices from its
 // scratch files and runs TransformLeftBlock / onedot_shufflesysdot / TransformRightBlock on the CPU (guess_wavefunction.C:524-636).  Here
 // the same files are loaded the same way, the StateInfo tables the transform reads are handed to b2d_guess_plan, and the arithmetic runs
 // on the device.  BASIC / TRANSPOSE guesses go to the reference's own function.
-void fill_stateinfo(b2d_stateinfo& o, const StateInfo& s, vector<vector<int32_t> >& keep) {
-  memset(&o, 0, sizeof(o));
-  auto hold = [&](const vector<int>& v) -> const int32_t* { keep.push_back(vector<int32_t>(v.begin(), v.end())); if (keep.back().empty()) keep.back().push_back(0); return keep.back().data(); };
-  auto quanta = [&](const StateInfo& t) -> const int32_t* {
-    vector<int> q;
-    for (size_t i = 0; i < t.quanta.size(); ++i) { q.push_back(t.quanta[i].get_n()); q.push_back(t.quanta[i].get_s().getirrep()); q.push_back(t.quanta[i].get_symm().getirrep()); }
-    return hold(q);
-  };
-  o.nq = (int32_t)s.quanta.size();
-  o.q = quanta(s);
-  o.dims = hold(s.quantaStates);
-  o.new_quanta_map = s.newQuantaMap.size() == s.quanta.size() && !s.newQuantaMap.empty() ? hold(s.newQuantaMap) : 0;
-  if (s.hasCollectedQuanta && s.unCollectedStateInfo) {
-    const StateInfo& u = *s.unCollectedStateInfo;
-    o.nunc = (int32_t)u.quanta.size();
-    o.unc_q = quanta(u);
-    o.unc_dims = hold(u.quantaStates);
-    o.unc_left = hold(u.leftUnMapQuanta);
-    o.unc_right = hold(u.rightUnMapQuanta);
-    vector<int> flat, begin(1, 0);
-    for (size_t q = 0; q < s.oldToNewState.size(); ++q) { flat.insert(flat.end(), s.oldToNewState[q].begin(), s.oldToNewState[q].end()); begin.push_back((int)flat.size()); }
-    o.old_to_new_begin = hold(begin);
-    o.old_to_new = hold(flat);
-  }
-}
-
 void real_guess(vector<Wavefunction>& solution, DiagonalMatrix& e, const SpinBlock& big, const guessWaveTypes& gw, const bool& onedot,
                 const bool& transpose_guess_wave, double additional_noise, int currentState) asm("__real_" SYM_guess_wavefunctions);
 void wrap_guess(vector<Wavefunction>& solution, DiagonalMatrix& e, const SpinBlock& big, const guessWaveTypes& gw, const bool& onedot,
@@ -446,158 +421,25 @@ void wrap_guess(vector<Wavefunction>& solution, DiagonalMatrix& e, const SpinBlo
 void wrap_guess(vector<Wavefunction>& solution, DiagonalMatrix& e, const SpinBlock& big, const guessWaveTypes& gw, const bool& onedot,
                 const bool& transpose_guess_wave, double additional_noise, int currentState) {
   const char* mode = getenv("B2D_DROPIN_GUESS");
-  const bool covered = mode && string(mode) == "device" && g.ctx && dmrginp.spinAdapted() && dmrginp.hamiltonian() != BCS && !dmrginp.transition_diff_irrep();
-  const bool on_device = covered && gw == TRANSFORM && big.get_leftBlock()->get_leftBlock();
+  if (!(mode && string(mode) == "device" && g.ctx) || gw == BASIC) { real_guess(solution, e, big, gw, onedot, transpose_guess_wave, additional_noise, currentState); return; }
   double t0 = now_s();
-  const StateInfo& bs = big.get_stateInfo();
-  if (covered && gw == TRANSPOSE && onedot && big.get_leftBlock()->get_rightBlock()) {
-    // first block iteration of a one-dot sweep: onedot_transpose_wavefunction (guess_wavefunction.C:100-112, :140-198) = mode 4
-    vector<int> wfsites = big.get_rightBlock()->get_sites();
-    wfsites.insert(wfsites.end(), big.get_leftBlock()->get_rightBlock()->get_sites().begin(), big.get_leftBlock()->get_rightBlock()->get_sites().end());
-    std::sort(wfsites.begin(), wfsites.end());
-    for (size_t i = 0; i < solution.size(); ++i) {
-      const int state = (dmrginp.setStateSpecific() || dmrginp.calc_type() == COMPRESS || dmrginp.calc_type() == MPS_NEVPT) ? currentState : (int)i;
-      StateInfo oldSI;
-      Wavefunction oldWave;
-      oldWave.LoadWavefunctionInfo(oldSI, wfsites, state);
-      if (oldWave.get_deltaQuantum_size() != 1) die("guess transpose: wavefunction with several target quanta: not covered");
-      solution[i].initialise(dmrginp.effective_molecule_quantum_vec(), &big, onedot);
-      vector<vector<int32_t> > keep;
-      keep.reserve(96);
-      b2d_guess_desc d;
-      memset(&d, 0, sizeof(d));
-      SpinQuantum dq = oldWave.get_deltaQuantum(0);
-      d.dq[0] = dq.get_n(); d.dq[1] = dq.get_s().getirrep(); d.dq[2] = dq.get_symm().getirrep();
-      d.mode = 4;
-      fill_stateinfo(d.left, *bs.leftStateInfo, keep);
-      fill_stateinfo(d.sys, *bs.leftStateInfo->leftStateInfo, keep);
-      fill_stateinfo(d.dot, *bs.leftStateInfo->rightStateInfo, keep);
-      fill_stateinfo(d.right, *bs.rightStateInfo, keep);
-      fill_stateinfo(d.oldleft, *oldSI.leftStateInfo, keep);
-      fill_stateinfo(d.oldcol, *oldSI.rightStateInfo, keep);
-      vector<uint8_t> allowed; vector<double> old;
-      for (int a = 0; a < oldWave.nrows(); ++a) for (int b = 0; b < oldWave.ncols(); ++b) {
-        allowed.push_back(oldWave.allowed(a, b) ? 1 : 0);
-        if (oldWave.allowed(a, b)) { const Matrix& m = oldWave.operator_element(a, b); old.insert(old.end(), m.Store(), m.Store() + m.Storage()); }
-      }
-      d.old_allowed = allowed.data();
-      double info[8];
-      ck(b2d_guess_plan(g.ctx, &d, info, 8), "b2d_guess_plan(one-dot transpose)");
-      vector<double> flat((size_t)info[3]);
-      if ((int64_t)flat.size() != g.W) die("guess transpose: trial vector length differs from the psi layout");
-      if (old.empty()) old.push_back(0);
-      ck(b2d_guess_transform(g.ctx, old.data(), 0, 0, -1, flat.data()), "b2d_guess_transform(one-dot transpose)");
-      collect(solution[i], flat);
-      oldSI.Free();
-    }
-    g.t_guess += now_s() - t0;
-    return;
-  }
-  if (covered && gw == TRANSPOSE && !onedot) {
-    // first block iteration of a sweep: transpose_previous_wavefunction (guess_wavefunction.C:55-84) = b2d_guess_desc mode 3
-    bool done = true;
-    for (size_t i = 0; i < solution.size() && done; ++i) {
-      const int state = (dmrginp.setStateSpecific() || dmrginp.calc_type() == COMPRESS || dmrginp.calc_type() == MPS_NEVPT) ? currentState : (int)i;
-      StateInfo oldSI;
-      Wavefunction oldWave;
-      oldWave.LoadWavefunctionInfo(oldSI, big.get_rightBlock()->get_sites(), state);     // :62
-      if (oldWave.get_onedot() || oldWave.get_deltaQuantum_size() != 1) { oldSI.Free(); done = false; break; }   // one-dot -> two-dot switch: the reference's own
-      solution[i].initialise(dmrginp.effective_molecule_quantum_vec(), &big, onedot);
-      vector<vector<int32_t> > keep;
-      keep.reserve(64);
-      b2d_guess_desc d;
-      memset(&d, 0, sizeof(d));
-      SpinQuantum dq = oldWave.get_deltaQuantum(0);
-      d.dq[0] = dq.get_n(); d.dq[1] = dq.get_s().getirrep(); d.dq[2] = dq.get_symm().getirrep();
-      d.mode = 3;
-      fill_stateinfo(d.left, *bs.leftStateInfo, keep);
-      fill_stateinfo(d.right, *bs.rightStateInfo, keep);
-      fill_stateinfo(d.oldleft, *oldSI.leftStateInfo, keep);
-      fill_stateinfo(d.oldcol, *oldSI.rightStateInfo, keep);
-      vector<uint8_t> allowed; vector<double> old;
-      for (int a = 0; a < oldWave.nrows(); ++a) for (int b = 0; b < oldWave.ncols(); ++b) {
-        allowed.push_back(oldWave.allowed(a, b) ? 1 : 0);
-        if (oldWave.allowed(a, b)) { const Matrix& m = oldWave.operator_element(a, b); old.insert(old.end(), m.Store(), m.Store() + m.Storage()); }
-      }
-      d.old_allowed = allowed.data();
-      double info[8];
-      ck(b2d_guess_plan(g.ctx, &d, info, 8), "b2d_guess_plan(transpose)");
-      vector<double> flat((size_t)info[3]);
-      if ((int64_t)flat.size() != g.W) die("guess transpose: trial vector length differs from the psi layout");
-      if (old.empty()) old.push_back(0);
-      ck(b2d_guess_transform(g.ctx, old.data(), 0, 0, -1, flat.data()), "b2d_guess_transform(transpose)");
-      collect(solution[i], flat);
-      oldSI.Free();
-    }
-    if (done) { g.t_guess += now_s() - t0; return; }
-  }
-  if (!on_device) { real_guess(solution, e, big, gw, onedot, transpose_guess_wave, additional_noise, currentState); return; }
+  // every root must be one of the covered forms, otherwise the whole call goes to the reference (it owns the loop over roots)
+  vector<b2d_binding::GuessBinding> B(solution.size());
   for (size_t i = 0; i < solution.size(); ++i) {
-    const int state = (dmrginp.setStateSpecific() || dmrginp.calc_type() == COMPRESS || dmrginp.calc_type() == MPS_NEVPT) ? currentState : (int)i;
+    const int state = (dmrginp.setStateSpecific() || dmrginp.calc_type() == COMPRESS || dmrginp.calc_type() == MPS_NEVPT) ? currentState : (int)i;   // :383
+    if (!b2d_binding::make_guess_binding(B[i], big, gw, onedot, transpose_guess_wave, state)) {
+      real_guess(solution, e, big, gw, onedot, transpose_guess_wave, additional_noise, currentState);
+      return;
+    }
+  }
+  for (size_t i = 0; i < solution.size(); ++i) {
     solution[i].initialise(dmrginp.effective_molecule_quantum_vec(), &big, onedot);     // guess_wavefunction.C:282
-    StateInfo oldSI;
-    Wavefunction oldWave;
-    vector<Matrix> lrot, rrot;
-    StateInfo newenv;
-    if (!onedot || transpose_guess_wave) {
-      oldWave.LoadWavefunctionInfo(oldSI, big.get_leftBlock()->get_leftBlock()->get_sites(), state);     // :537
-      LoadRotationMatrix(big.get_leftBlock()->get_leftBlock()->get_sites(), lrot, state);                // :538
-    } else {
-      oldWave.LoadWavefunctionInfo(oldSI, big.get_leftBlock()->get_sites(), state);                      // :541
-      LoadRotationMatrix(big.get_leftBlock()->get_sites(), lrot, state);                                 // :542
-    }
-    if (onedot && transpose_guess_wave) {                                                                // :617-622
-      vector<int> rotsites = big.get_rightBlock()->get_sites();
-      rotsites.insert(rotsites.end(), big.get_leftBlock()->get_rightBlock()->get_sites().begin(), big.get_leftBlock()->get_rightBlock()->get_sites().end());
-      std::sort(rotsites.begin(), rotsites.end());
-      LoadRotationMatrix(rotsites, rrot, state);
-      // the environment side with the dot still attached: the reference's own integer bookkeeping (:853-856)
-      TensorProduct(*(bs.rightStateInfo), *(bs.leftStateInfo->rightStateInfo), newenv, NO_PARTICLE_SPIN_NUMBER_CONSTRAINT);
-      newenv.CollectQuanta();
-    } else {
-      LoadRotationMatrix(big.get_rightBlock()->get_sites(), rrot, state);                                // :613 / :625
-    }
-    if (oldWave.get_deltaQuantum_size() != 1) die("guess transform: wavefunction with several target quanta: not covered");
-    vector<vector<int32_t> > keep;
-    keep.reserve(128);
-    b2d_guess_desc d;
-    memset(&d, 0, sizeof(d));
-    SpinQuantum dq = oldWave.get_deltaQuantum(0);
-    d.dq[0] = dq.get_n(); d.dq[1] = dq.get_s().getirrep(); d.dq[2] = dq.get_symm().getirrep();
-    d.mode = !onedot ? 0 : (transpose_guess_wave ? 1 : 2);
-    fill_stateinfo(d.left, *bs.leftStateInfo, keep);
-    fill_stateinfo(d.right, *bs.rightStateInfo, keep);
-    fill_stateinfo(d.oldleft, *oldSI.leftStateInfo, keep);
-    if (d.mode != 2) {
-      fill_stateinfo(d.sys, *bs.leftStateInfo->leftStateInfo, keep);
-      fill_stateinfo(d.dot, *bs.leftStateInfo->rightStateInfo, keep);
-    }
-    if (d.mode == 0) {
-      fill_stateinfo(d.oldright, *oldSI.rightStateInfo, keep);
-      fill_stateinfo(d.env, *oldSI.rightStateInfo->leftStateInfo, keep);
-    } else {
-      fill_stateinfo(d.oldcol, *oldSI.rightStateInfo, keep);
-      if (d.mode == 1) fill_stateinfo(d.oldright, newenv, keep);
-    }
-    vector<uint8_t> allowed; vector<double> old, lr, rr;
-    for (int a = 0; a < oldWave.nrows(); ++a) for (int b = 0; b < oldWave.ncols(); ++b) {
-      allowed.push_back(oldWave.allowed(a, b) ? 1 : 0);
-      if (oldWave.allowed(a, b)) { const Matrix& m = oldWave.operator_element(a, b); old.insert(old.end(), m.Store(), m.Store() + m.Storage()); }
-    }
-    vector<int32_t> lcols, rcols;
-    for (size_t q = 0; q < lrot.size(); ++q) { lcols.push_back(lrot[q].Ncols()); if (lrot[q].Ncols()) lr.insert(lr.end(), lrot[q].Store(), lrot[q].Store() + lrot[q].Storage()); }
-    for (size_t q = 0; q < rrot.size(); ++q) { rcols.push_back(rrot[q].Ncols()); if (rrot[q].Ncols()) rr.insert(rr.end(), rrot[q].Store(), rrot[q].Store() + rrot[q].Storage()); }
-    if ((int)lcols.size() != d.oldleft.nq || (int)rcols.size() != (d.mode == 1 ? d.oldright.nq : d.right.nq))
-      die("guess transform: rotation matrices do not match the StateInfo of their blocks");
-    d.old_allowed = allowed.data(); d.lrot_cols = lcols.data(); d.rrot_cols = rcols.data();
     double info[8];
-    ck(b2d_guess_plan(g.ctx, &d, info, 8), "b2d_guess_plan");
+    ck(b2d_guess_plan(g.ctx, &B[i].d, info, 8), "b2d_guess_plan");
     vector<double> flat((size_t)info[3]);
     if ((int64_t)flat.size() != g.W) die("guess transform: trial vector length differs from the psi layout");
-    if (old.empty()) old.push_back(0); if (lr.empty()) lr.push_back(0); if (rr.empty()) rr.push_back(0);
-    ck(b2d_guess_transform(g.ctx, old.data(), lr.data(), rr.data(), -1, flat.data()), "b2d_guess_transform");
+    ck(b2d_guess_transform(g.ctx, B[i].old.data(), B[i].lrot.data(), B[i].rrot.data(), -1, flat.data()), "b2d_guess_transform");
     collect(solution[i], flat);
-    oldSI.Free();
   }
   if (env_on("B2D_DROPIN_CHECK")) {   // the reference's own transform of every root (its loop maps root i to state i itself)
     vector<Wavefunction> ref(solution.size());
@@ -606,7 +448,7 @@ void wrap_guess(vector<Wavefunction>& solution, DiagonalMatrix& e, const SpinBlo
       vector<double> rf, gf; flatten(ref[i], rf); flatten(solution[i], gf);
       double worst = 0, scale = 0;
       for (size_t k = 0; k < rf.size() && k < gf.size(); ++k) { worst = std::max(worst, fabs(rf[k] - gf[k])); scale = std::max(scale, fabs(rf[k])); }
-      fprintf(stderr, "B2D_CHECK call=%d guess_transform root=%d max_abs_diff=%.3e (max |psi| %.3e)\n", g.call, (int)i, worst, scale);
+      fprintf(stderr, "B2D_CHECK call=%d guess_transform mode=%d root=%d max_abs_diff=%.3e (max |psi| %.3e)\n", g.call, (int)B[i].d.mode, (int)i, worst, scale);
     }
   }
   g.t_guess += now_s() - t0;

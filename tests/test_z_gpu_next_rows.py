@@ -173,3 +173,27 @@ def test_device_onedot_transpose_guess_matches_reference(path):
             assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-13
         finally:
             gt.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["c2_d2h_M50_onedot_tail", "hubbard_L16_M80"])
+def test_dropin_sweep_with_device_guess_and_batched_operator_construction(name):
+    """The unmodified reference sweep with the hot path on the GPU AND the two pieces finished after the GPU budget was spent switched on
+    (B2D_DROPIN_GUESS=device, opbuild_batch=1), in check mode: every transformed guess against the reference's own transform on the same
+    inputs, every sweep energy against the unmodified reference's golden sweeps (1e-8 Eh)."""
+    import re
+    import test_gpu_dropin as D
+    out, golden, stats = D.run_case(name, {"B2D_DROPIN_GUESS": "device", "B2D_DROPIN_OPTIONS": "opbuild_batch=1", "B2D_DROPIN_CHECK": "1"})
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
+    lines = [l for l in out.stderr.splitlines() if l.startswith("B2D_CHECK") and " guess_transform " in l]
+    assert lines, "no guess was transformed on the device"
+    modes = set()
+    for l in lines:
+        modes.add(int(re.search(r"mode=(\d+)", l).group(1)))
+        assert float(re.search(r"max_abs_diff=(\S+)", l).group(1)) < 1e-12, l
+    assert 0 in modes and 3 in modes
+    got = D.parse_sweeps(out.stdout)
+    assert len(got) == len(golden)
+    for (m1, s1, dw1, e1), (m2, s2, dw2, e2) in zip(got, golden):
+        assert (m1, s1) == (m2, s2) and abs(e1 - e2) <= 1e-8, (name, m1, s1, e1, e2)
+    print("%s: %d device guesses (modes %s), sweep energies within 1e-8 Eh" % (name, len(lines), sorted(modes)))

@@ -197,3 +197,22 @@ def test_dropin_sweep_with_device_guess_and_batched_operator_construction(name):
     for (m1, s1, dw1, e1), (m2, s2, dw2, e2) in zip(got, golden):
         assert (m1, s1) == (m2, s2) and abs(e1 - e2) <= 1e-8, (name, m1, s1, e1, e2)
     print("%s: %d device guesses (modes %s), sweep energies within 1e-8 Eh" % (name, len(lines), sorted(modes)))
+
+
+@pytest.mark.gpu
+def test_reference_known_answer_test_h2o_nosym():
+    """The reference's OWN known-answer test, verbatim (dmrg_tests/runtest:19-23: dmrg_tests/h2o_nosym/{FCIDUMP, dmrg.conf} - default
+    schedule with noise, default orbital reordering, two-dot -> one-dot - accepted by `test_energy.py 1 1.0e-6 -76.11460447`), run through
+    the GPU drop-in and judged by the reference's own criterion; also compared with the final energy of the CPU reference built here."""
+    import test_gpu_dropin as D
+    z = np.load(D.CASES)
+    target, tol = (float(x) for x in z["h2o_nosym_runtest/runtest"])
+    out, _, stats = D.run_case("h2o_nosym_runtest")
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-3000:]
+    got = D.parse_sweeps(out.stdout)
+    ref = D.parse_sweeps(z["h2o_nosym_runtest/ref_sweeps"].tobytes().decode())
+    assert got and abs(got[-1][3] - target) <= tol, (got[-1], target)            # test_energy.py: |E - E_ref| < 1e-6
+    assert abs(got[-1][3] - ref[-1][3]) <= 1e-7                                   # the CPU reference built here ends at -76.1146044053
+    assert "n_multiply" in stats
+    print("h2o_nosym (reference's own test): E = %.10f, published %.8f, CPU reference here %.10f, %d sweeps (reference: %d)" %
+          (got[-1][3], target, ref[-1][3], len(got), len(ref)))

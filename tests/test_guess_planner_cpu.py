@@ -236,3 +236,39 @@ def test_planned_onedot_transpose_guess_reproduces_the_reference_trial_vector(pa
             assert gt.flops == 0 and gt.shuffle_tasks > 0
         finally:
             gt.close()
+
+
+def test_planner_rejects_inconsistent_descriptions():
+    """Host-side validation (the reference aborts on such inputs; the C ABI returns an error with a message)."""
+    rec = dict(np.load(FIXTURES[0]))
+    p = "gw0."
+    tabs = tables(rec, 0)
+    lcols, rcols = rec[p + "lrot.shape"][:, 1].copy(), rec[p + "rrot.shape"][:, 1].copy()
+    with pytest.raises(hotpath.B2DError, match="mode must be"):
+        _plan_with_mode(7)
+    bad = lcols.copy()
+    k = int(np.flatnonzero(bad > 0)[0])
+    bad[k] += 1                                          # a left rotation matrix with one column too many
+    with pytest.raises(hotpath.B2DError, match="left rotation matrix does not match"):
+        hotpath.GuessTransform(rec[p + "dq"][:3], tabs, rec[p + "old.allowed"], bad, rcols, device=-1)
+    broken = dict(tabs)
+    broken["oldright"] = dict(tabs["oldright"])
+    broken["oldright"]["unc.dims"] = tabs["oldright"]["unc.dims"] + 1      # pieces no longer add up to the collected sectors
+    with pytest.raises(hotpath.B2DError, match="do not add up"):
+        hotpath.GuessTransform(rec[p + "dq"][:3], broken, rec[p + "old.allowed"], lcols, rcols, device=-1)
+
+
+def _plan_with_mode(mode):
+    lib = hotpath._lib.load()
+    import ctypes as C
+    ctx = C.c_void_p()
+    assert lib.b2d_create(-1, C.byref(ctx)) == 0
+    try:
+        d = hotpath._lib.GuessDescC()
+        d.mode = mode
+        out = np.zeros(8)
+        rc = lib.b2d_guess_plan(ctx, C.byref(d), out.ctypes.data_as(hotpath._lib.c_f64p), 8)
+        if rc:
+            raise hotpath.B2DError(lib.b2d_last_error(ctx).decode())
+    finally:
+        lib.b2d_destroy(ctx)

@@ -1,9 +1,12 @@
-"""GPU: the guess-wavefunction transform on the device (b2d_guess_plan + b2d_guess_transform through the C ABI) against
-the REAL reference's trial vectors (tests/golden/guess_*.npz: GuessWave::transform_previous_wavefunction, guess_wavefunction.C:524-636)
-and against the pinned oracle, on forward and backward block iterations of C2/D2h (two roots), H2O/C1 and Hubbard.
-Tolerance: 1e-12 relative (FP64 contractions with different summation order; north_star's bar for vectors is 1e-10).
-(File name: sorts after every other test module - this device path was finished after the round's GPU budget was spent, its planner is
-pinned on CPU by tests/test_guess_planner_cpu.py, and its first run on a B200 is the round-end one.)"""
+"""GPU: the rows of SURVEY.md 8f that were finished after this round's GPU budget was spent, through the C ABI:
+  * the guess-wavefunction transform on the device (b2d_guess_plan + b2d_guess_transform, N1) in its five forms - two-dot / one-dot
+    TRANSFORM, two-dot / one-dot TRANSPOSE - against the REAL reference's trial vectors (tests/golden/guess*_*.npz), the pinned oracle
+    and, on synthetic sectors of a few hundred states, the same plan executed with numpy; tolerance 1e-12 relative (FP64 contractions
+    with a different summation order; north_star's bar for vectors is 1e-10), the transpositions bit-exact;
+  * batched construction of the enlarged-block operators (option opbuild_batch, N2): bit-identical to the one-launch-per-product path;
+  * drop-in sweeps with both switched on, in check mode; the reference's own known-answer test (dmrg_tests/h2o_nosym) through the drop-in.
+(File name: sorts after every other test module; planners, oracles and the reference-side binding are pinned on CPU by
+tests/test_guess_planner_cpu.py, test_guess_oracle.py and test_guess_binding_cpu.py; the first run on a B200 is the round-end one.)"""
 import glob
 import os
 

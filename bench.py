@@ -378,8 +378,9 @@ def sweep_leg(a):
 
 
 def next_rows_leg(a):
-    """Rows of SURVEY.md 8f behind the C ABI (guess-wavefunction transform, N1) at the benchmark's size, in a process of its own: a
-    failure there is reported under "error" and never touches the measurements above."""
+    """Rows of SURVEY.md 8f behind the C ABI at the benchmark's size - the guess-wavefunction transform (N1) and, under
+    "operator_construction", the construction of the enlarged block's operators (N2: kron_scatter_kernel against the HBM roofline) - in a
+    process of its own: a failure there is reported under "error" and never touches the measurements above."""
     cmd = [sys.executable, os.path.join(ROOT, "scripts", "bench_next_rows.py"), "--norbs", str(a.norbs), "--nelec", str(a.nelec), "--M", str(a.M),
            "--left-sites", str(a.left_sites)]
     try:
@@ -568,7 +569,7 @@ def run_ours(a):
     if line is not None and world == 1 and not a.no_sweep:
         line["sweep"] = sweep_leg(a)
     if line is not None and world == 1 and not a.no_block_iteration:
-        line["guess_transform"] = next_rows_leg(a)
+        line["next_rows"] = next_rows_leg(a)      # guess-wavefunction transform (N1) + "operator_construction" (N2) at this size
     if line is not None:
         emit(line)
     if world > 1:

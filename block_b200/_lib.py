@@ -90,6 +90,7 @@ PROTOTYPES = {
     "b2d_set_product_stateinfo": (C.c_int, [ctx_p, C.c_int, c_i32p, c_i32p, C.c_int, c_i32p, c_i32p, c_i32p, c_i32p, c_i32p]),
     "b2d_product_op_create": (C.c_int, [ctx_p, c_i32p, C.c_int, C.POINTER(C.c_int)]),
     "b2d_product_op_accumulate": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double]),
+    "b2d_product_stats": (C.c_int, [ctx_p, c_f64p, C.c_int]),
     "b2d_product_op_size": (C.c_int64, [ctx_p, C.c_int]),
     "b2d_product_op_download": (C.c_int, [ctx_p, C.c_int, c_u8p, c_f64p]),
     "b2d_set_integrals": (C.c_int, [ctx_p, C.c_int, c_f64p, c_f64p, c_i32p, C.c_double, C.c_double]),

@@ -204,6 +204,9 @@ struct b2d_ctx {
   std::vector<KronTask> pend_kron;          // deferred tasks ...
   std::vector<int> pend_kron_round;         // ... and the round of each: how many earlier tasks hit the same destination piece
   std::map<std::array<int64_t, 3>, int> pend_kron_hits;
+  double kron_bytes = 0.0;                  // algorithmic bytes of the scatter tasks planned since b2d_set_product_stateinfo (8 x (|A| + |B| + 2 |dst piece|))
+  int64_t kron_ntasks = 0, kron_nproducts = 0;
+  int kron_last_rounds = 0;                 // rounds (launches) of the last batched flush
   Side stash[2];                            // children of the big block parked by b2d_stash_product / b2d_stash_side
   bool stash_set[2] = {false, false};
   Integrals integrals;                      // one- / two-electron integrals for the complementary operators (b2d_set_integrals)
@@ -1983,6 +1986,7 @@ int b2d_set_product_stateinfo(b2d_ctx* ctx, int nq, const int32_t* q, const int3
   if (!ctx || nq <= 0 || !q || !dims || nunc <= 0 || !lmap || !rmap || !unc_dims || !old_to_new_begin || !old_to_new)
     return fail(ctx, B2D_ERR_ARG, "b2d_set_product_stateinfo: bad arguments");
   ctx->pend_kron.clear(); ctx->pend_kron_round.clear(); ctx->pend_kron_hits.clear();   // deferred tasks of a product block nobody stashed
+  ctx->kron_bytes = 0.0; ctx->kron_ntasks = ctx->kron_nproducts = 0; ctx->kron_last_rounds = 0;
   const Side& L = ctx->side[0];
   const Side& R = ctx->side[1];
   if (L.nq == 0 || R.nq == 0) return fail(ctx, B2D_ERR_ARG, "b2d_set_product_stateinfo: set both children first (b2d_set_block)");
@@ -2048,9 +2052,12 @@ static int flush_product_tasks(b2d_ctx* ctx) {
   }
   int rc = upload_desc(ctx, ctx->kron_tasks, sorted.data(), sorted.size() * sizeof(KronTask));
   if (rc) return rc;
+  begin_timing(ctx);   // b2d_last_timing: device time of the whole batched construction
   for (int r = 0; r < nrounds; ++r)
     CU(launch_kron_scatter((const KronTask*)ctx->kron_tasks.p + count[r], count[r + 1] - count[r], ctx->stream, &ctx->launches));
+  end_timing(ctx);
   CU(cudaStreamSynchronize(ctx->stream));
+  ctx->kron_last_rounds = nrounds;
   ctx->pend_kron.clear(); ctx->pend_kron_round.clear(); ctx->pend_kron_hits.clear();
   return B2D_OK;
 }
@@ -2113,6 +2120,10 @@ static int product_op_accumulate_impl(b2d_ctx* ctx, int prod_id, int left_op, in
         }
       }
   } catch (const std::exception& e) { return fail(ctx, B2D_ERR_ARG, e.what()); }
+  for (const KronTask& k : tasks)
+    ctx->kron_bytes += 8.0 * ((k.a ? (double)k.a_rows * k.a_cols : 0.0) + (k.b ? (double)k.b_rows * k.b_cols : 0.0) + 2.0 * (double)k.a_rows * k.b_rows * k.a_cols * k.b_cols);
+  ctx->kron_ntasks += (int64_t)tasks.size();
+  ctx->kron_nproducts += 1;
   if (defer) {
     for (const KronTask& k : tasks) {
       int& hits = ctx->pend_kron_hits[std::array<int64_t, 3>{k.dst, (int64_t)k.row0, (int64_t)k.col0}];
@@ -2365,6 +2376,15 @@ int b2d_guess_transform(b2d_ctx* ctx, const double* old_wave, const double* left
     CU(cudaMemcpyAsync(trial, ctx->staging.p, (size_t)P.trial.W * 8, cudaMemcpyDeviceToHost, ctx->stream));
   }
   CU(cudaStreamSynchronize(ctx->stream));
+  return B2D_OK;
+}
+
+// statistics of the operator construction since b2d_set_product_stateinfo: out = {products, scatter tasks, algorithmic bytes, rounds of the
+// last batched flush}
+int b2d_product_stats(const b2d_ctx* ctx, double* out, int n) {
+  if (!ctx || !out) return B2D_ERR_ARG;
+  const double v[4] = {(double)ctx->kron_nproducts, (double)ctx->kron_ntasks, ctx->kron_bytes, (double)ctx->kron_last_rounds};
+  for (int i = 0; i < n && i < 4; ++i) out[i] = v[i];
   return B2D_OK;
 }
 

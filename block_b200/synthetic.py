@@ -223,3 +223,32 @@ def allowed_mask_pair(ql, qr, dq):
     """Wavefunction::AllowQuantaFor (wavefunction.C:393-415): block (i, j) exists iff dq is in q_i x q_j (C1)."""
     Nl, Sl, Nr, Sr = ql[:, 0][:, None], ql[:, 1][:, None], qr[:, 0][None, :], qr[:, 1][None, :]
     return (Nl + Nr == dq[0]) & (np.abs(Sl - Sr) <= dq[1]) & (dq[1] <= Sl + Sr) & ((Sl + Sr + dq[1]) % 2 == 0)
+
+
+# ---- construction of the enlarged-block operators at the same shape (SURVEY.md N2) ----------------------------------------------
+def make_opbuild_case(norbs=40, nelec=40, M=4000, left_sites=None, op_sites=6, other_sites=6, seed=20260, sigma_n=2.2, sigma_s=1.6):
+    """Children and product tables of the enlarged left block of make_big_block: (renormalised M-state block) x (one site).  The sector
+    tables are those of the full chain position; to bound memory the blocks carry the operator arrays of only `op_sites` own sites
+    (+ the dot) and `other_sites` sites of the other block.  Returns (left BlockSpec, dot BlockSpec, operators of the enlarged block,
+    product tables, h1, h2); operator values are seeded random numbers (the scatter's throughput does not depend on them)."""
+    nl = norbs // 2 if left_sites is None else left_sites
+    f = nelec / norbs
+    sys = renormalised_sectors(nl - 1, f * (nl - 1), M, sigma_n, sigma_s)
+    own = list(range(min(op_sites, nl - 1)))
+    dot_site = [nl - 1]
+    others = list(range(nl, min(norbs, nl + other_sites)))
+    left = make_block(sys, own, dot_site + others, loop=True)
+    dot = make_block({(0, 0): 1, (1, 1): 1, (2, 0): 1}, dot_site, own + others, loop=True)
+    enlarged = make_block(add_dot(sys), own + dot_site, others, loop=True)
+    rng = np.random.default_rng(seed)
+    for blk in (left, dot):
+        dims = blk.dims.astype(np.int64)
+        for op in blk.ops:
+            if op.data is None:
+                n = int((op.allowed.astype(np.int64) * np.outer(dims, dims)).sum())
+                op.data = rng.standard_normal(n) * 0.1
+    pt = product_tables(list(sys), np.array(list(sys.values()), np.int32))
+    h1 = rng.standard_normal((norbs, norbs)); h1 = h1 + h1.T
+    L = rng.standard_normal((norbs * norbs, 4)) * 0.1
+    h2 = (L @ L.T).reshape(norbs, norbs, norbs, norbs)
+    return left, dot, enlarged.ops, pt, h1, h2

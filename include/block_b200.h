@@ -285,6 +285,10 @@ int b2d_build_enlarged_op(b2d_ctx* ctx, int optype, int norb, const int32_t* orb
 int b2d_stash_product(b2d_ctx* ctx, int slot, int is_loop, int nsites, const int32_t* sites);
 int b2d_stash_side(b2d_ctx* ctx, int slot, int from_side);
 int b2d_assemble_big(b2d_ctx* ctx);
+/* Measurement: out[0..3] = {products, scatter tasks, ALGORITHMIC bytes of those tasks (8 x (|A| + |B| + 2 |destination piece|): operands read
+ * once, destination read-modified-written), launches of the last batched flush} since b2d_set_product_stateinfo; with option opbuild_batch
+ * b2d_last_timing gives the CUDA-event time of the batched flush. */
+int b2d_product_stats(const b2d_ctx* ctx, double* out, int n);
 int64_t b2d_product_op_size(const b2d_ctx* ctx, int prod_id);
 int b2d_product_op_download(b2d_ctx* ctx, int prod_id, uint8_t* allowed, double* data);   /* host layout of b2d_add_op */
 

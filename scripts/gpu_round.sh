@@ -21,3 +21,8 @@ PY
 done
 # 3. the bench's next-rows leg alone
 timeout 300 python scripts/bench_next_rows.py 2>&1 | tail -2 | tee gpurun_out/r16/bench_next_rows.json
+# 4. ncu launch list of the next-rows leg: DRAM traffic of kron_scatter_kernel (roofline.traffic of the operator construction) and of the
+#    guess transform's launches; a number printed under ncu is never a bench value
+timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -c 200 --csv \
+  --log-file gpurun_out/r16/ncu_next_rows_launches.csv python scripts/bench_next_rows.py --reps 1 > gpurun_out/r16/ncu_next_rows.log 2>&1
+grep -c kron_scatter gpurun_out/r16/ncu_next_rows_launches.csv

@@ -18,6 +18,7 @@
 #include "plan.hpp"
 #include "opbuild.hpp"
 #include "guess.hpp"
+#include "eig_block_jacobi.cuh"
 
 using namespace b2d;
 
@@ -200,7 +201,7 @@ struct b2d_ctx {
     bool set = false;
   } product;
   DevBuf kron_tasks;
-  bool opbuild_batch = false;               // b2d_build_enlarged_op defers its scatter tasks: one launch per ROUND for a whole child block
+  bool opbuild_batch = true;                // b2d_build_enlarged_op defers its scatter tasks: one launch per ROUND for a whole child block
   std::vector<KronTask> pend_kron;          // deferred tasks ...
   std::vector<int> pend_kron_round;         // ... and the round of each: how many earlier tasks hit the same destination piece
   std::map<std::array<int64_t, 3>, int> pend_kron_hits;
@@ -217,7 +218,9 @@ struct b2d_ctx {
   DevBuf dm_noise;
   Nccl nccl;
   Cusolver cusolver;
-  DevBuf eig_work, eig_info;
+  DevBuf eig_work, eig_info, eig_pairs;
+  bool eig_cusolver = false;   // diagnostic option: cusolverDnDsyevd for the large sectors instead of the block Jacobi kernel
+  int eig_block_sweeps = 0;    // sweeps of the last block-Jacobi solve
   bool persistent = false;   // option "persistent": 128 x 128 class as a persistent kernel with a cross-tile pipeline (measured: no gain, see profiles/README.md)
   DevBuf tile_counter;
   int eig_jacobi_max = 64;   // sectors up to this size use the hand-written Jacobi kernel, larger ones cusolverDnDsyevd
@@ -558,7 +561,8 @@ void b2d_destroy(b2d_ctx* ctx) {
     DevBuf* bufs[] = {&ctx->staging, &ctx->desc_scratch, &ctx->work, &ctx->parts, &ctx->trace_buf, &ctx->eig_work, &ctx->eig_info, &ctx->dm_noise, &ctx->flat_in, &ctx->flat_out, &ctx->psi_blocks, &ctx->diag_tasks,
                       &ctx->diag_begin, &ctx->partials, &ctx->scalars, &ctx->user_pool, &ctx->dav_pool, &ctx->rho, &ctx->eig_g, &ctx->eig_vt,
                       &ctx->eig_vals, &ctx->eig_sweeps, &ctx->sector_desc, &ctx->rot, &ctx->gather_desc, &ctx->gather_rows,
-                      &ctx->rotated_arena, &ctx->dsched.buf, &ctx->tile_counter, &ctx->diag_gather, &ctx->diag_pool, &ctx->kron_tasks};
+                      &ctx->rotated_arena, &ctx->dsched.buf, &ctx->tile_counter, &ctx->diag_gather, &ctx->diag_pool, &ctx->kron_tasks,
+                      &ctx->guess_image, &ctx->guess_trial, &ctx->eig_pairs};
     for (DevBuf* b : bufs) b->release();
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->pend_pinned) cudaFreeHost(ctx->pend_pinned);
@@ -620,6 +624,7 @@ int b2d_set_option(b2d_ctx* ctx, const char* key, double value) {
   else if (k == "multi_stream") ctx->multi_stream = value != 0;
   else if (k == "slice_iters") ctx->slice_iters = (int)value;
   else if (k == "eig_jacobi_max") ctx->eig_jacobi_max = (int)value;
+  else if (k == "eig_cusolver") ctx->eig_cusolver = value != 0;
   else if (k == "persistent") ctx->persistent = value != 0;
   else if (k == "phase_timing") ctx->phase_timing = value != 0;
   else if (k == "opbuild_batch") ctx->opbuild_batch = value != 0;
@@ -782,9 +787,23 @@ int b2d_plan(b2d_ctx* ctx, const int32_t* psi_dq, double core_energy, int hubbar
         OpRec* used[2] = {&ctx->side[0].ops[t.lop], &ctx->side[1].ops[t.rop]};
         for (OpRec* op : used) {
           if (op->dev || op->dev_size == 0 || op->pending) continue;
+          // room left in a slab that b2d_reset emptied (one context per sweep): reuse it, so that reset-and-plan cycles do not grow
+          // the arena; only what does not fit goes into a new exact-size slab below
+          const size_t bytes = ((size_t)op->dev_size * 8 + 255) / 256 * 256;
+          bool placed = false;
+          for (auto& sl : ctx->slabs)
+            if (sl.cap - sl.used >= bytes) {
+              op->dev = (double*)(sl.p + sl.used);
+              sl.used += bytes;
+              CU(cudaMemsetAsync(op->dev, 0, bytes, ctx->stream));
+              ctx->arena_doubles += op->dev_size;
+              placed = true;
+              break;
+            }
+          if (placed) continue;
           op->pending = true;
           need.push_back(op);
-          need_bytes += ((size_t)op->dev_size * 8 + 255) / 256 * 256;
+          need_bytes += bytes;
         }
       }
       if (need_bytes > 0) {   // one exact-size slab: at benchmark scale the arena is most of the GPU's memory
@@ -1349,11 +1368,81 @@ int b2d_diagonalise_dm(b2d_ctx* ctx, double* evals_out) {
   if (rc) return rc;
   begin_timing(ctx);
   CU(cudaMemcpyAsync(ctx->eig_g.p, ctx->rho.p, (size_t)ctx->rho_padded * 8, cudaMemcpyDeviceToDevice, ctx->stream));
-  if (!large.empty())   // Dsyevd works in place: rho_q -> eigenvectors (the Jacobi kernel initialises its own sectors of eig_vt)
+  if (!large.empty() && ctx->eig_cusolver)   // Dsyevd works in place: rho_q -> eigenvectors (the Jacobi kernels initialise their own sectors of eig_vt)
     CU(cudaMemcpyAsync(ctx->eig_vt.p, ctx->rho.p, (size_t)ctx->rho_padded * 8, cudaMemcpyDeviceToDevice, ctx->stream));
   CU(launch_sector_eig((const BlockDesc*)ctx->sector_desc.p, (int)small.size(), (double*)ctx->eig_g.p, (double*)ctx->eig_vt.p, (double*)ctx->eig_vals.p,
                        (int*)ctx->eig_sweeps.p, ctx->stream, &ctx->launches));
-  if (!large.empty()) {
+  if (!large.empty() && !ctx->eig_cusolver) {
+    // LARGE sectors: block one-sided Jacobi (eig_block_jacobi.cuh).  One launch = one step of the round-robin tournament over the 32-row
+    // blocks of every sector (one CTA per block pair); after each sweep (every block has met every other block of its sector once) the
+    // host reads one flag per sector: a sector in which a whole sweep applied no rotation has converged and its CTAs exit at once.
+    const int nl = (int)large.size();
+    std::vector<BJPair> sect(nl);
+    std::vector<int> nbe(nl);   // blocks per sector, rounded up to even (a dummy block sits out)
+    int steps = 1;
+    for (int k = 0; k < nl; ++k) {
+      const int q = large[k], d = L.dims[q];
+      BJPair s{};
+      s.off = ctx->rho_off[q]; s.d = d; s.ld = pad_ld(d); s.sector = k;
+      sect[k] = s;
+      const int nb = (d + BJ_B - 1) / BJ_B;
+      nbe[k] = nb + (nb & 1);
+      steps = std::max(steps, std::max(nbe[k] - 1, 1));
+    }
+    std::vector<BJPair> pairs;
+    std::vector<int> step_begin(steps + 1, 0);
+    for (int st = 0; st < steps; ++st) {
+      step_begin[st] = (int)pairs.size();
+      for (int k = 0; k < nl; ++k) {
+        const int d = sect[k].d, nb = (d + BJ_B - 1) / BJ_B, n = nbe[k];
+        auto rows = [&](int b) { return std::min(BJ_B, d - b * BJ_B); };
+        if (n <= 2) {                                   // one or two blocks: a single pair, every step
+          BJPair p = sect[k];
+          p.i0 = 0; p.ni = rows(0); p.j0 = BJ_B; p.nj = nb > 1 ? rows(1) : 0;
+          pairs.push_back(p);
+          continue;
+        }
+        const int r = st % (n - 1);                     // a sector with fewer blocks than the largest one simply starts its next sweep
+        for (int t = 0; t < n / 2; ++t) {
+          int a = (r + t) % (n - 1);
+          int b = t == 0 ? n - 1 : (r - t + (n - 1)) % (n - 1);
+          if (a > b) std::swap(a, b);
+          if (a >= nb) continue;
+          BJPair p = sect[k];
+          p.i0 = a * BJ_B; p.ni = rows(a);
+          if (b < nb) { p.j0 = b * BJ_B; p.nj = rows(b); } else { p.j0 = 0; p.nj = 0; }   // partner is the dummy block
+          pairs.push_back(p);
+        }
+      }
+    }
+    step_begin[steps] = (int)pairs.size();
+    rc = upload_desc(ctx, ctx->eig_pairs, pairs.data(), pairs.size() * sizeof(BJPair));
+    if (rc) return rc;
+    rc = upload_desc(ctx, ctx->eig_work, sect.data(), sect.size() * sizeof(BJPair));
+    if (rc) return rc;
+    CU(ctx->eig_info.reserve((size_t)2 * nl * sizeof(int)));
+    int* d_active = (int*)ctx->eig_info.p;
+    int* d_rotated = d_active + nl;
+    std::vector<int> flags(2 * nl, 0);
+    for (int k = 0; k < nl; ++k) flags[k] = 1;
+    CU(cudaMemcpyAsync(d_active, flags.data(), (size_t)2 * nl * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CU(launch_block_jacobi_init((const BJPair*)ctx->eig_work.p, nl, (double*)ctx->eig_vt.p, ctx->stream, &ctx->launches));
+    ctx->eig_block_sweeps = 0;
+    for (int sweep = 0; sweep < 40; ++sweep) {
+      for (int st = 0; st < steps; ++st)
+        CU(launch_block_jacobi_step((const BJPair*)ctx->eig_pairs.p + step_begin[st], step_begin[st + 1] - step_begin[st], (double*)ctx->eig_g.p,
+                                    (double*)ctx->eig_vt.p, d_active, d_rotated, 1e-15, ctx->stream, &ctx->launches));
+      CU(cudaMemcpyAsync(flags.data(), d_rotated, (size_t)nl * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+      ++ctx->eig_block_sweeps;
+      bool any = false;
+      for (int k = 0; k < nl; ++k) any = any || flags[k] != 0;
+      if (!any) break;
+      for (int k = 0; k < nl; ++k) flags[nl + k] = 0;   // active <- rotated, rotated <- 0
+      CU(cudaMemcpyAsync(d_active, flags.data(), (size_t)2 * nl * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    }
+  }
+  if (!large.empty() && ctx->eig_cusolver) {   // diagnostic option "eig_cusolver": the library call round 1 used (never the default)
     std::string err;
     if (!ctx->cusolver.load(err)) return fail(ctx, B2D_ERR_CUDA, err);
     if (ctx->cusolver.SetStream(ctx->cusolver.handle, ctx->stream) != 0) return fail(ctx, B2D_ERR_CUDA, "cusolverDnSetStream failed");
@@ -1382,10 +1471,11 @@ int b2d_diagonalise_dm(b2d_ctx* ctx, double* evals_out) {
     CU(cudaMemcpyAsync(info.data(), ctx->eig_info.p, large.size() * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
     CU(cudaStreamSynchronize(ctx->stream));
     for (int v : info) if (v != 0) return fail(ctx, B2D_ERR_CUDA, "cusolverDnDsyevd did not converge (info " + std::to_string(v) + ")");
-    // Divide-and-conquer leaves the SMALL eigenvalues of rho with absolute errors of ~1e-14 (measured against dsyev_), which is
-    // the size of the reference's clamp (1e-14) and a tenth of its keep threshold (1e-13, rotationmat.C:161,274).  The eigenvectors
-    // are good, so the eigenvalues are recomputed as Rayleigh quotients v_i.(rho v_i): G_q = Vt_q rho_q by the grouped contraction
-    // kernel, then one dot product per row - accurate to the rounding of one FP64 product (~1e-17), like dsyev_'s.
+  }
+  if (!large.empty()) {
+    // Eigenvalues as Rayleigh quotients v_i.(rho v_i) of the final eigenvectors with the ORIGINAL rho: G_q = Vt_q rho_q by the grouped
+    // contraction kernel, then one dot product per row - accurate to the rounding of one FP64 product (~1e-17 absolute), which is what the
+    // reference's clamp (1e-14) and keep threshold (1e-13, rotationmat.C:161,274) need, and free of the drift G accumulates over the sweeps.
     Schedule S;
     Chunk ch;
     std::vector<BlockDesc> lsd;

@@ -5,6 +5,8 @@
 #include <math.h>
 
 #include "gemm_grouped.cuh"
+#define B2D_EIG_KERNELS
+#include "eig_block_jacobi.cuh"
 
 namespace b2d {
 
@@ -46,6 +48,7 @@ cudaError_t gemm_init() {   // opt in to > 48 KB dynamic shared memory
   B2D_INIT(64, 128) B2D_INIT(64, 64) B2D_INIT(64, 32)
   B2D_INIT(32, 128) B2D_INIT(32, 64) B2D_INIT(32, 32)
 #undef B2D_INIT
+  if ((e = block_jacobi_setup()) != cudaSuccess) return e;
   return init_persistent();
 }
 
@@ -677,6 +680,23 @@ __global__ void __launch_bounds__(EIG_THREADS) rayleigh_kernel(const BlockDesc* 
 cudaError_t launch_rayleigh(const BlockDesc* sectors, int nsectors, const double* g, const double* vt, double* evals, cudaStream_t s, int64_t* launches) {
   if (nsectors == 0) return cudaSuccess;
   rayleigh_kernel<<<nsectors, EIG_THREADS, 0, s>>>(sectors, g, vt, evals);
+  B2D_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+
+cudaError_t block_jacobi_setup() {
+  return cudaFuncSetAttribute(block_jacobi_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BJ_SMEM);
+}
+cudaError_t launch_block_jacobi_init(const BJPair* sectors, int nsectors, double* vt, cudaStream_t s, int64_t* launches) {
+  if (nsectors == 0) return cudaSuccess;
+  block_jacobi_init_kernel<<<dim3(64, nsectors), 256, 0, s>>>(sectors, vt);
+  B2D_LAUNCH_CHECK();
+  return cudaSuccess;
+}
+cudaError_t launch_block_jacobi_step(const BJPair* pairs, int npairs, double* g, double* vt, const int* active, int* rotated, double tol, cudaStream_t s,
+                                     int64_t* launches) {
+  if (npairs == 0) return cudaSuccess;
+  block_jacobi_step_kernel<<<npairs, BJ_THREADS, BJ_SMEM, s>>>(pairs, g, vt, active, rotated, tol);
   B2D_LAUNCH_CHECK();
   return cudaSuccess;
 }

@@ -88,6 +88,13 @@ cudaError_t launch_diag(const BlockDesc* blocks, int nblocks, const DiagTask* ta
 // sectors[q] = {rows=cols=d_q, ld, dev_off = offset of G_q / Vt_q in g / vt, ref_off = offset of the eigenvalues}
 // On exit: rows of vt are the eigenvectors, evals[ref_off + i] the eigenvalue of row i (unsorted), sweeps[q] the sweep count.
 cudaError_t launch_sector_eig(const BlockDesc* sectors, int nsectors, double* g, double* vt, double* evals, int* sweeps, cudaStream_t s, int64_t* launches);
+// LARGE sectors: block one-sided Jacobi (eig_block_jacobi.cuh).  init: V = identity for the listed sectors; step: one launch = one step of
+// the round-robin tournament over 32-row blocks, one CTA per block pair, all sectors together.
+struct BJPair;
+cudaError_t block_jacobi_setup();
+cudaError_t launch_block_jacobi_init(const BJPair* sectors, int nsectors, double* vt, cudaStream_t s, int64_t* launches);
+cudaError_t launch_block_jacobi_step(const BJPair* pairs, int npairs, double* g, double* vt, const int* active, int* rotated, double tol, cudaStream_t s,
+                                     int64_t* launches);
 // evals[ref_off + i] = vt_i . g_i (Rayleigh quotients of the rows of vt, g = vt * rho): eigenvalues of library eigenvectors to the
 // absolute accuracy of one FP64 matrix product
 cudaError_t launch_rayleigh(const BlockDesc* sectors, int nsectors, const double* g, const double* vt, double* evals, cudaStream_t s, int64_t* launches);

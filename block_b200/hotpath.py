@@ -291,6 +291,12 @@ class SpinBlock:
             out.append(flat[off:off + d * d].reshape(d, d)); off += d * d
         return out
 
+    def set_density(self, blocks):
+        """Upload a density matrix (one d_q x d_q block per left sector): what a binding does when the caller hands diagonalise_dm a matrix."""
+        flat = np.concatenate([np.ascontiguousarray(b, dtype=np.float64).ravel() for b in blocks])
+        assert flat.size == int(self.lib.b2d_density_size(self._ctx))
+        self._ck(self.lib.b2d_density_upload(self._ctx, _p(flat, _lib.c_f64p)))
+
     def diagonalise_dm(self):
         """diagonalise_dm (rotationmat.C:258): per-sector eigenvalues (ascending, < 1e-14 -> 0)."""
         ev = np.empty(int(np.sum(self.left.dims)))

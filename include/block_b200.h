@@ -176,7 +176,11 @@ int b2d_diagonal(b2d_ctx* ctx, int dst_slot);
  * The Krylov vectors, sigma vectors, subspace matrix, its eigen-decomposition and the Olsen preconditioner all
  * stay on the device; the host only reads one convergence scalar per iteration.  The reference has no iteration cap
  * (linear.C:214 `maxiter` is unused); the option "max_davidson_iter" (default 2000) stops a runaway solve: the current
- * Ritz pairs are returned together with B2D_ERR_NOCONV. */
+ * Ritz pairs are returned together with B2D_ERR_NOCONV.
+ * Limits (B2D_ERR_ARG otherwise): 1 <= nroots <= deflation_min < deflation_max <= 30 - the subspace matrix, its eigenvectors and the
+ * fused multi-vector kernels are sized for 32 vectors.  The reference accepts any deflation_min_size / deflation_max_size from its input
+ * file (input.C); a binding keeps such runs working by leaving block_davidson to the reference and routing only its H applications here
+ * (b2d_multiplyH_host) - tests/dropin/block_gpu_hooks.cpp does exactly that. */
 int b2d_davidson(b2d_ctx* ctx, int nroots, int guess_slot0, int diag_slot, double normtol, int deflation_min,
                  int deflation_max, double* evals, int* n_multiply, double* residual);
 /* The same solve with `lowerStates` (state-specific form, currentRoot >= 0; linear.C:201-208, 311-317, 369-375): the first guess,

@@ -30,9 +30,8 @@
 //   B2D_DROPIN_WORKSPACE_MB   T workspace of the two-step contraction
 //   B2D_DROPIN_OPBUILD    "device" (default): a child of the big block that is an enlarged block is built on the GPU from ITS children
 //                         (SURVEY N2);  "host": the reference's Op::build constructs it on the CPU and it is uploaded
-//   B2D_DROPIN_GUESS      "device": the TRANSFORM guess of a two-dot block iteration (GuessWave::transform_previous_wavefunction,
-//                         SURVEY N1) is computed on the GPU (b2d_guess_plan + b2d_guess_transform);  default "host": the reference's own
-//                         (opt-in until the device path has been run on a B200)
+//   B2D_DROPIN_GUESS      "device" (default): TRANSFORM / TRANSPOSE guesses (GuessWave::transform_previous_wavefunction and its one-dot /
+//                         transpose forms) are computed on the GPU (b2d_guess_plan + b2d_guess_transform);  "host": the reference's own
 //   B2D_DROPIN_EIG        "host": diagnostic - the density-matrix eigen-decomposition and state selection stay with the reference
 //                         (dsyev_), everything else on the GPU: separates eigenvector non-uniqueness from arithmetic differences
 //   B2D_DROPIN_OPTIONS    "key=value,..." library options (b2d_set_option), e.g. eig_jacobi_max=512
@@ -421,7 +420,7 @@ void wrap_guess(vector<Wavefunction>& solution, DiagonalMatrix& e, const SpinBlo
 void wrap_guess(vector<Wavefunction>& solution, DiagonalMatrix& e, const SpinBlock& big, const guessWaveTypes& gw, const bool& onedot,
                 const bool& transpose_guess_wave, double additional_noise, int currentState) {
   const char* mode = getenv("B2D_DROPIN_GUESS");
-  if (!(mode && string(mode) == "device" && g.ctx) || gw == BASIC) { real_guess(solution, e, big, gw, onedot, transpose_guess_wave, additional_noise, currentState); return; }
+  if ((mode && string(mode) == "host") || !g.ctx || gw == BASIC) { real_guess(solution, e, big, gw, onedot, transpose_guess_wave, additional_noise, currentState); return; }
   double t0 = now_s();
   // every root must be one of the covered forms, otherwise the whole call goes to the reference (it owns the loop over roots)
   vector<b2d_binding::GuessBinding> B(solution.size());
@@ -483,7 +482,10 @@ void wrap_davidson(vector<Wavefunction>& b, DiagonalMatrix& h_diag, double normt
 void wrap_davidson(vector<Wavefunction>& b, DiagonalMatrix& h_diag, double normtol, const bool& warmUp, Davidson_functor& h_multiply, bool& useprecond,
                    int currentRoot, vector<Wavefunction>& lowerStates) {
   const char* mode = getenv("B2D_DROPIN_DAVIDSON");
-  if (mode && string(mode) == "host") {   // the reference's Davidson; every H application crosses the boundary with host buffers
+  // outside the device solver's limits (b2d_davidson: nroots <= deflation_min < deflation_max <= 30) the reference's own block_davidson
+  // runs with every H application on the GPU - a valid Block input never aborts because of the subspace size
+  const bool beyond_limits = dmrginp.deflation_max_size() > 30 || (int)b.size() > dmrginp.deflation_min_size() || dmrginp.deflation_max_size() <= dmrginp.deflation_min_size();
+  if ((mode && string(mode) == "host") || beyond_limits) {   // the reference's Davidson; every H application crosses the boundary with host buffers
     double t0 = now_s();
     real_davidson(b, h_diag, normtol, warmUp, h_multiply, useprecond, currentRoot, lowerStates);
     g.t_dav += now_s() - t0;

@@ -6,7 +6,7 @@
   * batched construction of the enlarged-block operators (option opbuild_batch, N2): bit-identical to the one-launch-per-product path;
   * drop-in sweeps with both switched on, in check mode; the reference's own known-answer test (dmrg_tests/h2o_nosym) through the drop-in.
 (File name: sorts after every other test module; planners, oracles and the reference-side binding are pinned on CPU by
-tests/test_guess_planner_cpu.py, test_guess_oracle.py and test_guess_binding_cpu.py; the first run on a B200 is the round-end one.)"""
+tests/test_guess_planner_cpu.py, test_guess_oracle.py and test_guess_binding_cpu.py; first green run on a B200: round 1's round-end suite.)"""
 import glob
 import os
 
@@ -18,11 +18,8 @@ from oracle import guess_oracle as G
 from test_guess_planner_cpu import make, make_onedot, make_onedot_transpose, make_transpose
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-# Everything in this module exercises device code that was finished AFTER this round's GPU budget was spent (planners and oracles are
-# pinned on CPU; the kernels themselves are the ones the rest of the suite verifies).  Until it has passed once on a B200 an unexpected
-# failure here must not mask the verified suite: non-strict xfail - reported as XPASS when it works, XFAIL when it does not.
-# TODO(round 2): remove this marker after the first green device run.
-pytestmark = pytest.mark.xfail(strict=False, reason="device path finished after the round's GPU budget was spent: first run on a B200 pending")
+# (Round 1 carried a non-strict xfail marker here until the first device run; all 24 tests passed on the driver's B200 at the end of
+# round 1 - GPUTEST_r01.json - so the module is a regular, strict part of the suite now.)
 FIXTURES = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "guess_*.npz")))
 
 

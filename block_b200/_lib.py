@@ -44,6 +44,7 @@ PROTOTYPES = {
     "b2d_add_op": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_int, c_i32p, C.c_int, c_i32p, C.c_int, c_u8p, c_f64p, C.POINTER(C.c_int)]),
     "b2d_add_op_blocks": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_int, c_i32p, C.c_int, c_i32p, C.c_int, c_u8p, C.POINTER(c_f64p), C.POINTER(C.c_int)]),
     "b2d_fill_op_random": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_uint64, C.c_double, C.c_int]),
+    "b2d_alloc_ops": (C.c_int, [ctx_p, C.c_int]),
     "b2d_download_op": (C.c_int, [ctx_p, C.c_int, C.c_int, c_f64p]),
     "b2d_op_size": (C.c_int64, [ctx_p, C.c_int, C.c_int]),
     "b2d_plan": (C.c_int, [ctx_p, c_i32p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int]),
@@ -106,6 +107,14 @@ PROTOTYPES = {
     "b2d_guess_plan": (C.c_int, [ctx_p, C.POINTER(GuessDescC), c_f64p, C.c_int]),
     "b2d_guess_plan_export": (C.c_int64, [ctx_p, C.c_int, C.c_void_p, C.c_int64]),
     "b2d_guess_transform": (C.c_int, [ctx_p, c_f64p, c_f64p, c_f64p, C.c_int, c_f64p]),
+    "b2d_cache_put_rotated": (C.c_int, [ctx_p, C.POINTER(C.c_uint64)]),
+    "b2d_cache_use": (C.c_int, [ctx_p, C.c_uint64, C.c_int, C.c_int]),
+    "b2d_cache_block_info": (C.c_int, [ctx_p, C.c_uint64, c_i32p, c_i32p, c_i32p]),
+    "b2d_cache_block_sectors": (C.c_int, [ctx_p, C.c_uint64, c_i32p, c_i32p, c_i32p]),
+    "b2d_cache_op_info": (C.c_int, [ctx_p, C.c_uint64, C.c_int, c_i32p, c_i32p, c_i32p, c_i32p, c_i64p]),
+    "b2d_cache_download_op": (C.c_int, [ctx_p, C.c_uint64, C.c_int, c_u8p, c_f64p]),
+    "b2d_cache_drop": (C.c_int, [ctx_p, C.c_uint64]),
+    "b2d_cache_stats": (C.c_int, [ctx_p, c_f64p, C.c_int]),
     "b2d_nccl_unique_id": (C.c_int, [c_u8p]),
     "b2d_comm_init": (C.c_int, [ctx_p, c_u8p, C.c_int, C.c_int]),
     "b2d_allreduce_slot": (C.c_int, [ctx_p, C.c_int]),

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -158,7 +159,7 @@ struct b2d_ctx {
   DevBuf parts;            // split-K partial copies of the destination wavefunction (run_sigma_schedule)
   int slice_iters = 256;   // pipeline iterations per split-K slice (0: no split)
   DevBuf psi_blocks;       // BlockDesc per psi block
-  DevBuf diag_tasks, diag_begin, diag_gather, diag_pool;
+  DevBuf diag_tasks, diag_begin, diag_gather, diag_pool, diag_regions;
   DevBuf partials, scalars;   // level-1 partial sums; G / theta / alpha / misc scalars
   double* h_pinned = nullptr; // 64 doubles
 
@@ -195,12 +196,21 @@ struct b2d_ctx {
 
   // enlarged-block operator construction: product StateInfo of side[0] (x) side[1] and the operators built on it
   struct Product {
+    double* identity = nullptr;             // factorised mode: identity block (max child sector size) in the arena, the `A` of TensorTrace factors
+    int identity_ld = 0;
+    std::vector<std::vector<std::pair<size_t, SubBlock>>> pend_subs;   // factorised mode: per operator, (stored block index, factor) in product order
+    struct Combo { std::vector<std::pair<const double*, bool>> parts; std::vector<double> ratios; const double* block; };
+    std::map<std::array<int64_t, 3>, std::vector<Combo>> combos;       // (first part address, m, n) -> pre-summed blocks, for sharing
     Side side;                              // collected sectors of the enlarged block + the operators built so far
     std::vector<int> lmap, rmap, unc_dims;  // leftUnMapQuanta / rightUnMapQuanta / unCollectedStateInfo->quantaStates
     std::vector<std::vector<int>> old_to_new;
     bool set = false;
   } product;
   DevBuf kron_tasks;
+  bool factorised = false;                  // option "factorised": operators of an enlarged block (renormalised block x one-site dot) are kept as lists of
+                                            // scaled sub-blocks of the renormalised operators instead of being materialised (16x less memory, no structural zeros)
+  int64_t combo_doubles = 0;                // pre-summed factor blocks allocated since the last reset
+  int64_t nsubs_direct = 0, nsubs_combo = 0;
   bool opbuild_batch = true;                // b2d_build_enlarged_op defers its scatter tasks: one launch per ROUND for a whole child block
   std::vector<KronTask> pend_kron;          // deferred tasks ...
   std::vector<int> pend_kron_round;         // ... and the round of each: how many earlier tasks hit the same destination piece
@@ -212,13 +222,26 @@ struct b2d_ctx {
   bool stash_set[2] = {false, false};
   Integrals integrals;                      // one- / two-electron integrals for the complementary operators (b2d_set_integrals)
   GuessPlan guess;                          // guess-wavefunction transform of the next block iteration (b2d_guess_plan)
-  DevBuf guess_image, guess_trial;
+  DevBuf guess_image, guess_trial, materialised;
 
+  // Device-side shadow of the reference's scratch files (SpinBlock::store / restore, save_load_block.C:23-108): renormalised
+  // blocks stay resident between block iterations, keyed by a token the binding hides in the host copy.  An entry owns one buffer: device
+  // memory while the cache is under its budget, pinned host memory beyond (copied back into the arena when the block is used).
+  struct CachedBlock {
+    Side side;                 // sectors + operators; op.dev holds the OFFSET (in doubles) from the buffer base while cached
+    DevBuf dev;                // device copy (cap == 0: spilled)
+    double* pinned = nullptr;  // pinned host copy of a spilled entry
+    int64_t doubles = 0;
+  };
+  std::map<uint64_t, CachedBlock> cache;
+  uint64_t cache_next_token = 1;
+  double cache_device_mb = 32768.0;   // option "cache_device_mb": device memory the cache may hold before it spills to pinned host memory
+  int64_t cache_device_doubles = 0, cache_hits = 0, cache_puts = 0;
   std::map<std::vector<int>, PsiLayout> layouts;   // wavefunction layouts for other target quanta (noise: O.psi sectors)
   DevBuf dm_noise;
   Nccl nccl;
   Cusolver cusolver;
-  DevBuf eig_work, eig_info, eig_pairs;
+  DevBuf eig_work, eig_info, eig_pairs, eig_tmp;
   bool eig_cusolver = false;   // diagnostic option: cusolverDnDsyevd for the large sectors instead of the block Jacobi kernel
   int eig_block_sweeps = 0;    // sweeps of the last block-Jacobi solve
   bool persistent = false;   // option "persistent": 128 x 128 class as a persistent kernel with a cross-tile pipeline (measured: no gain, see profiles/README.md)
@@ -261,6 +284,16 @@ cudaError_t arena_alloc(b2d_ctx* ctx, size_t bytes, double** out) {
   }
   ctx->slabs.push_back({p, cap, bytes});
   *out = (double*)p;
+  return cudaSuccess;
+}
+
+// arena allocation that also works on a planning-only context (CPU tests of the factorised planner): addresses from a private
+// counter that nothing dereferences
+cudaError_t arena_alloc_any(b2d_ctx* ctx, size_t bytes, double** out) {
+  if (ctx->has_device) return arena_alloc(ctx, bytes, out);
+  static uintptr_t fake = (uintptr_t)1 << 44;
+  *out = (double*)fake;
+  fake += (bytes + 255) / 256 * 256;
   return cudaSuccess;
 }
 
@@ -425,6 +458,7 @@ int run_schedule(b2d_ctx* ctx, const Schedule& S, const DevSchedule& D, double* 
     };
     for (size_t i = 0; i < D.chunks.size(); ++i) {
       cur_chunk = (int)i; cur_step = 0;
+      if (S.chunks[i].zero_work) CU(cudaMemsetAsync(ctx->work.p, 0, (size_t)S.chunks[i].work * 8, ctx->stream));
       int rc = run_batch(D.chunks[i].s1);
       if (rc) return rc;
       cur_step = 1;
@@ -459,6 +493,7 @@ int run_schedule(b2d_ctx* ctx, const Schedule& S, const DevSchedule& D, double* 
   };
   for (size_t i = 0; i < D.chunks.size(); ++i)
     for (int step = 0; step < 2; ++step) {
+      if (step == 0 && S.chunks[i].zero_work) CU(cudaMemsetAsync(ctx->work.p, 0, (size_t)S.chunks[i].work * 8, ctx->stream));
       const DevBatch& b = step == 0 ? D.chunks[i].s1 : D.chunks[i].s2;
       for (int c = 0; c < B2D_NUM_TILE_CLASSES; ++c) {
         if (b.ntiles[c] <= 0) continue;
@@ -518,7 +553,7 @@ void end_timing(b2d_ctx* ctx) { cudaEventRecord(ctx->ev[1], ctx->stream); }
 
 extern "C" {
 
-int b2d_abi_version(void) { return 3; }   // 3: b2d_build_enlarged_op takes the spin component; stash / assemble, guess transform
+int b2d_abi_version(void) { return 4; }   // 4: factorised operators, b2d_alloc_ops, block cache (b2d_cache_*); 3: stash / assemble, guess transform
 
 int b2d_create(int device, b2d_ctx** out) {
   if (!out) return B2D_ERR_ARG;
@@ -562,8 +597,9 @@ void b2d_destroy(b2d_ctx* ctx) {
                       &ctx->diag_begin, &ctx->partials, &ctx->scalars, &ctx->user_pool, &ctx->dav_pool, &ctx->rho, &ctx->eig_g, &ctx->eig_vt,
                       &ctx->eig_vals, &ctx->eig_sweeps, &ctx->sector_desc, &ctx->rot, &ctx->gather_desc, &ctx->gather_rows,
                       &ctx->rotated_arena, &ctx->dsched.buf, &ctx->tile_counter, &ctx->diag_gather, &ctx->diag_pool, &ctx->kron_tasks,
-                      &ctx->guess_image, &ctx->guess_trial, &ctx->eig_pairs};
+                      &ctx->guess_image, &ctx->guess_trial, &ctx->eig_pairs, &ctx->diag_regions, &ctx->materialised, &ctx->eig_tmp};
     for (DevBuf* b : bufs) b->release();
+    for (auto& kv : ctx->cache) { kv.second.dev.release(); if (kv.second.pinned) cudaFreeHost(kv.second.pinned); }
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->pend_pinned) cudaFreeHost(ctx->pend_pinned);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -607,6 +643,7 @@ int b2d_reset(b2d_ctx* ctx) {
   ctx->stash[0] = Side(); ctx->stash[1] = Side(); ctx->stash_set[0] = ctx->stash_set[1] = false;
   ctx->guess = GuessPlan();
   ctx->pend_kron.clear(); ctx->pend_kron_round.clear(); ctx->pend_kron_hits.clear();
+  ctx->combo_doubles = 0; ctx->nsubs_direct = ctx->nsubs_combo = 0;
   ctx->timing_valid = false;   // (the integrals belong to the whole calculation: b2d_reset keeps them)
   ctx->err.clear();
   return B2D_OK;
@@ -628,6 +665,8 @@ int b2d_set_option(b2d_ctx* ctx, const char* key, double value) {
   else if (k == "persistent") ctx->persistent = value != 0;
   else if (k == "phase_timing") ctx->phase_timing = value != 0;
   else if (k == "opbuild_batch") ctx->opbuild_batch = value != 0;
+  else if (k == "factorised") ctx->factorised = value != 0;
+  else if (k == "cache_device_mb") ctx->cache_device_mb = value;
   else return fail(ctx, B2D_ERR_ARG, "unknown option " + k);
   return B2D_OK;
 }
@@ -672,6 +711,16 @@ static int add_op_impl(b2d_ctx* ctx, int side, int optype, int norb, const int32
   op.fermion = fermion != 0;
   op.allowed.assign(allowed, allowed + (size_t)s.nq * s.nq);
   layout_op(s, op);
+  if ((data || blocks) && op.packed_size > 0 && op.packed_size <= 256) {   // the one-site dot: its 1 x 1 elements become alphas of factorised operators
+    op.host.resize((size_t)op.packed_size);
+    if (data) memcpy(op.host.data(), data, (size_t)op.packed_size * 8);
+    else {
+      int64_t off = 0, k = 0;
+      for (int i = 0; i < s.nq; ++i)
+        for (int j = 0; j < s.nq; ++j)
+          if (op.allowed[(size_t)i * s.nq + j]) { const int64_t n = (int64_t)s.dims[i] * s.dims[j]; memcpy(op.host.data() + off, blocks[k++], (size_t)n * 8); off += n; }
+    }
+  }
   // data == NULL: the blocks are materialised (zero-filled) by b2d_plan, and only if one of this rank's terms uses
   // the operator - under a term partition a rank never holds the other ranks' operators
   if (ctx->has_device && (data || blocks)) {
@@ -710,11 +759,28 @@ static int add_op_impl(b2d_ctx* ctx, int side, int optype, int norb, const int32
   return B2D_OK;
 }
 
+// Allocate (zero-filled) every operator of a side that was added without data: children of a product block never see b2d_plan, which
+// is where data-less operators are otherwise materialised (synthetic benchmark: b2d_fill_op_random fills them afterwards).
+int b2d_alloc_ops(b2d_ctx* ctx, int side) {
+  NEED_DEVICE();
+  if (side < 0 || side > 1) return fail(ctx, B2D_ERR_ARG, "b2d_alloc_ops: bad side");
+  CU(cudaSetDevice(ctx->device));
+  for (OpRec& op : ctx->side[side].ops) {
+    if (op.dev || op.dev_size == 0 || op.factorised) continue;
+    CU(arena_alloc(ctx, (size_t)op.dev_size * 8, &op.dev));
+    ctx->arena_doubles += op.dev_size;
+    CU(cudaMemsetAsync(op.dev, 0, (size_t)op.dev_size * 8, ctx->stream));
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  return B2D_OK;
+}
+
 int64_t b2d_op_size(const b2d_ctx* ctx, int side, int op_id) {
   if (!ctx || side < 0 || side > 1 || op_id < 0 || op_id >= (int)ctx->side[side].ops.size()) return -1;
   return ctx->side[side].ops[op_id].packed_size;
 }
 
+static int materialise_factorised(b2d_ctx* ctx, const Side& S, const OpRec& op, DevBuf& buf);
 int b2d_download_op(b2d_ctx* ctx, int side, int op_id, double* data) {
   NEED_DEVICE();
   { int frc = flush_pending_ops(ctx); if (frc) return frc; }
@@ -722,12 +788,18 @@ int b2d_download_op(b2d_ctx* ctx, int side, int op_id, double* data) {
   const Side& s = ctx->side[side];
   const OpRec& op = s.ops[op_id];
   if (op.packed_size == 0) return B2D_OK;
-  if (!op.dev) return fail(ctx, B2D_ERR_ARG, "b2d_download_op: operator is not resident on this rank (no term of this rank uses it)");
+  const double* dev = op.dev;
+  if (op.factorised) {
+    int mrc = materialise_factorised(ctx, s, op, ctx->materialised);
+    if (mrc) return mrc;
+    dev = (const double*)ctx->materialised.p;
+  }
+  if (!dev) return fail(ctx, B2D_ERR_ARG, "b2d_download_op: operator is not resident on this rank (no term of this rank uses it)");
   std::vector<BlockDesc> bd = op_blocks(s, op);
   CU(ctx->staging.reserve((size_t)op.packed_size * 8));
   int rc = upload_desc(ctx, ctx->desc_scratch, bd.data(), bd.size() * sizeof(BlockDesc));
   if (rc) return rc;
-  CU(launch_unpack((const BlockDesc*)ctx->desc_scratch.p, (int)bd.size(), op.dev, (double*)ctx->staging.p, ctx->stream, &ctx->launches));
+  CU(launch_unpack((const BlockDesc*)ctx->desc_scratch.p, (int)bd.size(), dev, (double*)ctx->staging.p, ctx->stream, &ctx->launches));
   CU(cudaMemcpyAsync(data, ctx->staging.p, (size_t)op.packed_size * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
   return B2D_OK;
@@ -739,6 +811,7 @@ int b2d_fill_op_random(b2d_ctx* ctx, int side, int op_id, uint64_t seed, double 
   if (side < 0 || side > 1 || op_id < 0 || op_id >= (int)ctx->side[side].ops.size()) return fail(ctx, B2D_ERR_ARG, "b2d_fill_op_random: bad arguments");
   const Side& s = ctx->side[side];
   const OpRec& op = s.ops[op_id];
+  if (op.factorised) return fail(ctx, B2D_ERR_ARG, "b2d_fill_op_random: a factorised operator has no storage of its own");
   if (op.packed_size == 0 || !op.dev) return B2D_OK;   // not resident on this rank: nothing to fill
   std::vector<BlockDesc> bd = op_blocks(s, op);
   int rc = upload_desc(ctx, ctx->desc_scratch, bd.data(), bd.size() * sizeof(BlockDesc));
@@ -786,7 +859,7 @@ int b2d_plan(b2d_ctx* ctx, const int32_t* psi_dq, double core_energy, int hubbar
       for (const Term& t : ctx->terms_mine) {
         OpRec* used[2] = {&ctx->side[0].ops[t.lop], &ctx->side[1].ops[t.rop]};
         for (OpRec* op : used) {
-          if (op->dev || op->dev_size == 0 || op->pending) continue;
+          if (op->dev || op->dev_size == 0 || op->pending || op->factorised) continue;
           // room left in a slab that b2d_reset emptied (one context per sweep): reuse it, so that reset-and-plan cycles do not grow
           // the arena; only what does not fit goes into a new exact-size slab below
           const size_t bytes = ((size_t)op->dev_size * 8 + 255) / 256 * 256;
@@ -894,9 +967,10 @@ int b2d_plan_stats(const b2d_ctx* ctx, double* out, int n) {
       useful += c.step1.class_flops[k] + c.step2.class_flops[k];
       issued += c.step1.class_padded[k] + c.step2.class_padded[k];
     }
-  double v[10] = {(double)ctx->sched.chunks.size(), (double)ctx->sched.n_step1, (double)ctx->sched.n_step2, (double)ctx->sched.n_tiles,
-                  (double)ctx->sched.work_max, (double)ctx->arena_doubles, (double)launches, ctx->sched.flops_exec, useful, issued};
-  for (int i = 0; i < n && i < 10; ++i) out[i] = v[i];
+  double v[13] = {(double)ctx->sched.chunks.size(), (double)ctx->sched.n_step1, (double)ctx->sched.n_step2, (double)ctx->sched.n_tiles,
+                  (double)ctx->sched.work_max, (double)ctx->arena_doubles, (double)launches, ctx->sched.flops_exec, useful, issued,
+                  (double)ctx->combo_doubles, (double)ctx->nsubs_direct, (double)ctx->nsubs_combo};
+  for (int i = 0; i < n && i < 13; ++i) out[i] = v[i];
   return B2D_OK;
 }
 
@@ -1048,8 +1122,9 @@ int b2d_diagonal(b2d_ctx* ctx, int dst_slot) {
   CU(cudaSetDevice(ctx->device));
   std::vector<DiagTask> tasks;
   std::vector<int> begin;
+  std::vector<BlockDesc> regions;   // the psi blocks, or their (row piece, column piece) sub-blocks when a child is a product of factorised operators
   try {
-    build_diag_tasks(ctx->side[0], ctx->side[1], ctx->psi, ctx->terms_mine, ctx->core_energy, ctx->hubbard, ctx->am, tasks, begin);
+    build_diag_tasks(ctx->side[0], ctx->side[1], ctx->psi, ctx->terms_mine, ctx->core_energy, ctx->hubbard, ctx->am, tasks, begin, regions);
   } catch (const std::exception& e) { return fail(ctx, B2D_ERR_ARG, e.what()); }
   // every (operator, sector) diagonal is read by ~d_other x #tasks threads with stride ld + 1: gather each distinct one ONCE into
   // a compact pool and point the tasks at it (stride 1: coalesced along j, broadcast along i)
@@ -1057,7 +1132,6 @@ int b2d_diagonal(b2d_ctx* ctx, int dst_slot) {
   {
     std::map<std::pair<int64_t, int>, int64_t> seen;   // (address, stride) -> pool offset
     int64_t pool = 0;
-    const PsiLayout& P = ctx->psi;
     auto remap = [&](int64_t& addr, int32_t& stride, int n) {
       if (!addr) return;
       auto key = std::make_pair(addr, (int)stride);
@@ -1070,14 +1144,14 @@ int b2d_diagonal(b2d_ctx* ctx, int dst_slot) {
       addr = it->second;   // pool offset for now; turned into an address below
       stride = 1;
     };
-    for (int p = 0; p < P.nblocks(); ++p)
+    for (size_t p = 0; p < regions.size(); ++p)
       for (int t = begin[p]; t < begin[p + 1]; ++t) {
-        remap(tasks[t].a, tasks[t].sa, P.rows[p]);
-        remap(tasks[t].b, tasks[t].sb, P.cols[p]);
+        remap(tasks[t].a, tasks[t].sa, regions[p].rows);
+        remap(tasks[t].b, tasks[t].sb, regions[p].cols);
       }
     CU(ctx->diag_pool.reserve((size_t)std::max<int64_t>(pool, 2) * 8));
     const int64_t base = (int64_t)(intptr_t)ctx->diag_pool.p;
-    for (int p = 0; p < P.nblocks(); ++p)
+    for (size_t p = 0; p < regions.size(); ++p)
       for (int t = begin[p]; t < begin[p + 1]; ++t) {
         if (tasks[t].sa == 1) tasks[t].a = base + 8 * tasks[t].a;
         if (tasks[t].sb == 1) tasks[t].b = base + 8 * tasks[t].b;
@@ -1089,10 +1163,12 @@ int b2d_diagonal(b2d_ctx* ctx, int dst_slot) {
   if (rc) return rc;
   rc = upload_desc(ctx, ctx->diag_begin, begin.data(), begin.size() * sizeof(int));
   if (rc) return rc;
+  rc = upload_desc(ctx, ctx->diag_regions, regions.data(), regions.size() * sizeof(BlockDesc));
+  if (rc) return rc;
   begin_timing(ctx);
   CU(cudaMemsetAsync(user_vec(ctx, dst_slot), 0, (size_t)ctx->psi.Wp * 8, ctx->stream));
   CU(launch_gather_diag((const DiagGather*)ctx->diag_gather.p, (int)gather.size(), (double*)ctx->diag_pool.p, ctx->stream, &ctx->launches));
-  CU(launch_diag((const BlockDesc*)ctx->psi_blocks.p, ctx->psi.nblocks(), (const DiagTask*)ctx->diag_tasks.p, (const int*)ctx->diag_begin.p,
+  CU(launch_diag((const BlockDesc*)ctx->diag_regions.p, (int)regions.size(), (const DiagTask*)ctx->diag_tasks.p, (const int*)ctx->diag_begin.p,
                  user_vec(ctx, dst_slot), ctx->stream, &ctx->launches));
   rc = allreduce(ctx, user_vec(ctx, dst_slot), ctx->psi.Wp);   // every rank added the terms it owns
   if (rc) return rc;
@@ -1442,6 +1518,58 @@ int b2d_diagonalise_dm(b2d_ctx* ctx, double* evals_out) {
       CU(cudaMemcpyAsync(d_active, flags.data(), (size_t)2 * nl * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     }
   }
+  if (!large.empty() && !ctx->eig_cusolver) {
+    // The accumulated rotations leave V orthonormal to ~(rotations per row) x eps ~ 1e-12 for sectors of several hundred states; the
+    // reference's dsyev_ eigenvectors are orthonormal to ~d x eps.  One Newton-Schulz step  V <- (3/2 I - 1/2 V V^T) V  squares the defect
+    // (1e-12 -> rounding level) with two dense products per sector in the grouped contraction kernel; rows stay eigenvectors to O(defect).
+    CU(ctx->eig_tmp.reserve((size_t)ctx->rho_padded * 8));
+    CU(cudaMemcpyAsync(ctx->eig_tmp.p, ctx->eig_vt.p, (size_t)ctx->rho_padded * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    CU(launch_scale((double*)ctx->eig_tmp.p, 1.5, ctx->rho_padded, ctx->stream, &ctx->launches));
+    Schedule S;
+    Chunk ch;
+    for (int q : large) {
+      const int d = L.dims[q];
+      GSeg sg;
+      memset(&sg, 0, sizeof(sg));
+      sg.a = sg.b = ctx->rho_off[q]; sg.a_base = sg.b_base = B2D_BASE_SRC;
+      sg.a_trans = 0; sg.b_kmajor = 1;                      // S = V V^T
+      sg.lda = sg.ldb = pad_ld(d); sg.k = d; sg.alpha = 1.0;
+      GGroup G;
+      memset(&G, 0, sizeof(G));
+      G.c = ctx->rho_off[q]; G.c_base = B2D_BASE_AUX; G.ldc = pad_ld(d); G.m = G.n = d; G.accumulate = 0;
+      G.seg_begin = (int)ch.step1.segs.size();
+      ch.step1.segs.push_back(sg);
+      G.seg_end = (int)ch.step1.segs.size();
+      ch.step1.groups.push_back(G);
+      memset(&sg, 0, sizeof(sg));
+      sg.a = ctx->rho_off[q]; sg.a_base = B2D_BASE_AUX; sg.a_trans = 0;   // S (symmetric)
+      sg.b = ctx->rho_off[q]; sg.b_base = B2D_BASE_SRC; sg.b_kmajor = 0;   // V
+      sg.lda = sg.ldb = pad_ld(d); sg.k = d; sg.alpha = -0.5;
+      G.c_base = B2D_BASE_DST; G.accumulate = 1;            // 3/2 V - 1/2 S V
+      G.seg_begin = (int)ch.step2.segs.size();
+      ch.step2.segs.push_back(sg);
+      G.seg_end = (int)ch.step2.segs.size();
+      ch.step2.groups.push_back(G);
+    }
+    make_tiles(ch.step1, ctx->forced_class);
+    make_tiles(ch.step2, ctx->forced_class);
+    ch.nterms = 1;
+    S.chunks.push_back(std::move(ch));
+    DevSchedule D;
+    rc = upload_schedule(ctx, S, D);
+    if (rc) return rc;
+    rc = run_schedule(ctx, S, D, (double*)ctx->eig_vt.p, (double*)ctx->eig_tmp.p, (double*)ctx->eig_g.p);
+    if (rc) return rc;
+    CU(cudaStreamSynchronize(ctx->stream));
+    D.buf.release();
+    std::swap(ctx->eig_vt, ctx->eig_tmp);                   // small sectors: 1.5 x their rows sit in the old buffer, so copy them over unscaled
+    for (int q = 0; q < L.nq; ++q)
+      if (L.dims[q] <= ctx->eig_jacobi_max)
+        CU(cudaMemcpyAsync((double*)ctx->eig_vt.p + ctx->rho_off[q], (const double*)ctx->eig_tmp.p + ctx->rho_off[q],
+                           (size_t)L.dims[q] * pad_ld(L.dims[q]) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    if (getenv("B2D_EIG_DEBUG")) fprintf(stderr, "b2d eig: %d large sectors (max %d states), %d block-Jacobi sweeps\n", (int)large.size(),
+                                         L.dims[*std::max_element(large.begin(), large.end(), [&](int a, int b) { return L.dims[a] < L.dims[b]; })], ctx->eig_block_sweeps);
+  }
   if (!large.empty() && ctx->eig_cusolver) {   // diagnostic option "eig_cusolver": the library call round 1 used (never the default)
     std::string err;
     if (!ctx->cusolver.load(err)) return fail(ctx, B2D_ERR_CUDA, err);
@@ -1667,7 +1795,7 @@ int b2d_transform_operators(b2d_ctx* ctx) {
       for (int b = 0; b < N.nq; ++b)
         r.allowed[(size_t)a * N.nq + b] = o.allowed[(size_t)ctx->rotated_old[a] * L.nq + ctx->rotated_old[b]];
     layout_op(N, r);
-    if (o.dev) total += align_up(r.dev_size, 32);   // operators another rank holds are rotated there
+    if (o.dev || o.factorised) total += align_up(r.dev_size, 32);   // operators another rank holds are rotated there
     N.ops.push_back(std::move(r));
   }
   CU(ctx->rotated_arena.reserve((size_t)std::max<int64_t>(total, 16) * 8));
@@ -1676,7 +1804,7 @@ int b2d_transform_operators(b2d_ctx* ctx) {
     int64_t off = 0;
     for (size_t m = 0; m < N.ops.size(); ++m) {
       OpRec& r = N.ops[m];
-      if (!L.ops[m].dev) { r.dev = nullptr; continue; }
+      if (!(L.ops[m].dev || L.ops[m].factorised)) { r.dev = nullptr; continue; }
       r.dev = (double*)ctx->rotated_arena.p + off;
       off += align_up(r.dev_size, 32);
     }
@@ -1698,31 +1826,49 @@ int b2d_transform_operators(b2d_ctx* ctx) {
   for (size_t m = 0; m < L.ops.size(); ++m) {
     const OpRec& o = L.ops[m];
     const OpRec& r = N.ops[m];
-    if (!o.dev) continue;
+    if (!(o.dev || o.factorised)) continue;
+    View ov{&L, &o, false};
     int64_t need = 0;
     for (int a = 0; a < N.nq; ++a)
       for (int b = 0; b < N.nq; ++b)
         if (r.allowed[(size_t)a * N.nq + b]) need += align_up((int64_t)L.dims[ctx->rotated_old[a]] * pad_ld(N.dims[b]), BLK_ALIGN);
     if (cur.nterms > 0 && cur.work + need > budget) close();
     cur.nterms++;
+    if (o.factorised) cur.zero_work = true;   // row pieces without a factor stay zero
+    std::vector<SubBlock> subs;
     for (int a = 0; a < N.nq; ++a)
       for (int b = 0; b < N.nq; ++b) {
         if (!r.allowed[(size_t)a * N.nq + b]) continue;
         const int Q = ctx->rotated_old[a], Qp = ctx->rotated_old[b];
-        const int dQ = L.dims[Q], dQp = L.dims[Qp], mQ = N.dims[a], mQp = N.dims[b];
+        const int dQ = L.dims[Q], mQ = N.dims[a], mQp = N.dims[b];
         const int64_t toff = cur.work;
         const int ldt = pad_ld(mQp);
         cur.work += align_up((int64_t)dQ * ldt, BLK_ALIGN);
-        GSeg s1;
-        memset(&s1, 0, sizeof(s1));
-        s1.a = (int64_t)(intptr_t)o.dev + 8 * o.off[(size_t)Q * L.nq + Qp]; s1.a_base = B2D_BASE_ABS; s1.a_trans = 0; s1.lda = pad_ld(dQp);
-        s1.b = ctx->rot_off[Qp]; s1.b_base = B2D_BASE_AUX; s1.b_kmajor = 0; s1.ldb = pad_ld(mQp);
-        s1.k = dQp; s1.alpha = 1.0;
-        GGroup g1;
-        memset(&g1, 0, sizeof(g1));
-        g1.c = toff; g1.c_base = B2D_BASE_WORK; g1.ldc = ldt; g1.m = dQ; g1.n = mQp; g1.accumulate = 0;
-        g1.seg_begin = (int)cur.step1.segs.size(); g1.seg_end = g1.seg_begin + 1;
-        cur.step1.segs.push_back(s1); cur.step1.groups.push_back(g1);
+        // tmp = O[Q,Q'] U_Q': one product for a materialised block; for a factorised one a group per row piece with one K segment per
+        // (row piece, column piece) factor, each reading its rows of U_Q'
+        subs.clear();
+        ov.for_each_sub(Q, Qp, [&](const SubBlock& sb) { subs.push_back(sb); });
+        std::stable_sort(subs.begin(), subs.end(), [](const SubBlock& x, const SubBlock& y) { return x.r0 < y.r0; });
+        for (size_t k0 = 0; k0 < subs.size();) {
+          size_t k1 = k0;
+          while (k1 < subs.size() && subs[k1].r0 == subs[k0].r0) ++k1;
+          GGroup g1;
+          memset(&g1, 0, sizeof(g1));
+          g1.c = toff + (int64_t)subs[k0].r0 * ldt; g1.c_base = B2D_BASE_WORK; g1.ldc = ldt; g1.m = subs[k0].m; g1.n = mQp; g1.accumulate = 0;
+          g1.seg_begin = (int)cur.step1.segs.size();
+          for (size_t k = k0; k < k1; ++k) {
+            const SubBlock& sb = subs[k];
+            GSeg s1;
+            memset(&s1, 0, sizeof(s1));
+            s1.a = (int64_t)(intptr_t)sb.a; s1.a_base = B2D_BASE_ABS; s1.a_trans = sb.t ? 1 : 0; s1.lda = sb.lda;
+            s1.b = ctx->rot_off[Qp] + (int64_t)sb.c0 * pad_ld(mQp); s1.b_base = B2D_BASE_AUX; s1.b_kmajor = 0; s1.ldb = pad_ld(mQp);
+            s1.k = sb.n; s1.alpha = sb.alpha;
+            cur.step1.segs.push_back(s1);
+          }
+          g1.seg_end = (int)cur.step1.segs.size();
+          cur.step1.groups.push_back(g1);
+          k0 = k1;
+        }
         GSeg s2;
         memset(&s2, 0, sizeof(s2));
         s2.a = ctx->rot_off[Q]; s2.a_base = B2D_BASE_AUX; s2.a_trans = 1; s2.lda = pad_ld(mQ);
@@ -1838,7 +1984,7 @@ std::vector<int> noise_operators(b2d_ctx* ctx) {
   for (int ty : types)
     for (size_t m = 0; m < L.ops.size(); ++m) {
       const OpRec& o = L.ops[m];
-      if (o.optype != ty || !o.dev) continue;
+      if (o.optype != ty || !(o.dev || o.factorised)) continue;
       int owner = 0;
       if (ctx->nranks > 1) owner = o.norb == 1 ? o.orbs[0] % ctx->nranks : trimap_2d(o.orbs[0], o.orbs[1], ctx->norbs) % ctx->nranks;
       if (owner == ctx->rank) out.push_back((int)m);
@@ -1859,7 +2005,7 @@ int b2d_tensor_multiply_one_host(b2d_ctx* ctx, int side, int op_id, int transpos
   if (side < 0 || side > 1 || op_id < 0 || op_id >= (int)ctx->side[side].ops.size() || !dst_dq || !c_flat || !v_flat)
     return fail(ctx, B2D_ERR_ARG, "b2d_tensor_multiply_one_host: bad arguments");
   const OpRec& op = ctx->side[side].ops[op_id];
-  if (!op.dev && op.dev_size > 0) return fail(ctx, B2D_ERR_ARG, "b2d_tensor_multiply_one_host: operator is not resident on this rank");
+  if (!op.resident()) return fail(ctx, B2D_ERR_ARG, "b2d_tensor_multiply_one_host: operator is not resident on this rank");
   CU(cudaSetDevice(ctx->device));
   int q[3] = {dst_dq[0], dst_dq[1], dst_dq[2]};
   const PsiLayout& Pd = layout_for(ctx, q);
@@ -2098,15 +2244,30 @@ int b2d_set_product_stateinfo(b2d_ctx* ctx, int nq, const int32_t* q, const int3
     }
     if (sum != dims[c]) return fail(ctx, B2D_ERR_ARG, "b2d_set_product_stateinfo: pieces do not add up to the sector size");
   }
+  // un-collected pieces of every collected sector: (offset, size) in concatenation order
+  P.side.pieces.resize(nq);
+  for (int c = 0; c < nq; ++c) {
+    int off = 0;
+    for (int u : P.old_to_new[c]) { P.side.pieces[c].emplace_back(off, unc_dims[u]); off += unc_dims[u]; }
+  }
   P.set = true;
   ctx->product = std::move(P);
   return B2D_OK;
 }
 
+// factorised form is possible when the right child is a one-site dot: every sector holds ONE state, so a product a (x) b is the
+// child operator's block times a number
+static bool product_is_factorisable(const b2d_ctx* ctx) {
+  if (!ctx->factorised || !ctx->product.set) return false;
+  for (int d : ctx->side[1].dims) if (d != 1) return false;
+  return true;
+}
+
 int b2d_product_op_create(b2d_ctx* ctx, const int32_t* dq, int fermion, int* prod_id) {
-  NEED_DEVICE();
+  if (!ctx) return B2D_ERR_ARG;
+  if (!ctx->has_device && !product_is_factorisable(ctx)) NEED_DEVICE();   // a factorised operator is host bookkeeping: planning-only contexts can build it
   if (!ctx->product.set || !dq || !prod_id) return fail(ctx, B2D_ERR_ARG, "b2d_product_op_create: call b2d_set_product_stateinfo first");
-  CU(cudaSetDevice(ctx->device));
+  if (ctx->has_device) CU(cudaSetDevice(ctx->device));
   Side& S = ctx->product.side;
   OpRec op;
   memcpy(op.dq, dq, sizeof(op.dq));
@@ -2115,11 +2276,29 @@ int b2d_product_op_create(b2d_ctx* ctx, const int32_t* dq, int fermion, int* pro
   for (int i = 0; i < S.nq; ++i)                       // SparseMatrix::allocate BaseOperator.C:123-145
     for (int j = 0; j < S.nq; ++j) op.allowed[(size_t)i * S.nq + j] = qn_allow(S.quantum(i), dq, S.quantum(j)) ? 1 : 0;
   layout_op(S, op);
-  if (op.dev_size > 0) {
+  if (product_is_factorisable(ctx)) {
+    op.factorised = true;   // no storage: b2d_product_op_accumulate records scaled sub-blocks of the left child's operators
+    b2d_ctx::Product& P = ctx->product;
+    if (!P.identity) {      // the `A` of TensorTrace products (identity on the renormalised block): one block of the largest sector size
+      int maxd = 1;
+      for (int d : ctx->side[0].dims) maxd = std::max(maxd, d);
+      P.identity_ld = pad_ld(maxd);
+      const size_t n = (size_t)maxd * P.identity_ld;
+      CU(arena_alloc_any(ctx, n * 8, &P.identity));
+      ctx->arena_doubles += (int64_t)n;
+      if (ctx->has_device) {
+        std::vector<double> eye(n, 0.0);
+        for (int i = 0; i < maxd; ++i) eye[(size_t)i * P.identity_ld + i] = 1.0;
+        CU(cudaMemcpyAsync(P.identity, eye.data(), n * 8, cudaMemcpyHostToDevice, ctx->stream));
+        CU(cudaStreamSynchronize(ctx->stream));
+      }
+    }
+  } else if (op.dev_size > 0) {
     CU(arena_alloc(ctx, (size_t)op.dev_size * 8, &op.dev));
     CU(cudaMemsetAsync(op.dev, 0, (size_t)op.dev_size * 8, ctx->stream));
   }
   S.ops.push_back(std::move(op));
+  ctx->product.pend_subs.resize(S.ops.size());
   *prod_id = (int)S.ops.size() - 1;
   return B2D_OK;
 }
@@ -2159,22 +2338,75 @@ int b2d_product_op_accumulate(b2d_ctx* ctx, int prod_id, int left_op, int left_t
   return product_op_accumulate_impl(ctx, prod_id, left_op, left_transposed, right_op, right_transposed, scale, false);
 }
 static int product_op_accumulate_impl(b2d_ctx* ctx, int prod_id, int left_op, int left_transposed, int right_op, int right_transposed, double scale, bool defer) {
-  NEED_DEVICE();
+  if (!ctx) return B2D_ERR_ARG;
   b2d_ctx::Product& P = ctx->product;
+  const bool host_only = !ctx->has_device && P.set && prod_id >= 0 && prod_id < (int)P.side.ops.size() && P.side.ops[prod_id].factorised;
+  if (!host_only) NEED_DEVICE();
   const Side& L = ctx->side[0];
   const Side& R = ctx->side[1];
   if (!P.set || prod_id < 0 || prod_id >= (int)P.side.ops.size() || left_op >= (int)L.ops.size() || right_op >= (int)R.ops.size() || (left_op < 0 && right_op < 0))
     return fail(ctx, B2D_ERR_ARG, "b2d_product_op_accumulate: bad arguments");
   if (std::fabs(scale) < 1e-20) return B2D_OK;        // TINY, operatorfunctions.C:148
-  { int frc = flush_pending_ops(ctx); if (frc) return frc; }
-  CU(cudaSetDevice(ctx->device));
+  if (!host_only) {
+    { int frc = flush_pending_ops(ctx); if (frc) return frc; }
+    CU(cudaSetDevice(ctx->device));
+  }
   const OpRec& c = P.side.ops[prod_id];
   const bool trace_l = left_op < 0, trace_r = right_op < 0;      // identity on that child: TensorTrace
   const OpRec* la = trace_l ? nullptr : &L.ops[left_op];
   const OpRec* rb = trace_r ? nullptr : &R.ops[right_op];
-  if ((la && la->dev_size > 0 && !la->dev) || (rb && rb->dev_size > 0 && !rb->dev)) return fail(ctx, B2D_ERR_ARG, "b2d_product_op_accumulate: child operator is not resident");
+  if (!host_only && ((la && la->dev_size > 0 && !la->dev) || (rb && rb->dev_size > 0 && !rb->dev && !c.factorised)))
+    return fail(ctx, B2D_ERR_ARG, "b2d_product_op_accumulate: child operator is not resident");
   View a{&L, la, left_transposed != 0}, b{&R, rb, right_transposed != 0};
   const int sa = la ? la->dq[1] : 0, sb = rb ? rb->dq[1] : 0, sc = c.dq[1];
+  if (c.factorised) {
+    // factorised operator: the same loop as below, but a product becomes one SCALED SUB-BLOCK per (row piece, column piece) - the child
+    // operator's block (or the identity block) times  f x (1 x 1 element of the dot operator)  - instead of a scatter into storage
+    if (rb && rb->host.empty() && rb->packed_size > 0) return fail(ctx, B2D_ERR_ARG, "factorised operator: the dot operator has no host copy (b2d_add_op with data)");
+    if (la && la->factorised) return fail(ctx, B2D_ERR_ARG, "factorised operator: the left child's operators must be materialised");
+    std::vector<int64_t> rb_ref;   // packed (host) offset of each allowed block of the dot operator
+    if (rb) {
+      rb_ref.assign((size_t)R.nq * R.nq, -1);
+      int64_t off = 0;
+      for (int i = 0; i < R.nq; ++i)
+        for (int j = 0; j < R.nq; ++j)
+          if (rb->allowed[(size_t)i * R.nq + j]) { rb_ref[(size_t)i * R.nq + j] = off; off += (int64_t)R.dims[i] * R.dims[j]; }
+    }
+    auto& out = P.pend_subs[prod_id];
+    try {
+      for (int cq = 0; cq < P.side.nq; ++cq)
+        for (int cqp = 0; cqp < P.side.nq; ++cqp) {
+          if (!c.allowed[(size_t)cq * P.side.nq + cqp]) continue;
+          int row = 0;
+          for (int oi : P.old_to_new[cq]) {
+            int col = 0;
+            for (int oj : P.old_to_new[cqp]) {
+              const int aq = P.lmap[oi], aqp = P.lmap[oj], bq = P.rmap[oi], bqp = P.rmap[oj];
+              const bool a_ok = trace_l ? aq == aqp : a.allowed(aq, aqp);
+              const bool b_ok = trace_r ? bq == bqp : b.allowed(bq, bqp);
+              if (a_ok && b_ok) {
+                double f = scale * ctx->am.ninej(L.quantum(aqp)[1], R.quantum(bqp)[1], P.side.quantum(cqp)[1], sa, sb, sc, L.quantum(aq)[1], R.quantum(bq)[1],
+                                                 P.side.quantum(cq)[1]);
+                if (!trace_l && !trace_r) f *= a.scaling(ctx->am, aq, aqp) * b.scaling(ctx->am, bq, bqp);
+                if (rb && rb->fermion && (L.quantum(aqp)[0] & 1)) f = -f;
+                if (rb) f *= rb->host[(size_t)(b.t ? rb_ref[(size_t)bqp * R.nq + bq] : rb_ref[(size_t)bq * R.nq + bqp])];   // 1 x 1 block: its own transpose
+                if (f != 0.0) {
+                  SubBlock sbk;
+                  sbk.r0 = row; sbk.c0 = col; sbk.m = L.dims[aq]; sbk.n = L.dims[aqp]; sbk.alpha = f;
+                  if (trace_l) { sbk.a = P.identity; sbk.lda = P.identity_ld; sbk.t = false; }
+                  else { sbk.a = la->dev + a.stored_off(aq, aqp); sbk.lda = a.stored_ld(aq, aqp); sbk.t = a.t; }
+                  out.emplace_back((size_t)cq * P.side.nq + cqp, sbk);
+                }
+              }
+              col += P.unc_dims[oj];
+            }
+            row += P.unc_dims[oi];
+          }
+        }
+    } catch (const std::exception& e) { return fail(ctx, B2D_ERR_ARG, e.what()); }
+    ctx->kron_nproducts += 1;
+    return B2D_OK;
+  }
   std::vector<KronTask> tasks;
   try {
     for (int cq = 0; cq < P.side.nq; ++cq)
@@ -2229,6 +2461,105 @@ static int product_op_accumulate_impl(b2d_ctx* ctx, int prod_id, int left_op, in
   return B2D_OK;
 }
 
+// Factorised operator complete (every product recorded): turn the product-ordered factor list into the per-block table the planners
+// read.  Factors that hit the same (row piece, column piece) are PRE-SUMMED into one block of the child's size ("combo", built on the
+// device by the scatter kernel in product order) - a complementary operator has one factor per site of the renormalised block there, and
+// contracting them one by one would multiply the flops -, except the common pair {child block, identity}: the identity stays a factor of
+// its own (no storage).  Combos with the same parts and proportional coefficients are shared: the spin-recoupling variants of a piece pair
+// (S_dot = 1/2 couples to S +- 1/2) differ only by their 9j prefactor, which goes into alpha.
+static int finalise_factorised_op(b2d_ctx* ctx, int prod_id) {
+  b2d_ctx::Product& P = ctx->product;
+  OpRec& op = P.side.ops[prod_id];
+  if (!op.factorised || !op.sub_begin.empty()) return B2D_OK;
+  auto& pend = P.pend_subs[prod_id];
+  std::stable_sort(pend.begin(), pend.end(), [](const std::pair<size_t, SubBlock>& x, const std::pair<size_t, SubBlock>& y) { return x.first < y.first; });
+  const size_t nb = (size_t)P.side.nq * P.side.nq;
+  op.sub_begin.assign(nb + 1, 0);
+  op.subs.clear();
+  size_t k = 0;
+  std::vector<const SubBlock*> list;
+  for (size_t b = 0; b < nb; ++b) {
+    op.sub_begin[b] = (int32_t)op.subs.size();
+    size_t k1 = k;
+    while (k1 < pend.size() && pend[k1].first == b) ++k1;
+    std::vector<bool> done(k1 - k, false);
+    for (size_t i = k; i < k1; ++i) {
+      if (done[i - k]) continue;
+      list.clear();
+      for (size_t j = i; j < k1; ++j)
+        if (!done[j - k] && pend[j].second.r0 == pend[i].second.r0 && pend[j].second.c0 == pend[i].second.c0) { list.push_back(&pend[j].second); done[j - k] = true; }
+      // merge repeated parts (same child block, same orientation)
+      std::vector<std::pair<const double*, bool>> parts;
+      std::vector<double> alphas;
+      std::vector<int> ldas;
+      for (const SubBlock* sb : list) {
+        bool merged = false;
+        for (size_t q = 0; q < parts.size(); ++q)
+          if (parts[q].first == sb->a && parts[q].second == sb->t) { alphas[q] += sb->alpha; merged = true; break; }
+        if (!merged) { parts.emplace_back(sb->a, sb->t); alphas.push_back(sb->alpha); ldas.push_back(sb->lda); }
+      }
+      const SubBlock& first = *list[0];
+      int nident = 0;
+      for (const auto& pr : parts) nident += pr.first == P.identity;
+      if (parts.size() == 1 || (parts.size() == 2 && nident == 1)) {
+        for (size_t q = 0; q < parts.size(); ++q) {
+          if (alphas[q] == 0.0) continue;
+          SubBlock sb = first;
+          sb.a = parts[q].first; sb.t = parts[q].second; sb.lda = ldas[q]; sb.alpha = alphas[q];
+          op.subs.push_back(sb);
+          ++ctx->nsubs_direct;
+        }
+        continue;
+      }
+      size_t lead = 0;
+      while (lead < alphas.size() && alphas[lead] == 0.0) ++lead;
+      if (lead == alphas.size()) continue;
+      std::vector<double> ratios(alphas.size());
+      for (size_t q = 0; q < alphas.size(); ++q) ratios[q] = alphas[q] / alphas[lead];
+      const std::array<int64_t, 3> key{(int64_t)(intptr_t)parts[0].first, (int64_t)first.m, (int64_t)first.n};
+      std::vector<b2d_ctx::Product::Combo>& cands = P.combos[key];
+      const double* block = nullptr;
+      for (const auto& c : cands) {
+        if (c.parts != parts) continue;
+        bool same = true;
+        for (size_t q = 0; q < ratios.size() && same; ++q) same = std::fabs(c.ratios[q] - ratios[q]) <= 1e-12 * std::max(std::fabs(ratios[q]), 1e-300);
+        if (same) { block = c.block; break; }
+      }
+      const int ldc = pad_ld(first.n);
+      if (!block) {
+        double* dst = nullptr;
+        const size_t n = (size_t)align_up((int64_t)first.m * ldc, BLK_ALIGN);
+        CU(arena_alloc_any(ctx, n * 8, &dst));
+        if (ctx->has_device) CU(cudaMemsetAsync(dst, 0, n * 8, ctx->stream));
+        ctx->arena_doubles += (int64_t)n; ctx->combo_doubles += (int64_t)n;
+        for (size_t q = 0; q < parts.size(); ++q) {
+          if (ratios[q] == 0.0) continue;
+          KronTask kt;
+          memset(&kt, 0, sizeof(kt));
+          kt.a = (int64_t)(intptr_t)parts[q].first; kt.b = 0; kt.dst = (int64_t)(intptr_t)dst; kt.coef = ratios[q];
+          kt.a_rows = first.m; kt.a_cols = first.n; kt.lda = ldas[q]; kt.a_t = parts[q].second ? 1 : 0;
+          kt.b_rows = kt.b_cols = 1; kt.ldb = 1; kt.b_t = 0; kt.row0 = kt.col0 = 0; kt.ldd = ldc;
+          int& hits = ctx->pend_kron_hits[std::array<int64_t, 3>{kt.dst, 0, 0}];
+          ctx->pend_kron.push_back(kt);
+          ctx->pend_kron_round.push_back(hits++);
+          ctx->kron_bytes += 8.0 * 3.0 * (double)first.m * first.n;
+          ++ctx->kron_ntasks;
+        }
+        cands.push_back(b2d_ctx::Product::Combo{parts, ratios, dst});
+        block = dst;
+      }
+      SubBlock sb = first;
+      sb.a = block; sb.lda = ldc; sb.t = false; sb.alpha = alphas[lead];
+      op.subs.push_back(sb);
+      ++ctx->nsubs_combo;
+    }
+    k = k1;
+  }
+  op.sub_begin[nb] = (int32_t)op.subs.size();
+  std::vector<std::pair<size_t, SubBlock>>().swap(pend);
+  return B2D_OK;
+}
+
 int b2d_set_integrals(b2d_ctx* ctx, int norbs, const double* v1, const double* v2, const int32_t* orbital_irreps, double one_tol, double two_tol) {
   if (!ctx || norbs <= 0 || !v1 || !v2 || !orbital_irreps) return fail(ctx, B2D_ERR_ARG, "b2d_set_integrals: bad arguments");
   Integrals& I = ctx->integrals;
@@ -2268,7 +2599,8 @@ int b2d_enlarged_op_products(b2d_ctx* ctx, int optype, int norb, const int32_t* 
 }
 
 int b2d_build_enlarged_op(b2d_ctx* ctx, int optype, int norb, const int32_t* orbs, int comp, const int32_t* dq, int fermion, int hubbard, int* prod_id) {
-  NEED_DEVICE();
+  if (!ctx) return B2D_ERR_ARG;
+  if (!ctx->has_device && !product_is_factorisable(ctx)) NEED_DEVICE();
   if (!prod_id) return fail(ctx, B2D_ERR_ARG, "b2d_build_enlarged_op: bad arguments");
   std::vector<ProductCall> calls;
   int rc = plan_enlarged_op(ctx, optype, norb, orbs, dq, hubbard, calls);
@@ -2281,17 +2613,19 @@ int b2d_build_enlarged_op(b2d_ctx* ctx, int optype, int norb, const int32_t* orb
     for (int k = 0; k < norb; ++k) op.orbs[k] = orbs[k];
   }
   for (const ProductCall& c : calls) {
-    rc = ctx->opbuild_batch ? product_op_accumulate_impl(ctx, *prod_id, c.lop, c.lt ? 1 : 0, c.rop, c.rt ? 1 : 0, c.scale, true)
-                            : b2d_product_op_accumulate(ctx, *prod_id, c.lop, c.lt ? 1 : 0, c.rop, c.rt ? 1 : 0, c.scale);
+    rc = (ctx->opbuild_batch || ctx->product.side.ops[*prod_id].factorised)
+             ? product_op_accumulate_impl(ctx, *prod_id, c.lop, c.lt ? 1 : 0, c.rop, c.rt ? 1 : 0, c.scale, true)
+             : b2d_product_op_accumulate(ctx, *prod_id, c.lop, c.lt ? 1 : 0, c.rop, c.rt ? 1 : 0, c.scale);
     if (rc) return rc;
   }
-  return B2D_OK;
+  return finalise_factorised_op(ctx, *prod_id);
 }
 
 // One child of the big block is ready (built on the device from ITS children, or uploaded as it is): park it, so that side 0 / side 1
 // are free to describe the children of the other one.  b2d_assemble_big then makes the two parked blocks the children of the big block.
 int b2d_stash_product(b2d_ctx* ctx, int slot, int is_loop, int nsites, const int32_t* sites) {
   if (!ctx || slot < 0 || slot > 1 || !ctx->product.set) return fail(ctx, B2D_ERR_ARG, "b2d_stash_product: no product block");
+  for (size_t m = 0; m < ctx->product.side.ops.size(); ++m) { int frc = finalise_factorised_op(ctx, (int)m); if (frc) return frc; }
   if (ctx->has_device) { int frc = flush_product_tasks(ctx); if (frc) return frc; }
   Side s = std::move(ctx->product.side);
   s.loop = is_loop != 0;
@@ -2478,6 +2812,45 @@ int b2d_product_stats(const b2d_ctx* ctx, double* out, int n) {
   return B2D_OK;
 }
 
+// A factorised operator written out as the dense sector blocks the reference's Op::build produces (check mode, tests): the scatter
+// kernel adds every scaled sub-block at its (row piece, column piece) position; factors of one position go to successive rounds.
+static int materialise_factorised(b2d_ctx* ctx, const Side& S, const OpRec& op, DevBuf& buf) {
+  CU(cudaSetDevice(ctx->device));
+  const size_t bytes = (size_t)std::max<int64_t>(op.dev_size, 16) * 8;
+  CU(buf.reserve(bytes));
+  CU(cudaMemsetAsync(buf.p, 0, bytes, ctx->stream));
+  std::vector<KronTask> tasks;
+  std::vector<int> round;
+  std::map<std::array<int64_t, 3>, int> hits;
+  int nrounds = 0;
+  for (int i = 0; i < S.nq; ++i)
+    for (int j = 0; j < S.nq; ++j) {
+      if (!op.allowed[(size_t)i * S.nq + j]) continue;
+      const size_t b = (size_t)i * S.nq + j;
+      for (int32_t k = op.sub_begin[b]; k < op.sub_begin[b + 1]; ++k) {
+        const SubBlock& sb = op.subs[k];
+        KronTask kt;
+        memset(&kt, 0, sizeof(kt));
+        kt.a = (int64_t)(intptr_t)sb.a; kt.b = 0; kt.dst = (int64_t)(intptr_t)((double*)buf.p + op.off[b]); kt.coef = sb.alpha;
+        kt.a_rows = sb.m; kt.a_cols = sb.n; kt.lda = sb.lda; kt.a_t = sb.t ? 1 : 0;
+        kt.b_rows = kt.b_cols = 1; kt.ldb = 1; kt.row0 = sb.r0; kt.col0 = sb.c0; kt.ldd = pad_ld(S.dims[j]);
+        int& h = hits[std::array<int64_t, 3>{kt.dst, (int64_t)kt.row0, (int64_t)kt.col0}];
+        tasks.push_back(kt); round.push_back(h);
+        nrounds = std::max(nrounds, ++h);
+      }
+    }
+  std::vector<int> count(nrounds + 1, 0);
+  for (int r : round) count[r + 1]++;
+  for (int r = 0; r < nrounds; ++r) count[r + 1] += count[r];
+  std::vector<KronTask> sorted(tasks.size());
+  { std::vector<int> at(count.begin(), count.end() - 1); for (size_t i = 0; i < tasks.size(); ++i) sorted[at[round[i]]++] = tasks[i]; }
+  int rc = upload_desc(ctx, ctx->kron_tasks, sorted.data(), sorted.size() * sizeof(KronTask));
+  if (rc) return rc;
+  for (int r = 0; r < nrounds; ++r)
+    CU(launch_kron_scatter((const KronTask*)ctx->kron_tasks.p + count[r], count[r + 1] - count[r], ctx->stream, &ctx->launches));
+  return B2D_OK;
+}
+
 int64_t b2d_product_op_size(const b2d_ctx* ctx, int prod_id) {
   if (!ctx || !ctx->product.set || prod_id < 0 || prod_id >= (int)ctx->product.side.ops.size()) return -1;
   return ctx->product.side.ops[prod_id].packed_size;
@@ -2486,18 +2859,169 @@ int64_t b2d_product_op_size(const b2d_ctx* ctx, int prod_id) {
 int b2d_product_op_download(b2d_ctx* ctx, int prod_id, uint8_t* allowed, double* data) {
   NEED_DEVICE();
   if (!ctx->product.set || prod_id < 0 || prod_id >= (int)ctx->product.side.ops.size()) return fail(ctx, B2D_ERR_ARG, "b2d_product_op_download: bad arguments");
+  { int frc = finalise_factorised_op(ctx, prod_id); if (frc) return frc; }
   { int frc = flush_product_tasks(ctx); if (frc) return frc; }
   const Side& S = ctx->product.side;
   const OpRec& op = S.ops[prod_id];
   if (allowed) memcpy(allowed, op.allowed.data(), op.allowed.size());
   if (!data || op.packed_size == 0) return B2D_OK;
+  const double* dev = op.dev;
+  if (op.factorised) {
+    int mrc = materialise_factorised(ctx, S, op, ctx->materialised);
+    if (mrc) return mrc;
+    dev = (const double*)ctx->materialised.p;
+  }
   std::vector<BlockDesc> bd = op_blocks(S, op);
   CU(ctx->staging.reserve((size_t)op.packed_size * 8));
   int rc = upload_desc(ctx, ctx->desc_scratch, bd.data(), bd.size() * sizeof(BlockDesc));
   if (rc) return rc;
-  CU(launch_unpack((const BlockDesc*)ctx->desc_scratch.p, (int)bd.size(), op.dev, (double*)ctx->staging.p, ctx->stream, &ctx->launches));
+  CU(launch_unpack((const BlockDesc*)ctx->desc_scratch.p, (int)bd.size(), dev, (double*)ctx->staging.p, ctx->stream, &ctx->launches));
   CU(cudaMemcpyAsync(data, ctx->staging.p, (size_t)op.packed_size * 8, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  return B2D_OK;
+}
+
+// ---- device-side shadow of the scratch files ------------------------------------------------------------
+// b2d_transform_operators leaves the renormalised left block in its own buffer; b2d_cache_put_rotated moves that buffer (no copy) into
+// the cache under a fresh token and b2d_cache_use makes a cached block a child of the next product / big block without any host traffic.
+int b2d_cache_put_rotated(b2d_ctx* ctx, uint64_t* token) {
+  NEED_DEVICE();
+  if (!ctx->have_rotated || !token) return fail(ctx, B2D_ERR_ARG, "b2d_cache_put_rotated: call b2d_transform_operators first");
+  CU(cudaSetDevice(ctx->device));
+  b2d_ctx::CachedBlock cb;
+  cb.side = ctx->rotated;
+  const double* base = (const double*)ctx->rotated_arena.p;
+  int64_t total = 0;
+  for (OpRec& op : cb.side.ops) {
+    if (op.dev) { op.cache_off = op.dev - base; total = std::max(total, op.cache_off + op.dev_size); op.dev = nullptr; }
+    else op.cache_off = -1;
+  }
+  cb.doubles = total;
+  if ((double)(ctx->cache_device_doubles + total) * 8.0 <= ctx->cache_device_mb * 1048576.0) {
+    cb.dev = ctx->rotated_arena;            // the buffer changes owner; b2d_transform_operators allocates a new one next time
+    ctx->rotated_arena = DevBuf();
+    ctx->cache_device_doubles += total;
+  } else {                                   // over budget: spill to pinned host memory
+    if (total > 0) {
+      if (cudaMallocHost(&cb.pinned, (size_t)total * 8) != cudaSuccess) return fail(ctx, B2D_ERR_CUDA, "b2d_cache_put_rotated: cudaMallocHost failed");
+      CU(cudaMemcpyAsync(cb.pinned, base, (size_t)total * 8, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+    }
+  }
+  ctx->have_rotated = false;
+  *token = ctx->cache_next_token++;
+  ctx->cache[*token] = std::move(cb);
+  ++ctx->cache_puts;
+  return B2D_OK;
+}
+
+int b2d_cache_use(b2d_ctx* ctx, uint64_t token, int side, int is_loop) {
+  NEED_DEVICE();
+  auto it = ctx->cache.find(token);
+  if (it == ctx->cache.end() || side < 0 || side > 1) return fail(ctx, B2D_ERR_ARG, "b2d_cache_use: unknown token");
+  CU(cudaSetDevice(ctx->device));
+  b2d_ctx::CachedBlock& cb = it->second;
+  const double* base = (const double*)cb.dev.p;
+  if (!base && cb.doubles > 0) {             // spilled entry: one H2D copy into the arena (freed by the next b2d_reset)
+    double* tmp = nullptr;
+    CU(arena_alloc(ctx, (size_t)cb.doubles * 8, &tmp));
+    CU(cudaMemcpyAsync(tmp, cb.pinned, (size_t)cb.doubles * 8, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    ctx->arena_doubles += cb.doubles;
+    base = tmp;
+  }
+  Side s = cb.side;
+  for (OpRec& op : s.ops) {
+    if (op.cache_off >= 0) op.dev = const_cast<double*>(base) + op.cache_off;
+    op.cache_off = -1;
+  }
+  s.loop = is_loop != 0;
+  ctx->side[side] = std::move(s);
+  ctx->planned = false;
+  ++ctx->cache_hits;
+  return B2D_OK;
+}
+
+int b2d_cache_block_info(const b2d_ctx* ctx, uint64_t token, int32_t* nq, int32_t* nops, int32_t* nsites) {
+  if (!ctx) return B2D_ERR_ARG;
+  auto it = ctx->cache.find(token);
+  if (it == ctx->cache.end()) return B2D_ERR_ARG;
+  if (nq) *nq = it->second.side.nq;
+  if (nops) *nops = (int32_t)it->second.side.ops.size();
+  if (nsites) *nsites = (int32_t)it->second.side.sites.size();
+  return B2D_OK;
+}
+int b2d_cache_block_sectors(const b2d_ctx* ctx, uint64_t token, int32_t* q, int32_t* dims, int32_t* sites) {
+  if (!ctx) return B2D_ERR_ARG;
+  auto it = ctx->cache.find(token);
+  if (it == ctx->cache.end()) return B2D_ERR_ARG;
+  const Side& s = it->second.side;
+  if (q) memcpy(q, s.q.data(), s.q.size() * sizeof(int32_t));
+  if (dims) memcpy(dims, s.dims.data(), s.dims.size() * sizeof(int32_t));
+  if (sites) memcpy(sites, s.sites.data(), s.sites.size() * sizeof(int32_t));
+  return B2D_OK;
+}
+int b2d_cache_op_info(const b2d_ctx* ctx, uint64_t token, int op_id, int32_t* optype, int32_t* norb, int32_t* orbs, int32_t* comp, int64_t* packed_size) {
+  if (!ctx) return B2D_ERR_ARG;
+  auto it = ctx->cache.find(token);
+  if (it == ctx->cache.end() || op_id < 0 || op_id >= (int)it->second.side.ops.size()) return B2D_ERR_ARG;
+  const OpRec& op = it->second.side.ops[op_id];
+  if (optype) *optype = op.optype;
+  if (norb) *norb = op.norb;
+  if (orbs) { orbs[0] = op.orbs[0]; orbs[1] = op.orbs[1]; }
+  if (comp) *comp = op.comp;
+  if (packed_size) *packed_size = op.packed_size;
+  return B2D_OK;
+}
+
+// packed blocks of one operator of a cached block back on the host (what the scratch file would have held): the binding calls this
+// when a host-side code path needs the real matrices after all
+int b2d_cache_download_op(b2d_ctx* ctx, uint64_t token, int op_id, uint8_t* allowed, double* data) {
+  NEED_DEVICE();
+  auto it = ctx->cache.find(token);
+  if (it == ctx->cache.end() || op_id < 0 || op_id >= (int)it->second.side.ops.size()) return fail(ctx, B2D_ERR_ARG, "b2d_cache_download_op: bad arguments");
+  CU(cudaSetDevice(ctx->device));
+  b2d_ctx::CachedBlock& cb = it->second;
+  const Side& S = cb.side;
+  const OpRec& op = S.ops[op_id];
+  if (allowed) memcpy(allowed, op.allowed.data(), op.allowed.size());
+  if (!data || op.packed_size == 0) return B2D_OK;
+  if (op.cache_off < 0) return fail(ctx, B2D_ERR_ARG, "b2d_cache_download_op: operator was not resident on this rank");
+  const int64_t off = op.cache_off;
+  const double* dev = nullptr;
+  if (cb.dev.p) dev = (const double*)cb.dev.p + off;
+  else {   // spilled: stage this operator's padded image on the device
+    CU(ctx->materialised.reserve((size_t)op.dev_size * 8));
+    CU(cudaMemcpyAsync(ctx->materialised.p, cb.pinned + off, (size_t)op.dev_size * 8, cudaMemcpyHostToDevice, ctx->stream));
+    dev = (const double*)ctx->materialised.p;
+  }
+  std::vector<BlockDesc> bd = op_blocks(S, op);
+  CU(ctx->staging.reserve((size_t)op.packed_size * 8));
+  int rc = upload_desc(ctx, ctx->desc_scratch, bd.data(), bd.size() * sizeof(BlockDesc));
+  if (rc) return rc;
+  CU(launch_unpack((const BlockDesc*)ctx->desc_scratch.p, (int)bd.size(), dev, (double*)ctx->staging.p, ctx->stream, &ctx->launches));
+  CU(cudaMemcpyAsync(data, ctx->staging.p, (size_t)op.packed_size * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return B2D_OK;
+}
+
+int b2d_cache_drop(b2d_ctx* ctx, uint64_t token) {
+  if (!ctx) return B2D_ERR_ARG;
+  auto it = ctx->cache.find(token);
+  if (it == ctx->cache.end()) return B2D_OK;
+  if (ctx->has_device) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
+  if (it->second.dev.p) { ctx->cache_device_doubles -= it->second.doubles; it->second.dev.release(); }
+  if (it->second.pinned) cudaFreeHost(it->second.pinned);
+  ctx->cache.erase(it);
+  return B2D_OK;
+}
+
+int b2d_cache_stats(const b2d_ctx* ctx, double* out, int n) {
+  if (!ctx || !out) return B2D_ERR_ARG;
+  double spilled = 0;
+  for (const auto& kv : ctx->cache) if (!kv.second.dev.p) spilled += (double)kv.second.doubles;
+  const double v[5] = {(double)ctx->cache.size(), (double)ctx->cache_device_doubles, spilled, (double)ctx->cache_puts, (double)ctx->cache_hits};
+  for (int i = 0; i < n && i < 5; ++i) out[i] = v[i];
   return B2D_OK;
 }
 

@@ -50,10 +50,16 @@ __global__ void __launch_bounds__(BJ_THREADS) block_jacobi_step_kernel(const BJP
   double* Ws = As + BJ_R * BJ_LDA;                   // [BJ_R][BJ_LDW]
   double* cs = Ws + BJ_R * BJ_LDW;                   // [32][4]: c, s, p, q of the round's rotations (p < 0: none)
   int* any_flag = reinterpret_cast<int*>(cs + 32 * 4);
+  int* sig_flag = any_flag + 1;                      // a rotation well above the noise threshold happened: the sector has not converged
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int d = pr.d, ld = pr.ld;
   // the Gram entries are d-term dot products: their rounding noise grows like sqrt(d), and a threshold below it would rotate noise for ever
-  tol *= fmax(1.0, sqrt((double)d / 64.0));
+  tol *= fmax(1.0, 0.5 * sqrt((double)d));
+  // Rows of G whose norm is below 1e-16 belong to eigenvalues below 1e-16 (rho has trace <= 1): two orders under the reference's clamp
+  // (1e-14 -> 0, rotationmat.C:274) and three under its keep threshold (1e-13, :161) - they are never retained.  Their direction is pure
+  // rounding noise of the density-matrix build, so "orthogonalising" them never converges; pairs that involve such a row are left alone
+  // (V stays orthogonal whatever is skipped; the retained vectors pick up at most a 1e-16 / lambda rotation into the null space).
+  const double floor2 = 1e-32;
   double* G = g + pr.off;
   double* V = vt + pr.off;
   auto row_of = [&](int r) -> int {   // local row -> row of the sector, or -1
@@ -99,7 +105,7 @@ __global__ void __launch_bounds__(BJ_THREADS) block_jacobi_step_kernel(const BJP
       for (int b = 0; b < 4; ++b) As[(ty * 4 + a) * BJ_LDA + tx * 4 + b] = acc[a][b];
   }
   for (int e = tid; e < BJ_R * BJ_R; e += BJ_THREADS) Ws[(e / BJ_R) * BJ_LDW + e % BJ_R] = (e / BJ_R == e % BJ_R) ? 1.0 : 0.0;
-  if (tid == 0) *any_flag = 0;
+  if (tid == 0) { *any_flag = 0; *sig_flag = 0; }
   __syncthreads();
 
   // ---- 2. two-sided cyclic Jacobi on A (64 x 64), rotations accumulated in W ----
@@ -114,7 +120,7 @@ __global__ void __launch_bounds__(BJ_THREADS) block_jacobi_step_kernel(const BJP
         const double app = As[a * BJ_LDA + a], aqq = As[b * BJ_LDA + b], apq = As[a * BJ_LDA + b];
         double c = 1.0, s = 0.0;
         int p = -1;
-        if (app > 0.0 && aqq > 0.0 && fabs(apq) > tol * sqrt(app * aqq)) {
+        if (app > floor2 && aqq > floor2 && fabs(apq) > tol * sqrt(app * aqq)) {
           const double zeta = (aqq - app) / (2.0 * apq);
           const double t = (zeta >= 0.0 ? 1.0 : -1.0) / (fabs(zeta) + sqrt(1.0 + zeta * zeta));
           c = 1.0 / sqrt(1.0 + t * t);
@@ -123,7 +129,10 @@ __global__ void __launch_bounds__(BJ_THREADS) block_jacobi_step_kernel(const BJP
         }
         cs[tid * 4 + 0] = c; cs[tid * 4 + 1] = s; cs[tid * 4 + 2] = (double)p; cs[tid * 4 + 3] = (double)b;
         const unsigned m = __ballot_sync(0xffffffffu, p >= 0);
-        if (tid == 0) *any_flag = m != 0;
+        // rotations between tol and 4 tol are applied but do not keep the sector alive: at that level the fresh Gram entries of the next
+        // sweep are rounding noise of the d-term dot products, and a whole sweep without ANY rotation would never happen
+        const unsigned ms = __ballot_sync(0xffffffffu, p >= 0 && fabs(apq) > 4.0 * tol * sqrt(app * aqq));
+        if (tid == 0) { *any_flag = m != 0; if (ms) *sig_flag = 1; }
       }
       __syncthreads();
       const int any = *any_flag;
@@ -159,7 +168,7 @@ __global__ void __launch_bounds__(BJ_THREADS) block_jacobi_step_kernel(const BJP
     applied_total = 1;
   }
   if (!applied_total) return;                        // the 64 rows were already mutually orthogonal: nothing to write
-  if (tid == 0) rotated[pr.sector] = 1;
+  if (tid == 0 && *sig_flag) rotated[pr.sector] = 1;
 
   // ---- 3. X <- W^T X for the rows of G and of V (new row r = sum_i W[i][r] x_i), in place ----
   for (int which = 0; which < 2; ++which) {

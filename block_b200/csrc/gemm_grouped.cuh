@@ -55,6 +55,12 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem, int src
   unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
 }
+// 8-byte variant for operands that start on an odd element (a column piece of a wavefunction / T block at an odd offset: the
+// factorised operators of an enlarged block address sub-blocks of psi, T and sigma): same zero-fill semantics, twice the copies
+__device__ __forceinline__ void cp_async8(void* smem, const void* gmem, int src_bytes) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(s), "l"(gmem), "r"(src_bytes));
+}
 // mbarrier primitives (shared::cta).  full[stage]: data of a pipeline stage has landed (every thread's cp.async group
 // arrives asynchronously); empty[stage]: every warp has finished reading the stage.
 __device__ __forceinline__ void mbar_init(uint64_t* b, int count) {
@@ -110,6 +116,7 @@ struct StageMeta {
 template <int R, int THREADS>
 __device__ __forceinline__ void stage_operand(double* smem, const double* g, int ld, bool kmajor, int r0, int k0, int r_total, int k_total) {
   const int tid = threadIdx.x;
+  const bool al16 = (reinterpret_cast<uintptr_t>(g) & 15) == 0;   // leading dimensions are even: the base address decides for every chunk
   if (kmajor) {
     constexpr int CPR = GEMM_BK / 2;           // 16-byte chunks per row
     constexpr int CHUNKS = R * CPR;
@@ -119,7 +126,9 @@ __device__ __forceinline__ void stage_operand(double* smem, const double* g, int
       int gr = r0 + row, gk = k0 + kc;
       int nv = (gr < r_total) ? min(max(k_total - gk, 0), 2) : 0;
       const double* src = nv > 0 ? g + (int64_t)gr * ld + gk : g;
-      cp_async16(smem + row * (GEMM_BK + GEMM_PAD) + kc, src, nv * 8);
+      double* dst = smem + row * (GEMM_BK + GEMM_PAD) + kc;
+      if (al16) cp_async16(dst, src, nv * 8);
+      else { cp_async8(dst, src, nv > 0 ? 8 : 0); cp_async8(dst + 1, nv > 1 ? src + 1 : g, nv > 1 ? 8 : 0); }
     }
   } else {
     constexpr int CPR = R / 2;
@@ -130,7 +139,9 @@ __device__ __forceinline__ void stage_operand(double* smem, const double* g, int
       int gk = k0 + krow, gr = r0 + rc;
       int nv = (gk < k_total) ? min(max(r_total - gr, 0), 2) : 0;
       const double* src = nv > 0 ? g + (int64_t)gk * ld + gr : g;
-      cp_async16(smem + krow * (R + GEMM_PAD) + rc, src, nv * 8);
+      double* dst = smem + krow * (R + GEMM_PAD) + rc;
+      if (al16) cp_async16(dst, src, nv * 8);
+      else { cp_async8(dst, src, nv > 0 ? 8 : 0); cp_async8(dst + 1, nv > 1 ? src + 1 : g, nv > 1 ? 8 : 0); }
     }
   }
 }
@@ -270,13 +281,14 @@ __global__ void __launch_bounds__(TileCfg<BM, BN>::THREADS)
         if (row >= grp.m || col >= grp.n) continue;
         double* dst = C + (int64_t)row * grp.ldc + col;
         double v0 = acc[i][j][2 * h], v1 = acc[i][j][2 * h + 1];
-        if (col + 1 < grp.n) {
+        if (col + 1 < grp.n && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
           double2 o;
           if (grp.accumulate) { o = *reinterpret_cast<double2*>(dst); o.x += v0; o.y += v1; }
           else { o.x = v0; o.y = v1; }
           *reinterpret_cast<double2*>(dst) = o;
         } else {
           dst[0] = grp.accumulate ? dst[0] + v0 : v0;
+          if (col + 1 < grp.n) dst[1] = grp.accumulate ? dst[1] + v1 : v1;   // output block at an odd column offset
         }
       }
   if (bases.trace && threadIdx.x == 0) {
@@ -418,13 +430,14 @@ __global__ void __launch_bounds__(TileCfg<BM, BN>::THREADS)
           if (row >= grp.m || col >= grp.n) continue;
           double* dst = C + (int64_t)row * grp.ldc + col;
           double v0 = acc[i][j][2 * h], v1 = acc[i][j][2 * h + 1];
-          if (col + 1 < grp.n) {
+          if (col + 1 < grp.n && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {
             double2 o;
             if (grp.accumulate) { o = *reinterpret_cast<double2*>(dst); o.x += v0; o.y += v1; }
             else { o.x = v0; o.y = v1; }
             *reinterpret_cast<double2*>(dst) = o;
           } else {
             dst[0] = grp.accumulate ? dst[0] + v0 : v0;
+            if (col + 1 < grp.n) dst[1] = grp.accumulate ? dst[1] + v1 : v1;
           }
         }
   }

@@ -31,6 +31,18 @@ inline int64_t align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
 enum { OP_HAM = 0, OP_CRE = 1, OP_CRE_CRE = 2, OP_DES_DESCOMP = 3, OP_CRE_DES = 4, OP_CRE_DESCOMP = 5, OP_CRE_CRE_DESCOMP = 6, OP_OVERLAP = 13 };
 
+// One (row piece, column piece) contribution to a sector block of a FACTORISED enlarged-block operator (see OpRec::factorised):
+//   block[r0 : r0 + m, c0 : c0 + n] += alpha * op(A),   op(A) = A (stored m x n) or A^T (stored n x m, t = true), leading dimension lda
+// A is a sector block of an operator of the renormalised child (or that product's identity block); the 1 x 1 element of the dot operator,
+// the 9j coefficient, Transposeview scalings and the fermion sign of operatorfunctions.C:205-218 are folded into alpha.
+struct SubBlock {
+  int32_t r0, c0, m, n;
+  const double* a;
+  int32_t lda;
+  bool t;
+  double alpha;
+};
+
 struct OpRec {
   int optype = 0, norb = 0, orbs[2] = {-1, -1}, comp = 0;
   int dq[3] = {0, 0, 0};
@@ -41,6 +53,15 @@ struct OpRec {
   int64_t dev_size = 0;           // padded device layout
   double* dev = nullptr;
   bool pending = false;           // selected for allocation by the current b2d_plan
+  int64_t cache_off = -1;         // inside a cached block (b2d_cache_*): offset of the operator from the entry's buffer, -1 if not resident
+  // Factorised form (operators of an enlarged block S (x) dot, SURVEY.md 7 "hard parts"): the block is never materialised; every allowed
+  // sector block (i,j) is the list subs[sub_begin[i * nq + j] .. sub_begin[i * nq + j + 1]) of scaled sub-blocks of the renormalised child's
+  // operators.  `off` / `dev_size` keep describing the materialised layout (used when the operator is materialised on request).
+  bool factorised = false;
+  std::vector<int32_t> sub_begin;
+  std::vector<SubBlock> subs;
+  std::vector<double> host;       // host copy of a SMALL operator's packed blocks (the one-site dot: its 1 x 1 elements become alphas)
+  bool resident() const { return dev != nullptr || factorised || dev_size == 0; }
 };
 
 struct Side {
@@ -50,6 +71,9 @@ struct Side {
   bool loop = false;
   std::vector<int> sites;
   std::vector<OpRec> ops;
+  // un-collected pieces of every sector (offset, size) when the block is a product S (x) dot (StateInfo::oldToNewState order); empty
+  // for a block that was uploaded as it is
+  std::vector<std::vector<std::pair<int, int>>> pieces;
   const int* quantum(int i) const { return &q[3 * i]; }
   int find(int optype, const int* orbs, int norb, int comp) const {
     for (size_t m = 0; m < ops.size(); ++m) {
@@ -91,6 +115,23 @@ struct View {
   int stored_ld(int i, int j) const { return pad_ld(t ? side->dims[i] : side->dims[j]); }
   double scaling(AngMom& am, int i, int j) const {
     return t ? am.transpose_scaling(op->dq[1], side->quantum(i)[1], side->quantum(j)[1]) : 1.0;
+  }
+  // view element (i,j) as scaled sub-blocks: one full-size entry for a materialised operator, the factor list otherwise
+  template <class F>
+  void for_each_sub(int i, int j, F&& f) const {
+    if (!op->factorised) {
+      SubBlock s;
+      s.r0 = 0; s.c0 = 0; s.m = side->dims[i]; s.n = side->dims[j];
+      s.a = op->dev + stored_off(i, j); s.lda = stored_ld(i, j); s.t = t; s.alpha = 1.0;
+      f(s);
+      return;
+    }
+    const size_t b = t ? (size_t)j * side->nq + i : (size_t)i * side->nq + j;
+    for (int32_t k = op->sub_begin[b]; k < op->sub_begin[b + 1]; ++k) {
+      SubBlock s = op->subs[k];
+      if (t) { std::swap(s.r0, s.c0); std::swap(s.m, s.n); s.t = !s.t; }
+      f(s);
+    }
   }
 };
 
@@ -327,6 +368,7 @@ struct Chunk {
   GemmBatch step1, step2;
   int64_t work = 0;   // doubles of T workspace
   int nterms = 0;
+  bool zero_work = false;   // a factorised left operator writes only the row pieces it has factors for: T must start from zero
 };
 
 struct Schedule {
@@ -346,11 +388,11 @@ inline Schedule build_schedule(const Side& L, const Side& R, const PsiLayout& P,
   Schedule S;
   const int S_psi = P.dq[1];
   Chunk cur;
-  std::vector<int> group_of;     // psi block -> group index inside cur.step2, -1
+  std::map<std::pair<int, int>, int> group_of;   // (psi block, first column of the output piece) -> group index inside cur.step2
   std::vector<std::vector<GSeg>> pending;   // per group: segments (merged into contiguous ranges at chunk close)
   auto open_chunk = [&]() {
     cur = Chunk();
-    group_of.assign(P.nblocks(), -1);
+    group_of.clear();
     pending.clear();
   };
   auto close_chunk = [&]() {
@@ -425,61 +467,84 @@ inline Schedule build_schedule(const Side& L, const Side& R, const PsiLayout& P,
       }
     if (cur.nterms > 0 && cur.work + need > work_budget) { close_chunk(); open_chunk(); }
     cur.nterms++;
+    if (lop.op->factorised) cur.zero_work = true;
+    std::vector<SubBlock> lsubs;
     for (const TBlock& b : tb) {
-      const int dl = L.dims[b.lQ], dlp = L.dims[b.lQp], drp = R.dims[b.rQp];
+      const int dl = L.dims[b.lQ], drp = R.dims[b.rQp];
       const int ldt = pad_ld(drp);
       const int64_t toff = cur.work;
       cur.work += align_up((int64_t)dl * ldt, BLK_ALIGN);
       // step 1:  T = s A_L^(c)[lQ,lQ'] src[lQ',rQ']                                  (operatorfunctions.C:512-516)
-      GSeg s1;
-      std::memset(&s1, 0, sizeof(s1));
-      s1.a = (int64_t)(intptr_t)(lop.op->dev) + 8 * lop.stored_off(b.lQ, b.lQp);   // absolute byte address
-      s1.a_base = B2D_BASE_ABS;
-      s1.a_trans = lop.t ? 1 : 0;                // stored block is (lQ', lQ): k x m
-      s1.lda = lop.stored_ld(b.lQ, b.lQp);
-      int pb = P.blk[(size_t)b.lQp * P.nr + b.rQp];
-      s1.b = P.dev_off[pb]; s1.b_base = B2D_BASE_SRC; s1.b_kmajor = 0; s1.ldb = P.ld[pb];
-      s1.k = dlp;
-      s1.alpha = 1.0;                            // the left scaling (:514) is folded into the step-2 factor below
+      // A materialised operator block is ONE product; a factorised one is a product per (row piece, column piece) factor: the row
+      // pieces are the output groups, the column pieces the K segments, each reading its rows of the source block
+      const int pb = P.blk[(size_t)b.lQp * P.nr + b.rQp];
+      lsubs.clear();
+      lop.for_each_sub(b.lQ, b.lQp, [&](const SubBlock& sb) { lsubs.push_back(sb); });
+      std::stable_sort(lsubs.begin(), lsubs.end(), [](const SubBlock& x, const SubBlock& y) { return x.r0 < y.r0; });
+      for (size_t k0 = 0; k0 < lsubs.size();) {
+        size_t k1 = k0;
+        while (k1 < lsubs.size() && lsubs[k1].r0 == lsubs[k0].r0) ++k1;
+        GGroup g1;
+        std::memset(&g1, 0, sizeof(g1));
+        g1.c = toff + (int64_t)lsubs[k0].r0 * ldt; g1.c_base = B2D_BASE_WORK; g1.ldc = ldt; g1.m = lsubs[k0].m; g1.n = drp; g1.accumulate = 0;
+        g1.seg_begin = (int)cur.step1.segs.size();
+        for (size_t k = k0; k < k1; ++k) {
+          const SubBlock& sb = lsubs[k];
+          GSeg s1;
+          std::memset(&s1, 0, sizeof(s1));
+          s1.a = (int64_t)(intptr_t)sb.a;                                           // absolute byte address
+          s1.a_base = B2D_BASE_ABS;
+          s1.a_trans = sb.t ? 1 : 0;                 // stored block is k x m
+          s1.lda = sb.lda;
+          s1.b = P.dev_off[pb] + (int64_t)sb.c0 * P.ld[pb]; s1.b_base = B2D_BASE_SRC; s1.b_kmajor = 0; s1.ldb = P.ld[pb];
+          s1.k = sb.n;
+          s1.alpha = sb.alpha;                       // 1 for a materialised operator; the left scaling (:514) is folded into the step-2 factor below
+          cur.step1.segs.push_back(s1);
+          cur.step1.flops += 2.0 * sb.m * sb.n * drp;
+        }
+        g1.seg_end = (int)cur.step1.segs.size();
+        cur.step1.groups.push_back(g1);
+        k0 = k1;
+      }
       const double left_scaling = lop.scaling(am, b.lQ, b.lQp);
-      GGroup g1;
-      std::memset(&g1, 0, sizeof(g1));
-      g1.c = toff; g1.c_base = B2D_BASE_WORK; g1.ldc = ldt; g1.m = dl; g1.n = drp; g1.accumulate = 0;
-      g1.seg_begin = (int)cur.step1.segs.size(); g1.seg_end = g1.seg_begin + 1;
-      cur.step1.segs.push_back(s1);
-      cur.step1.groups.push_back(g1);
-      cur.step1.flops += 2.0 * dl * dlp * drp;
       // step 2:  dst[lQ,rQ] += F T (A_R^(c)[rQ,rQ'])^T                                 (operatorfunctions.C:517-531)
       for (int rQ : rcol[b.rQp]) {
         if (!P.allowed(b.lQ, rQ)) continue;
-        const int dr = R.dims[rQ];
         double F = t.scale * am.ninej(L.quantum(b.lQp)[1], R.quantum(b.rQp)[1], S_psi, lop.spin(), rop.spin(), opq_spin,
                                       L.quantum(b.lQ)[1], R.quantum(rQ)[1], S_psi);            // :522-524
         if (rop.fermion() && (L.quantum(b.lQp)[0] & 1)) F = -F;                                 // :528
         F *= rop.scaling(am, rQ, b.rQp);                                                        // :529
         F *= left_scaling;                                                                      // :514
-        int db = P.blk[(size_t)b.lQ * P.nr + rQ];
-        int g = group_of[db];
-        if (g < 0) {
-          g = group_of[db] = (int)cur.step2.groups.size();
-          GGroup G;
-          std::memset(&G, 0, sizeof(G));
-          G.c = P.dev_off[db]; G.c_base = B2D_BASE_DST; G.ldc = P.ld[db]; G.m = dl; G.n = dr; G.accumulate = 1;
-          cur.step2.groups.push_back(G);
-          pending.emplace_back();
-        }
-        cur.step2.flops += 2.0 * dl * drp * dr;
-        if (F == 0.0) continue;                    // a vanishing recoupling coefficient contributes nothing
-        GSeg s2;
-        std::memset(&s2, 0, sizeof(s2));
-        s2.a = toff; s2.a_base = B2D_BASE_WORK; s2.a_trans = 0; s2.lda = ldt;
-        s2.b = (int64_t)(intptr_t)(rop.op->dev) + 8 * rop.stored_off(rQ, b.rQp);
-        s2.b_base = B2D_BASE_ABS;
-        s2.b_kmajor = rop.t ? 0 : 1;               // plain: stored (rQ,rQ') is n x k; view: stored (rQ',rQ) is k x n
-        s2.ldb = rop.stored_ld(rQ, b.rQp);
-        s2.k = drp;
-        s2.alpha = F;
-        pending[g].push_back(s2);
+        const int db = P.blk[(size_t)b.lQ * P.nr + rQ];
+        rop.for_each_sub(rQ, b.rQp, [&](const SubBlock& sb) {
+          // the rows [r0, r0 + m) of A_R[rQ,rQ'] are the COLUMNS [r0, r0 + m) of the destination block, its columns [c0, c0 + n) the
+          // columns of T this factor contracts
+          auto key = std::make_pair(db, (int)sb.r0);
+          auto it = group_of.find(key);
+          int g;
+          if (it == group_of.end()) {
+            g = (int)cur.step2.groups.size();
+            group_of.emplace(key, g);
+            GGroup G;
+            std::memset(&G, 0, sizeof(G));
+            G.c = P.dev_off[db] + sb.r0; G.c_base = B2D_BASE_DST; G.ldc = P.ld[db]; G.m = dl; G.n = sb.m; G.accumulate = 1;
+            cur.step2.groups.push_back(G);
+            pending.emplace_back();
+          } else g = it->second;
+          cur.step2.flops += 2.0 * dl * sb.n * sb.m;
+          const double Fa = F * sb.alpha;
+          if (Fa == 0.0) return;                     // a vanishing recoupling coefficient contributes nothing
+          GSeg s2;
+          std::memset(&s2, 0, sizeof(s2));
+          s2.a = toff + sb.c0; s2.a_base = B2D_BASE_WORK; s2.a_trans = 0; s2.lda = ldt;
+          s2.b = (int64_t)(intptr_t)sb.a;
+          s2.b_base = B2D_BASE_ABS;
+          s2.b_kmajor = sb.t ? 0 : 1;                // plain: stored block is n x k; transposed: stored k x n
+          s2.ldb = sb.lda;
+          s2.k = sb.n;
+          s2.alpha = Fa;
+          pending[g].push_back(s2);
+        });
       }
     }
   }
@@ -501,12 +566,11 @@ inline double add_one_op_groups(const Side& L, const Side& R, const PsiLayout& P
   View a{&S, &op, transposed};
   const int Sc = Ps.dq[1], Sv = Pd.dq[1];
   double flops = 0.0;
+  struct Item { SubBlock sb; double fac; int ps; };
+  std::vector<Item> items;
   for (int p = 0; p < Pd.nblocks(); ++p) {
     const int lQ = Pd.bl[p], rQ = Pd.br[p];
-    GGroup G;
-    std::memset(&G, 0, sizeof(G));
-    G.c = dst_off + Pd.dev_off[p]; G.c_base = dst_base; G.ldc = Pd.ld[p]; G.m = Pd.rows[p]; G.n = Pd.cols[p]; G.accumulate = 1;
-    G.seg_begin = (int)batch.segs.size();
+    items.clear();
     if (side == 0) {
       for (int lQp = 0; lQp < L.nq; ++lQp) {                                              // :347-366
         if (!a.allowed(lQ, lQp) || !Ps.allowed(lQp, rQ)) continue;
@@ -515,12 +579,7 @@ inline double add_one_op_groups(const Side& L, const Side& R, const PsiLayout& P
         flops += 2.0 * L.dims[lQ] * L.dims[lQp] * R.dims[rQ];
         if (fac == 0.0) continue;
         const int ps = Ps.blk[(size_t)lQp * Ps.nr + rQ];
-        GSeg sg;
-        std::memset(&sg, 0, sizeof(sg));
-        sg.a = (int64_t)(intptr_t)op.dev + 8 * a.stored_off(lQ, lQp); sg.a_base = B2D_BASE_ABS; sg.a_trans = transposed ? 1 : 0; sg.lda = a.stored_ld(lQ, lQp);
-        sg.b = src_off + Ps.dev_off[ps]; sg.b_base = src_base; sg.b_kmajor = 0; sg.ldb = Ps.ld[ps];
-        sg.k = L.dims[lQp]; sg.alpha = fac;
-        batch.segs.push_back(sg);
+        a.for_each_sub(lQ, lQp, [&](const SubBlock& sb) { items.push_back(Item{sb, fac, ps}); });
       }
     } else {
       for (int rQp = 0; rQp < R.nq; ++rQp) {                                              // :378-397
@@ -531,16 +590,43 @@ inline double add_one_op_groups(const Side& L, const Side& R, const PsiLayout& P
         flops += 2.0 * L.dims[lQ] * R.dims[rQp] * R.dims[rQ];
         if (fac == 0.0) continue;
         const int ps = Ps.blk[(size_t)lQ * Ps.nr + rQp];
-        GSeg sg;
-        std::memset(&sg, 0, sizeof(sg));
-        sg.a = src_off + Ps.dev_off[ps]; sg.a_base = src_base; sg.a_trans = 0; sg.lda = Ps.ld[ps];
-        sg.b = (int64_t)(intptr_t)op.dev + 8 * a.stored_off(rQ, rQp); sg.b_base = B2D_BASE_ABS; sg.b_kmajor = transposed ? 0 : 1; sg.ldb = a.stored_ld(rQ, rQp);
-        sg.k = R.dims[rQp]; sg.alpha = fac;
-        batch.segs.push_back(sg);
+        a.for_each_sub(rQ, rQp, [&](const SubBlock& sb) { items.push_back(Item{sb, fac, ps}); });
       }
     }
-    G.seg_end = (int)batch.segs.size();
-    if (G.seg_end > G.seg_begin) batch.groups.push_back(G);
+    // one group per output piece (rows r0.. of the destination block for a left operator, columns r0.. for a right operator);
+    // a materialised operator has the single piece r0 = 0
+    std::stable_sort(items.begin(), items.end(), [](const Item& x, const Item& y) { return x.sb.r0 < y.sb.r0; });
+    for (size_t k0 = 0; k0 < items.size();) {
+      size_t k1 = k0;
+      while (k1 < items.size() && items[k1].sb.r0 == items[k0].sb.r0) ++k1;
+      const SubBlock& first = items[k0].sb;
+      GGroup G;
+      std::memset(&G, 0, sizeof(G));
+      G.c_base = dst_base; G.ldc = Pd.ld[p]; G.accumulate = 1;
+      if (side == 0) { G.c = dst_off + Pd.dev_off[p] + (int64_t)first.r0 * Pd.ld[p]; G.m = first.m; G.n = Pd.cols[p]; }
+      else { G.c = dst_off + Pd.dev_off[p] + first.r0; G.m = Pd.rows[p]; G.n = first.m; }
+      G.seg_begin = (int)batch.segs.size();
+      for (size_t k = k0; k < k1; ++k) {
+        const SubBlock& sb = items[k].sb;
+        const int ps = items[k].ps;
+        const double f = items[k].fac * sb.alpha;
+        if (f == 0.0) continue;
+        GSeg sg;
+        std::memset(&sg, 0, sizeof(sg));
+        if (side == 0) {
+          sg.a = (int64_t)(intptr_t)sb.a; sg.a_base = B2D_BASE_ABS; sg.a_trans = sb.t ? 1 : 0; sg.lda = sb.lda;
+          sg.b = src_off + Ps.dev_off[ps] + (int64_t)sb.c0 * Ps.ld[ps]; sg.b_base = src_base; sg.b_kmajor = 0; sg.ldb = Ps.ld[ps];
+        } else {
+          sg.a = src_off + Ps.dev_off[ps] + sb.c0; sg.a_base = src_base; sg.a_trans = 0; sg.lda = Ps.ld[ps];
+          sg.b = (int64_t)(intptr_t)sb.a; sg.b_base = B2D_BASE_ABS; sg.b_kmajor = sb.t ? 0 : 1; sg.ldb = sb.lda;
+        }
+        sg.k = sb.n; sg.alpha = f;
+        batch.segs.push_back(sg);
+      }
+      G.seg_end = (int)batch.segs.size();
+      if (G.seg_end > G.seg_begin) batch.groups.push_back(G);
+      k0 = k1;
+    }
   }
   return flops;
 }
@@ -563,13 +649,44 @@ inline void add_density_segments(const PsiLayout& P, uint8_t base, int64_t off, 
 // ---------------------------------------------------------------------------------------------------------------
 // diag(H)
 // ---------------------------------------------------------------------------------------------------------------
+// `regions` receives one BlockDesc per (psi block, row piece, column piece) - the whole block when neither child is a product of
+// factorised operators -, `region_begin` the task range of each.  dev_off / ld address the region inside the padded wavefunction.
 inline void build_diag_tasks(const Side& L, const Side& R, const PsiLayout& P, const std::vector<Term>& terms, double core_energy,
-                             bool hubbard, AngMom& am, std::vector<DiagTask>& tasks, std::vector<int>& block_begin) {
+                             bool hubbard, AngMom& am, std::vector<DiagTask>& tasks, std::vector<int>& region_begin, std::vector<BlockDesc>& regions) {
   // per psi block: list of (f, diagA, diagB).  The term list of diagonalH mirrors multiplyH's with the *_d functors
   // (opxop.C:295-365): same operator pairs, scale 1 for c x ccd, `factor` (no parity) for cc x dd; H and e_core by trace.
   (void)hubbard;
   const int S_psi = P.dq[1];
-  std::vector<std::vector<DiagTask>> per(P.nblocks());
+  auto pieces_of = [](const Side& s, int q) {
+    if ((int)s.pieces.size() == s.nq && !s.pieces[q].empty()) return s.pieces[q];
+    return std::vector<std::pair<int, int>>(1, std::make_pair(0, s.dims[q]));
+  };
+  regions.clear();
+  std::vector<int> first_region(P.nblocks() + 1, 0);
+  std::vector<std::pair<int, int>> rp_of, cp_of;   // per region: row piece, column piece (offset, size)
+  for (int p = 0; p < P.nblocks(); ++p) {
+    first_region[p] = (int)regions.size();
+    for (const auto& rp : pieces_of(L, P.bl[p]))
+      for (const auto& cp : pieces_of(R, P.br[p])) {
+        BlockDesc d;
+        d.ref_off = 0; d.dev_off = P.dev_off[p] + (int64_t)rp.first * P.ld[p] + cp.first; d.rows = rp.second; d.cols = cp.second; d.ld = P.ld[p]; d.pad = 0;
+        regions.push_back(d);
+        rp_of.push_back(rp); cp_of.push_back(cp);
+      }
+  }
+  first_region[P.nblocks()] = (int)regions.size();
+  std::vector<std::vector<DiagTask>> per(regions.size());
+  struct DiagRef { int64_t addr; int stride; double alpha; };
+  // diagonal of view block (q,q) restricted to the piece [o, o + n): the factors whose sub-block lies on the block diagonal and covers it
+  auto diag_refs = [&](const View& v, int q, const std::pair<int, int>& piece, std::vector<DiagRef>& out) {
+    out.clear();
+    v.for_each_sub(q, q, [&](const SubBlock& sb) {
+      if (sb.r0 != sb.c0 || sb.m != sb.n) return;
+      if (piece.first < sb.r0 || piece.first + piece.second > sb.r0 + sb.m) return;
+      out.push_back(DiagRef{(int64_t)(intptr_t)sb.a + 8 * (int64_t)(piece.first - sb.r0) * (sb.lda + 1), sb.lda + 1, sb.alpha});
+    });
+  };
+  std::vector<DiagRef> da, db;
   auto add = [&](const Term& t, double scale, bool left_only, bool right_only) {
     View a{&L, &L.ops[t.lop], t.lt}, b{&R, &R.ops[t.rop], t.rt};
     for (int p = 0; p < P.nblocks(); ++p) {
@@ -580,12 +697,19 @@ inline void build_diag_tasks(const Side& L, const Side& R, const PsiLayout& P, c
       int sa = right_only ? 0 : a.spin(), sb = left_only ? 0 : b.spin();
       double f = scale * am.ninej(L.quantum(l)[1], R.quantum(r)[1], S_psi, sa, sb, 0, L.quantum(l)[1], R.quantum(r)[1], S_psi);
       if (!left_only && b.fermion() && (L.quantum(l)[0] & 1)) f = -f;
-      DiagTask d;
-      std::memset(&d, 0, sizeof(d));
-      d.f = f;
-      if (!right_only) { d.a = (int64_t)(intptr_t)a.op->dev + 8 * a.stored_off(l, l); d.sa = a.stored_ld(l, l) + 1; }
-      if (!left_only) { d.b = (int64_t)(intptr_t)b.op->dev + 8 * b.stored_off(r, r); d.sb = b.stored_ld(r, r) + 1; }
-      per[p].push_back(d);
+      for (int g = first_region[p]; g < first_region[p + 1]; ++g) {
+        if (!right_only) diag_refs(a, l, rp_of[g], da); else da.assign(1, DiagRef{0, 0, 1.0});
+        if (!left_only) diag_refs(b, r, cp_of[g], db); else db.assign(1, DiagRef{0, 0, 1.0});
+        for (const DiagRef& x : da)
+          for (const DiagRef& y : db) {
+            DiagTask d;
+            std::memset(&d, 0, sizeof(d));
+            d.f = f * x.alpha * y.alpha;
+            d.a = x.addr; d.sa = x.stride;
+            d.b = y.addr; d.sb = y.stride;
+            if (d.f != 0.0) per[g].push_back(d);
+          }
+      }
     }
   };
   // `terms` is (this rank's share of) enumerate_terms() output; under a term partition every rank adds its own
@@ -606,18 +730,18 @@ inline void build_diag_tasks(const Side& L, const Side& R, const PsiLayout& P, c
     add(t, scale, false, false);
   }
   tasks.clear();
-  block_begin.assign(P.nblocks() + 1, 0);
-  for (int p = 0; p < P.nblocks(); ++p) {
-    block_begin[p] = (int)tasks.size();
+  region_begin.assign(regions.size() + 1, 0);
+  for (size_t g = 0; g < regions.size(); ++g) {
+    region_begin[g] = (int)tasks.size();
     if (have_core && core_energy != 0.0) {
       DiagTask d;
       std::memset(&d, 0, sizeof(d));
       d.f = core_energy;
       tasks.push_back(d);
     }
-    tasks.insert(tasks.end(), per[p].begin(), per[p].end());
+    tasks.insert(tasks.end(), per[g].begin(), per[g].end());
   }
-  block_begin[P.nblocks()] = (int)tasks.size();
+  region_begin[regions.size()] = (int)tasks.size();
 }
 
 // ---------------------------------------------------------------------------------------------------------------

@@ -70,6 +70,68 @@ class SpinBlock:
             self._ck(self.lib.b2d_set_option(self._ctx, k.encode(), float(v)))
         self._describe(left, right, psi_dq, core_energy, hubbard, norbs, rank, nranks)
 
+    @classmethod
+    def from_products(cls, left_parts, right_parts, psi_dq, core_energy=0.0, hubbard=False, norbs=None, device=0, rank=0, nranks=1, options=None,
+                      integrals=None, fill_seed=20260):
+        """The big block of a two-dot step from the blocks a sweep actually holds: each child is (renormalised block) x (one-site dot),
+        given as (child BlockSpec, dot BlockSpec, product tables, BlockSpec of the enlarged block: sectors + operator list).  Every
+        operator of the enlarged blocks is built on the device from the grandchildren (b2d_build_enlarged_op) - as factor lists with
+        option "factorised", by the scatter kernel otherwise -, the blocks are parked (b2d_stash_product) and assembled.  Grandchild
+        operators without data are allocated and filled with the counter-based random stream (synthetic benchmark)."""
+        self = cls.__new__(cls)
+        self.lib = _lib.load()
+        self._ctx = C.c_void_p()
+        if self.lib.b2d_create(int(device), C.byref(self._ctx)):
+            raise B2DError("b2d_create: " + self.lib.b2d_last_error(None).decode())
+        self.device = device
+        for k, v in (options or {}).items():
+            self._ck(self.lib.b2d_set_option(self._ctx, k.encode(), float(v)))
+        if integrals is not None:
+            v1, v2, irr = (np.ascontiguousarray(integrals[0], np.float64), np.ascontiguousarray(integrals[1], np.float64), np.ascontiguousarray(integrals[2], np.int32))
+            self._ck(self.lib.b2d_set_integrals(self._ctx, len(irr), _p(v1, _lib.c_f64p), _p(v2, _lib.c_f64p), _p(irr, _lib.c_i32p), 1e-15, 1e-15))
+        self.op_ids = [[], []]
+        enlarged = []
+        for slot, (child, dot, tables, big) in enumerate((left_parts, right_parts)):
+            for side, blk in enumerate((child, dot)):
+                q = np.ascontiguousarray(blk.q, dtype=np.int32).reshape(-1, 3)
+                dims = np.ascontiguousarray(blk.dims, dtype=np.int32)
+                sites = np.ascontiguousarray(blk.sites, dtype=np.int32)
+                self._ck(self.lib.b2d_set_block(self._ctx, side, len(dims), _p(q, _lib.c_i32p), _p(dims, _lib.c_i32p), int(blk.loop), len(sites), _p(sites, _lib.c_i32p)))
+                ids = [self._add_op(side, op) for op in blk.ops]
+                if device >= 0 and any(op.data is None for op in blk.ops):
+                    self._ck(self.lib.b2d_alloc_ops(self._ctx, side))
+                    amp = 1.0 / float(np.sqrt(np.sum(dims)))
+                    for k, op in enumerate(blk.ops):
+                        if op.data is None:
+                            self._ck(self.lib.b2d_fill_op_random(self._ctx, side, ids[k], int(fill_seed) * 1000003 + slot * 500009 + side * 250007 + k, amp, 0))
+            tq = np.ascontiguousarray(tables["q"], np.int32).reshape(-1, 3)
+            td = np.ascontiguousarray(tables["dims"], np.int32)
+            lm, rm, ud = (np.ascontiguousarray(tables[k], np.int32) for k in ("unc.lmap", "unc.rmap", "unc.dims"))
+            ob, on = np.ascontiguousarray(tables["old_to_new_begin"], np.int32), np.ascontiguousarray(tables["old_to_new"], np.int32)
+            self._ck(self.lib.b2d_set_product_stateinfo(self._ctx, len(td), _p(tq, _lib.c_i32p), _p(td, _lib.c_i32p), len(ud), _p(lm, _lib.c_i32p),
+                                                         _p(rm, _lib.c_i32p), _p(ud, _lib.c_i32p), _p(ob, _lib.c_i32p), _p(on, _lib.c_i32p)))
+            assert np.array_equal(tq, np.asarray(big.q, np.int32).reshape(-1, 3)) and np.array_equal(td, np.asarray(big.dims, np.int32))
+            for op in big.ops:
+                o = np.asarray(list(op.orbs) + [-1, -1], dtype=np.int32)
+                dq = np.asarray(op.dq, dtype=np.int32)
+                pid = C.c_int(-1)
+                self._ck(self.lib.b2d_build_enlarged_op(self._ctx, int(op.optype), len(op.orbs), _p(o, _lib.c_i32p), int(op.comp), _p(dq, _lib.c_i32p),
+                                                        int(bool(op.fermion)), int(bool(hubbard)), C.byref(pid)))
+                self.op_ids[slot].append(pid.value)
+            sites = np.ascontiguousarray(big.sites, dtype=np.int32)
+            self._ck(self.lib.b2d_stash_product(self._ctx, slot, int(big.loop), len(sites), _p(sites, _lib.c_i32p)))
+            enlarged.append(big)
+        self._ck(self.lib.b2d_assemble_big(self._ctx))
+        self.left, self.right = enlarged
+        if norbs is None:
+            norbs = len(self.left.sites) + len(self.right.sites)
+        dq = np.asarray(psi_dq, dtype=np.int32)
+        self._ck(self.lib.b2d_plan(self._ctx, _p(dq, _lib.c_i32p), float(core_energy), int(bool(hubbard)), int(norbs), int(rank), int(nranks)))
+        self.size = int(self.lib.b2d_psi_size(self._ctx))
+        self.rank, self.nranks = rank, nranks
+        self._nslots = 0
+        return self
+
     def reset(self, left: BlockSpec, right: BlockSpec, psi_dq, core_energy=0.0, hubbard=False, norbs=None, rank=0, nranks=1):
         """b2d_reset + a new block description on the SAME context (streams, arena slabs and scratch buffers are kept): what a
         sweep does between block iterations."""
@@ -179,10 +241,10 @@ class SpinBlock:
         return float(self.lib.b2d_sigma_flops(self._ctx, int(all_ranks)))
 
     def plan_stats(self):
-        out = np.zeros(10)
-        self._ck(self.lib.b2d_plan_stats(self._ctx, _p(out, _lib.c_f64p), 10))
+        out = np.zeros(13)
+        self._ck(self.lib.b2d_plan_stats(self._ctx, _p(out, _lib.c_f64p), 13))
         keys = ["chunks", "step1_contractions", "step2_segments", "tiles", "workspace_doubles", "arena_doubles", "launches_per_sigma", "flops_executed",
-                "flops_in_tiles", "flops_issued"]
+                "flops_in_tiles", "flops_issued", "combo_doubles", "factors_direct", "factors_combo"]
         return dict(zip(keys, out.tolist()))
 
     # -- the reference's entry points ---------------------------------------------------------------------------
@@ -406,11 +468,13 @@ class ProductBlock:
     """Construction of the operators of an ENLARGED block (left child x right child) on the device: the TensorProduct / TensorTrace
     scatter of operatorfunctions.C:19-254 (first device step).  The caller decides which products enter an operator."""
 
-    def __init__(self, left: BlockSpec, right: BlockSpec, q, dims, lmap, rmap, unc_dims, old_to_new, device=0):
+    def __init__(self, left: BlockSpec, right: BlockSpec, q, dims, lmap, rmap, unc_dims, old_to_new, device=0, options=None):
         self.lib = _lib.load()
         self._ctx = C.c_void_p()
         if self.lib.b2d_create(int(device), C.byref(self._ctx)):
             raise B2DError("b2d_create: " + self.lib.b2d_last_error(None).decode())
+        for k, v in (options or {}).items():
+            self._ck(self.lib.b2d_set_option(self._ctx, k.encode(), float(v)))
         self.op_ids = [[], []]
         for side, blk in enumerate((left, right)):
             bq = np.ascontiguousarray(blk.q, dtype=np.int32).reshape(-1, 3)

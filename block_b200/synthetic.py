@@ -252,3 +252,81 @@ def make_opbuild_case(norbs=40, nelec=40, M=4000, left_sites=None, op_sites=6, o
     L = rng.standard_normal((norbs * norbs, 4)) * 0.1
     h2 = (L @ L.T).reshape(norbs, norbs, norbs, norbs)
     return left, dot, enlarged.ops, pt, h1, h2
+
+
+# ---- the same big block with FACTORISED enlarged-block operators (SURVEY.md 7 "hard parts"; option "factorised") ------------------------
+def make_child(sectors, sites, ccd_sites, normal, comp_pairs, loop):
+    """A child of an enlarged block with the operator arrays the construction of its parent reads: HAM, OVERLAP, CRE_i (own sites),
+    CRE_CRE_DESCOMP_i (ccd_sites), CRE_DES / CRE_CRE for its own site pairs (normal) and CRE_DESCOMP / DES_DESCOMP for comp_pairs."""
+    q = np.array([[N, s, 0] for (N, s) in sectors], dtype=np.int32)
+    dims = np.array(list(sectors.values()), dtype=np.int32)
+    blk = BlockSpec(q=q, dims=dims, sites=tuple(sites), loop=loop)
+    blk.ops.append(_op(q, HAM, (), 0, (0, 0, 0), False))
+    ovl = _op(q, OVERLAP, (), 0, (0, 0, 0), False)
+    ovl.data = np.concatenate([np.eye(int(d)).ravel() for d in dims])
+    blk.ops.append(ovl)
+    for i in sites:
+        blk.ops.append(_op(q, CRE, (i,), 0, (1, 1, 0), True))
+    for i in ccd_sites:
+        blk.ops.append(_op(q, CRE_CRE_DESCOMP, (i,), 0, (1, 1, 0), True))
+    if normal:
+        for a, i in enumerate(sites):
+            for j in sites[:a + 1]:
+                for comp, s in ((0, 0), (1, 2)):
+                    blk.ops.append(_op(q, CRE_DES, (i, j), comp, (0, s, 0), False))
+                    blk.ops.append(_op(q, CRE_CRE, (i, j), comp, (2, s, 0), False))
+    for (i, j) in comp_pairs:
+        assert i >= j
+        for comp, s in ((0, 0), (1, 2)):
+            blk.ops.append(_op(q, CRE_DESCOMP, (i, j), comp, (0, s, 0), False))
+            blk.ops.append(_op(q, DES_DESCOMP, (i, j), comp, (-2, s, 0), False))
+    return blk
+
+
+def make_product_case(norbs=40, nelec=40, M=4000, left_sites=None, seed=20260, sigma_n=2.2, sigma_s=1.6):
+    """Both children of the big block of make_big_block as PRODUCTS (renormalised M-state block) x (one site), described by THEIR children:
+    what a sweep holds in memory before the reference's Op::build (or b2d_build_enlarged_op) constructs the enlarged operators.
+    Returns dict(left=(child, dot, tables, enlarged), right=(...), h1, h2, dq); operator values are seeded random numbers: the dots get host
+    data (their 1 x 1 elements become factors), the M-state children are filled on the device."""
+    nl = norbs // 2 if left_sites is None else left_sites
+    f = nelec / norbs
+    lsites, rsites = list(range(nl)), list(range(nl, norbs))
+    s_sites, d_l = lsites[:-1], lsites[-1]          # S' and the system dot
+    d_r, e_sites = rsites[0], rsites[1:]            # environment dot and E'
+    sys = renormalised_sectors(len(s_sites), f * len(s_sites), M, sigma_n, sigma_s)
+    env = renormalised_sectors(len(e_sites), f * len(e_sites), M, sigma_n, sigma_s)
+    dot = {(0, 0): 1, (1, 1): 1, (2, 0): 1}
+    rng = np.random.default_rng(seed)
+
+    def pairs(a):   # i >= j over a sorted list
+        a = sorted(a)
+        return [(i, j) for k, i in enumerate(a) for j in a[:k + 1]]
+    # system side (normal two-index operators): S' needs the complementary operators that carry the dot index, the dot everything
+    s_child = make_child(sys, s_sites, [d_l] + rsites, True, [(I, d_l) for I in rsites] + [(d_l, d_l)], loop=False)
+    l_dot = make_child(dot, [d_l], s_sites + rsites, True, [(I, j) for j in s_sites for I in rsites], loop=True)
+    # environment side (complementary two-index operators for the pairs of the left block)
+    e_child = make_child(env, e_sites, lsites + [d_r], False, pairs(lsites + [d_r]), loop=False)
+    r_dot = make_child(dot, [d_r], lsites + e_sites, True, pairs(lsites) + [(j, I) for j in e_sites for I in lsites], loop=True)
+    for blk in (l_dot, r_dot):
+        dims = blk.dims.astype(np.int64)
+        for op in blk.ops:
+            if op.data is None:
+                n = int((op.allowed.astype(np.int64) * np.outer(dims, dims)).sum())
+                op.data = rng.standard_normal(n) * 0.3
+    lt = product_tables(list(sys), np.array(list(sys.values()), np.int32))
+    rt = product_tables(list(env), np.array(list(env.values()), np.int32))
+    left = make_block({(int(k[0]), int(k[1])): int(d) for k, d in zip(lt["q"], lt["dims"])}, lsites, rsites, loop=True)
+    right = make_block({(int(k[0]), int(k[1])): int(d) for k, d in zip(rt["q"], rt["dims"])}, rsites, lsites, loop=False)
+    h1 = rng.standard_normal((norbs, norbs)); h1 = h1 + h1.T
+    Lc = rng.standard_normal((norbs * norbs, 4)) * 0.1
+    h2 = (Lc @ Lc.T).reshape(norbs, norbs, norbs, norbs)
+    return dict(left=(s_child, l_dot, lt, left), right=(e_child, r_dot, rt, right), h1=h1, h2=h2, dq=(nelec, 0, 0), norbs=norbs, seed=seed)
+
+
+def make_big_block_from_products(case, device=0, options=None, factorised=True):
+    """SpinBlock whose two children are built ON THE DEVICE from the case's grandchildren: factorised (no enlarged operator is ever
+    materialised) or, for comparison at small M, materialised by the scatter kernel."""
+    opts = dict(options or {})
+    opts["factorised"] = 1 if factorised else 0
+    return SpinBlock.from_products(case["left"], case["right"], case["dq"], norbs=case["norbs"], device=device, options=opts,
+                                   integrals=(case["h1"], case["h2"], np.zeros(case["norbs"], np.int32)), fill_seed=case["seed"])

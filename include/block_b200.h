@@ -56,13 +56,18 @@ void b2d_destroy(b2d_ctx* ctx);
  * context and resets it between block iterations (the reference builds a new `big` SpinBlock per block iteration, sweep.C:182). */
 int b2d_reset(b2d_ctx* ctx);
 const char* b2d_last_error(const b2d_ctx* ctx);   /* ctx may be NULL: last error of a failed b2d_create */
-int b2d_abi_version(void);                        /* 3 */
+int b2d_abi_version(void);                        /* 4 */
 
 /* Tuning knobs (all optional): "workspace_mb" (T workspace for the two-step contraction), "max_davidson_iter",
  * "tile_class" (debug: -1 auto, 0/1/2 = square 128/64/32 DMMA tiles everywhere, 3 = auto with the tiny-sector warp kernel,
  * which auto already uses), "sync_debug", "phase_timing", "opbuild_batch" (b2d_build_enlarged_op defers its scatter tasks and
  * b2d_stash_product / b2d_product_op_download run them for the whole block, one launch per round instead of one per product; same
- * summation order, default off until measured). */
+ * summation order; default on), "factorised" (operators of an enlarged block whose right child is a one-site dot are NOT materialised:
+ * b2d_build_enlarged_op / b2d_product_op_accumulate record, per sector block, the list of scaled sub-blocks of the renormalised child's
+ * operators - operatorfunctions.C:188-250 rowstride / colstride structure - and sigma, diag(H), the noise products and the operator
+ * rotation contract those factors directly: ~16x less operator memory, no flops on the structural zeros of the Kronecker blocks),
+ * "eig_jacobi_max" (largest sector for the single-CTA Jacobi kernel, default 64; larger sectors use the block Jacobi kernel),
+ * "eig_cusolver" (diagnostic: cusolverDnDsyevd for the large sectors, never the default). */
 int b2d_set_option(b2d_ctx* ctx, const char* key, double value);
 
 /* ---- block description: replaces the host-side SpinBlock / StateInfo / Op_component objects ---------------- */
@@ -89,6 +94,10 @@ int b2d_add_op_blocks(b2d_ctx* ctx, int side, int optype, int norb, const int32_
 /* Synthetic-benchmark helper: fill an operator's device blocks with a counter-based uniform(-a,a) stream; if
  * symmetric != 0 the operator is made self-adjoint in the reduced-matrix-element sense (needs dq = (0,0,0)). */
 int b2d_fill_op_random(b2d_ctx* ctx, int side, int op_id, uint64_t seed, double amplitude, int symmetric);
+
+/* Allocate (zero-filled) every operator of a side that was added with data == NULL: needed for the children of a product block
+ * (b2d_set_product_stateinfo), which never go through b2d_plan. */
+int b2d_alloc_ops(b2d_ctx* ctx, int side);
 
 /* Copy an operator's blocks back in the host layout of b2d_add_op. */
 int b2d_download_op(b2d_ctx* ctx, int side, int op_id, double* data);
@@ -119,7 +128,8 @@ int b2d_terms(const b2d_ctx* ctx, int all_ranks, int32_t* left_op, int32_t* righ
 double b2d_sigma_flops(const b2d_ctx* ctx, int all_ranks);
 /* schedule statistics: out[0]=#chunks, [1]=#step-1 contractions, [2]=#step-2 segments, [3]=#sigma tiles,
  * [4]=workspace doubles, [5]=operator arena doubles, [6]=kernel launches per sigma, [7]=flops executed,
- * [8]=useful flops inside tiles, [9]=flops the tiles issue including ragged-edge padding */
+ * [8]=useful flops inside tiles, [9]=flops the tiles issue including ragged-edge padding, [10]=doubles of pre-summed factor blocks
+ * ("combos") of factorised operators, [11]=factors that point straight at a child operator's block, [12]=factors that point at a combo */
 int b2d_plan_stats(const b2d_ctx* ctx, double* out, int n);
 
 /* ---- device-resident wavefunction slots ------------------------------------------------------------------- */
@@ -370,6 +380,25 @@ int64_t b2d_guess_plan_export(const b2d_ctx* ctx, int what, void* out, int64_t c
  * (needs b2d_plan with the same children and target quantum: the layouts must be identical) ready for b2d_davidson, nothing
  * returns to the host; trial != NULL: it is (also) downloaded in FlattenInto order. */
 int b2d_guess_transform(b2d_ctx* ctx, const double* old_wave, const double* left_rot, const double* right_rot, int dst_slot, double* trial);
+
+/* ---- device-side shadow of the scratch files --------------------------------------------------
+ * The reference writes every renormalised block to a scratch file (SpinBlock::store, save_load_block.C:23-64, called at sweep.C:466) and
+ * reads the environment block back (SpinBlock::restore :66-108, initblocks.C:279-288) each block iteration.  Here the renormalised
+ * operators never leave the GPU: b2d_cache_put_rotated keeps the block b2d_transform_operators just produced under a token (the buffer
+ * changes owner, nothing is copied); b2d_cache_use makes a cached block child `side` of the next product (b2d_set_product_stateinfo) or
+ * big block (b2d_plan) in place of b2d_set_block + b2d_add_op.  The binding stores the token where the reference stores the matrices (see
+ * INTEGRATION.md), so it travels through the reference's own store / restore / copies.  Device memory beyond "cache_device_mb" (option,
+ * default 32 GB) spills to pinned host memory.  b2d_cache_download_op returns an operator in the host layout of b2d_add_op when a host
+ * code path needs the matrices after all; entries live until b2d_cache_drop / b2d_destroy (b2d_reset keeps them). */
+int b2d_cache_put_rotated(b2d_ctx* ctx, uint64_t* token);
+int b2d_cache_use(b2d_ctx* ctx, uint64_t token, int side, int is_loop);
+int b2d_cache_block_info(const b2d_ctx* ctx, uint64_t token, int32_t* nq, int32_t* nops, int32_t* nsites);
+int b2d_cache_block_sectors(const b2d_ctx* ctx, uint64_t token, int32_t* q, int32_t* dims, int32_t* sites);
+int b2d_cache_op_info(const b2d_ctx* ctx, uint64_t token, int op_id, int32_t* optype, int32_t* norb, int32_t* orbs, int32_t* comp, int64_t* packed_size);
+int b2d_cache_download_op(b2d_ctx* ctx, uint64_t token, int op_id, uint8_t* allowed, double* data);
+int b2d_cache_drop(b2d_ctx* ctx, uint64_t token);
+/* out[0..4] = {entries, doubles held on the device, doubles spilled to pinned host memory, puts, uses} */
+int b2d_cache_stats(const b2d_ctx* ctx, double* out, int n);
 
 /* ---- multi-GPU: partition of operator terms, NCCL all-reduce of the partial sigma --------------------------- */
 

@@ -32,6 +32,11 @@
 //                         (SURVEY N2);  "host": the reference's Op::build constructs it on the CPU and it is uploaded
 //   B2D_DROPIN_GUESS      "device" (default): TRANSFORM / TRANSPOSE guesses (GuessWave::transform_previous_wavefunction and its one-dot /
 //                         transpose forms) are computed on the GPU (b2d_guess_plan + b2d_guess_transform);  "host": the reference's own
+//   B2D_DROPIN_CACHE      "device" (default): renormalised blocks stay on the GPU between block iterations (b2d_cache_*); the host copy
+//                         the reference keeps (and writes to its scratch files) holds zeros and, in the first element of every sector block, a
+//                         NaN-boxed token that names the device entry - it travels through the reference's own copies / store / restore.
+//                         "host": every renormalised operator is downloaded after the rotation and uploaded again (round-1 behaviour; needed
+//                         for restartable scratch files).  Check mode and state-specific runs always use "host".
 //   B2D_DROPIN_EIG        "host": diagnostic - the density-matrix eigen-decomposition and state selection stay with the reference
 //                         (dsyev_), everything else on the GPU: separates eigenvector non-uniqueness from arithmetic differences
 //   B2D_DROPIN_OPTIONS    "key=value,..." library options (b2d_set_option), e.g. eig_jacobi_max=512
@@ -82,6 +87,43 @@ bool env_on(const char* k) { const char* v = getenv(k); return v && *v && strcmp
 
 struct OpRef { SparseMatrix* elem; int id; };
 
+// ---- token that names a device-resident block inside the reference's host copy --------------------------------------
+// A quiet NaN with a recognisable payload: anything on the host that consumed the "matrices" numerically would turn into NaN and fail
+// loudly instead of silently using zeros.
+const uint64_t TOKEN_MAGIC = 0x7FF8B2Dull;                   // bits 63..36 (28 bits): exponent all ones + quiet bit + a recognisable payload
+double token_to_double(uint64_t id) { uint64_t b = (TOKEN_MAGIC << 36) | (id & 0xFFFFFFFFFull); double d; memcpy(&d, &b, 8); return d; }
+bool double_to_token(double d, uint64_t* id) { uint64_t b; memcpy(&b, &d, 8); if ((b >> 36) != TOKEN_MAGIC) return false; *id = b & 0xFFFFFFFFFull; return true; }
+bool cache_enabled() {
+  const char* v = getenv("B2D_DROPIN_CACHE");
+  if (v && string(v) == "host") return false;
+  if (getenv("B2D_DROPIN_CHECK") && strcmp(getenv("B2D_DROPIN_CHECK"), "0") != 0) return false;   // check mode compares real host matrices
+  if (dmrginp.setStateSpecific()) return false;               // several blocks with the same sites (one per state)
+  if (!dmrginp.direct()) return false;                        // non-direct mode builds every enlarged operator from the host copies
+  return true;
+}
+std::map<vector<int>, uint64_t> g_latest_token;               // sites of a renormalised block -> its newest device entry (older ones are dropped)
+
+// token of a block whose operators live in the device cache, or 0
+uint64_t block_token(SpinBlock& b) {
+  for (std::map<opTypes, boost::shared_ptr<Op_component_base> >::iterator it = b.ops.begin(); it != b.ops.end(); ++it) {
+    Op_component_base& arr = *it->second;
+    for (int i = 0; i < arr.get_size(); ++i) {
+      vector<boost::shared_ptr<SparseMatrix> > vec = arr.get_local_element(i);
+      for (size_t c = 0; c < vec.size(); ++c) {
+        SparseMatrix& op = *vec[c];
+        if (!op.get_built()) return 0;
+        for (int a = 0; a < op.nrows(); ++a)
+          for (int q = 0; q < op.ncols(); ++q)
+            if (op.allowed(a, q) && op.operator_element(a, q).Storage() > 0) {
+              uint64_t id = 0;
+              return double_to_token(op.operator_element(a, q).Store()[0], &id) ? id : 0;
+            }
+      }
+    }
+  }
+  return 0;
+}
+
 struct Gpu {
   b2d_ctx* ctx = 0;              // created once, b2d_reset between block iterations
   bool active = false;           // the context currently describes a big block
@@ -103,6 +145,7 @@ struct Gpu {
   bool dirty = false;            // statistics of this context not written yet
   bool integrals_set = false;    // b2d_set_integrals done (kept across b2d_reset)
   int children_on_device = 0;    // children of big blocks built on the device so far
+  int cache_uses = 0;            // renormalised blocks taken from the device cache instead of being uploaded
   // check mode: CPU results kept between hooks
   SparseMatrix* chk_transform = 0;
   vector<DiagonalMatrix> chk_eigs;
@@ -149,9 +192,9 @@ void write_stats() {
   FILE* f = fopen(path, "a");
   if (!f) return;
   fprintf(f, "call=%d lsites=%d rsites=%d W=%lld sigma_flops=%.6e n_multiply=%d host_op_build_s=%.6f upload_s=%.6f diag_s=%.6f davidson_s=%.6f davidson_dev_ms=%.3f "
-             "density_s=%.6f eig_s=%.6f rotate_s=%.6f launches=%lld children_built_on_device=%d guess_s=%.6f\n",
+             "density_s=%.6f eig_s=%.6f rotate_s=%.6f launches=%lld children_built_on_device=%d guess_s=%.6f cache_uses=%d\n",
           g.call, (int)g.lsites.size(), (int)g.rsites.size(), (long long)g.W, g.flops, g.nmult, g.t_build, g.t_upload, g.t_diag, g.t_dav, g.dav_dev_ms, g.t_rho,
-          g.t_eig, g.t_rot, (long long)(b2d_kernel_launches(g.ctx) - g.launch0), g.children_on_device, g.t_guess);
+          g.t_eig, g.t_rot, (long long)(b2d_kernel_launches(g.ctx) - g.launch0), g.children_on_device, g.t_guess, g.cache_uses);
   fclose(f);
 }
 
@@ -164,6 +207,34 @@ void upload_block(int side, SpinBlock& b, vector<OpRef>* keep) {
     dims[i] = s.quantaStates[i];
   }
   vector<int32_t> sites(b.get_sites().begin(), b.get_sites().end());
+  if (uint64_t tok = block_token(b)) {
+    // the block's operators never left the GPU (its host matrices hold the token): make the cached entry this child
+    int32_t cnq = 0, cnops = 0, cns = 0;
+    if (b2d_cache_block_info(g.ctx, tok, &cnq, &cnops, &cns)) die("device block cache: unknown token in a host block (scratch files of another run? use B2D_DROPIN_CACHE=host)");
+    vector<int32_t> cq(3 * (size_t)cnq), cdims(cnq), csites(cns);
+    ck(b2d_cache_block_sectors(g.ctx, tok, cq.data(), cdims.data(), csites.data()), "b2d_cache_block_sectors");
+    if (cnq != nq || cq != q || cdims != dims || csites != sites) die("device block cache: the cached block's StateInfo differs from the host block's");
+    ck(b2d_cache_use(g.ctx, tok, side, b.is_loopblock() ? 1 : 0), "b2d_cache_use");
+    int k = 0;
+    for (std::map<opTypes, boost::shared_ptr<Op_component_base> >::iterator it = b.ops.begin(); it != b.ops.end(); ++it) {
+      Op_component_base& arr = *it->second;
+      for (int i = 0; i < arr.get_size(); ++i) {
+        vector<boost::shared_ptr<SparseMatrix> > vec = arr.get_local_element(i);
+        for (size_t c = 0; c < vec.size(); ++c, ++k) {
+          int32_t ty = -1, norb = -1, orbs[2] = {-1, -1}, comp = -1;
+          if (b2d_cache_op_info(g.ctx, tok, k, &ty, &norb, orbs, &comp, 0)) die("device block cache: fewer operators than the host block");
+          const std::vector<int>& ho = vec[c]->get_orbs();
+          bool same = ty == (int)it->first && norb == (int)ho.size() && comp == (int)c;
+          for (int t = 0; same && t < norb; ++t) same = orbs[t] == ho[t];
+          if (!same) die("device block cache: operator order differs from the host block's");
+          if (keep) keep->push_back(OpRef{vec[c].get(), k});
+        }
+      }
+    }
+    if (k != cnops) die("device block cache: operator count differs from the host block's");
+    ++g.cache_uses;
+    return;
+  }
   ck(b2d_set_block(g.ctx, side, nq, q.data(), dims.data(), b.is_loopblock() ? 1 : 0, (int)sites.size(), sites.data()), "b2d_set_block");
   vector<uint8_t> allowed((size_t)nq * nq);
   vector<const double*> blocks;
@@ -341,6 +412,8 @@ void ensure_ctx(const SpinBlock& big_c) {
       on_device = build_child_on_device(slot, child, keep);
     }
     if (!on_device) {
+      if (!block_token(child) && ((child.get_leftBlock() && block_token(*child.get_leftBlock())) || (child.get_rightBlock() && block_token(*child.get_rightBlock()))))
+        die("a block that cannot be built on the device has device-cached children (their host matrices hold tokens): run with B2D_DROPIN_CACHE=host");
       upload_block(0, child, keep);
       ck(b2d_stash_side(g.ctx, slot, 0), "b2d_stash_side");
     }
@@ -742,6 +815,28 @@ void wrap_transform(SpinBlock* self, vector<Matrix>& rot) {
   }
   int nnew = b2d_rotated_num_sectors(g.ctx);
   if (nnew != (int)self->get_stateInfo().quanta.size()) die("transform_operators: retained sector count differs from the reference's StateInfo");
+  if (!check && !(tmode && string(tmode) == "reference") && cache_enabled()) {
+    // the rotated operators stay on the device; the host copy keeps its zeroed blocks and gets the entry's token in the first
+    // element of every sector block (SpinBlock::store / restore and the reference's copies carry it along)
+    uint64_t tok = 0;
+    ck(b2d_cache_put_rotated(g.ctx, &tok), "b2d_cache_put_rotated");
+    const double tag = token_to_double(tok);
+    for (size_t k = 0; k < g.left_ops.size(); ++k) {
+      SparseMatrix& op = *g.left_ops[k].elem;
+      if ((int)k != g.left_ops[k].id) die("transform_operators: operator ids are not in upload order");
+      for (int a = 0; a < nnew; ++a)
+        for (int b = 0; b < nnew; ++b)
+          if (op.allowed(a, b) && op.operator_element(a, b).Storage() > 0) op.operator_element(a, b).Store()[0] = tag;
+    }
+    std::map<vector<int>, uint64_t>::iterator old = g_latest_token.find(self->get_sites());
+    if (old != g_latest_token.end()) ck(b2d_cache_drop(g.ctx, old->second), "b2d_cache_drop");   // the block this one replaces (same sites, previous sweep)
+    g_latest_token[self->get_sites()] = tok;
+    g.t_rot += now_s() - t0;
+    write_stats();
+    g.dirty = false;
+    release();
+    return;
+  }
   double worst = 0, scale = 0;
   vector<uint8_t> allowed((size_t)nnew * nnew);
   vector<double> data((size_t)std::max<int64_t>(b2d_rotated_total_size(g.ctx), 1));

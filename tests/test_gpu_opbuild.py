@@ -74,8 +74,9 @@ def test_device_tensor_products_rebuild_the_reference_operators(monkeypatch, pat
         pb.close()
 
 
+@pytest.mark.parametrize("factorised", [0, 1], ids=["materialised", "factorised"])
 @pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(f)[:-4] for f in FIXTURES])
-def test_build_enlarged_operators_without_the_oracle(path):
+def test_build_enlarged_operators_without_the_oracle(path, factorised):
     """b2d_build_enlarged_op: the library's own host planner (block_b200/csrc/opbuild.hpp) decides the products and the integral
     factors, the device performs them; inputs are only the two children, the product StateInfo and the integrals.  Every
     operator of the enlarged block must equal the one the REAL reference built."""
@@ -83,7 +84,7 @@ def test_build_enlarged_operators_without_the_oracle(path):
     pi, ref, ints = B.ProductInfo.from_record(rec), dumpio.block_from(rec, "LA."), B.Integrals.from_record(rec)
     hubbard = int(rec["meta"][7]) == B.O.HUBBARD_HAM
     left, right = hotpath.block_spec_from_record(rec, "LL."), hotpath.block_spec_from_record(rec, "LR.")
-    pb = hotpath.ProductBlock(left, right, pi.q, pi.dims, pi.lmap, pi.rmap, pi.unc_dims, pi.old_to_new, device=0)
+    pb = hotpath.ProductBlock(left, right, pi.q, pi.dims, pi.lmap, pi.rmap, pi.unc_dims, pi.old_to_new, device=0, options={"factorised": factorised})
     pb.set_integrals(ints.h1, ints.h2, ints.irreps, ints.one_tol, ints.two_tol)
     try:
         worst = 0.0

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.PROTOTYPES), declared ^ set(_lib.PROTOTYPES)
     for name in declared:
         assert hasattr(lib, name)
-    assert lib.b2d_abi_version() == 3
+    assert lib.b2d_abi_version() == 4
 
 
 def test_compute_without_device_fails_loudly(golden):

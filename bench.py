@@ -51,6 +51,30 @@ def workload_name(a):
         a.norbs, a.nelec, a.M, a.left_sites, a.norbs - a.left_sites)
 
 
+def factorised_self_check(sb, psi, nterms=4):
+    """Full-size parity of the FACTORISED operators against their own dense form: `nterms` operator-pair terms of multiplyH, evenly
+    spaced over the term list, through b2d_tensor_multiply - first with both operators as factor lists, then after b2d_materialise_op
+    wrote the same two operators out as dense sector blocks (the form whose parity against the REAL reference's TensorMultiply
+    tests/test_synthetic.py and round 1's bench pinned at 1.8e-15).  Returns (worst relative difference, #terms)."""
+    lops, rops, flags, scales = sb.terms(all_ranks=False)[:4]
+    pick = [int(i) for i in np.unique(np.linspace(2, len(lops) - 1, nterms).astype(int))]
+    sb.reserve(4)
+    sb.upload(0, psi)
+    worst = 0.0
+    for i in pick:
+        lo, ro, fl, sc = int(lops[i]), int(rops[i]), int(flags[i]), float(scales[i])
+        sb.clear(2)
+        sb.tensor_multiply_slots(lo, ro, bool(fl & 1), bool(fl & 2), 0, sc, 0, 2)
+        fac = sb.download(2)
+        sb._ck(sb.lib.b2d_materialise_op(sb._ctx, 0, lo))
+        sb._ck(sb.lib.b2d_materialise_op(sb._ctx, 1, ro))
+        sb.clear(2)
+        sb.tensor_multiply_slots(lo, ro, bool(fl & 1), bool(fl & 2), 0, sc, 0, 2)
+        den = sb.download(2)
+        worst = max(worst, float(np.linalg.norm(fac - den) / max(np.linalg.norm(den), 1e-300)))
+    return worst, len(pick)
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # CPU leg: the reference algorithm (oracle restatement, numpy/OpenBLAS dgemm) on a bounded sample of the terms
 # ---------------------------------------------------------------------------------------------------------------------
@@ -320,11 +344,12 @@ def block_iteration_leg(sb, a, psi, sigma_ms):
 def sweep_leg(a):
     """BASELINE.json's other headline figure, "two-site sweep wall time ... energy delta vs ref": the UNMODIFIED reference sweep
     (oracle/_ref/block.spin_adapted, all host threads) next to the same reference sweep with its hot path re-routed to this library
-    (oracle/_ref/block_gpu, tests/dropin/block_gpu_hooks.cpp) on one real FCIDUMP / dmrg.conf case of tests/golden/dropin_cases.npz.
-    Both run here, back to back, on this box; energies are compared sweep by sweep.  Block construction is inside both times (the
-    drop-in builds the children of the big block on the device).  A third run, "gpu_dropin_next_rows", switches on what
-    was finished after this round's GPU budget was spent (batched operator construction, guess-wavefunction transform on the device:
-    B2D_DROPIN_OPTIONS=opbuild_batch=1, B2D_DROPIN_GUESS=device); it is reported beside the other two and never replaces them."""
+    (oracle/_ref/block_gpu, tests/dropin/block_gpu_hooks.cpp) on one real FCIDUMP / dmrg.conf case of tests/golden/dropin_cases.npz
+    (default synthetic_16o_M300: random-integral FCIDUMP, 16 orbitals, M = 150 -> 300, Davidson tolerance 1e-12, four sweeps, golden
+    sweeps committed).  Both run here, back to back, on this box; energies are compared sweep by sweep, with each other and with the
+    golden sweeps.  Block construction is inside both times.  "gpu_dropin" is the default drop-in (enlarged-block operators built on the
+    device, guess wavefunctions transformed on the device, renormalised blocks cached on the device); "gpu_dropin_factorised" adds option
+    factorised (no enlarged-block operator is materialised)."""
     import re
     gpu_bin = os.path.join(ROOT, "oracle", "_ref", "block_gpu")
     ref_bin = os.path.join(ROOT, "oracle", "_ref", "block.spin_adapted")
@@ -337,15 +362,15 @@ def sweep_leg(a):
     pat = re.compile(r"M = (\d+)\s+state = (\d+)\s+Largest Discarded Weight = (\S+)\s+Sweep Energy = (\S+)")
     out = {"case": name, "host_threads": threads}
     energies = {}
-    for tag, exe in (("reference_cpu", ref_bin), ("gpu_dropin", gpu_bin), ("gpu_dropin_next_rows", gpu_bin)):
+    for tag, exe in (("reference_cpu", ref_bin), ("gpu_dropin", gpu_bin), ("gpu_dropin_factorised", gpu_bin)):
         work = tempfile.mkdtemp(prefix="sweep_%s_" % tag)
         for f in z[name + "/files"]:
             open(os.path.join(work, str(f)), "wb").write(z["%s/file/%s" % (name, f)].tobytes())
         conf = z[name + "/conf"].tobytes().decode() + "threads_per_node %d\n" % threads
         open(os.path.join(work, "dmrg.conf"), "w").write(conf)
         env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS=str(threads), B2D_DROPIN_STATS=os.path.join(work, "stats.txt"))
-        if tag == "gpu_dropin_next_rows":
-            env.update(B2D_DROPIN_OPTIONS="opbuild_batch=1", B2D_DROPIN_GUESS="device")
+        if tag == "gpu_dropin_factorised":
+            env.update(B2D_DROPIN_OPTIONS="factorised=1")
         t0 = time.perf_counter()
         try:
             r = subprocess.run([exe, "dmrg.conf"], cwd=work, env=env, capture_output=True, text=True, timeout=900)
@@ -367,8 +392,9 @@ def sweep_leg(a):
             out[tag]["hot_path_s"] = {k: tot.get(k, 0.0) for k in ("host_op_build_s", "upload_s", "guess_s", "diag_s", "davidson_s", "density_s", "eig_s", "rotate_s")}
             out[tag]["n_multiply"] = int(tot.get("n_multiply", 0))
             out[tag]["kernel_launches"] = int(tot.get("launches", 0))
-    if "reference_cpu" in energies and "gpu_dropin_next_rows" in energies and len(energies["reference_cpu"]) == len(energies["gpu_dropin_next_rows"]):
-        out["gpu_dropin_next_rows"]["max_abs_dE_per_sweep"] = max(abs(x - y) for x, y in zip(energies["reference_cpu"], energies["gpu_dropin_next_rows"]))
+            out[tag]["blocks_taken_from_device_cache"] = int(tot.get("cache_uses", 0))
+    if "reference_cpu" in energies and "gpu_dropin_factorised" in energies and len(energies["reference_cpu"]) == len(energies["gpu_dropin_factorised"]):
+        out["gpu_dropin_factorised"]["max_abs_dE_per_sweep"] = max(abs(x - y) for x, y in zip(energies["reference_cpu"], energies["gpu_dropin_factorised"]))
     if "reference_cpu" in energies and "gpu_dropin" in energies and len(energies["reference_cpu"]) == len(energies["gpu_dropin"]):
         out["max_abs_dE_per_sweep"] = max(abs(x - y) for x, y in zip(energies["reference_cpu"], energies["gpu_dropin"]))
         golden = [float(m.group(4)) for m in pat.finditer(z[name + "/sweeps"].tobytes().decode())] if name + "/sweeps" in z.files else []
@@ -409,8 +435,15 @@ def run_ours(a):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     t_setup = time.time()
-    sb = S.make_big_block(norbs=a.norbs, nelec=a.nelec, M=a.M, left_sites=a.left_sites, device=local, rank=rank, nranks=world,
-                          options=dict({"workspace_mb": a.workspace_mb, "slice_iters": a.slice_iters}, **{kv.split("=")[0]: float(kv.split("=")[1]) for kv in a.opt}))
+    options = dict({"workspace_mb": a.workspace_mb, "slice_iters": a.slice_iters}, **{kv.split("=")[0]: float(kv.split("=")[1]) for kv in a.opt})
+    if a.mode == "factorised":
+        # the blocks a sweep holds before a block iteration: renormalised M-state blocks + one-site dots; every operator of the two
+        # enlarged blocks is built on the device as a list of scaled sub-blocks of the renormalised operators (never materialised)
+        case = S.make_product_case(norbs=a.norbs, nelec=a.nelec, M=a.M, left_sites=a.left_sites)
+        sb = S.make_big_block_from_products(case, device=local, options=options, factorised=True, rank=rank, nranks=world)
+        sb.fill_seed = case["seed"]
+    else:
+        sb = S.make_big_block(norbs=a.norbs, nelec=a.nelec, M=a.M, left_sites=a.left_sites, device=local, rank=rank, nranks=world, options=options)
     if world > 1:   # the partial sigmas are summed by the library's own NCCL communicator (dlopen'ed libnccl of the torch wheel)
         ident = [SpinBlock.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ident, src=0)
@@ -474,7 +507,9 @@ def run_ours(a):
     lin_err = float(np.linalg.norm(sb.download(1) - (2.0 * hx - 3.0 * hy)) / np.linalg.norm(2.0 * hx - 3.0 * hy))
     # sigma_norm / sigma_probe are pure functions of the (seeded) workload: they must agree across --gpus 1/2/4/8 runs
     parity = {"linearity_rel": lin_err, "sigma_norm": float(np.linalg.norm(hx)), "sigma_probe": float(np.dot(hx, np.cos(np.arange(W))))}
-    if world == 1 and not a.no_cpu:
+    sb.sigma(0, 1)
+    parity["bit_reproducible"] = bool(np.array_equal(sb.download(1), hx))
+    if world == 1 and not a.no_cpu and a.mode == "materialised":
         from oracle import refbench
         if refbench.available():
             err, nt = reference_parity(sb, a, psi)
@@ -513,19 +548,26 @@ def run_ours(a):
         # roofline of the dominant kernel (128x128 DMMA tile class of the grouped contraction), timed live with events
         prof = sb.sigma_profile(0, 1)
         dmma, dfma = sb.measure_fp64_peak()
-        k_ms = sum(prof[(st, 0)][0] for st in range(2))
-        k_fl = sum(prof[(st, 0)][1] for st in range(2))
-        k_pad = sum(prof[(st, 0)][2] for st in range(2))
-        k_n = sum(prof[(st, 0)][3] for st in range(2))
+        # the dominant kernel = the tile class of the grouped contraction with the largest share of the step's time
+        cls_ms = {c: sum(prof[(st, c)][0] for st in range(2)) for c in range(10)}
+        kc = max(cls_ms, key=cls_ms.get)
+        k_ms = sum(prof[(st, kc)][0] for st in range(2))
+        k_fl = sum(prof[(st, kc)][1] for st in range(2))
+        k_pad = sum(prof[(st, kc)][2] for st in range(2))
+        k_n = sum(prof[(st, kc)][3] for st in range(2))
         tot_ms = sum(v[0] for v in prof.values())
+        tot_fl = sum(v[1] for v in prof.values())
+        kname = "grouped_gemm_kernel<%d,%d,*> (FP64 DMMA m16n8k8, %d warps x 32x32)" % (128 >> (kc // 3), 128 >> (kc % 3), (128 >> (kc // 3)) * (128 >> (kc % 3)) // 1024) if kc < 9 else "tiny_gemm_kernel"
         achieved = k_fl / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
         # DRAM bytes per launch of that kernel from the committed ncu capture of this same workload (profiles/README.md); other
         # workloads have no capture
-        default_workload = (a.norbs, a.nelec, a.M, a.left_sites, world) == (40, 40, 4000, 18, 1)
+        default_workload = (a.norbs, a.nelec, a.M, a.left_sites, world, a.mode) == (40, 40, 4000, 18, 1, "materialised")
         roof = {"bound": "tensor", "achieved": achieved, "peak": dmma, "unit": "TFLOP/s", "frac": achieved / dmma if dmma else None,
                 "traffic": 16.12e9 if default_workload else None,
                 "traffic_source": "profiles/r01_ncu_launches_sigma_fullsize.csv: dram__bytes_read.sum + dram__bytes_write.sum of the 36 launches / 36 (bytes per launch)" if default_workload else None,
-                "kernel": "grouped_gemm_kernel<128,128,*> (FP64 DMMA m16n8k8, 16 warps x 32x32)", "launches": int(k_n), "avg_launch_ms": k_ms / max(k_n, 1),
+                "kernel": kname, "launches": int(k_n), "avg_launch_ms": k_ms / max(k_n, 1),
+                "flops_basis": "EXECUTED flops of that kernel (useful 2mnk inside its tiles; structural zeros the factorised form skips are not credited)",
+                "whole_sigma_executed_tflops": tot_fl / (ms_step * 1e-3) / 1e12, "whole_sigma_frac_of_peak": tot_fl / (ms_step * 1e-3) / 1e12 / dmma if dmma else None,
                 "share_of_sigma": k_ms / tot_ms if tot_ms else None, "tile_fill": k_fl / k_pad if k_pad else None,
                 "peak_source": "live FP64 DMMA register-loop yardstick of this library on this GPU (MEASURED_PEAKS.json has no FP64 entry); DFMA loop %.1f TFLOP/s" % dfma,
                 "per_class": {("step%d_%dx%d" % (st + 1, 128 >> (c // 3), 128 >> (c % 3)) if c < 9 else "step%d_tiny8x8_warp" % (st + 1)): {"ms": v[0], "tflops": (v[1] / (v[0] * 1e-3) / 1e12 if v[0] > 0 else 0.0), "tile_fill": (v[1] / v[2] if v[2] else None),
@@ -537,16 +579,27 @@ def run_ours(a):
             pass
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup, "ms_per_step": ms_step,
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": workload_name(a), "psi_doubles": int(W), "terms": int(len(sb.terms(all_ranks=True)[0])),
+                "executed": {"flops_per_step": stats["flops_executed"], "gflops": stats["flops_executed"] / (ms_step * 1e-3) / 1e9,
+                             "ratio_to_algorithmic": stats["flops_executed"] / flops_mine if flops_mine else None,
+                             "note": "value = ALGORITHMIC flops (the dgemm flops the reference issues for this multiplyH, SURVEY 8d) / time; executed = what the kernels "
+                                     "compute: the factorised operators skip the structural zeros of the Kronecker blocks, T blocks nobody consumes are skipped in both modes"},
+                "config": {"workload": workload_name(a), "operators": a.mode, "psi_doubles": int(W), "terms": int(len(sb.terms(all_ranks=True)[0])),
                            "left_sectors": int(len(sb.left.dims)), "right_sectors": int(len(sb.right.dims)), "left_states": int(sb.left.dims.sum()),
                            "right_states": int(sb.right.dims.sum()), "sigma_flops": flops_alg, "rank0_flops": flops_mine,
-                           "operator_arena_gb_rank0": stats["arena_doubles"] * 8 / 1e9, "chunks": int(stats["chunks"]),
+                           "operator_arena_gb_rank0": stats["arena_doubles"] * 8 / 1e9, "presummed_factor_blocks_gb": stats["combo_doubles"] * 8 / 1e9,
+                           "factors": int(stats["factors_direct"] + stats["factors_combo"]), "chunks": int(stats["chunks"]),
                            "parallelism": "operator-term partition x%d + NCCL all-reduce of partial sigma" % world if world > 1 else "single GPU",
-                           "l2": "inputs larger than L2 (operator arena %.0f GB per step)" % (stats["arena_doubles"] * 8 / 1e9), "setup_s": t_setup},
+                           "l2": "inputs larger than L2 (operator arena %.0f GB + %.1f GB of T workspace per step)" % (stats["arena_doubles"] * 8 / 1e9, stats["workspace_doubles"] * 8 / 1e9),
+                           "setup_s": t_setup},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(W * 8), "d2h_bytes_per_step": int(W * 8)},
                 "gpu_launches": int(launches), "clocks": clk, "roofline": roof,
                 "parity": parity,
                 "hbm_peak_gbs": peaks.get("hbm_gbs")}
+    if line is not None and world == 1 and a.mode == "factorised":
+        err, nt = factorised_self_check(sb, psi)
+        line["parity"]["factorised_vs_dense_TensorMultiply_rel"] = err
+        line["parity"]["factorised_vs_dense_terms"] = nt
+        sb.upload(0, psi)
     if line is not None and world == 1 and not a.no_block_iteration:
         # a first pass with ONE Davidson iteration loads every kernel of the leg (CUDA loads modules lazily: the first launch of
         # a kernel costs tens of milliseconds) and sizes the scratch buffers; the second pass is the one reported
@@ -592,7 +645,11 @@ def main():
     ap.add_argument("--M", type=int, default=4000)
     # 18|22: the heaviest block iteration of the 40-orbital M=4000 sweep whose materialised operator arenas (152 GB) fit
     # ONE 180 GB B200; the mid-chain 20|20 iteration (185 GB) needs the term partition over >= 2 GPUs
-    ap.add_argument("--left-sites", type=int, default=18)
+    ap.add_argument("--left-sites", type=int, default=None)
+    # factorised (default): the operators of the two enlarged blocks are lists of scaled sub-blocks of the renormalised operators
+    # (SURVEY.md 7 "hard parts") - the mid-chain 20|20 block iteration, the heaviest of the sweep, fits one GPU; materialised: round 1's
+    # dense enlarged-block operators (18|22 is the heaviest that fits one 180 GB GPU)
+    ap.add_argument("--mode", default="factorised", choices=["factorised", "materialised"])
     ap.add_argument("--workspace-mb", type=float, default=8192.0)
     ap.add_argument("--slice-iters", type=int, default=256)
     ap.add_argument("--opt", action="append", default=[], help="extra library option key=value (b2d_set_option)")
@@ -600,11 +657,13 @@ def main():
     ap.add_argument("--no-block-iteration", action="store_true", help="skip the Davidson / density / eigen / rotation leg")
     ap.add_argument("--davidson-iters", type=int, default=6)
     ap.add_argument("--no-sweep", action="store_true", help="skip the whole-sweep leg (reference sweep vs the same sweep with the GPU hot path)")
-    ap.add_argument("--sweep-case", default="synthetic_18o_M500", help="case of tests/golden/dropin_cases.npz for the sweep leg")
+    ap.add_argument("--sweep-case", default="synthetic_16o_M300", help="case of tests/golden/dropin_cases.npz for the sweep leg")
     ap.add_argument("--profile-mode", action="store_true", help="for ncu: 1 warm-up sigma + --steps sigmas, nothing else, no JSON line")
     ap.add_argument("--cpu-budget-s", type=float, default=15.0)
     ap.add_argument("--ref-step-s", type=float, default=6.0)
     a = ap.parse_args()
+    if a.left_sites is None:
+        a.left_sites = a.norbs // 2 if a.mode == "factorised" else 18
     a.warmup = max(a.warmup, 3) if a.impl == "ours" else a.warmup
     if a.impl == "reference":
         run_reference(a)

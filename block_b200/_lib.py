@@ -45,6 +45,7 @@ PROTOTYPES = {
     "b2d_add_op_blocks": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_int, c_i32p, C.c_int, c_i32p, C.c_int, c_u8p, C.POINTER(c_f64p), C.POINTER(C.c_int)]),
     "b2d_fill_op_random": (C.c_int, [ctx_p, C.c_int, C.c_int, C.c_uint64, C.c_double, C.c_int]),
     "b2d_alloc_ops": (C.c_int, [ctx_p, C.c_int]),
+    "b2d_materialise_op": (C.c_int, [ctx_p, C.c_int, C.c_int]),
     "b2d_download_op": (C.c_int, [ctx_p, C.c_int, C.c_int, c_f64p]),
     "b2d_op_size": (C.c_int64, [ctx_p, C.c_int, C.c_int]),
     "b2d_plan": (C.c_int, [ctx_p, c_i32p, C.c_double, C.c_int, C.c_int, C.c_int, C.c_int]),

@@ -206,11 +206,13 @@ struct b2d_ctx {
     std::vector<std::vector<int>> old_to_new;
     bool set = false;
   } product;
-  DevBuf kron_tasks;
+  DevBuf kron_tasks, kron_tiles;
   bool factorised = false;                  // option "factorised": operators of an enlarged block (renormalised block x one-site dot) are kept as lists of
                                             // scaled sub-blocks of the renormalised operators instead of being materialised (16x less memory, no structural zeros)
+  bool presum_identity = true;              // option "presum_identity": a piece pair that receives {child block, identity} is pre-summed into one block (one K segment
+                                            // instead of two: ~7 % fewer executed flops at M = 4000 for ~5 GB more memory); off: both stay direct factors
   int64_t combo_doubles = 0;                // pre-summed factor blocks allocated since the last reset
-  int64_t nsubs_direct = 0, nsubs_combo = 0;
+  int64_t nsubs_direct = 0, nsubs_combo = 0, ncombos = 0;
   bool opbuild_batch = true;                // b2d_build_enlarged_op defers its scatter tasks: one launch per ROUND for a whole child block
   std::vector<KronTask> pend_kron;          // deferred tasks ...
   std::vector<int> pend_kron_round;         // ... and the round of each: how many earlier tasks hit the same destination piece
@@ -237,6 +239,7 @@ struct b2d_ctx {
   uint64_t cache_next_token = 1;
   double cache_device_mb = 32768.0;   // option "cache_device_mb": device memory the cache may hold before it spills to pinned host memory
   int64_t cache_device_doubles = 0, cache_hits = 0, cache_puts = 0;
+  std::vector<DevBuf> spare_bufs;     // buffers of dropped entries, reused by the next b2d_transform_operators (cudaMalloc of hundreds of MB costs ~10 ms)
   std::map<std::vector<int>, PsiLayout> layouts;   // wavefunction layouts for other target quanta (noise: O.psi sectors)
   DevBuf dm_noise;
   Nccl nccl;
@@ -321,6 +324,30 @@ int upload_desc(b2d_ctx* ctx, DevBuf& buf, const void* host, size_t bytes) {
   CU(buf.reserve(bytes));
   CU(cudaMemcpyAsync(buf.p, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));   // host vectors are temporaries
+  return B2D_OK;
+}
+
+// Scatter tasks round by round: tasks[round_begin[r] .. round_begin[r + 1]) never overlap in their destinations; the rounds run in stream
+// order.  One upload of the tasks, one of the band list (every task cut into bands of KRON_BAND destination rows for load balance).
+int run_kron_rounds(b2d_ctx* ctx, const std::vector<KronTask>& tasks, const std::vector<int>& round_begin) {
+  if (tasks.empty()) return B2D_OK;
+  int rc = upload_desc(ctx, ctx->kron_tasks, tasks.data(), tasks.size() * sizeof(KronTask));
+  if (rc) return rc;
+  std::vector<KronTile> tiles;
+  std::vector<int> tile_begin(round_begin.size(), 0);
+  for (size_t r = 0; r + 1 < round_begin.size(); ++r) {
+    tile_begin[r] = (int)tiles.size();
+    for (int t = round_begin[r]; t < round_begin[r + 1]; ++t) {
+      const int rows = tasks[t].a_rows * tasks[t].b_rows;
+      for (int b = 0; b * KRON_BAND < rows; ++b) tiles.push_back(KronTile{t, b});
+    }
+  }
+  tile_begin[round_begin.size() - 1] = (int)tiles.size();
+  rc = upload_desc(ctx, ctx->kron_tiles, tiles.data(), tiles.size() * sizeof(KronTile));
+  if (rc) return rc;
+  for (size_t r = 0; r + 1 < round_begin.size(); ++r)
+    CU(launch_kron_scatter((const KronTask*)ctx->kron_tasks.p, (const KronTile*)ctx->kron_tiles.p + tile_begin[r], tile_begin[r + 1] - tile_begin[r], ctx->stream,
+                           &ctx->launches));
   return B2D_OK;
 }
 
@@ -597,9 +624,10 @@ void b2d_destroy(b2d_ctx* ctx) {
                       &ctx->diag_begin, &ctx->partials, &ctx->scalars, &ctx->user_pool, &ctx->dav_pool, &ctx->rho, &ctx->eig_g, &ctx->eig_vt,
                       &ctx->eig_vals, &ctx->eig_sweeps, &ctx->sector_desc, &ctx->rot, &ctx->gather_desc, &ctx->gather_rows,
                       &ctx->rotated_arena, &ctx->dsched.buf, &ctx->tile_counter, &ctx->diag_gather, &ctx->diag_pool, &ctx->kron_tasks,
-                      &ctx->guess_image, &ctx->guess_trial, &ctx->eig_pairs, &ctx->diag_regions, &ctx->materialised, &ctx->eig_tmp};
+                      &ctx->guess_image, &ctx->guess_trial, &ctx->eig_pairs, &ctx->diag_regions, &ctx->materialised, &ctx->eig_tmp, &ctx->kron_tiles};
     for (DevBuf* b : bufs) b->release();
     for (auto& kv : ctx->cache) { kv.second.dev.release(); if (kv.second.pinned) cudaFreeHost(kv.second.pinned); }
+    for (DevBuf& b : ctx->spare_bufs) b.release();
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->pend_pinned) cudaFreeHost(ctx->pend_pinned);
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
@@ -643,7 +671,7 @@ int b2d_reset(b2d_ctx* ctx) {
   ctx->stash[0] = Side(); ctx->stash[1] = Side(); ctx->stash_set[0] = ctx->stash_set[1] = false;
   ctx->guess = GuessPlan();
   ctx->pend_kron.clear(); ctx->pend_kron_round.clear(); ctx->pend_kron_hits.clear();
-  ctx->combo_doubles = 0; ctx->nsubs_direct = ctx->nsubs_combo = 0;
+  ctx->combo_doubles = 0; ctx->nsubs_direct = ctx->nsubs_combo = ctx->ncombos = 0;
   ctx->timing_valid = false;   // (the integrals belong to the whole calculation: b2d_reset keeps them)
   ctx->err.clear();
   return B2D_OK;
@@ -666,6 +694,7 @@ int b2d_set_option(b2d_ctx* ctx, const char* key, double value) {
   else if (k == "phase_timing") ctx->phase_timing = value != 0;
   else if (k == "opbuild_batch") ctx->opbuild_batch = value != 0;
   else if (k == "factorised") ctx->factorised = value != 0;
+  else if (k == "presum_identity") ctx->presum_identity = value != 0;
   else if (k == "cache_device_mb") ctx->cache_device_mb = value;
   else return fail(ctx, B2D_ERR_ARG, "unknown option " + k);
   return B2D_OK;
@@ -967,10 +996,10 @@ int b2d_plan_stats(const b2d_ctx* ctx, double* out, int n) {
       useful += c.step1.class_flops[k] + c.step2.class_flops[k];
       issued += c.step1.class_padded[k] + c.step2.class_padded[k];
     }
-  double v[13] = {(double)ctx->sched.chunks.size(), (double)ctx->sched.n_step1, (double)ctx->sched.n_step2, (double)ctx->sched.n_tiles,
+  double v[14] = {(double)ctx->sched.chunks.size(), (double)ctx->sched.n_step1, (double)ctx->sched.n_step2, (double)ctx->sched.n_tiles,
                   (double)ctx->sched.work_max, (double)ctx->arena_doubles, (double)launches, ctx->sched.flops_exec, useful, issued,
-                  (double)ctx->combo_doubles, (double)ctx->nsubs_direct, (double)ctx->nsubs_combo};
-  for (int i = 0; i < n && i < 13; ++i) out[i] = v[i];
+                  (double)ctx->combo_doubles, (double)ctx->nsubs_direct, (double)ctx->nsubs_combo, (double)ctx->ncombos};
+  for (int i = 0; i < n && i < 14; ++i) out[i] = v[i];
   return B2D_OK;
 }
 
@@ -1798,8 +1827,21 @@ int b2d_transform_operators(b2d_ctx* ctx) {
     if (o.dev || o.factorised) total += align_up(r.dev_size, 32);   // operators another rank holds are rotated there
     N.ops.push_back(std::move(r));
   }
-  CU(ctx->rotated_arena.reserve((size_t)std::max<int64_t>(total, 16) * 8));
-  CU(cudaMemsetAsync(ctx->rotated_arena.p, 0, ctx->rotated_arena.cap, ctx->stream));
+  {
+    const size_t need_bytes = (size_t)std::max<int64_t>(total, 16) * 8;
+    if (ctx->rotated_arena.cap < need_bytes) {   // best-fitting buffer of a dropped cache entry before a fresh cudaMalloc
+      int best = -1;
+      for (size_t i = 0; i < ctx->spare_bufs.size(); ++i)
+        if (ctx->spare_bufs[i].cap >= need_bytes && (best < 0 || ctx->spare_bufs[i].cap < ctx->spare_bufs[best].cap)) best = (int)i;
+      if (best >= 0) {
+        ctx->rotated_arena.release();
+        ctx->rotated_arena = ctx->spare_bufs[best];
+        ctx->spare_bufs.erase(ctx->spare_bufs.begin() + best);
+      }
+    }
+    CU(ctx->rotated_arena.reserve(need_bytes));
+    CU(cudaMemsetAsync(ctx->rotated_arena.p, 0, need_bytes, ctx->stream));
+  }
   {
     int64_t off = 0;
     for (size_t m = 0; m < N.ops.size(); ++m) {
@@ -2244,6 +2286,10 @@ int b2d_set_product_stateinfo(b2d_ctx* ctx, int nq, const int32_t* q, const int3
     }
     if (sum != dims[c]) return fail(ctx, B2D_ERR_ARG, "b2d_set_product_stateinfo: pieces do not add up to the sector size");
   }
+  if (!ctx->has_device)   // planning-only context: distinct (never dereferenced) addresses per child operator, so that the factor bookkeeping of
+    for (int sd = 0; sd < 2; ++sd)   // factorised operators (sharing of pre-summed blocks, memory accounting) is the device run's
+      for (OpRec& op : ctx->side[sd].ops)
+        if (!op.dev && op.dev_size > 0) { arena_alloc_any(ctx, (size_t)op.dev_size * 8, &op.dev); ctx->arena_doubles += op.dev_size; }
   // un-collected pieces of every collected sector: (offset, size) in concatenation order
   P.side.pieces.resize(nq);
   for (int c = 0; c < nq; ++c) {
@@ -2295,6 +2341,7 @@ int b2d_product_op_create(b2d_ctx* ctx, const int32_t* dq, int fermion, int* pro
     }
   } else if (op.dev_size > 0) {
     CU(arena_alloc(ctx, (size_t)op.dev_size * 8, &op.dev));
+    ctx->arena_doubles += op.dev_size;
     CU(cudaMemsetAsync(op.dev, 0, (size_t)op.dev_size * 8, ctx->stream));
   }
   S.ops.push_back(std::move(op));
@@ -2319,11 +2366,11 @@ static int flush_product_tasks(b2d_ctx* ctx) {
     std::vector<int> at(count.begin(), count.end() - 1);
     for (size_t i = 0; i < ctx->pend_kron.size(); ++i) sorted[at[ctx->pend_kron_round[i]]++] = ctx->pend_kron[i];
   }
-  int rc = upload_desc(ctx, ctx->kron_tasks, sorted.data(), sorted.size() * sizeof(KronTask));
+  // round 0 = the first contribution to a piece of freshly zero-filled storage: it is stored, not read-modified-written
+  for (int i = 0; i < count[1]; ++i) sorted[i].pad |= 1;
+  begin_timing(ctx);   // b2d_last_timing: device time of the whole batched construction (incl. the descriptor uploads)
+  int rc = run_kron_rounds(ctx, sorted, count);
   if (rc) return rc;
-  begin_timing(ctx);   // b2d_last_timing: device time of the whole batched construction
-  for (int r = 0; r < nrounds; ++r)
-    CU(launch_kron_scatter((const KronTask*)ctx->kron_tasks.p + count[r], count[r + 1] - count[r], ctx->stream, &ctx->launches));
   end_timing(ctx);
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->kron_last_rounds = nrounds;
@@ -2393,7 +2440,9 @@ static int product_op_accumulate_impl(b2d_ctx* ctx, int prod_id, int left_op, in
                 if (f != 0.0) {
                   SubBlock sbk;
                   sbk.r0 = row; sbk.c0 = col; sbk.m = L.dims[aq]; sbk.n = L.dims[aqp]; sbk.alpha = f;
-                  if (trace_l) { sbk.a = P.identity; sbk.lda = P.identity_ld; sbk.t = false; }
+                  // the OVERLAP operator of a renormalised block is the identity (same bra and ket states; what the rotation leaves of it is
+                  // I + O(1e-16)): it is contracted as THE identity block, so that "child block + identity" stays a pair of direct factors
+                  if (trace_l || la->optype == OP_OVERLAP) { sbk.a = P.identity; sbk.lda = P.identity_ld; sbk.t = false; }
                   else { sbk.a = la->dev + a.stored_off(aq, aqp); sbk.lda = a.stored_ld(aq, aqp); sbk.t = a.t; }
                   out.emplace_back((size_t)cq * P.side.nq + cqp, sbk);
                 }
@@ -2454,9 +2503,8 @@ static int product_op_accumulate_impl(b2d_ctx* ctx, int prod_id, int left_op, in
     }
     return B2D_OK;
   }
-  int rc = upload_desc(ctx, ctx->kron_tasks, tasks.data(), tasks.size() * sizeof(KronTask));
+  int rc = run_kron_rounds(ctx, tasks, std::vector<int>{0, (int)tasks.size()});
   if (rc) return rc;
-  CU(launch_kron_scatter((const KronTask*)ctx->kron_tasks.p, (int)tasks.size(), ctx->stream, &ctx->launches));
   CU(cudaStreamSynchronize(ctx->stream));
   return B2D_OK;
 }
@@ -2501,7 +2549,7 @@ static int finalise_factorised_op(b2d_ctx* ctx, int prod_id) {
       const SubBlock& first = *list[0];
       int nident = 0;
       for (const auto& pr : parts) nident += pr.first == P.identity;
-      if (parts.size() == 1 || (parts.size() == 2 && nident == 1)) {
+      if (parts.size() == 1 || (parts.size() == 2 && nident == 1 && !ctx->presum_identity)) {
         for (size_t q = 0; q < parts.size(); ++q) {
           if (alphas[q] == 0.0) continue;
           SubBlock sb = first;
@@ -2532,6 +2580,7 @@ static int finalise_factorised_op(b2d_ctx* ctx, int prod_id) {
         CU(arena_alloc_any(ctx, n * 8, &dst));
         if (ctx->has_device) CU(cudaMemsetAsync(dst, 0, n * 8, ctx->stream));
         ctx->arena_doubles += (int64_t)n; ctx->combo_doubles += (int64_t)n;
+        if (getenv("B2D_FACT_DEBUG")) { static std::map<int, std::array<double, 3>> acc; auto& a = acc[op.optype]; a[0] += (double)n; a[1] += 1; a[2] += (double)parts.size(); fprintf(stderr, "FACT optype %d combos %.0f doubles %.3e avg parts %.1f | this: parts %d m %d n %d ident %d r0 %d c0 %d blk %zu\n", op.optype, a[1], a[0], a[2] / a[1], (int)parts.size(), first.m, first.n, nident, first.r0, first.c0, b); }
         for (size_t q = 0; q < parts.size(); ++q) {
           if (ratios[q] == 0.0) continue;
           KronTask kt;
@@ -2547,6 +2596,7 @@ static int finalise_factorised_op(b2d_ctx* ctx, int prod_id) {
         }
         cands.push_back(b2d_ctx::Product::Combo{parts, ratios, dst});
         block = dst;
+        ++ctx->ncombos;
       }
       SubBlock sb = first;
       sb.a = block; sb.lda = ldc; sb.t = false; sb.alpha = alphas[lead];
@@ -2776,13 +2826,10 @@ int b2d_guess_transform(b2d_ctx* ctx, const double* old_wave, const double* left
         t.pad = 0;
         tasks.push_back(t);
       }
-    rc = upload_desc(ctx, ctx->kron_tasks, tasks.data(), tasks.size() * sizeof(KronTask));
+    std::vector<int> round_begin(1, 0);
+    for (const auto& r : P.rounds) round_begin.push_back(round_begin.back() + (int)r.size());   // tasks of one round never overlap; the rounds accumulate in stream order
+    rc = run_kron_rounds(ctx, tasks, round_begin);
     if (rc) return rc;
-    size_t first = 0;
-    for (const auto& r : P.rounds) {   // tasks of one round never overlap; the rounds accumulate in stream order
-      CU(launch_kron_scatter((const KronTask*)ctx->kron_tasks.p + first, (int)r.size(), ctx->stream, &ctx->launches));
-      first += r.size();
-    }
   }
   rc = run_schedule(ctx, S3, D3, nullptr, dst, (double*)ctx->guess_image.p);
   end_timing(ctx);
@@ -2844,10 +2891,32 @@ static int materialise_factorised(b2d_ctx* ctx, const Side& S, const OpRec& op, 
   for (int r = 0; r < nrounds; ++r) count[r + 1] += count[r];
   std::vector<KronTask> sorted(tasks.size());
   { std::vector<int> at(count.begin(), count.end() - 1); for (size_t i = 0; i < tasks.size(); ++i) sorted[at[round[i]]++] = tasks[i]; }
-  int rc = upload_desc(ctx, ctx->kron_tasks, sorted.data(), sorted.size() * sizeof(KronTask));
-  if (rc) return rc;
-  for (int r = 0; r < nrounds; ++r)
-    CU(launch_kron_scatter((const KronTask*)ctx->kron_tasks.p + count[r], count[r + 1] - count[r], ctx->stream, &ctx->launches));
+  return run_kron_rounds(ctx, sorted, count);
+}
+
+// Write a factorised operator of a child of the planned big block out densely, in place: afterwards it is an ordinary materialised
+// operator (b2d_tensor_multiply, b2d_download_op, ... read the dense blocks).  The sigma schedule of the current plan keeps contracting
+// the factors.  Used for the full-size self-check of the benchmark: the same operator pair through both forms.
+int b2d_materialise_op(b2d_ctx* ctx, int side, int op_id) {
+  NEED_DEVICE();
+  if (side < 0 || side > 1 || op_id < 0 || op_id >= (int)ctx->side[side].ops.size()) return fail(ctx, B2D_ERR_ARG, "b2d_materialise_op: bad arguments");
+  Side& S = ctx->side[side];
+  OpRec& op = S.ops[op_id];
+  if (!op.factorised) return B2D_OK;
+  DevBuf tmp;
+  int rc = materialise_factorised(ctx, S, op, tmp);
+  if (rc) { tmp.release(); return rc; }
+  if (op.dev_size > 0) {
+    double* dst = nullptr;
+    cudaError_t e = arena_alloc(ctx, (size_t)op.dev_size * 8, &dst);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dst, tmp.p, (size_t)op.dev_size * 8, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    tmp.release();
+    if (e != cudaSuccess) return fail(ctx, B2D_ERR_CUDA, std::string("b2d_materialise_op: ") + cudaGetErrorString(e));
+    op.dev = dst;
+    ctx->arena_doubles += op.dev_size;
+  } else tmp.release();
+  op.factorised = false;
   return B2D_OK;
 }
 
@@ -3010,7 +3079,17 @@ int b2d_cache_drop(b2d_ctx* ctx, uint64_t token) {
   auto it = ctx->cache.find(token);
   if (it == ctx->cache.end()) return B2D_OK;
   if (ctx->has_device) { cudaSetDevice(ctx->device); cudaStreamSynchronize(ctx->stream); }
-  if (it->second.dev.p) { ctx->cache_device_doubles -= it->second.doubles; it->second.dev.release(); }
+  if (it->second.dev.p) {
+    ctx->cache_device_doubles -= it->second.doubles;
+    ctx->spare_bufs.push_back(it->second.dev);   // keep a few: the next renormalised block of this size takes it over
+    it->second.dev = DevBuf();
+    while (ctx->spare_bufs.size() > 6) {         // bounded: release the smallest
+      size_t k = 0;
+      for (size_t i = 1; i < ctx->spare_bufs.size(); ++i) if (ctx->spare_bufs[i].cap < ctx->spare_bufs[k].cap) k = i;
+      ctx->spare_bufs[k].release();
+      ctx->spare_bufs.erase(ctx->spare_bufs.begin() + k);
+    }
+  }
   if (it->second.pinned) cudaFreeHost(it->second.pinned);
   ctx->cache.erase(it);
   return B2D_OK;

@@ -4,6 +4,9 @@
 
 #include <math.h>
 
+#include <algorithm>
+#include <vector>
+
 #include "gemm_grouped.cuh"
 #define B2D_EIG_KERNELS
 #include "eig_block_jacobi.cuh"
@@ -536,29 +539,78 @@ __global__ void __launch_bounds__(256) diag_kernel(const BlockDesc* __restrict__
   }
 }
 
-// c += coef (a x b) on sub-blocks: one CTA per task; threads run over the destination sub-block with the column index fastest
-// (coalesced stores; A / B elements come from L1/L2 - B is 1 x 1 for a one-site dot).  Tasks of one launch never overlap.
-__global__ void __launch_bounds__(256) kron_scatter_kernel(const KronTask* __restrict__ tasks, int ntasks) {
-  for (int t = blockIdx.x; t < ntasks; t += gridDim.x) {
-    const KronTask k = tasks[t];
+// c += coef (a x b) on sub-blocks (HBM-bound scatter).  Work item = a band of KRON_BAND destination rows of one task (`tiles`, built on the
+// host: big and small pieces load-balance over the SMs); 8 warps, 4 rows each, lanes run along the destination columns (coalesced stores).
+// The common case - B is the 1 x 1 block of a one-site dot or the identity on it - needs no index arithmetic per element: the
+// destination is a scaled (possibly transposed) copy of the A block; a transposed A goes through a 32 x 33 shared-memory tile so that
+// both the reads and the writes are coalesced.  k.pad bit 0: the destination piece is known to be zero (first contribution to freshly
+// zero-filled storage): store instead of read-modify-write.  Tasks of one launch never overlap.
+
+__global__ void __launch_bounds__(256) kron_scatter_kernel(const KronTask* __restrict__ tasks, const KronTile* __restrict__ tiles, int ntiles) {
+  __shared__ double tile[32][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int w = blockIdx.x; w < ntiles; w += gridDim.x) {
+    const KronTask k = tasks[tiles[w].task];
     const double* A = reinterpret_cast<const double*>(k.a);
     const double* B = reinterpret_cast<const double*>(k.b);
     double* D = reinterpret_cast<double*>(k.dst);
     const int rows = k.a_rows * k.b_rows, cols = k.a_cols * k.b_cols;
-    const int64_t n = (int64_t)rows * cols;
-    for (int64_t e = threadIdx.x; e < n; e += blockDim.x) {
-      const int r = (int)(e / cols), c = (int)(e % cols);
-      const int ia = r / k.b_rows, ib = r % k.b_rows, ja = c / k.b_cols, jb = c % k.b_cols;
-      double va, vb;
-      if (A) va = k.a_t ? A[(int64_t)ja * k.lda + ia] : A[(int64_t)ia * k.lda + ja]; else va = ia == ja ? 1.0 : 0.0;
-      if (B) vb = k.b_t ? B[(int64_t)jb * k.ldb + ib] : B[(int64_t)ib * k.ldb + jb]; else vb = ib == jb ? 1.0 : 0.0;
-      D[(int64_t)(k.row0 + r) * k.ldd + k.col0 + c] += k.coef * va * vb;
+    const int r0 = tiles[w].band * KRON_BAND, r1 = min(r0 + KRON_BAND, rows);
+    const bool store = (k.pad & 1) != 0;
+    if (k.b_rows == 1 && k.b_cols == 1) {
+      const double f = k.coef * (B ? B[0] : 1.0);
+      if (!A) {                                   // identity (x) scalar: only the diagonal of the band
+        for (int r = r0 + threadIdx.x; r < r1; r += blockDim.x)
+          if (r < cols) { double* d = D + (int64_t)(k.row0 + r) * k.ldd + k.col0 + r; *d = store ? f : *d + f; }
+        // a stored piece must be fully defined: the off-diagonal part stays as it is (zero-filled storage) in both modes
+      } else if (!k.a_t) {
+        for (int r = r0 + warp; r < r1; r += 8) {
+          const double* src = A + (int64_t)r * k.lda;
+          double* dst = D + (int64_t)(k.row0 + r) * k.ldd + k.col0;
+          if (store) { for (int c = lane; c < cols; c += 32) dst[c] = f * src[c]; }
+          else { for (int c = lane; c < cols; c += 32) dst[c] += f * src[c]; }
+        }
+      } else {                                    // op(A)(r, c) = A[c][r]: 32 x 32 tiles through shared memory
+        for (int c0 = 0; c0 < cols; c0 += 32) {
+          __syncthreads();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int cc = c0 + warp + 8 * j, rr = r0 + lane;
+            tile[warp + 8 * j][lane] = (cc < cols && rr < r1) ? A[(int64_t)cc * k.lda + rr] : 0.0;
+          }
+          __syncthreads();
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int rr = r0 + warp + 8 * j, cc = c0 + lane;
+            if (rr < r1 && cc < cols) {
+              double* d = D + (int64_t)(k.row0 + rr) * k.ldd + k.col0 + cc;
+              const double v = f * tile[lane][warp + 8 * j];
+              *d = store ? v : *d + v;
+            }
+          }
+        }
+      }
+      continue;
+    }
+    // general Kronecker product (a dot of several sites: warm-up blocks): row indices are split once per row
+    for (int r = r0 + warp; r < r1; r += 8) {
+      const int ia = r / k.b_rows, ib = r % k.b_rows;
+      double* dst = D + (int64_t)(k.row0 + r) * k.ldd + k.col0;
+      for (int c = lane; c < cols; c += 32) {
+        const int ja = c / k.b_cols, jb = c % k.b_cols;
+        double va, vb;
+        if (A) va = k.a_t ? A[(int64_t)ja * k.lda + ia] : A[(int64_t)ia * k.lda + ja]; else va = ia == ja ? 1.0 : 0.0;
+        if (B) vb = k.b_t ? B[(int64_t)jb * k.ldb + ib] : B[(int64_t)ib * k.ldb + jb]; else vb = ib == jb ? 1.0 : 0.0;
+        const double v = k.coef * va * vb;
+        dst[c] = store ? v : dst[c] + v;
+      }
     }
   }
 }
-cudaError_t launch_kron_scatter(const KronTask* tasks, int ntasks, cudaStream_t s, int64_t* launches) {
-  if (ntasks == 0) return cudaSuccess;
-  kron_scatter_kernel<<<min(ntasks, 148 * 16), 256, 0, s>>>(tasks, ntasks);
+
+cudaError_t launch_kron_scatter(const KronTask* tasks, const KronTile* tiles, int ntiles, cudaStream_t s, int64_t* launches) {
+  if (ntiles == 0) return cudaSuccess;
+  kron_scatter_kernel<<<min(ntiles, 148 * 8), 256, 0, s>>>(tasks, tiles, ntiles);
   B2D_LAUNCH_CHECK();
   return cudaSuccess;
 }

@@ -73,7 +73,10 @@ struct KronTask {
   int32_t b_rows, b_cols, ldb, b_t;
   int32_t row0, col0, ldd, pad;
 };
-cudaError_t launch_kron_scatter(const KronTask* tasks, int ntasks, cudaStream_t s, int64_t* launches);
+// work item of the scatter kernel: a band of KRON_BAND destination rows of task `task` (index into the task array of the launch)
+constexpr int KRON_BAND = 32;
+struct KronTile { int32_t task, band; };
+cudaError_t launch_kron_scatter(const KronTask* tasks, const KronTile* tiles, int ntiles, cudaStream_t s, int64_t* launches);
 // diagonals of operator sector blocks gathered into a compact pool (stride ld + 1 -> 1) before diag(H) reads them thousands of times
 struct DiagGather {
   int64_t src;      // absolute byte address of the first diagonal element

@@ -323,10 +323,10 @@ def make_product_case(norbs=40, nelec=40, M=4000, left_sites=None, seed=20260, s
     return dict(left=(s_child, l_dot, lt, left), right=(e_child, r_dot, rt, right), h1=h1, h2=h2, dq=(nelec, 0, 0), norbs=norbs, seed=seed)
 
 
-def make_big_block_from_products(case, device=0, options=None, factorised=True):
+def make_big_block_from_products(case, device=0, options=None, factorised=True, rank=0, nranks=1):
     """SpinBlock whose two children are built ON THE DEVICE from the case's grandchildren: factorised (no enlarged operator is ever
     materialised) or, for comparison at small M, materialised by the scatter kernel."""
     opts = dict(options or {})
     opts["factorised"] = 1 if factorised else 0
-    return SpinBlock.from_products(case["left"], case["right"], case["dq"], norbs=case["norbs"], device=device, options=opts,
+    return SpinBlock.from_products(case["left"], case["right"], case["dq"], norbs=case["norbs"], device=device, options=opts, rank=rank, nranks=nranks,
                                    integrals=(case["h1"], case["h2"], np.zeros(case["norbs"], np.int32)), fill_seed=case["seed"])

@@ -299,6 +299,9 @@ int b2d_build_enlarged_op(b2d_ctx* ctx, int optype, int norb, const int32_t* orb
 int b2d_stash_product(b2d_ctx* ctx, int slot, int is_loop, int nsites, const int32_t* sites);
 int b2d_stash_side(b2d_ctx* ctx, int slot, int from_side);
 int b2d_assemble_big(b2d_ctx* ctx);
+/* Write a FACTORISED operator (option "factorised") of child `side` of the assembled big block out as dense sector blocks, in place; it is
+ * an ordinary materialised operator afterwards.  The benchmark uses it to run the same operator pair through both forms at full size. */
+int b2d_materialise_op(b2d_ctx* ctx, int side, int op_id);
 /* Measurement: out[0..3] = {products, scatter tasks, ALGORITHMIC bytes of those tasks (8 x (|A| + |B| + 2 |destination piece|): operands read
  * once, destination read-modified-written), launches of the last batched flush} since b2d_set_product_stateinfo; with option opbuild_batch
  * b2d_last_timing gives the CUDA-event time of the batched flush. */

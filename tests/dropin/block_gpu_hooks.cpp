@@ -87,6 +87,20 @@ bool env_on(const char* k) { const char* v = getenv(k); return v && *v && strcmp
 
 struct OpRef { SparseMatrix* elem; int id; };
 
+// B2D_DROPIN_TIMING=1: wall time per phase of the hooks, printed at exit (diagnostic)
+struct PhaseTimes {
+  std::map<string, double> t;
+  ~PhaseTimes() {
+    if (!getenv("B2D_DROPIN_TIMING")) return;
+    for (std::map<string, double>::iterator it = t.begin(); it != t.end(); ++it) fprintf(stderr, "B2D_TIMING %-28s %.3f s\n", it->first.c_str(), it->second);
+  }
+} g_phase;
+struct Phase {
+  const char* name; double t0;
+  explicit Phase(const char* n) : name(n), t0(now_s()) {}
+  ~Phase() { g_phase.t[name] += now_s() - t0; }
+};
+
 // ---- token that names a device-resident block inside the reference's host copy --------------------------------------
 // A quiet NaN with a recognisable payload: anything on the host that consumed the "matrices" numerically would turn into NaN and fail
 // loudly instead of silently using zeros.
@@ -214,7 +228,8 @@ void upload_block(int side, SpinBlock& b, vector<OpRef>* keep) {
     vector<int32_t> cq(3 * (size_t)cnq), cdims(cnq), csites(cns);
     ck(b2d_cache_block_sectors(g.ctx, tok, cq.data(), cdims.data(), csites.data()), "b2d_cache_block_sectors");
     if (cnq != nq || cq != q || cdims != dims || csites != sites) die("device block cache: the cached block's StateInfo differs from the host block's");
-    ck(b2d_cache_use(g.ctx, tok, side, b.is_loopblock() ? 1 : 0), "b2d_cache_use");
+    { Phase ph("cache_use"); ck(b2d_cache_use(g.ctx, tok, side, b.is_loopblock() ? 1 : 0), "b2d_cache_use"); }
+    Phase ph2("cache_verify");
     int k = 0;
     for (std::map<opTypes, boost::shared_ptr<Op_component_base> >::iterator it = b.ops.begin(); it != b.ops.end(); ++it) {
       Op_component_base& arr = *it->second;
@@ -781,8 +796,8 @@ void wrap_transform(SpinBlock* self, vector<Matrix>& rot) {
     if (kept[q]) flat.insert(flat.end(), rot[q].Store(), rot[q].Store() + rot[q].Storage());
   }
   if (flat.empty()) flat.push_back(0.0);
-  ck(b2d_rotation_upload(g.ctx, kept.data(), flat.data()), "b2d_rotation_upload");
-  ck(b2d_transform_operators(g.ctx), "b2d_transform_operators");
+  { Phase ph("rot_upload"); ck(b2d_rotation_upload(g.ctx, kept.data(), flat.data()), "b2d_rotation_upload"); }
+  { Phase ph("transform_device"); ck(b2d_transform_operators(g.ctx), "b2d_transform_operators"); }
   bool check = env_on("B2D_DROPIN_CHECK");
   const char* tmode = getenv("B2D_DROPIN_TRANSFORM");
   if (check || (tmode && string(tmode) == "reference")) {
@@ -794,6 +809,7 @@ void wrap_transform(SpinBlock* self, vector<Matrix>& rot) {
   } else {
     // the same bookkeeping done here (save_load_block.C:270-316), without building anything on the CPU: the un-rotated
     // operators are already on the device
+    Phase ph("transform_host_bookkeeping");
     StateInfo before = self->braStateInfo;
     vector<SpinQuantum> nquanta; vector<int> nstates, nmap;
     for (int q = 0; q < nq; ++q)
@@ -819,7 +835,8 @@ void wrap_transform(SpinBlock* self, vector<Matrix>& rot) {
     // the rotated operators stay on the device; the host copy keeps its zeroed blocks and gets the entry's token in the first
     // element of every sector block (SpinBlock::store / restore and the reference's copies carry it along)
     uint64_t tok = 0;
-    ck(b2d_cache_put_rotated(g.ctx, &tok), "b2d_cache_put_rotated");
+    { Phase ph("cache_put"); ck(b2d_cache_put_rotated(g.ctx, &tok), "b2d_cache_put_rotated"); }
+    Phase ph3("cache_tag_drop");
     const double tag = token_to_double(tok);
     for (size_t k = 0; k < g.left_ops.size(); ++k) {
       SparseMatrix& op = *g.left_ops[k].elem;
@@ -840,7 +857,8 @@ void wrap_transform(SpinBlock* self, vector<Matrix>& rot) {
   double worst = 0, scale = 0;
   vector<uint8_t> allowed((size_t)nnew * nnew);
   vector<double> data((size_t)std::max<int64_t>(b2d_rotated_total_size(g.ctx), 1));
-  ck(b2d_rotated_download_all(g.ctx, data.data()), "b2d_rotated_download_all");   // one device pass + one copy for every operator
+  { Phase ph("rotated_download"); ck(b2d_rotated_download_all(g.ctx, data.data()), "b2d_rotated_download_all"); }   // one device pass + one copy for every operator
+  Phase ph4("rotated_copy_to_host_blocks");
   size_t off = 0;
   for (size_t k = 0; k < g.left_ops.size(); ++k) {
     SparseMatrix& op = *g.left_ops[k].elem;

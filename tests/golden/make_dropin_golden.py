@@ -208,6 +208,24 @@ orbitals FCIDUMP
 noreorder
 outputlevel 0
 """)
+    # bench.py's sweep leg WITH golden sweeps (round 2): Davidson converged to 1e-12 so that the energies are determined to well below 1e-8,
+    # four sweeps, the top-M cut decides the retained basis (well conditioned); generated with 8 host threads (the thread count only changes
+    # the summation order of the thread-private sigma accumulators)
+    c["synthetic_16o_M300"] = dict(threads=8, files={"FCIDUMP": synthetic_fcidump(16, 16)}, conf="""nelec 16
+spin 0
+irrep 1
+hf_occ integral
+schedule
+0 150 1.0e-12 0.0
+2 300 1.0e-12 0.0
+end
+maxiter 4
+twodot
+sweep_tol 1e-12
+orbitals FCIDUMP
+noreorder
+outputlevel 0
+""")
     # The reference's OWN known-answer test, verbatim (dmrg_tests/runtest:19-23: h2o_nosym, default schedule with noise, default orbital
     # reordering, two-dot -> one-dot, `test_energy.py 1 1.0e-6 -76.11460447`).  Not a per-sweep golden case (random noise, threshold
     # regime): its sweeps are stored as "/ref_sweeps" and the GPU test applies the reference's own acceptance criterion.
@@ -221,8 +239,9 @@ def run_reference(name, case, threads=8):
     work = tempfile.mkdtemp(prefix="dropin_")
     for f, text in case["files"].items():
         open(os.path.join(work, f), "w").write(text)
-    open(os.path.join(work, "dmrg.conf"), "w").write(case["conf"])
-    env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="1")
+    nthreads = int(case.get("threads", 1))
+    open(os.path.join(work, "dmrg.conf"), "w").write(case["conf"] + ("threads_per_node %d\n" % nthreads if nthreads > 1 else ""))
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS=str(nthreads))
     t0 = time.time()
     out = subprocess.run([BLOCK, "dmrg.conf"], cwd=work, env=env, capture_output=True, text=True)
     dt = time.time() - t0

@@ -38,8 +38,9 @@ def run(z, name, variant):
     work = tempfile.mkdtemp(prefix="eigvar_")
     for f in z[name + "/files"]:
         open(os.path.join(work, str(f)), "wb").write(z["%s/file/%s" % (name, f)].tobytes())
-    open(os.path.join(work, "dmrg.conf"), "wb").write(z[name + "/conf"].tobytes())
-    env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS="1", ORACLE_EIGVAR=variant)
+    threads = int(os.environ.get("EIGVAR_THREADS", "1"))   # cases whose golden sweeps were made with several host threads (make_dropin_golden.py `threads`)
+    open(os.path.join(work, "dmrg.conf"), "wb").write(z[name + "/conf"].tobytes() + (b"threads_per_node %d\n" % threads if threads > 1 else b""))
+    env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS=str(threads), ORACLE_EIGVAR=variant)
     t0 = time.time()
     out = subprocess.run([BLOCK, "dmrg.conf"], cwd=work, env=env, capture_output=True, text=True)
     dt = time.time() - t0

@@ -69,23 +69,46 @@ def test_dropin_fails_loudly_without_a_device():
 
 # Conditioning of the comparison.  Every arithmetic step of the path is reproduced to ~1e-13 (see
 # test_every_hook_against_the_cpu_function), but ONE output of the path is not unique: the eigenvectors of the reduced density
-# matrix inside (near-)degenerate eigenspaces - in particular the near-null space (weights 1e-13 .. 1e-10, i.e. squares of
-# 3e-7 .. 1e-5 amplitudes of an FP64 wavefunction) that the reference keeps whenever its ABSOLUTE threshold (weight > 1e-13,
-# rotationmat.C:161) rather than the top-M cut decides the retained basis.  dsyev_ and the device eigen-solvers return different,
-# equally valid bases there, the retained subspaces differ by ~1e-3 rotations among states of weight ~1e-13, and while the
-# sweeps are still growing the basis (largest discarded weight < 1e-10) that is amplified into visibly different intermediate
-# energies, occasionally into a different local minimum at small M (h2o M = 60).  Measured on B200: with ONLY the
-# eigen-decomposition left to the reference (B2D_DROPIN_EIG=host, everything else on the GPU) every sweep of every case below
-# agrees to <= 1.5e-8 Eh, <= 1e-8 outside the threshold-regime sweeps (test_threshold_regime_cases_with_reference_eigenvectors).  The unmodified reference itself moves by up to
-# 7e-9 Eh in such sweeps when only its OpenMP thread count changes.
-# So: sweeps whose own or previous largest discarded weight is < 1e-10, and the cases listed here, get the documented looser
-# bound on the full-GPU run; every other sweep - and the final, converged one unless listed in NOT_CONVERGED_TO_SAME_MINIMUM - must
-# agree to 1e-8 Eh.
-THRESHOLD_SWEEP_DW = 1e-10
-THRESHOLD_SWEEP_BOUND = {"h2o_nosym_M500": 5e-3, "hubbard_L16_M1000": 1e-5, "h2o_nosym_M60": 1e-4}
-THRESHOLD_SWEEP_BOUND_DEFAULT = 1e-6
-NOT_CONVERGED_TO_SAME_MINIMUM = {"h2o_nosym_M60"}
+# matrix inside (near-)degenerate eigenspaces - in particular the near-null space (weights 1e-13 .. 1e-10) that the reference keeps
+# whenever its ABSOLUTE threshold (weight > 1e-13, rotationmat.C:161) rather than the top-M cut decides the retained basis.  While a
+# calculation is still growing its basis, which vectors of that space are kept steers the following block iterations, and the
+# intermediate sweep energies are chaotic in it.  This is a property of the REFERENCE, measured, not assumed:
+# tests/golden/eigvar_spread.npz (made by tests/golden/make_eigvar_golden.py from oracle/_ref/block_eigvar, summary in
+# profiles/r02_reference_eigensolver_spread.txt) holds the per-sweep energies of the unmodified reference with ONLY the eigen-solver
+# of diagonalise_dm exchanged - dsyev_ (control: bit-identical), dsyevd_ / dsyevr_ from the same OpenBLAS, dsyev_ on rho perturbed by
+# one rounding error per element, a plain one-sided Jacobi.  Where the reference does not move (c2_d2h, synthetic, Hubbard M = 80:
+# spread <= 1e-9) the GPU path is held to north_star's 1e-8 Eh; where it moves (Hubbard M = 1000: 2.9e-8 in one sweep; H2O M = 60:
+# 5e-5, the variants end in different minima; H2O M = 500: 1.8e-2 in sweeps 3-4, 1e-7 at the end) no implementation whose density
+# matrix or eigen-solver differs in the last bit can be held to 1e-8, and the bound is that measured spread with a factor 10 for the
+# small sample (four alternative solvers of a heavy-tailed quantity).  Measured on B200 (profiles/r02_dropin_sweeps.txt): H2O M = 500
+# deviates 6.9e-4 where the reference's own spread is 1.7e-2 and converges to the reference's energy to 1e-10.
+SPREAD = os.path.join(ROOT, "tests", "golden", "eigvar_spread.npz")
+SPREAD_FACTOR = 10.0
 ILL_CONDITIONED = ["h2o_nosym_M60", "h2o_nosym_M500", "hubbard_L16_M1000"]
+
+
+def sweep_bounds(name, n):
+    """Per sweep line: max(1e-8 Eh, 10 x the reference-vs-reference spread measured for that sweep)."""
+    with np.load(SPREAD) as z:
+        assert name + "/spread" in z.files, "no reference-vs-reference spread recorded for " + name
+        spread = z[name + "/spread"]
+    assert len(spread) == n
+    return [max(1e-8, SPREAD_FACTOR * float(x)) for x in spread]
+
+
+def test_spread_file_covers_every_case():
+    """CPU: every golden case has its reference-vs-reference spread, the control variant (the reference's own dsyev_ re-issued through the
+    hook) reproduces the unmodified reference digit for digit, and three quarters of all sweep lines are held to the strict 1e-8 bound."""
+    strict = total = 0
+    with np.load(SPREAD) as z, np.load(CASES) as g:
+        for n in case_names():
+            ref = np.array([e for _, _, _, e in parse_sweeps(g[n + "/sweeps"].tobytes().decode())])
+            variants = [str(v) for v in z[n + "/variants"]]
+            assert variants[0] == "dsyev" and len(variants) >= 4
+            assert np.abs(z[n + "/energies"][0] - ref).max() == 0.0, n
+            b = sweep_bounds(n, len(ref))
+            strict += sum(x == 1e-8 for x in b); total += len(b)
+    assert strict >= 0.75 * total, (strict, total)
 
 
 @pytest.mark.gpu
@@ -96,21 +119,14 @@ def test_sweep_energies_match_reference(name):
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     got = parse_sweeps(out.stdout)
     assert len(got) == len(golden), (len(got), len(golden), out.stdout[-2000:])
-    nroots = len({s for _, s, _, _ in golden})
+    bounds = sweep_bounds(name, len(golden))
     worst, strict = 0.0, 0
     for k, ((m1, s1, dw1, e1), (m2, s2, dw2, e2)) in enumerate(zip(got, golden)):
         assert (m1, s1) == (m2, s2)
         worst = max(worst, abs(e1 - e2))
-        final = k >= len(golden) - nroots
-        prev_dw = golden[k - nroots][2] if k >= nroots else dw2
-        threshold_sweep = min(dw2, prev_dw) < THRESHOLD_SWEEP_DW or name in NOT_CONVERGED_TO_SAME_MINIMUM
-        if name in NOT_CONVERGED_TO_SAME_MINIMUM:
-            final = False
-        bound = THRESHOLD_SWEEP_BOUND.get(name, THRESHOLD_SWEEP_BOUND_DEFAULT) if (threshold_sweep and not final) else 1e-8
-        strict += bound == 1e-8
-        assert abs(e1 - e2) <= bound, (name, k, m1, s1, e1, e2, bound)          # north_star: per-sweep energies within 1e-8 Eh
+        strict += bounds[k] == 1e-8
+        assert abs(e1 - e2) <= bounds[k], (name, k, m1, s1, e1, e2, bounds[k])   # north_star: per-sweep energies within 1e-8 Eh (or the reference's own spread)
         assert abs(dw1 - dw2) <= 2e-2 * abs(dw2) + 5e-12, (name, dw1, dw2)      # printed with 4 significant digits
-    assert strict >= nroots or name in NOT_CONVERGED_TO_SAME_MINIMUM
     assert "n_multiply" in stats and "launches" in stats                         # the hooks ran on the device
     print("%s: %d sweep energies (%d at the 1e-8 bound), worst |dE| = %.2e Eh" % (name, len(got), strict, worst))
 
@@ -125,11 +141,12 @@ def test_threshold_regime_cases_with_reference_eigenvectors(name):
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     got = parse_sweeps(out.stdout)
     assert len(got) == len(golden)
-    nroots = len({s for _, s, _, _ in golden})
+    with np.load(SPREAD) as z:
+        spread = z[name + "/spread"]
     for k, ((m1, s1, dw1, e1), (m2, s2, dw2, e2)) in enumerate(zip(got, golden)):
-        prev_dw = golden[k - nroots][2] if k >= nroots else dw2
-        # threshold-regime sweeps: the reference's own reproducibility there is ~7e-9 (thread count), so 5e-8; otherwise 1e-8
-        bound = 5e-8 if min(dw2, prev_dw) < THRESHOLD_SWEEP_DW else 1e-8
+        # sweeps in which the reference itself moves under a change of eigen-solver: 5e-8 (its own sensitivity to a one-rounding-error
+        # perturbation of rho there is up to 7e-8, variant "ulp"); every other sweep 1e-8
+        bound = 5e-8 if spread[k] > 1e-9 else 1e-8
         assert abs(e1 - e2) <= bound, (name, k, m1, s1, e1, e2)
     assert abs(got[-1][3] - golden[-1][3]) <= 1e-8
     assert "n_multiply" in stats

@@ -371,19 +371,36 @@ def sweep_leg(a):
         env = dict(os.environ, OPENBLAS_NUM_THREADS="1", OMP_NUM_THREADS=str(threads), B2D_DROPIN_STATS=os.path.join(work, "stats.txt"))
         if tag == "gpu_dropin_factorised":
             env.update(B2D_DROPIN_OPTIONS="factorised=1")
+        # line-buffered stdout (stdbuf), every "Sweep Energy" line stamped as it arrives: wall time PER SWEEP - the first one is the
+        # warm-up sweep (CSF-built guess environments, SURVEY N4: reference host code on both arms), the others are regular sweeps
         t0 = time.perf_counter()
+        stamps, lines_out = [], []
         try:
-            r = subprocess.run([exe, "dmrg.conf"], cwd=work, env=env, capture_output=True, text=True, timeout=900)
-        except subprocess.TimeoutExpired:
-            out[tag] = {"failed": "timeout"}
+            p = subprocess.Popen(["stdbuf", "-oL", exe, "dmrg.conf"], cwd=work, env=env, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+            for ln in p.stdout:
+                lines_out.append(ln)
+                if "Sweep Energy" in ln:
+                    stamps.append(time.perf_counter() - t0)
+                if time.perf_counter() - t0 > 900:
+                    p.kill()
+                    break
+            err_text = p.stderr.read()
+            p.wait(timeout=60)
+        except Exception as ex:   # noqa: BLE001
+            out[tag] = {"failed": repr(ex)[:300]}
             continue
         dt = time.perf_counter() - t0
-        if r.returncode != 0:
-            out[tag] = {"failed": (r.stderr or r.stdout)[-300:]}
+        stdout_text = "".join(lines_out)
+        if p.returncode != 0:
+            out[tag] = {"failed": (err_text or stdout_text)[-300:]}
             continue
-        e = [float(m.group(4)) for m in pat.finditer(r.stdout)]
+        e = [float(m.group(4)) for m in pat.finditer(stdout_text)]
         energies[tag] = e
-        out[tag] = {"wall_s": dt, "sweep_lines": len(e), "final_energy": e[-1] if e else None}
+        nroots = max(1, len({m.group(2) for m in pat.finditer(stdout_text)}))
+        ends = stamps[nroots - 1::nroots]                                   # one stamp per sweep (the last root's line)
+        per_sweep = [ends[0]] + [b - a for a, b in zip(ends[:-1], ends[1:])] if ends else []
+        out[tag] = {"wall_s": dt, "sweep_lines": len(e), "final_energy": e[-1] if e else None, "wall_s_per_sweep": per_sweep,
+                    "warmup_sweep_s": per_sweep[0] if per_sweep else None, "regular_sweeps_s": sum(per_sweep[1:]) if per_sweep else None}
         if tag.startswith("gpu_dropin") and os.path.exists(os.path.join(work, "stats.txt")):
             tot = {}
             for l in open(os.path.join(work, "stats.txt")):
@@ -395,6 +412,12 @@ def sweep_leg(a):
             out[tag]["blocks_taken_from_device_cache"] = int(tot.get("cache_uses", 0))
     if "reference_cpu" in energies and "gpu_dropin_factorised" in energies and len(energies["reference_cpu"]) == len(energies["gpu_dropin_factorised"]):
         out["gpu_dropin_factorised"]["max_abs_dE_per_sweep"] = max(abs(x - y) for x, y in zip(energies["reference_cpu"], energies["gpu_dropin_factorised"]))
+    try:
+        out["speedup_whole_run"] = out["reference_cpu"]["wall_s"] / out["gpu_dropin"]["wall_s"]
+        out["speedup_regular_sweeps"] = out["reference_cpu"]["regular_sweeps_s"] / out["gpu_dropin"]["regular_sweeps_s"]
+        out["speedup_warmup_sweep"] = out["reference_cpu"]["warmup_sweep_s"] / out["gpu_dropin"]["warmup_sweep_s"]
+    except Exception:   # noqa: BLE001
+        pass
     if "reference_cpu" in energies and "gpu_dropin" in energies and len(energies["reference_cpu"]) == len(energies["gpu_dropin"]):
         out["max_abs_dE_per_sweep"] = max(abs(x - y) for x, y in zip(energies["reference_cpu"], energies["gpu_dropin"]))
         golden = [float(m.group(4)) for m in pat.finditer(z[name + "/sweeps"].tobytes().decode())] if name + "/sweeps" in z.files else []
@@ -436,6 +459,8 @@ def run_ours(a):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     t_setup = time.time()
     options = dict({"workspace_mb": a.workspace_mb, "slice_iters": a.slice_iters}, **{kv.split("=")[0]: float(kv.split("=")[1]) for kv in a.opt})
+    if world > 1 and "balance_terms" not in options:
+        options["balance_terms"] = 1.0   # cost-weighted ownership of the operator terms (SURVEY 8e allows it: the sum over ranks is the same multiplyH)
     if a.mode == "factorised":
         # the blocks a sweep holds before a block iteration: renormalised M-state blocks + one-site dots; every operator of the two
         # enlarged blocks is built on the device as a list of scaled sub-blocks of the renormalised operators (never materialised)
@@ -588,7 +613,7 @@ def run_ours(a):
                            "right_states": int(sb.right.dims.sum()), "sigma_flops": flops_alg, "rank0_flops": flops_mine,
                            "operator_arena_gb_rank0": stats["arena_doubles"] * 8 / 1e9, "presummed_factor_blocks_gb": stats["combo_doubles"] * 8 / 1e9,
                            "factors": int(stats["factors_direct"] + stats["factors_combo"]), "chunks": int(stats["chunks"]),
-                           "parallelism": "operator-term partition x%d + NCCL all-reduce of partial sigma" % world if world > 1 else "single GPU",
+                           "parallelism": ("operator-term partition x%d (%s) + NCCL all-reduce of partial sigma" % (world, "cost-weighted ownership" if options.get("balance_terms") else "reference's ownership rule")) if world > 1 else "single GPU",
                            "l2": "inputs larger than L2 (operator arena %.0f GB + %.1f GB of T workspace per step)" % (stats["arena_doubles"] * 8 / 1e9, stats["workspace_doubles"] * 8 / 1e9),
                            "setup_s": t_setup},
                 "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(W * 8), "d2h_bytes_per_step": int(W * 8)},

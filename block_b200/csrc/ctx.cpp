@@ -213,6 +213,7 @@ struct b2d_ctx {
                                             // instead of two: ~7 % fewer executed flops at M = 4000 for ~5 GB more memory); off: both stay direct factors
   int64_t combo_doubles = 0;                // pre-summed factor blocks allocated since the last reset
   int64_t nsubs_direct = 0, nsubs_combo = 0, ncombos = 0;
+  bool balance_terms = false;               // option "balance_terms": cost-weighted term ownership under a term partition (default: the reference's rule)
   bool opbuild_batch = true;                // b2d_build_enlarged_op defers its scatter tasks: one launch per ROUND for a whole child block
   std::vector<KronTask> pend_kron;          // deferred tasks ...
   std::vector<int> pend_kron_round;         // ... and the round of each: how many earlier tasks hit the same destination piece
@@ -329,7 +330,9 @@ int upload_desc(b2d_ctx* ctx, DevBuf& buf, const void* host, size_t bytes) {
 
 // Scatter tasks round by round: tasks[round_begin[r] .. round_begin[r + 1]) never overlap in their destinations; the rounds run in stream
 // order.  One upload of the tasks, one of the band list (every task cut into bands of KRON_BAND destination rows for load balance).
-int run_kron_rounds(b2d_ctx* ctx, const std::vector<KronTask>& tasks, const std::vector<int>& round_begin) {
+void begin_timing(b2d_ctx* ctx);
+void end_timing(b2d_ctx* ctx);
+int run_kron_rounds(b2d_ctx* ctx, const std::vector<KronTask>& tasks, const std::vector<int>& round_begin, bool timed = false) {
   if (tasks.empty()) return B2D_OK;
   int rc = upload_desc(ctx, ctx->kron_tasks, tasks.data(), tasks.size() * sizeof(KronTask));
   if (rc) return rc;
@@ -345,9 +348,11 @@ int run_kron_rounds(b2d_ctx* ctx, const std::vector<KronTask>& tasks, const std:
   tile_begin[round_begin.size() - 1] = (int)tiles.size();
   rc = upload_desc(ctx, ctx->kron_tiles, tiles.data(), tiles.size() * sizeof(KronTile));
   if (rc) return rc;
+  if (timed) begin_timing(ctx);   // b2d_last_timing: device time of the scatter launches alone (descriptors are resident)
   for (size_t r = 0; r + 1 < round_begin.size(); ++r)
     CU(launch_kron_scatter((const KronTask*)ctx->kron_tasks.p, (const KronTile*)ctx->kron_tiles.p + tile_begin[r], tile_begin[r + 1] - tile_begin[r], ctx->stream,
                            &ctx->launches));
+  if (timed) end_timing(ctx);
   return B2D_OK;
 }
 
@@ -695,6 +700,7 @@ int b2d_set_option(b2d_ctx* ctx, const char* key, double value) {
   else if (k == "opbuild_batch") ctx->opbuild_batch = value != 0;
   else if (k == "factorised") ctx->factorised = value != 0;
   else if (k == "presum_identity") ctx->presum_identity = value != 0;
+  else if (k == "balance_terms") ctx->balance_terms = value != 0;
   else if (k == "cache_device_mb") ctx->cache_device_mb = value;
   else return fail(ctx, B2D_ERR_ARG, "unknown option " + k);
   return B2D_OK;
@@ -879,6 +885,15 @@ int b2d_plan(b2d_ctx* ctx, const int32_t* psi_dq, double core_energy, int hubbar
     int dq[3] = {psi_dq[0], psi_dq[1], psi_dq[2]};
     ctx->psi.build(ctx->side[0], ctx->side[1], dq);
     ctx->terms_all = enumerate_terms(ctx->side[0], ctx->side[1], core_energy, ctx->hubbard, norbs, nranks, ctx->am);
+    const int64_t budget0 = (int64_t)(ctx->workspace_mb * 1024.0 * 1024.0 / 8.0);
+    ctx->flops_all = -1.0;
+    if (nranks > 1 && ctx->balance_terms) {
+      // option "balance_terms": replace the reference's static rule (i % n, trimap_2d % n: max / mean flops 1.03 at 8 ranks) by a
+      // cost-weighted assignment; the SUM over ranks is the same multiplyH
+      Schedule all = build_schedule(ctx->side[0], ctx->side[1], ctx->psi, ctx->terms_all, 0, budget0, ctx->forced_class, ctx->am);
+      ctx->flops_all = all.flops_alg;
+      balance_owners(ctx->terms_all, all.term_flops, nranks);
+    }
     ctx->terms_mine.clear();
     for (const Term& t : ctx->terms_all) if (t.owner == rank) ctx->terms_mine.push_back(t);
     if (ctx->has_device) {   // materialise the device-allocated operators this rank's terms use
@@ -924,11 +939,11 @@ int b2d_plan(b2d_ctx* ctx, const int32_t* psi_dq, double core_energy, int hubbar
     }
     int64_t budget = (int64_t)(ctx->workspace_mb * 1024.0 * 1024.0 / 8.0);
     ctx->sched = build_schedule(ctx->side[0], ctx->side[1], ctx->psi, ctx->terms_mine, 0, budget, ctx->forced_class, ctx->am, ctx->slice_iters);
-    if (nranks > 1) {
+    if (nranks > 1 && ctx->flops_all < 0.0) {
       // algorithmic flops of the whole sigma (all ranks) without keeping the other ranks' schedules
       Schedule all = build_schedule(ctx->side[0], ctx->side[1], ctx->psi, ctx->terms_all, 0, budget, ctx->forced_class, ctx->am);
       ctx->flops_all = all.flops_alg;
-    } else ctx->flops_all = ctx->sched.flops_alg;
+    } else if (nranks <= 1) ctx->flops_all = ctx->sched.flops_alg;
   } catch (const std::exception& e) { return fail(ctx, B2D_ERR_ARG, std::string("b2d_plan: ") + e.what()); }
   ctx->planned = true;
   ctx->layouts.clear();
@@ -1159,11 +1174,11 @@ int b2d_diagonal(b2d_ctx* ctx, int dst_slot) {
   // a compact pool and point the tasks at it (stride 1: coalesced along j, broadcast along i)
   std::vector<DiagGather> gather;
   {
-    std::map<std::pair<int64_t, int>, int64_t> seen;   // (address, stride) -> pool offset
-    int64_t pool = 0;
+    std::map<std::array<int64_t, 3>, int64_t> seen;   // (address, stride, length) -> pool offset; the length is part of the key: the identity
+    int64_t pool = 0;                                  // block of a product is shared by pieces of every size
     auto remap = [&](int64_t& addr, int32_t& stride, int n) {
       if (!addr) return;
-      auto key = std::make_pair(addr, (int)stride);
+      const std::array<int64_t, 3> key{addr, (int64_t)stride, (int64_t)n};
       auto it = seen.find(key);
       if (it == seen.end()) {
         it = seen.emplace(key, pool).first;
@@ -2029,6 +2044,7 @@ std::vector<int> noise_operators(b2d_ctx* ctx) {
       if (o.optype != ty || !(o.dev || o.factorised)) continue;
       int owner = 0;
       if (ctx->nranks > 1) owner = o.norb == 1 ? o.orbs[0] % ctx->nranks : trimap_2d(o.orbs[0], o.orbs[1], ctx->norbs) % ctx->nranks;
+      if (ctx->nranks > 1 && ctx->balance_terms) owner = (int)(m % (size_t)ctx->nranks);   // any fixed partition of the operators will do: rho_n is all-reduced
       if (owner == ctx->rank) out.push_back((int)m);
     }
   return out;
@@ -2368,10 +2384,8 @@ static int flush_product_tasks(b2d_ctx* ctx) {
   }
   // round 0 = the first contribution to a piece of freshly zero-filled storage: it is stored, not read-modified-written
   for (int i = 0; i < count[1]; ++i) sorted[i].pad |= 1;
-  begin_timing(ctx);   // b2d_last_timing: device time of the whole batched construction (incl. the descriptor uploads)
-  int rc = run_kron_rounds(ctx, sorted, count);
+  int rc = run_kron_rounds(ctx, sorted, count, true);
   if (rc) return rc;
-  end_timing(ctx);
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->kron_last_rounds = nrounds;
   ctx->pend_kron.clear(); ctx->pend_kron_round.clear(); ctx->pend_kron_hits.clear();

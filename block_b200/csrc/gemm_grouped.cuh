@@ -215,7 +215,7 @@ __global__ void __launch_bounds__(TileCfg<BM, BN>::THREADS)
 
   // producer cursor over (segment, k0); the segment descriptor stays in registers until the segment is exhausted
   int ps = grp.seg_begin, pk = 0;
-  GSeg sg = segs[ps];
+  GSeg sg = segs[grp.seg_begin < grp.seg_end ? ps : 0];   // a group without segments (kiters == 0) stores zeros: rows of T no factor writes
   auto produce = [&](int stage) {
     const double* A = sg.a_base == B2D_BASE_ABS ? reinterpret_cast<const double*>(sg.a) : bases.p[sg.a_base] + sg.a;
     const double* B = sg.b_base == B2D_BASE_ABS ? reinterpret_cast<const double*>(sg.b) : bases.p[sg.b_base] + sg.b;
@@ -355,6 +355,7 @@ __global__ void __launch_bounds__(TileCfg<BM, BN>::THREADS)
     sg = segs[ps];
   };
   enter_tile(0);
+  while (p_valid && p_left == 0) enter_tile(++p_seq);   // tiles of groups without segments need no stages (they only store zeros)
   int pg = 0;               // stages produced so far (over all tiles of this CTA)
   auto produce_one = [&]() {
     const int slot = pg % STAGES;
@@ -377,7 +378,10 @@ __global__ void __launch_bounds__(TileCfg<BM, BN>::THREADS)
       pk = 0;
       if (++ps < p_send) sg = segs[ps];
     }
-    if (--p_left == 0) enter_tile(++p_seq);
+    if (--p_left == 0) {
+      enter_tile(++p_seq);
+      while (p_valid && p_left == 0) enter_tile(++p_seq);
+    }
   };
 
   const int ar = wm * 32 + g, br = wn * 32 + g;

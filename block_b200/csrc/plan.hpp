@@ -287,6 +287,22 @@ inline std::vector<Term> enumerate_terms(const Side& L, const Side& R, double co
   return terms;
 }
 
+// Cost-weighted ownership ("allow a cost-weighted reassignment as long as the sum is unchanged"): longest-processing-time
+// greedy over the terms' executed flops - sort by cost (ties: term order), give each term to the least loaded rank (ties: lowest rank).
+// Deterministic, so every rank computes the same assignment without communication.
+inline void balance_owners(std::vector<Term>& terms, const std::vector<double>& cost, int nranks) {
+  std::vector<int> order(terms.size());
+  for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[a] > cost[b]; });
+  std::vector<double> load(nranks, 0.0);
+  for (int i : order) {
+    int best = 0;
+    for (int r = 1; r < nranks; ++r) if (load[r] < load[best]) best = r;
+    terms[i].owner = best;
+    load[best] += cost[i];
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // grouped-contraction schedule
 // ---------------------------------------------------------------------------------------------------------------
@@ -378,6 +394,7 @@ struct Schedule {
   int64_t work_max = 0;
   int64_t n_step1 = 0, n_step2 = 0, n_tiles = 0;
   int nslices = 1;           // split-K copies of the destination used by step 2 (slice 0 is the destination itself)
+  std::vector<double> term_flops;   // executed flops of each term, in the order of the term list (cost-weighted ownership)
 };
 
 constexpr int SPLITK_MAX = 8;   // K slices of one sigma block computed by different CTAs into private partial copies
@@ -467,7 +484,9 @@ inline Schedule build_schedule(const Side& L, const Side& R, const PsiLayout& P,
       }
     if (cur.nterms > 0 && cur.work + need > work_budget) { close_chunk(); open_chunk(); }
     cur.nterms++;
-    if (lop.op->factorised) cur.zero_work = true;
+    const double flops_before = cur.step1.flops + cur.step2.flops;
+    // a factorised left operator writes only the row pieces it has factors for: the others are written as ZERO by groups without
+    // segments (the kernel stores its cleared accumulators) - cheaper than clearing the whole workspace per chunk
     std::vector<SubBlock> lsubs;
     for (const TBlock& b : tb) {
       const int dl = L.dims[b.lQ], drp = R.dims[b.rQp];
@@ -481,9 +500,20 @@ inline Schedule build_schedule(const Side& L, const Side& R, const PsiLayout& P,
       lsubs.clear();
       lop.for_each_sub(b.lQ, b.lQp, [&](const SubBlock& sb) { lsubs.push_back(sb); });
       std::stable_sort(lsubs.begin(), lsubs.end(), [](const SubBlock& x, const SubBlock& y) { return x.r0 < y.r0; });
+      int covered = 0;   // rows [0, covered) of this T block are written by the groups emitted so far
+      auto zero_rows = [&](int r_begin, int r_end) {
+        if (r_end <= r_begin) return;
+        GGroup gz;
+        std::memset(&gz, 0, sizeof(gz));
+        gz.c = toff + (int64_t)r_begin * ldt; gz.c_base = B2D_BASE_WORK; gz.ldc = ldt; gz.m = r_end - r_begin; gz.n = drp; gz.accumulate = 0;
+        gz.seg_begin = gz.seg_end = (int)cur.step1.segs.size();
+        cur.step1.groups.push_back(gz);
+      };
       for (size_t k0 = 0; k0 < lsubs.size();) {
         size_t k1 = k0;
         while (k1 < lsubs.size() && lsubs[k1].r0 == lsubs[k0].r0) ++k1;
+        zero_rows(covered, lsubs[k0].r0);
+        covered = lsubs[k0].r0 + lsubs[k0].m;
         GGroup g1;
         std::memset(&g1, 0, sizeof(g1));
         g1.c = toff + (int64_t)lsubs[k0].r0 * ldt; g1.c_base = B2D_BASE_WORK; g1.ldc = ldt; g1.m = lsubs[k0].m; g1.n = drp; g1.accumulate = 0;
@@ -506,6 +536,7 @@ inline Schedule build_schedule(const Side& L, const Side& R, const PsiLayout& P,
         cur.step1.groups.push_back(g1);
         k0 = k1;
       }
+      zero_rows(covered, dl);
       const double left_scaling = lop.scaling(am, b.lQ, b.lQp);
       // step 2:  dst[lQ,rQ] += F T (A_R^(c)[rQ,rQ'])^T                                 (operatorfunctions.C:517-531)
       for (int rQ : rcol[b.rQp]) {
@@ -547,6 +578,7 @@ inline Schedule build_schedule(const Side& L, const Side& R, const PsiLayout& P,
         });
       }
     }
+    S.term_flops.push_back(cur.step1.flops + cur.step2.flops - flops_before);
   }
   close_chunk();
   for (const Chunk& c : S.chunks) S.flops_exec += c.step1.flops + c.step2.flops;

@@ -41,7 +41,12 @@
 //                         (dsyev_), everything else on the GPU: separates eigenvector non-uniqueness from arithmetic differences
 //   B2D_DROPIN_OPTIONS    "key=value,..." library options (b2d_set_option), e.g. eig_jacobi_max=512
 //   B2D_DROPIN_STATS      file that receives one line per block iteration (timings, flops, H applications)
+//   RANK / WORLD_SIZE / LOCAL_RANK (torchrun) + B2D_NCCL_ID_FILE   several processes, one GPU each, run the SAME sweep: the operator terms of
+//                         multiplyH / diagonalH and the noise operators are partitioned over the ranks (b2d_plan(rank, nranks), cost-weighted
+//                         ownership) and the partial results all-reduced over NCCL inside the library; everything else is replicated (bit-identical
+//                         inputs on every rank - run the host side single-threaded).  Rank 0 writes the NCCL unique id to B2D_NCCL_ID_FILE.
 #include <sys/time.h>
+#include <unistd.h>
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
@@ -159,6 +164,7 @@ struct Gpu {
   bool dirty = false;            // statistics of this context not written yet
   bool integrals_set = false;    // b2d_set_integrals done (kept across b2d_reset)
   int children_on_device = 0;    // children of big blocks built on the device so far
+  int rank = 0, world = 1;       // term partition over processes (one GPU each)
   int cache_uses = 0;            // renormalised blocks taken from the device cache instead of being uploaded
   // check mode: CPU results kept between hooks
   SparseMatrix* chk_transform = 0;
@@ -400,8 +406,33 @@ void ensure_ctx(const SpinBlock& big_c) {
   if (dmrginp.hamiltonian() != QUANTUM_CHEMISTRY && dmrginp.hamiltonian() != HUBBARD) die("Hamiltonian type not covered by the GPU path");
   double t0 = now_s();
   g.t_build = 0;
-  int dev = getenv("B2D_DEVICE") ? atoi(getenv("B2D_DEVICE")) : 0;
-  if (!g.ctx && b2d_create(dev, &g.ctx)) die(string("b2d_create: ") + b2d_last_error(0));
+  g.world = getenv("WORLD_SIZE") ? atoi(getenv("WORLD_SIZE")) : 1;
+  g.rank = getenv("RANK") ? atoi(getenv("RANK")) : 0;
+  int dev = getenv("B2D_DEVICE") ? atoi(getenv("B2D_DEVICE")) : (g.world > 1 && getenv("LOCAL_RANK") ? atoi(getenv("LOCAL_RANK")) : 0);
+  if (!g.ctx) {
+    if (b2d_create(dev, &g.ctx)) die(string("b2d_create: ") + b2d_last_error(0));
+    if (g.world > 1) {   // distribute.C's boost::mpi split of the operator terms -> one process per GPU, NCCL all-reduce of the partial sigma
+      const char* idf = getenv("B2D_NCCL_ID_FILE");
+      if (!idf) die("WORLD_SIZE > 1 needs B2D_NCCL_ID_FILE (a path every rank can read: rank 0 writes the NCCL unique id there)");
+      uint8_t id[128];
+      if (g.rank == 0) {
+        if (b2d_nccl_unique_id(id)) die(string("b2d_nccl_unique_id: ") + b2d_last_error(0));
+        string tmp = string(idf) + ".tmp";
+        FILE* f = fopen(tmp.c_str(), "wb");
+        if (!f || fwrite(id, 1, 128, f) != 128) die("cannot write B2D_NCCL_ID_FILE");
+        fclose(f);
+        rename(tmp.c_str(), idf);
+      } else {
+        double t0w = now_s();
+        FILE* f = 0;
+        while (!(f = fopen(idf, "rb"))) { if (now_s() - t0w > 300) die("timed out waiting for B2D_NCCL_ID_FILE"); usleep(20000); }
+        if (fread(id, 1, 128, f) != 128) die("short read of B2D_NCCL_ID_FILE");
+        fclose(f);
+      }
+      ck(b2d_comm_init(g.ctx, id, g.rank, g.world), "b2d_comm_init");
+      ck(b2d_set_option(g.ctx, "balance_terms", 1.0), "b2d_set_option");
+    }
+  }
   g.active = true;
   g.launch0 = b2d_kernel_launches(g.ctx);
   if (getenv("B2D_DROPIN_WORKSPACE_MB")) ck(b2d_set_option(g.ctx, "workspace_mb", atof(getenv("B2D_DROPIN_WORKSPACE_MB"))), "b2d_set_option");
@@ -437,7 +468,7 @@ void ensure_ctx(const SpinBlock& big_c) {
   SpinQuantum tq = dmrginp.effective_molecule_quantum();
   int32_t dq[3] = {tq.get_n(), tq.get_s().getirrep(), tq.get_symm().getirrep()};
   int norbs = (int)dmrginp.spin_orbs_symmetry().size() / 2;
-  ck(b2d_plan(g.ctx, dq, coreEnergy[big.get_integralIndex()], dmrginp.hamiltonian() == HUBBARD ? 1 : 0, norbs, 0, 1), "b2d_plan");
+  ck(b2d_plan(g.ctx, dq, coreEnergy[big.get_integralIndex()], dmrginp.hamiltonian() == HUBBARD ? 1 : 0, norbs, g.rank, g.world), "b2d_plan");
   g.W = b2d_psi_size(g.ctx);
   g.flops = b2d_sigma_flops(g.ctx, 1);
   g.t_upload = now_s() - t0 - g.t_build;

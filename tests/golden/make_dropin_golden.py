@@ -226,6 +226,24 @@ orbitals FCIDUMP
 noreorder
 outputlevel 0
 """)
+    # P4 stand-in (BASELINE configs[3]; SURVEY 8d: the C2 cc-pVDZ file is not in the tree): arenes/28_28_fie, 28 orbitals / 28 electrons, C1,
+    # at an M the CPU reference still finishes here (8 host threads); the M = 2000 run of the same FCIDUMP is GPU-only (scripts/gpu_p4.sh)
+    c["arenes28_M400"] = dict(threads=8, files={"FCIDUMP": open(os.path.join(REF, "dmrg_tests", "dmrg_parameters", "arenes", "28_28_fie", "FCIDUMP")).read()}, conf="""nelec 28
+spin 0
+irrep 1
+hf_occ integral
+schedule
+0 200 1.0e-10 1.0e-4
+2 400 1.0e-10 0.0
+end
+maxiter 4
+twodot
+sweep_tol 1e-12
+orbitals FCIDUMP
+noreorder
+outputlevel 0
+warmup local_2site
+""")
     # The reference's OWN known-answer test, verbatim (dmrg_tests/runtest:19-23: h2o_nosym, default schedule with noise, default orbital
     # reordering, two-dot -> one-dot, `test_energy.py 1 1.0e-6 -76.11460447`).  Not a per-sweep golden case (random noise, threshold
     # regime): its sweeps are stored as "/ref_sweeps" and the GPU test applies the reference's own acceptance criterion.

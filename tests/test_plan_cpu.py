@@ -101,3 +101,29 @@ def test_term_partition_follows_reference_rule(golden, nranks):
                     t = tri(norbs - half - 1) + norbs - half + tri(half) + (i - half) * half + j
                 assert ow[k] == t % nranks
     assert sorted(seen) == list(range(total))      # every term executed exactly once
+
+
+def test_cost_weighted_term_ownership_balances_flops():
+    """Option balance_terms ("allow a cost-weighted reassignment as long as the sum is unchanged"): the union of the ranks'
+    term lists is the single-rank list, the sets are disjoint, and the executed flops per rank are within 1 % of the mean where the
+    reference's static rule (i % n, trimap_2d % n) is several per cent off.  Planning only (no device)."""
+    from block_b200 import synthetic as S
+    world = 8
+    shares = {}
+    for balance in (0, 1):
+        seen, fl = [], []
+        for rank in range(world):
+            sb = S.make_big_block(norbs=24, nelec=24, M=300, left_sites=11, device=-1, rank=rank, nranks=world, options={"balance_terms": balance}, fill=False)
+            lo, ro, flg, sc, ow = sb.terms(all_ranks=True)
+            mine = np.nonzero(ow == rank)[0]
+            mlo, mro, mfl, msc, _ = sb.terms(all_ranks=False)
+            assert np.array_equal(lo[mine], mlo) and np.array_equal(ro[mine], mro) and np.array_equal(flg[mine], mfl)
+            seen.append(set(int(i) for i in mine))
+            fl.append(sb.plan_stats()["flops_executed"])
+            total_terms = len(lo)
+            sb.close()
+        assert sum(len(x) for x in seen) == total_terms and len(set().union(*seen)) == total_terms     # exhaustive and disjoint
+        shares[balance] = max(fl) / (sum(fl) / world)
+    assert shares[1] < 1.01, shares
+    assert shares[1] <= shares[0]
+    print("max / mean executed flops per rank at %d ranks: reference rule %.4f, cost-weighted %.4f" % (world, shares[0], shares[1]))

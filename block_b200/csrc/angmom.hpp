@@ -23,7 +23,7 @@ namespace b2d {
 
 struct AngMom {
   double fact[171];
-  std::unordered_map<uint64_t, double> memo9, memo6, memocg;
+  std::unordered_map<uint64_t, double> memo9, memo6, memocg, memots;
   AngMom() {
     fact[0] = 1.0;
     for (int i = 1; i <= 170; ++i) fact[i] = fact[i - 1] * i;
@@ -123,11 +123,16 @@ struct AngMom {
 
   // Transposeview::get_scaling(leftq, rightq) for an operator of spin cs (conjugacy 't')
   double transpose_scaling(int cs, int ls, int rs) {
+    const uint64_t k = key({cs, ls, rs});
+    auto it = memots.find(k);
+    if (it != memots.end()) return it->second;
     for (int lsz = -ls; lsz <= ls; lsz += 2)
       for (int rsz = -rs; rsz <= rs; rsz += 2) {
         double cleb = clebsch(ls, lsz, cs, -cs, rs, rsz);
         if (std::fabs(cleb) <= NUMERICAL_ZERO) continue;
-        return ((cs & 1) ? -1.0 : 1.0) * cleb / clebsch(rs, rsz, cs, cs, ls, lsz);
+        const double r = ((cs & 1) ? -1.0 : 1.0) * cleb / clebsch(rs, rsz, cs, cs, ls, lsz);
+        memots.emplace(k, r);
+        return r;
       }
     throw std::runtime_error("Transposeview::get_scaling: inappropriate sector quanta");
   }

@@ -2578,7 +2578,17 @@ static int finalise_factorised_op(b2d_ctx* ctx, int prod_id) {
       if (lead == alphas.size()) continue;
       std::vector<double> ratios(alphas.size());
       for (size_t q = 0; q < alphas.size(); ++q) ratios[q] = alphas[q] / alphas[lead];
-      const std::array<int64_t, 3> key{(int64_t)(intptr_t)parts[0].first, (int64_t)first.m, (int64_t)first.n};
+      // bucket key: the parts (addresses, orientation) and the coefficient ratios quantised to ~1e-8 of the largest one - candidates in a
+      // bucket are then compared exactly (1e-12); two equal vectors straddling a quantisation boundary merely miss the sharing
+      uint64_t hk = 1469598103934665603ull;
+      auto mixin = [&](uint64_t v) { hk ^= v; hk *= 1099511628211ull; };
+      double rmax = 0.0;
+      for (double r : ratios) rmax = std::max(rmax, std::fabs(r));
+      for (size_t q = 0; q < parts.size(); ++q) {
+        mixin((uint64_t)(intptr_t)parts[q].first); mixin(parts[q].second ? 2 : 1);
+        mixin((uint64_t)(int64_t)std::llround(ratios[q] / rmax * 67108864.0));
+      }
+      const std::array<int64_t, 3> key{(int64_t)hk, (int64_t)first.m, (int64_t)first.n};
       std::vector<b2d_ctx::Product::Combo>& cands = P.combos[key];
       const double* block = nullptr;
       for (const auto& c : cands) {
@@ -2595,6 +2605,7 @@ static int finalise_factorised_op(b2d_ctx* ctx, int prod_id) {
         if (ctx->has_device) CU(cudaMemsetAsync(dst, 0, n * 8, ctx->stream));
         ctx->arena_doubles += (int64_t)n; ctx->combo_doubles += (int64_t)n;
         if (getenv("B2D_FACT_DEBUG")) { static std::map<int, std::array<double, 3>> acc; auto& a = acc[op.optype]; a[0] += (double)n; a[1] += 1; a[2] += (double)parts.size(); fprintf(stderr, "FACT optype %d combos %.0f doubles %.3e avg parts %.1f | this: parts %d m %d n %d ident %d r0 %d c0 %d blk %zu\n", op.optype, a[1], a[0], a[2] / a[1], (int)parts.size(), first.m, first.n, nident, first.r0, first.c0, b); }
+        int round = 0;   // the block is fresh: its parts simply take successive rounds (no lookup in the hit table)
         for (size_t q = 0; q < parts.size(); ++q) {
           if (ratios[q] == 0.0) continue;
           KronTask kt;
@@ -2602,9 +2613,8 @@ static int finalise_factorised_op(b2d_ctx* ctx, int prod_id) {
           kt.a = (int64_t)(intptr_t)parts[q].first; kt.b = 0; kt.dst = (int64_t)(intptr_t)dst; kt.coef = ratios[q];
           kt.a_rows = first.m; kt.a_cols = first.n; kt.lda = ldas[q]; kt.a_t = parts[q].second ? 1 : 0;
           kt.b_rows = kt.b_cols = 1; kt.ldb = 1; kt.b_t = 0; kt.row0 = kt.col0 = 0; kt.ldd = ldc;
-          int& hits = ctx->pend_kron_hits[std::array<int64_t, 3>{kt.dst, 0, 0}];
           ctx->pend_kron.push_back(kt);
-          ctx->pend_kron_round.push_back(hits++);
+          ctx->pend_kron_round.push_back(round++);
           ctx->kron_bytes += 8.0 * 3.0 * (double)first.m * first.n;
           ++ctx->kron_ntasks;
         }

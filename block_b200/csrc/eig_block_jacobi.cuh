@@ -25,6 +25,7 @@ constexpr int BJ_B = 32;             // rows per block
 constexpr int BJ_R = 2 * BJ_B;       // rows per pair
 constexpr int BJ_THREADS = 256;
 constexpr int BJ_CH = 64;            // columns per streamed chunk
+constexpr int BJ_INNER_SWEEPS = 2;
 constexpr int BJ_LDX = BJ_CH + 1;    // shared-memory leading dimensions (odd: conflict-free column access)
 constexpr int BJ_LDA = BJ_R + 1;
 constexpr int BJ_LDW = BJ_R + 2;     // even: W rows are read as double2
@@ -110,7 +111,9 @@ __global__ void __launch_bounds__(BJ_THREADS) block_jacobi_step_kernel(const BJP
 
   // ---- 2. two-sided cyclic Jacobi on A (64 x 64), rotations accumulated in W ----
   int applied_total = 0;
-  for (int sweep = 0; sweep < 40; ++sweep) {
+  // at most BJ_INNER_SWEEPS sweeps over the 64 x 64 pivot block per step: the step is latency-bound (three CTA barriers per round, 63
+  // rounds per sweep), and diagonalising the pivot block to convergence buys no outer sweep - the pairs meet again next sweep anyway
+  for (int sweep = 0; sweep < BJ_INNER_SWEEPS; ++sweep) {
     int applied_sweep = 0;
     for (int round = 0; round < BJ_R - 1; ++round) {
       if (tid < 32) {

@@ -167,7 +167,7 @@ def _sample_order(nterms, max_terms):
     return order[::4] + order[1::4] + order[2::4] + order[3::4]   # a truncated sample still covers every term family
 
 
-def cpu_sigma_reference(a, budget_s=10.0, max_terms=48, state={}):
+def cpu_sigma_reference(a, budget_s=10.0, max_terms=192, state={}):
     """Time the REAL reference's operatorfunctions::TensorMultiply (oracle/_ref/ref_bench: the unmodified reference
     objects compiled by oracle/Makefile, OpenMP over operator terms with single-threaded OpenBLAS dgemm inside, exactly how
     multiplyH parallelises: operatorloops.h:87-97) on an evenly spaced sample of the SAME multiplyH's term list.
@@ -572,7 +572,15 @@ def run_ours(a):
     if rank == 0 or world == 1:
         # roofline of the dominant kernel (128x128 DMMA tile class of the grouped contraction), timed live with events
         prof = sb.sigma_profile(0, 1)
-        dmma, dfma = sb.measure_fp64_peak()
+        dmma_live, dfma = sb.measure_fp64_peak()
+        # the roofline denominator is PINNED: profiles/r02_fp64_yardstick.json (tracked; the same register-loop yardstick measured on a B200 of this
+        # pool with its clock record); the live measurement of this run is reported next to it
+        dmma, pinned = dmma_live, False
+        try:
+            dmma = float(json.load(open(os.path.join(ROOT, "profiles", "r02_fp64_yardstick.json")))["fp64_dmma_tflops"])
+            pinned = True
+        except Exception:   # noqa: BLE001
+            pass
         # the dominant kernel = the tile class of the grouped contraction with the largest share of the step's time
         cls_ms = {c: sum(prof[(st, c)][0] for st in range(2)) for c in range(10)}
         kc = max(cls_ms, key=cls_ms.get)
@@ -587,14 +595,19 @@ def run_ours(a):
         # DRAM bytes per launch of that kernel from the committed ncu capture of this same workload (profiles/README.md); other
         # workloads have no capture
         default_workload = (a.norbs, a.nelec, a.M, a.left_sites, world, a.mode) == (40, 40, 4000, 18, 1, "materialised")
+        default_factorised = (a.norbs, a.nelec, a.M, a.left_sites, world, a.mode) == (40, 40, 4000, 20, 1, "factorised")
         roof = {"bound": "tensor", "achieved": achieved, "peak": dmma, "unit": "TFLOP/s", "frac": achieved / dmma if dmma else None,
-                "traffic": 16.12e9 if default_workload else None,
-                "traffic_source": "profiles/r01_ncu_launches_sigma_fullsize.csv: dram__bytes_read.sum + dram__bytes_write.sum of the 36 launches / 36 (bytes per launch)" if default_workload else None,
+                "traffic": 16.12e9 if default_workload else (14.27e9 if default_factorised and kc == 0 else None),
+                "traffic_source": ("profiles/r01_ncu_launches_sigma_fullsize.csv: dram__bytes_read.sum + dram__bytes_write.sum of the 36 launches / 36 (bytes per launch)" if default_workload else
+                                   ("profiles/r02_ncu_launches_sigma_factorised.csv: dram__bytes_read.sum + dram__bytes_write.sum of the 88 launches of grouped_gemm_kernel<128,128,1> / 88 "
+                                    "(bytes per launch); whole sigma 1.09 TB = 0.86 TB/s: FP64-pipe bound" if default_factorised and kc == 0 else None)),
                 "kernel": kname, "launches": int(k_n), "avg_launch_ms": k_ms / max(k_n, 1),
                 "flops_basis": "EXECUTED flops of that kernel (useful 2mnk inside its tiles; structural zeros the factorised form skips are not credited)",
                 "whole_sigma_executed_tflops": tot_fl / (ms_step * 1e-3) / 1e12, "whole_sigma_frac_of_peak": tot_fl / (ms_step * 1e-3) / 1e12 / dmma if dmma else None,
                 "share_of_sigma": k_ms / tot_ms if tot_ms else None, "tile_fill": k_fl / k_pad if k_pad else None,
-                "peak_source": "live FP64 DMMA register-loop yardstick of this library on this GPU (MEASURED_PEAKS.json has no FP64 entry); DFMA loop %.1f TFLOP/s" % dfma,
+                "peak_live": dmma_live,
+                "peak_source": ("profiles/r02_fp64_yardstick.json (pinned FP64 DMMA register-loop yardstick with its clock record; MEASURED_PEAKS.json has no FP64 entry); "
+                                if pinned else "live FP64 DMMA register-loop yardstick of this library on this GPU (MEASURED_PEAKS.json has no FP64 entry); ") + "live this run: DMMA %.2f, DFMA %.1f TFLOP/s" % (dmma_live, dfma),
                 "per_class": {("step%d_%dx%d" % (st + 1, 128 >> (c // 3), 128 >> (c % 3)) if c < 9 else "step%d_tiny8x8_warp" % (st + 1)): {"ms": v[0], "tflops": (v[1] / (v[0] * 1e-3) / 1e12 if v[0] > 0 else 0.0), "tile_fill": (v[1] / v[2] if v[2] else None),
                                                                "launches": int(v[3])} for (st, c), v in prof.items() if v[3] > 0}}
         peaks = {}
@@ -684,8 +697,8 @@ def main():
     ap.add_argument("--no-sweep", action="store_true", help="skip the whole-sweep leg (reference sweep vs the same sweep with the GPU hot path)")
     ap.add_argument("--sweep-case", default="synthetic_16o_M300", help="case of tests/golden/dropin_cases.npz for the sweep leg")
     ap.add_argument("--profile-mode", action="store_true", help="for ncu: 1 warm-up sigma + --steps sigmas, nothing else, no JSON line")
-    ap.add_argument("--cpu-budget-s", type=float, default=15.0)
-    ap.add_argument("--ref-step-s", type=float, default=6.0)
+    ap.add_argument("--cpu-budget-s", type=float, default=20.0)
+    ap.add_argument("--ref-step-s", type=float, default=20.0)   # >= 128 terms of the multiplyH per reference step on a 16-core host
     a = ap.parse_args()
     if a.left_sites is None:
         a.left_sites = a.norbs // 2 if a.mode == "factorised" else 18

@@ -238,7 +238,7 @@ struct b2d_ctx {
   };
   std::map<uint64_t, CachedBlock> cache;
   uint64_t cache_next_token = 1;
-  double cache_device_mb = 32768.0;   // option "cache_device_mb": device memory the cache may hold before it spills to pinned host memory
+  double cache_device_mb = 0.0;       // option "cache_device_mb": device memory the cache may hold before it spills to pinned host memory (<= 0: automatic)
   int64_t cache_device_doubles = 0, cache_hits = 0, cache_puts = 0;
   std::vector<DevBuf> spare_bufs;     // buffers of dropped entries, reused by the next b2d_transform_operators (cudaMalloc of hundreds of MB costs ~10 ms)
   std::map<std::vector<int>, PsiLayout> layouts;   // wavefunction layouts for other target quanta (noise: O.psi sectors)
@@ -2990,7 +2990,15 @@ int b2d_cache_put_rotated(b2d_ctx* ctx, uint64_t* token) {
     else op.cache_off = -1;
   }
   cb.doubles = total;
-  if ((double)(ctx->cache_device_doubles + total) * 8.0 <= ctx->cache_device_mb * 1048576.0) {
+  // device budget: option cache_device_mb, or (default, <= 0) automatic - keep the block on the device while at least 35 % of the GPU's
+  // memory stays free for the operator arena and the workspaces of the next block iterations
+  bool on_device = (double)(ctx->cache_device_doubles + total) * 8.0 <= ctx->cache_device_mb * 1048576.0;
+  if (ctx->cache_device_mb <= 0.0) {
+    size_t free_b = 0, total_b = 0;
+    CU(cudaMemGetInfo(&free_b, &total_b));
+    on_device = (double)free_b >= 0.35 * (double)total_b;
+  }
+  if (on_device) {
     cb.dev = ctx->rotated_arena;            // the buffer changes owner; b2d_transform_operators allocates a new one next time
     ctx->rotated_arena = DevBuf();
     ctx->cache_device_doubles += total;

@@ -564,11 +564,54 @@ __global__ void __launch_bounds__(256) kron_scatter_kernel(const KronTask* __res
           if (r < cols) { double* d = D + (int64_t)(k.row0 + r) * k.ldd + k.col0 + r; *d = store ? f : *d + f; }
         // a stored piece must be fully defined: the off-diagonal part stays as it is (zero-filled storage) in both modes
       } else if (!k.a_t) {
-        for (int r = r0 + warp; r < r1; r += 8) {
-          const double* src = A + (int64_t)r * k.lda;
-          double* dst = D + (int64_t)(k.row0 + r) * k.ldd + k.col0;
-          if (store) { for (int c = lane; c < cols; c += 32) dst[c] = f * src[c]; }
-          else { for (int c = lane; c < cols; c += 32) dst[c] += f * src[c]; }
+        // each warp owns 4 rows of the band and walks the columns two at a time: 4 independent 16-byte loads (and, when the destination is
+        // accumulated, 4 more) are in flight per lane before the first store - the kernel is latency-bound otherwise
+        const int rb = r0 + warp * 4;
+        const bool dst16 = ((k.col0 & 1) == 0) && ((reinterpret_cast<uintptr_t>(D) & 15) == 0) && ((k.ldd & 1) == 0);
+        const bool src16 = ((reinterpret_cast<uintptr_t>(A) & 15) == 0) && ((k.lda & 1) == 0);
+        const int cpair = cols & ~1;
+        if (dst16 && src16) {
+          for (int c = 2 * lane; c < cpair; c += 64) {
+            double2 v[4], o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (rb + j < r1) v[j] = *reinterpret_cast<const double2*>(A + (int64_t)(rb + j) * k.lda + c);
+            if (!store) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                if (rb + j < r1) o[j] = *reinterpret_cast<const double2*>(D + (int64_t)(k.row0 + rb + j) * k.ldd + k.col0 + c);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (rb + j < r1) {
+                double2 w;
+                w.x = store ? f * v[j].x : o[j].x + f * v[j].x;
+                w.y = store ? f * v[j].y : o[j].y + f * v[j].y;
+                *reinterpret_cast<double2*>(D + (int64_t)(k.row0 + rb + j) * k.ldd + k.col0 + c) = w;
+              }
+          }
+          if ((cols & 1) && lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (rb + j < r1) {
+                double* d = D + (int64_t)(k.row0 + rb + j) * k.ldd + k.col0 + cpair;
+                const double v = f * A[(int64_t)(rb + j) * k.lda + cpair];
+                *d = store ? v : *d + v;
+              }
+          }
+        } else {
+          for (int c = lane; c < cols; c += 32) {
+            double v[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (rb + j < r1) v[j] = A[(int64_t)(rb + j) * k.lda + c];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              if (rb + j < r1) {
+                double* d = D + (int64_t)(k.row0 + rb + j) * k.ldd + k.col0 + c;
+                *d = store ? f * v[j] : *d + f * v[j];
+              }
+          }
         }
       } else {                                    // op(A)(r, c) = A[c][r]: 32 x 32 tiles through shared memory
         for (int c0 = 0; c0 < cols; c0 += 32) {
@@ -610,7 +653,7 @@ __global__ void __launch_bounds__(256) kron_scatter_kernel(const KronTask* __res
 
 cudaError_t launch_kron_scatter(const KronTask* tasks, const KronTile* tiles, int ntiles, cudaStream_t s, int64_t* launches) {
   if (ntiles == 0) return cudaSuccess;
-  kron_scatter_kernel<<<min(ntiles, 148 * 8), 256, 0, s>>>(tasks, tiles, ntiles);
+  kron_scatter_kernel<<<min(ntiles, 148 * 16), 256, 0, s>>>(tasks, tiles, ntiles);
   B2D_LAUNCH_CHECK();
   return cudaSuccess;
 }

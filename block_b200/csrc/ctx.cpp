@@ -4,6 +4,7 @@
 #include <dlfcn.h>
 
 #include <algorithm>
+#include <set>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -27,6 +28,19 @@ namespace {
 
 std::string g_create_error;
 
+// cudaMalloc that, when the device is full, first lets the live contexts on this device give memory back (empty arena slabs, spare
+// buffers, then cached blocks that are not children of the current block iteration move to pinned host memory) and tries again
+bool release_device_memory(size_t bytes);
+inline cudaError_t device_malloc(void** p, size_t bytes) {
+  cudaError_t e = cudaMalloc(p, bytes);
+  if (e == cudaErrorMemoryAllocation) {
+    cudaGetLastError();
+    if (release_device_memory(bytes)) e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) cudaGetLastError();
+  }
+  return e;
+}
+
 struct DevBuf {   // growable raw device buffer
   void* p = nullptr;
   size_t cap = 0;
@@ -34,7 +48,7 @@ struct DevBuf {   // growable raw device buffer
     if (bytes <= cap) return cudaSuccess;
     if (p) cudaFree(p);
     p = nullptr; cap = 0;
-    cudaError_t e = cudaMalloc(&p, bytes);
+    cudaError_t e = device_malloc(&p, bytes);
     if (e == cudaSuccess) cap = bytes;
     return e;
   }
@@ -238,6 +252,8 @@ struct b2d_ctx {
   };
   std::map<uint64_t, CachedBlock> cache;
   uint64_t cache_next_token = 1;
+  std::set<uint64_t> cache_in_use;    // entries that are children of the current block iteration (until b2d_reset): never evicted
+  int64_t cache_evictions = 0;
   double cache_device_mb = 0.0;       // option "cache_device_mb": device memory the cache may hold before it spills to pinned host memory (<= 0: automatic)
   int64_t cache_device_doubles = 0, cache_hits = 0, cache_puts = 0;
   std::vector<DevBuf> spare_bufs;     // buffers of dropped entries, reused by the next b2d_transform_operators (cudaMalloc of hundreds of MB costs ~10 ms)
@@ -280,10 +296,10 @@ cudaError_t arena_alloc(b2d_ctx* ctx, size_t bytes, double** out) {
     if (s.cap - s.used >= bytes) { *out = (double*)(s.p + s.used); s.used += bytes; return cudaSuccess; }
   size_t cap = std::max(bytes, (size_t)256 << 20);
   char* p = nullptr;
-  cudaError_t e = cudaMalloc(&p, cap);
+  cudaError_t e = device_malloc((void**)&p, cap);
   if (e != cudaSuccess) {   // fall back to an exact-size slab
     cap = bytes;
-    e = cudaMalloc(&p, cap);
+    e = device_malloc((void**)&p, cap);
     if (e != cudaSuccess) return e;
   }
   ctx->slabs.push_back({p, cap, bytes});
@@ -587,6 +603,49 @@ extern "C" {
 
 int b2d_abi_version(void) { return 4; }   // 4: factorised operators, b2d_alloc_ops, block cache (b2d_cache_*); 3: stash / assemble, guess transform
 
+static std::vector<b2d_ctx*> g_live_ctx;   // contexts the memory-pressure handler may ask for memory
+
+extern "C++" {
+namespace {
+bool release_device_memory(size_t bytes) {
+  int dev = -1;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  auto enough = [&]() {
+    size_t free_b = 0, total_b = 0;
+    return cudaMemGetInfo(&free_b, &total_b) == cudaSuccess && free_b >= bytes + ((size_t)256 << 20);
+  };
+  bool any = false;
+  for (b2d_ctx* c : g_live_ctx) {
+    if (!c->has_device || c->device != dev) continue;
+    cudaStreamSynchronize(c->stream);
+    for (size_t i = 0; i < c->slabs.size();)
+      if (c->slabs[i].used == 0) { cudaFree(c->slabs[i].p); c->slabs.erase(c->slabs.begin() + i); any = true; }
+      else ++i;
+    for (DevBuf& b : c->spare_bufs) { if (b.p) any = true; b.release(); }
+    c->spare_bufs.clear();
+  }
+  if (any && enough()) return true;
+  for (b2d_ctx* c : g_live_ctx) {
+    if (!c->has_device || c->device != dev) continue;
+    for (auto& kv : c->cache) {               // oldest first: in a sweep the oldest blocks of the other direction are needed last
+      b2d_ctx::CachedBlock& cb = kv.second;
+      if (!cb.dev.p || cb.doubles <= 0 || c->cache_in_use.count(kv.first)) continue;
+      double* host = nullptr;
+      if (cudaMallocHost(&host, (size_t)cb.doubles * 8) != cudaSuccess) { cudaGetLastError(); return any && enough(); }
+      if (cudaMemcpy(host, cb.dev.p, (size_t)cb.doubles * 8, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaFreeHost(host); cudaGetLastError(); return any && enough(); }
+      cb.pinned = host;
+      cb.dev.release();
+      c->cache_device_doubles -= cb.doubles;
+      ++c->cache_evictions;
+      any = true;
+      if (enough()) return true;
+    }
+  }
+  return any && enough();
+}
+}   // namespace
+}   // extern "C++"
+
 int b2d_create(int device, b2d_ctx** out) {
   if (!out) return B2D_ERR_ARG;
   *out = nullptr;
@@ -614,11 +673,13 @@ int b2d_create(int device, b2d_ctx** out) {
     CU(c->tile_counter.reserve(256));
   }
   *out = c.release();
+  g_live_ctx.push_back(*out);
   return B2D_OK;
 }
 
 void b2d_destroy(b2d_ctx* ctx) {
   if (!ctx) return;
+  g_live_ctx.erase(std::remove(g_live_ctx.begin(), g_live_ctx.end(), ctx), g_live_ctx.end());
   if (ctx->has_device) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
@@ -663,6 +724,7 @@ int b2d_reset(b2d_ctx* ctx) {
   ctx->dsched = DevSchedule();
   ctx->flops_all = 0.0;
   for (auto& sl : ctx->slabs) sl.used = 0;
+  ctx->cache_in_use.clear();
   ctx->arena_doubles = 0;
   ctx->pend_used = 0; ctx->pend_desc.clear();
   ctx->nuser = 0; ctx->ndav = 0;
@@ -925,7 +987,7 @@ int b2d_plan(b2d_ctx* ctx, const int32_t* psi_dq, double core_energy, int hubbar
       }
       if (need_bytes > 0) {   // one exact-size slab: at benchmark scale the arena is most of the GPU's memory
         char* slab = nullptr;
-        CU(cudaMalloc(&slab, need_bytes));
+        CU(device_malloc((void**)&slab, need_bytes));
         ctx->slabs.push_back({slab, need_bytes, need_bytes});
         CU(cudaMemsetAsync(slab, 0, need_bytes, ctx->stream));
         size_t off = 0;
@@ -2541,31 +2603,46 @@ static int finalise_factorised_op(b2d_ctx* ctx, int prod_id) {
   OpRec& op = P.side.ops[prod_id];
   if (!op.factorised || !op.sub_begin.empty()) return B2D_OK;
   auto& pend = P.pend_subs[prod_id];
-  std::stable_sort(pend.begin(), pend.end(), [](const std::pair<size_t, SubBlock>& x, const std::pair<size_t, SubBlock>& y) { return x.first < y.first; });
+  // by stored block, then by (row piece, column piece); stable: the contributions to one piece keep the order of the products
+  std::stable_sort(pend.begin(), pend.end(), [](const std::pair<size_t, SubBlock>& x, const std::pair<size_t, SubBlock>& y) {
+    if (x.first != y.first) return x.first < y.first;
+    if (x.second.r0 != y.second.r0) return x.second.r0 < y.second.r0;
+    return x.second.c0 < y.second.c0;
+  });
   const size_t nb = (size_t)P.side.nq * P.side.nq;
   op.sub_begin.assign(nb + 1, 0);
   op.subs.clear();
   size_t k = 0;
   std::vector<const SubBlock*> list;
+  std::unordered_map<uint64_t, size_t> part_index;
+  std::vector<std::pair<const double*, bool>> parts;
+  std::vector<double> alphas, ratios;
+  std::vector<int> ldas;
   for (size_t b = 0; b < nb; ++b) {
     op.sub_begin[b] = (int32_t)op.subs.size();
     size_t k1 = k;
     while (k1 < pend.size() && pend[k1].first == b) ++k1;
-    std::vector<bool> done(k1 - k, false);
-    for (size_t i = k; i < k1; ++i) {
-      if (done[i - k]) continue;
+    for (size_t i = k, i1; i < k1; i = i1) {
       list.clear();
-      for (size_t j = i; j < k1; ++j)
-        if (!done[j - k] && pend[j].second.r0 == pend[i].second.r0 && pend[j].second.c0 == pend[i].second.c0) { list.push_back(&pend[j].second); done[j - k] = true; }
-      // merge repeated parts (same child block, same orientation)
-      std::vector<std::pair<const double*, bool>> parts;
-      std::vector<double> alphas;
-      std::vector<int> ldas;
+      for (i1 = i; i1 < k1 && pend[i1].second.r0 == pend[i].second.r0 && pend[i1].second.c0 == pend[i].second.c0; ++i1) list.push_back(&pend[i1].second);
+      // merge repeated parts (same child block, same orientation); parts keep the order of their first appearance
+      parts.clear(); alphas.clear(); ldas.clear();
+      if (list.size() == 1) { parts.emplace_back(list[0]->a, list[0]->t); alphas.push_back(list[0]->alpha); ldas.push_back(list[0]->lda); }
+      else if (list.size() <= 8) {
+        for (const SubBlock* sb : list) {
+          bool merged = false;
+          for (size_t q = 0; q < parts.size(); ++q)
+            if (parts[q].first == sb->a && parts[q].second == sb->t) { alphas[q] += sb->alpha; merged = true; break; }
+          if (!merged) { parts.emplace_back(sb->a, sb->t); alphas.push_back(sb->alpha); ldas.push_back(sb->lda); }
+        }
+      } else {
+      part_index.clear();
       for (const SubBlock* sb : list) {
-        bool merged = false;
-        for (size_t q = 0; q < parts.size(); ++q)
-          if (parts[q].first == sb->a && parts[q].second == sb->t) { alphas[q] += sb->alpha; merged = true; break; }
-        if (!merged) { parts.emplace_back(sb->a, sb->t); alphas.push_back(sb->alpha); ldas.push_back(sb->lda); }
+        const uint64_t pk = ((uint64_t)(intptr_t)sb->a << 1) | (sb->t ? 1u : 0u);   // operator blocks are 8-byte aligned
+        auto ins = part_index.emplace(pk, parts.size());
+        if (!ins.second) alphas[ins.first->second] += sb->alpha;
+        else { parts.emplace_back(sb->a, sb->t); alphas.push_back(sb->alpha); ldas.push_back(sb->lda); }
+      }
       }
       const SubBlock& first = *list[0];
       int nident = 0;
@@ -2583,7 +2660,7 @@ static int finalise_factorised_op(b2d_ctx* ctx, int prod_id) {
       size_t lead = 0;
       while (lead < alphas.size() && alphas[lead] == 0.0) ++lead;
       if (lead == alphas.size()) continue;
-      std::vector<double> ratios(alphas.size());
+      ratios.resize(alphas.size());
       for (size_t q = 0; q < alphas.size(); ++q) ratios[q] = alphas[q] / alphas[lead];
       // bucket key: the parts (addresses, orientation) and the coefficient ratios quantised to ~1e-8 of the largest one - candidates in a
       // bucket are then compared exactly (1e-12); two equal vectors straddling a quantisation boundary merely miss the sharing
@@ -3047,6 +3124,7 @@ int b2d_cache_use(b2d_ctx* ctx, uint64_t token, int side, int is_loop) {
   s.loop = is_loop != 0;
   ctx->side[side] = std::move(s);
   ctx->planned = false;
+  ctx->cache_in_use.insert(token);
   ++ctx->cache_hits;
   return B2D_OK;
 }
@@ -3139,8 +3217,15 @@ int b2d_cache_stats(const b2d_ctx* ctx, double* out, int n) {
   if (!ctx || !out) return B2D_ERR_ARG;
   double spilled = 0;
   for (const auto& kv : ctx->cache) if (!kv.second.dev.p) spilled += (double)kv.second.doubles;
-  const double v[5] = {(double)ctx->cache.size(), (double)ctx->cache_device_doubles, spilled, (double)ctx->cache_puts, (double)ctx->cache_hits};
-  for (int i = 0; i < n && i < 5; ++i) out[i] = v[i];
+  const double v[6] = {(double)ctx->cache.size(), (double)ctx->cache_device_doubles, spilled, (double)ctx->cache_puts, (double)ctx->cache_hits, (double)ctx->cache_evictions};
+  for (int i = 0; i < n && i < 6; ++i) out[i] = v[i];
+  return B2D_OK;
+}
+
+int b2d_cache_spill(b2d_ctx* ctx, double bytes) {
+  NEED_DEVICE();
+  CU(cudaSetDevice(ctx->device));
+  release_device_memory(bytes > 0 ? (size_t)bytes : 0);
   return B2D_OK;
 }
 

@@ -422,6 +422,45 @@ class SpinBlock:
             ops.append((allowed.astype(bool), data[:n]))
         return old, dims, ops
 
+    # -- device-side shadow of the scratch files (save_load_block.C:23-108) ----------------------------------
+    def cache_put_rotated(self):
+        """The renormalised left block that transform_operators left on the device becomes a cache entry: returns its token."""
+        tok = C.c_uint64(0)
+        self._ck(self.lib.b2d_cache_put_rotated(self._ctx, C.byref(tok)))
+        return int(tok.value)
+
+    def cache_block_info(self, token):
+        nq, nops, ns = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        self._ck(self.lib.b2d_cache_block_info(self._ctx, C.c_uint64(token), C.byref(nq), C.byref(nops), C.byref(ns)))
+        return nq.value, nops.value, ns.value
+
+    def cache_download_op(self, token, op_id):
+        nq, _, _ = self.cache_block_info(token)
+        size = C.c_int64(0)
+        self._ck(self.lib.b2d_cache_op_info(self._ctx, C.c_uint64(token), op_id, None, None, None, None, C.byref(size)))
+        allowed = np.zeros((nq, nq), np.uint8)
+        data = np.empty(max(int(size.value), 1))
+        self._ck(self.lib.b2d_cache_download_op(self._ctx, C.c_uint64(token), op_id, _p(allowed, _lib.c_u8p), _p(data, _lib.c_f64p)))
+        return allowed.astype(bool), data[:int(size.value)]
+
+    def cache_use(self, token, side, is_loop=False):
+        self._ck(self.lib.b2d_cache_use(self._ctx, C.c_uint64(token), int(side), int(is_loop)))
+
+    def cache_drop(self, token):
+        self._ck(self.lib.b2d_cache_drop(self._ctx, C.c_uint64(token)))
+
+    def cache_spill(self, nbytes):
+        self._ck(self.lib.b2d_cache_spill(self._ctx, float(nbytes)))
+
+    def cache_stats(self):
+        out = np.zeros(6)
+        self._ck(self.lib.b2d_cache_stats(self._ctx, _p(out, _lib.c_f64p), 6))
+        return dict(zip(["entries", "device_doubles", "spilled_doubles", "puts", "uses", "evictions"], out))
+
+    def release_block(self):
+        """b2d_reset: forget the block description (the cache entries stay)."""
+        self._ck(self.lib.b2d_reset(self._ctx))
+
     # -- measurement ---------------------------------------------------------------------------------------------
     def last_timing_ms(self):
         out = np.zeros(4)

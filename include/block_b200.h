@@ -400,8 +400,14 @@ int b2d_cache_block_sectors(const b2d_ctx* ctx, uint64_t token, int32_t* q, int3
 int b2d_cache_op_info(const b2d_ctx* ctx, uint64_t token, int op_id, int32_t* optype, int32_t* norb, int32_t* orbs, int32_t* comp, int64_t* packed_size);
 int b2d_cache_download_op(b2d_ctx* ctx, uint64_t token, int op_id, uint8_t* allowed, double* data);
 int b2d_cache_drop(b2d_ctx* ctx, uint64_t token);
-/* out[0..4] = {entries, doubles held on the device, doubles spilled to pinned host memory, puts, uses} */
+/* out[0..5] = {entries, doubles held on the device, doubles spilled to pinned host memory, puts, uses, evictions} */
 int b2d_cache_stats(const b2d_ctx* ctx, double* out, int n);
+/* Memory pressure (the role of the scratch DISK of save_load_block.C:23-108 when the blocks of a sweep exceed the memory: P5 at M = 4000
+ * stores 20 - 60 GB per block).  Every device allocation of the library that fails first releases the empty arena slabs and spare
+ * buffers and then moves cached blocks that are not children of the current block iteration (oldest first) to pinned host memory, and
+ * tries again.  b2d_cache_spill asks for the same explicitly until `bytes` of device memory are free (a host that needs GPU memory for
+ * itself; the tests).  Returns B2D_OK also when less could be freed: b2d_cache_stats tells what moved. */
+int b2d_cache_spill(b2d_ctx* ctx, double bytes);
 
 /* ---- multi-GPU: partition of operator terms, NCCL all-reduce of the partial sigma --------------------------- */
 

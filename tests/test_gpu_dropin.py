@@ -136,6 +136,21 @@ def test_sweep_energies_match_reference(name):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("name", ["c2_d2h_M50", "hubbard_L16_M80", "synthetic_14o_M200"])
+def test_sweep_energies_with_materialised_operators(name):
+    """The drop-in's default contracts FACTORISED enlarged-block operators; B2D_DROPIN_OPTIONS=factorised=0 builds the
+    materialised operators of round 1 (kron_scatter_kernel): same sweeps, same bounds."""
+    out, golden, stats = run_case(name, {"B2D_DROPIN_OPTIONS": "factorised=0"})
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+    got = parse_sweeps(out.stdout)
+    assert len(got) == len(golden)
+    bounds = sweep_bounds(name, len(golden))
+    for k, ((m1, s1, dw1, e1), (m2, s2, dw2, e2)) in enumerate(zip(got, golden)):
+        assert (m1, s1) == (m2, s2)
+        assert abs(e1 - e2) <= bounds[k], (name, k, e1, e2, bounds[k])
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("name", ILL_CONDITIONED)
 def test_threshold_regime_cases_with_reference_eigenvectors(name):
     """B2D_DROPIN_EIG=host: diagonalH, Davidson, density matrix, noise and operator rotation on the GPU, only dsyev_ + state

@@ -39,7 +39,8 @@
 //                         for restartable scratch files).  Check mode and state-specific runs always use "host".
 //   B2D_DROPIN_EIG        "host": diagnostic - the density-matrix eigen-decomposition and state selection stay with the reference
 //                         (dsyev_), everything else on the GPU: separates eigenvector non-uniqueness from arithmetic differences
-//   B2D_DROPIN_OPTIONS    "key=value,..." library options (b2d_set_option), e.g. eig_jacobi_max=512; factorised=0 (the default here is 1)
+//   B2D_DROPIN_OPTIONS    "key=value,..." library options (b2d_set_option), e.g. eig_jacobi_max=512; factorised=0|1 (default: per block iteration by size,
+//                         B2D_DROPIN_FACTORISED_MIN_STATES)
 //   B2D_DROPIN_STATS      file that receives one line per block iteration (timings, flops, H applications)
 //   RANK / WORLD_SIZE / LOCAL_RANK (torchrun) + B2D_NCCL_ID_FILE   several processes, one GPU each, run the SAME sweep: the operator terms of
 //                         multiplyH / diagonalH and the noise operators are partitioned over the ranks (b2d_plan(rank, nranks), cost-weighted
@@ -473,9 +474,14 @@ void ensure_ctx(const SpinBlock& big_c) {
   g.active = true;
   g.launch0 = b2d_kernel_launches(g.ctx);
   if (getenv("B2D_DROPIN_WORKSPACE_MB")) ck(b2d_set_option(g.ctx, "workspace_mb", atof(getenv("B2D_DROPIN_WORKSPACE_MB"))), "b2d_set_option");
-  // default of the drop-in: FACTORISED enlarged-block operators (no enlarged operator is materialised; measured faster from
-  // M ~ 1000 on and 16 x smaller in memory); B2D_DROPIN_OPTIONS="factorised=0" selects the materialised operators
-  ck(b2d_set_option(g.ctx, "factorised", 1.0), "b2d_set_option");
+  // default of the drop-in, per block iteration: FACTORISED enlarged-block operators (no enlarged operator is materialised; 16 x
+  // smaller in memory, measured faster from M ~ 1000 on) when an enlarged child has at least B2D_DROPIN_FACTORISED_MIN_STATES states
+  // (default 3000), materialised ones below (less host planning per block iteration).  B2D_DROPIN_OPTIONS="factorised=0|1" forces one form.
+  {
+    static const int min_states = getenv("B2D_DROPIN_FACTORISED_MIN_STATES") ? atoi(getenv("B2D_DROPIN_FACTORISED_MIN_STATES")) : 3000;
+    const int states = std::max(big.get_leftBlock()->get_stateInfo().totalStates, big.get_rightBlock()->get_stateInfo().totalStates);
+    ck(b2d_set_option(g.ctx, "factorised", states >= min_states ? 1.0 : 0.0), "b2d_set_option");
+  }
   if (getenv("B2D_DROPIN_OPTIONS")) {   // "key=value,key=value" -> b2d_set_option
     string all = getenv("B2D_DROPIN_OPTIONS");
     size_t pos = 0;

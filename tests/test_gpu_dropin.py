@@ -130,24 +130,26 @@ def test_sweep_energies_match_reference(name):
         worst = max(worst, abs(e1 - e2))
         strict += bounds[k] == 1e-8
         assert abs(e1 - e2) <= bounds[k], (name, k, m1, s1, e1, e2, bounds[k])   # north_star: per-sweep energies within 1e-8 Eh (or the reference's own spread)
-        assert abs(dw1 - dw2) <= 2e-2 * abs(dw2) + 5e-12, (name, dw1, dw2)      # printed with 4 significant digits
+        if bounds[k] == 1e-8:                                                    # (a sweep whose energy the reference itself cannot reproduce has no defined discarded weight either)
+            assert abs(dw1 - dw2) <= 2e-2 * abs(dw2) + 5e-12, (name, dw1, dw2)  # printed with 4 significant digits
     assert "n_multiply" in stats and "launches" in stats                         # the hooks ran on the device
     print("%s: %d sweep energies (%d at the 1e-8 bound), worst |dE| = %.2e Eh" % (name, len(got), strict, worst))
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["c2_d2h_M50", "hubbard_L16_M80", "synthetic_14o_M200"])
-def test_sweep_energies_with_materialised_operators(name):
-    """The drop-in's default contracts FACTORISED enlarged-block operators; B2D_DROPIN_OPTIONS=factorised=0 builds the
-    materialised operators of round 1 (kron_scatter_kernel): same sweeps, same bounds."""
-    out, golden, stats = run_case(name, {"B2D_DROPIN_OPTIONS": "factorised=0"})
+@pytest.mark.parametrize("mode", ["factorised=1", "factorised=0"])
+@pytest.mark.parametrize("name", ["c2_d2h_M50", "c2_d2h_M50_noise", "c2_d2h_M50_onedot_tail", "hubbard_L16_M1000", "synthetic_14o_M200"])
+def test_sweep_energies_with_either_operator_form(name, mode):
+    """The drop-in chooses per block iteration between FACTORISED enlarged-block operators (large blocks) and the materialised
+    operators of round 1 (kron_scatter_kernel; small blocks).  Forced to one form for the whole run: same sweeps, same bounds."""
+    out, golden, stats = run_case(name, {"B2D_DROPIN_OPTIONS": mode})
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
     got = parse_sweeps(out.stdout)
     assert len(got) == len(golden)
     bounds = sweep_bounds(name, len(golden))
     for k, ((m1, s1, dw1, e1), (m2, s2, dw2, e2)) in enumerate(zip(got, golden)):
         assert (m1, s1) == (m2, s2)
-        assert abs(e1 - e2) <= bounds[k], (name, k, e1, e2, bounds[k])
+        assert abs(e1 - e2) <= bounds[k], (name, mode, k, e1, e2, bounds[k])
 
 
 @pytest.mark.gpu

@@ -172,6 +172,7 @@ struct b2d_ctx {
   DevBuf trace_buf;        // B2D_TRACE diagnostic
   DevBuf parts;            // split-K partial copies of the destination wavefunction (run_sigma_schedule)
   int slice_iters = 256;   // pipeline iterations per split-K slice (0: no split)
+  int slice_iters_narrow = 0;   // option "slice_iters_narrow": slice length for sigma blocks with a dimension <= 64 (0: as the others)
   DevBuf psi_blocks;       // BlockDesc per psi block
   DevBuf diag_tasks, diag_begin, diag_gather, diag_pool, diag_regions;
   DevBuf partials, scalars;   // level-1 partial sums; G / theta / alpha / misc scalars
@@ -755,6 +756,7 @@ int b2d_set_option(b2d_ctx* ctx, const char* key, double value) {
   else if (k == "sync_debug") ctx->sync_debug = value != 0;
   else if (k == "multi_stream") ctx->multi_stream = value != 0;
   else if (k == "slice_iters") ctx->slice_iters = (int)value;
+  else if (k == "slice_iters_narrow") ctx->slice_iters_narrow = (int)value;
   else if (k == "eig_jacobi_max") ctx->eig_jacobi_max = (int)value;
   else if (k == "eig_cusolver") ctx->eig_cusolver = value != 0;
   else if (k == "persistent") ctx->persistent = value != 0;
@@ -1000,7 +1002,7 @@ int b2d_plan(b2d_ctx* ctx, const int32_t* psi_dq, double core_energy, int hubbar
       }
     }
     int64_t budget = (int64_t)(ctx->workspace_mb * 1024.0 * 1024.0 / 8.0);
-    ctx->sched = build_schedule(ctx->side[0], ctx->side[1], ctx->psi, ctx->terms_mine, 0, budget, ctx->forced_class, ctx->am, ctx->slice_iters);
+    ctx->sched = build_schedule(ctx->side[0], ctx->side[1], ctx->psi, ctx->terms_mine, 0, budget, ctx->forced_class, ctx->am, ctx->slice_iters, ctx->slice_iters_narrow);
     if (nranks > 1 && ctx->flops_all < 0.0) {
       // algorithmic flops of the whole sigma (all ranks) without keeping the other ranks' schedules
       Schedule all = build_schedule(ctx->side[0], ctx->side[1], ctx->psi, ctx->terms_all, 0, budget, ctx->forced_class, ctx->am);
@@ -1008,6 +1010,22 @@ int b2d_plan(b2d_ctx* ctx, const int32_t* psi_dq, double core_energy, int hubbar
     } else if (nranks <= 1) ctx->flops_all = ctx->sched.flops_alg;
   } catch (const std::exception& e) { return fail(ctx, B2D_ERR_ARG, std::string("b2d_plan: ") + e.what()); }
   ctx->planned = true;
+  if (getenv("B2D_PLAN_DEBUG")) {   // per step and tile class: tiles, pipeline iterations in total and of the longest tile (its serial length)
+    for (int st = 0; st < 2; ++st)
+      for (int k = 0; k < B2D_NUM_TILE_CLASSES; ++k) {
+        int64_t ntiles = 0, iters = 0, longest = 0, launches = 0, sum_longest = 0;
+        for (const Chunk& c : ctx->sched.chunks) {
+          const GemmBatch& b = st ? c.step2 : c.step1;
+          if (b.tiles[k].empty()) continue;
+          ++launches;
+          int64_t lmax = 0;
+          for (const GTile& t : b.tiles[k]) { const int64_t it = b.groups[t.group].kiters; iters += it; lmax = std::max(lmax, it); }
+          ntiles += (int64_t)b.tiles[k].size(); longest = std::max(longest, lmax); sum_longest += lmax;
+        }
+        if (launches) fprintf(stderr, "B2D_PLAN step %d class %d: launches %lld tiles %lld iterations %lld longest tile %lld sum over launches of the longest %lld\n", st + 1, k,
+                              (long long)launches, (long long)ntiles, (long long)iters, (long long)longest, (long long)sum_longest);
+      }
+  }
   ctx->layouts.clear();
   ctx->have_eig = ctx->have_rot = ctx->have_rotated = false;
   if (ctx->has_device) {

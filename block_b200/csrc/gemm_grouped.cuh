@@ -216,9 +216,6 @@ __global__ void __launch_bounds__(TileCfg<BM, BN>::THREADS)
   // producer cursor over (segment, k0); the segment descriptor stays in registers until the segment is exhausted
   int ps = grp.seg_begin, pk = 0;
   GSeg sg = segs[grp.seg_begin < grp.seg_end ? ps : 0];   // a group without segments (kiters == 0) stores zeros: rows of T no factor writes
-  // The NEXT descriptor is fetched one segment ahead: a factorised operator's segments are 2 - 4 pipeline iterations long, and in the
-  // narrow tile classes (few warps per CTA, few CTAs per SM) a descriptor fetch at the switch itself is ~1 us of exposed latency
-  GSeg sg_next = segs[ps + 1 < grp.seg_end ? ps + 1 : (grp.seg_begin < grp.seg_end ? ps : 0)];
   auto produce = [&](int stage) {
     const double* A = sg.a_base == B2D_BASE_ABS ? reinterpret_cast<const double*>(sg.a) : bases.p[sg.a_base] + sg.a;
     const double* B = sg.b_base == B2D_BASE_ABS ? reinterpret_cast<const double*>(sg.b) : bases.p[sg.b_base] + sg.b;
@@ -235,9 +232,7 @@ __global__ void __launch_bounds__(TileCfg<BM, BN>::THREADS)
     pk += GEMM_BK;
     if (pk >= sg.k) {
       pk = 0;
-      ++ps;
-      sg = sg_next;
-      if (ps + 1 < grp.seg_end) sg_next = segs[ps + 1];
+      if (++ps < grp.seg_end) sg = segs[ps];
     }
   };
 

@@ -803,18 +803,34 @@ cudaError_t launch_sector_eig(const BlockDesc* sectors, int nsectors, double* g,
   return cudaSuccess;
 }
 
-__global__ void gather_rotation_kernel(const GatherDesc* __restrict__ desc, const int* __restrict__ src_rows, const double* __restrict__ vt, double* __restrict__ u) {
-  const GatherDesc g = desc[blockIdx.x];
-  const int64_t n = (int64_t)g.d * g.ncols;
-  for (int64_t e = threadIdx.x; e < n; e += blockDim.x) {
-    int c = (int)(e / g.d), j = (int)(e % g.d);   // j fastest: coalesced reads of the eigenvector row
-    u[g.u_off + (int64_t)j * g.ld_u + c] = vt[g.vt_off + (int64_t)src_rows[g.row_begin + c] * g.ld_vt + j];
+// U_q[j, c] = Vt_q[row(c), j]: kept eigenvectors (rows of Vt) become the columns of the rotation matrix.  32 x 32 tiles through shared
+// memory: reads run along j (an eigenvector row), writes along c (a row of U) - both coalesced; grid.y = sector, grid.x strides over
+// the tiles of that sector.
+__global__ void __launch_bounds__(256) gather_rotation_kernel(const GatherDesc* __restrict__ desc, const int* __restrict__ src_rows, const double* __restrict__ vt, double* __restrict__ u) {
+  __shared__ double tile[32][33];
+  const GatherDesc g = desc[blockIdx.y];
+  const int tj = (g.d + 31) / 32, tc = (g.ncols + 31) / 32;
+  for (int t = blockIdx.x; t < tj * tc; t += gridDim.x) {
+    const int j0 = (t % tj) * 32, c0 = (t / tj) * 32;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+      const int c = c0 + r, j = j0 + threadIdx.x;
+      if (c < g.ncols && j < g.d) tile[r][threadIdx.x] = vt[g.vt_off + (int64_t)src_rows[g.row_begin + c] * g.ld_vt + j];
+    }
+    __syncthreads();
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+      const int j = j0 + r, c = c0 + threadIdx.x;
+      if (c < g.ncols && j < g.d) u[g.u_off + (int64_t)j * g.ld_u + c] = tile[threadIdx.x][r];
+    }
+    __syncthreads();
   }
 }
 cudaError_t launch_gather_rotation(const GatherDesc* desc, int nsectors, const int* src_rows, const double* vt, double* u, cudaStream_t s, int64_t* launches) {
   if (nsectors == 0) return cudaSuccess;
-  gather_rotation_kernel<<<nsectors, 256, 0, s>>>(desc, src_rows, vt, u);
-  B2D_LAUNCH_CHECK();
+  for (int s0 = 0; s0 < nsectors; s0 += 65535) {   // grid.y limit
+    const int ns = std::min(nsectors - s0, 65535);
+    gather_rotation_kernel<<<dim3(48, ns), dim3(32, 8), 0, s>>>(desc + s0, src_rows, vt, u);
+    B2D_LAUNCH_CHECK();
+  }
   return cudaSuccess;
 }
 

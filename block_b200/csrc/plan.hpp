@@ -398,11 +398,10 @@ struct Schedule {
 };
 
 constexpr int SPLITK_MAX = 8;   // K slices of one sigma block computed by different CTAs into private partial copies
-constexpr int SPLITK_NARROW_MAX = 32;   // ... of a sigma block with a dimension <= 64 (option slice_iters_narrow)
 
 // Build the two-step schedule for a list of operator pairs:  dst[lQ,rQ] += F * (s A_L[lQ,lQ'] src[lQ',rQ']) A_R[rQ,rQ']^T
 inline Schedule build_schedule(const Side& L, const Side& R, const PsiLayout& P, const std::vector<Term>& terms, int opq_spin,
-                               int64_t work_budget, int forced_class, AngMom& am, int slice_iters = 256, int slice_iters_narrow = 0) {
+                               int64_t work_budget, int forced_class, AngMom& am, int slice_iters = 256) {
   Schedule S;
   const int S_psi = P.dq[1];
   Chunk cur;
@@ -426,10 +425,6 @@ inline Schedule build_schedule(const Side& L, const Side& R, const PsiLayout& P,
       int64_t iters = 0;
       for (const GSeg& sg : pending[g]) iters += (sg.k + 15) / 16;
       int ns = (int)std::min<int64_t>(SPLITK_MAX, std::max<int64_t>(1, (iters + slice_iters / 2) / std::max(slice_iters, 1)));
-      // a sigma block narrower than 64 rows or columns is covered by a handful of narrow tiles whose K loop is latency bound (short
-      // segments, one descriptor fetch each): cut it into more, shorter slices so that the launch has enough CTAs to hide that latency
-      if (slice_iters_narrow > 0 && (G0.m <= 64 || G0.n <= 64))
-        ns = (int)std::min<int64_t>(SPLITK_NARROW_MAX, std::max<int64_t>(1, (iters + slice_iters_narrow / 2) / slice_iters_narrow));
       if (slice_iters <= 0) ns = 1;
       S.nslices = std::max(S.nslices, ns);
       size_t pos = 0;

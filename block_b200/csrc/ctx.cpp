@@ -172,6 +172,7 @@ struct b2d_ctx {
   DevBuf trace_buf;        // B2D_TRACE diagnostic
   DevBuf parts;            // split-K partial copies of the destination wavefunction (run_sigma_schedule)
   int slice_iters = 256;   // pipeline iterations per split-K slice (0: no split)
+  int slice_iters_narrow = 0;   // option "slice_iters_narrow": finer slices for the narrow tiles of a sigma block (0: the same slices as its 128 x 128 tiles)
   DevBuf psi_blocks;       // BlockDesc per psi block
   DevBuf diag_tasks, diag_begin, diag_gather, diag_pool, diag_regions;
   DevBuf partials, scalars;   // level-1 partial sums; G / theta / alpha / misc scalars
@@ -755,6 +756,7 @@ int b2d_set_option(b2d_ctx* ctx, const char* key, double value) {
   else if (k == "sync_debug") ctx->sync_debug = value != 0;
   else if (k == "multi_stream") ctx->multi_stream = value != 0;
   else if (k == "slice_iters") ctx->slice_iters = (int)value;
+  else if (k == "slice_iters_narrow") ctx->slice_iters_narrow = (int)value;
   else if (k == "eig_jacobi_max") ctx->eig_jacobi_max = (int)value;
   else if (k == "eig_cusolver") ctx->eig_cusolver = value != 0;
   else if (k == "persistent") ctx->persistent = value != 0;
@@ -1000,7 +1002,7 @@ int b2d_plan(b2d_ctx* ctx, const int32_t* psi_dq, double core_energy, int hubbar
       }
     }
     int64_t budget = (int64_t)(ctx->workspace_mb * 1024.0 * 1024.0 / 8.0);
-    ctx->sched = build_schedule(ctx->side[0], ctx->side[1], ctx->psi, ctx->terms_mine, 0, budget, ctx->forced_class, ctx->am, ctx->slice_iters);
+    ctx->sched = build_schedule(ctx->side[0], ctx->side[1], ctx->psi, ctx->terms_mine, 0, budget, ctx->forced_class, ctx->am, ctx->slice_iters, ctx->slice_iters_narrow);
     if (nranks > 1 && ctx->flops_all < 0.0) {
       // algorithmic flops of the whole sigma (all ranks) without keeping the other ranks' schedules
       Schedule all = build_schedule(ctx->side[0], ctx->side[1], ctx->psi, ctx->terms_all, 0, budget, ctx->forced_class, ctx->am);

@@ -366,6 +366,7 @@ inline void make_tiles(GemmBatch& b, int forced_class) {
     for (const auto& bm : mb)
       for (const auto& bn : nb) {
         const int c = 3 * bm.second + bn.second;
+        if ((G.pad0 == 1 && c != 0) || (G.pad0 == 2 && c == 0)) continue;   // split-K families of one sigma block (build_schedule): 128 x 128 tiles / the others
         const int tm = 128 >> bm.second, tn = 128 >> bn.second;
         const int um = std::min(tm, G.m - bm.first), un = std::min(tn, G.n - bn.first);
         b.class_flops[c] += 2.0 * um * un * (double)ktot;
@@ -398,10 +399,11 @@ struct Schedule {
 };
 
 constexpr int SPLITK_MAX = 8;   // K slices of one sigma block computed by different CTAs into private partial copies
+constexpr int SPLITK_NARROW_MAX = 32;   // ... for the narrow tiles of a sigma block (option slice_iters_narrow)
 
 // Build the two-step schedule for a list of operator pairs:  dst[lQ,rQ] += F * (s A_L[lQ,lQ'] src[lQ',rQ']) A_R[rQ,rQ']^T
 inline Schedule build_schedule(const Side& L, const Side& R, const PsiLayout& P, const std::vector<Term>& terms, int opq_spin,
-                               int64_t work_budget, int forced_class, AngMom& am, int slice_iters = 256) {
+                               int64_t work_budget, int forced_class, AngMom& am, int slice_iters = 256, int slice_iters_narrow = 0) {
   Schedule S;
   const int S_psi = P.dq[1];
   Chunk cur;
@@ -426,21 +428,41 @@ inline Schedule build_schedule(const Side& L, const Side& R, const PsiLayout& P,
       for (const GSeg& sg : pending[g]) iters += (sg.k + 15) / 16;
       int ns = (int)std::min<int64_t>(SPLITK_MAX, std::max<int64_t>(1, (iters + slice_iters / 2) / std::max(slice_iters, 1)));
       if (slice_iters <= 0) ns = 1;
-      S.nslices = std::max(S.nslices, ns);
-      size_t pos = 0;
-      int64_t done = 0;
-      for (int sl = 0; sl < ns; ++sl) {
-        GGroup G = G0;
-        if (sl > 0) { G.c_base = B2D_BASE_AUX; G.c = G0.c + (int64_t)(sl - 1) * P.Wp; }
-        G.seg_begin = (int)cur.step2.segs.size();
-        const int64_t target = iters * (sl + 1) / ns;
-        while (pos < pending[g].size() && (done < target || sl == ns - 1)) {
-          done += (pending[g][pos].k + 15) / 16;
-          cur.step2.segs.push_back(pending[g][pos++]);
-        }
-        G.seg_end = (int)cur.step2.segs.size();
-        if (G.seg_end > G.seg_begin) sliced.push_back(G);
+      // The narrow tiles of a sigma block (remainder bands of a ragged sector: few warps per CTA, latency bound per pipeline iteration) run
+      // the same K loop as its 128 x 128 tiles and finish long after them.  Option slice_iters_narrow: they get their OWN, finer slicing
+      // (a second family of slice groups that make_tiles restricts to the narrow classes), i.e. more and shorter CTAs.
+      int ns_narrow = 0;
+      bool has_big = false, has_narrow = false;
+      if (slice_iters_narrow > 0 && slice_iters > 0 && !((forced_class == -1 || forced_class == 3) && G0.m <= B2D_TINY_DIM && G0.n <= B2D_TINY_DIM)) {
+        const int fc = forced_class == 3 ? -1 : forced_class;
+        std::vector<std::pair<int, int>> mb, nb;
+        make_bands(G0.m, fc >= 10 ? fc / 10 - 1 : fc, mb);
+        make_bands(G0.n, fc >= 10 ? fc % 10 : fc, nb);
+        for (const auto& bm : mb)
+          for (const auto& bn : nb) { if (bm.second == 0 && bn.second == 0) has_big = true; else has_narrow = true; }
+        ns_narrow = (int)std::min<int64_t>(SPLITK_NARROW_MAX, std::max<int64_t>(1, (iters + slice_iters_narrow / 2) / slice_iters_narrow));
+        if (!has_narrow || ns_narrow <= ns) ns_narrow = 0;
       }
+      auto emit_family = [&](int nsl, uint8_t filter) {
+        S.nslices = std::max(S.nslices, nsl);
+        size_t pos = 0;
+        int64_t done = 0;
+        for (int sl = 0; sl < nsl; ++sl) {
+          GGroup G = G0;
+          G.pad0 = filter;
+          if (sl > 0) { G.c_base = B2D_BASE_AUX; G.c = G0.c + (int64_t)(sl - 1) * P.Wp; }
+          G.seg_begin = (int)cur.step2.segs.size();
+          const int64_t target = iters * (sl + 1) / nsl;
+          while (pos < pending[g].size() && (done < target || sl == nsl - 1)) {
+            done += (pending[g][pos].k + 15) / 16;
+            cur.step2.segs.push_back(pending[g][pos++]);
+          }
+          G.seg_end = (int)cur.step2.segs.size();
+          if (G.seg_end > G.seg_begin) sliced.push_back(G);
+        }
+      };
+      if (ns_narrow > 0 && has_big) { emit_family(ns, 1); emit_family(ns_narrow, 2); }
+      else emit_family(ns_narrow > 0 ? ns_narrow : ns, 0);
     }
     cur.step2.groups.swap(sliced);
     make_tiles(cur.step1, forced_class);

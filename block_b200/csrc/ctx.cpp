@@ -172,6 +172,7 @@ struct b2d_ctx {
   DevBuf trace_buf;        // B2D_TRACE diagnostic
   DevBuf parts;            // split-K partial copies of the destination wavefunction (run_sigma_schedule)
   int slice_iters = 256;   // pipeline iterations per split-K slice (0: no split)
+  bool partition_renorm = false;   // option "partition_renormalisation": several ranks that ALL hold the whole block divide the eigen-decomposition (sectors) and the operator rotation (operators) and all-reduce the results
   int slice_iters_narrow = 0;   // option "slice_iters_narrow": finer slices for the narrow tiles of a sigma block (0: the same slices as its 128 x 128 tiles)
   DevBuf psi_blocks;       // BlockDesc per psi block
   DevBuf diag_tasks, diag_begin, diag_gather, diag_pool, diag_regions;
@@ -757,6 +758,7 @@ int b2d_set_option(b2d_ctx* ctx, const char* key, double value) {
   else if (k == "multi_stream") ctx->multi_stream = value != 0;
   else if (k == "slice_iters") ctx->slice_iters = (int)value;
   else if (k == "slice_iters_narrow") ctx->slice_iters_narrow = (int)value;
+  else if (k == "partition_renormalisation") ctx->partition_renorm = value != 0.0;
   else if (k == "eig_jacobi_max") ctx->eig_jacobi_max = (int)value;
   else if (k == "eig_cusolver") ctx->eig_cusolver = value != 0;
   else if (k == "persistent") ctx->persistent = value != 0;
@@ -1564,6 +1566,28 @@ int b2d_diagonalise_dm(b2d_ctx* ctx, double* evals_out) {
   for (int q = 0; q < L.nq; ++q) {
     if (L.dims[q] <= ctx->eig_jacobi_max) small.push_back(sd[q]); else large.push_back(q);
   }
+  // Several ranks holding the same density matrix (option partition_renormalisation; SURVEY 8e "rho eigensolve: sectors round-robin"): the
+  // LARGE sectors are divided by cost (d^3, longest first), rank 0 also takes the small ones, everybody starts from zero-filled results
+  // and one all-reduce at the end gives every rank every sector - each value is computed by exactly one rank, so all ranks hold the
+  // same bits.
+  const bool part = ctx->partition_renorm && ctx->nranks > 1 && ctx->nccl.comm && !ctx->eig_cusolver;
+  if (part) {
+    std::vector<int> order = large;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return L.dims[a] > L.dims[b]; });
+    std::vector<double> load(ctx->nranks, 0.0);
+    std::vector<int> mine;
+    for (int q : order) {
+      int best = 0;
+      for (int r = 1; r < ctx->nranks; ++r) if (load[r] < load[best]) best = r;
+      load[best] += (double)L.dims[q] * L.dims[q] * L.dims[q];
+      if (best == ctx->rank) mine.push_back(q);
+    }
+    std::sort(mine.begin(), mine.end());
+    large.swap(mine);
+    if (ctx->rank != 0) small.clear();
+    CU(cudaMemsetAsync(ctx->eig_vt.p, 0, (size_t)ctx->rho_padded * 8, ctx->stream));
+    CU(cudaMemsetAsync(ctx->eig_vals.p, 0, (size_t)nev * 8, ctx->stream));
+  }
   int rc = upload_desc(ctx, ctx->sector_desc, small.data(), small.size() * sizeof(BlockDesc));
   if (rc) return rc;
   begin_timing(ctx);
@@ -1688,7 +1712,7 @@ int b2d_diagonalise_dm(b2d_ctx* ctx, double* evals_out) {
     D.buf.release();
     std::swap(ctx->eig_vt, ctx->eig_tmp);                   // small sectors: 1.5 x their rows sit in the old buffer, so copy them over unscaled
     for (int q = 0; q < L.nq; ++q)
-      if (L.dims[q] <= ctx->eig_jacobi_max)
+      if (L.dims[q] <= ctx->eig_jacobi_max)   // (partitioned: on ranks other than 0 these are zeros in both buffers)
         CU(cudaMemcpyAsync((double*)ctx->eig_vt.p + ctx->rho_off[q], (const double*)ctx->eig_tmp.p + ctx->rho_off[q],
                            (size_t)L.dims[q] * pad_ld(L.dims[q]) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
     if (getenv("B2D_EIG_DEBUG")) fprintf(stderr, "b2d eig: %d large sectors (max %d states), %d block-Jacobi sweeps\n", (int)large.size(),
@@ -1765,6 +1789,12 @@ int b2d_diagonalise_dm(b2d_ctx* ctx, double* evals_out) {
                        (double*)ctx->eig_vals.p, ctx->stream, &ctx->launches));
     CU(cudaStreamSynchronize(ctx->stream));
     D.buf.release();
+  }
+  if (part) {
+    rc = allreduce(ctx, (double*)ctx->eig_vt.p, ctx->rho_padded);
+    if (rc) return rc;
+    rc = allreduce(ctx, (double*)ctx->eig_vals.p, nev);
+    if (rc) return rc;
   }
   end_timing(ctx);
   std::vector<double> raw(nev);
@@ -1958,12 +1988,38 @@ int b2d_transform_operators(b2d_ctx* ctx) {
     S.chunks.push_back(std::move(cur));
     cur = Chunk();
   };
-  double* rot = (double*)ctx->rot.p;
-  (void)rot;
+  // Several ranks that all hold the whole block (option partition_renormalisation; SURVEY 8e "rotation"): the operators are divided by
+  // cost (longest first), every rank rotates its share into the zero-filled arena - the same layout everywhere - and one all-reduce
+  // completes the block on every rank with identical bits.
+  const bool part = ctx->partition_renorm && ctx->nranks > 1 && ctx->nccl.comm;
+  std::vector<char> mine_op(L.ops.size(), 1);
+  if (part) {
+    std::vector<double> cost(L.ops.size(), 0.0);
+    for (size_t m = 0; m < L.ops.size(); ++m) {
+      const OpRec& r = N.ops[m];
+      if (!(L.ops[m].dev || L.ops[m].factorised)) continue;
+      for (int a = 0; a < N.nq; ++a)
+        for (int b = 0; b < N.nq; ++b)
+          if (r.allowed[(size_t)a * N.nq + b]) {
+            const double dQ = L.dims[ctx->rotated_old[a]], dQp = L.dims[ctx->rotated_old[b]];
+            cost[m] += dQ * (dQp + N.dims[a]) * N.dims[b];
+          }
+    }
+    std::vector<int> order(L.ops.size());
+    for (size_t m = 0; m < order.size(); ++m) order[m] = (int)m;
+    std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return cost[x] > cost[y]; });
+    std::vector<double> load(ctx->nranks, 0.0);
+    for (int m : order) {
+      int best = 0;
+      for (int r = 1; r < ctx->nranks; ++r) if (load[r] < load[best]) best = r;
+      load[best] += cost[m];
+      mine_op[m] = best == ctx->rank;
+    }
+  }
   for (size_t m = 0; m < L.ops.size(); ++m) {
     const OpRec& o = L.ops[m];
     const OpRec& r = N.ops[m];
-    if (!(o.dev || o.factorised)) continue;
+    if (!(o.dev || o.factorised) || !mine_op[m]) continue;
     View ov{&L, &o, false};
     int64_t need = 0;
     for (int a = 0; a < N.nq; ++a)
@@ -2025,6 +2081,7 @@ int b2d_transform_operators(b2d_ctx* ctx) {
   if (rc) return rc;
   begin_timing(ctx);
   rc = run_schedule(ctx, S, D, nullptr, (double*)ctx->rotated_arena.p, (double*)ctx->rot.p);
+  if (!rc && part) rc = allreduce(ctx, (double*)ctx->rotated_arena.p, total);
   end_timing(ctx);
   CU(cudaStreamSynchronize(ctx->stream));
   D.buf.release();

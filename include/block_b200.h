@@ -67,7 +67,11 @@ int b2d_abi_version(void);                        /* 4 */
  * operators - operatorfunctions.C:188-250 rowstride / colstride structure - and sigma, diag(H), the noise products and the operator
  * rotation contract those factors directly: ~16x less operator memory, no flops on the structural zeros of the Kronecker blocks),
  * "eig_jacobi_max" (largest sector for the single-CTA Jacobi kernel, default 64; larger sectors use the block Jacobi kernel),
- * "eig_cusolver" (diagnostic: cusolverDnDsyevd for the large sectors, never the default). */
+ * "eig_cusolver" (diagnostic: cusolverDnDsyevd for the large sectors, never the default), "slice_iters" (pipeline iterations per
+ * split-K slice of a sigma block, default 256, at most 8 slices), "slice_iters_narrow" (> 0: the narrow tiles of a sigma block - the
+ * remainder bands of ragged sectors - get their own, finer slicing, at most 32 slices; default 0 = off: measured +0.7 % on the
+ * benchmark for 2 GB of partial buffers), "presum_identity", "balance_terms" (cost-weighted term ownership for several ranks),
+ * "cache_device_mb" (device budget of the block cache; <= 0: automatic). */
 int b2d_set_option(b2d_ctx* ctx, const char* key, double value);
 
 /* ---- block description: replaces the host-side SpinBlock / StateInfo / Op_component objects ---------------- */

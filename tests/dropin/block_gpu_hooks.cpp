@@ -469,6 +469,8 @@ void ensure_ctx(const SpinBlock& big_c) {
       }
       ck(b2d_comm_init(g.ctx, id, g.rank, g.world), "b2d_comm_init");
       ck(b2d_set_option(g.ctx, "balance_terms", 1.0), "b2d_set_option");
+      // every rank holds the whole block here: the eigen-decomposition (sectors) and the operator rotation (operators) are divided too
+      if (!getenv("B2D_DROPIN_REPLICATE_RENORM")) ck(b2d_set_option(g.ctx, "partition_renormalisation", 1.0), "b2d_set_option");
     }
   }
   g.active = true;

@@ -1,6 +1,7 @@
 """GPU (needs >= 2 devices; skipped on a one-GPU box): the drop-in sweep on 2 GPUs - one process per GPU under torchrun, the operator
 terms of multiplyH / diagonalH and the noise operators partitioned over the ranks (distribute.C's boost::mpi split -> b2d_plan(rank,
-nranks)), partial sigma / diag(H) / noise density matrices all-reduced over NCCL inside the library.  Every rank must print the same sweep
+nranks)), partial sigma / diag(H) / noise density matrices all-reduced over NCCL inside the library; the eigen-decomposition of the density matrix
+(sectors) and the operator rotation (operators) are divided over the ranks as well (option partition_renormalisation).  Every rank must print the same sweep
 energies, and they must be the unmodified reference's (same bounds as tests/test_gpu_dropin.py)."""
 import json
 import os
@@ -27,7 +28,7 @@ def _free_port():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["c2_d2h_M50_noise", "hubbard_L16_M80"])
+@pytest.mark.parametrize("name", ["c2_d2h_M50_noise", "hubbard_L16_M80", "hubbard_L16_M1000"])   # the last one has sectors for the (partitioned) block-Jacobi solver
 def test_two_gpu_sweep_matches_reference(name):
     if _gpus() < 2:
         pytest.skip("needs 2 GPUs (gpurun --gpus 2)")

@@ -164,6 +164,19 @@ struct b2d_ctx {
   // operator uploads are batched: host images and block descriptors of the operators added since the last flush
   // (one H2D copy + one pack launch per flush instead of three synchronisations per operator)
   double* pend_pinned = nullptr;          // pinned host staging (cudaMallocHost): the H2D copy of a flush is a true DMA
+  struct PinnedBuf {                      // grow-only pinned host buffer for large descriptor arrays (scatter tasks and their tiles)
+    void* p = nullptr; size_t cap = 0;
+    bool reserve(size_t bytes) {
+      if (bytes <= cap) return true;
+      if (p) cudaFreeHost(p);
+      p = nullptr; cap = 0;
+      size_t want = std::max(bytes + bytes / 2, (size_t)1 << 20);
+      if (cudaMallocHost(&p, want) != cudaSuccess) { cudaGetLastError(); p = nullptr; return false; }
+      cap = want;
+      return true;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+  } kron_pinned_tasks, kron_pinned_tiles;
   size_t pend_cap = 0, pend_used = 0;     // doubles
   std::vector<BlockDesc> pend_desc;
 
@@ -216,6 +229,12 @@ struct b2d_ctx {
     int identity_ld = 0;
     std::vector<std::vector<std::pair<size_t, SubBlock>>> pend_subs;   // factorised mode: per operator, (stored block index, factor) in product order
     std::map<int, std::vector<int>> pair_hits;   // deferred scatter: per operator, contributions received so far by each (row piece, column piece)
+    // Scatter tasks of one product as a TEMPLATE: every product of an operator whose left factor has the same quantum numbers, orientation
+    // and allowed pattern and whose right factor is the same operator has the same tasks up to the left operator's base address and the
+    // scale (a complementary operator is a sum of hundreds of such products)
+    struct FactorTemplate { size_t blk; SubBlock sb; int64_t a_off; bool identity; };   // factorised operators: the same idea for the factor lists
+    struct KronTemplate { std::vector<KronTask> tasks; std::vector<int> pair; int pair_count = 0; double bytes = 0.0; int left_owner = -1; std::vector<FactorTemplate> factors; };
+    std::map<std::array<int64_t, 8>, KronTemplate> kron_templates;
     struct Combo { std::vector<std::pair<const double*, bool>> parts; std::vector<double> ratios; const double* block; };
     std::map<std::array<int64_t, 3>, std::vector<Combo>> combos;       // (first part address, m, n) -> pre-summed blocks, for sharing
     Side side;                              // collected sectors of the enlarged block + the operators built so far
@@ -350,22 +369,42 @@ int upload_desc(b2d_ctx* ctx, DevBuf& buf, const void* host, size_t bytes) {
 // order.  One upload of the tasks, one of the band list (every task cut into bands of KRON_BAND destination rows for load balance).
 void begin_timing(b2d_ctx* ctx);
 void end_timing(b2d_ctx* ctx);
-int run_kron_rounds(b2d_ctx* ctx, const std::vector<KronTask>& tasks, const std::vector<int>& round_begin, bool timed = false) {
-  if (tasks.empty()) return B2D_OK;
-  int rc = upload_desc(ctx, ctx->kron_tasks, tasks.data(), tasks.size() * sizeof(KronTask));
-  if (rc) return rc;
-  std::vector<KronTile> tiles;
+// tasks_pinned: the array lives in pinned host memory (ctx->kron_pinned_tasks): its upload is one DMA without the driver's staging copy
+int run_kron_rounds(b2d_ctx* ctx, const KronTask* tasks, size_t ntasks, const std::vector<int>& round_begin, bool timed = false, bool tasks_pinned = false) {
+  if (ntasks == 0) return B2D_OK;
+  int rc = B2D_OK;
+  if (tasks_pinned) {
+    CU(ctx->kron_tasks.reserve(ntasks * sizeof(KronTask)));
+    CU(cudaMemcpyAsync(ctx->kron_tasks.p, tasks, ntasks * sizeof(KronTask), cudaMemcpyHostToDevice, ctx->stream));
+  } else {
+    rc = upload_desc(ctx, ctx->kron_tasks, tasks, ntasks * sizeof(KronTask));
+    if (rc) return rc;
+  }
+  size_t ntiles = 0;
+  for (size_t t = 0; t < ntasks; ++t) ntiles += (size_t)(tasks[t].a_rows * tasks[t].b_rows + KRON_BAND - 1) / KRON_BAND;
+  std::vector<KronTile> tiles_pageable;
+  KronTile* tiles = nullptr;
+  const bool tiles_pinned = ctx->kron_pinned_tiles.reserve(std::max<size_t>(ntiles, 1) * sizeof(KronTile));
+  if (tiles_pinned) tiles = (KronTile*)ctx->kron_pinned_tiles.p;
+  else { tiles_pageable.resize(std::max<size_t>(ntiles, 1)); tiles = tiles_pageable.data(); }
   std::vector<int> tile_begin(round_begin.size(), 0);
+  size_t nt = 0;
   for (size_t r = 0; r + 1 < round_begin.size(); ++r) {
-    tile_begin[r] = (int)tiles.size();
+    tile_begin[r] = (int)nt;
     for (int t = round_begin[r]; t < round_begin[r + 1]; ++t) {
       const int rows = tasks[t].a_rows * tasks[t].b_rows;
-      for (int b = 0; b * KRON_BAND < rows; ++b) tiles.push_back(KronTile{t, b});
+      for (int b = 0; b * KRON_BAND < rows; ++b) tiles[nt++] = KronTile{t, b};
     }
   }
-  tile_begin[round_begin.size() - 1] = (int)tiles.size();
-  rc = upload_desc(ctx, ctx->kron_tiles, tiles.data(), tiles.size() * sizeof(KronTile));
-  if (rc) return rc;
+  tile_begin[round_begin.size() - 1] = (int)nt;
+  if (tiles_pinned) {
+    CU(ctx->kron_tiles.reserve(std::max<size_t>(nt, 1) * sizeof(KronTile)));
+    CU(cudaMemcpyAsync(ctx->kron_tiles.p, tiles, nt * sizeof(KronTile), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));   // the pinned buffers are reused by the next flush
+  } else {
+    rc = upload_desc(ctx, ctx->kron_tiles, tiles, nt * sizeof(KronTile));
+    if (rc) return rc;
+  }
   if (timed) begin_timing(ctx);   // b2d_last_timing: device time of the scatter launches alone (descriptors are resident)
   for (size_t r = 0; r + 1 < round_begin.size(); ++r)
     CU(launch_kron_scatter((const KronTask*)ctx->kron_tasks.p, (const KronTile*)ctx->kron_tiles.p + tile_begin[r], tile_begin[r + 1] - tile_begin[r], ctx->stream,
@@ -375,6 +414,10 @@ int run_kron_rounds(b2d_ctx* ctx, const std::vector<KronTask>& tasks, const std:
 }
 
 // pack every pending operator image into its padded device blocks (dev_off is absolute: base pointer 0)
+int run_kron_rounds(b2d_ctx* ctx, const std::vector<KronTask>& tasks, const std::vector<int>& round_begin, bool timed = false) {
+  return run_kron_rounds(ctx, tasks.data(), tasks.size(), round_begin, timed, false);
+}
+
 int flush_pending_ops(b2d_ctx* ctx) {
   if (ctx->pend_desc.empty()) { ctx->pend_used = 0; return B2D_OK; }
   CU(cudaSetDevice(ctx->device));
@@ -698,6 +741,7 @@ void b2d_destroy(b2d_ctx* ctx) {
     for (DevBuf& b : ctx->spare_bufs) b.release();
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->pend_pinned) cudaFreeHost(ctx->pend_pinned);
+    ctx->kron_pinned_tasks.release(); ctx->kron_pinned_tiles.release();
     for (auto& ev : ctx->ev) if (ev) cudaEventDestroy(ev);
     for (auto& ev : ctx->phase_events) cudaEventDestroy(ev);
     for (auto& st : ctx->side_streams) if (st) cudaStreamDestroy(st);
@@ -2514,14 +2558,19 @@ static int flush_product_tasks(b2d_ctx* ctx) {
   std::vector<int> count(nrounds + 1, 0);
   for (int r : ctx->pend_kron_round) count[r + 1]++;
   for (int r = 0; r < nrounds; ++r) count[r + 1] += count[r];
-  std::vector<KronTask> sorted(ctx->pend_kron.size());
+  const size_t ntasks = ctx->pend_kron.size();
+  std::vector<KronTask> sorted_pageable;
+  const bool pinned = ctx->kron_pinned_tasks.reserve(ntasks * sizeof(KronTask));   // counting sort straight into pinned memory
+  KronTask* sorted = nullptr;
+  if (pinned) sorted = (KronTask*)ctx->kron_pinned_tasks.p;
+  else { sorted_pageable.resize(ntasks); sorted = sorted_pageable.data(); }
   {
     std::vector<int> at(count.begin(), count.end() - 1);
-    for (size_t i = 0; i < ctx->pend_kron.size(); ++i) sorted[at[ctx->pend_kron_round[i]]++] = ctx->pend_kron[i];
+    for (size_t i = 0; i < ntasks; ++i) sorted[at[ctx->pend_kron_round[i]]++] = ctx->pend_kron[i];
   }
   // round 0 = the first contribution to a piece of freshly zero-filled storage: it is stored, not read-modified-written
   for (int i = 0; i < count[1]; ++i) sorted[i].pad |= 1;
-  int rc = run_kron_rounds(ctx, sorted, count, true);
+  int rc = run_kron_rounds(ctx, sorted, ntasks, count, true, pinned);
   if (rc) return rc;
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->kron_last_rounds = nrounds;
@@ -2571,6 +2620,74 @@ static int product_op_accumulate_impl(b2d_ctx* ctx, int prod_id, int left_op, in
           if (rb->allowed[(size_t)i * R.nq + j]) { rb_ref[(size_t)i * R.nq + j] = off; off += (int64_t)R.dims[i] * R.dims[j]; }
     }
     auto& out = P.pend_subs[prod_id];
+    // the factors for scale = 1 and a left operator stored at address 0: a template shared by the products of this operator with the same
+    // structure (see KronTemplate)
+    const bool left_is_identity = trace_l || la->optype == OP_OVERLAP;
+    const std::array<int64_t, 8> fkey{(int64_t)prod_id, trace_l ? -1 : (int64_t)la->dq[0], trace_l ? 0 : (int64_t)la->dq[1], trace_l ? 0 : (int64_t)la->dq[2],
+                                      (int64_t)(left_transposed != 0), (int64_t)right_op, (int64_t)(right_transposed != 0), (int64_t)(left_is_identity ? 1 : 0) + 2};
+    b2d_ctx::Product::KronTemplate* tp = &P.kron_templates[fkey];
+    b2d_ctx::Product::KronTemplate fresh;
+    if (tp->left_owner >= 0 && la && (L.ops[tp->left_owner].dev_size != la->dev_size || L.ops[tp->left_owner].packed_size != la->packed_size)) tp = &fresh;
+    if (tp->pair_count == 0) {
+      b2d_ctx::Product::KronTemplate& T = *tp;
+      T.left_owner = la ? left_op : -1;
+      try {
+        for (int cq = 0; cq < P.side.nq; ++cq)
+          for (int cqp = 0; cqp < P.side.nq; ++cqp) {
+            if (!c.allowed[(size_t)cq * P.side.nq + cqp]) continue;
+            int row = 0;
+            for (int oi : P.old_to_new[cq]) {
+              int col = 0;
+              for (int oj : P.old_to_new[cqp]) {
+                const int aq = P.lmap[oi], aqp = P.lmap[oj], bq = P.rmap[oi], bqp = P.rmap[oj];
+                const bool a_ok = trace_l ? aq == aqp : a.allowed(aq, aqp);
+                const bool b_ok = trace_r ? bq == bqp : b.allowed(bq, bqp);
+                if (a_ok && b_ok) {
+                  double f = ctx->am.ninej(L.quantum(aqp)[1], R.quantum(bqp)[1], P.side.quantum(cqp)[1], sa, sb, sc, L.quantum(aq)[1], R.quantum(bq)[1],
+                                           P.side.quantum(cq)[1]);
+                  if (!trace_l && !trace_r) f *= a.scaling(ctx->am, aq, aqp) * b.scaling(ctx->am, bq, bqp);
+                  if (rb && rb->fermion && (L.quantum(aqp)[0] & 1)) f = -f;
+                  if (rb) f *= rb->host[(size_t)(b.t ? rb_ref[(size_t)bqp * R.nq + bq] : rb_ref[(size_t)bq * R.nq + bqp])];   // 1 x 1 block: its own transpose
+                  if (f != 0.0) {
+                    b2d_ctx::Product::FactorTemplate ft;
+                    ft.blk = (size_t)cq * P.side.nq + cqp;
+                    ft.sb.r0 = row; ft.sb.c0 = col; ft.sb.m = L.dims[aq]; ft.sb.n = L.dims[aqp]; ft.sb.alpha = f;
+                    // the OVERLAP operator of a renormalised block is the identity (same bra and ket states; what the rotation leaves of it is
+                    // I + O(1e-16)): it is contracted as THE identity block, so that "child block + identity" stays a pair of direct factors
+                    ft.identity = left_is_identity;
+                    if (ft.identity) { ft.sb.a = P.identity; ft.sb.lda = P.identity_ld; ft.sb.t = false; ft.a_off = 0; }
+                    else { ft.sb.a = nullptr; ft.a_off = a.stored_off(aq, aqp); ft.sb.lda = a.stored_ld(aq, aqp); ft.sb.t = a.t; }
+                    T.factors.push_back(ft);
+                  }
+                }
+                col += P.unc_dims[oj];
+              }
+              row += P.unc_dims[oi];
+            }
+          }
+      } catch (const std::exception& e) { T = b2d_ctx::Product::KronTemplate(); return fail(ctx, B2D_ERR_ARG, e.what()); }
+      T.pair_count = 1;
+    }
+    for (const b2d_ctx::Product::FactorTemplate& ft : tp->factors) {
+      SubBlock sbk = ft.sb;
+      if (!ft.identity) sbk.a = la->dev + ft.a_off;
+      sbk.alpha *= scale;
+      out.emplace_back(ft.blk, sbk);
+    }
+    return B2D_OK;
+  }
+  // the tasks for scale = 1 and a left operator stored at address 0 (template, shared by the products of this operator with the same
+  // structure); the loop below runs once per template
+  const std::array<int64_t, 8> tkey{(int64_t)prod_id, trace_l ? -1 : (int64_t)la->dq[0], trace_l ? 0 : (int64_t)la->dq[1], trace_l ? 0 : (int64_t)la->dq[2],
+                                    (int64_t)(left_transposed != 0), (int64_t)right_op, (int64_t)(right_transposed != 0), trace_l ? 0 : (int64_t)la->allowed.size()};
+  b2d_ctx::Product::KronTemplate* tp = &P.kron_templates[tkey];
+  b2d_ctx::Product::KronTemplate fresh;
+  if (tp->left_owner >= 0 && la && (L.ops[tp->left_owner].dev_size != la->dev_size || L.ops[tp->left_owner].packed_size != la->packed_size))
+    tp = &fresh;   // same quantum numbers but another block pattern (never with the reference's allocate rule, BaseOperator.C:123-145): no sharing
+  if (tp->pair_count == 0) {
+    b2d_ctx::Product::KronTemplate& T = *tp;
+    T.left_owner = la ? left_op : -1;
+    int pair_index = 0;
     try {
       for (int cq = 0; cq < P.side.nq; ++cq)
         for (int cqp = 0; cqp < P.side.nq; ++cqp) {
@@ -2582,73 +2699,41 @@ static int product_op_accumulate_impl(b2d_ctx* ctx, int prod_id, int left_op, in
               const int aq = P.lmap[oi], aqp = P.lmap[oj], bq = P.rmap[oi], bqp = P.rmap[oj];
               const bool a_ok = trace_l ? aq == aqp : a.allowed(aq, aqp);
               const bool b_ok = trace_r ? bq == bqp : b.allowed(bq, bqp);
+              ++pair_index;
               if (a_ok && b_ok) {
-                double f = scale * ctx->am.ninej(L.quantum(aqp)[1], R.quantum(bqp)[1], P.side.quantum(cqp)[1], sa, sb, sc, L.quantum(aq)[1], R.quantum(bq)[1],
-                                                 P.side.quantum(cq)[1]);
+                T.pair.push_back(pair_index - 1);
+                // operatorfunctions.C:205-218 (TensorProduct) / :83-107 (TensorTrace: no get_scaling there)
+                double f = ctx->am.ninej(L.quantum(aqp)[1], R.quantum(bqp)[1], P.side.quantum(cqp)[1], sa, sb, sc, L.quantum(aq)[1], R.quantum(bq)[1],
+                                         P.side.quantum(cq)[1]);
                 if (!trace_l && !trace_r) f *= a.scaling(ctx->am, aq, aqp) * b.scaling(ctx->am, bq, bqp);
                 if (rb && rb->fermion && (L.quantum(aqp)[0] & 1)) f = -f;
-                if (rb) f *= rb->host[(size_t)(b.t ? rb_ref[(size_t)bqp * R.nq + bq] : rb_ref[(size_t)bq * R.nq + bqp])];   // 1 x 1 block: its own transpose
-                if (f != 0.0) {
-                  SubBlock sbk;
-                  sbk.r0 = row; sbk.c0 = col; sbk.m = L.dims[aq]; sbk.n = L.dims[aqp]; sbk.alpha = f;
-                  // the OVERLAP operator of a renormalised block is the identity (same bra and ket states; what the rotation leaves of it is
-                  // I + O(1e-16)): it is contracted as THE identity block, so that "child block + identity" stays a pair of direct factors
-                  if (trace_l || la->optype == OP_OVERLAP) { sbk.a = P.identity; sbk.lda = P.identity_ld; sbk.t = false; }
-                  else { sbk.a = la->dev + a.stored_off(aq, aqp); sbk.lda = a.stored_ld(aq, aqp); sbk.t = a.t; }
-                  out.emplace_back((size_t)cq * P.side.nq + cqp, sbk);
-                }
+                KronTask k;
+                memset(&k, 0, sizeof(k));
+                k.coef = f;
+                k.a_rows = L.dims[aq]; k.a_cols = L.dims[aqp]; k.b_rows = R.dims[bq]; k.b_cols = R.dims[bqp];
+                if (!trace_l) { k.a = 8 * a.stored_off(aq, aqp); k.lda = a.stored_ld(aq, aqp); k.a_t = a.t ? 1 : 0; }   // + the operator's address, per product
+                if (!trace_r) { k.b = (int64_t)(intptr_t)rb->dev + 8 * b.stored_off(bq, bqp); k.ldb = b.stored_ld(bq, bqp); k.b_t = b.t ? 1 : 0; }
+                k.dst = (int64_t)(intptr_t)c.dev + 8 * c.off[(size_t)cq * P.side.nq + cqp];
+                k.ldd = pad_ld(P.side.dims[cqp]);
+                k.row0 = row; k.col0 = col;
+                T.tasks.push_back(k);
+                T.bytes += 8.0 * ((trace_l ? 0.0 : (double)k.a_rows * k.a_cols) + (trace_r ? 0.0 : (double)k.b_rows * k.b_cols) + 2.0 * (double)k.a_rows * k.b_rows * k.a_cols * k.b_cols);
               }
               col += P.unc_dims[oj];
             }
             row += P.unc_dims[oi];
           }
         }
-    } catch (const std::exception& e) { return fail(ctx, B2D_ERR_ARG, e.what()); }
-    ctx->kron_nproducts += 1;
-    return B2D_OK;
+    } catch (const std::exception& e) { T = b2d_ctx::Product::KronTemplate(); return fail(ctx, B2D_ERR_ARG, e.what()); }
+    T.pair_count = std::max(pair_index, 1);
   }
-  std::vector<KronTask> tasks;
-  tasks.reserve(256);
-  std::vector<int> task_pair;   // position of each task's (row piece, column piece) in the loop order below: the same for every product of this operator
-  int pair_index = 0;
-  try {
-    for (int cq = 0; cq < P.side.nq; ++cq)
-      for (int cqp = 0; cqp < P.side.nq; ++cqp) {
-        if (!c.allowed[(size_t)cq * P.side.nq + cqp]) continue;
-        int row = 0;
-        for (int oi : P.old_to_new[cq]) {
-          int col = 0;
-          for (int oj : P.old_to_new[cqp]) {
-            const int aq = P.lmap[oi], aqp = P.lmap[oj], bq = P.rmap[oi], bqp = P.rmap[oj];
-            const bool a_ok = trace_l ? aq == aqp : a.allowed(aq, aqp);
-            const bool b_ok = trace_r ? bq == bqp : b.allowed(bq, bqp);
-            ++pair_index;
-            if (a_ok && b_ok) {
-              task_pair.push_back(pair_index - 1);
-              // operatorfunctions.C:205-218 (TensorProduct) / :83-107 (TensorTrace: no get_scaling there)
-              double f = scale * ctx->am.ninej(L.quantum(aqp)[1], R.quantum(bqp)[1], P.side.quantum(cqp)[1], sa, sb, sc, L.quantum(aq)[1], R.quantum(bq)[1],
-                                               P.side.quantum(cq)[1]);
-              if (!trace_l && !trace_r) f *= a.scaling(ctx->am, aq, aqp) * b.scaling(ctx->am, bq, bqp);
-              if (rb && rb->fermion && (L.quantum(aqp)[0] & 1)) f = -f;
-              KronTask k;
-              memset(&k, 0, sizeof(k));
-              k.coef = f;
-              k.a_rows = L.dims[aq]; k.a_cols = L.dims[aqp]; k.b_rows = R.dims[bq]; k.b_cols = R.dims[bqp];
-              if (!trace_l) { k.a = (int64_t)(intptr_t)la->dev + 8 * a.stored_off(aq, aqp); k.lda = a.stored_ld(aq, aqp); k.a_t = a.t ? 1 : 0; }
-              if (!trace_r) { k.b = (int64_t)(intptr_t)rb->dev + 8 * b.stored_off(bq, bqp); k.ldb = b.stored_ld(bq, bqp); k.b_t = b.t ? 1 : 0; }
-              k.dst = (int64_t)(intptr_t)c.dev + 8 * c.off[(size_t)cq * P.side.nq + cqp];
-              k.ldd = pad_ld(P.side.dims[cqp]);
-              k.row0 = row; k.col0 = col;
-              tasks.push_back(k);
-            }
-            col += P.unc_dims[oj];
-          }
-          row += P.unc_dims[oi];
-        }
-      }
-  } catch (const std::exception& e) { return fail(ctx, B2D_ERR_ARG, e.what()); }
-  for (const KronTask& k : tasks)
-    ctx->kron_bytes += 8.0 * ((k.a ? (double)k.a_rows * k.a_cols : 0.0) + (k.b ? (double)k.b_rows * k.b_cols : 0.0) + 2.0 * (double)k.a_rows * k.b_rows * k.a_cols * k.b_cols);
+  const b2d_ctx::Product::KronTemplate& T = *tp;
+  const std::vector<int>& task_pair = T.pair;
+  const int pair_index = T.pair_count;
+  const int64_t a_base = trace_l ? 0 : (int64_t)(intptr_t)la->dev;
+  std::vector<KronTask> tasks(T.tasks);
+  for (KronTask& k : tasks) { k.a += a_base; k.coef *= scale; }
+  ctx->kron_bytes += T.bytes;
   ctx->kron_ntasks += (int64_t)tasks.size();
   ctx->kron_nproducts += 1;
   if (defer) {

@@ -71,7 +71,9 @@ int b2d_abi_version(void);                        /* 4 */
  * split-K slice of a sigma block, default 256, at most 8 slices), "slice_iters_narrow" (> 0: the narrow tiles of a sigma block - the
  * remainder bands of ragged sectors - get their own, finer slicing, at most 32 slices; default 0 = off: measured +0.7 % on the
  * benchmark for 2 GB of partial buffers), "presum_identity", "balance_terms" (cost-weighted term ownership for several ranks),
- * "cache_device_mb" (device budget of the block cache; <= 0: automatic). */
+ * "cache_device_mb" (device budget of the block cache; <= 0: automatic), "partition_renormalisation" (several ranks that ALL hold the
+ * whole block - the multi-process drop-in - divide the sectors of b2d_diagonalise_dm and the operators of b2d_transform_operators by
+ * cost and all-reduce the zero-filled results: every rank ends with identical bits; every rank must set it). */
 int b2d_set_option(b2d_ctx* ctx, const char* key, double value);
 
 /* ---- block description: replaces the host-side SpinBlock / StateInfo / Op_component objects ---------------- */

@@ -232,8 +232,8 @@ struct b2d_ctx {
     // Scatter tasks of one product as a TEMPLATE: every product of an operator whose left factor has the same quantum numbers, orientation
     // and allowed pattern and whose right factor is the same operator has the same tasks up to the left operator's base address and the
     // scale (a complementary operator is a sum of hundreds of such products)
-    struct FactorTemplate { size_t blk; SubBlock sb; int64_t a_off; bool identity; };   // factorised operators: the same idea for the factor lists
-    struct KronTemplate { std::vector<KronTask> tasks; std::vector<int> pair; int pair_count = 0; double bytes = 0.0; int left_owner = -1; std::vector<FactorTemplate> factors; };
+    struct FactorTemplate { size_t blk; SubBlock sb; int64_t a_off; bool identity; double m2, h; };   // alpha = ((scale * sb.alpha) * m2) * h: the reference's order of operations   // factorised operators: the same idea for the factor lists
+    struct KronTemplate { std::vector<KronTask> tasks; std::vector<double> m2; std::vector<int> pair; int pair_count = 0; double bytes = 0.0; int left_owner = -1; std::vector<FactorTemplate> factors; };   // task coefficient = (scale * tasks[i].coef) * m2[i]
     std::map<std::array<int64_t, 8>, KronTemplate> kron_templates;
     struct Combo { std::vector<std::pair<const double*, bool>> parts; std::vector<double> ratios; const double* block; };
     std::map<std::array<int64_t, 3>, std::vector<Combo>> combos;       // (first part address, m, n) -> pre-summed blocks, for sharing
@@ -2643,15 +2643,18 @@ static int product_op_accumulate_impl(b2d_ctx* ctx, int prod_id, int left_op, in
                 const bool a_ok = trace_l ? aq == aqp : a.allowed(aq, aqp);
                 const bool b_ok = trace_r ? bq == bqp : b.allowed(bq, bqp);
                 if (a_ok && b_ok) {
-                  double f = ctx->am.ninej(L.quantum(aqp)[1], R.quantum(bqp)[1], P.side.quantum(cqp)[1], sa, sb, sc, L.quantum(aq)[1], R.quantum(bq)[1],
-                                           P.side.quantum(cq)[1]);
-                  if (!trace_l && !trace_r) f *= a.scaling(ctx->am, aq, aqp) * b.scaling(ctx->am, bq, bqp);
-                  if (rb && rb->fermion && (L.quantum(aqp)[0] & 1)) f = -f;
-                  if (rb) f *= rb->host[(size_t)(b.t ? rb_ref[(size_t)bqp * R.nq + bq] : rb_ref[(size_t)bq * R.nq + bqp])];   // 1 x 1 block: its own transpose
-                  if (f != 0.0) {
+                  // f = ((scale * 9j) * scalings) * dot element, sign in between (exact): the three factors are kept apart so that a product
+                  // evaluates them in the reference's order (operatorfunctions.C:205-218) - the template changes no bit
+                  const double n9 = ctx->am.ninej(L.quantum(aqp)[1], R.quantum(bqp)[1], P.side.quantum(cqp)[1], sa, sb, sc, L.quantum(aq)[1], R.quantum(bq)[1],
+                                                  P.side.quantum(cq)[1]);
+                  double m2 = (!trace_l && !trace_r) ? a.scaling(ctx->am, aq, aqp) * b.scaling(ctx->am, bq, bqp) : 1.0;
+                  if (rb && rb->fermion && (L.quantum(aqp)[0] & 1)) m2 = -m2;
+                  const double h = rb ? rb->host[(size_t)(b.t ? rb_ref[(size_t)bqp * R.nq + bq] : rb_ref[(size_t)bq * R.nq + bqp])] : 1.0;   // 1 x 1 block: its own transpose
+                  if (n9 * m2 * h != 0.0) {
                     b2d_ctx::Product::FactorTemplate ft;
                     ft.blk = (size_t)cq * P.side.nq + cqp;
-                    ft.sb.r0 = row; ft.sb.c0 = col; ft.sb.m = L.dims[aq]; ft.sb.n = L.dims[aqp]; ft.sb.alpha = f;
+                    ft.m2 = m2; ft.h = h;
+                    ft.sb.r0 = row; ft.sb.c0 = col; ft.sb.m = L.dims[aq]; ft.sb.n = L.dims[aqp]; ft.sb.alpha = n9;
                     // the OVERLAP operator of a renormalised block is the identity (same bra and ket states; what the rotation leaves of it is
                     // I + O(1e-16)): it is contracted as THE identity block, so that "child block + identity" stays a pair of direct factors
                     ft.identity = left_is_identity;
@@ -2671,8 +2674,8 @@ static int product_op_accumulate_impl(b2d_ctx* ctx, int prod_id, int left_op, in
     for (const b2d_ctx::Product::FactorTemplate& ft : tp->factors) {
       SubBlock sbk = ft.sb;
       if (!ft.identity) sbk.a = la->dev + ft.a_off;
-      sbk.alpha *= scale;
-      out.emplace_back(ft.blk, sbk);
+      sbk.alpha = ((scale * ft.sb.alpha) * ft.m2) * ft.h;
+      if (sbk.alpha != 0.0) out.emplace_back(ft.blk, sbk);
     }
     return B2D_OK;
   }
@@ -2703,13 +2706,16 @@ static int product_op_accumulate_impl(b2d_ctx* ctx, int prod_id, int left_op, in
               if (a_ok && b_ok) {
                 T.pair.push_back(pair_index - 1);
                 // operatorfunctions.C:205-218 (TensorProduct) / :83-107 (TensorTrace: no get_scaling there)
-                double f = ctx->am.ninej(L.quantum(aqp)[1], R.quantum(bqp)[1], P.side.quantum(cqp)[1], sa, sb, sc, L.quantum(aq)[1], R.quantum(bq)[1],
-                                         P.side.quantum(cq)[1]);
-                if (!trace_l && !trace_r) f *= a.scaling(ctx->am, aq, aqp) * b.scaling(ctx->am, bq, bqp);
-                if (rb && rb->fermion && (L.quantum(aqp)[0] & 1)) f = -f;
+                // coefficient = (scale * 9j) * scalings with the sign (exact) folded into the second factor: a product evaluates it in the
+                // reference's order, the template changes no bit
+                const double n9 = ctx->am.ninej(L.quantum(aqp)[1], R.quantum(bqp)[1], P.side.quantum(cqp)[1], sa, sb, sc, L.quantum(aq)[1], R.quantum(bq)[1],
+                                                P.side.quantum(cq)[1]);
+                double m2 = (!trace_l && !trace_r) ? a.scaling(ctx->am, aq, aqp) * b.scaling(ctx->am, bq, bqp) : 1.0;
+                if (rb && rb->fermion && (L.quantum(aqp)[0] & 1)) m2 = -m2;
+                T.m2.push_back(m2);
                 KronTask k;
                 memset(&k, 0, sizeof(k));
-                k.coef = f;
+                k.coef = n9;
                 k.a_rows = L.dims[aq]; k.a_cols = L.dims[aqp]; k.b_rows = R.dims[bq]; k.b_cols = R.dims[bqp];
                 if (!trace_l) { k.a = 8 * a.stored_off(aq, aqp); k.lda = a.stored_ld(aq, aqp); k.a_t = a.t ? 1 : 0; }   // + the operator's address, per product
                 if (!trace_r) { k.b = (int64_t)(intptr_t)rb->dev + 8 * b.stored_off(bq, bqp); k.ldb = b.stored_ld(bq, bqp); k.b_t = b.t ? 1 : 0; }
@@ -2732,7 +2738,7 @@ static int product_op_accumulate_impl(b2d_ctx* ctx, int prod_id, int left_op, in
   const int pair_index = T.pair_count;
   const int64_t a_base = trace_l ? 0 : (int64_t)(intptr_t)la->dev;
   std::vector<KronTask> tasks(T.tasks);
-  for (KronTask& k : tasks) { k.a += a_base; k.coef *= scale; }
+  for (size_t i = 0; i < tasks.size(); ++i) { tasks[i].a += a_base; tasks[i].coef = (scale * tasks[i].coef) * T.m2[i]; }
   ctx->kron_bytes += T.bytes;
   ctx->kron_ntasks += (int64_t)tasks.size();
   ctx->kron_nproducts += 1;

@@ -1,4 +1,5 @@
 # round 2, call 21: who gets the SMs - A/B of stream priorities (narrow tile classes first) and of the persistent kernel's CTA count
+# (the B2D_NARROW_PRIORITY / B2D_PERSISTENT_CTAS knobs this script sets existed only for this experiment: no effect, reverted - profiles/README.md)
 mkdir -p gpurun_out/r2_21
 run() {
   TAG=$1; shift

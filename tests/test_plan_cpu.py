@@ -127,3 +127,20 @@ def test_cost_weighted_term_ownership_balances_flops():
     assert shares[1] < 1.01, shares
     assert shares[1] <= shares[0]
     print("max / mean executed flops per rank at %d ranks: reference rule %.4f, cost-weighted %.4f" % (world, shares[0], shares[1]))
+
+
+def test_narrow_tiles_get_their_own_split_k_family():
+    """Option slice_iters_narrow: the narrow tiles of a sigma block (remainder bands of ragged sectors) are cut into more, shorter split-K
+    slices than its 128 x 128 tiles - a second family of slice groups restricted to the narrow tile classes.  The work is unchanged (same
+    executed flops, same useful flops inside the tiles), only the number of tiles grows.  Planning only (no device)."""
+    from block_b200 import synthetic as S
+    stats = {}
+    for narrow in (0, 32):
+        sb = S.make_big_block(norbs=24, nelec=24, M=600, left_sites=11, device=-1, options={"slice_iters": 64, "slice_iters_narrow": narrow}, fill=False)
+        stats[narrow] = sb.plan_stats()
+        sb.close()
+    a, b = stats[0], stats[32]
+    assert a["flops_executed"] == b["flops_executed"]
+    assert abs(a["flops_in_tiles"] - b["flops_in_tiles"]) <= 1e-9 * a["flops_in_tiles"]
+    assert b["tiles"] > a["tiles"], (a["tiles"], b["tiles"])
+    assert a["step1_contractions"] == b["step1_contractions"]

@@ -228,11 +228,14 @@ def run_reference(a):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # a step = a bounded sample of the same multiplyH: --ref-step-s seconds of the box's host cores, shortened so that the whole
+    # --steps K --warmup W run stays within --ref-total-s (default 360 s: 16 s per step, >= 128 terms on 16 cores, at the driver's K = 20, W = 5)
+    step_s = min(a.ref_step_s, a.ref_total_s / max(a.steps + 0.5 * a.warmup, 1.0))
     for _ in range(a.warmup):
-        cpu_leg(a, a.ref_step_s / 2)
+        cpu_leg(a, step_s / 2)
     t, fl, last = 0.0, 0.0, None
     for _ in range(a.steps):
-        last = cpu_leg(a, a.ref_step_s)
+        last = cpu_leg(a, step_s)
         t += last[4]
         fl += last[5]
     value = fl / t / 1e9
@@ -711,6 +714,7 @@ def main():
     ap.add_argument("--sweep-case", default="synthetic_16o_M300", help="case of tests/golden/dropin_cases.npz for the sweep leg")
     ap.add_argument("--profile-mode", action="store_true", help="for ncu: 1 warm-up sigma + --steps sigmas, nothing else, no JSON line")
     ap.add_argument("--cpu-budget-s", type=float, default=20.0)
+    ap.add_argument("--ref-total-s", type=float, default=360.0, help="--impl reference: CPU time budget of the whole run (steps are shortened to fit)")
     ap.add_argument("--ref-step-s", type=float, default=20.0)   # >= 128 terms of the multiplyH per reference step on a 16-core host
     a = ap.parse_args()
     if a.left_sites is None:
